@@ -1,0 +1,657 @@
+/*
+ * oracle/hbls_oracle.c -- TEST INFRASTRUCTURE + CPU BASELINE ONLY.
+ *
+ * Plain-C restatement (6 x 64-bit Montgomery limbs) of the BLS12-381 arithmetic Harmony reaches through
+ * cgo: github.com/harmony-one/bls v0.0.6 (reference go.mod:27) -> herumi libbls384_256 + libmcl built with
+ * BLS_SWAP_G=1 (reference Makefile:68-70).  That native library is NOT in /root/reference and cannot be built
+ * here (no Go toolchain, sources not vendored), so this file restates its published algorithm
+ *  and is PINNED, through tests/test_oracle.py, against
+ *   - oracle/pyref.py (independent big-int restatement) and
+ *   - every byte-level fixture of the reference (tests/golden/ref_fixtures.json: 35 sk->pk, 1 (sk,msg)->sig).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
+ * library.  The product (harmony_b200/csrc) never links or calls it.
+ *
+ * Reference call sites restated (composition as the Go code performs it):
+ *   crypto/bls/mask.go:58-64    AggregateSig           -> ho_aggregate_sigs
+ *   crypto/bls/mask.go:113-134  Mask.SetMask           -> ho_mask_aggregate / ho_committee_*
+ *   internal/chain/engine.go:619-642 verifySignature   -> ho_fast_aggregate_verify
+ *   consensus/leader.go:257-287 Deserialize+VerifyHash -> ho_verify_hash
+ *   consensus/construct.go:97-114 SignHash             -> ho_sign_hash
+ *
+ * An Fp-mul / Fp-sqr counter (ho_counters_*) is the source of the ALGORITHMIC work figure used by bench.py
+ * (1 Fp mul = 300 MAC32, 1 Fp sqr = 234 MAC32).
+ */
+#include <stdint.h>
+#include <stddef.h>
+#include <string.h>
+#include <stdlib.h>
+#include "ho_constants.h"
+
+typedef uint64_t u64;
+typedef unsigned __int128 u128;
+typedef uint8_t u8;
+
+static __thread u64 g_cnt_mul, g_cnt_sqr;
+
+/* ------------------------------------------------------------------ Fp */
+typedef struct { u64 l[6]; } fp;
+
+static inline void fp_set(fp *r, const u64 *k) { memcpy(r->l, k, 48); }
+static inline void fp_zero(fp *r) { memset(r, 0, 48); }
+static inline int fp_is_zero(const fp *a) { return (a->l[0] | a->l[1] | a->l[2] | a->l[3] | a->l[4] | a->l[5]) == 0; }
+static inline int fp_eq(const fp *a, const fp *b) { return memcmp(a, b, 48) == 0; }
+static inline int limbs_geq_p(const u64 *t) {
+    for (int i = 5; i >= 0; i--) { if (t[i] > K_P[i]) return 1; if (t[i] < K_P[i]) return 0; }
+    return 1;
+}
+#include <x86intrin.h>
+typedef unsigned long long ull;
+/* s = t - p, returns borrow */
+static inline unsigned char limbs_sub_p_to(u64 *s, const u64 *t) {
+    unsigned char br = 0;
+    br = _subborrow_u64(br, t[0], K_P[0], (ull *)&s[0]); br = _subborrow_u64(br, t[1], K_P[1], (ull *)&s[1]);
+    br = _subborrow_u64(br, t[2], K_P[2], (ull *)&s[2]); br = _subborrow_u64(br, t[3], K_P[3], (ull *)&s[3]);
+    br = _subborrow_u64(br, t[4], K_P[4], (ull *)&s[4]); br = _subborrow_u64(br, t[5], K_P[5], (ull *)&s[5]);
+    return br;
+}
+static inline void fp_add(fp *r, const fp *a, const fp *b) {
+    u64 t[6], s[6]; unsigned char c = 0;
+    for (int i = 0; i < 6; i++) c = _addcarry_u64(c, a->l[i], b->l[i], (ull *)&t[i]);
+    unsigned char br = limbs_sub_p_to(s, t);      /* a+b < 2p < 2^382: no carry out */
+    for (int i = 0; i < 6; i++) r->l[i] = br ? t[i] : s[i];
+}
+static inline void fp_sub(fp *r, const fp *a, const fp *b) {
+    u64 t[6]; unsigned char br = 0, c = 0;
+    for (int i = 0; i < 6; i++) br = _subborrow_u64(br, a->l[i], b->l[i], (ull *)&t[i]);
+    u64 mask = (u64)0 - (u64)br;
+    for (int i = 0; i < 6; i++) c = _addcarry_u64(c, t[i], K_P[i] & mask, (ull *)&r->l[i]);
+}
+static inline void fp_neg(fp *r, const fp *a) {
+    if (fp_is_zero(a)) { fp_zero(r); return; }
+    fp p; fp_set(&p, K_P); fp_sub(r, &p, a);
+}
+static inline void fp_dbl(fp *r, const fp *a) { fp_add(r, a, a); }
+
+static inline void fp_mont(fp *r, const fp *a, const fp *b) {
+    u64 t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 6; i++) {
+        u128 c = 0; u64 bi = b->l[i];
+        for (int j = 0; j < 6; j++) { c += (u128)a->l[j] * bi + t[j]; t[j] = (u64)c; c >>= 64; }
+        c += t[6]; t[6] = (u64)c; t[7] = (u64)(c >> 64);
+        u64 m = t[0] * K_N0;
+        c = (u128)m * K_P[0] + t[0]; c >>= 64;
+        for (int j = 1; j < 6; j++) { c += (u128)m * K_P[j] + t[j]; t[j - 1] = (u64)c; c >>= 64; }
+        c += t[6]; t[5] = (u64)c; t[6] = t[7] + (u64)(c >> 64);
+    }
+    u64 s[6]; unsigned char br = limbs_sub_p_to(s, t);   /* result < 2p: t[6] == 0 */
+    for (int i = 0; i < 6; i++) r->l[i] = br ? t[i] : s[i];
+}
+static inline void fp_mul(fp *r, const fp *a, const fp *b) { g_cnt_mul++; fp_mont(r, a, b); }
+static inline void fp_sqr(fp *r, const fp *a) { g_cnt_sqr++; fp_mont(r, a, a); }
+
+static void fp_from_int_limbs(fp *r, const u64 *v) { fp t, r2; memcpy(t.l, v, 48); fp_set(&r2, K_R2); fp_mul(r, &t, &r2); }
+static void fp_to_int_limbs(u64 *v, const fp *a) { fp one = {{1, 0, 0, 0, 0, 0}}, t; fp_mont(&t, a, &one); memcpy(v, t.l, 48); }
+/* little-endian 48 bytes (canonical integer) <-> Montgomery; returns 0 if value >= p */
+static int fp_from_bytes(fp *r, const u8 *b) {
+    u64 v[6]; memcpy(v, b, 48);
+    if (limbs_geq_p(v)) return 0;
+    fp_from_int_limbs(r, v); return 1;
+}
+static void fp_to_bytes(u8 *b, const fp *a) { u64 v[6]; fp_to_int_limbs(v, a); memcpy(b, v, 48); }
+static int fp_is_odd(const fp *a) { u64 v[6]; fp_to_int_limbs(v, a); return (int)(v[0] & 1); }
+
+/* r = a^e, e = 6 little-endian u64 limbs (plain integer), 4-bit fixed window */
+static void fp_pow(fp *r, const fp *a, const u64 *e) {
+    fp tbl[16]; fp_set(&tbl[0], K_ONE); tbl[1] = *a;
+    for (int i = 2; i < 16; i++) fp_mul(&tbl[i], &tbl[i - 1], a);
+    fp acc; fp_set(&acc, K_ONE); int started = 0;
+    for (int i = 95; i >= 0; i--) {
+        unsigned w = (unsigned)(e[i / 16] >> (4 * (i % 16))) & 15;
+        if (started) { fp_sqr(&acc, &acc); fp_sqr(&acc, &acc); fp_sqr(&acc, &acc); fp_sqr(&acc, &acc); }
+        if (w) { if (started) fp_mul(&acc, &acc, &tbl[w]); else { acc = tbl[w]; started = 1; } }
+    }
+    *r = acc;
+}
+static void fp_inv(fp *r, const fp *a) { fp_pow(r, a, K_P_MINUS_2); }
+/* mcl Fp::squareRoot, p = 3 mod 4: candidate a^((p+1)/4); 1 iff it squares back */
+static int fp_sqrt(fp *r, const fp *a) {
+    fp y, y2; fp_pow(&y, a, K_P_PLUS_1_DIV_4); fp_sqr(&y2, &y);
+    if (!fp_eq(&y2, a)) return 0;
+    *r = y; return 1;
+}
+static int fp_legendre(const fp *a) {
+    if (fp_is_zero(a)) return 0;
+    fp t, one; fp_pow(&t, a, K_P_MINUS_1_DIV_2); fp_set(&one, K_ONE);
+    return fp_eq(&t, &one) ? 1 : -1;
+}
+
+/* ------------------------------------------------------------------ Fp2 = Fp[i]/(i^2+1) */
+typedef struct { fp a, b; } fp2;
+static inline void fp2_zero(fp2 *r) { memset(r, 0, sizeof *r); }
+static inline void fp2_one(fp2 *r) { fp_set(&r->a, K_ONE); fp_zero(&r->b); }
+static inline int fp2_is_zero(const fp2 *x) { return fp_is_zero(&x->a) && fp_is_zero(&x->b); }
+static inline int fp2_eq(const fp2 *x, const fp2 *y) { return fp_eq(&x->a, &y->a) && fp_eq(&x->b, &y->b); }
+static inline void fp2_add(fp2 *r, const fp2 *x, const fp2 *y) { fp_add(&r->a, &x->a, &y->a); fp_add(&r->b, &x->b, &y->b); }
+static inline void fp2_sub(fp2 *r, const fp2 *x, const fp2 *y) { fp_sub(&r->a, &x->a, &y->a); fp_sub(&r->b, &x->b, &y->b); }
+static inline void fp2_neg(fp2 *r, const fp2 *x) { fp_neg(&r->a, &x->a); fp_neg(&r->b, &x->b); }
+static inline void fp2_conj(fp2 *r, const fp2 *x) { r->a = x->a; fp_neg(&r->b, &x->b); }
+static inline void fp2_dbl(fp2 *r, const fp2 *x) { fp2_add(r, x, x); }
+static void fp2_mul(fp2 *r, const fp2 *x, const fp2 *y) {
+    fp t0, t1, t2, s0, s1;
+    fp_mul(&t0, &x->a, &y->a); fp_mul(&t1, &x->b, &y->b);
+    fp_add(&s0, &x->a, &x->b); fp_add(&s1, &y->a, &y->b); fp_mul(&t2, &s0, &s1);
+    fp_sub(&r->a, &t0, &t1); fp_sub(&t2, &t2, &t0); fp_sub(&r->b, &t2, &t1);
+}
+static void fp2_sqr(fp2 *r, const fp2 *x) {
+    fp s, d, m;
+    fp_add(&s, &x->a, &x->b); fp_sub(&d, &x->a, &x->b); fp_mul(&m, &x->a, &x->b);
+    fp_mul(&r->a, &s, &d); fp_dbl(&r->b, &m);
+}
+static inline void fp2_mul_fp(fp2 *r, const fp2 *x, const fp *k) { fp_mul(&r->a, &x->a, k); fp_mul(&r->b, &x->b, k); }
+static inline void fp2_mul_xi(fp2 *r, const fp2 *x) { fp t; fp_sub(&t, &x->a, &x->b); fp_add(&r->b, &x->a, &x->b); r->a = t; }
+static void fp2_norm(fp *r, const fp2 *x) { fp t; fp_sqr(r, &x->a); fp_sqr(&t, &x->b); fp_add(r, r, &t); }
+static void fp2_inv(fp2 *r, const fp2 *x) {
+    fp n; fp2_norm(&n, x); fp_inv(&n, &n);
+    fp_mul(&r->a, &x->a, &n); fp_mul(&r->b, &x->b, &n); fp_neg(&r->b, &r->b);
+}
+/* mcl Fp2::squareRoot: determines which of +-y is produced */
+static int fp2_sqrt(fp2 *r, const fp2 *x) {
+    fp t1, t2, inv2;
+    if (fp_is_zero(&x->b)) {
+        if (fp_sqrt(&t1, &x->a)) { r->a = t1; fp_zero(&r->b); }
+        else { fp_neg(&t2, &x->a); if (!fp_sqrt(&t1, &t2)) return 0; fp_zero(&r->a); r->b = t1; }
+        return 1;
+    }
+    fp2_norm(&t1, x);
+    if (!fp_sqrt(&t1, &t1)) return 0;
+    fp_set(&inv2, K_INV2);
+    fp_add(&t2, &x->a, &t1); fp_mul(&t2, &t2, &inv2);
+    if (!fp_sqrt(&t2, &t2)) {
+        fp_sub(&t2, &x->a, &t1); fp_mul(&t2, &t2, &inv2);
+        if (!fp_sqrt(&t2, &t2)) return 0;
+    }
+    fp c = t2;
+    fp_dbl(&t2, &t2); fp_inv(&t2, &t2);
+    fp_mul(&r->b, &x->b, &t2); r->a = c;
+    return 1;
+}
+
+/* ------------------------------------------------------------------ Fp6 = Fp2[v]/(v^3 - xi) */
+typedef struct { fp2 c0, c1, c2; } fp6;
+static inline void fp6_add(fp6 *r, const fp6 *x, const fp6 *y) { fp2_add(&r->c0, &x->c0, &y->c0); fp2_add(&r->c1, &x->c1, &y->c1); fp2_add(&r->c2, &x->c2, &y->c2); }
+static inline void fp6_sub(fp6 *r, const fp6 *x, const fp6 *y) { fp2_sub(&r->c0, &x->c0, &y->c0); fp2_sub(&r->c1, &x->c1, &y->c1); fp2_sub(&r->c2, &x->c2, &y->c2); }
+static inline void fp6_neg(fp6 *r, const fp6 *x) { fp2_neg(&r->c0, &x->c0); fp2_neg(&r->c1, &x->c1); fp2_neg(&r->c2, &x->c2); }
+static inline void fp6_mul_v(fp6 *r, const fp6 *x) { fp2 t; fp2_mul_xi(&t, &x->c2); r->c2 = x->c1; r->c1 = x->c0; r->c0 = t; }
+static void fp6_mul(fp6 *r, const fp6 *x, const fp6 *y) {
+    fp2 v0, v1, v2, t0, t1, t2, s;
+    fp2_mul(&v0, &x->c0, &y->c0); fp2_mul(&v1, &x->c1, &y->c1); fp2_mul(&v2, &x->c2, &y->c2);
+    fp2_add(&t0, &x->c1, &x->c2); fp2_add(&s, &y->c1, &y->c2); fp2_mul(&t0, &t0, &s);
+    fp2_sub(&t0, &t0, &v1); fp2_sub(&t0, &t0, &v2); fp2_mul_xi(&t0, &t0); fp2_add(&t0, &t0, &v0);
+    fp2_add(&t1, &x->c0, &x->c1); fp2_add(&s, &y->c0, &y->c1); fp2_mul(&t1, &t1, &s);
+    fp2_sub(&t1, &t1, &v0); fp2_sub(&t1, &t1, &v1); fp2_mul_xi(&s, &v2); fp2_add(&t1, &t1, &s);
+    fp2_add(&t2, &x->c0, &x->c2); fp2_add(&s, &y->c0, &y->c2); fp2_mul(&t2, &t2, &s);
+    fp2_sub(&t2, &t2, &v0); fp2_sub(&t2, &t2, &v2); fp2_add(&t2, &t2, &v1);
+    r->c0 = t0; r->c1 = t1; r->c2 = t2;
+}
+static void fp6_sqr(fp6 *r, const fp6 *x) { fp6_mul(r, x, x); }
+/* x * (b0 + b1 v) */
+static void fp6_mul_by_01(fp6 *r, const fp6 *x, const fp2 *b0, const fp2 *b1) {
+    fp2 v0, v1, t0, t1, t2, s;
+    fp2_mul(&v0, &x->c0, b0); fp2_mul(&v1, &x->c1, b1);
+    fp2_mul(&t0, &x->c2, b1); fp2_mul_xi(&t0, &t0); fp2_add(&t0, &t0, &v0);
+    fp2_add(&t1, &x->c0, &x->c1); fp2_add(&s, b0, b1); fp2_mul(&t1, &t1, &s); fp2_sub(&t1, &t1, &v0); fp2_sub(&t1, &t1, &v1);
+    fp2_mul(&t2, &x->c2, b0); fp2_add(&t2, &t2, &v1);
+    r->c0 = t0; r->c1 = t1; r->c2 = t2;
+}
+/* x * (b1 v) */
+static void fp6_mul_by_1(fp6 *r, const fp6 *x, const fp2 *b1) {
+    fp2 t0, t1, t2;
+    fp2_mul(&t0, &x->c2, b1); fp2_mul_xi(&t0, &t0);
+    fp2_mul(&t1, &x->c0, b1); fp2_mul(&t2, &x->c1, b1);
+    r->c0 = t0; r->c1 = t1; r->c2 = t2;
+}
+static void fp6_inv(fp6 *r, const fp6 *x) {
+    fp2 t0, t1, t2, s, d;
+    fp2_sqr(&t0, &x->c0); fp2_mul(&s, &x->c1, &x->c2); fp2_mul_xi(&s, &s); fp2_sub(&t0, &t0, &s);
+    fp2_sqr(&t1, &x->c2); fp2_mul_xi(&t1, &t1); fp2_mul(&s, &x->c0, &x->c1); fp2_sub(&t1, &t1, &s);
+    fp2_sqr(&t2, &x->c1); fp2_mul(&s, &x->c0, &x->c2); fp2_sub(&t2, &t2, &s);
+    fp2_mul(&d, &x->c2, &t1); fp2_mul(&s, &x->c1, &t2); fp2_add(&d, &d, &s); fp2_mul_xi(&d, &d);
+    fp2_mul(&s, &x->c0, &t0); fp2_add(&d, &d, &s);
+    fp2_inv(&d, &d);
+    fp2_mul(&r->c0, &t0, &d); fp2_mul(&r->c1, &t1, &d); fp2_mul(&r->c2, &t2, &d);
+}
+
+/* ------------------------------------------------------------------ Fp12 = Fp6[w]/(w^2 - v) */
+typedef struct { fp6 c0, c1; } fp12;
+static void fp12_one(fp12 *r) { memset(r, 0, sizeof *r); fp2_one(&r->c0.c0); }
+static int fp12_is_one(const fp12 *x) { fp12 o; fp12_one(&o); return memcmp(x, &o, sizeof o) == 0; }
+static void fp12_mul(fp12 *r, const fp12 *x, const fp12 *y) {
+    fp6 v0, v1, s, t;
+    fp6_mul(&v0, &x->c0, &y->c0); fp6_mul(&v1, &x->c1, &y->c1);
+    fp6_add(&s, &x->c0, &x->c1); fp6_add(&t, &y->c0, &y->c1); fp6_mul(&s, &s, &t);
+    fp6_sub(&s, &s, &v0); fp6_sub(&s, &s, &v1);
+    fp6_mul_v(&t, &v1); fp6_add(&r->c0, &v0, &t); r->c1 = s;
+}
+static void fp12_sqr(fp12 *r, const fp12 *x) {
+    /* (a+bw)^2 = (a+b)(a+vb) - ab - v ab + 2ab w */
+    fp6 ab, s, t;
+    fp6_mul(&ab, &x->c0, &x->c1);
+    fp6_add(&s, &x->c0, &x->c1); fp6_mul_v(&t, &x->c1); fp6_add(&t, &t, &x->c0); fp6_mul(&s, &s, &t);
+    fp6_sub(&s, &s, &ab); fp6_mul_v(&t, &ab); fp6_sub(&r->c0, &s, &t);
+    fp6_add(&r->c1, &ab, &ab);
+}
+static void fp12_conj(fp12 *r, const fp12 *x) { r->c0 = x->c0; fp6_neg(&r->c1, &x->c1); }
+static void fp12_inv(fp12 *r, const fp12 *x) {
+    fp6 t0, t1;
+    fp6_sqr(&t0, &x->c0); fp6_sqr(&t1, &x->c1); fp6_mul_v(&t1, &t1); fp6_sub(&t0, &t0, &t1);
+    fp6_inv(&t0, &t0);
+    fp6_mul(&r->c0, &x->c0, &t0); fp6_mul(&t1, &x->c1, &t0); fp6_neg(&r->c1, &t1);
+}
+/* sparse multiply by a line (o0 + o1 v) + (o4 v) w : coefficients at w^0, w^2, w^3 */
+static void fp12_mul_by_014(fp12 *r, const fp12 *x, const fp2 *o0, const fp2 *o1, const fp2 *o4) {
+    fp6 aa, bb, s; fp2 o14;
+    fp6_mul_by_01(&aa, &x->c0, o0, o1);
+    fp6_mul_by_1(&bb, &x->c1, o4);
+    fp2_add(&o14, o1, o4);
+    fp6_add(&s, &x->c0, &x->c1); fp6_mul_by_01(&s, &s, o0, &o14);
+    fp6_sub(&s, &s, &aa); fp6_sub(&s, &s, &bb);
+    fp6_mul_v(&bb, &bb); fp6_add(&r->c0, &aa, &bb); r->c1 = s;
+}
+/* coefficient of w^k (k = 2i + j) <-> tower slot */
+static fp2 *fp12_slot(fp12 *x, int k) { fp6 *h = (k & 1) ? &x->c1 : &x->c0; int i = k >> 1; return i == 0 ? &h->c0 : (i == 1 ? &h->c1 : &h->c2); }
+static void fp12_frob(fp12 *r, const fp12 *x) {
+    fp12 t = *x;
+    for (int k = 0; k < 6; k++) {
+        fp2 *s = fp12_slot(&t, k), g; fp2_conj(s, s);
+        memcpy(&g.a, K_FROB1[k][0], 48); memcpy(&g.b, K_FROB1[k][1], 48);
+        fp2_mul(s, s, &g);
+    }
+    *r = t;
+}
+static void fp12_frob2(fp12 *r, const fp12 *x) {
+    fp12 t = *x;
+    for (int k = 0; k < 6; k++) { fp2 *s = fp12_slot(&t, k); fp g; fp_set(&g, K_FROB2[k]); fp2_mul_fp(s, s, &g); }
+    *r = t;
+}
+/* Granger-Scott squaring, valid in the cyclotomic subgroup (after the easy part of the final exponentiation) */
+static void fp4_sqr(fp2 *c0, fp2 *c1, const fp2 *a, const fp2 *b) {
+    fp2 t0, t1, t2;
+    fp2_sqr(&t0, a); fp2_sqr(&t1, b);
+    fp2_mul_xi(&t2, &t1); fp2_add(c0, &t2, &t0);
+    fp2_add(&t2, a, b); fp2_sqr(&t2, &t2); fp2_sub(&t2, &t2, &t0); fp2_sub(c1, &t2, &t1);
+}
+static void fp12_cyc_sqr(fp12 *r, const fp12 *x) {
+    fp2 z0 = x->c0.c0, z4 = x->c0.c1, z3 = x->c0.c2, z2 = x->c1.c0, z1 = x->c1.c1, z5 = x->c1.c2;
+    fp2 t0, t1, t2, t3;
+    fp4_sqr(&t0, &t1, &z0, &z1);
+    fp2_sub(&z0, &t0, &z0); fp2_dbl(&z0, &z0); fp2_add(&z0, &z0, &t0);
+    fp2_add(&z1, &t1, &z1); fp2_dbl(&z1, &z1); fp2_add(&z1, &z1, &t1);
+    fp4_sqr(&t0, &t1, &z2, &z3);
+    fp4_sqr(&t2, &t3, &z4, &z5);
+    fp2_sub(&z4, &t0, &z4); fp2_dbl(&z4, &z4); fp2_add(&z4, &z4, &t0);
+    fp2_add(&z5, &t1, &z5); fp2_dbl(&z5, &z5); fp2_add(&z5, &z5, &t1);
+    fp2_mul_xi(&t0, &t3);
+    fp2_add(&z2, &t0, &z2); fp2_dbl(&z2, &z2); fp2_add(&z2, &z2, &t0);
+    fp2_sub(&z3, &t2, &z3); fp2_dbl(&z3, &z3); fp2_add(&z3, &z3, &t2);
+    r->c0.c0 = z0; r->c0.c1 = z4; r->c0.c2 = z3; r->c1.c0 = z2; r->c1.c1 = z1; r->c1.c2 = z5;
+}
+/* r = x^|z| for cyclotomic x */
+static void fp12_cyc_exp_zabs(fp12 *r, const fp12 *x) {
+    fp12 acc = *x;
+    for (int i = 62; i >= 0; i--) {
+        fp12_cyc_sqr(&acc, &acc);
+        if ((K_Z_ABS >> i) & 1) fp12_mul(&acc, &acc, x);
+    }
+    *r = acc;
+}
+/* r = x^z (z negative): conj of x^|z| in the cyclotomic subgroup */
+static void fp12_cyc_exp_z(fp12 *r, const fp12 *x) { fp12_cyc_exp_zabs(r, x); fp12_conj(r, r); }
+
+/* ------------------------------------------------------------------ curves: templated over the coordinate field */
+#define FT fp
+#define PT g1
+#define F_(n) fp_##n
+#define C_(n) g1_##n
+#define CURVE_B_INIT(b) fp_set(b, K_B1)
+#include "ho_curve_tmpl.h"
+#undef FT
+#undef PT
+#undef F_
+#undef C_
+#undef CURVE_B_INIT
+
+#define FT fp2
+#define PT g2
+#define F_(n) fp2_##n
+#define C_(n) g2_##n
+#define CURVE_B_INIT(b) do { memcpy(&(b)->a, K_B2[0], 48); memcpy(&(b)->b, K_B2[1], 48); } while (0)
+#include "ho_curve_tmpl.h"
+#undef FT
+#undef PT
+#undef F_
+#undef C_
+#undef CURVE_B_INIT
+
+static void g1_generator(g1 *r) { fp_set(&r->x, K_G1_X); fp_set(&r->y, K_G1_Y); fp_set(&r->z, K_ONE); }
+
+/* ---- psi on E'(Fp2) (affine input) and fast subgroup tests (same boolean as [r]P == O) */
+static void g2_psi_affine(g2 *r, const g2 *a /* z == 1 */) {
+    fp2 cx, cy; memcpy(&cx.a, K_PSI_CX[0], 48); memcpy(&cx.b, K_PSI_CX[1], 48); memcpy(&cy.a, K_PSI_CY[0], 48); memcpy(&cy.b, K_PSI_CY[1], 48);
+    fp2_conj(&r->x, &a->x); fp2_mul(&r->x, &r->x, &cx);
+    fp2_conj(&r->y, &a->y); fp2_mul(&r->y, &r->y, &cy);
+    fp2_one(&r->z);
+}
+static void g2_psi(g2 *r, const g2 *p) {
+    if (g2_is_inf(p)) { g2_set_inf(r); return; }
+    g2 a; g2_normalize(&a, p); g2_psi_affine(r, &a);
+}
+static void g2_mul_zabs(g2 *r, const g2 *p) {
+    g2 acc = *p;
+    for (int i = 62; i >= 0; i--) { g2_dbl(&acc, &acc); if ((K_Z_ABS >> i) & 1) g2_add(&acc, &acc, p); }
+    *r = acc;
+}
+/* Q in G2  <=>  psi(Q) == [z]Q  (z < 0) */
+static int g2_in_subgroup(const g2 *p) {
+    if (g2_is_inf(p)) return 1;
+    g2 a, b; g2_psi(&a, p); g2_mul_zabs(&b, p); g2_neg(&b, &b);
+    return g2_eq(&a, &b);
+}
+/* P in G1  <=>  phi(P) == -[z^2]P, phi(x,y) = (beta x, y) */
+static int g1_in_subgroup(const g1 *p) {
+    if (g1_is_inf(p)) return 1;
+    g1 a, b = *p, c; g1_normalize(&a, p);
+    for (int k = 0; k < 2; k++) {
+        c = b;
+        for (int i = 62; i >= 0; i--) { g1_dbl(&c, &c); if ((K_Z_ABS >> i) & 1) g1_add(&c, &c, &b); }
+        b = c;
+    }
+    g1_neg(&b, &b);
+    fp beta; fp_set(&beta, K_BETA); fp_mul(&a.x, &a.x, &beta);
+    return g1_eq(&a, &b);
+}
+
+/* ------------------------------------------------------------------ serialisation */
+static void g1_serialize(u8 out[48], const g1 *p) {
+    if (g1_is_inf(p)) { memset(out, 0, 48); return; }
+    g1 a; g1_normalize(&a, p); fp_to_bytes(out, &a.x);
+    if (fp_is_odd(&a.y)) out[47] |= 0x80;
+}
+static int g1_deserialize(g1 *r, const u8 in[48], int check_order) {
+    u8 b[48]; memcpy(b, in, 48);
+    int allz = 1; for (int i = 0; i < 48; i++) if (b[i]) { allz = 0; break; }
+    if (allz) { g1_set_inf(r); return 1; }
+    int odd = b[47] >> 7; b[47] &= 0x7f;
+    fp x, y, t, bb;
+    if (!fp_from_bytes(&x, b)) return 0;
+    fp_sqr(&t, &x); fp_mul(&t, &t, &x); fp_set(&bb, K_B1); fp_add(&t, &t, &bb);
+    if (!fp_sqrt(&y, &t)) return 0;
+    if (fp_is_odd(&y) != odd) fp_neg(&y, &y);
+    r->x = x; r->y = y; fp_set(&r->z, K_ONE);
+    if (check_order && !g1_in_subgroup(r)) return 0;
+    return 1;
+}
+static void g2_serialize(u8 out[96], const g2 *p) {
+    if (g2_is_inf(p)) { memset(out, 0, 96); return; }
+    g2 a; g2_normalize(&a, p); fp_to_bytes(out, &a.x.a); fp_to_bytes(out + 48, &a.x.b);
+    if (fp_is_odd(&a.y.a)) out[95] |= 0x80;
+}
+static int g2_deserialize(g2 *r, const u8 in[96], int check_order) {
+    u8 b[96]; memcpy(b, in, 96);
+    int allz = 1; for (int i = 0; i < 96; i++) if (b[i]) { allz = 0; break; }
+    if (allz) { g2_set_inf(r); return 1; }
+    int odd = b[95] >> 7; b[95] &= 0x7f;
+    fp2 x, y, t, bb;
+    if (!fp_from_bytes(&x.a, b) || !fp_from_bytes(&x.b, b + 48)) return 0;
+    fp2_sqr(&t, &x); fp2_mul(&t, &t, &x); memcpy(&bb.a, K_B2[0], 48); memcpy(&bb.b, K_B2[1], 48); fp2_add(&t, &t, &bb);
+    if (!fp2_sqrt(&y, &t)) return 0;
+    if (fp_is_odd(&y.a) != odd) fp2_neg(&y, &y);
+    r->x = x; r->y = y; fp2_one(&r->z);
+    if (check_order && !g2_in_subgroup(r)) return 0;
+    return 1;
+}
+
+/* ------------------------------------------------------------------ message -> G2 */
+static void hash_to_fp(fp *t, const u8 *msg, size_t len) {
+    /* mcl Fp::setArrayMask: first min(len,48) bytes little-endian, masked to 381 bits, then 380 if still >= p */
+    u8 b[48]; memset(b, 0, 48); memcpy(b, msg, len > 48 ? 48 : len);
+    u64 v[6]; memcpy(v, b, 48);
+    v[5] &= (1ull << 61) - 1;
+    if (limbs_geq_p(v)) v[5] &= (1ull << 60) - 1;
+    fp_from_int_limbs(t, v);
+}
+/* mcl MapTo::calcBN on Fp2 (Fouque-Tibouchi / Shallue-van de Woestijne) */
+static int sw_map_g2(g2 *r, const fp2 *t) {
+    if (fp2_is_zero(t)) return 0;
+    fp n, c1, c2, one; fp2 w, x, y, g, bb;
+    fp_set(&c1, K_SW_C1); fp_set(&c2, K_SW_C2); fp_set(&one, K_ONE);
+    memcpy(&bb.a, K_B2[0], 48); memcpy(&bb.b, K_B2[1], 48);
+    fp2_norm(&n, t); int negative = fp_legendre(&n) < 0;
+    fp2_sqr(&w, t); fp2_add(&w, &w, &bb); fp_add(&w.a, &w.a, &one);
+    if (fp2_is_zero(&w)) return 0;
+    fp2_inv(&w, &w); fp2_mul_fp(&w, &w, &c1); fp2_mul(&w, &w, t);
+    for (int i = 0; i < 3; i++) {
+        if (i == 0) { fp2_mul(&x, t, &w); fp2_neg(&x, &x); fp_add(&x.a, &x.a, &c2); }
+        else if (i == 1) { fp2_neg(&x, &x); fp_sub(&x.a, &x.a, &one); }
+        else { fp2_sqr(&x, &w); fp2_inv(&x, &x); fp_add(&x.a, &x.a, &one); }
+        fp2_sqr(&g, &x); fp2_mul(&g, &g, &x); fp2_add(&g, &g, &bb);
+        if (fp2_sqrt(&y, &g)) {
+            if (negative) fp2_neg(&y, &y);
+            r->x = x; r->y = y; fp2_one(&r->z);
+            return 1;
+        }
+    }
+    return 0;
+}
+/* Budroni-Pintore: [z^2 - z - 1]P + psi([z - 1]P) + psi^2([2]P) */
+static void g2_clear_cofactor(g2 *r, const g2 *p) {
+    g2 zp, z2p, t1, t2, t3, np;
+    g2_mul_zabs(&zp, p); g2_neg(&zp, &zp);            /* [z]P */
+    g2_mul_zabs(&z2p, &zp); g2_neg(&z2p, &z2p);        /* [z^2]P */
+    g2_neg(&np, p);
+    g2_add(&t1, &z2p, &np); g2_neg(&t2, &zp); g2_add(&t1, &t1, &t2);   /* [z^2 - z - 1]P */
+    g2_add(&t2, &zp, &np); g2_psi(&t2, &t2);                            /* psi([z-1]P) */
+    g2_dbl(&t3, p); g2_psi(&t3, &t3); g2_psi(&t3, &t3);                 /* psi^2([2]P) */
+    g2_add(&t1, &t1, &t2); g2_add(r, &t1, &t3);
+}
+static int map_to_g2(g2 *r, const u8 *msg, size_t len) {
+    fp2 t; hash_to_fp(&t.a, msg, len); fp_zero(&t.b);
+    g2 a; if (!sw_map_g2(&a, &t)) return 0;
+    g2_clear_cofactor(r, &a); return 1;
+}
+
+/* ------------------------------------------------------------------ pairing: multi-pair optimal-ate Miller loop + final exponentiation */
+typedef struct { fp2 x, y, z; } g2proj;   /* homogeneous projective on the twist */
+/* doubling step: line (c0, c2*xP, c3*yP) at w^0, w^2, w^3 */
+static void ml_dbl(g2proj *t, fp2 *l0, fp2 *l2, fp2 *l3) {
+    fp2 A, B, C, E, F, H, s, b3; fp inv2; fp_set(&inv2, K_INV2);
+    memcpy(&b3.a, K_B2_3[0], 48); memcpy(&b3.b, K_B2_3[1], 48);
+    fp2_mul(&A, &t->x, &t->y); fp2_mul_fp(&A, &A, &inv2);
+    fp2_sqr(&B, &t->y); fp2_sqr(&C, &t->z);
+    fp2_mul(&E, &b3, &C);
+    fp2_dbl(&F, &E); fp2_add(&F, &F, &E);
+    fp2_add(&H, &t->y, &t->z); fp2_sqr(&H, &H); fp2_sub(&H, &H, &B); fp2_sub(&H, &H, &C);    /* 2YZ */
+    fp2_sub(l0, &B, &E);                                    /* Y^2 - 3b'Z^2 */
+    fp2_sqr(&s, &t->x); fp2_dbl(l2, &s); fp2_add(l2, l2, &s); fp2_neg(l2, l2);   /* -3X^2 */
+    *l3 = H;
+    fp2 x3, y3, e2;
+    fp2_sub(&x3, &B, &F); fp2_mul(&x3, &x3, &A);
+    fp2_add(&y3, &B, &F); fp2_mul_fp(&y3, &y3, &inv2); fp2_sqr(&y3, &y3);
+    fp2_sqr(&e2, &E); fp2_dbl(&s, &e2); fp2_add(&s, &s, &e2); fp2_sub(&y3, &y3, &s);
+    fp2_mul(&t->z, &B, &H); t->x = x3; t->y = y3;
+}
+/* addition step T += Q (Q affine) */
+static void ml_add(g2proj *t, const fp2 *qx, const fp2 *qy, fp2 *l0, fp2 *l2, fp2 *l3) {
+    fp2 th, mu, C, D, E, F, G, H, s;
+    fp2_mul(&th, qy, &t->z); fp2_sub(&th, &t->y, &th);
+    fp2_mul(&mu, qx, &t->z); fp2_sub(&mu, &t->x, &mu);
+    fp2_mul(l0, &th, qx); fp2_mul(&s, &mu, qy); fp2_sub(l0, l0, &s);
+    fp2_neg(l2, &th); *l3 = mu;
+    fp2_sqr(&C, &th); fp2_sqr(&D, &mu); fp2_mul(&E, &mu, &D); fp2_mul(&F, &t->z, &C); fp2_mul(&G, &t->x, &D);
+    fp2_add(&H, &E, &F); fp2_sub(&H, &H, &G); fp2_sub(&H, &H, &G);
+    fp2 x3, y3;
+    fp2_mul(&x3, &mu, &H);
+    fp2_sub(&y3, &G, &H); fp2_mul(&y3, &y3, &th); fp2_mul(&s, &E, &t->y); fp2_sub(&y3, &y3, &s);
+    fp2_mul(&t->z, &t->z, &E); t->x = x3; t->y = y3;
+}
+#define HO_MAX_PAIRS 16
+/* f = prod_i f_{|z|,Q_i}(P_i); P_i, Q_i affine (z==1), identities must be filtered by the caller */
+static void miller_loop(fp12 *f, int n, const g1 *ps, const g2 *qs) {
+    g2proj T[HO_MAX_PAIRS]; fp2 l0, l2, l3;
+    for (int k = 0; k < n; k++) { T[k].x = qs[k].x; T[k].y = qs[k].y; fp2_one(&T[k].z); }
+    fp12_one(f);
+    for (int i = 62; i >= 0; i--) {
+        fp12_sqr(f, f);
+        for (int k = 0; k < n; k++) {
+            ml_dbl(&T[k], &l0, &l2, &l3);
+            fp2_mul_fp(&l2, &l2, &ps[k].x); fp2_mul_fp(&l3, &l3, &ps[k].y);
+            fp12_mul_by_014(f, f, &l0, &l2, &l3);
+        }
+        if ((K_Z_ABS >> i) & 1) for (int k = 0; k < n; k++) {
+            ml_add(&T[k], &qs[k].x, &qs[k].y, &l0, &l2, &l3);
+            fp2_mul_fp(&l2, &l2, &ps[k].x); fp2_mul_fp(&l3, &l3, &ps[k].y);
+            fp12_mul_by_014(f, f, &l0, &l2, &l3);
+        }
+    }
+    fp12_conj(f, f);
+}
+/* f^((p^12-1)/r * 3): easy part then (z-1)^2 (z+p) (z^2+p^2-1) + 3 */
+static void final_exp(fp12 *r, const fp12 *f) {
+    fp12 t0, t1, t2, m;
+    fp12_conj(&t0, f); fp12_inv(&t1, f); fp12_mul(&m, &t0, &t1);
+    fp12_frob2(&t0, &m); fp12_mul(&m, &t0, &m);
+    /* a = m^(z-1) */
+    fp12_cyc_exp_z(&t0, &m); fp12_conj(&t1, &m); fp12_mul(&t0, &t0, &t1);
+    /* b = a^(z-1) */
+    fp12_cyc_exp_z(&t1, &t0); fp12_conj(&t2, &t0); fp12_mul(&t1, &t1, &t2);
+    /* c = b^(z+p) */
+    fp12_cyc_exp_z(&t0, &t1); fp12_frob(&t2, &t1); fp12_mul(&t0, &t0, &t2);
+    /* d = c^(z^2+p^2-1) */
+    fp12_cyc_exp_z(&t1, &t0); fp12_cyc_exp_z(&t1, &t1); fp12_frob2(&t2, &t0); fp12_mul(&t1, &t1, &t2);
+    fp12_conj(&t2, &t0); fp12_mul(&t1, &t1, &t2);
+    /* * m^3 */
+    fp12_cyc_sqr(&t2, &m); fp12_mul(&t2, &t2, &m); fp12_mul(r, &t1, &t2);
+}
+static int pairing_product_is_one(int n, const g1 *ps, const g2 *qs) {
+    g1 pa[HO_MAX_PAIRS]; g2 qa[HO_MAX_PAIRS]; int m = 0;
+    for (int k = 0; k < n; k++) {
+        if (g1_is_inf(&ps[k]) || g2_is_inf(&qs[k])) continue;
+        g1_normalize(&pa[m], &ps[k]); g2_normalize(&qa[m], &qs[k]); m++;
+    }
+    fp12 f; miller_loop(&f, m, pa, qa); final_exp(&f, &f);
+    return fp12_is_one(&f);
+}
+
+/* ------------------------------------------------------------------ scalars */
+static int fr_from_bytes(u64 k[4], const u8 b[32]) {
+    memcpy(k, b, 32);
+    for (int i = 3; i >= 0; i--) { if (k[i] > K_R_ORDER[i]) return 0; if (k[i] < K_R_ORDER[i]) return 1; }
+    return 0;
+}
+
+/* ================================================================== exported API (ctypes) */
+#define API __attribute__((visibility("default")))
+
+API void ho_counters_reset(void) { g_cnt_mul = g_cnt_sqr = 0; }
+API void ho_counters_get(u64 out[2]) { out[0] = g_cnt_mul; out[1] = g_cnt_sqr; }
+
+/* --- field-level probes for kernel parity tests: canonical little-endian 48-byte values */
+API int ho_fp_mul(const u8 *a, const u8 *b, u8 *out) { fp x, y; if (!fp_from_bytes(&x, a) || !fp_from_bytes(&y, b)) return -1; fp_mul(&x, &x, &y); fp_to_bytes(out, &x); return 0; }
+API int ho_fp_add(const u8 *a, const u8 *b, u8 *out) { fp x, y; if (!fp_from_bytes(&x, a) || !fp_from_bytes(&y, b)) return -1; fp_add(&x, &x, &y); fp_to_bytes(out, &x); return 0; }
+API int ho_fp_sub(const u8 *a, const u8 *b, u8 *out) { fp x, y; if (!fp_from_bytes(&x, a) || !fp_from_bytes(&y, b)) return -1; fp_sub(&x, &x, &y); fp_to_bytes(out, &x); return 0; }
+API int ho_fp_inv(const u8 *a, u8 *out) { fp x; if (!fp_from_bytes(&x, a)) return -1; fp_inv(&x, &x); fp_to_bytes(out, &x); return 0; }
+API int ho_fp_sqrt(const u8 *a, u8 *out) { fp x; if (!fp_from_bytes(&x, a)) return -1; if (!fp_sqrt(&x, &x)) return 0; fp_to_bytes(out, &x); return 1; }
+API int ho_fp2_mul(const u8 *a, const u8 *b, u8 *out) {
+    fp2 x, y; if (!fp_from_bytes(&x.a, a) || !fp_from_bytes(&x.b, a + 48) || !fp_from_bytes(&y.a, b) || !fp_from_bytes(&y.b, b + 48)) return -1;
+    fp2_mul(&x, &x, &y); fp_to_bytes(out, &x.a); fp_to_bytes(out + 48, &x.b); return 0; }
+API int ho_fp2_sqrt(const u8 *a, u8 *out) {
+    fp2 x; if (!fp_from_bytes(&x.a, a) || !fp_from_bytes(&x.b, a + 48)) return -1;
+    if (!fp2_sqrt(&x, &x)) return 0; fp_to_bytes(out, &x.a); fp_to_bytes(out + 48, &x.b); return 1; }
+
+/* --- keys / signatures */
+API int ho_get_public_key(const u8 sk[32], u8 pk48[48]) {
+    u64 k[4]; if (!fr_from_bytes(k, sk)) return -1;
+    g1 g, r; g1_generator(&g); g1_mul(&r, &g, k, 4); g1_serialize(pk48, &r); return 0;
+}
+API int ho_map_to_g2(const u8 *msg, size_t len, u8 out96[96]) { g2 h; if (!map_to_g2(&h, msg, len)) return -1; g2_serialize(out96, &h); return 0; }
+API int ho_sign_hash(const u8 sk[32], const u8 *msg, size_t len, u8 sig96[96]) {
+    u64 k[4]; if (!fr_from_bytes(k, sk)) return -1;
+    g2 h, s; if (!map_to_g2(&h, msg, len)) return -1;
+    g2_mul(&s, &h, k, 4); g2_serialize(sig96, &s); return 0;
+}
+API int ho_pk_deserialize_check(const u8 pk48[48]) { g1 p; return g1_deserialize(&p, pk48, 1); }
+API int ho_sig_deserialize_check(const u8 sig96[96]) { g2 p; return g2_deserialize(&p, sig96, 1); }
+/* a+b, a-b on serialized points (Deserialize; Add/Sub; Serialize) */
+API int ho_pk_add(const u8 a[48], const u8 b[48], int sub, u8 out[48]) {
+    g1 p, q; if (!g1_deserialize(&p, a, 0) || !g1_deserialize(&q, b, 0)) return -1;
+    if (sub) g1_neg(&q, &q);
+    g1_add(&p, &p, &q); g1_serialize(out, &p); return 0;
+}
+API int ho_sig_add(const u8 a[96], const u8 b[96], u8 out[96]) {
+    g2 p, q; if (!g2_deserialize(&p, a, 0) || !g2_deserialize(&q, b, 0)) return -1;
+    g2_add(&p, &p, &q); g2_serialize(out, &p); return 0;
+}
+static int verify_core(const g2 *sig, const g1 *pk, const u8 *msg, size_t len) {
+    g2 h; if (!map_to_g2(&h, msg, len)) return 0;
+    g1 ps[2]; g2 qs[2];
+    g1_generator(&ps[0]); qs[0] = *sig; g1_neg(&ps[1], pk); qs[1] = h;
+    return pairing_product_is_one(2, ps, qs);
+}
+/* leader.go:257-287 pattern: Sign.Deserialize + (cached) pubkey + VerifyHash */
+API int ho_verify_hash(const u8 sig96[96], const u8 pk48[48], const u8 *msg, size_t len) {
+    g2 s; g1 p;
+    if (!g2_deserialize(&s, sig96, 1)) return 0;
+    if (!g1_deserialize(&p, pk48, 1)) return 0;
+    return verify_core(&s, &p, msg, len);
+}
+/* crypto/bls/mask.go:58-64 */
+API int ho_aggregate_sigs(size_t n, const u8 *sigs96, u8 out96[96]) {
+    g2 acc, s; g2_set_inf(&acc);
+    for (size_t i = 0; i < n; i++) { if (!g2_deserialize(&s, sigs96 + 96 * i, 1)) return -1; g2_add(&acc, &acc, &s); }
+    g2_serialize(out96, &acc); return 0;
+}
+
+/* --- committee = decoded pubkey table (the reference keeps it in epochCtx / BLSPubKeyCache: engine.go:644-659, mask.go:35-55) */
+typedef struct { size_t n; g1 *pk; } ho_committee;
+API void *ho_committee_new(size_t n, const u8 *pks48) {
+    ho_committee *c = (ho_committee *)malloc(sizeof *c); c->n = n; c->pk = (g1 *)malloc(sizeof(g1) * (n ? n : 1));
+    for (size_t i = 0; i < n; i++) if (!g1_deserialize(&c->pk[i], pks48 + 48 * i, 1)) { free(c->pk); free(c); return NULL; }
+    return c;
+}
+API void ho_committee_free(void *h) { ho_committee *c = (ho_committee *)h; if (c) { free(c->pk); free(c); } }
+static int committee_mask(const ho_committee *c, const u8 *bitmap, size_t blen, g1 *acc) {
+    if (blen != (c->n + 7) >> 3) return -1;
+    g1_set_inf(acc);
+    for (size_t i = 0; i < c->n; i++) if (bitmap[i >> 3] & (1u << (i & 7))) g1_add(acc, acc, &c->pk[i]);
+    return 0;
+}
+/* mask.go:113-134 SetMask on a fresh Mask, then Serialize */
+API int ho_committee_mask_aggregate(void *h, const u8 *bitmap, size_t blen, u8 out48[48]) {
+    g1 acc; if (committee_mask((ho_committee *)h, bitmap, blen, &acc)) return -1;
+    g1_serialize(out48, &acc); return 0;
+}
+/* engine.go:619-642: Deserialize sig, SetMask, VerifyHash(mask.AggregatePublic, payload) -> 1/0, -1 on bitmap length error */
+API int ho_committee_aggregate_verify(void *h, const u8 *bitmap, size_t blen, const u8 sig96[96], const u8 *msg, size_t len) {
+    g2 s; g1 acc;
+    if (!g2_deserialize(&s, sig96, 1)) return 0;
+    if (committee_mask((ho_committee *)h, bitmap, blen, &acc)) return -1;
+    return verify_core(&s, &acc, msg, len);
+}
+API int ho_mask_aggregate(size_t n, const u8 *pks48, const u8 *bitmap, size_t blen, u8 out48[48]) {
+    void *c = ho_committee_new(n, pks48); if (!c) return -2;
+    int rc = ho_committee_mask_aggregate(c, bitmap, blen, out48); ho_committee_free(c); return rc;
+}
+API int ho_fast_aggregate_verify(size_t n, const u8 *pks48, const u8 *bitmap, size_t blen, const u8 sig96[96], const u8 *msg, size_t len) {
+    void *c = ho_committee_new(n, pks48); if (!c) return 0;
+    int rc = ho_committee_aggregate_verify(c, bitmap, blen, sig96, msg, len); ho_committee_free(c); return rc;
+}
+/* generic pairing-product check on serialized points: prod e(P_i, Q_i) == 1 */
+API int ho_pairing_check(size_t n, const u8 *g1s48, const u8 *g2s96) {
+    if (n > HO_MAX_PAIRS) return -1;
+    g1 ps[HO_MAX_PAIRS]; g2 qs[HO_MAX_PAIRS];
+    for (size_t i = 0; i < n; i++) { if (!g1_deserialize(&ps[i], g1s48 + 48 * i, 0) || !g2_deserialize(&qs[i], g2s96 + 96 * i, 0)) return -1; }
+    return pairing_product_is_one((int)n, ps, qs);
+}
+/* [k]P on serialized points (parity probes for the CUDA scalar-mul kernels) */
+API int ho_g1_mul(const u8 p48[48], const u8 k32[32], u8 out[48]) { g1 p; u64 k[4]; memcpy(k, k32, 32); if (!g1_deserialize(&p, p48, 0)) return -1; g1_mul(&p, &p, k, 4); g1_serialize(out, &p); return 0; }
+API int ho_g2_mul(const u8 p96[96], const u8 k32[32], u8 out[96]) { g2 p; u64 k[4]; memcpy(k, k32, 32); if (!g2_deserialize(&p, p96, 0)) return -1; g2_mul(&p, &p, k, 4); g2_serialize(out, &p); return 0; }
