@@ -1,0 +1,361 @@
+"""harmony_b200/bls.py -- ctypes binding of libhbls.so (include/hbls.h) with the reference's Go names.
+
+Mirrors, identifier for identifier, what Harmony code calls on this path:
+  github.com/harmony-one/bls/ffi/go/bls : Init, SecretKey, PublicKey, Sign
+  crypto/bls                            : Mask (mask.go:67-242), AggregateSig (mask.go:58-64),
+                                          BytesToBLSPublicKey + LRU (mask.go:35-55), SeparateSigAndMask (bls.go:120-136)
+plus the BASELINE.json names FastAggregateVerify / VerifyAggregateSig as wrappers over
+SetMask + VerifyHash (internal/chain/engine.go:630-640).
+
+Every group / field operation goes through the C ABI into CUDA kernels.  No CPU fallback: if the shared library
+or a CUDA device is missing this module raises.
+"""
+import ctypes, os
+from collections import OrderedDict
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "lib", "libhbls.so")
+
+BLS12_381 = 5
+_COMPILED_TIME_VAR = 46
+PublicKeySizeInBytes = 48
+BLSSignatureSizeInBytes = 96
+
+ERR_CUDA, ERR_ARG, ERR_DECODE = -100, -2, -3
+
+_lib = None
+_inited = False
+
+class HblsError(RuntimeError):
+    pass
+
+class _Sec(ctypes.Structure):
+    _fields_ = [("d", ctypes.c_uint64 * 4)]
+class _Pub(ctypes.Structure):
+    _fields_ = [("d", ctypes.c_uint64 * 18)]
+class _Sig(ctypes.Structure):
+    _fields_ = [("d", ctypes.c_uint64 * 36)]
+
+def lib():
+    """Load libhbls.so (built in-tree by harmony_b200/build.py); raise loudly when absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise HblsError(f"{_LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(the BLS backend is CUDA-only; there is no CPU fallback)")
+        L = ctypes.CDLL(_LIB_PATH)
+        c = ctypes
+        vp, sz, u8p = c.c_void_p, c.c_size_t, c.c_char_p
+        def sig(name, res, *args):
+            f = getattr(L, name); f.restype = res; f.argtypes = list(args)
+        sig("blsInit", c.c_int, c.c_int, c.c_int)
+        sig("hbls_init_device", c.c_int, c.c_int)
+        sig("blsSecretKeySetByCSPRNG", c.c_int, c.POINTER(_Sec))
+        sig("blsGetPublicKey", None, c.POINTER(_Pub), c.POINTER(_Sec))
+        sig("blsSignHash", c.c_int, c.POINTER(_Sig), c.POINTER(_Sec), u8p, sz)
+        sig("blsVerifyHash", c.c_int, c.POINTER(_Sig), c.POINTER(_Pub), u8p, sz)
+        sig("blsSign", None, c.POINTER(_Sig), c.POINTER(_Sec), u8p, sz)
+        sig("blsVerify", c.c_int, c.POINTER(_Sig), c.POINTER(_Pub), u8p, sz)
+        sig("blsPublicKeyAdd", None, c.POINTER(_Pub), c.POINTER(_Pub))
+        sig("blsPublicKeySub", None, c.POINTER(_Pub), c.POINTER(_Pub))
+        sig("blsSignatureAdd", None, c.POINTER(_Sig), c.POINTER(_Sig))
+        sig("blsSecretKeySerialize", sz, vp, sz, c.POINTER(_Sec))
+        sig("blsPublicKeySerialize", sz, vp, sz, c.POINTER(_Pub))
+        sig("blsSignatureSerialize", sz, vp, sz, c.POINTER(_Sig))
+        sig("blsSecretKeyDeserialize", sz, c.POINTER(_Sec), u8p, sz)
+        sig("blsPublicKeyDeserialize", sz, c.POINTER(_Pub), u8p, sz)
+        sig("blsSignatureDeserialize", sz, c.POINTER(_Sig), u8p, sz)
+        sig("blsSecretKeyIsEqual", c.c_int, c.POINTER(_Sec), c.POINTER(_Sec))
+        sig("blsPublicKeyIsEqual", c.c_int, c.POINTER(_Pub), c.POINTER(_Pub))
+        sig("blsSignatureIsEqual", c.c_int, c.POINTER(_Sig), c.POINTER(_Sig))
+        sig("hbls_committee_create", c.c_int, c.POINTER(vp), u8p, sz, c.POINTER(sz))
+        sig("hbls_committee_destroy", None, vp)
+        sig("hbls_committee_size", sz, vp)
+        sig("hbls_mask_aggregate", c.c_int, vp, u8p, sz, vp)
+        sig("hbls_aggregate_sigs", c.c_int, u8p, sz, vp)
+        sig("hbls_aggregate_verify", c.c_int, vp, u8p, sz, u8p, u8p, sz)
+        sig("hbls_aggregate_verify_batch", c.c_int, vp, sz, vp, sz, vp, vp, sz, vp)
+        sig("hbls_aggregate_verify_batch_device", c.c_int, vp, sz, vp, sz, vp, vp, sz, vp, vp)
+        sig("hbls_verify_batch", c.c_int, sz, vp, vp, vp, sz, vp)
+        sig("hbls_sign_hash_batch", c.c_int, sz, vp, vp, sz, vp, vp)
+        sig("hbls_get_public_key_batch", c.c_int, sz, vp, vp)
+        sig("hbls_map_to_g2", c.c_int, u8p, sz, vp)
+        sig("hbls_fp_mul_batch", c.c_int, sz, vp, vp, vp)
+        sig("hbls_kernel_launch_count", c.c_uint64)
+        sig("hbls_probe_mac32_per_s", c.c_double, c.c_int)
+        _lib = L
+    return _lib
+
+def Init(curve=BLS12_381, device=None):
+    """bls.Init(bls.BLS12_381) (crypto/bls/mask.go:18-20).  Raises when no CUDA device is usable."""
+    global _inited
+    L = lib()
+    rc = L.hbls_init_device(device) if device is not None else L.blsInit(curve, _COMPILED_TIME_VAR)
+    if rc != 0:
+        raise HblsError(f"blsInit failed rc={rc}: a CUDA device is required (no CPU fallback)")
+    _inited = True
+
+def _need():
+    if not _inited:
+        Init()
+    return _lib
+
+def _buf(b):
+    return bytes(b)
+
+# ------------------------------------------------------------------ ffi/go/bls value types
+class SecretKey:
+    def __init__(self): self.v = _Sec()
+    def SetByCSPRNG(self):
+        if _need().blsSecretKeySetByCSPRNG(ctypes.byref(self.v)) != 0: raise HblsError("SetByCSPRNG failed")
+    def GetPublicKey(self):
+        pk = PublicKey(); _need().blsGetPublicKey(ctypes.byref(pk.v), ctypes.byref(self.v)); return pk
+    def SignHash(self, h: bytes):
+        """nil (None) on failure, like the Go wrapper (callers check != nil: consensus/construct.go:101)."""
+        s = Sign()
+        return s if _need().blsSignHash(ctypes.byref(s.v), ctypes.byref(self.v), _buf(h), len(h)) == 0 else None
+    def Sign(self, m):
+        m = m.encode() if isinstance(m, str) else m
+        s = Sign(); _need().blsSign(ctypes.byref(s.v), ctypes.byref(self.v), _buf(m), len(m)); return s
+    def Serialize(self) -> bytes:
+        out = ctypes.create_string_buffer(32); n = _need().blsSecretKeySerialize(out, 32, ctypes.byref(self.v)); return out.raw[:n]
+    def Deserialize(self, b: bytes):
+        if _need().blsSecretKeyDeserialize(ctypes.byref(self.v), _buf(b), len(b)) == 0: raise ValueError("err blsSecretKeyDeserialize")
+    def SerializeToHexStr(self): return self.Serialize().hex()
+    def DeserializeHexStr(self, s: str): self.Deserialize(bytes.fromhex(s))
+    def IsEqual(self, o): return _need().blsSecretKeyIsEqual(ctypes.byref(self.v), ctypes.byref(o.v)) == 1
+
+class PublicKey:
+    """Zero value = identity (crypto/bls/mask.go:88).  Plain value type: copy() is a struct copy."""
+    def __init__(self): self.v = _Pub()
+    def copy(self):
+        p = PublicKey(); ctypes.memmove(ctypes.byref(p.v), ctypes.byref(self.v), ctypes.sizeof(_Pub)); return p
+    def Serialize(self) -> bytes:
+        out = ctypes.create_string_buffer(48); n = _need().blsPublicKeySerialize(out, 48, ctypes.byref(self.v)); return out.raw[:n]
+    def Deserialize(self, b: bytes):
+        if _need().blsPublicKeyDeserialize(ctypes.byref(self.v), _buf(b), len(b)) == 0: raise ValueError("err blsPublicKeyDeserialize")
+    def SerializeToHexStr(self): return self.Serialize().hex()
+    def DeserializeHexStr(self, s: str): self.Deserialize(bytes.fromhex(s))
+    def Add(self, rhs): _need().blsPublicKeyAdd(ctypes.byref(self.v), ctypes.byref(rhs.v))
+    def Sub(self, rhs): _need().blsPublicKeySub(ctypes.byref(self.v), ctypes.byref(rhs.v))
+    def IsEqual(self, o): return _need().blsPublicKeyIsEqual(ctypes.byref(self.v), ctypes.byref(o.v)) == 1
+
+class Sign:
+    """Zero value = identity (crypto/bls/mask.go:59)."""
+    def __init__(self): self.v = _Sig()
+    def copy(self):
+        p = Sign(); ctypes.memmove(ctypes.byref(p.v), ctypes.byref(self.v), ctypes.sizeof(_Sig)); return p
+    def Serialize(self) -> bytes:
+        out = ctypes.create_string_buffer(96); n = _need().blsSignatureSerialize(out, 96, ctypes.byref(self.v)); return out.raw[:n]
+    def Deserialize(self, b: bytes):
+        if _need().blsSignatureDeserialize(ctypes.byref(self.v), _buf(b), len(b)) == 0: raise ValueError("err blsSignatureDeserialize")
+    def SerializeToHexStr(self): return self.Serialize().hex()
+    def DeserializeHexStr(self, s: str): self.Deserialize(bytes.fromhex(s))
+    def Add(self, rhs): _need().blsSignatureAdd(ctypes.byref(self.v), ctypes.byref(rhs.v))
+    def VerifyHash(self, pub: PublicKey, h: bytes) -> bool:
+        return _need().blsVerifyHash(ctypes.byref(self.v), ctypes.byref(pub.v), _buf(h), len(h)) == 1
+    def Verify(self, pub: PublicKey, m) -> bool:
+        m = m.encode() if isinstance(m, str) else m
+        return _need().blsVerify(ctypes.byref(self.v), ctypes.byref(pub.v), _buf(m), len(m)) == 1
+    def IsEqual(self, o): return _need().blsSignatureIsEqual(ctypes.byref(self.v), ctypes.byref(o.v)) == 1
+
+# ------------------------------------------------------------------ crypto/bls (bls.go, mask.go)
+class PublicKeyWrapper:
+    """crypto/bls/bls.go:30-33: serialized + deserialized form."""
+    def __init__(self, bytes_: bytes, obj: PublicKey): self.Bytes = bytes(bytes_); self.Object = obj
+    def Hex(self): return self.Bytes.hex()
+
+class PrivateKeyWrapper:
+    def __init__(self, pri: SecretKey, pub: PublicKeyWrapper): self.Pri = pri; self.Pub = pub
+
+def WrapperFromPrivateKey(pri: SecretKey) -> PrivateKeyWrapper:
+    pub = pri.GetPublicKey()
+    return PrivateKeyWrapper(pri, PublicKeyWrapper(pub.Serialize(), pub))
+
+def RandPrivateKey() -> SecretKey:
+    s = SecretKey(); s.SetByCSPRNG(); return s
+
+_BLS_PUBKEY_CACHE_SIZE = 1024
+BLSPubKeyCache = OrderedDict()
+
+def BytesToBLSPublicKey(b: bytes) -> PublicKey:
+    """crypto/bls/mask.go:35-55 incl. the 1024-entry LRU keyed by the raw bytes."""
+    if len(b) == 0: raise ValueError("BytesToBLSPublicKey: empty input")
+    k = bytes(b)
+    if k in BLSPubKeyCache:
+        BLSPubKeyCache.move_to_end(k); return BLSPubKeyCache[k].copy()
+    pk = PublicKey(); pk.Deserialize(k)
+    BLSPubKeyCache[k] = pk.copy()
+    if len(BLSPubKeyCache) > _BLS_PUBKEY_CACHE_SIZE: BLSPubKeyCache.popitem(last=False)
+    return pk
+
+def AggregateSig(sigs) -> Sign:
+    """crypto/bls/mask.go:58-64: fold Sign.Add from the zero value."""
+    agg = Sign()
+    for s in sigs: agg.Add(s)
+    return agg
+
+def SeparateSigAndMask(commit_sigs: bytes):
+    """crypto/bls/bls.go:120-136."""
+    if len(commit_sigs) < BLSSignatureSizeInBytes:
+        raise ValueError("no mask data found in commit sigs")
+    return bytes(commit_sigs[:96]), bytes(commit_sigs[96:])
+
+class Committee:
+    """Device-resident decoded public-key table (hbls_committee_*): the GPU analogue of the epochCtx cache of
+    internal/chain/engine.go:644-659.  Keys are decoded and subgroup-checked once, on the GPU."""
+    def __init__(self, pubkeys48):
+        L = _need()
+        blob = b"".join(bytes(p) for p in pubkeys48)
+        self.n = len(blob) // 48
+        self.h = ctypes.c_void_p()
+        bad = ctypes.c_size_t(0)
+        rc = L.hbls_committee_create(ctypes.byref(self.h), blob, self.n, ctypes.byref(bad))
+        if rc == ERR_DECODE: raise ValueError(f"invalid public key at index {bad.value}")
+        if rc != 0: raise HblsError(f"hbls_committee_create rc={rc}")
+    def __del__(self):
+        try:
+            if self.h and _lib is not None: _lib.hbls_committee_destroy(self.h); self.h = None
+        except Exception: pass
+    def __len__(self): return self.n
+    def blen(self): return (self.n + 7) >> 3
+    def MaskAggregate(self, bitmap: bytes) -> bytes:
+        out = ctypes.create_string_buffer(48)
+        rc = _lib.hbls_mask_aggregate(self.h, _buf(bitmap), len(bitmap), out)
+        if rc == ERR_ARG: raise ValueError(f"mismatching bitmap lengths expectedBitmapLength {self.blen()} providedBitmapLength {len(bitmap)}")
+        if rc != 0: raise HblsError(f"hbls_mask_aggregate rc={rc}")
+        return out.raw
+    def AggregateVerify(self, bitmap: bytes, sig96: bytes, msg: bytes) -> bool:
+        rc = _lib.hbls_aggregate_verify(self.h, _buf(bitmap), len(bitmap), _buf(sig96), _buf(msg), len(msg))
+        if rc == ERR_ARG: raise ValueError(f"mismatching bitmap lengths expectedBitmapLength {self.blen()} providedBitmapLength {len(bitmap)}")
+        if rc < 0: raise HblsError(f"hbls_aggregate_verify rc={rc}")
+        return rc == 1
+    def AggregateVerifyBatch(self, bitmaps: bytes, sigs96: bytes, msgs: bytes, msg_len: int) -> bytes:
+        B = len(sigs96) // 96
+        assert len(bitmaps) == B * self.blen() and len(msgs) == B * msg_len
+        res = ctypes.create_string_buffer(B if B else 1)
+        rc = _lib.hbls_aggregate_verify_batch(self.h, B, _buf(bitmaps), self.blen(), _buf(sigs96), _buf(msgs), msg_len, res)
+        if rc != 0: raise HblsError(f"hbls_aggregate_verify_batch rc={rc}")
+        return res.raw[:B]
+
+def FastAggregateVerify(committee: Committee, bitmap: bytes, sig96: bytes, msg: bytes) -> bool:
+    """BASELINE.json name; == Deserialize + Mask.SetMask + aggSig.VerifyHash(mask.AggregatePublic, msg)
+    (internal/chain/engine.go:630-640)."""
+    return committee.AggregateVerify(bitmap, sig96, msg)
+VerifyAggregateSig = FastAggregateVerify
+
+def AggregateSigBytes(sigs96) -> bytes:
+    """AggregateSig on serialized signatures (consensus/quorum/quorum.go:164-196 re-decodes hex ballots)."""
+    blob = b"".join(bytes(s) for s in sigs96)
+    out = ctypes.create_string_buffer(96)
+    rc = _need().hbls_aggregate_sigs(blob, len(blob) // 96, out)
+    if rc == ERR_DECODE: raise ValueError("err blsSignatureDeserialize")
+    if rc != 0: raise HblsError(f"hbls_aggregate_sigs rc={rc}")
+    return out.raw
+
+def VerifyBatch(pks48: bytes, sigs96: bytes, msgs: bytes, msg_len: int) -> bytes:
+    k = len(sigs96) // 96
+    res = ctypes.create_string_buffer(k if k else 1)
+    rc = _need().hbls_verify_batch(k, _buf(pks48), _buf(sigs96), _buf(msgs), msg_len, res)
+    if rc != 0: raise HblsError(f"hbls_verify_batch rc={rc}")
+    return res.raw[:k]
+
+def SignHashBatch(sks32: bytes, msgs: bytes, msg_len: int):
+    k = len(sks32) // 32
+    out = ctypes.create_string_buffer(96 * k if k else 1); ok = ctypes.create_string_buffer(k if k else 1)
+    rc = _need().hbls_sign_hash_batch(k, _buf(sks32), _buf(msgs), msg_len, out, ok)
+    if rc != 0: raise HblsError(f"hbls_sign_hash_batch rc={rc}")
+    return out.raw[:96 * k], ok.raw[:k]
+
+def GetPublicKeyBatch(sks32: bytes) -> bytes:
+    k = len(sks32) // 32
+    out = ctypes.create_string_buffer(48 * k if k else 1)
+    rc = _need().hbls_get_public_key_batch(k, _buf(sks32), out)
+    if rc != 0: raise HblsError(f"hbls_get_public_key_batch rc={rc}")
+    return out.raw[:48 * k]
+
+def MapToG2(msg: bytes):
+    out = ctypes.create_string_buffer(96)
+    rc = _need().hbls_map_to_g2(_buf(msg), len(msg), out)
+    return out.raw if rc == 0 else None
+
+def FpMulBatch(a48: bytes, b48: bytes) -> bytes:
+    n = len(a48) // 48
+    out = ctypes.create_string_buffer(48 * n if n else 1)
+    rc = _need().hbls_fp_mul_batch(n, _buf(a48), _buf(b48), out)
+    if rc != 0: raise HblsError(f"hbls_fp_mul_batch rc={rc}")
+    return out.raw[:48 * n]
+
+class Mask:
+    """crypto/bls/mask.go:67-242 -- participation bitmap + running aggregate public key (Add on 0->1, Sub on 1->0)."""
+    def __init__(self, publics):
+        self.Publics = list(publics)
+        self.PublicsIndex = {p.Bytes: i for i, p in enumerate(self.Publics)}
+        self.Bitmap = bytearray(self.Len())
+        self.AggregatePublic = PublicKey()
+    def Clear(self):
+        self.Bitmap = bytearray(self.Len()); self.AggregatePublic = PublicKey()
+    def Mask(self): return bytes(self.Bitmap)
+    def Len(self): return (len(self.Publics) + 7) >> 3
+    def SetMask(self, mask: bytes):
+        if self.Len() != len(mask):
+            raise ValueError(f"mismatching bitmap lengths expectedBitmapLength {self.Len()} providedBitmapLength {len(mask)}")
+        for i in range(len(self.Publics)):
+            byt, msk = i >> 3, 1 << (i & 7)
+            if (self.Bitmap[byt] & msk) == 0 and (mask[byt] & msk) != 0:
+                self.Bitmap[byt] ^= msk; self.AggregatePublic.Add(self.Publics[i].Object)
+            if (self.Bitmap[byt] & msk) != 0 and (mask[byt] & msk) == 0:
+                self.Bitmap[byt] ^= msk; self.AggregatePublic.Sub(self.Publics[i].Object)
+    def SetBit(self, i: int, enable: bool):
+        if i >= len(self.Publics): raise IndexError("index out of range")
+        byt, msk = i >> 3, 1 << (i & 7)
+        if (self.Bitmap[byt] & msk) == 0 and enable:
+            self.Bitmap[byt] ^= msk; self.AggregatePublic.Add(self.Publics[i].Object)
+        if (self.Bitmap[byt] & msk) != 0 and not enable:
+            self.Bitmap[byt] ^= msk; self.AggregatePublic.Sub(self.Publics[i].Object)
+    def GetPubKeyFromMask(self, flag: bool):
+        return [p.Object for i, p in enumerate(self.Publics) if bool(self.Bitmap[i >> 3] & (1 << (i & 7))) == flag]
+    def GetSignedPubKeysFromBitmap(self, bitmap: bytes):
+        if self.Len() != len(bitmap):
+            raise ValueError(f"mismatching bitmap lengths expectedBitmapLength {self.Len()} providedBitmapLength {len(bitmap)}")
+        return [p for i, p in enumerate(self.Publics) if bitmap[i >> 3] & (1 << (i & 7))]
+    def IndexEnabled(self, i: int) -> bool:
+        if i >= len(self.Publics): raise IndexError("index out of range")
+        return (self.Bitmap[i >> 3] & (1 << (i & 7))) != 0
+    def KeyEnabled(self, public: bytes) -> bool:
+        if public not in self.PublicsIndex: raise KeyError("key not found")
+        return self.IndexEnabled(self.PublicsIndex[public])
+    def SetKey(self, public: bytes, enable: bool):
+        if public not in self.PublicsIndex: raise KeyError("key not found")
+        self.SetBit(self.PublicsIndex[public], enable)
+    def SetKeysAtomic(self, publics, enable: bool):
+        idx = []
+        for k in publics:
+            if k.Bytes not in self.PublicsIndex: raise KeyError("key not found")
+            idx.append(self.PublicsIndex[k.Bytes])
+        for i in idx: self.SetBit(i, enable)
+    def CountEnabled(self) -> int:
+        return sum(1 for i in range(len(self.Publics)) if self.Bitmap[i >> 3] & (1 << (i & 7)))
+    def CountTotal(self) -> int: return len(self.Publics)
+
+def NewMask(publics) -> Mask: return Mask(publics)
+
+def AggregateMasks(a: bytes, b: bytes) -> bytes:
+    if len(a) != len(b): raise ValueError("mismatching Bitmap lengths")
+    return bytes(x | y for x, y in zip(a, b))
+
+class CompletePolicy:
+    def Check(self, m: Mask) -> bool: return m.CountEnabled() == m.CountTotal()
+class ThresholdPolicy:
+    def __init__(self, thold: int): self.thold = thold
+    def Check(self, m: Mask) -> bool: return m.CountEnabled() >= self.thold
+def NewThresholdPolicy(thold: int): return ThresholdPolicy(thold)
+
+def ConstructCommitPayload(is_staking: bool, block_hash: bytes, block_num: int, view_id: int) -> bytes:
+    """consensus/signature/signature.go:12-24."""
+    out = block_num.to_bytes(8, "little") + bytes(block_hash)
+    if is_staking: out += view_id.to_bytes(8, "little")
+    return out
+
+def KernelLaunchCount() -> int: return int(lib().hbls_kernel_launch_count())
+def ProbeMac32PerS(iters: int = 4096) -> float: return float(_need().hbls_probe_mac32_per_s(iters))

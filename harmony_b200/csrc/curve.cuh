@@ -1,0 +1,284 @@
+// harmony_b200/csrc/curve.cuh -- G1 = E(Fp): y^2 = x^3 + 4 and G2 = E'(Fp2): y^2 = x^3 + 4(1+i), Jacobian coordinates.
+// SWAP_G layout of the reference: public keys live in G1 (48 B), signatures in G2 (96 B)
+// (reference crypto/bls/bls.go:18-21).  The all-zero struct is the identity, matching the zero-value Go structs
+// the reference starts every aggregate from (crypto/bls/mask.go:59,88).
+#pragma once
+#include "tower.cuh"
+
+namespace hb {
+
+// ---- overloads so the point arithmetic is written once for both coordinate fields
+HB_DEV void f_add(fp& r, const fp& a, const fp& b) { fp_add(r, a, b); }
+HB_DEV void f_sub(fp& r, const fp& a, const fp& b) { fp_sub(r, a, b); }
+HB_DEV void f_dbl(fp& r, const fp& a) { fp_dbl(r, a); }
+HB_DEV void f_neg(fp& r, const fp& a) { fp_neg(r, a); }
+HB_DEV void f_mul(fp& r, const fp& a, const fp& b) { fp_mul(r, a, b); }
+HB_DEV void f_sqr(fp& r, const fp& a) { fp_sqr(r, a); }
+HB_DEV void f_inv(fp& r, const fp& a) { fp_inv(r, a); }
+HB_DEV bool f_is_zero(const fp& a) { return fp_is_zero(a); }
+HB_DEV bool f_eq(const fp& a, const fp& b) { return fp_eq(a, b); }
+HB_DEV void f_zero(fp& r) { fp_zero(r); }
+HB_DEV void f_one(fp& r) { fp_one(r); }
+HB_DEV void f_cmov(fp& r, const fp& a, bool c) { fp_cmov(r, a, c); }
+
+HB_DEV void f_add(fp2& r, const fp2& a, const fp2& b) { fp2_add(r, a, b); }
+HB_DEV void f_sub(fp2& r, const fp2& a, const fp2& b) { fp2_sub(r, a, b); }
+HB_DEV void f_dbl(fp2& r, const fp2& a) { fp2_dbl(r, a); }
+HB_DEV void f_neg(fp2& r, const fp2& a) { fp2_neg(r, a); }
+HB_DEV void f_mul(fp2& r, const fp2& a, const fp2& b) { fp2_mul(r, a, b); }
+HB_DEV void f_sqr(fp2& r, const fp2& a) { fp2_sqr(r, a); }
+HB_DEV void f_inv(fp2& r, const fp2& a) { fp2_inv(r, a); }
+HB_DEV bool f_is_zero(const fp2& a) { return fp2_is_zero(a); }
+HB_DEV bool f_eq(const fp2& a, const fp2& b) { return fp2_eq(a, b); }
+HB_DEV void f_zero(fp2& r) { fp2_zero(r); }
+HB_DEV void f_one(fp2& r) { fp2_one(r); }
+HB_DEV void f_cmov(fp2& r, const fp2& a, bool c) { fp2_cmov(r, a, c); }
+
+template <class F> struct jac { F x, y, z; };     // Jacobian: (X/Z^2, Y/Z^3); z == 0 <=> identity
+template <class F> struct aff { F x, y; };        // affine; x == y == 0 encodes the identity (not on either curve)
+typedef jac<fp> g1; typedef jac<fp2> g2;
+typedef aff<fp> g1a; typedef aff<fp2> g2a;
+
+template <class F> HB_DEV bool pt_is_inf(const jac<F>& p) { return f_is_zero(p.z); }
+template <class F> HB_DEV void pt_set_inf(jac<F>& p) { f_zero(p.x); f_zero(p.y); f_zero(p.z); }
+template <class F> HB_DEV void pt_neg(jac<F>& r, const jac<F>& p) { r.x = p.x; f_neg(r.y, p.y); r.z = p.z; }
+template <class F> HB_DEV bool aff_is_inf(const aff<F>& p) { return f_is_zero(p.x) && f_is_zero(p.y); }
+template <class F> HB_DEV void pt_from_aff(jac<F>& r, const aff<F>& a) {
+    if (aff_is_inf(a)) { pt_set_inf(r); return; }
+    r.x = a.x; r.y = a.y; f_one(r.z);
+}
+
+template <class F> HB_NOINLINE void pt_dbl(jac<F>& r, const jac<F>& p) {
+    if (pt_is_inf(p)) { pt_set_inf(r); return; }
+    F A, B, C, D, E, Fq, t;
+    f_sqr(A, p.x); f_sqr(B, p.y); f_sqr(C, B);
+    f_add(D, p.x, B); f_sqr(D, D); f_sub(D, D, A); f_sub(D, D, C); f_dbl(D, D);
+    f_dbl(E, A); f_add(E, E, A);
+    f_sqr(Fq, E);
+    f_mul(t, p.y, p.z); f_dbl(r.z, t);
+    f_dbl(t, D); f_sub(r.x, Fq, t);
+    f_sub(t, D, r.x); f_mul(t, t, E);
+    f_dbl(C, C); f_dbl(C, C); f_dbl(C, C);
+    f_sub(r.y, t, C);
+}
+
+template <class F> HB_NOINLINE void pt_add(jac<F>& r, const jac<F>& p, const jac<F>& q) {
+    if (pt_is_inf(p)) { r = q; return; }
+    if (pt_is_inf(q)) { r = p; return; }
+    F Z1Z1, Z2Z2, U1, U2, S1, S2, H, R, HH, HHH, V, t;
+    f_sqr(Z1Z1, p.z); f_sqr(Z2Z2, q.z);
+    f_mul(U1, p.x, Z2Z2); f_mul(U2, q.x, Z1Z1);
+    f_mul(S1, p.y, q.z); f_mul(S1, S1, Z2Z2);
+    f_mul(S2, q.y, p.z); f_mul(S2, S2, Z1Z1);
+    f_sub(H, U2, U1); f_sub(R, S2, S1);
+    if (f_is_zero(H)) {
+        if (f_is_zero(R)) { pt_dbl(r, p); return; }
+        pt_set_inf(r); return;
+    }
+    f_sqr(HH, H); f_mul(HHH, H, HH); f_mul(V, U1, HH);
+    f_mul(t, p.z, q.z); f_mul(r.z, t, H);
+    f_sqr(t, R); f_sub(t, t, HHH); f_sub(t, t, V); f_sub(r.x, t, V);
+    f_sub(t, V, r.x); f_mul(t, t, R); f_mul(S1, S1, HHH); f_sub(r.y, t, S1);
+}
+
+// r = p + q with q affine (the committee table is stored affine: 8 M + 3 S instead of 12 M + 4 S)
+template <class F> HB_NOINLINE void pt_add_mixed(jac<F>& r, const jac<F>& p, const aff<F>& q) {
+    if (aff_is_inf(q)) { r = p; return; }
+    if (pt_is_inf(p)) { r.x = q.x; r.y = q.y; f_one(r.z); return; }
+    F Z1Z1, U2, S2, H, R, HH, HHH, V, t;
+    f_sqr(Z1Z1, p.z);
+    f_mul(U2, q.x, Z1Z1);
+    f_mul(S2, q.y, p.z); f_mul(S2, S2, Z1Z1);
+    f_sub(H, U2, p.x); f_sub(R, S2, p.y);
+    if (f_is_zero(H)) {
+        if (f_is_zero(R)) { pt_dbl(r, p); return; }
+        pt_set_inf(r); return;
+    }
+    f_sqr(HH, H); f_mul(HHH, H, HH); f_mul(V, p.x, HH);
+    F y1 = p.y;
+    f_mul(r.z, p.z, H);
+    f_sqr(t, R); f_sub(t, t, HHH); f_sub(t, t, V); f_sub(r.x, t, V);
+    f_sub(t, V, r.x); f_mul(t, t, R); f_mul(y1, y1, HHH); f_sub(r.y, t, y1);
+}
+
+template <class F> HB_NOINLINE bool pt_eq(const jac<F>& p, const jac<F>& q) {
+    if (pt_is_inf(p) || pt_is_inf(q)) return pt_is_inf(p) && pt_is_inf(q);
+    F Z1Z1, Z2Z2, a, b;
+    f_sqr(Z1Z1, p.z); f_sqr(Z2Z2, q.z);
+    f_mul(a, p.x, Z2Z2); f_mul(b, q.x, Z1Z1);
+    if (!f_eq(a, b)) return false;
+    f_mul(a, p.y, q.z); f_mul(a, a, Z2Z2);
+    f_mul(b, q.y, p.z); f_mul(b, b, Z1Z1);
+    return f_eq(a, b);
+}
+
+template <class F> HB_NOINLINE void pt_to_aff(aff<F>& r, const jac<F>& p) {
+    if (pt_is_inf(p)) { f_zero(r.x); f_zero(r.y); return; }
+    F zi, zi2;
+    f_inv(zi, p.z); f_sqr(zi2, zi);
+    f_mul(r.x, p.x, zi2); f_mul(zi2, zi2, zi); f_mul(r.y, p.y, zi2);
+}
+
+// r = [k]p, k = nw little-endian 32-bit words; 4-bit fixed window, uniform control flow
+template <class F> HB_NOINLINE void pt_mul(jac<F>& r, const jac<F>& p, const uint32_t* k, int nw) {
+    jac<F> tbl[16];
+    pt_set_inf(tbl[0]); tbl[1] = p;
+    for (int i = 2; i < 16; i++) pt_add(tbl[i], tbl[i - 1], p);
+    jac<F> acc; pt_set_inf(acc);
+    for (int i = nw * 8 - 1; i >= 0; i--) {
+        uint32_t w = (k[i >> 3] >> (4 * (i & 7))) & 15u;
+        pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc); pt_dbl(acc, acc);
+        if (w) pt_add(acc, acc, tbl[w]);
+    }
+    r = acc;
+}
+// r = [|z|]p, |z| = 0xd201000000010000 (sparse: 63 doublings + 5 additions)
+template <class F> HB_NOINLINE void pt_mul_zabs(jac<F>& r, const jac<F>& p) {
+    jac<F> acc = p;
+    for (int i = 62; i >= 0; i--) {
+        pt_dbl(acc, acc);
+        if ((K_Z_ABS >> i) & 1) pt_add(acc, acc, p);
+    }
+    r = acc;
+}
+
+HB_DEV void g1_generator(g1& r) { fp_set(r.x, K_G1_X); fp_set(r.y, K_G1_Y); fp_one(r.z); }
+
+// ------------------------------------------------------------------ endomorphisms and subgroup membership
+// psi(x, y) = (conj(x) * cx, conj(y) * cy): acts as [p] (== [z] on G2)
+HB_DEV void g2_psi_aff(g2a& r, const g2a& a) {
+    fp2 cx, cy; fp2_const(cx, K_PSI_CX); fp2_const(cy, K_PSI_CY);
+    fp2 t; fp2_conj(t, a.x); fp2_mul(r.x, t, cx);
+    fp2_conj(t, a.y); fp2_mul(r.y, t, cy);
+}
+// Jacobian form: psi(X, Y, Z) = (conj(X) cx, conj(Y) cy, conj(Z)) -- no inversion
+HB_DEV void g2_psi(g2& r, const g2& p) {
+    fp2 cx, cy; fp2_const(cx, K_PSI_CX); fp2_const(cy, K_PSI_CY);
+    fp2 t; fp2_conj(t, p.x); fp2_mul(r.x, t, cx);
+    fp2_conj(t, p.y); fp2_mul(r.y, t, cy);
+    fp2_conj(r.z, p.z);
+}
+// psi^2(X, Y, Z) = (X * N(cx), -Y, Z)
+HB_DEV void g2_psi2(g2& r, const g2& p) {
+    fp c; fp_set(c, K_PSI2_CX);
+    fp2_mul_fp(r.x, p.x, c); fp2_neg(r.y, p.y); r.z = p.z;
+}
+// Q in G2  <=>  psi(Q) == [z]Q   (same boolean as [r]Q == O)
+HB_DEV bool g2_in_subgroup(const g2& p) {
+    if (pt_is_inf(p)) return true;
+    g2 a, b; g2_psi(a, p); pt_mul_zabs(b, p); pt_neg(b, b);
+    return pt_eq(a, b);
+}
+// P in G1  <=>  phi(P) == -[z^2]P, phi(x, y) = (beta x, y)
+HB_DEV bool g1_in_subgroup(const g1& p) {
+    if (pt_is_inf(p)) return true;
+    g1 a = p, b;
+    pt_mul_zabs(b, p); pt_mul_zabs(b, b); pt_neg(b, b);
+    fp beta; fp_set(beta, K_BETA); fp_mul(a.x, a.x, beta);
+    return pt_eq(a, b);
+}
+
+// ------------------------------------------------------------------ codecs (reference crypto/bls/bls.go:67-71,109-118)
+// bytes are little-endian; the 12 u32 words of a canonical coordinate ARE its 48 bytes on this little-endian target
+HB_DEV void load_words(uint32_t* w, const uint8_t* b, int n) {
+    for (int i = 0; i < n; i++) w[i] = (uint32_t)b[4 * i] | ((uint32_t)b[4 * i + 1] << 8) | ((uint32_t)b[4 * i + 2] << 16) | ((uint32_t)b[4 * i + 3] << 24);
+}
+HB_DEV void store_words(uint8_t* b, const uint32_t* w, int n) {
+    for (int i = 0; i < n; i++) { b[4 * i] = (uint8_t)w[i]; b[4 * i + 1] = (uint8_t)(w[i] >> 8); b[4 * i + 2] = (uint8_t)(w[i] >> 16); b[4 * i + 3] = (uint8_t)(w[i] >> 24); }
+}
+HB_DEV bool fp_is_odd(const fp& a) { fp v; fp_to_int(v, a); return v.l[0] & 1u; }
+
+HB_NOINLINE void g1_serialize(uint8_t* out, const g1& p) {
+    if (pt_is_inf(p)) { for (int i = 0; i < 48; i++) out[i] = 0; return; }
+    g1a a; pt_to_aff(a, p);
+    fp v; fp_to_int(v, a.x); store_words(out, v.l, 12);
+    if (fp_is_odd(a.y)) out[47] |= 0x80;
+}
+// returns false on: coordinate >= p, x not on curve, (check_order) not in the r-torsion
+HB_NOINLINE bool g1_deserialize(g1& r, const uint8_t* in, bool check_order) {
+    fp v; load_words(v.l, in, 12);
+    if (fp_is_zero(v)) { pt_set_inf(r); return true; }
+    bool odd = (v.l[11] >> 31) != 0; v.l[11] &= 0x7fffffffu;
+    if (fp_int_geq_p(v)) return false;
+    fp x, y, t, b;
+    fp_from_int(x, v);
+    fp_sqr(t, x); fp_mul(t, t, x); fp_set(b, K_B1); fp_add(t, t, b);
+    if (!fp_sqrt(y, t)) return false;
+    if (fp_is_odd(y) != odd) fp_neg(y, y);
+    r.x = x; r.y = y; fp_one(r.z);
+    if (check_order && !g1_in_subgroup(r)) return false;
+    return true;
+}
+HB_NOINLINE void g2_serialize(uint8_t* out, const g2& p) {
+    if (pt_is_inf(p)) { for (int i = 0; i < 96; i++) out[i] = 0; return; }
+    g2a a; pt_to_aff(a, p);
+    fp v; fp_to_int(v, a.x.a); store_words(out, v.l, 12);
+    fp_to_int(v, a.x.b); store_words(out + 48, v.l, 12);
+    if (fp_is_odd(a.y.a)) out[95] |= 0x80;
+}
+HB_NOINLINE bool g2_deserialize(g2& r, const uint8_t* in, bool check_order) {
+    fp va, vb; load_words(va.l, in, 12); load_words(vb.l, in + 48, 12);
+    if (fp_is_zero(va) && fp_is_zero(vb)) { pt_set_inf(r); return true; }
+    bool odd = (vb.l[11] >> 31) != 0; vb.l[11] &= 0x7fffffffu;
+    if (fp_int_geq_p(va) || fp_int_geq_p(vb)) return false;
+    fp2 x, y, t, b;
+    fp_from_int(x.a, va); fp_from_int(x.b, vb);
+    fp2_sqr(t, x); fp2_mul(t, t, x); fp2_const(b, K_B2); fp2_add(t, t, b);
+    if (!fp2_sqrt(y, t)) return false;
+    if (fp_is_odd(y.a) != odd) fp2_neg(y, y);
+    r.x = x; r.y = y; fp2_one(r.z);
+    if (check_order && !g2_in_subgroup(r)) return false;
+    return true;
+}
+
+// ------------------------------------------------------------------ message -> G2 (SignHash/VerifyHash of the reference)
+// mcl Fp::setArrayMask: first min(len, 48) bytes little-endian, masked to 381 bits, to 380 if still >= p
+HB_DEV void hash_to_fp(fp& t, const uint8_t* msg, uint32_t len) {
+    uint8_t b[48];
+    uint32_t n = len > 48 ? 48 : len;
+    for (uint32_t i = 0; i < 48; i++) b[i] = i < n ? msg[i] : 0;
+    fp v; load_words(v.l, b, 12);
+    v.l[11] &= 0x1fffffffu;
+    if (fp_int_geq_p(v)) v.l[11] &= 0x0fffffffu;
+    fp_from_int(t, v);
+}
+// mcl MapTo::calcBN over Fp2 (Shallue-van de Woestijne / Fouque-Tibouchi); false when the map is undefined (t = 0)
+HB_NOINLINE bool sw_map_g2(g2& r, const fp2& t) {
+    if (fp2_is_zero(t)) return false;
+    fp n, c1, c2, one; fp2 w, x, y, g, bb;
+    fp_set(c1, K_SW_C1); fp_set(c2, K_SW_C2); fp_one(one); fp2_const(bb, K_B2);
+    fp2_norm(n, t); bool negative = fp_legendre(n) < 0;
+    fp2_sqr(w, t); fp2_add(w, w, bb); fp_add(w.a, w.a, one);
+    if (fp2_is_zero(w)) return false;
+    fp2_inv(w, w); fp2_mul_fp(w, w, c1); fp2_mul(w, w, t);
+    for (int i = 0; i < 3; i++) {
+        if (i == 0) { fp2_mul(x, t, w); fp2_neg(x, x); fp_add(x.a, x.a, c2); }
+        else if (i == 1) { fp2_neg(x, x); fp_sub(x.a, x.a, one); }
+        else { fp2_sqr(x, w); fp2_inv(x, x); fp_add(x.a, x.a, one); }
+        fp2_sqr(g, x); fp2_mul(g, g, x); fp2_add(g, g, bb);
+        if (fp2_sqrt(y, g)) {
+            if (negative) fp2_neg(y, y);
+            r.x = x; r.y = y; fp2_one(r.z);
+            return true;
+        }
+    }
+    return false;
+}
+// Budroni-Pintore cofactor clearing: [z^2 - z - 1]P + psi([z - 1]P) + psi^2([2]P)   (plain h2 gives other bytes)
+HB_NOINLINE void g2_clear_cofactor(g2& r, const g2& p) {
+    g2 zp, z2p, t1, t2, t3, np;
+    pt_mul_zabs(zp, p); pt_neg(zp, zp);
+    pt_mul_zabs(z2p, zp); pt_neg(z2p, z2p);
+    pt_neg(np, p);
+    pt_add(t1, z2p, np); pt_neg(t2, zp); pt_add(t1, t1, t2);
+    pt_add(t2, zp, np); g2_psi(t2, t2);
+    pt_dbl(t3, p); g2_psi2(t3, t3);
+    pt_add(t1, t1, t2); pt_add(r, t1, t3);
+}
+HB_NOINLINE bool map_to_g2(g2& r, const uint8_t* msg, uint32_t len) {
+    fp2 t; hash_to_fp(t.a, msg, len); fp_zero(t.b);
+    g2 a; if (!sw_map_g2(a, t)) return false;
+    g2_clear_cofactor(r, a); return true;
+}
+
+}  // namespace hb

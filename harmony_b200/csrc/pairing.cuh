@@ -1,0 +1,76 @@
+// harmony_b200/csrc/pairing.cuh -- optimal-ate Miller loop and final exponentiation on BLS12-381.
+// Replaces the pairing inside Sign.VerifyHash (reference consensus/leader.go:173,287; internal/chain/engine.go:638;
+// consensus/validator.go:228).  The reference only exposes e(B, sig) == e(pk, H(m)) as a boolean, so the loop
+// shape (projective twist coordinates, lines scaled by subfield elements, exponent 3*(p^12-1)/r) is free.
+#pragma once
+#include "curve.cuh"
+
+namespace hb {
+
+struct g2proj { fp2 x, y, z; };    // homogeneous projective point on the twist
+
+// doubling step; line = l0 + (l2 * xP) w^2 + (l3 * yP) w^3 up to an Fp2 factor
+HB_NOINLINE void ml_dbl(g2proj& t, fp2& l0, fp2& l2, fp2& l3) {
+    fp2 A, B, C, E, F, H, s, b3; fp inv2;
+    fp_set(inv2, K_INV2); fp2_const(b3, K_B2_3);
+    fp2_mul(A, t.x, t.y); fp2_mul_fp(A, A, inv2);
+    fp2_sqr(B, t.y); fp2_sqr(C, t.z);
+    fp2_mul(E, b3, C);
+    fp2_dbl(F, E); fp2_add(F, F, E);
+    fp2_add(H, t.y, t.z); fp2_sqr(H, H); fp2_sub(H, H, B); fp2_sub(H, H, C);     // 2YZ
+    fp2_sub(l0, B, E);                                                            // Y^2 - 3b'Z^2
+    fp2_sqr(s, t.x); fp2_dbl(l2, s); fp2_add(l2, l2, s); fp2_neg(l2, l2);         // -3X^2
+    l3 = H;
+    fp2 x3, y3, e2;
+    fp2_sub(x3, B, F); fp2_mul(x3, x3, A);
+    fp2_add(y3, B, F); fp2_mul_fp(y3, y3, inv2); fp2_sqr(y3, y3);
+    fp2_sqr(e2, E); fp2_dbl(s, e2); fp2_add(s, s, e2); fp2_sub(y3, y3, s);
+    fp2_mul(t.z, B, H); t.x = x3; t.y = y3;
+}
+// addition step T += Q, Q affine
+HB_NOINLINE void ml_add(g2proj& t, const g2a& q, fp2& l0, fp2& l2, fp2& l3) {
+    fp2 th, mu, C, D, E, F, G, H, s;
+    fp2_mul(th, q.y, t.z); fp2_sub(th, t.y, th);
+    fp2_mul(mu, q.x, t.z); fp2_sub(mu, t.x, mu);
+    fp2_mul(l0, th, q.x); fp2_mul(s, mu, q.y); fp2_sub(l0, l0, s);
+    fp2_neg(l2, th); l3 = mu;
+    fp2_sqr(C, th); fp2_sqr(D, mu); fp2_mul(E, mu, D); fp2_mul(F, t.z, C); fp2_mul(G, t.x, D);
+    fp2_add(H, E, F); fp2_sub(H, H, G); fp2_sub(H, H, G);
+    fp2 x3, y3;
+    fp2_mul(x3, mu, H);
+    fp2_sub(y3, G, H); fp2_mul(y3, y3, th); fp2_mul(s, E, t.y); fp2_sub(y3, y3, s);
+    fp2_mul(t.z, t.z, E); t.x = x3; t.y = y3;
+}
+// f = f_{|z|,Q}(P) (conjugation for z < 0 omitted: f == 1 after final exp  <=>  conj(f) == 1 after final exp,
+// and a product of such values is conjugated as a whole).  Identity inputs give f = 1.
+HB_NOINLINE void miller_loop(fp12& f, const g1a& p, const g2a& q) {
+    fp12_one(f);
+    if (aff_is_inf(p) || aff_is_inf(q)) return;
+    g2proj T; T.x = q.x; T.y = q.y; fp2_one(T.z);
+    fp2 l0, l2, l3;
+    for (int i = 62; i >= 0; i--) {
+        fp12_sqr(f, f);
+        ml_dbl(T, l0, l2, l3);
+        fp2_mul_fp(l2, l2, p.x); fp2_mul_fp(l3, l3, p.y);
+        fp12_mul_by_014(f, f, l0, l2, l3);
+        if ((K_Z_ABS >> i) & 1) {
+            ml_add(T, q, l0, l2, l3);
+            fp2_mul_fp(l2, l2, p.x); fp2_mul_fp(l3, l3, p.y);
+            fp12_mul_by_014(f, f, l0, l2, l3);
+        }
+    }
+}
+// r = f^(3 (p^12 - 1) / r): easy part, then (z-1)^2 (z+p) (z^2+p^2-1) + 3
+HB_NOINLINE void final_exp(fp12& r, const fp12& f) {
+    fp12 t0, t1, t2, m;
+    fp12_conj(t0, f); fp12_inv(t1, f); fp12_mul(m, t0, t1);
+    fp12_frob2(t0, m); fp12_mul(m, t0, m);
+    fp12_cyc_exp_z(t0, m); fp12_conj(t1, m); fp12_mul(t0, t0, t1);               // a = m^(z-1)
+    fp12_cyc_exp_z(t1, t0); fp12_conj(t2, t0); fp12_mul(t1, t1, t2);             // b = a^(z-1)
+    fp12_cyc_exp_z(t0, t1); fp12_frob(t2, t1); fp12_mul(t0, t0, t2);             // c = b^(z+p)
+    fp12_cyc_exp_z(t1, t0); fp12_cyc_exp_z(t1, t1); fp12_frob2(t2, t0); fp12_mul(t1, t1, t2);
+    fp12_conj(t2, t0); fp12_mul(t1, t1, t2);                                     // d = c^(z^2+p^2-1)
+    fp12_cyc_sqr(t2, m); fp12_mul(t2, t2, m); fp12_mul(r, t1, t2);               // d * m^3
+}
+
+}  // namespace hb

@@ -1,0 +1,281 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes on libhbls.so), against the CPU oracle
+(oracle/hbls_oracle.c, pinned to the reference fixtures) and the committed golden vectors.  Bar: bit-exact bytes
+and identical booleans.  Restates the reference's functional pins:
+  consensus/quorum/quorom_test.go:73-125,381-552  crypto/bls/mask_test.go  consensus/construct_test.go:130-300
+"""
+import os, random
+import pytest
+from harmony_b200 import workload as wl
+
+pytestmark = pytest.mark.gpu
+
+P = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+
+def test_fp_mul_parity(gbls, oracle):
+    rng = random.Random(1)
+    edge = [0, 1, 2, P - 1, P - 2, (1 << 384) % P, (1 << 380), (1 << 381) - 1 - ((1 << 381) - 1 >= P) * P]
+    n = 20000
+    vals_a = [rng.randrange(P) for _ in range(n)] + [a for a in edge for _ in edge]
+    vals_b = [rng.randrange(P) for _ in range(n)] + [b for _ in edge for b in edge]
+    a = b"".join(v.to_bytes(48, "little") for v in vals_a); b = b"".join(v.to_bytes(48, "little") for v in vals_b)
+    out = gbls.FpMulBatch(a, b)
+    for i, (x, y) in enumerate(zip(vals_a, vals_b)):
+        assert int.from_bytes(out[48 * i:48 * i + 48], "little") == x * y % P, (i, hex(x), hex(y))
+    # and the C oracle agrees on a sample
+    for i in range(0, n, 997):
+        assert oracle.fp_mul(a[48 * i:48 * i + 48], b[48 * i:48 * i + 48]) == out[48 * i:48 * i + 48]
+
+def test_golden_sk_to_pk(gbls, fixtures):
+    sks = b"".join(bytes.fromhex(v["sk"]) for v in fixtures["sk_pk"])
+    pks = gbls.GetPublicKeyBatch(sks)
+    for i, v in enumerate(fixtures["sk_pk"]):
+        assert pks[48 * i:48 * i + 48].hex() == v["pk"], v["src"]
+    # single-op API
+    v = fixtures["sk_pk"][0]
+    sk = gbls.SecretKey(); sk.DeserializeHexStr(v["sk"])
+    assert sk.GetPublicKey().SerializeToHexStr() == v["pk"]
+    assert sk.SerializeToHexStr() == v["sk"]
+
+def test_golden_signature(gbls, fixtures):
+    sv = fixtures["sig_vectors"][0]
+    sk = gbls.SecretKey(); sk.DeserializeHexStr(sv["sk"])
+    msg = bytes.fromhex(sv["msg"])
+    sig = sk.SignHash(msg)
+    assert sig is not None and sig.SerializeToHexStr() == sv["sig"]
+    pk = gbls.PublicKey(); pk.DeserializeHexStr(sv["pk"])
+    s2 = gbls.Sign(); s2.DeserializeHexStr(sv["sig"])
+    assert s2.IsEqual(sig)
+    assert s2.VerifyHash(pk, msg)
+    assert not s2.VerifyHash(pk, bytes([msg[0] ^ 1]) + msg[1:])
+    # staking/types/validator.go:510-532 VerifyBLSKey composition through the batch entry
+    assert gbls.VerifyBatch(bytes.fromhex(sv["pk"]), bytes.fromhex(sv["sig"]), msg, 32) == b"\x01"
+
+def test_genesis_pubkeys_decode(gbls, oracle, fixtures):
+    pks = [bytes.fromhex(h) for h in fixtures["genesis_pubkeys_sample"][:64]]
+    c = gbls.Committee(pks)          # decodes + subgroup-checks all of them on the GPU
+    assert len(c) == len(pks)
+    for p in pks[:8]:
+        assert oracle.pk_check(p)
+    bm = bytes([0xff] * ((len(pks) + 7) // 8 - 1) + [(1 << ((len(pks) - 1) % 8 + 1)) - 1])
+    assert c.MaskAggregate(bm) == oracle.mask_aggregate(pks, bm)
+
+def test_map_to_g2_parity(gbls, oracle):
+    rng = random.Random(7)
+    msgs = [b"\x01", bytes(8), rng.randbytes(32), rng.randbytes(48), rng.randbytes(64), b"\xff" * 48, bytes(31) + b"\x01"]
+    msgs += [rng.randbytes(rng.choice([1, 8, 32, 40, 48])) for _ in range(24)]
+    for m in msgs:
+        assert gbls.MapToG2(m) == oracle.map_to_g2(m), m.hex()
+    assert gbls.MapToG2(bytes(32)) is None and oracle.map_to_g2(bytes(32)) is None     # t = 0: map undefined
+    assert gbls.MapToG2(b"") is None
+
+def test_sign_batch_parity(gbls, oracle):
+    n = 40
+    sks = [wl.sk_bytes(wl.seeded_sk("t-sign", i)) for i in range(n)]
+    msgs = [wl.seeded_bytes("t-sign/m", i, 32) for i in range(n)]
+    sigs, ok = gbls.SignHashBatch(b"".join(sks), b"".join(msgs), 32)
+    assert ok == b"\x01" * n
+    pks = gbls.GetPublicKeyBatch(b"".join(sks))
+    for i in range(n):
+        assert sigs[96 * i:96 * i + 96] == oracle.sign_hash(sks[i], msgs[i])
+        assert pks[48 * i:48 * i + 48] == oracle.get_public_key(sks[i])
+
+def _committee(tag, n):
+    sks = [wl.seeded_sk(tag, i) for i in range(n)]
+    return sks
+
+def test_config1_four_keys(gbls, oracle):
+    """BASELINE configs[0]: 4 keys sign one 32-byte msg, AggregateSig + Verify; bit-exact vs the oracle."""
+    sks = _committee("c1", 4)
+    msg = wl.seeded_bytes("c1/msg", 0, 32)
+    sko = [gbls.SecretKey() for _ in sks]
+    for s, k in zip(sko, sks): s.Deserialize(wl.sk_bytes(k))
+    pubs = [s.GetPublicKey() for s in sko]
+    sigs = [s.SignHash(msg) for s in sko]
+    for k, p, s in zip(sks, pubs, sigs):
+        assert p.Serialize() == oracle.get_public_key(wl.sk_bytes(k))
+        assert s.Serialize() == oracle.sign_hash(wl.sk_bytes(k), msg)
+    agg = gbls.AggregateSig(sigs)
+    o_agg = oracle.aggregate_sigs([s.Serialize() for s in sigs])
+    assert agg.Serialize() == o_agg
+    assert gbls.AggregateSigBytes([s.Serialize() for s in sigs]) == o_agg
+    wrappers = [gbls.PublicKeyWrapper(p.Serialize(), p) for p in pubs]
+    mask = gbls.NewMask(wrappers)
+    mask.SetMask(b"\x0f")
+    o_apk = oracle.mask_aggregate([w.Bytes for w in wrappers], b"\x0f")
+    assert mask.AggregatePublic.Serialize() == o_apk
+    assert agg.VerifyHash(mask.AggregatePublic, msg)
+    bad = bytes([msg[0] ^ 1]) + msg[1:]
+    assert not agg.VerifyHash(mask.AggregatePublic, bad)
+    # Sub on 1 -> 0 (mask.go:128-131)
+    mask.SetMask(b"\x07")
+    assert mask.AggregatePublic.Serialize() == oracle.mask_aggregate([w.Bytes for w in wrappers], b"\x07")
+    assert not agg.VerifyHash(mask.AggregatePublic, msg)
+    # FastAggregateVerify wrapper == SetMask + VerifyHash
+    com = gbls.Committee([w.Bytes for w in wrappers])
+    assert gbls.FastAggregateVerify(com, b"\x0f", agg.Serialize(), msg)
+    assert not gbls.FastAggregateVerify(com, b"\x07", agg.Serialize(), msg)
+    assert oracle.fast_aggregate_verify([w.Bytes for w in wrappers], b"\x0f", o_agg, msg) == 1
+    with pytest.raises(ValueError):
+        com.AggregateVerify(b"\x0f\x00", agg.Serialize(), msg)
+
+def test_invalid_aggregate_sig_duplicate_signer(gbls):
+    """consensus/quorum/quorom_test.go:503-552: an aggregate containing one signer twice fails against the
+    de-duplicated key set; the correct set verifies."""
+    sks = _committee("dup", 4)
+    msg = wl.seeded_bytes("dup/msg", 0, 32)
+    sko = []
+    for k in sks:
+        s = gbls.SecretKey(); s.Deserialize(wl.sk_bytes(k)); sko.append(s)
+    pubs = [s.GetPublicKey() for s in sko]
+    sigs = [s.SignHash(msg) for s in sko]
+    agg_dup = gbls.AggregateSig([sigs[0], sigs[1], sigs[1]])
+    agg_ok = gbls.AggregateSig([sigs[0], sigs[1]])
+    apk = gbls.PublicKey(); apk.Add(pubs[0]); apk.Add(pubs[1])
+    assert not agg_dup.VerifyHash(apk, msg)
+    assert agg_ok.VerifyHash(apk, msg)
+
+def test_config2_250_committee_rounds(gbls, oracle):
+    """BASELINE configs[1] at test size: 250-validator committee, rounds with k in {167, 200, 250} signers,
+    48-byte commit payloads; booleans vs the oracle incl. corrupted rounds."""
+    n = 250
+    sks = _committee("c2", n)
+    pks_blob = gbls.GetPublicKeyBatch(b"".join(wl.sk_bytes(k) for k in sks))
+    pks = [pks_blob[48 * i:48 * i + 48] for i in range(n)]
+    for i in (0, 17, 249):
+        assert pks[i] == oracle.get_public_key(wl.sk_bytes(sks[i]))
+    com = gbls.Committee(pks)
+    och = oracle.committee(pks)
+    ks = [167, 200, 250, 167, 200, 250, 1, 249]
+    B = len(ks)
+    bitmaps = [wl.bitmap_with_k("c2", j, n, ks[j]) for j in range(B)]
+    msgs = [wl.commit_payload("c2", j) for j in range(B)]
+    agg_sks = [wl.sk_bytes(wl.round_signer_sum(sks, bitmaps[j])) for j in range(B)]
+    sigs_blob, ok = gbls.SignHashBatch(b"".join(agg_sks), b"".join(msgs), 48)
+    assert ok == b"\x01" * B
+    sigs = [sigs_blob[96 * j:96 * j + 96] for j in range(B)]
+    assert sigs[0] == oracle.sign_hash(agg_sks[0], msgs[0])
+    # mask aggregation bytes
+    for j in (0, 2, 6):
+        assert com.MaskAggregate(bitmaps[j]) == oracle.committee_mask_aggregate(och, bitmaps[j])
+    # corrupt: round 3 wrong message, round 4 bitmap with one extra/missing signer, round 5 signature of another round
+    msgs_t = list(msgs); bms_t = list(bitmaps); sigs_t = list(sigs)
+    msgs_t[3] = bytes([msgs[3][9] ^ 0x40]).join([msgs[3][:9], msgs[3][10:]])
+    b4 = bytearray(bitmaps[4]); b4[0] ^= 1; bms_t[4] = bytes(b4)
+    sigs_t[5] = sigs[2]
+    res = com.AggregateVerifyBatch(b"".join(bms_t), b"".join(sigs_t), b"".join(msgs_t), 48)
+    exp = bytes(1 if oracle.committee_aggregate_verify(och, bms_t[j], sigs_t[j], msgs_t[j]) == 1 else 0 for j in range(B))
+    assert res == exp
+    assert list(res) == [1, 1, 1, 0, 0, 0, 1, 1]
+    # single-round entry
+    assert com.AggregateVerify(bitmaps[0], sigs[0], msgs[0]) is True
+    assert com.AggregateVerify(bitmaps[0], sigs[1], msgs[0]) is False
+
+def test_individual_sigs_aggregate_250(gbls, oracle):
+    """R5: aggregate 250 individually produced signatures on one message; bytes equal oracle and equal the
+    signature made with the summed key."""
+    n = 250
+    sks = _committee("c2", n)
+    msg = wl.commit_payload("agg", 0)
+    sigs_blob, ok = gbls.SignHashBatch(b"".join(wl.sk_bytes(k) for k in sks), msg * n, 48)
+    assert ok == b"\x01" * n
+    sigs = [sigs_blob[96 * i:96 * i + 96] for i in range(n)]
+    agg = gbls.AggregateSigBytes(sigs)
+    assert agg == oracle.aggregate_sigs(sigs)
+    assert agg == oracle.sign_hash(wl.sk_bytes(sum(sks) % wl.R_ORDER), msg)
+    assert gbls.AggregateSigBytes([]) == bytes(96)
+
+def test_verify_batch_triples(gbls, oracle):
+    """BASELINE configs[3] at test size: independent (pk, msg, sig) triples with invalid items at seeded positions."""
+    k = 96
+    sks = [wl.sk_bytes(wl.seeded_sk("c4", i)) for i in range(k)]
+    msgs = [wl.seeded_bytes("c4/m", i, 32) for i in range(k)]
+    pks = gbls.GetPublicKeyBatch(b"".join(sks))
+    sigs_blob, _ = gbls.SignHashBatch(b"".join(sks), b"".join(msgs), 32)
+    sigs = [bytearray(sigs_blob[96 * i:96 * i + 96]) for i in range(k)]
+    msgs_t = [bytearray(m) for m in msgs]
+    bad = {5: "msg", 17: "sigswap", 40: "sigbyte", 41: "sigbyte", 77: "pkswap"}
+    pk_list = [bytearray(pks[48 * i:48 * i + 48]) for i in range(k)]
+    for i, kind in bad.items():
+        if kind == "msg": msgs_t[i][3] ^= 0x10
+        elif kind == "sigswap": sigs[i] = bytearray(sigs_blob[96 * 18:96 * 19])
+        elif kind == "sigbyte": sigs[i][10] ^= 0x01
+        elif kind == "pkswap": pk_list[i] = bytearray(pks[48 * 78:48 * 79])
+    res = gbls.VerifyBatch(b"".join(bytes(p) for p in pk_list), b"".join(bytes(s) for s in sigs), b"".join(bytes(m) for m in msgs_t), 32)
+    exp = bytes(1 if oracle.verify_hash(bytes(sigs[i]), bytes(pk_list[i]), bytes(msgs_t[i])) else 0 for i in range(k))
+    assert res == exp
+    assert all(res[i] == 0 for i in bad) and sum(res) == k - len(bad)
+
+def test_deserialize_rejects(gbls, oracle):
+    """Deserialize error behaviour: x >= p, x not on curve, point outside the r-torsion."""
+    pk = gbls.PublicKey()
+    with pytest.raises(ValueError): pk.Deserialize(b"\xff" * 48)
+    with pytest.raises(ValueError): pk.Deserialize(b"\x00" * 47)
+    rng = random.Random(3)
+    n_bad = 0
+    for _ in range(12):
+        b = bytearray(rng.randbytes(48)); b[47] &= 0x99
+        exp = oracle.pk_check(bytes(b))
+        try: pk.Deserialize(bytes(b)); got = True
+        except ValueError: got = False
+        assert got == exp; n_bad += (not exp)
+    assert n_bad > 0
+    sg = gbls.Sign()
+    for _ in range(8):
+        b = bytearray(rng.randbytes(96)); b[95] &= 0x99; b[47] &= 0x19
+        exp = oracle.sig_check(bytes(b))
+        try: sg.Deserialize(bytes(b)); got = True
+        except ValueError: got = False
+        assert got == exp
+    # identity encodings round-trip
+    pk.Deserialize(bytes(48)); assert pk.Serialize() == bytes(48)
+    sg.Deserialize(bytes(96)); assert sg.Serialize() == bytes(96)
+
+def test_mask_semantics(gbls):
+    """crypto/bls/mask_test.go: bitmap length errors, SetBit/SetKey/SetKeysAtomic, CountEnabled, policies."""
+    sks = _committee("mask", 9)
+    wr = []
+    for k in sks:
+        s = gbls.SecretKey(); s.Deserialize(wl.sk_bytes(k)); wr.append(gbls.WrapperFromPrivateKey(s).Pub)
+    m = gbls.NewMask(wr)
+    assert m.Len() == 2 and m.CountTotal() == 9 and m.CountEnabled() == 0
+    with pytest.raises(ValueError): m.SetMask(b"\x01")
+    m.SetBit(0, True); m.SetKey(wr[8].Bytes, True)
+    assert m.Mask() == b"\x01\x01" and m.CountEnabled() == 2
+    exp = gbls.PublicKey(); exp.Add(wr[0].Object); exp.Add(wr[8].Object)
+    assert m.AggregatePublic.IsEqual(exp)
+    with pytest.raises(IndexError): m.SetBit(9, True)
+    with pytest.raises(KeyError): m.SetKey(b"\x00" * 48, True)
+    m.SetKeysAtomic([wr[1], wr[2]], True)
+    assert m.IndexEnabled(1) and m.KeyEnabled(wr[2].Bytes) and not m.IndexEnabled(3)
+    m.SetBit(0, False); m.SetBit(8, False); m.SetKeysAtomic([wr[1], wr[2]], False)
+    assert m.AggregatePublic.Serialize() == bytes(48) and m.CountEnabled() == 0
+    assert gbls.NewThresholdPolicy(1).Check(m) is False and gbls.CompletePolicy().Check(m) is False
+    m.SetMask(b"\xff\x01"); assert gbls.CompletePolicy().Check(m)
+    assert gbls.AggregateMasks(b"\x01\x02", b"\x10\x02") == b"\x11\x02"
+
+def test_string_sign_verify_roundtrip(gbls):
+    """Sign(string)/Verify(string): bytes unpinned by the reference (A.7); self-consistent round trip as its tests use it."""
+    s = gbls.RandPrivateKey(); p = s.GetPublicKey()
+    sig = s.Sign("test message")
+    assert sig.Verify(p, "test message") and not sig.Verify(p, "test messagf")
+
+def test_large_batch_properties(gbls):
+    """Full-size property check (BASELINE size B=2048 rounds of a 250 committee): all-valid batch verifies, and
+    flipping seeded rounds flips exactly those results."""
+    n, B = 250, 2048
+    sks = _committee("c2", n)
+    pks_blob = gbls.GetPublicKeyBatch(b"".join(wl.sk_bytes(k) for k in sks))
+    com = gbls.Committee([pks_blob[48 * i:48 * i + 48] for i in range(n)])
+    # 16 distinct bitmaps/keys reused across rounds keeps host-side generation cheap
+    bms = [wl.bitmap_with_k("prop", j, n, [167, 200, 250][j % 3]) for j in range(16)]
+    agg = [wl.sk_bytes(wl.round_signer_sum(sks, bm)) for bm in bms]
+    msgs = [wl.commit_payload("prop", j) for j in range(B)]
+    sigs, ok = gbls.SignHashBatch(b"".join(agg[j % 16] for j in range(B)), b"".join(msgs), 48)
+    assert ok == b"\x01" * B
+    bitmaps = b"".join(bms[j % 16] for j in range(B))
+    res = com.AggregateVerifyBatch(bitmaps, sigs, b"".join(msgs), 48)
+    assert res == b"\x01" * B
+    rng = random.Random(11); flip = set(rng.sample(range(B), 20))
+    msgs2 = [bytes([m[8] ^ 1]).join([m[:8], m[9:]]) if j in flip else m for j, m in enumerate(msgs)]
+    res2 = com.AggregateVerifyBatch(bitmaps, sigs, b"".join(msgs2), 48)
+    assert all((res2[j] == 0) == (j in flip) for j in range(B))
