@@ -83,6 +83,8 @@ def lib():
         sig("hbls_fp_mul_batch", c.c_int, sz, vp, vp, vp)
         sig("hbls_kernel_launch_count", c.c_uint64)
         sig("hbls_probe_mac32_per_s", c.c_double, c.c_int)
+        sig("hbls_stage_timing_enable", None, c.c_int)
+        sig("hbls_stage_timing_get", c.c_int, c.POINTER(c.c_float), c.c_int)
         _lib = L
     return _lib
 
@@ -359,3 +361,10 @@ def ConstructCommitPayload(is_staking: bool, block_hash: bytes, block_num: int, 
 
 def KernelLaunchCount() -> int: return int(lib().hbls_kernel_launch_count())
 def ProbeMac32PerS(iters: int = 4096) -> float: return float(_need().hbls_probe_mac32_per_s(iters))
+
+STAGE_NAMES = ["k_mask_aggregate", "k_g1_normalize", "k_g2_decode", "k_hash_to_g2", "k_miller_verify", "k_final_verify"]
+def StageTimingEnable(on: bool): lib().hbls_stage_timing_enable(1 if on else 0)
+def StageTimingGet():
+    buf = (ctypes.c_float * 8)()
+    n = lib().hbls_stage_timing_get(buf, 8)
+    return [float(buf[i]) for i in range(n)]

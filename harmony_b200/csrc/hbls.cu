@@ -24,6 +24,8 @@ struct Ctx {
     uint8_t* scratch = nullptr; size_t scratch_cap = 0;     // device bump arena
     uint8_t* pinned = nullptr; size_t pinned_cap = 0;       // host staging (pinned)
     std::atomic<uint64_t> launches{0};
+    bool stage_timing = false; bool stage_valid = false;
+    cudaEvent_t ev[8] = {};
 };
 Ctx g;
 
@@ -79,12 +81,18 @@ VerifyBufs carve_verify(Arena& ar, size_t B) {
     v.f = ar.take<fp12>(2 * B); v.ok_sig = ar.take<uint8_t>(B); v.ok_hm = ar.take<uint8_t>(B); v.ok_pk = ar.take<uint8_t>(B);
     return v;
 }
+#define STAGE_EV(i, strm) do { if (g.stage_timing) cudaEventRecord(g.ev[i], (strm)); } while (0)
 void launch_verify_tail(size_t B, const VerifyBufs& v, const uint8_t* d_sig96, const uint8_t* d_msgs, uint32_t msg_len,
                         const uint8_t* ok_pk, uint8_t* d_results, cudaStream_t s) {
+    STAGE_EV(2, s);
     LAUNCH(k_g2_decode, blocks_for(B, TPB), TPB, s, B, d_sig96, v.sig, v.ok_sig, 1);
+    STAGE_EV(3, s);
     LAUNCH(k_hash_to_g2, blocks_for(B, TPB), TPB, s, B, d_msgs, msg_len, v.hm, v.ok_hm);
+    STAGE_EV(4, s);
     LAUNCH(k_miller_verify, blocks_for(2 * B, TPB), TPB, s, B, v.sig, v.pkneg, v.hm, v.f);
+    STAGE_EV(5, s);
     LAUNCH(k_final_verify, blocks_for(B, TPB), TPB, s, B, v.f, v.ok_sig, v.ok_hm, ok_pk, d_results);
+    STAGE_EV(6, s);
 }
 
 int single_op(int op, const void* a, size_t an, const void* b, size_t bn, void* out, size_t on, int* rc_out, uint32_t len = 0) {
@@ -354,9 +362,12 @@ int hbls_aggregate_sigs(const uint8_t* sig96, size_t n, uint8_t out96[96]) {
 static int agg_verify_device_locked(const hbls_committee* c, size_t B, const uint8_t* d_bitmaps, size_t blen, const uint8_t* d_sigs,
                                     const uint8_t* d_msgs, size_t msg_len, uint8_t* d_results, cudaStream_t s, Arena& ar) {
     VerifyBufs v = carve_verify(ar, B);
+    STAGE_EV(0, s);
     LAUNCH(k_mask_aggregate, blocks_for(B * 32, 128), 128, s, B, c->n, c->table, d_bitmaps, blen, v.apk);
+    STAGE_EV(1, s);
     LAUNCH(k_g1_normalize, blocks_for(B, TPB), TPB, s, B, v.apk, v.pkneg, 1);
     launch_verify_tail(B, v, d_sigs, d_msgs, (uint32_t)msg_len, nullptr, d_results, s);
+    if (g.stage_timing) g.stage_valid = true;
     return 0;
 }
 int hbls_aggregate_verify_batch_device(const hbls_committee* c, size_t B, const void* d_bitmaps, size_t blen, const void* d_sigs96,
@@ -467,6 +478,19 @@ int hbls_fp_mul_batch(size_t n, const uint8_t* a48, const uint8_t* b48, uint8_t*
     return 0;
 }
 
+void hbls_stage_timing_enable(int on) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (on && !g.ev[0]) for (int i = 0; i < 8; i++) cudaEventCreate(&g.ev[i]);
+    g.stage_timing = on != 0; g.stage_valid = false;
+}
+int hbls_stage_timing_get(float* ms_out, int max_stages) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (!g.stage_valid) return 0;
+    if (cudaEventSynchronize(g.ev[6]) != cudaSuccess) return 0;
+    int n = max_stages < 6 ? max_stages : 6;
+    for (int i = 0; i < n; i++) { float ms = 0; cudaEventElapsedTime(&ms, g.ev[i], g.ev[i + 1]); ms_out[i] = ms; }
+    return n;
+}
 double hbls_probe_mac32_per_s(int iters) {
     if (ensure_init()) return -1.0;
     std::lock_guard<std::mutex> lk(g.mu);

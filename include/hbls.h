@@ -118,6 +118,12 @@ int hbls_map_to_g2(const void* msg, size_t msg_len, uint8_t out96[96]);
 int hbls_fp_mul_batch(size_t n, const uint8_t* a48, const uint8_t* b48, uint8_t* out48);
 /* number of kernels this library has launched so far */
 uint64_t hbls_kernel_launch_count(void);
+/* per-kernel device timing of the aggregate-verify pipeline (CUDA events on the launching stream).
+ * enable(1) makes every following hbls_aggregate_verify_batch[_device] call record events between its kernels;
+ * get() waits for the last recorded pipeline and returns the number of stages written to ms_out, in launch order:
+ * 0 k_mask_aggregate, 1 k_g1_normalize, 2 k_g2_decode, 3 k_hash_to_g2, 4 k_miller_verify, 5 k_final_verify */
+void hbls_stage_timing_enable(int on);
+int hbls_stage_timing_get(float* ms_out, int max_stages);
 /* integer-pipe probe: runs `iters` dependent-free IMAD.WIDE.U32 MACs per thread on the whole chip and returns
  * the achieved MAC32/s (roofline denominator measured on this box), <0 on error */
 double hbls_probe_mac32_per_s(int iters);

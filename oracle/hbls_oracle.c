@@ -655,3 +655,28 @@ API int ho_pairing_check(size_t n, const u8 *g1s48, const u8 *g2s96) {
 /* [k]P on serialized points (parity probes for the CUDA scalar-mul kernels) */
 API int ho_g1_mul(const u8 p48[48], const u8 k32[32], u8 out[48]) { g1 p; u64 k[4]; memcpy(k, k32, 32); if (!g1_deserialize(&p, p48, 0)) return -1; g1_mul(&p, &p, k, 4); g1_serialize(out, &p); return 0; }
 API int ho_g2_mul(const u8 p96[96], const u8 k32[32], u8 out[96]) { g2 p; u64 k[4]; memcpy(k, k32, 32); if (!g2_deserialize(&p, p96, 0)) return -1; g2_mul(&p, &p, k, 4); g2_serialize(out, &p); return 0; }
+
+/* per-stage Fp mul/sqr counts of one aggregate verification, staged exactly like the CUDA pipeline
+ * (bench.py roofline: algorithmic MAC32 of each kernel).  out[2*s], out[2*s+1] = (mul, sqr) of stage s:
+ * 0 mask aggregate, 1 apk -> affine, 2 signature decode (+ subgroup check), 3 hash-to-G2 (+ affine),
+ * 4 two Miller loops, 5 f1*f2 + final exponentiation.  Returns the verify boolean. */
+API int ho_profile_aggregate_verify(void *h, const u8 *bitmap, size_t blen, const u8 sig96[96], const u8 *msg, size_t len, u64 out[12]) {
+    u64 m0, s0;
+#define HO_STAGE(i) do { out[2 * (i)] = g_cnt_mul - m0; out[2 * (i) + 1] = g_cnt_sqr - s0; m0 = g_cnt_mul; s0 = g_cnt_sqr; } while (0)
+    m0 = g_cnt_mul; s0 = g_cnt_sqr;
+    g1 acc; if (committee_mask((ho_committee *)h, bitmap, blen, &acc)) return -1;
+    HO_STAGE(0);
+    g1 ps[2]; g2 qs[2];
+    g1_generator(&ps[0]); g1_normalize(&ps[1], &acc); g1_neg(&ps[1], &ps[1]);
+    HO_STAGE(1);
+    int ok = g2_deserialize(&qs[0], sig96, 1);
+    HO_STAGE(2);
+    g2 hm; int okh = map_to_g2(&hm, msg, len); if (okh) g2_normalize(&qs[1], &hm);
+    HO_STAGE(3);
+    if (!ok || !okh || g2_is_inf(&qs[0]) || g1_is_inf(&acc)) { for (int i = 8; i < 12; i++) out[i] = 0; return 0; }
+    fp12 f; miller_loop(&f, 2, ps, qs);
+    HO_STAGE(4);
+    final_exp(&f, &f);
+    HO_STAGE(5);
+    return fp12_is_one(&f);
+}
