@@ -14,7 +14,7 @@ import ctypes, os
 from collections import OrderedDict
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "lib", "libhbls.so")
+_LIB_PATH = os.environ.get("HBLS_LIB") or os.path.join(_HERE, "lib", "libhbls.so")
 
 BLS12_381 = 5
 _COMPILED_TIME_VAR = 46

@@ -1,7 +1,7 @@
 """harmony_b200/build.py -- in-tree builds (no JIT cache): the CUDA product library and the CPU oracle.
 
     libhbls.so          nvcc -gencode arch=compute_100a,code=sm_100a   (product; harmony_b200/lib/)
-    libhbls_host.so     g++  (C++ host mirror of crypto/bls, multibls, quorum helpers; links libhbls.so)
+    hbls_host_test      g++  (C++ host mirror hbls_host.hpp + restated reference tests; links libhbls.so)
     libhbls_oracle.so   gcc  (oracle/: TEST INFRASTRUCTURE, never loaded by the product path)
 """
 import os, subprocess, sys
@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "harmony_b200", "csrc")
 LIBDIR = os.path.join(ROOT, "harmony_b200", "lib")
 LIB = os.path.join(LIBDIR, "libhbls.so")
-HOSTLIB = os.path.join(LIBDIR, "libhbls_host.so")
+HOSTTEST = os.path.join(LIBDIR, "hbls_host_test")
 ORACLE_LIB = os.path.join(ROOT, "oracle", "libhbls_oracle.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -39,17 +39,15 @@ def build_cuda(force=False, verbose=False):
     return LIB
 
 def build_host(force=False):
-    src = os.path.join(ROOT, "harmony_b200", "host", "hbls_host.cpp")
-    if not os.path.exists(src):
-        return None
-    srcs = _sources(os.path.join(ROOT, "harmony_b200", "host"), (".cpp", ".hpp")) + [os.path.join(ROOT, "include", "hbls.h"),
-                                                                                     os.path.join(ROOT, "include", "hbls_host.h")]
-    if not force and _newer(HOSTLIB, srcs) and os.path.getmtime(HOSTLIB) >= os.path.getmtime(LIB):
-        return HOSTLIB
-    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wall", "-o", HOSTLIB, src,
-           "-L" + LIBDIR, "-lhbls", "-Wl,-rpath,$ORIGIN"]
+    """C++ host mirror (header-only hbls_host.hpp) + its test driver, linked against libhbls.so."""
+    hd = os.path.join(ROOT, "harmony_b200", "host")
+    src = os.path.join(hd, "hbls_host_test.cpp")
+    srcs = [src, os.path.join(hd, "hbls_host.hpp"), os.path.join(ROOT, "include", "hbls.h")]
+    if not force and _newer(HOSTTEST, srcs) and os.path.getmtime(HOSTTEST) >= os.path.getmtime(LIB):
+        return HOSTTEST
+    cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-o", HOSTTEST, src, "-L" + LIBDIR, "-lhbls", "-Wl,-rpath,$ORIGIN", "-pthread", "-ldl", "-lrt"]
     subprocess.check_call(cmd)
-    return HOSTLIB
+    return HOSTTEST
 
 def build_oracle(force=False):
     od = os.path.join(ROOT, "oracle")

@@ -164,13 +164,13 @@ HB_DEV void g2_psi2(g2& r, const g2& p) {
     fp2_mul_fp(r.x, p.x, c); fp2_neg(r.y, p.y); r.z = p.z;
 }
 // Q in G2  <=>  psi(Q) == [z]Q   (same boolean as [r]Q == O)
-HB_DEV bool g2_in_subgroup(const g2& p) {
+HB_NOINLINE bool g2_in_subgroup(const g2& p) {
     if (pt_is_inf(p)) return true;
     g2 a, b; g2_psi(a, p); pt_mul_zabs(b, p); pt_neg(b, b);
     return pt_eq(a, b);
 }
 // P in G1  <=>  phi(P) == -[z^2]P, phi(x, y) = (beta x, y)
-HB_DEV bool g1_in_subgroup(const g1& p) {
+HB_NOINLINE bool g1_in_subgroup(const g1& p) {
     if (pt_is_inf(p)) return true;
     g1 a = p, b;
     pt_mul_zabs(b, p); pt_mul_zabs(b, b); pt_neg(b, b);
@@ -205,8 +205,9 @@ HB_NOINLINE bool g1_deserialize(g1& r, const uint8_t* in, bool check_order) {
     fp_sqr(t, x); fp_mul(t, t, x); fp_set(b, K_B1); fp_add(t, t, b);
     if (!fp_sqrt(y, t)) return false;
     if (fp_is_odd(y) != odd) fp_neg(y, y);
-    r.x = x; r.y = y; fp_one(r.z);
-    if (check_order && !g1_in_subgroup(r)) return false;
+    g1 q; q.x = x; q.y = y; fp_one(q.z);
+    if (check_order && !g1_in_subgroup(q)) return false;
+    r = q;
     return true;
 }
 HB_NOINLINE void g2_serialize(uint8_t* out, const g2& p) {
@@ -226,8 +227,9 @@ HB_NOINLINE bool g2_deserialize(g2& r, const uint8_t* in, bool check_order) {
     fp2_sqr(t, x); fp2_mul(t, t, x); fp2_const(b, K_B2); fp2_add(t, t, b);
     if (!fp2_sqrt(y, t)) return false;
     if (fp_is_odd(y.a) != odd) fp2_neg(y, y);
-    r.x = x; r.y = y; fp2_one(r.z);
-    if (check_order && !g2_in_subgroup(r)) return false;
+    g2 q; q.x = x; q.y = y; fp2_one(q.z);
+    if (check_order && !g2_in_subgroup(q)) return false;
+    r = q;
     return true;
 }
 

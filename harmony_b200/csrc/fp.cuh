@@ -11,8 +11,34 @@
 #pragma once
 #include <stdint.h>
 
+// HB_HOST_EMU: tests/emu compiles these headers with g++ and software carry flags so that the device LOGIC can be
+// checked against the oracle on the CPU-only build box (test harness only -- never part of libhbls.so).
+#ifdef HB_HOST_EMU
+#define __device__
+#define __forceinline__ inline
+#define __noinline__
+#define __constant__
+#endif
+
 #define HB_DEV __device__ __forceinline__
 #define HB_NOINLINE __device__ __noinline__
+// code-size knobs (the pairing kernels are instruction-fetch sensitive): outline the cheap field ops
+#ifndef HB_OUTLINE_FP
+#define HB_OUTLINE_FP 0
+#endif
+#ifndef HB_OUTLINE_FP2
+#define HB_OUTLINE_FP2 1
+#endif
+#if HB_OUTLINE_FP
+#define HB_FPFN __device__ __noinline__
+#else
+#define HB_FPFN __device__ __forceinline__
+#endif
+#if HB_OUTLINE_FP2
+#define HB_FP2FN __device__ __noinline__
+#else
+#define HB_FP2FN __device__ __forceinline__
+#endif
 
 namespace hb {
 
@@ -41,6 +67,20 @@ HB_DEV uint32_t p_limb(int i) {
     }
 }
 
+#ifdef HB_HOST_EMU
+static thread_local uint32_t hb_cf = 0;
+inline void hb_acc3(uint32_t& d, uint64_t x, uint64_t y, uint64_t z) { uint64_t t = x + y + z; d = (uint32_t)t; hb_cf = (uint32_t)(t >> 32); }
+inline void mad_lo_cc(uint32_t& d, uint32_t a, uint32_t b, uint32_t c)  { hb_acc3(d, (uint32_t)((uint64_t)a * b), c, 0); }
+inline void madc_lo_cc(uint32_t& d, uint32_t a, uint32_t b, uint32_t c) { hb_acc3(d, (uint32_t)((uint64_t)a * b), c, hb_cf); }
+inline void madc_hi_cc(uint32_t& d, uint32_t a, uint32_t b, uint32_t c) { hb_acc3(d, (uint32_t)(((uint64_t)a * b) >> 32), c, hb_cf); }
+inline void add_cc(uint32_t& d, uint32_t a, uint32_t b)  { hb_acc3(d, a, b, 0); }
+inline void addc_cc(uint32_t& d, uint32_t a, uint32_t b) { hb_acc3(d, a, b, hb_cf); }
+inline void addc(uint32_t& d, uint32_t a, uint32_t b)    { d = a + b + hb_cf; }
+inline void hb_sub3(uint32_t& d, uint32_t a, uint32_t b, uint32_t bin) { uint64_t t = (uint64_t)a - b - bin; d = (uint32_t)t; hb_cf = (uint32_t)(t >> 63); }
+inline void sub_cc(uint32_t& d, uint32_t a, uint32_t b)  { hb_sub3(d, a, b, 0); }
+inline void subc_cc(uint32_t& d, uint32_t a, uint32_t b) { hb_sub3(d, a, b, hb_cf); }
+inline void subc(uint32_t& d, uint32_t a, uint32_t b)    { d = a - b - hb_cf; }
+#else
 // ---- single-instruction PTX wrappers; CC.CF flows between consecutive volatile asm statements
 HB_DEV void mad_lo_cc(uint32_t& d, uint32_t a, uint32_t b, uint32_t c)  { asm volatile("mad.lo.cc.u32 %0, %1, %2, %3;"  : "=r"(d) : "r"(a), "r"(b), "r"(c)); }
 HB_DEV void madc_lo_cc(uint32_t& d, uint32_t a, uint32_t b, uint32_t c) { asm volatile("madc.lo.cc.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); }
@@ -51,6 +91,8 @@ HB_DEV void addc(uint32_t& d, uint32_t a, uint32_t b)    { asm volatile("addc.u3
 HB_DEV void sub_cc(uint32_t& d, uint32_t a, uint32_t b)  { asm volatile("sub.cc.u32 %0, %1, %2;"  : "=r"(d) : "r"(a), "r"(b)); }
 HB_DEV void subc_cc(uint32_t& d, uint32_t a, uint32_t b) { asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); }
 HB_DEV void subc(uint32_t& d, uint32_t a, uint32_t b)    { asm volatile("subc.u32 %0, %1, %2;"    : "=r"(d) : "r"(a), "r"(b)); }
+
+#endif
 
 // acc[0..11] (six 64-bit lanes) += {a[0], a[2], ..., a[10]} * b ; carry rippled into acc[12], acc[13]
 HB_DEV void lane_mad(uint32_t* acc, const uint32_t* a, uint32_t b) {
@@ -147,9 +189,9 @@ HB_DEV void fp_sub_regs(uint32_t* r, const uint32_t* a, const uint32_t* b) {
 }
 
 // ------------------------------------------------------------------ struct-level API
-HB_DEV void fp_add(fp& r, const fp& a, const fp& b) { fp_add_regs(r.l, a.l, b.l); }
-HB_DEV void fp_sub(fp& r, const fp& a, const fp& b) { fp_sub_regs(r.l, a.l, b.l); }
-HB_DEV void fp_dbl(fp& r, const fp& a) { fp_add_regs(r.l, a.l, a.l); }
+HB_FPFN void fp_add(fp& r, const fp& a, const fp& b) { fp_add_regs(r.l, a.l, b.l); }
+HB_FPFN void fp_sub(fp& r, const fp& a, const fp& b) { fp_sub_regs(r.l, a.l, b.l); }
+HB_FPFN void fp_dbl(fp& r, const fp& a) { fp_add_regs(r.l, a.l, a.l); }
 HB_DEV bool fp_is_zero(const fp& a) {
     uint32_t o = 0;
 #pragma unroll
@@ -166,9 +208,18 @@ HB_DEV void fp_zero(fp& r) {
 #pragma unroll
     for (int j = 0; j < 12; j++) r.l[j] = 0;
 }
-HB_DEV void fp_neg(fp& r, const fp& a) {
-    fp z; fp_zero(z);
-    fp_sub_regs(r.l, z.l, a.l);    // 0 - a + p, and 0 - 0 stays 0
+HB_FPFN void fp_neg(fp& r, const fp& a) {
+    // p - a, forced to 0 when a == 0 (a is canonical, so p - a never borrows)
+    uint32_t t[12], nz = 0;
+#pragma unroll
+    for (int j = 0; j < 12; j++) nz |= a.l[j];
+    sub_cc(t[0], HB_P0, a.l[0]);
+#pragma unroll
+    for (int j = 1; j < 11; j++) subc_cc(t[j], p_limb(j), a.l[j]);
+    subc(t[11], HB_P11, a.l[11]);
+    const uint32_t m = nz ? 0xffffffffu : 0u;
+#pragma unroll
+    for (int j = 0; j < 12; j++) r.l[j] = t[j] & m;
 }
 HB_DEV void fp_set(fp& r, const uint32_t* k) {
 #pragma unroll

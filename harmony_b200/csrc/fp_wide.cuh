@@ -1,0 +1,150 @@
+// harmony_b200/csrc/fp_wide.cuh -- unreduced 768-bit products + one Montgomery reduction ("lazy reduction").
+//
+// Fp2 products are the unit of work of the pairing (Miller loop / final exponentiation are ~100% Fp2 mul/sqr), so
+// they are computed register-resident in one piece:
+//     (a0 + a1 i)(b0 + b1 i):  t0 = a0 b0, t1 = a1 b1, t2 = (a0+a1)(b0+b1) as 24-limb integers,
+//                              c0 = redc(t0 + (p^2 - t1)),  c1 = redc(t2 - t0 - t1)
+// = 3 x 144 + 2 x 156 = 744 IMAD.WIDE instead of 3 x 300, no intermediate trips through local memory, and three
+// independent carry-chain families for the scheduler to interleave.
+#pragma once
+#include "fp.cuh"
+
+namespace hb {
+
+// T[0..23] = a * b (plain integer product of two 12-limb values, any a, b < 2^384)
+HB_DEV void mul_wide(uint32_t* T, const uint32_t* a, const uint32_t* b) {
+    uint32_t x[26], y[26];          // x: 64-bit lanes at even limb positions, y: lanes at odd positions (absolute)
+#pragma unroll
+    for (int i = 0; i < 26; i++) { x[i] = 0; y[i] = 0; }
+#pragma unroll
+    for (int i = 0; i < 12; i += 2) {
+        lane_mad(x + i, a, b[i]);               // a_even * b_i   -> even positions
+        lane_mad(y + i + 1, a + 1, b[i]);       // a_odd  * b_i   -> odd positions
+        lane_mad(y + i + 1, a, b[i + 1]);       // a_even * b_i+1 -> odd positions
+        lane_mad(x + i + 2, a + 1, b[i + 1]);   // a_odd  * b_i+1 -> even positions
+    }
+    T[0] = x[0];
+    add_cc(T[1], x[1], y[1]);
+#pragma unroll
+    for (int j = 2; j < 23; j++) addc_cc(T[j], x[j], y[j]);
+    addc(T[23], x[23], y[23]);
+}
+
+// r[0..11] = T / 2^384 mod p for T < p * 2^384; result canonical in [0, p).  T is consumed.
+HB_DEV void redc_wide(uint32_t* r, const uint32_t* T) {
+    uint32_t x[28], y[28];
+#pragma unroll
+    for (int i = 0; i < 28; i++) { x[i] = i < 12 ? T[i] : 0; y[i] = 0; }
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        const int q = 2 * k;
+        const uint32_t m0 = x[q] * HB_N0;
+        lane_mad_p<0>(x + q, m0);
+        lane_mad_p<1>(y + q + 1, m0);
+        const uint32_t m1 = (x[q + 1] + y[q + 1]) * HB_N0;
+        lane_mad_p<0>(y + q + 1, m1);
+        lane_mad_p<1>(x + q + 2, m1);
+        uint32_t dead;
+        add_cc(dead, x[q + 1], y[q + 1]);
+        addc_cc(x[q + 2], x[q + 2], y[q + 2]);
+#pragma unroll
+        for (int j = q + 3; j < q + 15; j++) addc_cc(x[j], x[j], 0);
+        addc(x[q + 15], x[q + 15], 0);
+        (void)dead;
+    }
+    // (T_low + m p) / R = X[12..] + Y[13..] ; then add T_high
+    add_cc(x[13], x[13], y[13]);
+#pragma unroll
+    for (int j = 14; j < 24; j++) addc_cc(x[j], x[j], y[j]);
+    add_cc(x[12], x[12], T[12]);
+#pragma unroll
+    for (int j = 13; j < 23; j++) addc_cc(x[j], x[j], T[j]);
+    addc(x[23], x[23], T[23]);
+    uint32_t s[12];
+    sub_cc(s[0], x[12], HB_P0);
+#pragma unroll
+    for (int j = 1; j < 12; j++) subc_cc(s[j], x[12 + j], p_limb(j));
+    uint32_t borrow;
+    subc(borrow, 0, 0);
+#pragma unroll
+    for (int j = 0; j < 12; j++) r[j] = borrow ? x[12 + j] : s[j];
+}
+
+// p^2 as 24 little-endian 32-bit limbs (immediates)
+HB_DEV uint32_t p2_limb(int i) {
+    switch (i) {
+    case 0: return 0x1c718e39u; case 1: return 0x26aa0000u; case 2: return 0x76382eabu; case 3: return 0x7ced6b1du;
+    case 4: return 0x62113cfdu; case 5: return 0x162c3383u; case 6: return 0x3e71b743u; case 7: return 0x66bf91edu;
+    case 8: return 0x7091a049u; case 9: return 0x292e85a8u; case 10: return 0x86185c7bu; case 11: return 0x1d68619cu;
+    case 12: return 0x0978ef01u; case 13: return 0xf5314933u; case 14: return 0x16ddca6eu; case 15: return 0x50a62cfdu;
+    case 16: return 0x349e8bd0u; case 17: return 0x66e59e49u; case 18: return 0x0e7046b4u; case 19: return 0xe2dc90e5u;
+    case 20: return 0xa22f25e9u; case 21: return 0x4bd278eau; case 22: return 0xb8c35fc7u; default: return 0x02a437a4u;
+    }
+}
+
+// 24-limb helpers (no reduction)
+HB_DEV void wide_sub(uint32_t* r, const uint32_t* a, const uint32_t* b) {     // r = a - b (caller guarantees a >= b)
+    sub_cc(r[0], a[0], b[0]);
+#pragma unroll
+    for (int j = 1; j < 23; j++) subc_cc(r[j], a[j], b[j]);
+    subc(r[23], a[23], b[23]);
+}
+HB_DEV void wide_add(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    add_cc(r[0], a[0], b[0]);
+#pragma unroll
+    for (int j = 1; j < 23; j++) addc_cc(r[j], a[j], b[j]);
+    addc(r[23], a[23], b[23]);
+}
+HB_DEV void wide_p2_minus(uint32_t* r, const uint32_t* b) {                    // r = p^2 - b, b <= p^2
+    sub_cc(r[0], p2_limb(0), b[0]);
+#pragma unroll
+    for (int j = 1; j < 23; j++) subc_cc(r[j], p2_limb(j), b[j]);
+    subc(r[23], p2_limb(23), b[23]);
+}
+HB_DEV void limbs_add12(uint32_t* r, const uint32_t* a, const uint32_t* b) {   // r = a + b, no reduction (< 2^384 by contract)
+    add_cc(r[0], a[0], b[0]);
+#pragma unroll
+    for (int j = 1; j < 11; j++) addc_cc(r[j], a[j], b[j]);
+    addc(r[11], a[11], b[11]);
+}
+// r = a - b + p (in (0, 2p)), no reduction
+HB_DEV void limbs_sub12_plus_p(uint32_t* r, const uint32_t* a, const uint32_t* b) {
+    uint32_t t[12];
+    sub_cc(t[0], a[0], b[0]);
+#pragma unroll
+    for (int j = 1; j < 11; j++) subc_cc(t[j], a[j], b[j]);
+    subc(t[11], a[11], b[11]);
+    add_cc(r[0], t[0], HB_P0);
+#pragma unroll
+    for (int j = 1; j < 11; j++) addc_cc(r[j], t[j], p_limb(j));
+    addc(r[11], t[11], HB_P11);
+}
+
+// (ra + rb i) = (xa + xb i)(ya + yb i), all canonical
+HB_DEV void fp2_mul_regs(uint32_t* ra, uint32_t* rb, const uint32_t* xa, const uint32_t* xb, const uint32_t* ya, const uint32_t* yb) {
+    uint32_t t0[24], t1[24], t2[24], s0[12], s1[12];
+    mul_wide(t0, xa, ya);
+    mul_wide(t1, xb, yb);
+    limbs_add12(s0, xa, xb);
+    limbs_add12(s1, ya, yb);
+    mul_wide(t2, s0, s1);
+    wide_sub(t2, t2, t0);
+    wide_sub(t2, t2, t1);                 // a0 b1 + a1 b0 < 2 p^2
+    redc_wide(rb, t2);
+    wide_p2_minus(t1, t1);
+    wide_add(t0, t0, t1);                 // a0 b0 - a1 b1 + p^2 in (0, 2 p^2)
+    redc_wide(ra, t0);
+}
+// (ra + rb i) = (xa + xb i)^2
+HB_DEV void fp2_sqr_regs(uint32_t* ra, uint32_t* rb, const uint32_t* xa, const uint32_t* xb) {
+    uint32_t t0[24], t1[24], s[12], d[12];
+    limbs_add12(s, xa, xb);               // < 2p
+    limbs_sub12_plus_p(d, xa, xb);        // in (0, 2p)
+    mul_wide(t0, s, d);                   // < 4 p^2 < p R
+    mul_wide(t1, xa, xb);
+    wide_add(t1, t1, t1);                 // 2 a0 a1 < 2 p^2
+    redc_wide(ra, t0);
+    redc_wide(rb, t1);
+}
+
+}  // namespace hb

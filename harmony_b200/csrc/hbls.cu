@@ -67,7 +67,14 @@ int reserve_pinned(size_t bytes) {
 inline unsigned blocks_for(size_t n, unsigned tpb) { return (unsigned)((n + tpb - 1) / tpb); }
 #define LAUNCH(kern, grid, block, strm, ...) do { kern<<<(grid), (block), 0, (strm)>>>(__VA_ARGS__); g.launches++; } while (0)
 
-constexpr unsigned TPB = 64;      // heavy kernels: ~250 registers/thread, 4 CTAs/SM
+constexpr unsigned TPB = 64;      // heavy kernels: 64-thread CTAs
+// persistent launch geometry for the grid-stride kernels: at most `tpsm` resident threads per SM (HBLS_TPSM, default 256)
+unsigned heavy_blocks(size_t n) {
+    static int tpsm = [] { const char* e = getenv("HBLS_TPSM"); int v = e ? atoi(e) : 256; return v < 64 ? 64 : v; }();
+    size_t cap = (size_t)g.sm_count * (size_t)(tpsm / TPB);
+    size_t need = (n + TPB - 1) / TPB;
+    return (unsigned)(need < cap ? need : cap);
+}
 
 // ------------------------------------------------------------------ one verification pass over device-resident inputs.
 // pk_neg: affine -apk (or -pk) per round; sig/hm decoded inside.  arena must hold verify_scratch_bytes(B).
@@ -85,13 +92,13 @@ VerifyBufs carve_verify(Arena& ar, size_t B) {
 void launch_verify_tail(size_t B, const VerifyBufs& v, const uint8_t* d_sig96, const uint8_t* d_msgs, uint32_t msg_len,
                         const uint8_t* ok_pk, uint8_t* d_results, cudaStream_t s) {
     STAGE_EV(2, s);
-    LAUNCH(k_g2_decode, blocks_for(B, TPB), TPB, s, B, d_sig96, v.sig, v.ok_sig, 1);
+    LAUNCH(k_g2_decode, heavy_blocks(B), TPB, s, B, d_sig96, v.sig, v.ok_sig, 1);
     STAGE_EV(3, s);
-    LAUNCH(k_hash_to_g2, blocks_for(B, TPB), TPB, s, B, d_msgs, msg_len, v.hm, v.ok_hm);
+    LAUNCH(k_hash_to_g2, heavy_blocks(B), TPB, s, B, d_msgs, msg_len, v.hm, v.ok_hm);
     STAGE_EV(4, s);
-    LAUNCH(k_miller_verify, blocks_for(2 * B, TPB), TPB, s, B, v.sig, v.pkneg, v.hm, v.f);
+    LAUNCH(k_miller_verify, heavy_blocks(2 * B), TPB, s, B, v.sig, v.pkneg, v.hm, v.f);
     STAGE_EV(5, s);
-    LAUNCH(k_final_verify, blocks_for(B, TPB), TPB, s, B, v.f, v.ok_sig, v.ok_hm, ok_pk, d_results);
+    LAUNCH(k_final_verify, heavy_blocks(B), TPB, s, B, v.f, v.ok_sig, v.ok_hm, ok_pk, d_results);
     STAGE_EV(6, s);
 }
 
@@ -188,6 +195,12 @@ int hbls_init_device(int device) {
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
     g.device = device; g.sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    // the heavy kernels keep their Fp12 temporaries in per-thread local memory: give L1 the whole 228 KB
+    cudaFuncSetAttribute(k_miller_verify, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    cudaFuncSetAttribute(k_final_verify, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    cudaFuncSetAttribute(k_hash_to_g2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    cudaFuncSetAttribute(k_g2_decode, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    cudaFuncSetAttribute(k_mask_aggregate, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     g.ready = true;
     return 0;
 }
@@ -347,7 +360,7 @@ int hbls_aggregate_sigs(const uint8_t* sig96, size_t n, uint8_t out96[96]) {
     std::vector<uint8_t> ok(nn, 1);
     if (n) {
         CK(cudaMemcpyAsync(din, sig96, n * 96, cudaMemcpyHostToDevice, g.stream));
-        LAUNCH(k_g2_decode, blocks_for(n, TPB), TPB, g.stream, n, din, dpts, dok, 1);
+        LAUNCH(k_g2_decode, heavy_blocks(n), TPB, g.stream, n, din, dpts, dok, 1);
     }
     LAUNCH(k_g2_sum, 1, HB_SUM_THREADS, g.stream, n, dpts, dsum);
     LAUNCH(k_g2_serialize, 1, 32, g.stream, (size_t)1, dsum, dout);
@@ -463,6 +476,8 @@ int hbls_get_public_key_batch(size_t k, const uint8_t* sk32, uint8_t* pk48_out) 
     return 0;
 }
 
+int hbls_debug_g2(const uint8_t sig96[96], uint8_t out512[512]) {
+    int rc = -1; if (int e = single_op(OP_DBG_G2, sig96, 96, nullptr, 0, out512, 512, &rc)) return e; return rc; }
 int hbls_fp_mul_batch(size_t n, const uint8_t* a48, const uint8_t* b48, uint8_t* out48) {
     if (int e = ensure_init()) return e;
     if (n == 0) return 0;

@@ -12,7 +12,9 @@
 
 namespace hb {
 
-#define HB_TID (blockIdx.x * blockDim.x + threadIdx.x)
+#define HB_TID ((size_t)blockIdx.x * blockDim.x + threadIdx.x)
+#define HB_STRIDE ((size_t)gridDim.x * blockDim.x)      // heavy kernels are persistent grid-stride loops: resident threads are capped
+                                                        // so the per-thread working set (~3 KB of Fp12 temporaries) stays in L1/L2
 
 // ---- parity probe: canonical LE operands -> Montgomery -> product -> canonical
 __global__ void k_fp_mul(size_t n, const uint8_t* a, const uint8_t* b, uint8_t* out) {
@@ -33,12 +35,13 @@ __global__ void k_g1_decode(size_t n, const uint8_t* in, g1a* out, uint8_t* ok, 
     out[i] = a; ok[i] = good ? 1 : 0;
 }
 __global__ void k_g2_decode(size_t n, const uint8_t* in, g2a* out, uint8_t* ok, int check_order) {
-    size_t i = HB_TID; if (i >= n) return;
+  for (size_t i = HB_TID; i < n; i += HB_STRIDE) {
     g2 p; bool good = g2_deserialize(p, in + 96 * i, check_order != 0);
     g2a a;
     if (!good || pt_is_inf(p)) { fp2_zero(a.x); fp2_zero(a.y); }
     else { a.x = p.x; a.y = p.y; }
     out[i] = a; ok[i] = good ? 1 : 0;
+  }
 }
 
 // ---- warp shuffle of a whole point
@@ -101,31 +104,34 @@ __global__ void __launch_bounds__(HB_SUM_THREADS) k_g2_sum(size_t n, const g2a* 
 
 // ---- message -> G2 (hash part of R6/R7), affine output
 __global__ void k_hash_to_g2(size_t n, const uint8_t* msgs, uint32_t msg_len, g2a* out, uint8_t* ok) {
-    size_t i = HB_TID; if (i >= n) return;
+  for (size_t i = HB_TID; i < n; i += HB_STRIDE) {
     g2 h; bool good = map_to_g2(h, msgs + (size_t)msg_len * i, msg_len);
     g2a a;
     if (!good) { fp2_zero(a.x); fp2_zero(a.y); } else pt_to_aff(a, h);
     out[i] = a; ok[i] = good ? 1 : 0;
+  }
 }
 
 // ---- verification (R7/R8): two Miller loops per round, one thread each:
 //      t even: f = ML(B, sig_j)        t odd: f = ML(-pk_j, H(m_j))
 __global__ void k_miller_verify(size_t B, const g2a* sig, const g1a* pk_neg, const g2a* hm, fp12* f) {
-    size_t t = HB_TID; if (t >= 2 * B) return;
+  for (size_t t = HB_TID; t < 2 * B; t += HB_STRIDE) {
     size_t j = t >> 1;
     g1a p; g2a q;
     if (t & 1) { p = pk_neg[j]; q = hm[j]; }
     else { fp_set(p.x, K_G1_X); fp_set(p.y, K_G1_Y); q = sig[j]; }
     fp12 r; miller_loop(r, p, q);
     f[t] = r;
+  }
 }
 // result_j = ok flags && FE(f_2j * f_2j+1) == 1
 __global__ void k_final_verify(size_t B, const fp12* f, const uint8_t* ok_a, const uint8_t* ok_b, const uint8_t* ok_c, uint8_t* results) {
-    size_t j = HB_TID; if (j >= B) return;
+  for (size_t j = HB_TID; j < B; j += HB_STRIDE) {
     bool good = (!ok_a || ok_a[j]) && (!ok_b || ok_b[j]) && (!ok_c || ok_c[j]);
     fp12 m, a = f[2 * j], b = f[2 * j + 1];
     fp12_mul(m, a, b); final_exp(m, m);
     results[j] = (good && fp12_is_one(m)) ? 1 : 0;
+  }
 }
 
 // ---- scalar multiplication batches (R6 sign, R14 GetPublicKey)
@@ -143,7 +149,7 @@ __global__ void k_sign_hash(size_t n, const uint8_t* sk32, const uint8_t* msgs, 
 }
 
 // ---- single-element ops behind the herumi-shaped C ABI (one thread; latency is launch-bound)
-enum { OP_G1_ADD = 1, OP_G1_SUB, OP_G2_ADD, OP_G1_EQ, OP_G2_EQ, OP_G1_SER, OP_G2_SER, OP_G1_DES, OP_G2_DES, OP_MAP_SER };
+enum { OP_G1_ADD = 1, OP_G1_SUB, OP_G2_ADD, OP_G1_EQ, OP_G2_EQ, OP_G1_SER, OP_G2_SER, OP_G1_DES, OP_G2_DES, OP_MAP_SER, OP_DBG_G2 };
 __global__ void k_single(int op, const void* a, const void* b, void* out, int* rc, uint32_t len) {
     if (HB_TID != 0) return;
     switch (op) {
@@ -158,6 +164,21 @@ __global__ void k_single(int op, const void* a, const void* b, void* out, int* r
     case OP_G1_DES: { g1 x; bool g = g1_deserialize(x, (const uint8_t*)a, true); if (g) *(g1*)out = x; *rc = g ? 48 : 0; break; }
     case OP_G2_DES: { g2 x; bool g = g2_deserialize(x, (const uint8_t*)a, true); if (g) *(g2*)out = x; *rc = g ? 96 : 0; break; }
     case OP_MAP_SER: { g2 h; bool g = map_to_g2(h, (const uint8_t*)a, len); if (g) g2_serialize((uint8_t*)out, h); *rc = g ? 0 : -1; break; }
+    case OP_DBG_G2: {   // step-by-step G2 decode probe (debug aid): flags in out[0..31], four serialized points after
+        uint8_t* o = (uint8_t*)out; const uint8_t* in = (const uint8_t*)a;
+        fp va, vb; load_words(va.l, in, 12); load_words(vb.l, in + 48, 12);
+        bool odd = (vb.l[11] >> 31) != 0; vb.l[11] &= 0x7fffffffu;
+        fp2 x, y, t, b2; fp_from_int(x.a, va); fp_from_int(x.b, vb);
+        fp2_sqr(t, x); fp2_mul(t, t, x); fp2_const(b2, K_B2); fp2_add(t, t, b2);
+        o[0] = fp2_sqrt(y, t) ? 1 : 0;
+        o[1] = fp_is_odd(y.a) ? 1 : 0; o[2] = odd ? 1 : 0;
+        if ((o[1] != 0) != odd) fp2_neg(y, y);
+        o[3] = fp_is_odd(y.a) ? 1 : 0;
+        g2 P; P.x = x; P.y = y; fp2_one(P.z);
+        g2 A, B, C, D; g2_psi(A, P); pt_mul_zabs(B, P); pt_neg(C, B); D = B; pt_neg(D, D);
+        o[4] = pt_eq(A, C) ? 1 : 0; o[5] = pt_eq(A, D) ? 1 : 0; o[6] = pt_eq(C, D) ? 1 : 0; o[7] = g2_in_subgroup(P) ? 1 : 0;
+        g2_serialize(o + 32, A); g2_serialize(o + 128, B); g2_serialize(o + 224, C); g2_serialize(o + 320, D); g2_serialize(o + 416, P);
+        *rc = 0; break; }
     default: *rc = -1;
     }
 }

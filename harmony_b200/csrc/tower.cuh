@@ -4,9 +4,67 @@
 // tower basis and formulas are free; results are checked as booleans against oracle/.
 #pragma once
 #include "fp.cuh"
+#include "fp_wide.cuh"
 #include "hbls_constants.cuh"
 
 namespace hb {
+// per-helper outlining switches (code size vs call overhead); -DHB_OL_<NAME>=0/1, default = HB_OUTLINE_FP2
+#ifndef HB_OL_ADD
+#define HB_OL_ADD HB_OUTLINE_FP2
+#endif
+#if HB_OL_ADD
+#define HB_ATTR_ADD __device__ __noinline__
+#else
+#define HB_ATTR_ADD __device__ __forceinline__
+#endif
+#ifndef HB_OL_SUB
+#define HB_OL_SUB HB_OUTLINE_FP2
+#endif
+#if HB_OL_SUB
+#define HB_ATTR_SUB __device__ __noinline__
+#else
+#define HB_ATTR_SUB __device__ __forceinline__
+#endif
+#ifndef HB_OL_NEG
+#define HB_OL_NEG HB_OUTLINE_FP2
+#endif
+#if HB_OL_NEG
+#define HB_ATTR_NEG __device__ __noinline__
+#else
+#define HB_ATTR_NEG __device__ __forceinline__
+#endif
+#ifndef HB_OL_CONJ
+#define HB_OL_CONJ HB_OUTLINE_FP2
+#endif
+#if HB_OL_CONJ
+#define HB_ATTR_CONJ __device__ __noinline__
+#else
+#define HB_ATTR_CONJ __device__ __forceinline__
+#endif
+#ifndef HB_OL_DBL
+#define HB_OL_DBL HB_OUTLINE_FP2
+#endif
+#if HB_OL_DBL
+#define HB_ATTR_DBL __device__ __noinline__
+#else
+#define HB_ATTR_DBL __device__ __forceinline__
+#endif
+#ifndef HB_OL_MULFP
+#define HB_OL_MULFP HB_OUTLINE_FP2
+#endif
+#if HB_OL_MULFP
+#define HB_ATTR_MULFP __device__ __noinline__
+#else
+#define HB_ATTR_MULFP __device__ __forceinline__
+#endif
+#ifndef HB_OL_MULXI
+#define HB_OL_MULXI HB_OUTLINE_FP2
+#endif
+#if HB_OL_MULXI
+#define HB_ATTR_MULXI __device__ __noinline__
+#else
+#define HB_ATTR_MULXI __device__ __forceinline__
+#endif
 
 struct fp2 { fp a, b; };
 struct fp6 { fp2 c0, c1, c2; };
@@ -59,14 +117,36 @@ HB_DEV void fp2_zero(fp2& r) { fp_zero(r.a); fp_zero(r.b); }
 HB_DEV void fp2_one(fp2& r) { fp_one(r.a); fp_zero(r.b); }
 HB_DEV bool fp2_is_zero(const fp2& x) { return fp_is_zero(x.a) && fp_is_zero(x.b); }
 HB_DEV bool fp2_eq(const fp2& x, const fp2& y) { return fp_eq(x.a, y.a) && fp_eq(x.b, y.b); }
-HB_DEV void fp2_add(fp2& r, const fp2& x, const fp2& y) { fp_add(r.a, x.a, y.a); fp_add(r.b, x.b, y.b); }
-HB_DEV void fp2_sub(fp2& r, const fp2& x, const fp2& y) { fp_sub(r.a, x.a, y.a); fp_sub(r.b, x.b, y.b); }
-HB_DEV void fp2_neg(fp2& r, const fp2& x) { fp_neg(r.a, x.a); fp_neg(r.b, x.b); }
-HB_DEV void fp2_conj(fp2& r, const fp2& x) { r.a = x.a; fp_neg(r.b, x.b); }
-HB_DEV void fp2_dbl(fp2& r, const fp2& x) { fp_dbl(r.a, x.a); fp_dbl(r.b, x.b); }
+HB_ATTR_ADD void fp2_add(fp2& r, const fp2& x, const fp2& y) { fp_add(r.a, x.a, y.a); fp_add(r.b, x.b, y.b); }
+HB_ATTR_SUB void fp2_sub(fp2& r, const fp2& x, const fp2& y) { fp_sub(r.a, x.a, y.a); fp_sub(r.b, x.b, y.b); }
+HB_ATTR_NEG void fp2_neg(fp2& r, const fp2& x) { fp_neg(r.a, x.a); fp_neg(r.b, x.b); }
+HB_ATTR_CONJ void fp2_conj(fp2& r, const fp2& x) { r.a = x.a; fp_neg(r.b, x.b); }
+HB_ATTR_DBL void fp2_dbl(fp2& r, const fp2& x) { fp_dbl(r.a, x.a); fp_dbl(r.b, x.b); }
 HB_DEV void fp2_const(fp2& r, const uint32_t k[2][12]) { fp_set(r.a, k[0]); fp_set(r.b, k[1]); }
 HB_DEV void fp2_cmov(fp2& r, const fp2& x, bool c) { fp_cmov(r.a, x.a, c); fp_cmov(r.b, x.b, c); }
 
+#ifndef HB_FUSED_FP2
+#define HB_FUSED_FP2 1
+#endif
+#if HB_FUSED_FP2
+// register-resident Karatsuba with lazy reduction (fp_wide.cuh): 744 IMAD.WIDE, operands touched once
+HB_NOINLINE void fp2_mul(fp2& r, const fp2& x, const fp2& y) {
+    uint32_t xa[12], xb[12], ya[12], yb[12], ra[12], rb[12];
+#pragma unroll
+    for (int j = 0; j < 12; j++) { xa[j] = x.a.l[j]; xb[j] = x.b.l[j]; ya[j] = y.a.l[j]; yb[j] = y.b.l[j]; }
+    fp2_mul_regs(ra, rb, xa, xb, ya, yb);
+#pragma unroll
+    for (int j = 0; j < 12; j++) { r.a.l[j] = ra[j]; r.b.l[j] = rb[j]; }
+}
+HB_NOINLINE void fp2_sqr(fp2& r, const fp2& x) {
+    uint32_t xa[12], xb[12], ra[12], rb[12];
+#pragma unroll
+    for (int j = 0; j < 12; j++) { xa[j] = x.a.l[j]; xb[j] = x.b.l[j]; }
+    fp2_sqr_regs(ra, rb, xa, xb);
+#pragma unroll
+    for (int j = 0; j < 12; j++) { r.a.l[j] = ra[j]; r.b.l[j] = rb[j]; }
+}
+#else
 HB_NOINLINE void fp2_mul(fp2& r, const fp2& x, const fp2& y) {
     fp t0, t1, t2, s0, s1;
     fp_mul(t0, x.a, y.a); fp_mul(t1, x.b, y.b);
@@ -78,8 +158,9 @@ HB_NOINLINE void fp2_sqr(fp2& r, const fp2& x) {
     fp_add(s, x.a, x.b); fp_sub(d, x.a, x.b); fp_mul(m, x.a, x.b);
     fp_mul(r.a, s, d); fp_dbl(r.b, m);
 }
-HB_DEV void fp2_mul_fp(fp2& r, const fp2& x, const fp& k) { fp_mul(r.a, x.a, k); fp_mul(r.b, x.b, k); }
-HB_DEV void fp2_mul_xi(fp2& r, const fp2& x) { fp t; fp_sub(t, x.a, x.b); fp_add(r.b, x.a, x.b); r.a = t; }
+#endif
+HB_ATTR_MULFP void fp2_mul_fp(fp2& r, const fp2& x, const fp& k) { fp_mul(r.a, x.a, k); fp_mul(r.b, x.b, k); }
+HB_ATTR_MULXI void fp2_mul_xi(fp2& r, const fp2& x) { fp t; fp_sub(t, x.a, x.b); fp_add(r.b, x.a, x.b); r.a = t; }
 HB_DEV void fp2_norm(fp& r, const fp2& x) { fp t; fp_sqr(r, x.a); fp_sqr(t, x.b); fp_add(r, r, t); }
 HB_NOINLINE void fp2_inv(fp2& r, const fp2& x) {
     fp n; fp2_norm(n, x); fp_inv(n, n);

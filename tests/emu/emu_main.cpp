@@ -1,0 +1,29 @@
+// tests/emu/emu_main.cpp -- TEST HARNESS ONLY: compiles the device headers (harmony_b200/csrc/*.cuh) for the host with
+// software carry flags (HB_HOST_EMU) so tests can diff the device LOGIC against the oracle without a GPU.
+// Never linked into libhbls.so; the product has no CPU path.
+#define HB_HOST_EMU 1
+#include <cstring>
+#include "../../harmony_b200/csrc/pairing.cuh"
+using namespace hb;
+static void ld(fp& r, const uint8_t* b) { fp v; load_words(v.l, b, 12); fp_from_int(r, v); }
+static void st(uint8_t* b, const fp& a) { fp v; fp_to_int(v, a); store_words(b, v.l, 12); }
+extern "C" {
+void emu_fp_mul(const uint8_t* a, const uint8_t* b, uint8_t* o) { fp x, y; ld(x, a); ld(y, b); fp_mul(x, x, y); st(o, x); }
+void emu_fp_sqr(const uint8_t* a, uint8_t* o) { fp x; ld(x, a); fp_sqr(x, x); st(o, x); }
+void emu_fp_addsubneg(const uint8_t* a, const uint8_t* b, uint8_t* o) { fp x, y, r; ld(x, a); ld(y, b); fp_add(r, x, y); st(o, r); fp_sub(r, x, y); st(o + 48, r); fp_neg(r, x); st(o + 96, r); }
+void emu_fp2_mul(const uint8_t* a, const uint8_t* b, uint8_t* o) { fp2 x, y; ld(x.a, a); ld(x.b, a + 48); ld(y.a, b); ld(y.b, b + 48); fp2_mul(x, x, y); st(o, x.a); st(o + 48, x.b); }
+void emu_fp2_sqr(const uint8_t* a, uint8_t* o) { fp2 x; ld(x.a, a); ld(x.b, a + 48); fp2_sqr(x, x); st(o, x.a); st(o + 48, x.b); }
+int emu_map_to_g2(const uint8_t* msg, uint32_t len, uint8_t* out96) { g2 h; if (!map_to_g2(h, msg, len)) return -1; g2_serialize(out96, h); return 0; }
+int emu_g2_check(const uint8_t* in96) { g2 p; return g2_deserialize(p, in96, true) ? 1 : 0; }
+int emu_g1_check(const uint8_t* in48) { g1 p; return g1_deserialize(p, in48, true) ? 1 : 0; }
+int emu_g1_mul_gen(const uint8_t* sk32, uint8_t* out48) { uint32_t k[8]; load_words(k, sk32, 8); g1 g, r; g1_generator(g); pt_mul(r, g, k, 8); g1_serialize(out48, r); return 0; }
+// e(B, sig) * e(-pk, H(m)) == 1 on serialized inputs (the VerifyHash composition of the kernels)
+int emu_verify(const uint8_t* sig96, const uint8_t* pk48, const uint8_t* msg, uint32_t len) {
+    g2 s, h; g1 p;
+    if (!g2_deserialize(s, sig96, true) || !g1_deserialize(p, pk48, true) || !map_to_g2(h, msg, len)) return 0;
+    g2a sa, ha; g1a pa, ga; pt_to_aff(sa, s); pt_to_aff(ha, h); pt_to_aff(pa, p); fp_neg(pa.y, pa.y);
+    fp_set(ga.x, K_G1_X); fp_set(ga.y, K_G1_Y);
+    fp12 f1, f2, m; miller_loop(f1, ga, sa); miller_loop(f2, pa, ha); fp12_mul(m, f1, f2); final_exp(m, m);
+    return fp12_is_one(m) ? 1 : 0;
+}
+}

@@ -1,0 +1,62 @@
+"""CPU test of the DEVICE LOGIC: harmony_b200/csrc/*.cuh compiled for the host with software carry flags
+(tests/emu/emu_main.cpp, HB_HOST_EMU) and diffed against big-int arithmetic and the oracle.  Test harness only:
+the product library has no CPU path; this merely lets kernel arithmetic be checked where no GPU exists."""
+import ctypes, os, random, subprocess
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+P = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+
+@pytest.fixture(scope="session")
+def emu():
+    src = os.path.join(ROOT, "tests", "emu", "emu_main.cpp")
+    out = os.path.join(ROOT, "tests", "emu", "libhbls_emu.so")
+    deps = [src] + [os.path.join(ROOT, "harmony_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "harmony_b200", "csrc")) if f.endswith(".cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", out, src])
+    return ctypes.CDLL(out)
+
+def b48(v): return v.to_bytes(48, "little")
+def i48(b): return int.from_bytes(b, "little")
+
+def test_emu_field_ops(emu):
+    rng = random.Random(21)
+    edge = [0, 1, 2, P - 1, P - 2, (1 << 384) % P, 1 << 380, (P - 1) // 2]
+    pairs = [(rng.randrange(P), rng.randrange(P)) for _ in range(3000)] + [(a, b) for a in edge for b in edge]
+    o = ctypes.create_string_buffer(144)
+    for a, b in pairs:
+        emu.emu_fp_mul(b48(a), b48(b), o); assert i48(o.raw[:48]) == a * b % P, (hex(a), hex(b))
+        emu.emu_fp_addsubneg(b48(a), b48(b), o)
+        assert i48(o.raw[:48]) == (a + b) % P and i48(o.raw[48:96]) == (a - b) % P and i48(o.raw[96:144]) == (-a) % P
+    for a, _ in pairs[:500] + pairs[-64:]:
+        emu.emu_fp_sqr(b48(a), o); assert i48(o.raw[:48]) == a * a % P
+
+def test_emu_fp2_mul_sqr(emu):
+    rng = random.Random(22)
+    edge = [0, 1, P - 1, P - 2, (1 << 384) % P]
+    xs = [(rng.randrange(P), rng.randrange(P)) for _ in range(2000)] + [(a, b) for a in edge for b in edge]
+    ys = [(rng.randrange(P), rng.randrange(P)) for _ in range(2000)] + [(b, a) for a in edge for b in edge][::-1]
+    o = ctypes.create_string_buffer(96)
+    for (a0, a1), (b0, b1) in zip(xs, ys):
+        emu.emu_fp2_mul(b48(a0) + b48(a1), b48(b0) + b48(b1), o)
+        assert i48(o.raw[:48]) == (a0 * b0 - a1 * b1) % P and i48(o.raw[48:]) == (a0 * b1 + a1 * b0) % P
+        emu.emu_fp2_sqr(b48(a0) + b48(a1), o)
+        assert i48(o.raw[:48]) == (a0 * a0 - a1 * a1) % P and i48(o.raw[48:]) == (2 * a0 * a1) % P
+
+def test_emu_map_sign_verify(emu, oracle, fixtures):
+    from harmony_b200 import workload as wl
+    rng = random.Random(23)
+    o = ctypes.create_string_buffer(96)
+    for m in [b"\x01", rng.randbytes(32), rng.randbytes(48), b"\xff" * 48]:
+        assert emu.emu_map_to_g2(m, len(m), o) == 0 and o.raw == oracle.map_to_g2(m)
+    assert emu.emu_map_to_g2(bytes(8), 8, o) == -1
+    sv = fixtures["sig_vectors"][0]
+    sig, pk, msg = bytes.fromhex(sv["sig"]), bytes.fromhex(sv["pk"]), bytes.fromhex(sv["msg"])
+    assert emu.emu_g2_check(sig) == 1 and emu.emu_g1_check(pk) == 1
+    assert emu.emu_verify(sig, pk, msg, len(msg)) == 1
+    assert emu.emu_verify(sig, pk, b"\x00" + msg[1:], len(msg)) == 0
+    pkb = ctypes.create_string_buffer(48)
+    for v in fixtures["sk_pk"][:4]:
+        emu.emu_g1_mul_gen(bytes.fromhex(v["sk"]), pkb); assert pkb.raw.hex() == v["pk"]
+    bad = bytearray(sig); bad[3] ^= 1
+    assert emu.emu_g2_check(bytes(bad)) == (1 if oracle.sig_check(bytes(bad)) else 0)

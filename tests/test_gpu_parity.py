@@ -279,3 +279,13 @@ def test_large_batch_properties(gbls):
     msgs2 = [bytes([m[8] ^ 1]).join([m[:8], m[9:]]) if j in flip else m for j, m in enumerate(msgs)]
     res2 = com.AggregateVerifyBatch(bitmaps, sigs, b"".join(msgs2), 48)
     assert all((res2[j] == 0) == (j in flip) for j in range(B))
+
+def test_cpp_host_mirror(gbls):
+    """The C++ host mirror (harmony_b200/host/hbls_host.hpp: crypto/bls Mask, multibls, quorum.AggregateVotes,
+    chain.verifySignature) restating mask_test.go / quorom_test.go, run as a native binary over libhbls.so."""
+    import subprocess
+    from harmony_b200 import build
+    exe = build.build_host()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "all checks passed" in r.stdout
