@@ -250,21 +250,30 @@ HB_NOINLINE bool sw_map_g2(g2& r, const fp2& t) {
     fp n, c1, c2, one; fp2 w, x, y, g, bb;
     fp_set(c1, K_SW_C1); fp_set(c2, K_SW_C2); fp_one(one); fp2_const(bb, K_B2);
     fp2_norm(n, t); bool negative = fp_legendre(n) < 0;
-    fp2_sqr(w, t); fp2_add(w, w, bb); fp_add(w.a, w.a, one);
-    if (fp2_is_zero(w)) return false;
-    fp2_inv(w, w); fp2_mul_fp(w, w, c1); fp2_mul(w, w, t);
-    for (int i = 0; i < 3; i++) {
-        if (i == 0) { fp2_mul(x, t, w); fp2_neg(x, x); fp_add(x.a, x.a, c2); }
-        else if (i == 1) { fp2_neg(x, x); fp_sub(x.a, x.a, one); }
-        else { fp2_sqr(x, w); fp2_inv(x, x); fp_add(x.a, x.a, one); }
-        fp2_sqr(g, x); fp2_mul(g, g, x); fp2_add(g, g, bb);
-        if (fp2_sqrt(y, g)) {
-            if (negative) fp2_neg(y, y);
-            r.x = x; r.y = y; fp2_one(r.z);
-            return true;
-        }
+    // Same candidates and same "first x_i with x_i^3 + b square" rule as mcl, but with warp-uniform control flow:
+    // one shared inversion (u * c1 t)^-1 yields both w and 1/w, squareness of g(x_1), g(x_2) is decided by the
+    // Legendre symbol of the Fp2 norm, and only ONE Fp2 square root (of the selected candidate) is taken.
+    fp2 u, ct, d, x2, x3, g2v;
+    fp2_sqr(u, t); fp2_add(u, u, bb); fp_add(u.a, u.a, one);        // u = t^2 + b + 1
+    if (fp2_is_zero(u)) return false;
+    fp2_mul_fp(ct, t, c1);                                          // c1 t
+    fp2_mul(d, u, ct); fp2_inv(d, d);                               // (u c1 t)^-1
+    fp2_sqr(w, ct); fp2_mul(w, w, d);                               // w = c1 t / u
+    fp2_sqr(x3, u); fp2_mul(x3, x3, d); fp2_sqr(x3, x3); fp_add(x3.a, x3.a, one);   // x3 = 1 + 1/w^2
+    fp2_mul(x, t, w); fp2_neg(x, x); fp_add(x.a, x.a, c2);          // x1 = c2 - t w
+    fp2_neg(x2, x); fp_sub(x2.a, x2.a, one);                        // x2 = -x1 - 1
+    fp2_sqr(g, x); fp2_mul(g, g, x); fp2_add(g, g, bb);
+    fp2_sqr(g2v, x2); fp2_mul(g2v, g2v, x2); fp2_add(g2v, g2v, bb);
+    fp n1, n2; fp2_norm(n1, g); fp2_norm(n2, g2v);
+    const bool sq1 = fp_legendre(n1) >= 0, sq2 = fp_legendre(n2) >= 0;
+    if (!sq1) {
+        if (sq2) { x = x2; g = g2v; }
+        else { x = x3; fp2_sqr(g, x); fp2_mul(g, g, x); fp2_add(g, g, bb); }
     }
-    return false;
+    if (!fp2_sqrt(y, g)) return false;                              // cannot happen: one of the three is a square
+    if (negative) fp2_neg(y, y);
+    r.x = x; r.y = y; fp2_one(r.z);
+    return true;
 }
 // Budroni-Pintore cofactor clearing: [z^2 - z - 1]P + psi([z - 1]P) + psi^2([2]P)   (plain h2 gives other bytes)
 HB_NOINLINE void g2_clear_cofactor(g2& r, const g2& p) {

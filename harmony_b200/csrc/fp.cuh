@@ -239,6 +239,6 @@ HB_NOINLINE void fp_mul(fp& r, const fp& a, const fp& b) {
 #pragma unroll
     for (int j = 0; j < 12; j++) r.l[j] = rr[j];
 }
-HB_DEV void fp_sqr(fp& r, const fp& a) { fp_mul(r, a, a); }
+// fp_sqr lives in fp_wide.cuh (dedicated 78-product squaring + one reduction)
 
 }  // namespace hb

@@ -70,6 +70,51 @@ HB_DEV void redc_wide(uint32_t* r, const uint32_t* T) {
     for (int j = 0; j < 12; j++) r[j] = borrow ? x[12 + j] : s[j];
 }
 
+// acc[0..2N-1] (N 64-bit lanes) += {a[0], a[2], ..., a[2N-2]} * b ; carry rippled into acc[2N], acc[2N+1]
+template <int N> HB_DEV void lane_mad_n(uint32_t* acc, const uint32_t* a, uint32_t b) {
+    if (N == 0) return;
+    mad_lo_cc(acc[0], a[0], b, acc[0]);
+    madc_hi_cc(acc[1], a[0], b, acc[1]);
+#pragma unroll
+    for (int j = 1; j < N; j++) {
+        madc_lo_cc(acc[2 * j], a[2 * j], b, acc[2 * j]);
+        madc_hi_cc(acc[2 * j + 1], a[2 * j], b, acc[2 * j + 1]);
+    }
+    addc_cc(acc[2 * N], acc[2 * N], 0);
+    addc(acc[2 * N + 1], acc[2 * N + 1], 0);
+}
+template <int I> HB_DEV void sqr_row(uint32_t* x, uint32_t* y, const uint32_t* a) {
+    // off-diagonal products a_I * a_j, j > I: odd distance -> Y lanes at 2I+1, even distance -> X lanes at 2I+2
+    lane_mad_n<(12 - I) / 2>(y + 2 * I + 1, a + I + 1, a[I]);
+    lane_mad_n<(11 - I) / 2>(x + 2 * I + 2, a + I + 2, a[I]);
+}
+// T[0..23] = a^2: 66 off-diagonal products once, doubled by a 1-bit shift, plus 12 diagonal squares (78 IMAD.WIDE)
+HB_DEV void sqr_wide(uint32_t* T, const uint32_t* a) {
+    uint32_t x[28], y[28];
+#pragma unroll
+    for (int i = 0; i < 28; i++) { x[i] = 0; y[i] = 0; }
+    sqr_row<0>(x, y, a); sqr_row<1>(x, y, a); sqr_row<2>(x, y, a); sqr_row<3>(x, y, a);
+    sqr_row<4>(x, y, a); sqr_row<5>(x, y, a); sqr_row<6>(x, y, a); sqr_row<7>(x, y, a);
+    sqr_row<8>(x, y, a); sqr_row<9>(x, y, a); sqr_row<10>(x, y, a);
+    uint32_t s[24];
+    s[0] = 0;
+    add_cc(s[1], x[1], y[1]);
+#pragma unroll
+    for (int j = 2; j < 23; j++) addc_cc(s[j], x[j], y[j]);
+    addc(s[23], x[23], y[23]);
+    uint32_t d[24];                       // 2 * S
+    d[0] = 0;
+#pragma unroll
+    for (int j = 1; j < 24; j++) d[j] = (s[j] << 1) | (s[j - 1] >> 31);
+    mad_lo_cc(T[0], a[0], a[0], d[0]);
+    madc_hi_cc(T[1], a[0], a[0], d[1]);
+#pragma unroll
+    for (int j = 1; j < 12; j++) {
+        madc_lo_cc(T[2 * j], a[j], a[j], d[2 * j]);
+        madc_hi_cc(T[2 * j + 1], a[j], a[j], d[2 * j + 1]);
+    }
+}
+
 // p^2 as 24 little-endian 32-bit limbs (immediates)
 HB_DEV uint32_t p2_limb(int i) {
     switch (i) {
@@ -120,6 +165,17 @@ HB_DEV void limbs_sub12_plus_p(uint32_t* r, const uint32_t* a, const uint32_t* b
     addc(r[11], t[11], HB_P11);
 }
 
+// r = a^2 / R mod p: 78 + 156 = 234 IMAD.WIDE (the exponentiation chains of sqrt / inverse / Legendre are ~80% squarings)
+HB_NOINLINE void fp_sqr(fp& r, const fp& a) {
+    uint32_t ra[12], T[24], rr[12];
+#pragma unroll
+    for (int j = 0; j < 12; j++) ra[j] = a.l[j];
+    sqr_wide(T, ra);
+    redc_wide(rr, T);
+#pragma unroll
+    for (int j = 0; j < 12; j++) r.l[j] = rr[j];
+}
+
 // (ra + rb i) = (xa + xb i)(ya + yb i), all canonical
 HB_DEV void fp2_mul_regs(uint32_t* ra, uint32_t* rb, const uint32_t* xa, const uint32_t* xb, const uint32_t* ya, const uint32_t* yb) {
     uint32_t t0[24], t1[24], t2[24], s0[12], s1[12];
@@ -145,6 +201,27 @@ HB_DEV void fp2_sqr_regs(uint32_t* ra, uint32_t* rb, const uint32_t* xa, const u
     wide_add(t1, t1, t1);                 // 2 a0 a1 < 2 p^2
     redc_wide(ra, t0);
     redc_wide(rb, t1);
+}
+
+// variant 2: register-resident Karatsuba built from three interleaved-reduction (CIOS) products, canonical add/sub
+HB_DEV void fp2_mul_regs_cios(uint32_t* ra, uint32_t* rb, const uint32_t* xa, const uint32_t* xb, const uint32_t* ya, const uint32_t* yb) {
+    uint32_t t0[12], t1[12], t2[12], s0[12], s1[12];
+    fp_mul_regs(t0, xa, ya);
+    fp_mul_regs(t1, xb, yb);
+    fp_add_regs(s0, xa, xb);
+    fp_add_regs(s1, ya, yb);
+    fp_mul_regs(t2, s0, s1);
+    fp_sub_regs(ra, t0, t1);
+    fp_sub_regs(t2, t2, t0);
+    fp_sub_regs(rb, t2, t1);
+}
+HB_DEV void fp2_sqr_regs_cios(uint32_t* ra, uint32_t* rb, const uint32_t* xa, const uint32_t* xb) {
+    uint32_t s[12], d[12], m[12];
+    fp_add_regs(s, xa, xb);
+    fp_sub_regs(d, xa, xb);
+    fp_mul_regs(m, xa, xb);
+    fp_mul_regs(ra, s, d);
+    fp_add_regs(rb, m, m);
 }
 
 }  // namespace hb

@@ -96,9 +96,18 @@ void launch_verify_tail(size_t B, const VerifyBufs& v, const uint8_t* d_sig96, c
     STAGE_EV(3, s);
     LAUNCH(k_hash_to_g2, heavy_blocks(B), TPB, s, B, d_msgs, msg_len, v.hm, v.ok_hm);
     STAGE_EV(4, s);
-    LAUNCH(k_miller_verify, heavy_blocks(2 * B), TPB, s, B, v.sig, v.pkneg, v.hm, v.f);
-    STAGE_EV(5, s);
-    LAUNCH(k_final_verify, heavy_blocks(B), TPB, s, B, v.f, v.ok_sig, v.ok_hm, ok_pk, d_results);
+    static const int fuse_mode = [] { const char* e = getenv("HBLS_FUSE"); return e ? atoi(e) : -1; }();   // -1 auto, 0 split, 1 fused
+    const bool fused = fuse_mode == 1 || (fuse_mode == -1 && B >= (size_t)g.sm_count * 256);
+    if (fused) {
+        // batch alone fills the chip: one thread per round, 2-pair loop with shared squarings + final exponentiation
+        STAGE_EV(5, s);
+        LAUNCH(k_pairing_verify, heavy_blocks(B), TPB, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
+    } else {
+        // small batch: two threads per round for the Miller loops (more parallelism), then one for the exponentiation
+        LAUNCH(k_miller_verify, heavy_blocks(2 * B), TPB, s, B, v.sig, v.pkneg, v.hm, v.f);
+        STAGE_EV(5, s);
+        LAUNCH(k_final_verify, heavy_blocks(B), TPB, s, B, v.f, v.ok_sig, v.ok_hm, ok_pk, d_results);
+    }
     STAGE_EV(6, s);
 }
 
@@ -198,6 +207,7 @@ int hbls_init_device(int device) {
     // the heavy kernels keep their Fp12 temporaries in per-thread local memory: give L1 the whole 228 KB
     cudaFuncSetAttribute(k_miller_verify, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_final_verify, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    cudaFuncSetAttribute(k_pairing_verify, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_hash_to_g2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_g2_decode, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_mask_aggregate, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
@@ -376,7 +386,10 @@ static int agg_verify_device_locked(const hbls_committee* c, size_t B, const uin
                                     const uint8_t* d_msgs, size_t msg_len, uint8_t* d_results, cudaStream_t s, Arena& ar) {
     VerifyBufs v = carve_verify(ar, B);
     STAGE_EV(0, s);
-    LAUNCH(k_mask_aggregate, blocks_for(B * 32, 128), 128, s, B, c->n, c->table, d_bitmaps, blen, v.apk);
+    if (B >= (size_t)g.sm_count * 256)
+        LAUNCH(k_mask_aggregate_serial, heavy_blocks(B), TPB, s, B, c->n, c->table, d_bitmaps, blen, v.apk);
+    else
+        LAUNCH(k_mask_aggregate, blocks_for(B * 32, 128), 128, s, B, c->n, c->table, d_bitmaps, blen, v.apk);
     STAGE_EV(1, s);
     LAUNCH(k_g1_normalize, blocks_for(B, TPB), TPB, s, B, v.apk, v.pkneg, 1);
     launch_verify_tail(B, v, d_sigs, d_msgs, (uint32_t)msg_len, nullptr, d_results, s);

@@ -12,6 +12,9 @@
 
 namespace hb {
 
+#ifndef HB_MINBLOCKS
+#define HB_MINBLOCKS 4      // 64-thread CTAs: 4 => up to 255 regs/thread, 8 => 128
+#endif
 #define HB_TID ((size_t)blockIdx.x * blockDim.x + threadIdx.x)
 #define HB_STRIDE ((size_t)gridDim.x * blockDim.x)      // heavy kernels are persistent grid-stride loops: resident threads are capped
                                                         // so the per-thread working set (~3 KB of Fp12 temporaries) stays in L1/L2
@@ -67,6 +70,17 @@ __global__ void k_mask_aggregate(size_t B, size_t n, const g1a* __restrict__ tab
     }
     if (lane == 0) out[warp] = acc;
 }
+// large-batch form: one thread per round walks the whole table (no shuffle tree, table rows are warp-broadcast loads)
+__global__ void k_mask_aggregate_serial(size_t B, size_t n, const g1a* __restrict__ table, const uint8_t* __restrict__ bitmaps, size_t blen, g1* out) {
+  for (size_t j = HB_TID; j < B; j += HB_STRIDE) {
+    const uint8_t* bm = bitmaps + j * blen;
+    g1 acc; pt_set_inf(acc);
+    for (size_t i = 0; i < n; i++) {
+        if (bm[i >> 3] & (1u << (i & 7))) { g1a q = table[i]; pt_add_mixed(acc, acc, q); }
+    }
+    out[j] = acc;
+  }
+}
 __global__ void k_g1_normalize(size_t n, const g1* in, g1a* out, int negate) {
     size_t i = HB_TID; if (i >= n) return;
     g1 p = in[i]; g1a a; pt_to_aff(a, p);
@@ -114,7 +128,7 @@ __global__ void k_hash_to_g2(size_t n, const uint8_t* msgs, uint32_t msg_len, g2
 
 // ---- verification (R7/R8): two Miller loops per round, one thread each:
 //      t even: f = ML(B, sig_j)        t odd: f = ML(-pk_j, H(m_j))
-__global__ void k_miller_verify(size_t B, const g2a* sig, const g1a* pk_neg, const g2a* hm, fp12* f) {
+__global__ void __launch_bounds__(64, HB_MINBLOCKS) k_miller_verify(size_t B, const g2a* sig, const g1a* pk_neg, const g2a* hm, fp12* f) {
   for (size_t t = HB_TID; t < 2 * B; t += HB_STRIDE) {
     size_t j = t >> 1;
     g1a p; g2a q;
@@ -125,11 +139,24 @@ __global__ void k_miller_verify(size_t B, const g2a* sig, const g1a* pk_neg, con
   }
 }
 // result_j = ok flags && FE(f_2j * f_2j+1) == 1
-__global__ void k_final_verify(size_t B, const fp12* f, const uint8_t* ok_a, const uint8_t* ok_b, const uint8_t* ok_c, uint8_t* results) {
+__global__ void __launch_bounds__(64, HB_MINBLOCKS) k_final_verify(size_t B, const fp12* f, const uint8_t* ok_a, const uint8_t* ok_b, const uint8_t* ok_c, uint8_t* results) {
   for (size_t j = HB_TID; j < B; j += HB_STRIDE) {
     bool good = (!ok_a || ok_a[j]) && (!ok_b || ok_b[j]) && (!ok_c || ok_c[j]);
     fp12 m, a = f[2 * j], b = f[2 * j + 1];
     fp12_mul(m, a, b); final_exp(m, m);
+    results[j] = (good && fp12_is_one(m)) ? 1 : 0;
+  }
+}
+
+// fused form used when the batch alone fills the chip: one thread per round runs the 2-pair Miller loop (shared
+// squarings) and the final exponentiation back to back -- no Fp12 round trip through HBM
+__global__ void __launch_bounds__(64, HB_MINBLOCKS) k_pairing_verify(size_t B, const g2a* sig, const g1a* pk_neg, const g2a* hm,
+                                 const uint8_t* ok_a, const uint8_t* ok_b, const uint8_t* ok_c, uint8_t* results) {
+  for (size_t j = HB_TID; j < B; j += HB_STRIDE) {
+    bool good = (!ok_a || ok_a[j]) && (!ok_b || ok_b[j]) && (!ok_c || ok_c[j]);
+    g1a gen, p2 = pk_neg[j]; g2a q1 = sig[j], q2 = hm[j];
+    fp_set(gen.x, K_G1_X); fp_set(gen.y, K_G1_Y);
+    fp12 m; miller_loop2(m, gen, q1, p2, q2); final_exp(m, m);
     results[j] = (good && fp12_is_one(m)) ? 1 : 0;
   }
 }

@@ -60,6 +60,25 @@ HB_NOINLINE void miller_loop(fp12& f, const g1a& p, const g2a& q) {
         }
     }
 }
+// two pairs at once: f = f_{|z|,Q1}(P1) * f_{|z|,Q2}(P2) sharing the 63 Fp12 squarings (-18% vs two single loops).
+// This is the shape of every verification: (B, sig) and (-pk, H(m)).
+HB_NOINLINE void miller_loop2(fp12& f, const g1a& p1, const g2a& q1, const g1a& p2, const g2a& q2) {
+    fp12_one(f);
+    const bool on1 = !(aff_is_inf(p1) || aff_is_inf(q1)), on2 = !(aff_is_inf(p2) || aff_is_inf(q2));
+    g2proj T1, T2;
+    T1.x = q1.x; T1.y = q1.y; fp2_one(T1.z);
+    T2.x = q2.x; T2.y = q2.y; fp2_one(T2.z);
+    fp2 l0, l2, l3;
+    for (int i = 62; i >= 0; i--) {
+        fp12_sqr(f, f);
+        if (on1) { ml_dbl(T1, l0, l2, l3); fp2_mul_fp(l2, l2, p1.x); fp2_mul_fp(l3, l3, p1.y); fp12_mul_by_014(f, f, l0, l2, l3); }
+        if (on2) { ml_dbl(T2, l0, l2, l3); fp2_mul_fp(l2, l2, p2.x); fp2_mul_fp(l3, l3, p2.y); fp12_mul_by_014(f, f, l0, l2, l3); }
+        if ((K_Z_ABS >> i) & 1) {
+            if (on1) { ml_add(T1, q1, l0, l2, l3); fp2_mul_fp(l2, l2, p1.x); fp2_mul_fp(l3, l3, p1.y); fp12_mul_by_014(f, f, l0, l2, l3); }
+            if (on2) { ml_add(T2, q2, l0, l2, l3); fp2_mul_fp(l2, l2, p2.x); fp2_mul_fp(l3, l3, p2.y); fp12_mul_by_014(f, f, l0, l2, l3); }
+        }
+    }
+}
 // r = f^(3 (p^12 - 1) / r): easy part, then (z-1)^2 (z+p) (z^2+p^2-1) + 3
 HB_NOINLINE void final_exp(fp12& r, const fp12& f) {
     fp12 t0, t1, t2, m;

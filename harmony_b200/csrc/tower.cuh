@@ -126,7 +126,7 @@ HB_DEV void fp2_const(fp2& r, const uint32_t k[2][12]) { fp_set(r.a, k[0]); fp_s
 HB_DEV void fp2_cmov(fp2& r, const fp2& x, bool c) { fp_cmov(r.a, x.a, c); fp_cmov(r.b, x.b, c); }
 
 #ifndef HB_FUSED_FP2
-#define HB_FUSED_FP2 1
+#define HB_FUSED_FP2 0      // 0: three out-of-line CIOS products (fastest measured); 1: lazy-reduction fused; 2: fused CIOS (see DESIGN.md results log)
 #endif
 #if HB_FUSED_FP2
 // register-resident Karatsuba with lazy reduction (fp_wide.cuh): 744 IMAD.WIDE, operands touched once
@@ -134,7 +134,11 @@ HB_NOINLINE void fp2_mul(fp2& r, const fp2& x, const fp2& y) {
     uint32_t xa[12], xb[12], ya[12], yb[12], ra[12], rb[12];
 #pragma unroll
     for (int j = 0; j < 12; j++) { xa[j] = x.a.l[j]; xb[j] = x.b.l[j]; ya[j] = y.a.l[j]; yb[j] = y.b.l[j]; }
+#if HB_FUSED_FP2 == 2
+    fp2_mul_regs_cios(ra, rb, xa, xb, ya, yb);
+#else
     fp2_mul_regs(ra, rb, xa, xb, ya, yb);
+#endif
 #pragma unroll
     for (int j = 0; j < 12; j++) { r.a.l[j] = ra[j]; r.b.l[j] = rb[j]; }
 }
@@ -142,7 +146,11 @@ HB_NOINLINE void fp2_sqr(fp2& r, const fp2& x) {
     uint32_t xa[12], xb[12], ra[12], rb[12];
 #pragma unroll
     for (int j = 0; j < 12; j++) { xa[j] = x.a.l[j]; xb[j] = x.b.l[j]; }
+#if HB_FUSED_FP2 == 2
+    fp2_sqr_regs_cios(ra, rb, xa, xb);
+#else
     fp2_sqr_regs(ra, rb, xa, xb);
+#endif
 #pragma unroll
     for (int j = 0; j < 12; j++) { r.a.l[j] = ra[j]; r.b.l[j] = rb[j]; }
 }

@@ -1,0 +1,35 @@
+"""harmony_b200/shard.py -- multi-GPU plumbing for the BLS path (one process per GPU, torch.distributed).
+
+Rounds / triples are independent, so items shard by contiguous index range with NO data-path collective;
+the only communication is bookkeeping: max-over-ranks of the device times, sum of the verified counts, and (for the
+gathered-result API) an all-gather of the per-rank result bytes.  Works with backend "nccl" (GPU box) and "gloo"
+(CPU tests, world_size 2)."""
+import torch
+import torch.distributed as dist
+
+def shard_range(n: int, rank: int, world: int):
+    """Contiguous item range [lo, hi) of `rank`: i in [g*n/G, (g+1)*n/G)."""
+    return (rank * n) // world, ((rank + 1) * n) // world
+
+def reduce_step_stats(dev_ms: float, e2e_ms: float, nsig: float, device=None):
+    """(max dev_ms, max e2e_ms, sum nsig) over ranks; identity when not initialised."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return dev_ms, e2e_ms, nsig
+    t = torch.tensor([dev_ms, e2e_ms], dtype=torch.float64, device=device)
+    s = torch.tensor([nsig], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    return float(t[0]), float(t[1]), float(s[0])
+
+def gather_results(local: bytes, n_total: int, device=None) -> bytes:
+    """All ranks obtain the n_total result bytes in item order (each rank verified its shard_range)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return bytes(local)
+    world, rank = dist.get_world_size(), dist.get_rank()
+    sizes = [shard_range(n_total, r, world)[1] - shard_range(n_total, r, world)[0] for r in range(world)]
+    pad = max(sizes)
+    mine = torch.zeros(pad, dtype=torch.uint8, device=device)
+    mine[:len(local)] = torch.frombuffer(bytearray(local), dtype=torch.uint8).to(mine.device)
+    outs = [torch.zeros(pad, dtype=torch.uint8, device=device) for _ in range(world)]
+    dist.all_gather(outs, mine)
+    return b"".join(bytes(o[:sz].cpu().numpy().tobytes()) for o, sz in zip(outs, sizes))

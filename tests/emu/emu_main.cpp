@@ -24,6 +24,8 @@ int emu_verify(const uint8_t* sig96, const uint8_t* pk48, const uint8_t* msg, ui
     g2a sa, ha; g1a pa, ga; pt_to_aff(sa, s); pt_to_aff(ha, h); pt_to_aff(pa, p); fp_neg(pa.y, pa.y);
     fp_set(ga.x, K_G1_X); fp_set(ga.y, K_G1_Y);
     fp12 f1, f2, m; miller_loop(f1, ga, sa); miller_loop(f2, pa, ha); fp12_mul(m, f1, f2); final_exp(m, m);
-    return fp12_is_one(m) ? 1 : 0;
+    fp12 m2; miller_loop2(m2, ga, sa, pa, ha); final_exp(m2, m2);
+    int a = fp12_is_one(m) ? 1 : 0, b = fp12_is_one(m2) ? 1 : 0;
+    return a == b ? a : -7;            // split and fused pairing forms must agree
 }
 }
