@@ -30,6 +30,30 @@ HB_DEV void mul_wide(uint32_t* T, const uint32_t* a, const uint32_t* b) {
     addc(T[23], x[23], y[23]);
 }
 
+// T[0..23] = a1 * b1 + a2 * b2 accumulated in ONE pair of lane accumulators (one merge instead of two + a wide add);
+// caller guarantees the sum < 2^768
+HB_DEV void mul_wide2(uint32_t* T, const uint32_t* a1, const uint32_t* b1, const uint32_t* a2, const uint32_t* b2) {
+    uint32_t x[26], y[26];
+#pragma unroll
+    for (int i = 0; i < 26; i++) { x[i] = 0; y[i] = 0; }
+#pragma unroll
+    for (int i = 0; i < 12; i += 2) {
+        lane_mad(x + i, a1, b1[i]);
+        lane_mad(y + i + 1, a1 + 1, b1[i]);
+        lane_mad(y + i + 1, a1, b1[i + 1]);
+        lane_mad(x + i + 2, a1 + 1, b1[i + 1]);
+        lane_mad(x + i, a2, b2[i]);
+        lane_mad(y + i + 1, a2 + 1, b2[i]);
+        lane_mad(y + i + 1, a2, b2[i + 1]);
+        lane_mad(x + i + 2, a2 + 1, b2[i + 1]);
+    }
+    T[0] = x[0];
+    add_cc(T[1], x[1], y[1]);
+#pragma unroll
+    for (int j = 2; j < 23; j++) addc_cc(T[j], x[j], y[j]);
+    addc(T[23], x[23], y[23]);
+}
+
 // r[0..11] = T / 2^384 mod p for T < p * 2^384; result canonical in [0, p).  T is consumed.
 HB_DEV void redc_wide(uint32_t* r, const uint32_t* T) {
     uint32_t x[28], y[28];
@@ -80,8 +104,7 @@ template <int N> HB_DEV void lane_mad_n(uint32_t* acc, const uint32_t* a, uint32
         madc_lo_cc(acc[2 * j], a[2 * j], b, acc[2 * j]);
         madc_hi_cc(acc[2 * j + 1], a[2 * j], b, acc[2 * j + 1]);
     }
-    addc_cc(acc[2 * N], acc[2 * N], 0);
-    addc(acc[2 * N + 1], acc[2 * N + 1], 0);
+    addc(acc[2 * N], acc[2 * N], 0);
 }
 template <int I> HB_DEV void sqr_row(uint32_t* x, uint32_t* y, const uint32_t* a) {
     // off-diagonal products a_I * a_j, j > I: odd distance -> Y lanes at 2I+1, even distance -> X lanes at 2I+2

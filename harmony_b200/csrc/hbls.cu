@@ -64,6 +64,8 @@ int reserve_pinned(size_t bytes) {
     g.pinned_cap = bytes + bytes / 4 + 4096;
     return 0;
 }
+unsigned split_blocks(size_t nthreads);
+unsigned light_blocks(size_t n);
 inline unsigned blocks_for(size_t n, unsigned tpb) { return (unsigned)((n + tpb - 1) / tpb); }
 #define LAUNCH(kern, grid, block, strm, ...) do { kern<<<(grid), (block), 0, (strm)>>>(__VA_ARGS__); g.launches++; } while (0)
 
@@ -76,6 +78,20 @@ unsigned heavy_blocks(size_t n) {
     return (unsigned)(need < cap ? need : cap);
 }
 
+// small-state kernels (decode, hash): working set fits L1/L2 at any occupancy -> let the register count decide
+unsigned light_blocks(size_t n) {
+    static int tpsm = [] { const char* e = getenv("HBLS_TPSM_LIGHT"); int v = e ? atoi(e) : 1024; return v < 64 ? 64 : v; }();
+    size_t cap = (size_t)g.sm_count * (size_t)(tpsm / TPB);
+    size_t need = (n + TPB - 1) / TPB;
+    return (unsigned)(need < cap ? need : cap);
+}
+// lane-pair kernels: resident threads per SM from HBLS_TPSM_SPLIT (default 512)
+unsigned split_blocks(size_t nthreads) {
+    static int tpsm = [] { const char* e = getenv("HBLS_TPSM_SPLIT"); int v = e ? atoi(e) : 512; return v < 64 ? 64 : v; }();
+    size_t cap = (size_t)g.sm_count * (size_t)(tpsm / HB_TPB_SPLIT);
+    size_t need = (nthreads + HB_TPB_SPLIT - 1) / HB_TPB_SPLIT;
+    return (unsigned)(need < cap ? need : cap);
+}
 // ------------------------------------------------------------------ one verification pass over device-resident inputs.
 // pk_neg: affine -apk (or -pk) per round; sig/hm decoded inside.  arena must hold verify_scratch_bytes(B).
 size_t verify_scratch_bytes(size_t B) {
@@ -98,7 +114,12 @@ void launch_verify_tail(size_t B, const VerifyBufs& v, const uint8_t* d_sig96, c
     STAGE_EV(4, s);
     static const int fuse_mode = [] { const char* e = getenv("HBLS_FUSE"); return e ? atoi(e) : -1; }();   // -1 auto, 0 split, 1 fused
     const bool fused = fuse_mode == 1 || (fuse_mode == -1 && B >= (size_t)g.sm_count * 256);
-    if (fused) {
+    static const int split_mode = [] { const char* e = getenv("HBLS_SPLIT"); return e ? atoi(e) : 1; }();                // lane-pair pairing kernel
+    if (fused && split_mode) {
+        STAGE_EV(5, s);
+        LAUNCH(k_pairing_verify_split, split_blocks(2 * B), HB_TPB_SPLIT, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
+        LAUNCH(k_pairing_fixup, heavy_blocks(B), TPB, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
+    } else if (fused) {
         // batch alone fills the chip: one thread per round, 2-pair loop with shared squarings + final exponentiation
         STAGE_EV(5, s);
         LAUNCH(k_pairing_verify, heavy_blocks(B), TPB, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
@@ -208,6 +229,7 @@ int hbls_init_device(int device) {
     cudaFuncSetAttribute(k_miller_verify, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_final_verify, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_pairing_verify, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    cudaFuncSetAttribute(k_pairing_verify_split, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_hash_to_g2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_g2_decode, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_mask_aggregate, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
@@ -387,7 +409,7 @@ static int agg_verify_device_locked(const hbls_committee* c, size_t B, const uin
     VerifyBufs v = carve_verify(ar, B);
     STAGE_EV(0, s);
     if (B >= (size_t)g.sm_count * 256)
-        LAUNCH(k_mask_aggregate_serial, heavy_blocks(B), TPB, s, B, c->n, c->table, d_bitmaps, blen, v.apk);
+        LAUNCH(k_mask_aggregate_serial, light_blocks(B), TPB, s, B, c->n, c->table, d_bitmaps, blen, v.apk);
     else
         LAUNCH(k_mask_aggregate, blocks_for(B * 32, 128), 128, s, B, c->n, c->table, d_bitmaps, blen, v.apk);
     STAGE_EV(1, s);
@@ -518,6 +540,18 @@ int hbls_stage_timing_get(float* ms_out, int max_stages) {
     int n = max_stages < 6 ? max_stages : 6;
     for (int i = 0; i < n; i++) { float ms = 0; cudaEventElapsedTime(&ms, g.ev[i], g.ev[i + 1]); ms_out[i] = ms; }
     return n;
+}
+int hbls_selftest_split(uint32_t iters) {
+    if (int e = ensure_init()) return e;
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (int e = reserve(4096)) return e;
+    uint32_t* d = reinterpret_cast<uint32_t*>(g.scratch);
+    CK(cudaMemsetAsync(d, 0, 4, g.stream));
+    LAUNCH(k_selftest_fp2h, 8, 64, g.stream, iters, 20240922u, d);
+    uint32_t bad = 0;
+    CK(cudaMemcpyAsync(&bad, d, 4, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return (int)bad;
 }
 double hbls_probe_mac32_per_s(int iters) {
     if (ensure_init()) return -1.0;

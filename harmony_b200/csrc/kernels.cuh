@@ -161,6 +161,82 @@ __global__ void __launch_bounds__(64, HB_MINBLOCKS) k_pairing_verify(size_t B, c
   }
 }
 
+// ---- lane-pair form: lanes (2k, 2k+1) co-own round j (even lane = real parts, odd lane = imaginary parts of every Fp2).
+// Half the per-thread state of k_pairing_verify => twice the warps for the same L1/L2 footprint.  Control flow is
+// data-oblivious; rounds with an identity operand (never the case for honest input) are flagged 0xFF and recomputed by
+// k_pairing_fixup with the thread-per-round code.
+#ifndef HB_TPB_SPLIT
+#define HB_TPB_SPLIT 512
+#endif
+#ifndef HB_MINBLOCKS_SPLIT
+#define HB_MINBLOCKS_SPLIT 1        // 1 x 512 threads x 128 regs per SM, lock-stepped per Miller / exponentiation iteration
+#endif
+__global__ void __launch_bounds__(HB_TPB_SPLIT, HB_MINBLOCKS_SPLIT) k_pairing_verify_split(size_t B, const g2a* sig, const g1a* pk_neg, const g2a* hm,
+                                 const uint8_t* ok_a, const uint8_t* ok_b, const uint8_t* ok_c, uint8_t* results) {
+    const int role = threadIdx.x & 1;
+    const size_t ppg = HB_STRIDE >> 1;                                  // pairs per grid sweep
+    for (size_t it = 0; ; it++) {
+        const size_t warp_first = it * ppg + ((HB_TID & ~(size_t)31) >> 1);
+        if (warp_first >= B) break;                                     // warp-uniform exit
+        const size_t j = it * ppg + (HB_TID >> 1);
+        const bool valid = j < B;
+        const size_t jj = valid ? j : B - 1;
+        bool good = (!ok_a || ok_a[jj]) && (!ok_b || ok_b[jj]) && (!ok_c || ok_c[jj]);
+        g1a gen, p2 = pk_neg[jj];
+        fp_set(gen.x, K_G1_X); fp_set(gen.y, K_G1_Y);
+        const fp* s4 = reinterpret_cast<const fp*>(&sig[jj]);           // x.a, x.b, y.a, y.b
+        const fp* h4 = reinterpret_cast<const fp*>(&hm[jj]);
+        fp2h q1x, q1y, q2x, q2y;
+        q1x.c = s4[role]; q1y.c = s4[2 + role]; q2x.c = h4[role]; q2y.c = h4[2 + role];
+        const bool irregular = (fp2_is_zero(q1x) && fp2_is_zero(q1y)) || (fp2_is_zero(q2x) && fp2_is_zero(q2y)) ||
+                               (fp_is_zero(p2.x) && fp_is_zero(p2.y));
+        fp12_t<fp2h> m;
+        miller_loop2<fp2h>(m, gen, q1x, q1y, p2, q2x, q2y, true, true);
+        final_exp(m, m);
+        const bool one = fp12_is_one(m);
+        if (valid && role == 0) results[j] = irregular ? 0xFF : ((good && one) ? 1 : 0);
+    }
+}
+__global__ void k_pairing_fixup(size_t B, const g2a* sig, const g1a* pk_neg, const g2a* hm,
+                                const uint8_t* ok_a, const uint8_t* ok_b, const uint8_t* ok_c, uint8_t* results) {
+  for (size_t j = HB_TID; j < B; j += HB_STRIDE) {
+    if (results[j] != 0xFF) continue;
+    bool good = (!ok_a || ok_a[j]) && (!ok_b || ok_b[j]) && (!ok_c || ok_c[j]);
+    g1a gen, p2 = pk_neg[j]; g2a q1 = sig[j], q2 = hm[j];
+    fp_set(gen.x, K_G1_X); fp_set(gen.y, K_G1_Y);
+    fp12 m; miller_loop2(m, gen, q1, p2, q2); final_exp(m, m);
+    results[j] = (good && fp12_is_one(m)) ? 1 : 0;
+  }
+}
+// device self-test of the lane-pair Fp2 primitives against the single-thread ones on pseudo-random operands
+__global__ void k_selftest_fp2h(uint32_t n, uint32_t seed, uint32_t* mismatches) {
+    const int role = threadIdx.x & 1;
+    for (uint32_t it = 0; it < n; it++) {
+        uint32_t st = seed + 7919u * (uint32_t)(HB_TID >> 1) + 104729u * it;
+        fp2 x, y;
+        uint32_t* w[4] = {x.a.l, x.b.l, y.a.l, y.b.l};
+        for (int c = 0; c < 4; c++) { for (int k = 0; k < 12; k++) { st = st * 1664525u + 1013904223u; w[c][k] = st ^ (st >> 13); } w[c][11] &= 0x0fffffffu; }
+        fp2h hx, hy, hr; hx.c = role ? x.b : x.a; hy.c = role ? y.b : y.a;
+        fp2 r; uint32_t bad = 0;
+#define HB_CHK() do { const fp& e = role ? r.b : r.a; if (!fp_eq(e, hr.c)) bad++; } while (0)
+        fp2_mul(r, x, y); fp2_mul(hr, hx, hy); HB_CHK();
+        fp2_sqr(r, x); fp2_sqr(hr, hx); HB_CHK();
+        fp2_mul_xi(r, x); fp2_mul_xi(hr, hx); HB_CHK();
+        fp2_conj(r, y); fp2_conj(hr, hy); HB_CHK();
+        fp2_add(r, x, y); fp2_add(hr, hx, hy); HB_CHK();
+        fp2_sub(r, x, y); fp2_sub(hr, hx, hy); HB_CHK();
+        fp2_neg(r, x); fp2_neg(hr, hx); HB_CHK();
+        fp2_dbl(r, y); fp2_dbl(hr, hy); HB_CHK();
+        fp2_mul_fp(r, x, y.a); fp2_mul_fp(hr, hx, y.a); HB_CHK();
+        fp2_inv(r, x); fp2_inv(hr, hx); HB_CHK();
+        fp2_one(r); fp2_one(hr); HB_CHK();
+        fp2_const(r, K_PSI_CX); fp2_const(hr, K_PSI_CX); HB_CHK();
+        if (fp2_is_zero(hx) != fp2_is_zero(x)) bad++;
+        fp2 z; fp2_zero(z); fp2h hz; fp2_zero(hz); if (!fp2_is_zero(hz)) bad++;
+        if (bad) atomicAdd(mismatches, bad);
+    }
+}
+
 // ---- scalar multiplication batches (R6 sign, R14 GetPublicKey)
 __global__ void k_g1_mul_gen(size_t n, const uint8_t* sk32, g1* out) {
     size_t i = HB_TID; if (i >= n) return;

@@ -7,39 +7,42 @@
 
 namespace hb {
 
-struct g2proj { fp2 x, y, z; };    // homogeneous projective point on the twist
+template <class E> struct g2proj_t { E x, y, z; };    // homogeneous projective point on the twist
+typedef g2proj_t<fp2> g2proj;
 
 // doubling step; line = l0 + (l2 * xP) w^2 + (l3 * yP) w^3 up to an Fp2 factor
-HB_NOINLINE void ml_dbl(g2proj& t, fp2& l0, fp2& l2, fp2& l3) {
-    fp2 A, B, C, E, F, H, s, b3; fp inv2;
+template <class E> HB_NOINLINE void ml_dbl(g2proj_t<E>& t, E& l0, E& l2, E& l3) {
+    hb_lockstep2<E>();
+    E A, B, C, Ee, F, H, s, b3; fp inv2;
     fp_set(inv2, K_INV2); fp2_const(b3, K_B2_3);
     fp2_mul(A, t.x, t.y); fp2_mul_fp(A, A, inv2);
     fp2_sqr(B, t.y); fp2_sqr(C, t.z);
-    fp2_mul(E, b3, C);
-    fp2_dbl(F, E); fp2_add(F, F, E);
+    fp2_mul(Ee, b3, C);
+    fp2_dbl(F, Ee); fp2_add(F, F, Ee);
     fp2_add(H, t.y, t.z); fp2_sqr(H, H); fp2_sub(H, H, B); fp2_sub(H, H, C);     // 2YZ
-    fp2_sub(l0, B, E);                                                            // Y^2 - 3b'Z^2
+    fp2_sub(l0, B, Ee);                                                           // Y^2 - 3b'Z^2
     fp2_sqr(s, t.x); fp2_dbl(l2, s); fp2_add(l2, l2, s); fp2_neg(l2, l2);         // -3X^2
     l3 = H;
-    fp2 x3, y3, e2;
+    E x3, y3, e2;
     fp2_sub(x3, B, F); fp2_mul(x3, x3, A);
     fp2_add(y3, B, F); fp2_mul_fp(y3, y3, inv2); fp2_sqr(y3, y3);
-    fp2_sqr(e2, E); fp2_dbl(s, e2); fp2_add(s, s, e2); fp2_sub(y3, y3, s);
+    fp2_sqr(e2, Ee); fp2_dbl(s, e2); fp2_add(s, s, e2); fp2_sub(y3, y3, s);
     fp2_mul(t.z, B, H); t.x = x3; t.y = y3;
 }
 // addition step T += Q, Q affine
-HB_NOINLINE void ml_add(g2proj& t, const g2a& q, fp2& l0, fp2& l2, fp2& l3) {
-    fp2 th, mu, C, D, E, F, G, H, s;
-    fp2_mul(th, q.y, t.z); fp2_sub(th, t.y, th);
-    fp2_mul(mu, q.x, t.z); fp2_sub(mu, t.x, mu);
-    fp2_mul(l0, th, q.x); fp2_mul(s, mu, q.y); fp2_sub(l0, l0, s);
+template <class E> HB_NOINLINE void ml_add(g2proj_t<E>& t, const E& qx, const E& qy, E& l0, E& l2, E& l3) {
+    hb_lockstep2<E>();
+    E th, mu, C, D, Ee, F, G, H, s;
+    fp2_mul(th, qy, t.z); fp2_sub(th, t.y, th);
+    fp2_mul(mu, qx, t.z); fp2_sub(mu, t.x, mu);
+    fp2_mul(l0, th, qx); fp2_mul(s, mu, qy); fp2_sub(l0, l0, s);
     fp2_neg(l2, th); l3 = mu;
-    fp2_sqr(C, th); fp2_sqr(D, mu); fp2_mul(E, mu, D); fp2_mul(F, t.z, C); fp2_mul(G, t.x, D);
-    fp2_add(H, E, F); fp2_sub(H, H, G); fp2_sub(H, H, G);
-    fp2 x3, y3;
+    fp2_sqr(C, th); fp2_sqr(D, mu); fp2_mul(Ee, mu, D); fp2_mul(F, t.z, C); fp2_mul(G, t.x, D);
+    fp2_add(H, Ee, F); fp2_sub(H, H, G); fp2_sub(H, H, G);
+    E x3, y3;
     fp2_mul(x3, mu, H);
-    fp2_sub(y3, G, H); fp2_mul(y3, y3, th); fp2_mul(s, E, t.y); fp2_sub(y3, y3, s);
-    fp2_mul(t.z, t.z, E); t.x = x3; t.y = y3;
+    fp2_sub(y3, G, H); fp2_mul(y3, y3, th); fp2_mul(s, Ee, t.y); fp2_sub(y3, y3, s);
+    fp2_mul(t.z, t.z, Ee); t.x = x3; t.y = y3;
 }
 // f = f_{|z|,Q}(P) (conjugation for z < 0 omitted: f == 1 after final exp  <=>  conj(f) == 1 after final exp,
 // and a product of such values is conjugated as a whole).  Identity inputs give f = 1.
@@ -54,34 +57,38 @@ HB_NOINLINE void miller_loop(fp12& f, const g1a& p, const g2a& q) {
         fp2_mul_fp(l2, l2, p.x); fp2_mul_fp(l3, l3, p.y);
         fp12_mul_by_014(f, f, l0, l2, l3);
         if ((K_Z_ABS >> i) & 1) {
-            ml_add(T, q, l0, l2, l3);
+            ml_add(T, q.x, q.y, l0, l2, l3);
             fp2_mul_fp(l2, l2, p.x); fp2_mul_fp(l3, l3, p.y);
             fp12_mul_by_014(f, f, l0, l2, l3);
         }
     }
 }
 // two pairs at once: f = f_{|z|,Q1}(P1) * f_{|z|,Q2}(P2) sharing the 63 Fp12 squarings (-18% vs two single loops).
-// This is the shape of every verification: (B, sig) and (-pk, H(m)).
-HB_NOINLINE void miller_loop2(fp12& f, const g1a& p1, const g2a& q1, const g1a& p2, const g2a& q2) {
+// This is the shape of every verification: (B, sig) and (-pk, H(m)).  on1/on2 = pair is not an identity pair.
+template <class E> HB_NOINLINE void miller_loop2(fp12_t<E>& f, const g1a& p1, const E& q1x, const E& q1y, const g1a& p2, const E& q2x, const E& q2y,
+                                                 bool on1, bool on2) {
     fp12_one(f);
-    const bool on1 = !(aff_is_inf(p1) || aff_is_inf(q1)), on2 = !(aff_is_inf(p2) || aff_is_inf(q2));
-    g2proj T1, T2;
-    T1.x = q1.x; T1.y = q1.y; fp2_one(T1.z);
-    T2.x = q2.x; T2.y = q2.y; fp2_one(T2.z);
-    fp2 l0, l2, l3;
+    g2proj_t<E> T1, T2;
+    T1.x = q1x; T1.y = q1y; fp2_one(T1.z);
+    T2.x = q2x; T2.y = q2y; fp2_one(T2.z);
+    E l0, l2, l3;
     for (int i = 62; i >= 0; i--) {
+        hb_lockstep<E>();
         fp12_sqr(f, f);
         if (on1) { ml_dbl(T1, l0, l2, l3); fp2_mul_fp(l2, l2, p1.x); fp2_mul_fp(l3, l3, p1.y); fp12_mul_by_014(f, f, l0, l2, l3); }
         if (on2) { ml_dbl(T2, l0, l2, l3); fp2_mul_fp(l2, l2, p2.x); fp2_mul_fp(l3, l3, p2.y); fp12_mul_by_014(f, f, l0, l2, l3); }
         if ((K_Z_ABS >> i) & 1) {
-            if (on1) { ml_add(T1, q1, l0, l2, l3); fp2_mul_fp(l2, l2, p1.x); fp2_mul_fp(l3, l3, p1.y); fp12_mul_by_014(f, f, l0, l2, l3); }
-            if (on2) { ml_add(T2, q2, l0, l2, l3); fp2_mul_fp(l2, l2, p2.x); fp2_mul_fp(l3, l3, p2.y); fp12_mul_by_014(f, f, l0, l2, l3); }
+            if (on1) { ml_add(T1, q1x, q1y, l0, l2, l3); fp2_mul_fp(l2, l2, p1.x); fp2_mul_fp(l3, l3, p1.y); fp12_mul_by_014(f, f, l0, l2, l3); }
+            if (on2) { ml_add(T2, q2x, q2y, l0, l2, l3); fp2_mul_fp(l2, l2, p2.x); fp2_mul_fp(l3, l3, p2.y); fp12_mul_by_014(f, f, l0, l2, l3); }
         }
     }
 }
+HB_DEV void miller_loop2(fp12& f, const g1a& p1, const g2a& q1, const g1a& p2, const g2a& q2) {
+    miller_loop2<fp2>(f, p1, q1.x, q1.y, p2, q2.x, q2.y, !(aff_is_inf(p1) || aff_is_inf(q1)), !(aff_is_inf(p2) || aff_is_inf(q2)));
+}
 // r = f^(3 (p^12 - 1) / r): easy part, then (z-1)^2 (z+p) (z^2+p^2-1) + 3
-HB_NOINLINE void final_exp(fp12& r, const fp12& f) {
-    fp12 t0, t1, t2, m;
+template <class E> HB_NOINLINE void final_exp(fp12_t<E>& r, const fp12_t<E>& f) {
+    fp12_t<E> t0, t1, t2, m;
     fp12_conj(t0, f); fp12_inv(t1, f); fp12_mul(m, t0, t1);
     fp12_frob2(t0, m); fp12_mul(m, t0, m);
     fp12_cyc_exp_z(t0, m); fp12_conj(t1, m); fp12_mul(t0, t0, t1);               // a = m^(z-1)

@@ -67,8 +67,6 @@ namespace hb {
 #endif
 
 struct fp2 { fp a, b; };
-struct fp6 { fp2 c0, c1, c2; };
-struct fp12 { fp6 c0, c1; };
 
 HB_DEV void fp_const(fp& r, const uint32_t* k) { fp_set(r, k); }
 HB_DEV void fp_one(fp& r) { fp_set(r, K_ONE); }
@@ -197,13 +195,136 @@ HB_NOINLINE bool fp2_sqrt(fp2& r, const fp2& x) {
     return true;
 }
 
-// ------------------------------------------------------------------ Fp6
-HB_DEV void fp6_add(fp6& r, const fp6& x, const fp6& y) { fp2_add(r.c0, x.c0, y.c0); fp2_add(r.c1, x.c1, y.c1); fp2_add(r.c2, x.c2, y.c2); }
-HB_DEV void fp6_sub(fp6& r, const fp6& x, const fp6& y) { fp2_sub(r.c0, x.c0, y.c0); fp2_sub(r.c1, x.c1, y.c1); fp2_sub(r.c2, x.c2, y.c2); }
-HB_DEV void fp6_neg(fp6& r, const fp6& x) { fp2_neg(r.c0, x.c0); fp2_neg(r.c1, x.c1); fp2_neg(r.c2, x.c2); }
-HB_DEV void fp6_mul_v(fp6& r, const fp6& x) { fp2 t; fp2_mul_xi(t, x.c2); r.c2 = x.c1; r.c1 = x.c0; r.c0 = t; }
-HB_NOINLINE void fp6_mul(fp6& r, const fp6& x, const fp6& y) {
-    fp2 v0, v1, v2, t0, t1, t2, s;
+// ------------------------------------------------------------------ Fp2 split across a lane pair (fp2h)
+// Two adjacent lanes (2k, 2k+1) co-own every Fp2 value of one pairing: the even lane holds the real part, the odd lane
+// the imaginary part.  Per-thread state (and stack traffic) of the Miller loop / final exponentiation halves, so twice
+// as many warps fit the same L1/L2 footprint; products exchange 24 words by __shfl_xor and cost 2 wide products + 1
+// reduction per lane (schoolbook, perfectly balanced); squarings cost 1 + 1.  All role-dependent choices are selects,
+// so the instruction stream is identical in both lanes.  Control flow must be pair-uniform (it is: the pairing code is
+// data-oblivious), because the exchanges use full-warp shuffles.
+struct fp2h { fp c; };
+#ifdef HB_HOST_EMU
+// host emulation runs one logical pair at a time: the partner component lives in a side slot
+struct fp2h_emu_ctx { int role; };
+static thread_local fp2h_emu_ctx hb_emu = {0};
+#endif
+HB_DEV int fp2h_role() {
+#ifdef HB_HOST_EMU
+    return hb_emu.role;
+#else
+    return threadIdx.x & 1;
+#endif
+}
+#ifndef HB_HOST_EMU
+HB_DEV void fp2h_partner(fp& r, const fp& x) {
+#pragma unroll
+    for (int j = 0; j < 12; j++) r.l[j] = __shfl_xor_sync(0xffffffffu, x.l[j], 1);
+}
+HB_DEV void fp2_zero(fp2h& r) { fp_zero(r.c); }
+HB_DEV void fp2_one(fp2h& r) { fp o; fp_one(o); fp z; fp_zero(z); r.c = z; fp_cmov(r.c, o, fp2h_role() == 0); }
+HB_DEV bool fp2_is_zero(const fp2h& x) {
+    bool mine = fp_is_zero(x.c);
+    bool other = __shfl_xor_sync(0xffffffffu, mine ? 1 : 0, 1) != 0;
+    return mine && other;
+}
+HB_DEV void fp2_const(fp2h& r, const uint32_t k[2][12]) { fp_set(r.c, k[fp2h_role()]); }
+HB_ATTR_ADD void fp2_add(fp2h& r, const fp2h& x, const fp2h& y) { fp_add(r.c, x.c, y.c); }
+HB_ATTR_SUB void fp2_sub(fp2h& r, const fp2h& x, const fp2h& y) { fp_sub(r.c, x.c, y.c); }
+HB_ATTR_NEG void fp2_neg(fp2h& r, const fp2h& x) { fp_neg(r.c, x.c); }
+HB_ATTR_DBL void fp2_dbl(fp2h& r, const fp2h& x) { fp_dbl(r.c, x.c); }
+HB_ATTR_CONJ void fp2_conj(fp2h& r, const fp2h& x) { fp n; fp_neg(n, x.c); r.c = x.c; fp_cmov(r.c, n, fp2h_role() == 1); }
+HB_ATTR_MULFP void fp2_mul_fp(fp2h& r, const fp2h& x, const fp& k) { fp_mul(r.c, x.c, k); }
+// xi * (a + b i) = (a - b) + (a + b) i
+HB_ATTR_MULXI void fp2_mul_xi(fp2h& r, const fp2h& x) {
+    fp o, s, d; fp2h_partner(o, x.c);
+    fp_add(s, x.c, o);                 // role 1 result
+    fp_sub(d, x.c, o);                 // role 0 result (a - b)
+    r.c = s; fp_cmov(r.c, d, fp2h_role() == 0);
+}
+// real: xo*yo + xp*(p - yp) ; imag: xo*yp + xp*yo   (o = own, p = partner): both lanes ADD two wide products that share
+// one accumulator pair (mul_wide2), then reduce once -- 288 + 156 IMAD.WIDE per lane
+HB_NOINLINE void fp2_mul(fp2h& r, const fp2h& x, const fp2h& y) {
+    const bool im = fp2h_role() == 1;
+    uint32_t xo[12], yo[12], xp[12], yp[12], A[12], B[12], T[24], rr[12];
+#pragma unroll
+    for (int j = 0; j < 12; j++) { xo[j] = x.c.l[j]; yo[j] = y.c.l[j]; }
+#pragma unroll
+    for (int j = 0; j < 12; j++) { xp[j] = __shfl_xor_sync(0xffffffffu, xo[j], 1); yp[j] = __shfl_xor_sync(0xffffffffu, yo[j], 1); }
+    uint32_t ny[12];                                   // p - yp in (0, p]
+    sub_cc(ny[0], HB_P0, yp[0]);
+#pragma unroll
+    for (int j = 1; j < 11; j++) subc_cc(ny[j], p_limb(j), yp[j]);
+    subc(ny[11], HB_P11, yp[11]);
+#pragma unroll
+    for (int j = 0; j < 12; j++) { A[j] = im ? yp[j] : yo[j]; B[j] = im ? yo[j] : ny[j]; }
+    mul_wide2(T, xo, A, xp, B);                        // < 2 p^2 < p R
+    redc_wide(rr, T);
+#pragma unroll
+    for (int j = 0; j < 12; j++) r.c.l[j] = rr[j];
+}
+// real: (xo + xp)(xo - xp) ; imag: 2 xo xp -- 1 wide product + 1 reduction per lane
+HB_NOINLINE void fp2_sqr(fp2h& r, const fp2h& x) {
+    const bool im = fp2h_role() == 1;
+    uint32_t xo[12], xp[12], s[12], d[12], t[12], A[12], B[12], T[24], rr[12];
+#pragma unroll
+    for (int j = 0; j < 12; j++) xo[j] = x.c.l[j];
+#pragma unroll
+    for (int j = 0; j < 12; j++) xp[j] = __shfl_xor_sync(0xffffffffu, xo[j], 1);
+    limbs_add12(s, xo, xp);            // < 2p
+    limbs_sub12_plus_p(d, xo, xp);     // in (0, 2p)
+    limbs_add12(t, xp, xp);            // 2 xp < 2p
+#pragma unroll
+    for (int j = 0; j < 12; j++) { A[j] = im ? xo[j] : s[j]; B[j] = im ? t[j] : d[j]; }
+    mul_wide(T, A, B);                 // < 4 p^2 < p R
+    redc_wide(rr, T);
+#pragma unroll
+    for (int j = 0; j < 12; j++) r.c.l[j] = rr[j];
+}
+HB_NOINLINE void fp2_inv(fp2h& r, const fp2h& x) {
+    fp sq, o, n; fp_sqr(sq, x.c); fp2h_partner(o, sq); fp_add(n, sq, o);      // a^2 + b^2 (both lanes)
+    fp_inv(n, n);
+    fp t, m; fp_mul(t, x.c, n); fp_neg(m, t);
+    r.c = t; fp_cmov(r.c, m, fp2h_role() == 1);
+}
+#endif  // !HB_HOST_EMU
+
+// Lock-step hint: with many resident warps the pairing is instruction-fetch bound (ncu: stall_no_instruction ~5 per
+// issue at 16 warps/SM) because warps drift through ~60 KB of hot code.  The lane-pair kernels keep every thread of a
+// CTA alive with identical trip counts, so a CTA barrier per Fp12 operation keeps its warps on the same cache lines.
+template <class E> HB_DEV void hb_lockstep() {}
+#ifndef HB_HOST_EMU
+#ifndef HB_LOCKSTEP
+#define HB_LOCKSTEP 1
+#endif
+#if HB_LOCKSTEP
+template <> HB_DEV void hb_lockstep<fp2h>() { __syncthreads(); }
+#endif
+#endif
+// finer-grained barriers (HB_LOCKSTEP >= 2: every Fp12-level operation, >= 3: every Fp6 product)
+template <class E> HB_DEV void hb_lockstep2() {
+#if defined(HB_LOCKSTEP) && HB_LOCKSTEP >= 2
+    hb_lockstep<E>();
+#endif
+}
+template <class E> HB_DEV void hb_lockstep3() {
+#if defined(HB_LOCKSTEP) && HB_LOCKSTEP >= 3
+    hb_lockstep<E>();
+#endif
+}
+
+// ------------------------------------------------------------------ Fp6 / Fp12, generic over the Fp2 carrier E (fp2 or fp2h)
+template <class E> struct fp6_t { E c0, c1, c2; };
+template <class E> struct fp12_t { fp6_t<E> c0, c1; };
+typedef fp6_t<fp2> fp6;
+typedef fp12_t<fp2> fp12;
+
+template <class E> HB_DEV void fp6_add(fp6_t<E>& r, const fp6_t<E>& x, const fp6_t<E>& y) { fp2_add(r.c0, x.c0, y.c0); fp2_add(r.c1, x.c1, y.c1); fp2_add(r.c2, x.c2, y.c2); }
+template <class E> HB_DEV void fp6_sub(fp6_t<E>& r, const fp6_t<E>& x, const fp6_t<E>& y) { fp2_sub(r.c0, x.c0, y.c0); fp2_sub(r.c1, x.c1, y.c1); fp2_sub(r.c2, x.c2, y.c2); }
+template <class E> HB_DEV void fp6_neg(fp6_t<E>& r, const fp6_t<E>& x) { fp2_neg(r.c0, x.c0); fp2_neg(r.c1, x.c1); fp2_neg(r.c2, x.c2); }
+template <class E> HB_DEV void fp6_mul_v(fp6_t<E>& r, const fp6_t<E>& x) { E t; fp2_mul_xi(t, x.c2); r.c2 = x.c1; r.c1 = x.c0; r.c0 = t; }
+template <class E> HB_NOINLINE void fp6_mul(fp6_t<E>& r, const fp6_t<E>& x, const fp6_t<E>& y) {
+    hb_lockstep3<E>();
+    E v0, v1, v2, t0, t1, t2, s;
     fp2_mul(v0, x.c0, y.c0); fp2_mul(v1, x.c1, y.c1); fp2_mul(v2, x.c2, y.c2);
     fp2_add(t0, x.c1, x.c2); fp2_add(s, y.c1, y.c2); fp2_mul(t0, t0, s);
     fp2_sub(t0, t0, v1); fp2_sub(t0, t0, v2); fp2_mul_xi(t0, t0); fp2_add(t0, t0, v0);
@@ -214,8 +335,8 @@ HB_NOINLINE void fp6_mul(fp6& r, const fp6& x, const fp6& y) {
     r.c0 = t0; r.c1 = t1; r.c2 = t2;
 }
 // x * (b0 + b1 v)
-HB_NOINLINE void fp6_mul_by_01(fp6& r, const fp6& x, const fp2& b0, const fp2& b1) {
-    fp2 v0, v1, t0, t1, t2, s;
+template <class E> HB_NOINLINE void fp6_mul_by_01(fp6_t<E>& r, const fp6_t<E>& x, const E& b0, const E& b1) {
+    E v0, v1, t0, t1, t2, s;
     fp2_mul(v0, x.c0, b0); fp2_mul(v1, x.c1, b1);
     fp2_mul(t0, x.c2, b1); fp2_mul_xi(t0, t0); fp2_add(t0, t0, v0);
     fp2_add(t1, x.c0, x.c1); fp2_add(s, b0, b1); fp2_mul(t1, t1, s); fp2_sub(t1, t1, v0); fp2_sub(t1, t1, v1);
@@ -223,14 +344,14 @@ HB_NOINLINE void fp6_mul_by_01(fp6& r, const fp6& x, const fp2& b0, const fp2& b
     r.c0 = t0; r.c1 = t1; r.c2 = t2;
 }
 // x * (b1 v)
-HB_NOINLINE void fp6_mul_by_1(fp6& r, const fp6& x, const fp2& b1) {
-    fp2 t0, t1, t2;
+template <class E> HB_NOINLINE void fp6_mul_by_1(fp6_t<E>& r, const fp6_t<E>& x, const E& b1) {
+    E t0, t1, t2;
     fp2_mul(t0, x.c2, b1); fp2_mul_xi(t0, t0);
     fp2_mul(t1, x.c0, b1); fp2_mul(t2, x.c1, b1);
     r.c0 = t0; r.c1 = t1; r.c2 = t2;
 }
-HB_NOINLINE void fp6_inv(fp6& r, const fp6& x) {
-    fp2 t0, t1, t2, s, d;
+template <class E> HB_NOINLINE void fp6_inv(fp6_t<E>& r, const fp6_t<E>& x) {
+    E t0, t1, t2, s, d;
     fp2_sqr(t0, x.c0); fp2_mul(s, x.c1, x.c2); fp2_mul_xi(s, s); fp2_sub(t0, t0, s);
     fp2_sqr(t1, x.c2); fp2_mul_xi(t1, t1); fp2_mul(s, x.c0, x.c1); fp2_sub(t1, t1, s);
     fp2_sqr(t2, x.c1); fp2_mul(s, x.c0, x.c2); fp2_sub(t2, t2, s);
@@ -240,39 +361,41 @@ HB_NOINLINE void fp6_inv(fp6& r, const fp6& x) {
     fp2_mul(r.c0, t0, d); fp2_mul(r.c1, t1, d); fp2_mul(r.c2, t2, d);
 }
 
-// ------------------------------------------------------------------ Fp12
-HB_DEV void fp12_one(fp12& r) {
+template <class E> HB_DEV void fp12_one(fp12_t<E>& r) {
     fp2_one(r.c0.c0); fp2_zero(r.c0.c1); fp2_zero(r.c0.c2); fp2_zero(r.c1.c0); fp2_zero(r.c1.c1); fp2_zero(r.c1.c2);
 }
-HB_DEV bool fp12_is_one(const fp12& x) {
-    fp one; fp_one(one);
-    return fp_eq(x.c0.c0.a, one) && fp_is_zero(x.c0.c0.b) && fp2_is_zero(x.c0.c1) && fp2_is_zero(x.c0.c2) &&
+template <class E> HB_DEV bool fp12_is_one(const fp12_t<E>& x) {
+    E one, d; fp2_one(one); fp2_sub(d, x.c0.c0, one);
+    return fp2_is_zero(d) && fp2_is_zero(x.c0.c1) && fp2_is_zero(x.c0.c2) &&
            fp2_is_zero(x.c1.c0) && fp2_is_zero(x.c1.c1) && fp2_is_zero(x.c1.c2);
 }
-HB_NOINLINE void fp12_mul(fp12& r, const fp12& x, const fp12& y) {
-    fp6 v0, v1, s, t;
+template <class E> HB_NOINLINE void fp12_mul(fp12_t<E>& r, const fp12_t<E>& x, const fp12_t<E>& y) {
+    hb_lockstep2<E>();
+    fp6_t<E> v0, v1, s, t;
     fp6_mul(v0, x.c0, y.c0); fp6_mul(v1, x.c1, y.c1);
     fp6_add(s, x.c0, x.c1); fp6_add(t, y.c0, y.c1); fp6_mul(s, s, t);
     fp6_sub(s, s, v0); fp6_sub(s, s, v1);
     fp6_mul_v(t, v1); fp6_add(r.c0, v0, t); r.c1 = s;
 }
-HB_NOINLINE void fp12_sqr(fp12& r, const fp12& x) {
-    fp6 ab, s, t;
+template <class E> HB_NOINLINE void fp12_sqr(fp12_t<E>& r, const fp12_t<E>& x) {
+    hb_lockstep2<E>();
+    fp6_t<E> ab, s, t;
     fp6_mul(ab, x.c0, x.c1);
     fp6_add(s, x.c0, x.c1); fp6_mul_v(t, x.c1); fp6_add(t, t, x.c0); fp6_mul(s, s, t);
     fp6_sub(s, s, ab); fp6_mul_v(t, ab); fp6_sub(r.c0, s, t);
     fp6_add(r.c1, ab, ab);
 }
-HB_DEV void fp12_conj(fp12& r, const fp12& x) { r.c0 = x.c0; fp6_neg(r.c1, x.c1); }
-HB_NOINLINE void fp12_inv(fp12& r, const fp12& x) {
-    fp6 t0, t1;
+template <class E> HB_DEV void fp12_conj(fp12_t<E>& r, const fp12_t<E>& x) { r.c0 = x.c0; fp6_neg(r.c1, x.c1); }
+template <class E> HB_NOINLINE void fp12_inv(fp12_t<E>& r, const fp12_t<E>& x) {
+    fp6_t<E> t0, t1;
     fp6_mul(t0, x.c0, x.c0); fp6_mul(t1, x.c1, x.c1); fp6_mul_v(t1, t1); fp6_sub(t0, t0, t1);
     fp6_inv(t0, t0);
     fp6_mul(r.c0, x.c0, t0); fp6_mul(t1, x.c1, t0); fp6_neg(r.c1, t1);
 }
 // sparse multiply by a Miller line (o0 + o1 v) + (o4 v) w : non-zero coefficients at w^0, w^2, w^3
-HB_NOINLINE void fp12_mul_by_014(fp12& r, const fp12& x, const fp2& o0, const fp2& o1, const fp2& o4) {
-    fp6 aa, bb, s; fp2 o14;
+template <class E> HB_NOINLINE void fp12_mul_by_014(fp12_t<E>& r, const fp12_t<E>& x, const E& o0, const E& o1, const E& o4) {
+    hb_lockstep2<E>();
+    fp6_t<E> aa, bb, s; E o14;
     fp6_mul_by_01(aa, x.c0, o0, o1);
     fp6_mul_by_1(bb, x.c1, o4);
     fp2_add(o14, o1, o4);
@@ -281,34 +404,35 @@ HB_NOINLINE void fp12_mul_by_014(fp12& r, const fp12& x, const fp2& o0, const fp
     fp6_mul_v(bb, bb); fp6_add(r.c0, aa, bb); r.c1 = s;
 }
 // coefficient of w^k (k = 2i + j) <-> tower slot
-HB_DEV fp2& fp12_slot(fp12& x, int k) {
-    fp6& h = (k & 1) ? x.c1 : x.c0;
+template <class E> HB_DEV E& fp12_slot(fp12_t<E>& x, int k) {
+    fp6_t<E>& h = (k & 1) ? x.c1 : x.c0;
     int i = k >> 1;
     return i == 0 ? h.c0 : (i == 1 ? h.c1 : h.c2);
 }
-HB_NOINLINE void fp12_frob(fp12& r, const fp12& x) {
-    fp12 t = x;
+template <class E> HB_NOINLINE void fp12_frob(fp12_t<E>& r, const fp12_t<E>& x) {
+    fp12_t<E> t = x;
     for (int k = 0; k < 6; k++) {
-        fp2& s = fp12_slot(t, k); fp2 g;
+        E& s = fp12_slot(t, k); E g;
         fp2_conj(s, s); fp2_const(g, K_FROB1[k]); fp2_mul(s, s, g);
     }
     r = t;
 }
-HB_NOINLINE void fp12_frob2(fp12& r, const fp12& x) {
-    fp12 t = x;
-    for (int k = 0; k < 6; k++) { fp2& s = fp12_slot(t, k); fp g; fp_set(g, K_FROB2[k]); fp2_mul_fp(s, s, g); }
+template <class E> HB_NOINLINE void fp12_frob2(fp12_t<E>& r, const fp12_t<E>& x) {
+    fp12_t<E> t = x;
+    for (int k = 0; k < 6; k++) { E& s = fp12_slot(t, k); fp g; fp_set(g, K_FROB2[k]); fp2_mul_fp(s, s, g); }
     r = t;
 }
 // Granger-Scott squaring in the cyclotomic subgroup (valid after the easy part of the final exponentiation)
-HB_DEV void fp4_sqr(fp2& c0, fp2& c1, const fp2& a, const fp2& b) {
-    fp2 t0, t1, t2;
+template <class E> HB_DEV void fp4_sqr(E& c0, E& c1, const E& a, const E& b) {
+    E t0, t1, t2;
     fp2_sqr(t0, a); fp2_sqr(t1, b);
     fp2_mul_xi(t2, t1); fp2_add(c0, t2, t0);
     fp2_add(t2, a, b); fp2_sqr(t2, t2); fp2_sub(t2, t2, t0); fp2_sub(c1, t2, t1);
 }
-HB_NOINLINE void fp12_cyc_sqr(fp12& r, const fp12& x) {
-    fp2 z0 = x.c0.c0, z4 = x.c0.c1, z3 = x.c0.c2, z2 = x.c1.c0, z1 = x.c1.c1, z5 = x.c1.c2;
-    fp2 t0, t1, t2, t3;
+template <class E> HB_NOINLINE void fp12_cyc_sqr(fp12_t<E>& r, const fp12_t<E>& x) {
+    hb_lockstep2<E>();
+    E z0 = x.c0.c0, z4 = x.c0.c1, z3 = x.c0.c2, z2 = x.c1.c0, z1 = x.c1.c1, z5 = x.c1.c2;
+    E t0, t1, t2, t3;
     fp4_sqr(t0, t1, z0, z1);
     fp2_sub(z0, t0, z0); fp2_dbl(z0, z0); fp2_add(z0, z0, t0);
     fp2_add(z1, t1, z1); fp2_dbl(z1, z1); fp2_add(z1, z1, t1);
@@ -322,9 +446,10 @@ HB_NOINLINE void fp12_cyc_sqr(fp12& r, const fp12& x) {
     r.c0.c0 = z0; r.c0.c1 = z4; r.c0.c2 = z3; r.c1.c0 = z2; r.c1.c1 = z1; r.c1.c2 = z5;
 }
 // r = x^z, z = -0xd201000000010000, x in the cyclotomic subgroup
-HB_NOINLINE void fp12_cyc_exp_z(fp12& r, const fp12& x) {
-    fp12 acc = x;
+template <class E> HB_NOINLINE void fp12_cyc_exp_z(fp12_t<E>& r, const fp12_t<E>& x) {
+    fp12_t<E> acc = x;
     for (int i = 62; i >= 0; i--) {
+        hb_lockstep<E>();
         fp12_cyc_sqr(acc, acc);
         if ((K_Z_ABS >> i) & 1) fp12_mul(acc, acc, x);
     }

@@ -118,6 +118,11 @@ int hbls_map_to_g2(const void* msg, size_t msg_len, uint8_t out96[96]);
 int hbls_fp_mul_batch(size_t n, const uint8_t* a48, const uint8_t* b48, uint8_t* out48);
 /* number of kernels this library has launched so far */
 uint64_t hbls_kernel_launch_count(void);
+/* device self-test of the lane-pair (split Fp2) primitives used by k_pairing_verify_split against the single-thread
+ * primitives on pseudo-random operands: returns the number of mismatches (0 = pass), <0 on error */
+int hbls_selftest_split(uint32_t iters);
+/* decode-step probe used while chasing a toolchain miscompile (tools/dbg_g2.py); 0 ok */
+int hbls_debug_g2(const uint8_t sig96[96], uint8_t out512[512]);
 /* per-kernel device timing of the aggregate-verify pipeline (CUDA events on the launching stream).
  * enable(1) makes every following hbls_aggregate_verify_batch[_device] call record events between its kernels;
  * get() waits for the last recorded pipeline and returns the number of stages written to ms_out, in launch order:

@@ -29,3 +29,9 @@ int emu_verify(const uint8_t* sig96, const uint8_t* pk48, const uint8_t* msg, ui
     return a == b ? a : -7;            // split and fused pairing forms must agree
 }
 }
+extern "C" void emu_mul_wide2(const uint8_t* a1, const uint8_t* b1, const uint8_t* a2, const uint8_t* b2, uint8_t* out96) {
+    uint32_t A1[12], B1[12], A2[12], B2[12], T[24];
+    load_words(A1, a1, 12); load_words(B1, b1, 12); load_words(A2, a2, 12); load_words(B2, b2, 12);
+    mul_wide2(T, A1, B1, A2, B2); store_words(out96, T, 24);
+}
+extern "C" void emu_sqr_wide_redc(const uint8_t* a, uint8_t* out96) { uint32_t A[12], T[24]; load_words(A, a, 12); sqr_wide(T, A); store_words(out96, T, 24); }

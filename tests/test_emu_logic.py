@@ -60,3 +60,17 @@ def test_emu_map_sign_verify(emu, oracle, fixtures):
         emu.emu_g1_mul_gen(bytes.fromhex(v["sk"]), pkb); assert pkb.raw.hex() == v["pk"]
     bad = bytearray(sig); bad[3] ^= 1
     assert emu.emu_g2_check(bytes(bad)) == (1 if oracle.sig_check(bytes(bad)) else 0)
+
+def test_emu_wide_products(emu):
+    """Unreduced 768-bit products: a1*b1 + a2*b2 in one accumulator pair (operands up to 2^384 - 1), and a^2."""
+    rng = random.Random(24)
+    M = (1 << 384) - 1
+    o = ctypes.create_string_buffer(96)
+    cases = [(rng.randrange(P), rng.randrange(P), rng.randrange(P), rng.randrange(P)) for _ in range(1500)]
+    cases += [(P - 1, P - 1, P - 1, P), (P, P, P, P), (0, 0, 0, 0), (M, 1, 0, 0), (1 << 383, 1 << 383, 1 << 383, (1 << 383) - 1), (2 * P - 1, 2 * P - 1, 0, 0)]
+    for a1, b1, a2, b2 in cases:
+        if a1 * b1 + a2 * b2 >= 1 << 768: continue
+        emu.emu_mul_wide2(b48(a1), b48(b1), b48(a2), b48(b2), o)
+        assert int.from_bytes(o.raw, "little") == a1 * b1 + a2 * b2
+    for a in [c[0] for c in cases] + [M, P, 2 * P - 1]:
+        emu.emu_sqr_wide_redc(b48(a), o); assert int.from_bytes(o.raw, "little") == a * a
