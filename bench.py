@@ -251,7 +251,7 @@ def run_gpu(args):
     names = list(bls.STAGE_NAMES)
     if stage_ms[4] < 0.02 * stage_ms[5]:           # fused launch: Miller loops + final exponentiation in k_pairing_verify
         macs = macs[:4] + [0.0, macs[4] + macs[5]]
-        names[5] = "k_pairing_verify"
+        names[5] = "k_pairing_verify_split" if os.environ.get("HBLS_SPLIT", "1") != "0" else "k_pairing_verify"
     dom = int(np.argmax(stage_ms))
     achieved = macs[dom] * B / (stage_ms[dom] * 1e-3)
     total_macs = sum(macs)

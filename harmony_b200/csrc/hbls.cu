@@ -115,9 +115,14 @@ void launch_verify_tail(size_t B, const VerifyBufs& v, const uint8_t* d_sig96, c
     static const int fuse_mode = [] { const char* e = getenv("HBLS_FUSE"); return e ? atoi(e) : -1; }();   // -1 auto, 0 split, 1 fused
     const bool fused = fuse_mode == 1 || (fuse_mode == -1 && B >= (size_t)g.sm_count * 256);
     static const int split_mode = [] { const char* e = getenv("HBLS_SPLIT"); return e ? atoi(e) : 1; }();                // lane-pair pairing kernel
-    if (fused && split_mode) {
+    if (split_mode) {
+        // default at every batch size: a lane pair per round (half the per-thread state, half the single-round latency).
+        // Large batches use 512-thread lock-stepped CTAs (one per SM); small ones 64-thread CTAs spread over the SMs.
         STAGE_EV(5, s);
-        LAUNCH(k_pairing_verify_split, split_blocks(2 * B), HB_TPB_SPLIT, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
+        if (2 * B >= (size_t)g.sm_count * HB_TPB_SPLIT)
+            LAUNCH(k_pairing_verify_split, split_blocks(2 * B), HB_TPB_SPLIT, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
+        else
+            LAUNCH(k_pairing_verify_split, blocks_for(2 * B, 64), 64, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
         LAUNCH(k_pairing_fixup, heavy_blocks(B), TPB, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
     } else if (fused) {
         // batch alone fills the chip: one thread per round, 2-pair loop with shared squarings + final exponentiation
@@ -323,8 +328,8 @@ int blsVerifyHash(const blsSignature* sig, const blsPublicKey* pub, const void* 
     LAUNCH(k_g1_normalize, 1, 32, g.stream, (size_t)1, v.apk, v.pkneg, 1);
     LAUNCH(k_g2_normalize, 1, 32, g.stream, (size_t)1, dsig, v.sig);
     LAUNCH(k_hash_to_g2, 1, 32, g.stream, (size_t)1, dmsg, (uint32_t)size, v.hm, v.ok_hm);
-    LAUNCH(k_miller_verify, 1, 32, g.stream, (size_t)1, v.sig, v.pkneg, v.hm, v.f);
-    LAUNCH(k_final_verify, 1, 32, g.stream, (size_t)1, v.f, (const uint8_t*)v.ok_hm, (const uint8_t*)nullptr, (const uint8_t*)nullptr, dres);
+    LAUNCH(k_pairing_verify_split, 1, 64, g.stream, (size_t)1, v.sig, v.pkneg, v.hm, (const uint8_t*)v.ok_hm, (const uint8_t*)nullptr, (const uint8_t*)nullptr, dres);
+    LAUNCH(k_pairing_fixup, 1, 32, g.stream, (size_t)1, v.sig, v.pkneg, v.hm, (const uint8_t*)v.ok_hm, (const uint8_t*)nullptr, (const uint8_t*)nullptr, dres);
     uint8_t res = 0;
     cudaMemcpyAsync(&res, dres, 1, cudaMemcpyDeviceToHost, g.stream);
     if (cudaStreamSynchronize(g.stream) != cudaSuccess) return 0;

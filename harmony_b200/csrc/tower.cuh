@@ -228,14 +228,22 @@ HB_DEV bool fp2_is_zero(const fp2h& x) {
     return mine && other;
 }
 HB_DEV void fp2_const(fp2h& r, const uint32_t k[2][12]) { fp_set(r.c, k[fp2h_role()]); }
-HB_ATTR_ADD void fp2_add(fp2h& r, const fp2h& x, const fp2h& y) { fp_add(r.c, x.c, y.c); }
-HB_ATTR_SUB void fp2_sub(fp2h& r, const fp2h& x, const fp2h& y) { fp_sub(r.c, x.c, y.c); }
-HB_ATTR_NEG void fp2_neg(fp2h& r, const fp2h& x) { fp_neg(r.c, x.c); }
-HB_ATTR_DBL void fp2_dbl(fp2h& r, const fp2h& x) { fp_dbl(r.c, x.c); }
-HB_ATTR_CONJ void fp2_conj(fp2h& r, const fp2h& x) { fp n; fp_neg(n, x.c); r.c = x.c; fp_cmov(r.c, n, fp2h_role() == 1); }
+#ifndef HB_SPLIT_INLINE
+#define HB_SPLIT_INLINE 1
+#endif
+#if HB_SPLIT_INLINE
+#define HB_ATTR_H __device__ __forceinline__
+#else
+#define HB_ATTR_H __device__ __noinline__
+#endif
+HB_ATTR_H void fp2_add(fp2h& r, const fp2h& x, const fp2h& y) { fp_add(r.c, x.c, y.c); }
+HB_ATTR_H void fp2_sub(fp2h& r, const fp2h& x, const fp2h& y) { fp_sub(r.c, x.c, y.c); }
+HB_ATTR_H void fp2_neg(fp2h& r, const fp2h& x) { fp_neg(r.c, x.c); }
+HB_ATTR_H void fp2_dbl(fp2h& r, const fp2h& x) { fp_dbl(r.c, x.c); }
+HB_ATTR_H void fp2_conj(fp2h& r, const fp2h& x) { fp n; fp_neg(n, x.c); r.c = x.c; fp_cmov(r.c, n, fp2h_role() == 1); }
 HB_ATTR_MULFP void fp2_mul_fp(fp2h& r, const fp2h& x, const fp& k) { fp_mul(r.c, x.c, k); }
 // xi * (a + b i) = (a - b) + (a + b) i
-HB_ATTR_MULXI void fp2_mul_xi(fp2h& r, const fp2h& x) {
+HB_ATTR_H void fp2_mul_xi(fp2h& r, const fp2h& x) {
     fp o, s, d; fp2h_partner(o, x.c);
     fp_add(s, x.c, o);                 // role 1 result
     fp_sub(d, x.c, o);                 // role 0 result (a - b)

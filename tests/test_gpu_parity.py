@@ -289,3 +289,41 @@ def test_cpp_host_mirror(gbls):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "all checks passed" in r.stdout
+
+def test_vrf_roundtrip_and_batch(gbls, oracle):
+    """crypto/vrf/bls/bls_vrf_test.go restated: evaluate/verify round trip, truncated proofs and bit flips reject;
+    proof bytes equal the oracle's SignHash(sha256(alpha))."""
+    import hashlib
+    from harmony_b200 import vrf
+    sk = gbls.SecretKey(); sk.Deserialize(wl.sk_bytes(wl.seeded_sk("vrf", 0)))
+    signer = vrf.NewVRFSigner(sk); verifier = vrf.NewVRFVerifier(sk.GetPublicKey())
+    alpha = b"this is a test input"
+    beta, pi = signer.Evaluate(alpha)
+    assert pi == oracle.sign_hash(wl.sk_bytes(wl.seeded_sk("vrf", 0)), hashlib.sha256(alpha).digest())
+    assert beta == hashlib.sha256(pi).digest() and verifier.ProofToHash(alpha, pi) == beta
+    with pytest.raises(vrf.ErrInvalidVRF): verifier.ProofToHash(b"other input", pi)
+    with pytest.raises(vrf.ErrInvalidVRF): verifier.ProofToHash(alpha, b"")
+    with pytest.raises(ValueError): verifier.ProofToHash(alpha, pi[:95])
+    bad = bytearray(pi); bad[7] ^= 0x04
+    with pytest.raises((ValueError, vrf.ErrInvalidVRF)): verifier.ProofToHash(alpha, bytes(bad))
+    pk48 = sk.GetPublicKey().Serialize()
+    out = vrf.ProofToHashBatch([pk48] * 4, [alpha, b"x", alpha, alpha], [pi, pi, bytes(bad), pi[:10]])
+    assert out[0] == beta and out[1] is None and out[2] is None and out[3] is None
+
+def test_config3_four_shards_and_config5_1000_committee(gbls, oracle):
+    """BASELINE configs[2] (4 shards x 250 validators, 4 distinct messages) and configs[4] (1000-validator committee,
+    125-byte bitmap) at test size: booleans vs the oracle, one corrupted shard."""
+    for n, nshards, tag in ((250, 4, "c3"), (1000, 1, "c5")):
+        for sh in range(nshards):
+            sks = [wl.seeded_sk(f"{tag}/{sh}", i) for i in range(n)]
+            pks_blob = gbls.GetPublicKeyBatch(b"".join(wl.sk_bytes(k) for k in sks))
+            pks = [pks_blob[48 * i:48 * i + 48] for i in range(n)]
+            com = gbls.Committee(pks); och = oracle.committee(pks)
+            bm = wl.bitmap_with_k(f"{tag}/{sh}", 0, n, wl.quorum_k(n))
+            assert len(bm) == (n + 7) // 8
+            msg = wl.commit_payload(f"{tag}/{sh}", 0)
+            sig = oracle.sign_hash(wl.sk_bytes(wl.round_signer_sum(sks, bm)), msg)
+            if sh == 2: msg = bytes([msg[0] ^ 2]) + msg[1:]
+            exp = oracle.committee_aggregate_verify(och, bm, sig, msg) == 1
+            assert com.AggregateVerify(bm, sig, msg) == exp == (sh != 2)
+            assert com.MaskAggregate(bm) == oracle.committee_mask_aggregate(och, bm)
