@@ -154,6 +154,8 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the BLS backend has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep stdout to the single JSON line (no NCCL version banner)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"): os.environ["NCCL_DEBUG"] = "WARN"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from harmony_b200 import bls
@@ -285,7 +287,7 @@ def run_gpu(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (12x32-bit Montgomery limbs, IMAD.WIDE)",
             "data": "synthetic",
-            "config": {"workload": "FBFT commit-phase: 250-validator committee, single message per round, FastAggregateVerify on 1xB200 (BASELINE configs[1])",
+            "config": {"workload": "FBFT commit-phase: 250-validator committee, single message per round, FastAggregateVerify per round (BASELINE configs[1]), " + f"{world}xB200",
                        "committee": N_COMMITTEE, "rounds_per_step_per_gpu": B, "signers_per_round": "167/200/250 cycling", "msg_len": MSG_LEN,
                        "sharding": "rounds by index, no data-path collective", "l2": "256 MiB flush between timed steps",
                        "timing": "CUDA events per step on the launching stream, max over ranks"},
