@@ -212,6 +212,7 @@ struct Sha512 {
 struct hbls_committee {
     size_t n = 0;
     g1a* table = nullptr;       // device, affine, Montgomery
+    g1* total = nullptr;        // device, sum of all rows (lets dense bitmaps be aggregated from their complement)
 };
 
 extern "C" {
@@ -359,16 +360,18 @@ int hbls_committee_create(hbls_committee** out, const uint8_t* pk48, size_t n, s
     if (n) {
         CK(cudaMemcpyAsync(din, pk48, n * 48, cudaMemcpyHostToDevice, g.stream));
         LAUNCH(k_g1_decode, blocks_for(n, TPB), TPB, g.stream, n, din, c->table, dok, 1, 0);
+        CK(cudaMalloc(&c->total, sizeof(g1)));
+        LAUNCH(k_g1_sum, 1, 128, g.stream, n, c->table, c->total);
         CK(cudaMemcpyAsync(ok.data(), dok, n, cudaMemcpyDeviceToHost, g.stream));
         CK(cudaStreamSynchronize(g.stream));
     }
     for (size_t i = 0; i < n; i++) if (!ok[i]) {
         if (bad_index) *bad_index = i;
-        cudaFree(c->table); delete c; return HBLS_ERR_DECODE;
+        cudaFree(c->table); cudaFree(c->total); delete c; return HBLS_ERR_DECODE;
     }
     *out = c; return 0;
 }
-void hbls_committee_destroy(hbls_committee* c) { if (!c) return; std::lock_guard<std::mutex> lk(g.mu); cudaFree(c->table); delete c; }
+void hbls_committee_destroy(hbls_committee* c) { if (!c) return; std::lock_guard<std::mutex> lk(g.mu); cudaFree(c->table); cudaFree(c->total); delete c; }
 size_t hbls_committee_size(const hbls_committee* c) { return c ? c->n : 0; }
 
 int hbls_mask_aggregate(const hbls_committee* c, const uint8_t* bitmap, size_t blen, uint8_t out_pk48[48]) {
@@ -414,7 +417,7 @@ static int agg_verify_device_locked(const hbls_committee* c, size_t B, const uin
     VerifyBufs v = carve_verify(ar, B);
     STAGE_EV(0, s);
     if (B >= (size_t)g.sm_count * 256)
-        LAUNCH(k_mask_aggregate_serial, light_blocks(B), TPB, s, B, c->n, c->table, d_bitmaps, blen, v.apk);
+        LAUNCH(k_mask_aggregate_serial, light_blocks(B), TPB, s, B, c->n, c->table, c->total, d_bitmaps, blen, v.apk);
     else
         LAUNCH(k_mask_aggregate, blocks_for(B * 32, 128), 128, s, B, c->n, c->table, d_bitmaps, blen, v.apk);
     STAGE_EV(1, s);

@@ -327,3 +327,25 @@ def test_config3_four_shards_and_config5_1000_committee(gbls, oracle):
             exp = oracle.committee_aggregate_verify(och, bm, sig, msg) == 1
             assert com.AggregateVerify(bm, sig, msg) == exp == (sh != 2)
             assert com.MaskAggregate(bm) == oracle.committee_mask_aggregate(och, bm)
+
+def test_full_size_batch_serial_mask_and_lockstep_kernels(gbls):
+    """BASELINE configs[1] at bench size (37 888 rounds = one full wave): exercises the large-batch kernels
+    (complement-based serial mask aggregation, 512-thread lock-stepped lane-pair pairing).  Every honest round verifies;
+    rounds whose bitmap gains/loses a signer, or whose payload changes, are exactly the ones rejected."""
+    import bench
+    n, B = 250, 148 * 256
+    sks = bench.make_committee_sks()
+    pks_blob = gbls.GetPublicKeyBatch(b"".join(wl.sk_bytes(k) for k in sks))
+    com = gbls.Committee([pks_blob[48 * i:48 * i + 48] for i in range(n)])
+    bitmaps, agg_sk, msgs, nsig = bench.make_rounds(sks, B, seed=7)
+    sigs, ok = gbls.SignHashBatch(agg_sk, msgs, 48)
+    assert ok == b"\x01" * B
+    rng = random.Random(5)
+    bad = sorted(rng.sample(range(B), 24))
+    bm = bytearray(bitmaps); mm = bytearray(msgs)
+    for t, j in enumerate(bad):
+        if t % 3 == 0: bm[32 * j + 3] ^= 0x10                  # flip one participation bit (add or remove a signer)
+        elif t % 3 == 1: mm[48 * j + 20] ^= 0x01               # different block hash
+        else: bm[32 * j + 31] ^= 0x02                          # bit 249: last validator
+    res = com.AggregateVerifyBatch(bytes(bm), sigs, bytes(mm), 48)
+    assert [j for j in range(B) if res[j] == 0] == bad
