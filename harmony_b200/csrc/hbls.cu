@@ -106,10 +106,14 @@ VerifyBufs carve_verify(Arena& ar, size_t B) {
 }
 #define STAGE_EV(i, strm) do { if (g.stage_timing) cudaEventRecord(g.ev[i], (strm)); } while (0)
 void launch_verify_tail(size_t B, const VerifyBufs& v, const uint8_t* d_sig96, const uint8_t* d_msgs, uint32_t msg_len,
-                        const uint8_t* ok_pk, uint8_t* d_results, cudaStream_t s) {
+                        const uint8_t* ok_pk, uint8_t* d_results, cudaStream_t s, bool same_msg = false) {
     STAGE_EV(2, s);
     LAUNCH(k_g2_decode, heavy_blocks(B), TPB, s, B, d_sig96, v.sig, v.ok_sig, 1);
     STAGE_EV(3, s);
+    if (same_msg && B > 1) {
+        LAUNCH(k_hash_to_g2, 1, TPB, s, (size_t)1, d_msgs, msg_len, v.hm, v.ok_hm);
+        LAUNCH(k_broadcast_hm, blocks_for(B, 256), 256, s, B, v.hm, v.ok_hm);
+    } else
     LAUNCH(k_hash_to_g2, heavy_blocks(B), TPB, s, B, d_msgs, msg_len, v.hm, v.ok_hm);
     STAGE_EV(4, s);
     static const int fuse_mode = [] { const char* e = getenv("HBLS_FUSE"); return e ? atoi(e) : -1; }();   // -1 auto, 0 split, 1 fused
@@ -412,8 +416,12 @@ int hbls_aggregate_sigs(const uint8_t* sig96, size_t n, uint8_t out96[96]) {
 }
 
 // ------------------------------------------------------------------ aggregate verification
+static bool all_messages_equal(const uint8_t* msgs, size_t n, size_t msg_len) {
+    for (size_t i = 1; i < n; i++) if (memcmp(msgs, msgs + i * msg_len, msg_len) != 0) return false;
+    return n > 1;
+}
 static int agg_verify_device_locked(const hbls_committee* c, size_t B, const uint8_t* d_bitmaps, size_t blen, const uint8_t* d_sigs,
-                                    const uint8_t* d_msgs, size_t msg_len, uint8_t* d_results, cudaStream_t s, Arena& ar) {
+                                    const uint8_t* d_msgs, size_t msg_len, uint8_t* d_results, cudaStream_t s, Arena& ar, bool same_msg = false) {
     VerifyBufs v = carve_verify(ar, B);
     STAGE_EV(0, s);
     if (B >= (size_t)g.sm_count * 256)
@@ -422,7 +430,7 @@ static int agg_verify_device_locked(const hbls_committee* c, size_t B, const uin
         LAUNCH(k_mask_aggregate, blocks_for(B * 32, 128), 128, s, B, c->n, c->table, d_bitmaps, blen, v.apk);
     STAGE_EV(1, s);
     LAUNCH(k_g1_normalize, blocks_for(B, TPB), TPB, s, B, v.apk, v.pkneg, 1);
-    launch_verify_tail(B, v, d_sigs, d_msgs, (uint32_t)msg_len, nullptr, d_results, s);
+    launch_verify_tail(B, v, d_sigs, d_msgs, (uint32_t)msg_len, nullptr, d_results, s, same_msg);
     if (g.stage_timing) g.stage_valid = true;
     return 0;
 }
@@ -453,7 +461,7 @@ int hbls_aggregate_verify_batch(const hbls_committee* c, size_t B, const uint8_t
     if (blen) CK(cudaMemcpyAsync(dbm, bitmaps, B * blen, cudaMemcpyHostToDevice, g.stream));
     CK(cudaMemcpyAsync(dsig, sigs96, B * 96, cudaMemcpyHostToDevice, g.stream));
     if (msg_len) CK(cudaMemcpyAsync(dmsg, msgs, B * msg_len, cudaMemcpyHostToDevice, g.stream));
-    agg_verify_device_locked(c, B, dbm, blen, dsig, dmsg, msg_len, dres, g.stream, ar);
+    agg_verify_device_locked(c, B, dbm, blen, dsig, dmsg, msg_len, dres, g.stream, ar, all_messages_equal(msgs, B, msg_len));
     CK(cudaMemcpyAsync(results, dres, B, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
     return 0;
@@ -480,7 +488,7 @@ int hbls_verify_batch(size_t k, const uint8_t* pk48, const uint8_t* sig96, const
     CK(cudaMemcpyAsync(dsig, sig96, k * 96, cudaMemcpyHostToDevice, g.stream));
     if (msg_len) CK(cudaMemcpyAsync(dmsg, msgs, k * msg_len, cudaMemcpyHostToDevice, g.stream));
     LAUNCH(k_g1_decode, blocks_for(k, TPB), TPB, g.stream, k, dpk, v.pkneg, v.ok_pk, 1, 1);
-    launch_verify_tail(k, v, dsig, dmsg, (uint32_t)msg_len, v.ok_pk, dres, g.stream);
+    launch_verify_tail(k, v, dsig, dmsg, (uint32_t)msg_len, v.ok_pk, dres, g.stream, all_messages_equal(msgs, k, msg_len));
     CK(cudaMemcpyAsync(results, dres, k, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
     return 0;

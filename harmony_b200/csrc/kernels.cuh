@@ -153,6 +153,13 @@ __global__ void k_hash_to_g2(size_t n, const uint8_t* msgs, uint32_t msg_len, g2
   }
 }
 
+// same-message batches (the leader's prepare / commit vote collection, consensus/leader.go:127-290: every vote signs
+// the same block hash / commit payload): H(m) is computed once and replicated
+__global__ void k_broadcast_hm(size_t n, g2a* hm, uint8_t* ok) {
+    size_t i = HB_TID; if (i == 0 || i >= n) return;
+    hm[i] = hm[0]; ok[i] = ok[0];
+}
+
 // ---- verification (R7/R8): two Miller loops per round, one thread each:
 //      t even: f = ML(B, sig_j)        t odd: f = ML(-pk_j, H(m_j))
 __global__ void __launch_bounds__(64, HB_MINBLOCKS) k_miller_verify(size_t B, const g2a* sig, const g1a* pk_neg, const g2a* hm, fp12* f) {
@@ -215,8 +222,9 @@ __global__ void __launch_bounds__(HB_TPB_SPLIT, HB_MINBLOCKS_SPLIT) k_pairing_ve
         const fp* h4 = reinterpret_cast<const fp*>(&hm[jj]);
         fp2h q1x, q1y, q2x, q2y;
         q1x.c = s4[role]; q1y.c = s4[2 + role]; q2x.c = h4[role]; q2y.c = h4[2 + role];
-        const bool irregular = (fp2_is_zero(q1x) && fp2_is_zero(q1y)) || (fp2_is_zero(q2x) && fp2_is_zero(q2y)) ||
-                               (fp_is_zero(p2.x) && fp_is_zero(p2.y));
+        // NB: no short-circuit around fp2_is_zero(fp2h) -- it shuffles across the whole warp
+        const bool z1x = fp2_is_zero(q1x), z1y = fp2_is_zero(q1y), z2x = fp2_is_zero(q2x), z2y = fp2_is_zero(q2y);
+        const bool irregular = (z1x & z1y) | (z2x & z2y) | (fp_is_zero(p2.x) & fp_is_zero(p2.y));
         fp12_t<fp2h> m;
         miller_loop2<fp2h>(m, gen, q1x, q1y, p2, q2x, q2y, true, true);
         final_exp(m, m);

@@ -373,9 +373,12 @@ template <class E> HB_DEV void fp12_one(fp12_t<E>& r) {
     fp2_one(r.c0.c0); fp2_zero(r.c0.c1); fp2_zero(r.c0.c2); fp2_zero(r.c1.c0); fp2_zero(r.c1.c1); fp2_zero(r.c1.c2);
 }
 template <class E> HB_DEV bool fp12_is_one(const fp12_t<E>& x) {
+    // every term is evaluated (no short-circuit): for the lane-pair carrier fp2_is_zero contains a full-warp shuffle,
+    // which must be executed by all lanes even when another round in the warp already knows its answer
     E one, d; fp2_one(one); fp2_sub(d, x.c0.c0, one);
-    return fp2_is_zero(d) && fp2_is_zero(x.c0.c1) && fp2_is_zero(x.c0.c2) &&
-           fp2_is_zero(x.c1.c0) && fp2_is_zero(x.c1.c1) && fp2_is_zero(x.c1.c2);
+    const bool z0 = fp2_is_zero(d), z1 = fp2_is_zero(x.c0.c1), z2 = fp2_is_zero(x.c0.c2);
+    const bool z3 = fp2_is_zero(x.c1.c0), z4 = fp2_is_zero(x.c1.c1), z5 = fp2_is_zero(x.c1.c2);
+    return z0 & z1 & z2 & z3 & z4 & z5;
 }
 template <class E> HB_NOINLINE void fp12_mul(fp12_t<E>& r, const fp12_t<E>& x, const fp12_t<E>& y) {
     hb_lockstep2<E>();

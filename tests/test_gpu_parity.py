@@ -347,5 +347,40 @@ def test_full_size_batch_serial_mask_and_lockstep_kernels(gbls):
         if t % 3 == 0: bm[32 * j + 3] ^= 0x10                  # flip one participation bit (add or remove a signer)
         elif t % 3 == 1: mm[48 * j + 20] ^= 0x01               # different block hash
         else: bm[32 * j + 31] ^= 0x02                          # bit 249: last validator
-    res = com.AggregateVerifyBatch(bytes(bm), sigs, bytes(mm), 48)
-    assert [j for j in range(B) if res[j] == 0] == bad
+    sg = bytearray(sigs)
+    extra = {100: "x>=p", 2000: "random", 2001: "random", 30000: "identity", 31000: "zero-msg", B - 1: "x>=p"}
+    for j, kind in extra.items():
+        assert j not in bad
+        if kind == "x>=p": sg[96 * j:96 * j + 96] = b"\xff" * 96
+        elif kind == "random": sg[96 * j:96 * j + 96] = bytes([(7 * j + 13 * t) & 0xff for t in range(95)] + [0x05])
+        elif kind == "identity": sg[96 * j:96 * j + 96] = bytes(96)
+        elif kind == "zero-msg": mm[48 * j:48 * j + 48] = bytes(48)
+    res = com.AggregateVerifyBatch(bytes(bm), bytes(sg), bytes(mm), 48)
+    got = {j for j in range(B) if res[j] != 1}; exp = set(bad) | set(extra)
+    assert got == exp, ("unexpected rejects", sorted(got - exp)[:10], "unexpected accepts", sorted(exp - got)[:10], len(got))
+
+def test_leader_vote_collection_same_message(gbls, oracle):
+    """R9 (consensus/leader.go:227-290 onCommit loop): 250 validators each send an individual signature on the SAME
+    commit payload; the leader verifies every vote.  One device call (bitmap with a single bit per vote, H(m) computed
+    once); a multi-key vote (two bits, aggregated signature: leader.go:283 signerPubKey.Add) and two bad votes included."""
+    n = 250
+    sks = _committee("c2", n)
+    pks_blob = gbls.GetPublicKeyBatch(b"".join(wl.sk_bytes(k) for k in sks))
+    pks = [pks_blob[48 * i:48 * i + 48] for i in range(n)]
+    com = gbls.Committee(pks)
+    msg = wl.commit_payload("leader", 1)
+    sigs_blob, ok = gbls.SignHashBatch(b"".join(wl.sk_bytes(k) for k in sks), msg * n, 48)
+    sigs = [bytearray(sigs_blob[96 * i:96 * i + 96]) for i in range(n)]
+    bms = []
+    for i in range(n):
+        bm = bytearray(32); bm[i >> 3] |= 1 << (i & 7); bms.append(bm)
+    # vote 7 is a multi-key vote: keys 7 and 8 signed, signatures aggregated by the sender
+    sigs[7] = bytearray(oracle.aggregate_sigs([bytes(sigs[7]), bytes(sigs[8])])); bms[7][1] |= 1
+    sigs[30] = bytearray(sigs_blob[96 * 31:96 * 32])            # someone else's signature
+    bms[99][0] |= 1                                            # claims an extra signer
+    res = com.AggregateVerifyBatch(b"".join(bytes(b) for b in bms), b"".join(bytes(s) for s in sigs), msg * n, 48)
+    assert [i for i in range(n) if res[i] == 0] == [30, 99]
+    assert oracle.verify_hash(bytes(sigs[5]), pks[5], msg) and not oracle.verify_hash(bytes(sigs[30]), pks[30], msg)
+    # same votes as independent (pk, msg, sig) triples
+    res2 = gbls.VerifyBatch(b"".join(pks[:40]), b"".join(bytes(s) for s in sigs[:40]), msg * 40, 48)
+    assert [i for i in range(40) if res2[i] == 0] == [7, 30]    # vote 7 only verifies against pk7 + pk8
