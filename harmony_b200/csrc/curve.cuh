@@ -249,7 +249,10 @@ HB_NOINLINE bool sw_map_g2(g2& r, const fp2& t) {
     if (fp2_is_zero(t)) return false;
     fp n, c1, c2, one; fp2 w, x, y, g, bb;
     fp_set(c1, K_SW_C1); fp_set(c2, K_SW_C2); fp_one(one); fp2_const(bb, K_B2);
-    fp2_norm(n, t); bool negative = fp_legendre(n) < 0;
+    // negative = Legendre(N(t)) < 0.  SignHash / VerifyHash always map t = (t0, 0): N(t) = t0^2 is a square, so the
+    // exponentiation is skipped for them (uniform branch); the general case keeps mcl's rule.
+    bool negative = false;
+    if (!fp_is_zero(t.b)) { fp2_norm(n, t); negative = fp_legendre(n) < 0; }
     // Same candidates and same "first x_i with x_i^3 + b square" rule as mcl, but with warp-uniform control flow:
     // one shared inversion (u * c1 t)^-1 yields both w and 1/w, squareness of g(x_1), g(x_2) is decided by the
     // Legendre symbol of the Fp2 norm, and only ONE Fp2 square root (of the selected candidate) is taken.

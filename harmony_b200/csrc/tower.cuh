@@ -93,6 +93,13 @@ HB_DEV bool fp_sqrt(fp& r, const fp& a) {
     if (!fp_eq(y2, a)) return false;
     r = y; return true;
 }
+// one exponentiation for BOTH the square root and its inverse: u = a^((p-3)/4) => a*u = a^((p+1)/4) (exactly the
+// candidate mcl's Fp::squareRoot produces) and, when a is a square, u = 1/sqrt(a).  false iff a is a non-residue.
+HB_DEV bool fp_sqrt_inv(fp& root, fp& inv_root, const fp& a) {
+    fp u, c, c2; fp_pow(u, a, K_P_MINUS_3_DIV_4); fp_mul(c, u, a); fp_sqr(c2, c);
+    if (!fp_eq(c2, a)) return false;
+    root = c; inv_root = u; return true;
+}
 HB_DEV int fp_legendre(const fp& a) {
     if (fp_is_zero(a)) return 0;
     fp t, one; fp_pow(t, a, K_P_MINUS_1_DIV_2); fp_one(one);
@@ -184,14 +191,14 @@ HB_NOINLINE bool fp2_sqrt(fp2& r, const fp2& x) {
     fp2_norm(t1, x);
     if (!fp_sqrt(t1, t1)) return false;
     fp_set(inv2, K_INV2);
+    fp c, ci;
     fp_add(t2, x.a, t1); fp_mul(t2, t2, inv2);
-    if (!fp_sqrt(t2, t2)) {
+    if (!fp_sqrt_inv(c, ci, t2)) {
         fp_sub(t2, x.a, t1); fp_mul(t2, t2, inv2);
-        if (!fp_sqrt(t2, t2)) return false;
+        if (!fp_sqrt_inv(c, ci, t2)) return false;
     }
-    fp c = t2;
-    fp_dbl(t2, t2); fp_inv(t2, t2);
-    fp_mul(r.b, x.b, t2); r.a = c;
+    // y.b = b / (2c) = b * (1/c) * (1/2): the inverse came with the root, no second exponentiation
+    fp_mul(t2, x.b, ci); fp_mul(r.b, t2, inv2); r.a = c;
     return true;
 }
 
@@ -380,6 +387,22 @@ template <class E> HB_DEV bool fp12_is_one(const fp12_t<E>& x) {
     const bool z3 = fp2_is_zero(x.c1.c0), z4 = fp2_is_zero(x.c1.c1), z5 = fp2_is_zero(x.c1.c2);
     return z0 & z1 & z2 & z3 & z4 & z5;
 }
+#ifndef HB_HOST_EMU
+// lane-pair carrier: each lane tests its own six components, ONE shuffle combines the pair's verdicts
+HB_DEV bool fp12_is_one(const fp12_t<fp2h>& x) {
+    fp one; fp_one(one);
+    const bool re = fp2h_role() == 0;
+    uint32_t acc = 0;
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+        acc |= x.c0.c0.c.l[j] ^ (re ? one.l[j] : 0u);
+        acc |= x.c0.c1.c.l[j] | x.c0.c2.c.l[j] | x.c1.c0.c.l[j] | x.c1.c1.c.l[j] | x.c1.c2.c.l[j];
+    }
+    const int mine = acc == 0;
+    const int other = __shfl_xor_sync(0xffffffffu, mine, 1);
+    return mine && other;
+}
+#endif
 template <class E> HB_NOINLINE void fp12_mul(fp12_t<E>& r, const fp12_t<E>& x, const fp12_t<E>& y) {
     hb_lockstep2<E>();
     fp6_t<E> v0, v1, s, t;
