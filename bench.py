@@ -235,6 +235,19 @@ def run_gpu(args):
         rc = L.hbls_aggregate_verify_batch(com.h, 1, h_bm.data_ptr(), blen, h_sig.data_ptr(), h_msg.data_ptr(), MSG_LEN, h_res.data_ptr())
         lat.append((time.perf_counter() - t0) * 1e3)
     single_round_ms = float(np.median(lat))
+    # informational: the leader's commit-phase vote collection (R9, consensus/leader.go:227-290): 250 individual
+    # signatures on ONE payload, one device call (single-bit bitmaps; H(m) computed once)
+    vmsg = msgs[:MSG_LEN]
+    vsigs, vok = bls.SignHashBatch(b"".join(wl.sk_bytes(k) for k in sks), vmsg * N_COMMITTEE, MSG_LEN)
+    vbm = bytearray(N_COMMITTEE * blen)
+    for i in range(N_COMMITTEE): vbm[i * blen + (i >> 3)] |= 1 << (i & 7)
+    vlat = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        vres = com.AggregateVerifyBatch(bytes(vbm), vsigs, vmsg * N_COMMITTEE, MSG_LEN)
+        vlat.append((time.perf_counter() - t0) * 1e3)
+    assert vres == b"\x01" * N_COMMITTEE
+    votes250_ms = float(np.median(vlat))
 
     from harmony_b200 import shard
     dev_ms_max, e2e_ms_max, nsig_total = shard.reduce_step_stats(dev_ms, e2e_s * 1e3, float(nsig), device="cuda")
@@ -294,7 +307,7 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": "sigs/s", "h2d_bytes_per_step": B * (blen + 96 + MSG_LEN), "d2h_bytes_per_step": B,
                     "ms_per_step": e2e_ms_max / args.steps, "api": "hbls_aggregate_verify_batch (pinned host buffers)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "wall_s_timed_region": t_wall,
-            "single_round_latency_ms": single_round_ms}
+            "single_round_latency_ms": single_round_ms, "leader_250_votes_same_msg_latency_ms": votes250_ms}
     if cpu: line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
     if world > 1: dist.destroy_process_group()

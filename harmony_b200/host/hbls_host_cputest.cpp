@@ -1,0 +1,39 @@
+// harmony_b200/host/hbls_host_cputest.cpp -- CPU-only checks of the host mirror's non-arithmetic logic (no GPU needed):
+// hex codecs, commit payload bytes (consensus/signature/signature_test.go), sig||bitmap parsing (internal/chain/sig.go,
+// crypto/bls/bls.go:120-136), quorum threshold / popcount (quorum.go:409-411, one-node-one-vote.go:57-72), the 1024-entry
+// public-key LRU (crypto/bls/mask.go:35-55), and that every group operation refuses to run without blsInit (no CPU fallback).
+#include <cstdio>
+#include "hbls_host.hpp"
+using namespace harmony;
+static int g_fail = 0;
+#define CHECK(c) do { if (!(c)) { fprintf(stderr, "CHECK FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); g_fail++; } } while (0)
+int main() {
+    std::vector<uint8_t> b; CHECK(bls_core::unhex("00ff10Ab", b) && b == std::vector<uint8_t>({0x00, 0xff, 0x10, 0xab}));
+    CHECK(!bls_core::unhex("0", b) && !bls_core::unhex("zz", b));
+    CHECK(bls_core::hex(b.data(), 4) == "00ff10ab");
+    std::array<uint8_t, 32> h; for (int i = 0; i < 32; i++) h[i] = (uint8_t)(0xa0 + i);
+    auto p = signature::ConstructCommitPayload(true, h, 0x0102030405060708ull, 0x1112131415161718ull);
+    CHECK(p.size() == 48 && p[0] == 0x08 && p[7] == 0x01 && p[8] == 0xa0 && p[39] == 0xbf && p[40] == 0x18 && p[47] == 0x11);
+    CHECK(signature::ConstructCommitPayload(false, h, 7, 9).size() == 40);
+    std::vector<uint8_t> payload(96 + 32, 0); payload[0] = 1; payload[96] = 0xfe; payload[127] = 0x03;
+    bls::SerializedSignature s96; std::vector<uint8_t> bm;
+    CHECK(chain::ParseCommitSigAndBitmap(payload, s96, bm) && s96[0] == 1 && bm.size() == 32 && bm[0] == 0xfe && bm[31] == 0x03);
+    CHECK(!chain::ParseCommitSigAndBitmap(std::vector<uint8_t>(95), s96, bm));
+    std::vector<uint8_t> a, m; CHECK(bls::SeparateSigAndMask(payload, a, m) && a.size() == 96 && m == bm);
+    CHECK(!bls::SeparateSigAndMask(std::vector<uint8_t>(10), a, m));
+    CHECK(quorum::TwoThirdsSignersCount(250) == 167 && quorum::TwoThirdsSignersCount(4) == 3 && quorum::TwoThirdsSignersCount(1000) == 667);
+    CHECK(quorum::CountOneBits({0xff, 0x01, 0x80}) == 10);
+    bls::PubKeyCache cache(3); bls_core::PublicKey pk{}; pk.v.d[0] = 1;
+    cache.Add("a", pk); pk.v.d[0] = 2; cache.Add("b", pk); pk.v.d[0] = 3; cache.Add("c", pk);
+    bls_core::PublicKey out{}; CHECK(cache.Get("a", out) && out.v.d[0] == 1);          // "a" becomes most recent
+    pk.v.d[0] = 4; cache.Add("d", pk);                                                   // evicts "b"
+    CHECK(cache.Len() == 3 && !cache.Get("b", out) && cache.Get("c", out) && cache.Get("d", out) && out.v.d[0] == 4);
+    std::vector<uint8_t> o; CHECK(bls::AggregateMasks({1, 2}, {4, 2}, o) && o == std::vector<uint8_t>({5, 2}) && !bls::AggregateMasks({1}, {1, 2}, o));
+    bls::SerializedPublicKey z{}; CHECK(bls::IsEmpty(z) && bls::Hex(z).size() == 96);
+    // no CPU fallback: without blsInit (no device here) group operations fail instead of computing on the host
+    bls_core::PublicKey q{}; std::vector<uint8_t> k48(48, 0); k48[0] = 1;
+    CHECK(!q.Deserialize(k48));
+    CHECK(hbls_kernel_launch_count() == 0);
+    if (g_fail) { fprintf(stderr, "%d check(s) failed\n", g_fail); return 1; }
+    printf("hbls_host_cputest: all checks passed\n"); return 0;
+}

@@ -34,3 +34,15 @@ def test_no_cpu_fallback_without_gpu():
 def test_struct_sizes_match_herumi():
     from harmony_b200 import bls
     assert ctypes.sizeof(bls._Sec) == 32 and ctypes.sizeof(bls._Pub) == 144 and ctypes.sizeof(bls._Sig) == 288
+
+def test_cpp_host_mirror_cpu_logic():
+    """Pure-host parts of the C++ mirror (payload bytes, sig||bitmap parsing, quorum threshold, LRU) on the CPU; the binary
+    links libhbls.so but never initialises it."""
+    import subprocess
+    from harmony_b200 import build
+    build.build_cuda()
+    hd = os.path.join(ROOT, "harmony_b200", "host"); exe = os.path.join(build.LIBDIR, "hbls_host_cputest")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(hd, "hbls_host_cputest.cpp"),
+                           "-L" + build.LIBDIR, "-lhbls", "-Wl,-rpath,$ORIGIN", "-pthread", "-ldl", "-lrt"])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60, env={**os.environ, "CUDA_VISIBLE_DEVICES": ""})
+    assert r.returncode == 0 and "all checks passed" in r.stdout, r.stdout + r.stderr
