@@ -84,6 +84,7 @@ def lib():
         sig("hbls_kernel_launch_count", c.c_uint64)
         sig("hbls_probe_mac32_per_s", c.c_double, c.c_int)
         sig("hbls_selftest_split", c.c_int, c.c_uint32)
+        sig("hbls_set_batch_mode", None, c.c_int)
         sig("hbls_stage_timing_enable", None, c.c_int)
         sig("hbls_stage_timing_get", c.c_int, c.POINTER(c.c_float), c.c_int)
         _lib = L
@@ -361,6 +362,7 @@ def ConstructCommitPayload(is_staking: bool, block_hash: bytes, block_num: int, 
     return out
 
 def SelfTestSplit(iters: int = 16) -> int: return int(_need().hbls_selftest_split(iters))
+def SetBatchMode(mode: int): lib().hbls_set_batch_mode(int(mode))
 def KernelLaunchCount() -> int: return int(lib().hbls_kernel_launch_count())
 def ProbeMac32PerS(iters: int = 4096) -> float: return float(_need().hbls_probe_mac32_per_s(iters))
 

@@ -142,6 +142,18 @@ template <class F> HB_NOINLINE void pt_mul_zabs(jac<F>& r, const jac<F>& p) {
     r = acc;
 }
 
+// r = [k]p for a 64-bit k (random-linear-combination coefficients): plain MSB-first double-and-add
+template <class F> HB_NOINLINE void pt_mul_u64(jac<F>& r, const jac<F>& p, uint64_t k) {
+    jac<F> acc; pt_set_inf(acc);
+    for (int i = 63; i >= 0; i--) { pt_dbl(acc, acc); if ((k >> i) & 1) pt_add(acc, acc, p); }
+    r = acc;
+}
+template <class F> HB_NOINLINE void pt_mul_u64_aff(jac<F>& r, const aff<F>& p, uint64_t k) {
+    jac<F> acc; pt_set_inf(acc);
+    for (int i = 63; i >= 0; i--) { pt_dbl(acc, acc); if ((k >> i) & 1) pt_add_mixed(acc, acc, p); }
+    r = acc;
+}
+
 HB_DEV void g1_generator(g1& r) { fp_set(r.x, K_G1_X); fp_set(r.y, K_G1_Y); fp_one(r.z); }
 
 // ------------------------------------------------------------------ endomorphisms and subgroup membership

@@ -25,6 +25,8 @@ struct Ctx {
     uint8_t* pinned = nullptr; size_t pinned_cap = 0;       // host staging (pinned)
     std::atomic<uint64_t> launches{0};
     bool stage_timing = false; bool stage_valid = false;
+    int batch_mode = 1;                                     // 1: random-linear-combination groups + exact fallback, 0: exact per round
+    uint64_t rlc_seed[2] = {0, 0}; uint64_t rlc_calls = 0;
     cudaEvent_t ev[8] = {};
 };
 Ctx g;
@@ -95,18 +97,21 @@ unsigned split_blocks(size_t nthreads) {
 // ------------------------------------------------------------------ one verification pass over device-resident inputs.
 // pk_neg: affine -apk (or -pk) per round; sig/hm decoded inside.  arena must hold verify_scratch_bytes(B).
 size_t verify_scratch_bytes(size_t B) {
-    return B * (sizeof(g2a) * 2 + sizeof(g1a) + sizeof(g1) + sizeof(fp12) * 2 + 8) + 16 * 256;
+    return B * (sizeof(g2a) * 2 + sizeof(g1a) * 2 + sizeof(g1) + sizeof(g2) + sizeof(fp12) * 2 + 16) + (B / HB_RLC_G + 1) * (sizeof(g2a) + 8) + 32 * 256;
 }
-struct VerifyBufs { g2a* sig; g2a* hm; g1a* pkneg; g1* apk; fp12* f; uint8_t* ok_sig; uint8_t* ok_hm; uint8_t* ok_pk; };
+struct VerifyBufs { g2a* sig; g2a* hm; g1a* pkneg; g1* apk; fp12* f; uint8_t* ok_sig; uint8_t* ok_hm; uint8_t* ok_pk;
+                    g1a* pk_scaled; g2* S; uint8_t* bad; g2a* Sg; uint8_t* group_ok; int* any_fail; };
 VerifyBufs carve_verify(Arena& ar, size_t B) {
     VerifyBufs v;
     v.sig = ar.take<g2a>(B); v.hm = ar.take<g2a>(B); v.pkneg = ar.take<g1a>(B); v.apk = ar.take<g1>(B);
     v.f = ar.take<fp12>(2 * B); v.ok_sig = ar.take<uint8_t>(B); v.ok_hm = ar.take<uint8_t>(B); v.ok_pk = ar.take<uint8_t>(B);
+    v.pk_scaled = ar.take<g1a>(B); v.S = ar.take<g2>(B); v.bad = ar.take<uint8_t>(B);
+    v.Sg = ar.take<g2a>(B / HB_RLC_G + 1); v.group_ok = ar.take<uint8_t>(B / HB_RLC_G + 1); v.any_fail = ar.take<int>(1);
     return v;
 }
 #define STAGE_EV(i, strm) do { if (g.stage_timing) cudaEventRecord(g.ev[i], (strm)); } while (0)
 void launch_verify_tail(size_t B, const VerifyBufs& v, const uint8_t* d_sig96, const uint8_t* d_msgs, uint32_t msg_len,
-                        const uint8_t* ok_pk, uint8_t* d_results, cudaStream_t s, bool same_msg = false) {
+                        const uint8_t* ok_pk, uint8_t* d_results, cudaStream_t s, bool same_msg = false, const g1* apk_jac = nullptr) {
     STAGE_EV(2, s);
     LAUNCH(k_g2_decode, heavy_blocks(B), TPB, s, B, d_sig96, v.sig, v.ok_sig, 1);
     STAGE_EV(3, s);
@@ -119,15 +124,41 @@ void launch_verify_tail(size_t B, const VerifyBufs& v, const uint8_t* d_sig96, c
     static const int fuse_mode = [] { const char* e = getenv("HBLS_FUSE"); return e ? atoi(e) : -1; }();   // -1 auto, 0 split, 1 fused
     const bool fused = fuse_mode == 1 || (fuse_mode == -1 && B >= (size_t)g.sm_count * 256);
     static const int split_mode = [] { const char* e = getenv("HBLS_SPLIT"); return e ? atoi(e) : 1; }();                // lane-pair pairing kernel
-    if (split_mode) {
+    static const int rlc_env = [] { const char* e = getenv("HBLS_RLC"); return e ? atoi(e) : 1; }();
+    static const size_t rlc_min = [] { const char* e = getenv("HBLS_RLC_MIN"); return e ? (size_t)atol(e) : (size_t)1024; }();
+    if (split_mode && rlc_env && g.batch_mode == 1 && apk_jac && B >= rlc_min) {
+        // batched form (north-star "batched Miller loop + shared final exponentiation"): groups of HB_RLC_G rounds
+        const size_t ng = B / HB_RLC_G, nr = ng * HB_RLC_G, tail = B - nr;
+        const uint64_t s0 = g.rlc_seed[0] + 0x9e3779b97f4a7c15ull * (++g.rlc_calls), s1 = g.rlc_seed[1] ^ (g.rlc_calls << 32);
+        cudaMemsetAsync(v.any_fail, 0, sizeof(int), s);
+        LAUNCH(k_rlc_scale, heavy_blocks(nr), TPB, s, nr, ng, apk_jac, v.sig, v.hm, v.ok_sig, v.ok_hm, s0, s1, v.pk_scaled, v.S, v.bad);
+        LAUNCH(k_rlc_group_sum, heavy_blocks(ng), TPB, s, ng, v.S, v.Sg);
+        STAGE_EV(5, s);
+        if (2 * ng >= (size_t)g.sm_count * HB_TPB_SPLIT)
+            LAUNCH(k_rlc_pairing_split, split_blocks(2 * ng), HB_TPB_SPLIT, s, ng, v.pk_scaled, v.hm, v.Sg, v.bad, v.group_ok);
+        else
+            LAUNCH(k_rlc_pairing_split, blocks_for(2 * ng, 64), 64, s, ng, v.pk_scaled, v.hm, v.Sg, v.bad, v.group_ok);
+        LAUNCH(k_rlc_finish, blocks_for(nr, 256), 256, s, nr, ng, v.group_ok, d_results, v.any_fail);
+        // exact per-round pass: returns immediately unless a group failed (then every round is recomputed exactly)
+        if (2 * B >= (size_t)g.sm_count * HB_TPB_SPLIT)
+            LAUNCH(k_pairing_verify_split, split_blocks(2 * B), HB_TPB_SPLIT, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results, v.any_fail);
+        else
+            LAUNCH(k_pairing_verify_split, blocks_for(2 * B, 64), 64, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results, v.any_fail);
+        LAUNCH(k_pairing_fixup, heavy_blocks(B), TPB, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results, v.any_fail);
+        if (tail) {       // the < G rounds that do not fill a group are always verified exactly
+            LAUNCH(k_pairing_verify_split, blocks_for(2 * tail, 64), 64, s, tail, v.sig + nr, v.pkneg + nr, v.hm + nr, v.ok_sig + nr, v.ok_hm + nr,
+                   (const uint8_t*)nullptr, d_results + nr, (const int*)nullptr);
+            LAUNCH(k_pairing_fixup, 1, TPB, s, tail, v.sig + nr, v.pkneg + nr, v.hm + nr, v.ok_sig + nr, v.ok_hm + nr, (const uint8_t*)nullptr, d_results + nr, (const int*)nullptr);
+        }
+    } else if (split_mode) {
         // default at every batch size: a lane pair per round (half the per-thread state, half the single-round latency).
         // Large batches use 512-thread lock-stepped CTAs (one per SM); small ones 64-thread CTAs spread over the SMs.
         STAGE_EV(5, s);
         if (2 * B >= (size_t)g.sm_count * HB_TPB_SPLIT)
-            LAUNCH(k_pairing_verify_split, split_blocks(2 * B), HB_TPB_SPLIT, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
+            LAUNCH(k_pairing_verify_split, split_blocks(2 * B), HB_TPB_SPLIT, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results, (const int*)nullptr);
         else
-            LAUNCH(k_pairing_verify_split, blocks_for(2 * B, 64), 64, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
-        LAUNCH(k_pairing_fixup, heavy_blocks(B), TPB, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
+            LAUNCH(k_pairing_verify_split, blocks_for(2 * B, 64), 64, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results, (const int*)nullptr);
+        LAUNCH(k_pairing_fixup, heavy_blocks(B), TPB, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results, (const int*)nullptr);
     } else if (fused) {
         // batch alone fills the chip: one thread per round, 2-pair loop with shared squarings + final exponentiation
         STAGE_EV(5, s);
@@ -235,6 +266,8 @@ int hbls_init_device(int device) {
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
     g.device = device; g.sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    { FILE* f = fopen("/dev/urandom", "rb"); if (!f || fread(g.rlc_seed, 1, 16, f) != 16) { if (f) fclose(f); fprintf(stderr, "[hbls] cannot read /dev/urandom\n"); return HBLS_ERR_CUDA; } fclose(f); }
+    cudaFuncSetAttribute(k_rlc_pairing_split, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     // the heavy kernels keep their Fp12 temporaries in per-thread local memory: give L1 the whole 228 KB
     cudaFuncSetAttribute(k_miller_verify, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_final_verify, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
@@ -253,6 +286,7 @@ int blsInit(int curve, int compiledTimeVar) {
     return hbls_init_device(d ? atoi(d) : 0);
 }
 uint64_t hbls_kernel_launch_count(void) { return g.launches.load(); }
+void hbls_set_batch_mode(int mode) { std::lock_guard<std::mutex> lk(g.mu); g.batch_mode = mode ? 1 : 0; }
 
 // ------------------------------------------------------------------ secret keys (host bytes; no group arithmetic)
 int blsSecretKeySetByCSPRNG(blsSecretKey* sec) {
@@ -333,8 +367,8 @@ int blsVerifyHash(const blsSignature* sig, const blsPublicKey* pub, const void* 
     LAUNCH(k_g1_normalize, 1, 32, g.stream, (size_t)1, v.apk, v.pkneg, 1);
     LAUNCH(k_g2_normalize, 1, 32, g.stream, (size_t)1, dsig, v.sig);
     LAUNCH(k_hash_to_g2, 1, 32, g.stream, (size_t)1, dmsg, (uint32_t)size, v.hm, v.ok_hm);
-    LAUNCH(k_pairing_verify_split, 1, 64, g.stream, (size_t)1, v.sig, v.pkneg, v.hm, (const uint8_t*)v.ok_hm, (const uint8_t*)nullptr, (const uint8_t*)nullptr, dres);
-    LAUNCH(k_pairing_fixup, 1, 32, g.stream, (size_t)1, v.sig, v.pkneg, v.hm, (const uint8_t*)v.ok_hm, (const uint8_t*)nullptr, (const uint8_t*)nullptr, dres);
+    LAUNCH(k_pairing_verify_split, 1, 64, g.stream, (size_t)1, v.sig, v.pkneg, v.hm, (const uint8_t*)v.ok_hm, (const uint8_t*)nullptr, (const uint8_t*)nullptr, dres, (const int*)nullptr);
+    LAUNCH(k_pairing_fixup, 1, 32, g.stream, (size_t)1, v.sig, v.pkneg, v.hm, (const uint8_t*)v.ok_hm, (const uint8_t*)nullptr, (const uint8_t*)nullptr, dres, (const int*)nullptr);
     uint8_t res = 0;
     cudaMemcpyAsync(&res, dres, 1, cudaMemcpyDeviceToHost, g.stream);
     if (cudaStreamSynchronize(g.stream) != cudaSuccess) return 0;
@@ -430,7 +464,7 @@ static int agg_verify_device_locked(const hbls_committee* c, size_t B, const uin
         LAUNCH(k_mask_aggregate, blocks_for(B * 32, 128), 128, s, B, c->n, c->table, d_bitmaps, blen, v.apk);
     STAGE_EV(1, s);
     LAUNCH(k_g1_normalize, blocks_for(B, TPB), TPB, s, B, v.apk, v.pkneg, 1);
-    launch_verify_tail(B, v, d_sigs, d_msgs, (uint32_t)msg_len, nullptr, d_results, s, same_msg);
+    launch_verify_tail(B, v, d_sigs, d_msgs, (uint32_t)msg_len, nullptr, d_results, s, same_msg, v.apk);
     if (g.stage_timing) g.stage_valid = true;
     return 0;
 }

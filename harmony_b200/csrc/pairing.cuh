@@ -86,6 +86,29 @@ template <class E> HB_NOINLINE void miller_loop2(fp12_t<E>& f, const g1a& p1, co
 HB_DEV void miller_loop2(fp12& f, const g1a& p1, const g2a& q1, const g1a& p2, const g2a& q2) {
     miller_loop2<fp2>(f, p1, q1.x, q1.y, p2, q2.x, q2.y, !(aff_is_inf(p1) || aff_is_inf(q1)), !(aff_is_inf(p2) || aff_is_inf(q2)));
 }
+// NP pairs at once with ONE shared accumulator: f = prod_k f_{|z|,Q_k}(P_k).  Used by the random-linear-combination
+// batch: rounds of a group contribute (-r_j apk_j, H(m_j)), the last pair is (B, sum_j r_j sigma_j).  P_k / Q_k stay in
+// global memory (read again at the five addition steps); only the running points T_k live in the thread.
+template <class E, int NP> HB_NOINLINE void miller_loop_multi(fp12_t<E>& f, const g1a* const* ps, const E* qx, const E* qy) {
+    fp12_one(f);
+    g2proj_t<E> T[NP];
+    for (int k = 0; k < NP; k++) { T[k].x = qx[k]; T[k].y = qy[k]; fp2_one(T[k].z); }
+    E l0, l2, l3;
+    for (int i = 62; i >= 0; i--) {
+        hb_lockstep<E>();
+        fp12_sqr(f, f);
+        for (int k = 0; k < NP; k++) {
+            const fp px = ps[k]->x, py = ps[k]->y;          // staged into thread-local storage: field routines take local operands
+            ml_dbl(T[k], l0, l2, l3); fp2_mul_fp(l2, l2, px); fp2_mul_fp(l3, l3, py); fp12_mul_by_014(f, f, l0, l2, l3);
+        }
+        if ((K_Z_ABS >> i) & 1) {
+            for (int k = 0; k < NP; k++) {
+                const fp px = ps[k]->x, py = ps[k]->y;
+                ml_add(T[k], qx[k], qy[k], l0, l2, l3); fp2_mul_fp(l2, l2, px); fp2_mul_fp(l3, l3, py); fp12_mul_by_014(f, f, l0, l2, l3);
+            }
+        }
+    }
+}
 // r = f^(3 (p^12 - 1) / r): easy part, then (z-1)^2 (z+p) (z^2+p^2-1) + 3
 template <class E> HB_NOINLINE void final_exp(fp12_t<E>& r, const fp12_t<E>& f) {
     fp12_t<E> t0, t1, t2, m;

@@ -97,6 +97,13 @@ int hbls_aggregate_verify(const hbls_committee* c, const uint8_t* bitmap, size_t
  * bitmaps: B*blen bytes; sigs96: B*96; msgs: B*msg_len (msg_len <= 64); results[j] = 1/0. */
 int hbls_aggregate_verify_batch(const hbls_committee* c, size_t B, const uint8_t* bitmaps, size_t blen,
                                 const uint8_t* sigs96, const uint8_t* msgs, size_t msg_len, uint8_t* results);
+/* How the two batch entries above check the pairing equations.
+ * mode 1 (default): random-linear-combination groups -- 4 rounds share one Miller accumulator and one final exponentiation
+ *   (prod_j [e(B, sigma_j) e(-apk_j, H_j)]^{r_j} == 1, fresh 64-bit r_j per call); if any group fails or holds an undecodable
+ *   round, every round is recomputed exactly, so results are the exact booleans (a bad round survives the batched test
+ *   with probability 2^-64).  Batches under 1024 rounds always use mode 0.
+ * mode 0: the exact per-round check only (identical semantics to N calls of hbls_aggregate_verify). */
+void hbls_set_batch_mode(int mode);
 /* same, every pointer already in device memory (HBM); stream = cudaStream_t or NULL; asynchronous on that stream */
 int hbls_aggregate_verify_batch_device(const hbls_committee* c, size_t B, const void* d_bitmaps, size_t blen,
                                        const void* d_sigs96, const void* d_msgs, size_t msg_len,

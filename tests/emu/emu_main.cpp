@@ -35,3 +35,21 @@ extern "C" void emu_mul_wide2(const uint8_t* a1, const uint8_t* b1, const uint8_
     mul_wide2(T, A1, B1, A2, B2); store_words(out96, T, 24);
 }
 extern "C" void emu_sqr_wide_redc(const uint8_t* a, uint8_t* out96) { uint32_t A[12], T[24]; load_words(A, a, 12); sqr_wide(T, A); store_words(out96, T, 24); }
+// random-linear-combination group check (the math of k_rlc_scale / k_rlc_group_sum / k_rlc_pairing_split with the fp2 carrier):
+// 7 (pk, sig, msg) rounds + coefficients r -> prod_j e(-r_j pk_j, H_j) * e(B, sum r_j sig_j) == 1 ?
+extern "C" int emu_rlc_group(const uint8_t* pks48, const uint8_t* sigs96, const uint8_t* msgs, uint32_t len, const uint64_t* r) {
+    const int G = 7;
+    static g1a P[G + 1]; fp2 qx[G + 1], qy[G + 1]; const g1a* ps[G + 1];
+    g2 acc; pt_set_inf(acc);
+    for (int k = 0; k < G; k++) {
+        g1 pk; g2 sg, h;
+        if (!g1_deserialize(pk, pks48 + 48 * k, true) || !g2_deserialize(sg, sigs96 + 96 * k, true) || !map_to_g2(h, msgs + len * k, len)) return -1;
+        g1 rp; pt_mul_u64(rp, pk, r[k]); pt_to_aff(P[k], rp); fp_neg(P[k].y, P[k].y);
+        g2a sa; pt_to_aff(sa, sg); g2 rs; pt_mul_u64_aff(rs, sa, r[k]); pt_add(acc, acc, rs);
+        g2a ha; pt_to_aff(ha, h); qx[k] = ha.x; qy[k] = ha.y; ps[k] = &P[k];
+    }
+    g2a sga; pt_to_aff(sga, acc); qx[G] = sga.x; qy[G] = sga.y;
+    fp_set(P[G].x, K_G1_X); fp_set(P[G].y, K_G1_Y); ps[G] = &P[G];
+    fp12 m; miller_loop_multi<fp2, G + 1>(m, ps, qx, qy); final_exp(m, m);
+    return fp12_is_one(m) ? 1 : 0;
+}

@@ -74,3 +74,29 @@ def test_emu_wide_products(emu):
         assert int.from_bytes(o.raw, "little") == a1 * b1 + a2 * b2
     for a in [c[0] for c in cases] + [M, P, 2 * P - 1]:
         emu.emu_sqr_wide_redc(b48(a), o); assert int.from_bytes(o.raw, "little") == a * a
+
+def test_emu_rlc_group(emu, oracle):
+    """Random-linear-combination group check (7 rounds, one shared Miller accumulator + one final exponentiation):
+    accepts honest rounds for any coefficients, rejects when one round's signature or message is wrong."""
+    from harmony_b200 import workload as wl
+    G = 7
+    sks = [wl.sk_bytes(wl.seeded_sk("rlc", i)) for i in range(G)]
+    pks = [oracle.get_public_key(s) for s in sks]
+    msgs = [wl.commit_payload("rlc", i) for i in range(G)]
+    sigs = [oracle.sign_hash(s, m) for s, m in zip(sks, msgs)]
+    rng = random.Random(31)
+    r = (ctypes.c_uint64 * G)(*[rng.getrandbits(64) | 1 for _ in range(G)])
+    assert emu.emu_rlc_group(b"".join(pks), b"".join(sigs), b"".join(msgs), 48, r) == 1
+    bad_sigs = list(sigs); bad_sigs[3] = sigs[4]
+    assert emu.emu_rlc_group(b"".join(pks), b"".join(bad_sigs), b"".join(msgs), 48, r) == 0
+    bad_msgs = list(msgs); bad_msgs[6] = bytes([msgs[6][0] ^ 1]) + msgs[6][1:]
+    assert emu.emu_rlc_group(b"".join(pks), b"".join(sigs), b"".join(bad_msgs), 48, r) == 0
+    # two wrong rounds that would cancel WITHOUT random coefficients (sig_a + d, sig_b - d): still rejected
+    r1 = (ctypes.c_uint64 * G)(*[1] * G)
+    d = oracle.sign_hash(wl.sk_bytes(12345), b"delta" * 8)
+    import sys, os
+    sys.path.insert(0, os.path.join(ROOT, "oracle")); import pyref as o
+    D = o.g2_deserialize(d); A = o.g2_deserialize(sigs[0]); Bp = o.g2_deserialize(sigs[1])
+    forged = list(sigs); forged[0] = o.g2_serialize(o.pt_add(o.FP2, A, D)); forged[1] = o.g2_serialize(o.pt_sub(o.FP2, Bp, D))
+    assert emu.emu_rlc_group(b"".join(pks), b"".join(forged), b"".join(msgs), 48, r1) == 1      # unit coefficients are fooled ...
+    assert emu.emu_rlc_group(b"".join(pks), b"".join(forged), b"".join(msgs), 48, r) == 0       # ... random ones are not

@@ -384,3 +384,29 @@ def test_leader_vote_collection_same_message(gbls, oracle):
     # same votes as independent (pk, msg, sig) triples
     res2 = gbls.VerifyBatch(b"".join(pks[:40]), b"".join(bytes(s) for s in sigs[:40]), msg * 40, 48)
     assert [i for i in range(40) if res2[i] == 0] == [7, 30]    # vote 7 only verifies against pk7 + pk8
+
+def test_batch_mode_rlc_equals_exact(gbls):
+    """hbls_set_batch_mode: the random-linear-combination form (groups of 4 rounds, one final exponentiation per group,
+    exact fallback) returns the same booleans as the exact per-round form -- on an all-valid batch (no fallback taken), on
+    batches with rejected rounds, and for a batch size that leaves a partial group."""
+    n = 250
+    sks = _committee("c2", n)
+    pks_blob = gbls.GetPublicKeyBatch(b"".join(wl.sk_bytes(k) for k in sks))
+    com = gbls.Committee([pks_blob[48 * i:48 * i + 48] for i in range(n)])
+    B = 1024 + 3                                                  # 256 strided groups of 4 + 3 tail rounds
+    bms = [wl.bitmap_with_k("rlc", j, n, [167, 200, 250][j % 3]) for j in range(16)]
+    agg = [wl.sk_bytes(wl.round_signer_sum(sks, bm)) for bm in bms]
+    msgs = [wl.commit_payload("rlc", j) for j in range(B)]
+    sigs, ok = gbls.SignHashBatch(b"".join(agg[j % 16] for j in range(B)), b"".join(msgs), 48)
+    bitmaps = b"".join(bms[j % 16] for j in range(B))
+    try:
+        for bad in ([], [5], [0, 6, 7, 500, B - 1], [B - 2]):
+            m2 = [bytes([m[9] ^ 4]).join([m[:9], m[10:]]) if j in bad else m for j, m in enumerate(msgs)]
+            out = {}
+            for mode in (1, 0):
+                gbls.SetBatchMode(mode)
+                out[mode] = com.AggregateVerifyBatch(bitmaps, sigs, b"".join(m2), 48)
+            assert out[1] == out[0]
+            assert [j for j in range(B) if out[1][j] == 0] == bad
+    finally:
+        gbls.SetBatchMode(1)
