@@ -100,6 +100,11 @@ def cpu_rounds_per_s(orc, pks, bitmaps, sigs, msgs, blen, budget_s, threads):
     dt = time.perf_counter() - t0
     return sum(done) / dt, sum(done), all(good)
 
+# executed work of the batched pairing stage per round (G = 4): see run_gpu / tests/test_emu_logic.py::test_emu_rlc_stage_counts
+RLC_EXEC_FP_OPS = {"scale": (7856, 2576), "pairing": (34661, 764)}       # (Fp mul, Fp sqr) per GROUP of 4 rounds
+RLC_EXEC_MAC32_SCALE = (RLC_EXEC_FP_OPS["scale"][0] * 300 + RLC_EXEC_FP_OPS["scale"][1] * 234) / 4
+RLC_EXEC_MAC32_PAIRING = (RLC_EXEC_FP_OPS["pairing"][0] * 300 + RLC_EXEC_FP_OPS["pairing"][1] * 234) / 4
+
 def stage_mac32_per_round(orc, pks, bitmaps, sigs, msgs, blen, sample=12):
     """ALGORITHMIC work per round and per pipeline stage from the oracle's Fp mul/sqr counter."""
     h = orc.committee(pks)
@@ -225,6 +230,18 @@ def run_gpu(args):
     barrier()
     stage_ms /= n_stage
 
+    # the exact per-round algorithm (batch mode 0: one 2-pair Miller loop + final exponentiation per round) on the same batch
+    bls.SetBatchMode(0)
+    ex_evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
+    with torch.cuda.stream(stream):
+        flush.zero_(); step_device()
+        for a, b in ex_evs:
+            flush.zero_(); a.record(stream); step_device(); b.record(stream)
+    barrier()
+    exact_ms = float(np.median([a.elapsed_time(b) for a, b in ex_evs]))
+    assert int(d_res.sum().item()) == B
+    bls.SetBatchMode(1)
+
     # e2e: host buffers through the public C-ABI call, copies inside the timed region
     step_host(); torch.cuda.synchronize()
     barrier()
@@ -270,22 +287,36 @@ def run_gpu(args):
     S = min(B, 64)
     macs = stage_mac32_per_round(orc, pks, bitmaps, sigs, msgs, blen, sample=min(12, S))
     names = list(bls.STAGE_NAMES)
-    if stage_ms[4] < 0.02 * stage_ms[5]:           # fused launch: Miller loops + final exponentiation in k_pairing_verify
+    exact_macs = list(macs)                         # the oracle's per-round (exact) algorithm, stage by stage
+    rlc = bls.GetBatchMode() == 1 and B >= 1024 and os.environ.get("HBLS_RLC", "1") != "0"
+    if rlc:
+        # batched form: slot 4 = coefficient scaling + group sums, slot 5 = (G+1)-pair Miller loop + ONE final exponentiation
+        # per group of G = 4 rounds.  Executed Fp-mul/sqr counts of that algorithm come from the device code compiled
+        # for the host (tests/emu: emu_rlc_stage_counts; pinned by tests/test_emu_logic.py), x300 / x234 MAC32 each.
+        names[4], names[5] = "k_rlc_scale+k_rlc_group_sum", "k_rlc_pairing_split"
+        macs = macs[:4] + [RLC_EXEC_MAC32_SCALE, RLC_EXEC_MAC32_PAIRING]
+    elif stage_ms[4] < 0.02 * stage_ms[5]:         # fused launch: Miller loops + final exponentiation in one kernel
         macs = macs[:4] + [0.0, macs[4] + macs[5]]
         names[5] = "k_pairing_verify_split" if os.environ.get("HBLS_SPLIT", "1") != "0" else "k_pairing_verify"
     dom = int(np.argmax(stage_ms))
     achieved = macs[dom] * B / (stage_ms[dom] * 1e-3)
     total_macs = sum(macs)
+    step_s = dev_ms / args.steps * 1e-3
     bytes_per_round = blen + 96 + MSG_LEN + 1
     roofline = {"bound": "int32-imad", "kernel": names[dom], "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TMAC32/s",
                 "frac": achieved / peak, "traffic": None,
                 "peak_source": "hbls_probe_mac32_per_s: register-resident IMAD.WIDE.U32 probe measured live on this GPU",
+                "algorithm": ("random-linear-combination batch check, groups of 4 rounds (exact per-round pass only when a group fails)"
+                              if rlc else "exact per-round FastAggregateVerify"),
+                "work_counted": "Fp multiplications/squarings the kernel's algorithm performs (x300 / x234 MAC32), not instructions issued",
                 "algorithmic_mac32_per_round": total_macs, "kernel_mac32_per_round": macs[dom],
-                "pipeline_frac": total_macs * B / (dev_ms / args.steps * 1e-3) / peak,
+                "pipeline_frac": total_macs * B / step_s / peak,
+                "exact_algorithm_mac32_per_round": sum(exact_macs),
+                "pipeline_frac_exact_equivalent": sum(exact_macs) * B / step_s / peak,
                 "stage_ms_note": "per-kernel CUDA-event times from 3 extra passes after the timed region",
                 "stage_ms": {n: float(m) for n, m in zip(names, stage_ms)},
                 "stage_mac32_per_round": {n: m for n, m in zip(names, macs)},
-                "hbm_algorithmic_gbs": bytes_per_round * B / (dev_ms / args.steps * 1e-3) / 1e9}
+                "hbm_algorithmic_gbs": bytes_per_round * B / step_s / 1e9}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         roofline["hbm_peak_gbs_measured"] = peaks.get("hbm_gbs")
@@ -314,6 +345,8 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": "sigs/s", "h2d_bytes_per_step": B * (blen + 96 + MSG_LEN), "d2h_bytes_per_step": B,
                     "ms_per_step": e2e_ms_max / args.steps, "api": "hbls_aggregate_verify_batch (pinned host buffers)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "wall_s_timed_region": t_wall,
+            "exact_mode": {"ms_per_step": exact_ms, "value_this_rank": nsig / (exact_ms * 1e-3), "unit": "sigs/s",
+                           "note": "hbls_set_batch_mode(0): every round verified on its own (no random linear combination), rank 0, 3 steps"},
             "single_round_latency_ms": single_round_ms, "leader_250_votes_same_msg_latency_ms": votes250_ms}
     if cpu: line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)
@@ -324,7 +357,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--rounds", type=int, default=75776, help="rounds per step per GPU (default = 2 full waves of 148 SMs x 256 threads)")
+    ap.add_argument("--rounds", type=int, default=151552, help="rounds per step per GPU (default: 37 888 groups of 4 = one lane pair per group on 148 SMs x 512 threads)")
     ap.add_argument("--impl", default="hbls", choices=["hbls", "reference"])
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "hbls":

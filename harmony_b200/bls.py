@@ -85,6 +85,7 @@ def lib():
         sig("hbls_probe_mac32_per_s", c.c_double, c.c_int)
         sig("hbls_selftest_split", c.c_int, c.c_uint32)
         sig("hbls_set_batch_mode", None, c.c_int)
+        sig("hbls_get_batch_mode", c.c_int)
         sig("hbls_stage_timing_enable", None, c.c_int)
         sig("hbls_stage_timing_get", c.c_int, c.POINTER(c.c_float), c.c_int)
         _lib = L
@@ -363,6 +364,7 @@ def ConstructCommitPayload(is_staking: bool, block_hash: bytes, block_num: int, 
 
 def SelfTestSplit(iters: int = 16) -> int: return int(_need().hbls_selftest_split(iters))
 def SetBatchMode(mode: int): lib().hbls_set_batch_mode(int(mode))
+def GetBatchMode() -> int: return int(lib().hbls_get_batch_mode())
 def KernelLaunchCount() -> int: return int(lib().hbls_kernel_launch_count())
 def ProbeMac32PerS(iters: int = 4096) -> float: return float(_need().hbls_probe_mac32_per_s(iters))
 

@@ -154,6 +154,29 @@ template <class F> HB_NOINLINE void pt_mul_u64_aff(jac<F>& r, const aff<F>& p, u
     r = acc;
 }
 
+// [a + b lambda] P from P and P2 = [lambda] P with one shared 32-step ladder (a, b 32-bit): 32 doublings + <= 32 additions
+template <class F> HB_NOINLINE void pt_mul_2d(jac<F>& r, const jac<F>& p, const jac<F>& p2, uint32_t a, uint32_t b) {
+    jac<F> t; pt_add(t, p, p2);
+    jac<F> acc; pt_set_inf(acc);
+    for (int i = 31; i >= 0; i--) {
+        pt_dbl(acc, acc);
+        const int sel = ((a >> i) & 1) | (((b >> i) & 1) << 1);
+        if (sel) pt_add(acc, acc, sel == 1 ? p : (sel == 2 ? p2 : t));
+    }
+    r = acc;
+}
+template <class F> HB_NOINLINE void pt_mul_2d_aff(jac<F>& r, const aff<F>& p, const aff<F>& p2, uint32_t a, uint32_t b) {
+    jac<F> t; pt_from_aff(t, p); pt_add_mixed(t, t, p2);
+    jac<F> acc; pt_set_inf(acc);
+    for (int i = 31; i >= 0; i--) {
+        pt_dbl(acc, acc);
+        const int sel = ((a >> i) & 1) | (((b >> i) & 1) << 1);
+        if (sel == 3) pt_add(acc, acc, t);
+        else if (sel) pt_add_mixed(acc, acc, sel == 1 ? p : p2);
+    }
+    r = acc;
+}
+
 HB_DEV void g1_generator(g1& r) { fp_set(r.x, K_G1_X); fp_set(r.y, K_G1_Y); fp_one(r.z); }
 
 // ------------------------------------------------------------------ endomorphisms and subgroup membership
@@ -188,6 +211,22 @@ HB_NOINLINE bool g1_in_subgroup(const g1& p) {
     pt_mul_zabs(b, p); pt_mul_zabs(b, b); pt_neg(b, b);
     fp beta; fp_set(beta, K_BETA); fp_mul(a.x, a.x, beta);
     return pt_eq(a, b);
+}
+
+// Batch-verification coefficient applied to one round: the 64-bit draw c = (b << 32 | a) stands for the scalar
+// s = a + b z^2 (mod r) -- 2^64 distinct values, and [z^2] is an endomorphism on both groups:
+//   G1: [z^2](x, y) = -phi(x, y) = (beta x, -y)      (g1_in_subgroup above: phi = -[z^2])
+//   G2: [z^2] = psi^2,  psi^2(x, y) = (N(cx) x, -y)   (psi = [p] = [z] on G2)
+// so both scalings are 32-step two-base ladders instead of 64-step ones.  Inputs must lie in G1 / G2 (the callers'
+// points are sums of subgroup-checked keys and subgroup-checked signatures).
+HB_DEV void rlc_scale_pair(g1& ra, g2& rs, const g1& apk, const g2a& sig, uint64_t c) {
+    const uint32_t a = (uint32_t)c | 1u, b = (uint32_t)(c >> 32);
+    g1 p2; fp beta; fp_set(beta, K_BETA);
+    fp_mul(p2.x, apk.x, beta); fp_neg(p2.y, apk.y); p2.z = apk.z;
+    pt_mul_2d(ra, apk, p2, a, b);
+    g2a q2; fp cx; fp_set(cx, K_PSI2_CX);
+    fp2_mul_fp(q2.x, sig.x, cx); fp2_neg(q2.y, sig.y);
+    pt_mul_2d_aff(rs, sig, q2, a, b);
 }
 
 // ------------------------------------------------------------------ codecs (reference crypto/bls/bls.go:67-71,109-118)

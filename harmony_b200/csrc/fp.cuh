@@ -243,7 +243,14 @@ HB_DEV void fp_cmov(fp& r, const fp& a, bool c) {
 }
 
 // out-of-line multipliers keep the instruction footprint of the pairing kernels inside the L1.5 I-cache
+#ifdef HB_HOST_EMU
+static thread_local uint64_t hb_emu_cnt_mul = 0, hb_emu_cnt_sqr = 0;      // executed-work counters (tests / bench bookkeeping)
+#define HB_EMU_COUNT(x) (++(x))
+#else
+#define HB_EMU_COUNT(x) ((void)0)
+#endif
 HB_NOINLINE void fp_mul(fp& r, const fp& a, const fp& b) {
+    HB_EMU_COUNT(hb_emu_cnt_mul);
     uint32_t ra[12], rb[12], rr[12];
 #pragma unroll
     for (int j = 0; j < 12; j++) { ra[j] = a.l[j]; rb[j] = b.l[j]; }

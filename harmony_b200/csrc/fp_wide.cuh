@@ -190,6 +190,7 @@ HB_DEV void limbs_sub12_plus_p(uint32_t* r, const uint32_t* a, const uint32_t* b
 
 // r = a^2 / R mod p: 78 + 156 = 234 IMAD.WIDE (the exponentiation chains of sqrt / inverse / Legendre are ~80% squarings)
 HB_NOINLINE void fp_sqr(fp& r, const fp& a) {
+    HB_EMU_COUNT(hb_emu_cnt_sqr);
     uint32_t ra[12], T[24], rr[12];
 #pragma unroll
     for (int j = 0; j < 12; j++) ra[j] = a.l[j];

@@ -287,6 +287,7 @@ int blsInit(int curve, int compiledTimeVar) {
 }
 uint64_t hbls_kernel_launch_count(void) { return g.launches.load(); }
 void hbls_set_batch_mode(int mode) { std::lock_guard<std::mutex> lk(g.mu); g.batch_mode = mode ? 1 : 0; }
+int hbls_get_batch_mode(void) { std::lock_guard<std::mutex> lk(g.mu); return g.batch_mode; }
 
 // ------------------------------------------------------------------ secret keys (host bytes; no group arithmetic)
 int blsSecretKeySetByCSPRNG(blsSecretKey* sec) {

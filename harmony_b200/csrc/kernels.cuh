@@ -270,9 +270,8 @@ __global__ void k_rlc_scale(size_t B, size_t ng, const g1* apk, const g2a* sig, 
     const uint64_t r = rlc_coeff(s0, s1, j / ng);
     g1 a = apk[j]; g2a sg = sig[j]; g2a h = hm[j];
     const bool b = !ok_sig[j] || !ok_hm[j] || pt_is_inf(a) || aff_is_inf(sg) || aff_is_inf(h);
-    g1 ra; pt_mul_u64(ra, a, r);
+    g1 ra; g2 rs; rlc_scale_pair(ra, rs, a, sg, r);
     g1a pa; pt_to_aff(pa, ra); fp_neg(pa.y, pa.y);
-    g2 rs; pt_mul_u64_aff(rs, sg, r);
     pk_scaled_neg[j] = pa; S[j] = rs; bad[j] = b ? 1 : 0;
   }
 }

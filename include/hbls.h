@@ -104,6 +104,7 @@ int hbls_aggregate_verify_batch(const hbls_committee* c, size_t B, const uint8_t
  *   with probability 2^-64).  Batches under 1024 rounds always use mode 0.
  * mode 0: the exact per-round check only (identical semantics to N calls of hbls_aggregate_verify). */
 void hbls_set_batch_mode(int mode);
+int  hbls_get_batch_mode(void);
 /* same, every pointer already in device memory (HBM); stream = cudaStream_t or NULL; asynchronous on that stream */
 int hbls_aggregate_verify_batch_device(const hbls_committee* c, size_t B, const void* d_bitmaps, size_t blen,
                                        const void* d_sigs96, const void* d_msgs, size_t msg_len,

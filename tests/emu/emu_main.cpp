@@ -44,12 +44,49 @@ extern "C" int emu_rlc_group(const uint8_t* pks48, const uint8_t* sigs96, const 
     for (int k = 0; k < G; k++) {
         g1 pk; g2 sg, h;
         if (!g1_deserialize(pk, pks48 + 48 * k, true) || !g2_deserialize(sg, sigs96 + 96 * k, true) || !map_to_g2(h, msgs + len * k, len)) return -1;
-        g1 rp; pt_mul_u64(rp, pk, r[k]); pt_to_aff(P[k], rp); fp_neg(P[k].y, P[k].y);
-        g2a sa; pt_to_aff(sa, sg); g2 rs; pt_mul_u64_aff(rs, sa, r[k]); pt_add(acc, acc, rs);
+        g2a sa; pt_to_aff(sa, sg); g1 rp; g2 rs; rlc_scale_pair(rp, rs, pk, sa, r[k]); pt_add(acc, acc, rs);
+        pt_to_aff(P[k], rp); fp_neg(P[k].y, P[k].y);
         g2a ha; pt_to_aff(ha, h); qx[k] = ha.x; qy[k] = ha.y; ps[k] = &P[k];
     }
     g2a sga; pt_to_aff(sga, acc); qx[G] = sga.x; qy[G] = sga.y;
     fp_set(P[G].x, K_G1_X); fp_set(P[G].y, K_G1_Y); ps[G] = &P[G];
     fp12 m; miller_loop_multi<fp2, G + 1>(m, ps, qx, qy); final_exp(m, m);
     return fp12_is_one(m) ? 1 : 0;
+}
+// executed Fp mul / sqr counts of the batched pairing stage for one group of G = 4 rounds (bench.py: "executed" roofline):
+// out[0..1] = scaling of the 4 rounds (r * apk -> affine, r * sigma), out[2..3] = group sum + 5-pair Miller loop + final exp
+extern "C" int emu_rlc_stage_counts(const uint8_t* pks48, const uint8_t* sigs96, const uint8_t* msgs, uint32_t len, uint64_t* out) {
+    const int G = 4;
+    static g1a P[G + 1]; fp2 qx[G + 1], qy[G + 1]; const g1a* ps[G + 1];
+    g1 pk[G]; g2a sa[G]; g2a ha[G];
+    for (int k = 0; k < G; k++) {
+        g2 sg, h;
+        if (!g1_deserialize(pk[k], pks48 + 48 * k, true) || !g2_deserialize(sg, sigs96 + 96 * k, true) || !map_to_g2(h, msgs + len * k, len)) return -1;
+        pt_to_aff(sa[k], sg); pt_to_aff(ha[k], h);
+    }
+    uint64_t m0 = hb_emu_cnt_mul, s0 = hb_emu_cnt_sqr;
+    g2 S[G];
+    for (int k = 0; k < G; k++) {
+        const uint64_t r = 0x9e3779b97f4a7c15ull * (k + 1) | 1ull;
+        g1 rp; rlc_scale_pair(rp, S[k], pk[k], sa[k], r); pt_to_aff(P[k], rp); fp_neg(P[k].y, P[k].y);
+        qx[k] = ha[k].x; qy[k] = ha[k].y; ps[k] = &P[k];
+    }
+    out[0] = hb_emu_cnt_mul - m0; out[1] = hb_emu_cnt_sqr - s0; m0 = hb_emu_cnt_mul; s0 = hb_emu_cnt_sqr;
+    g2 acc; pt_set_inf(acc);
+    for (int k = 0; k < G; k++) pt_add(acc, acc, S[k]);
+    g2a sga; pt_to_aff(sga, acc); qx[G] = sga.x; qy[G] = sga.y;
+    fp_set(P[G].x, K_G1_X); fp_set(P[G].y, K_G1_Y); ps[G] = &P[G];
+    fp12 m; miller_loop_multi<fp2, G + 1>(m, ps, qx, qy); final_exp(m, m);
+    out[2] = hb_emu_cnt_mul - m0; out[3] = hb_emu_cnt_sqr - s0;
+    return fp12_is_one(m) ? 1 : 0;
+}
+// the two-base ladder against the plain ladder on the full scalar s = a + b z^2 mod r (8 LE words from the test)
+extern "C" int emu_rlc_scale_check(const uint8_t* pk48, const uint8_t* sig96, uint64_t c, const uint32_t* s_words) {
+    g1 pk; g2 sg;
+    if (!g1_deserialize(pk, pk48, true) || !g2_deserialize(sg, sig96, true)) return -1;
+    g2a sa; pt_to_aff(sa, sg);
+    g1 ra, ea; g2 rs, es;
+    rlc_scale_pair(ra, rs, pk, sa, c);
+    pt_mul(ea, pk, s_words, 8); pt_mul(es, sg, s_words, 8);
+    return (pt_eq(ra, ea) ? 1 : 0) | (pt_eq(rs, es) ? 2 : 0);
 }

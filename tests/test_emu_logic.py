@@ -100,3 +100,36 @@ def test_emu_rlc_group(emu, oracle):
     forged = list(sigs); forged[0] = o.g2_serialize(o.pt_add(o.FP2, A, D)); forged[1] = o.g2_serialize(o.pt_sub(o.FP2, Bp, D))
     assert emu.emu_rlc_group(b"".join(pks), b"".join(forged), b"".join(msgs), 48, r1) == 1      # unit coefficients are fooled ...
     assert emu.emu_rlc_group(b"".join(pks), b"".join(forged), b"".join(msgs), 48, r) == 0       # ... random ones are not
+
+
+def test_emu_rlc_two_base_ladder(emu, oracle):
+    """The batch coefficient c = (b << 32 | a) is applied as s = a + b z^2 through the [z^2] endomorphisms
+    ((beta x, -y) on G1, psi^2 on G2) with a shared 32-step ladder; it must equal the plain ladder on s mod r."""
+    from harmony_b200 import workload as wl
+    emu.emu_rlc_scale_check.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint32)]
+    z = -0xd201000000010000
+    R = z ** 4 - z * z + 1
+    rng = random.Random(77)
+    for t, c in enumerate([0xffffffff00000000, 1, 0xffffffffffffffff, rng.getrandbits(64), rng.getrandbits(64)]):
+        sk = wl.sk_bytes(wl.seeded_sk("glv", t)); pk = oracle.get_public_key(sk)
+        sg = oracle.sign_hash(sk, wl.commit_payload("glv", t))
+        a, b = (c & 0xffffffff) | 1, c >> 32
+        s = (a + b * z * z) % R
+        words = (ctypes.c_uint32 * 8)(*[(s >> (32 * i)) & 0xffffffff for i in range(8)])
+        assert emu.emu_rlc_scale_check(pk, sg, c, words) == 3
+
+
+def test_emu_rlc_stage_counts(emu, oracle):
+    """bench.py's executed-work figures for the batched pairing stage are the Fp mul/sqr counts of the device code itself."""
+    import importlib.util
+    from harmony_b200 import workload as wl
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py")); bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    G = 4
+    sks = [wl.sk_bytes(wl.seeded_sk("cnt", i)) for i in range(G)]; pks = [oracle.get_public_key(s) for s in sks]
+    msgs = [wl.commit_payload("cnt", i) for i in range(G)]; sigs = [oracle.sign_hash(s, m) for s, m in zip(sks, msgs)]
+    out = (ctypes.c_uint64 * 4)()
+    assert emu.emu_rlc_stage_counts(b"".join(pks), b"".join(sigs), b"".join(msgs), 48, out) == 1
+    assert (out[2], out[3]) == bench.RLC_EXEC_FP_OPS["pairing"]
+    sm, ss = bench.RLC_EXEC_FP_OPS["scale"]                   # depends on the coefficients' bit pattern: within 5 %
+    assert abs(out[0] - sm) <= 0.05 * sm and abs(out[1] - ss) <= 0.05 * ss
