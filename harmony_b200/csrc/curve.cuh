@@ -276,7 +276,7 @@ HB_NOINLINE bool g2_deserialize(g2& r, const uint8_t* in, bool check_order) {
     fp2 x, y, t, b;
     fp_from_int(x.a, va); fp_from_int(x.b, vb);
     fp2_sqr(t, x); fp2_mul(t, t, x); fp2_const(b, K_B2); fp2_add(t, t, b);
-    if (!fp2_sqrt(y, t)) return false;
+    if (!fp2_sqrt_anysign(y, t)) return false;                    // the parity bit picks the sign below
     if (fp_is_odd(y.a) != odd) fp2_neg(y, y);
     g2 q; q.x = x; q.y = y; fp2_one(q.z);
     if (check_order && !g2_in_subgroup(q)) return false;

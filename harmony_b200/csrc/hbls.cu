@@ -128,16 +128,25 @@ void launch_verify_tail(size_t B, const VerifyBufs& v, const uint8_t* d_sig96, c
     static const size_t rlc_min = [] { const char* e = getenv("HBLS_RLC_MIN"); return e ? (size_t)atol(e) : (size_t)1024; }();
     if (split_mode && rlc_env && g.batch_mode == 1 && apk_jac && B >= rlc_min) {
         // batched form (north-star "batched Miller loop + shared final exponentiation"): groups of HB_RLC_G rounds
-        const size_t ng = B / HB_RLC_G, nr = ng * HB_RLC_G, tail = B - nr;
+        // group size: 8 once that still gives every SM a full CTA of lane pairs (fewer Miller-loop pairs and final
+        // exponentiations per round), else 4
+        static const int g_env = [] { const char* e = getenv("HBLS_RLC_G"); return e ? atoi(e) : 0; }();
+        const size_t G = g_env == 4 || g_env == 8 ? (size_t)g_env : (2 * (B / 8) >= (size_t)g.sm_count * HB_TPB_SPLIT ? 8 : 4);
+        const size_t ng = B / G, nr = ng * G, tail = B - nr;
         const uint64_t s0 = g.rlc_seed[0] + 0x9e3779b97f4a7c15ull * (++g.rlc_calls), s1 = g.rlc_seed[1] ^ (g.rlc_calls << 32);
         cudaMemsetAsync(v.any_fail, 0, sizeof(int), s);
         LAUNCH(k_rlc_scale, heavy_blocks(nr), TPB, s, nr, ng, apk_jac, v.sig, v.hm, v.ok_sig, v.ok_hm, s0, s1, v.pk_scaled, v.S, v.bad);
-        LAUNCH(k_rlc_group_sum, heavy_blocks(ng), TPB, s, ng, v.S, v.Sg);
-        STAGE_EV(5, s);
-        if (2 * ng >= (size_t)g.sm_count * HB_TPB_SPLIT)
-            LAUNCH(k_rlc_pairing_split, split_blocks(2 * ng), HB_TPB_SPLIT, s, ng, v.pk_scaled, v.hm, v.Sg, v.bad, v.group_ok);
-        else
-            LAUNCH(k_rlc_pairing_split, blocks_for(2 * ng, 64), 64, s, ng, v.pk_scaled, v.hm, v.Sg, v.bad, v.group_ok);
+        const bool full = 2 * ng >= (size_t)g.sm_count * HB_TPB_SPLIT;
+        const unsigned pb = full ? split_blocks(2 * ng) : blocks_for(2 * ng, 64), pt = full ? HB_TPB_SPLIT : 64;
+        if (G == 8) {
+            LAUNCH(k_rlc_group_sum<8>, heavy_blocks(ng), TPB, s, ng, v.S, v.Sg);
+            STAGE_EV(5, s);
+            LAUNCH(k_rlc_pairing_split<8>, pb, pt, s, ng, v.pk_scaled, v.hm, v.Sg, v.bad, v.group_ok);
+        } else {
+            LAUNCH(k_rlc_group_sum<4>, heavy_blocks(ng), TPB, s, ng, v.S, v.Sg);
+            STAGE_EV(5, s);
+            LAUNCH(k_rlc_pairing_split<4>, pb, pt, s, ng, v.pk_scaled, v.hm, v.Sg, v.bad, v.group_ok);
+        }
         LAUNCH(k_rlc_finish, blocks_for(nr, 256), 256, s, nr, ng, v.group_ok, d_results, v.any_fail);
         // exact per-round pass: returns immediately unless a group failed (then every round is recomputed exactly)
         if (2 * B >= (size_t)g.sm_count * HB_TPB_SPLIT)
@@ -267,7 +276,8 @@ int hbls_init_device(int device) {
     g.device = device; g.sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     { FILE* f = fopen("/dev/urandom", "rb"); if (!f || fread(g.rlc_seed, 1, 16, f) != 16) { if (f) fclose(f); fprintf(stderr, "[hbls] cannot read /dev/urandom\n"); return HBLS_ERR_CUDA; } fclose(f); }
-    cudaFuncSetAttribute(k_rlc_pairing_split, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    cudaFuncSetAttribute(k_rlc_pairing_split<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    cudaFuncSetAttribute(k_rlc_pairing_split<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     // the heavy kernels keep their Fp12 temporaries in per-thread local memory: give L1 the whole 228 KB
     cudaFuncSetAttribute(k_miller_verify, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_final_verify, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);

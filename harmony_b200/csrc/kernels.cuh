@@ -251,7 +251,7 @@ __global__ void k_pairing_fixup(size_t B, const g2a* sig, const g1a* pk_neg, con
 // round that did not decode -- makes the exact per-round kernels run afterwards, so results stay exact booleans
 // (a bad round survives the batched test with probability 2^-64).
 #ifndef HB_RLC_G
-#define HB_RLC_G 4       // measured best on B200 at 75 776 rounds/step (3: 76 ms, 4: 48 ms, 5: 68 ms, 7: 65 ms for the pairing stage)
+#define HB_RLC_G 4       // smallest group size (scratch is sized for it); the host picks 4 or 8 per call.  Measured best on B200 at 75 776 rounds/step (3: 76 ms, 4: 48 ms, 5: 68 ms, 7: 65 ms for the pairing stage)
 #endif
 // Groups are STRIDED: group g = rounds {g, g + ng, g + 2 ng, ...}; the coefficient depends only on the position k inside the
 // group (r_k, fresh per call), so the 32 consecutive rounds of a warp share one scalar and the double-and-add ladders run
@@ -276,15 +276,15 @@ __global__ void k_rlc_scale(size_t B, size_t ng, const g1* apk, const g2a* sig, 
   }
 }
 // per group: affine sum of its S_j
-__global__ void k_rlc_group_sum(size_t ngroups, const g2* S, g2a* Sg) {
+template <int G> __global__ void k_rlc_group_sum(size_t ngroups, const g2* S, g2a* Sg) {
   for (size_t g = HB_TID; g < ngroups; g += HB_STRIDE) {
     g2 acc; pt_set_inf(acc);
-    for (int k = 0; k < HB_RLC_G; k++) { g2 t = S[(size_t)k * ngroups + g]; pt_add(acc, acc, t); }
+    for (int k = 0; k < G; k++) { g2 t = S[(size_t)k * ngroups + g]; pt_add(acc, acc, t); }
     g2a a; pt_to_aff(a, acc); Sg[g] = a;
   }
 }
 // lane pair per group: (G + 1)-pair Miller loop, final exponentiation, verdict
-__global__ void __launch_bounds__(HB_TPB_SPLIT, HB_MINBLOCKS_SPLIT) k_rlc_pairing_split(size_t ngroups, const g1a* pk_scaled_neg, const g2a* hm, const g2a* Sg,
+template <int G> __global__ void __launch_bounds__(HB_TPB_SPLIT, HB_MINBLOCKS_SPLIT) k_rlc_pairing_split(size_t ngroups, const g1a* pk_scaled_neg, const g2a* hm, const g2a* Sg,
                                  const uint8_t* bad, uint8_t* group_ok) {
     const int role = threadIdx.x & 1;
     const size_t ppg = HB_STRIDE >> 1;
@@ -297,20 +297,20 @@ __global__ void __launch_bounds__(HB_TPB_SPLIT, HB_MINBLOCKS_SPLIT) k_rlc_pairin
         const size_t g = it * ppg + (HB_TID >> 1);
         const bool valid = g < ngroups;
         const size_t gg = valid ? g : ngroups - 1;
-        const g1a* ps[HB_RLC_G + 1]; fp2h qx[HB_RLC_G + 1], qy[HB_RLC_G + 1];
+        const g1a* ps[G + 1]; fp2h qx[G + 1], qy[G + 1];
         bool anybad = false;
-        for (int k = 0; k < HB_RLC_G; k++) {
+        for (int k = 0; k < G; k++) {
             const size_t j = (size_t)k * ngroups + gg;
             ps[k] = &pk_scaled_neg[j];
             const fp* h4 = reinterpret_cast<const fp*>(&hm[j]);
             qx[k].c = h4[role]; qy[k].c = h4[2 + role];
             anybad |= bad[j] != 0;
         }
-        ps[HB_RLC_G] = &gen_sh;
+        ps[G] = &gen_sh;
         const fp* s4 = reinterpret_cast<const fp*>(&Sg[gg]);
-        qx[HB_RLC_G].c = s4[role]; qy[HB_RLC_G].c = s4[2 + role];
+        qx[G].c = s4[role]; qy[G].c = s4[2 + role];
         fp12_t<fp2h> m;
-        miller_loop_multi<fp2h, HB_RLC_G + 1>(m, ps, qx, qy);
+        miller_loop_multi<fp2h, G + 1>(m, ps, qx, qy);
         final_exp(m, m);
         const bool one = fp12_is_one(m);
         if (valid && role == 0) group_ok[g] = (one && !anybad) ? 1 : 0;

@@ -90,3 +90,9 @@ extern "C" int emu_rlc_scale_check(const uint8_t* pk48, const uint8_t* sig96, ui
     pt_mul(ea, pk, s_words, 8); pt_mul(es, sg, s_words, 8);
     return (pt_eq(ra, ea) ? 1 : 0) | (pt_eq(rs, es) ? 2 : 0);
 }
+// Jacobi-symbol Legendre against the exponentiation on n values (Montgomery limbs in, 12 words each); returns mismatches
+extern "C" int emu_legendre_check(const uint32_t* vals, int n) {
+    int bad = 0;
+    for (int i = 0; i < n; i++) { fp a; for (int j = 0; j < 12; j++) a.l[j] = vals[12 * i + j]; if (fp_legendre(a) != fp_legendre_pow(a)) bad++; }
+    return bad;
+}

@@ -133,3 +133,14 @@ def test_emu_rlc_stage_counts(emu, oracle):
     assert (out[2], out[3]) == bench.RLC_EXEC_FP_OPS["pairing"]
     sm, ss = bench.RLC_EXEC_FP_OPS["scale"]                   # depends on the coefficients' bit pattern: within 5 %
     assert abs(out[0] - sm) <= 0.05 * sm and abs(out[1] - ss) <= 0.05 * ss
+
+
+def test_emu_legendre_jacobi(emu):
+    """The Legendre symbol used by the SW map is a binary Jacobi symbol; it must agree with a^((p-1)/2) everywhere."""
+    p = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+    rng = random.Random(9)
+    vals = [0, 1, 2, 3, 4, p - 1, p - 2, (p - 1) // 2, 1 << 380] + [rng.randrange(p) for _ in range(200)]
+    arr = (ctypes.c_uint32 * (12 * len(vals)))()
+    for i, v in enumerate(vals):
+        for j in range(12): arr[12 * i + j] = (v >> (32 * j)) & 0xffffffff
+    assert emu.emu_legendre_check(arr, len(vals)) == 0
