@@ -100,10 +100,18 @@ def cpu_rounds_per_s(orc, pks, bitmaps, sigs, msgs, blen, budget_s, threads):
     dt = time.perf_counter() - t0
     return sum(done) / dt, sum(done), all(good)
 
-# executed work of the batched pairing stage per round (G = 4): see run_gpu / tests/test_emu_logic.py::test_emu_rlc_stage_counts
-RLC_EXEC_FP_OPS = {"scale": (7856, 2576), "pairing": (34661, 764)}       # (Fp mul, Fp sqr) per GROUP of 4 rounds
-RLC_EXEC_MAC32_SCALE = (RLC_EXEC_FP_OPS["scale"][0] * 300 + RLC_EXEC_FP_OPS["scale"][1] * 234) / 4
-RLC_EXEC_MAC32_PAIRING = (RLC_EXEC_FP_OPS["pairing"][0] * 300 + RLC_EXEC_FP_OPS["pairing"][1] * 234) / 4
+# executed work of the batched pairing stage: (Fp mul, Fp sqr) per GROUP of G rounds, counted by running the device code
+# compiled for the host (tests/emu: emu_rlc_stage_counts; pinned by tests/test_emu_logic.py::test_emu_rlc_stage_counts)
+RLC_EXEC_FP_OPS = {4: {"scale": (7856, 2576), "pairing": (34661, 764)},
+                   8: {"scale": (15046, 5094), "pairing": (54329, 764)}}
+def rlc_group_size(B, sm_count, tpb_split=512):
+    """Mirror of the host's choice in hbls.cu launch_verify_tail: 8 when B/8 lane pairs still fill every SM, else 4."""
+    env = os.environ.get("HBLS_RLC_G")
+    if env in ("4", "8"): return int(env)
+    return 8 if 2 * (B // 8) >= sm_count * tpb_split else 4
+def rlc_exec_mac32(G):
+    ops = RLC_EXEC_FP_OPS[G]
+    return tuple((ops[k][0] * 300 + ops[k][1] * 234) / G for k in ("scale", "pairing"))
 
 def stage_mac32_per_round(orc, pks, bitmaps, sigs, msgs, blen, sample=12):
     """ALGORITHMIC work per round and per pipeline stage from the oracle's Fp mul/sqr counter."""
@@ -291,10 +299,11 @@ def run_gpu(args):
     rlc = bls.GetBatchMode() == 1 and B >= 1024 and os.environ.get("HBLS_RLC", "1") != "0"
     if rlc:
         # batched form: slot 4 = coefficient scaling + group sums, slot 5 = (G+1)-pair Miller loop + ONE final exponentiation
-        # per group of G = 4 rounds.  Executed Fp-mul/sqr counts of that algorithm come from the device code compiled
+        # per group of G rounds (G = 8 when the batch fills the chip that way, else 4).  Executed Fp-mul/sqr counts of that algorithm come from the device code compiled
         # for the host (tests/emu: emu_rlc_stage_counts; pinned by tests/test_emu_logic.py), x300 / x234 MAC32 each.
-        names[4], names[5] = "k_rlc_scale+k_rlc_group_sum", "k_rlc_pairing_split"
-        macs = macs[:4] + [RLC_EXEC_MAC32_SCALE, RLC_EXEC_MAC32_PAIRING]
+        G = rlc_group_size(B, torch.cuda.get_device_properties(local).multi_processor_count)
+        names[4], names[5] = "k_rlc_scale+k_rlc_group_sum", f"k_rlc_pairing_split<{G}>"
+        macs = macs[:4] + list(rlc_exec_mac32(G))
     elif stage_ms[4] < 0.02 * stage_ms[5]:         # fused launch: Miller loops + final exponentiation in one kernel
         macs = macs[:4] + [0.0, macs[4] + macs[5]]
         names[5] = "k_pairing_verify_split" if os.environ.get("HBLS_SPLIT", "1") != "0" else "k_pairing_verify"
@@ -306,7 +315,7 @@ def run_gpu(args):
     roofline = {"bound": "int32-imad", "kernel": names[dom], "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TMAC32/s",
                 "frac": achieved / peak, "traffic": None,
                 "peak_source": "hbls_probe_mac32_per_s: register-resident IMAD.WIDE.U32 probe measured live on this GPU",
-                "algorithm": ("random-linear-combination batch check, groups of 4 rounds (exact per-round pass only when a group fails)"
+                "algorithm": (f"random-linear-combination batch check, groups of {G} rounds (exact per-round pass only when a group fails)"
                               if rlc else "exact per-round FastAggregateVerify"),
                 "work_counted": "Fp multiplications/squarings the kernel's algorithm performs (x300 / x234 MAC32), not instructions issued",
                 "algorithmic_mac32_per_round": total_macs, "kernel_mac32_per_round": macs[dom],
@@ -357,7 +366,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--rounds", type=int, default=151552, help="rounds per step per GPU (default: 37 888 groups of 4 = one lane pair per group on 148 SMs x 512 threads)")
+    ap.add_argument("--rounds", type=int, default=303104, help="rounds per step per GPU (default: 37 888 groups of 8 = one lane pair per group on 148 SMs x 512 threads)")
     ap.add_argument("--impl", default="hbls", choices=["hbls", "reference"])
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "hbls":

@@ -234,14 +234,20 @@ HB_NOINLINE bool fp2_sqrt(fp2& r, const fp2& x) {
     fp2_norm(t1, x);
     if (!fp_sqrt(t1, t1)) return false;
     fp_set(inv2, K_INV2);
-    fp c, ci;
+    // mcl: c = sqrt((a + s)/2), or sqrt((a - s)/2) when the first is a non-residue, always the root t^((p+1)/4)
+    // (the one that is itself a residue); then (c, b / 2c).  One exponentiation serves both cases: with
+    // u = t^((p-3)/4), c = t u:  c^2 == t -> (c, b u / 2).  Otherwise c^2 == -t and u == -1/c, the other half is
+    // (b u / 2)^2, its residue root is sigma * (-b u / 2) with sigma = Legendre(-b u / 2), and b / 2c' = sigma c.
+    fp u, c, c2, h;
     fp_add(t2, x.a, t1); fp_mul(t2, t2, inv2);
-    if (!fp_sqrt_inv(c, ci, t2)) {
-        fp_sub(t2, x.a, t1); fp_mul(t2, t2, inv2);
-        if (!fp_sqrt_inv(c, ci, t2)) return false;
-    }
-    // y.b = b / (2c) = b * (1/c) * (1/2): the inverse came with the root, no second exponentiation
-    fp_mul(t2, x.b, ci); fp_mul(r.b, t2, inv2); r.a = c;
+    fp_pow(u, t2, K_P_MINUS_3_DIV_4); fp_mul(c, u, t2); fp_sqr(c2, c);
+    fp_mul(h, x.b, u); fp_mul(h, h, inv2);                    // b u / 2
+    if (fp_eq(c2, t2)) { r.a = c; r.b = h; return true; }
+    fp_neg(c2, c2);
+    if (!fp_eq(c2, t2)) return false;
+    fp_neg(h, h);
+    if (fp_legendre(h) < 0) { fp_neg(h, h); fp_neg(c, c); }
+    r.a = h; r.b = c;
     return true;
 }
 

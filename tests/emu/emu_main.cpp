@@ -53,10 +53,9 @@ extern "C" int emu_rlc_group(const uint8_t* pks48, const uint8_t* sigs96, const 
     fp12 m; miller_loop_multi<fp2, G + 1>(m, ps, qx, qy); final_exp(m, m);
     return fp12_is_one(m) ? 1 : 0;
 }
-// executed Fp mul / sqr counts of the batched pairing stage for one group of G = 4 rounds (bench.py: "executed" roofline):
+// executed Fp mul / sqr counts of the batched pairing stage for one group of G rounds (bench.py: "executed" roofline):
 // out[0..1] = scaling of the 4 rounds (r * apk -> affine, r * sigma), out[2..3] = group sum + 5-pair Miller loop + final exp
-extern "C" int emu_rlc_stage_counts(const uint8_t* pks48, const uint8_t* sigs96, const uint8_t* msgs, uint32_t len, uint64_t* out) {
-    const int G = 4;
+template <int G> static int rlc_stage_counts(const uint8_t* pks48, const uint8_t* sigs96, const uint8_t* msgs, uint32_t len, uint64_t* out) {
     static g1a P[G + 1]; fp2 qx[G + 1], qy[G + 1]; const g1a* ps[G + 1];
     g1 pk[G]; g2a sa[G]; g2a ha[G];
     for (int k = 0; k < G; k++) {
@@ -79,6 +78,9 @@ extern "C" int emu_rlc_stage_counts(const uint8_t* pks48, const uint8_t* sigs96,
     fp12 m; miller_loop_multi<fp2, G + 1>(m, ps, qx, qy); final_exp(m, m);
     out[2] = hb_emu_cnt_mul - m0; out[3] = hb_emu_cnt_sqr - s0;
     return fp12_is_one(m) ? 1 : 0;
+}
+extern "C" int emu_rlc_stage_counts(int G, const uint8_t* pks48, const uint8_t* sigs96, const uint8_t* msgs, uint32_t len, uint64_t* out) {
+    return G == 8 ? rlc_stage_counts<8>(pks48, sigs96, msgs, len, out) : rlc_stage_counts<4>(pks48, sigs96, msgs, len, out);
 }
 // the two-base ladder against the plain ladder on the full scalar s = a + b z^2 mod r (8 LE words from the test)
 extern "C" int emu_rlc_scale_check(const uint8_t* pk48, const uint8_t* sig96, uint64_t c, const uint32_t* s_words) {

@@ -125,14 +125,15 @@ def test_emu_rlc_stage_counts(emu, oracle):
     from harmony_b200 import workload as wl
     spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py")); bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
-    G = 4
-    sks = [wl.sk_bytes(wl.seeded_sk("cnt", i)) for i in range(G)]; pks = [oracle.get_public_key(s) for s in sks]
-    msgs = [wl.commit_payload("cnt", i) for i in range(G)]; sigs = [oracle.sign_hash(s, m) for s, m in zip(sks, msgs)]
-    out = (ctypes.c_uint64 * 4)()
-    assert emu.emu_rlc_stage_counts(b"".join(pks), b"".join(sigs), b"".join(msgs), 48, out) == 1
-    assert (out[2], out[3]) == bench.RLC_EXEC_FP_OPS["pairing"]
-    sm, ss = bench.RLC_EXEC_FP_OPS["scale"]                   # depends on the coefficients' bit pattern: within 5 %
-    assert abs(out[0] - sm) <= 0.05 * sm and abs(out[1] - ss) <= 0.05 * ss
+    for G in (4, 8):
+        sks = [wl.sk_bytes(wl.seeded_sk("cnt", i)) for i in range(G)]; pks = [oracle.get_public_key(s) for s in sks]
+        msgs = [wl.commit_payload("cnt", i) for i in range(G)]; sigs = [oracle.sign_hash(s, m) for s, m in zip(sks, msgs)]
+        out = (ctypes.c_uint64 * 4)()
+        assert emu.emu_rlc_stage_counts(G, b"".join(pks), b"".join(sigs), b"".join(msgs), 48, out) == 1
+        assert (out[2], out[3]) == bench.RLC_EXEC_FP_OPS[G]["pairing"]
+        sm, ss = bench.RLC_EXEC_FP_OPS[G]["scale"]                # depends on the coefficients' bit pattern: within 5 %
+        assert abs(out[0] - sm) <= 0.05 * sm and abs(out[1] - ss) <= 0.05 * ss
+    assert bench.rlc_group_size(303104, 148) == 8 and bench.rlc_group_size(151552, 148) == 4
 
 
 def test_emu_legendre_jacobi(emu):
