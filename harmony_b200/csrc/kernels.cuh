@@ -108,7 +108,8 @@ __global__ void __launch_bounds__(128) k_g1_sum(size_t n, const g1a* in, g1* out
     }
     if (threadIdx.x == 0) out[0] = acc;
 }
-__global__ void k_g1_normalize(size_t n, const g1* in, g1a* out, int negate) {
+__global__ void k_g1_normalize(size_t n, const g1* in, g1a* out, int negate, const int* run_if) {
+    if (run_if && !*run_if) return;          // deferred form: only needed when the batched check sends rounds to the exact pass
     size_t i = HB_TID; if (i >= n) return;
     g1 p = in[i]; g1a a; pt_to_aff(a, p);
     if (negate) fp_neg(a.y, a.y);
