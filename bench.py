@@ -104,6 +104,7 @@ def cpu_rounds_per_s(orc, pks, bitmaps, sigs, msgs, blen, budget_s, threads):
 # compiled for the host (tests/emu: emu_rlc_stage_counts; pinned by tests/test_emu_logic.py::test_emu_rlc_stage_counts)
 RLC_EXEC_FP_OPS = {4: {"scale": (7856, 2576), "pairing": (34661, 764)},
                    8: {"scale": (15046, 5094), "pairing": (54329, 764)}}
+NCU_DRAM_BYTES_PER_LAUNCH = {("k_rlc_pairing_split<8>", 303104): 28.78e9 + 109.09e9}
 def rlc_group_size(B, sm_count, tpb_split=512):
     """Mirror of the host's choice in hbls.cu launch_verify_tail: 8 when B/8 lane pairs still fill every SM, else 4."""
     env = os.environ.get("HBLS_RLC_G")
@@ -295,13 +296,15 @@ def run_gpu(args):
     S = min(B, 64)
     macs = stage_mac32_per_round(orc, pks, bitmaps, sigs, msgs, blen, sample=min(12, S))
     names = list(bls.STAGE_NAMES)
+    sm_count = torch.cuda.get_device_properties(local).multi_processor_count
+    if B >= sm_count * 256: names[0] = "k_mask_aggregate_serial"
     exact_macs = list(macs)                         # the oracle's per-round (exact) algorithm, stage by stage
     rlc = bls.GetBatchMode() == 1 and B >= 1024 and os.environ.get("HBLS_RLC", "1") != "0"
     if rlc:
         # batched form: slot 4 = coefficient scaling + group sums, slot 5 = (G+1)-pair Miller loop + ONE final exponentiation
         # per group of G rounds (G = 8 when the batch fills the chip that way, else 4).  Executed Fp-mul/sqr counts of that algorithm come from the device code compiled
         # for the host (tests/emu: emu_rlc_stage_counts; pinned by tests/test_emu_logic.py), x300 / x234 MAC32 each.
-        G = rlc_group_size(B, torch.cuda.get_device_properties(local).multi_processor_count)
+        G = rlc_group_size(B, sm_count)
         names[4], names[5] = "k_rlc_scale+k_rlc_group_sum", f"k_rlc_pairing_split<{G}>"
         macs = macs[:4] + list(rlc_exec_mac32(G))
     elif stage_ms[4] < 0.02 * stage_ms[5]:         # fused launch: Miller loops + final exponentiation in one kernel
@@ -313,7 +316,11 @@ def run_gpu(args):
     step_s = dev_ms / args.steps * 1e-3
     bytes_per_round = blen + 96 + MSG_LEN + 1
     roofline = {"bound": "int32-imad", "kernel": names[dom], "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TMAC32/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak,
+                # DRAM bytes of ONE launch of the dominant kernel from the committed ncu --set full capture of this workload
+                # (profiles/r1_ncu_rlc_pairing_g8.txt): per-thread Fp12 temporaries spilling past L2, not input traffic
+                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((names[dom], B)),
+                "traffic_source": "profiles/r1_ncu_rlc_pairing_g8.txt (dram__bytes_read.sum + dram__bytes_write.sum)" if (names[dom], B) in NCU_DRAM_BYTES_PER_LAUNCH else None,
                 "peak_source": "hbls_probe_mac32_per_s: register-resident IMAD.WIDE.U32 probe measured live on this GPU",
                 "algorithm": (f"random-linear-combination batch check, groups of {G} rounds (exact per-round pass only when a group fails)"
                               if rlc else "exact per-round FastAggregateVerify"),

@@ -136,6 +136,7 @@ template <class F> HB_NOINLINE void pt_mul(jac<F>& r, const jac<F>& p, const uin
 template <class F> HB_NOINLINE void pt_mul_zabs(jac<F>& r, const jac<F>& p) {
     jac<F> acc = p;
     for (int i = 62; i >= 0; i--) {
+        HB_USYNC();
         pt_dbl(acc, acc);
         if ((K_Z_ABS >> i) & 1) pt_add(acc, acc, p);
     }
@@ -159,6 +160,7 @@ template <class F> HB_NOINLINE void pt_mul_2d(jac<F>& r, const jac<F>& p, const 
     jac<F> t; pt_add(t, p, p2);
     jac<F> acc; pt_set_inf(acc);
     for (int i = 31; i >= 0; i--) {
+        HB_USYNC();
         pt_dbl(acc, acc);
         const int sel = ((a >> i) & 1) | (((b >> i) & 1) << 1);
         if (sel) pt_add(acc, acc, sel == 1 ? p : (sel == 2 ? p2 : t));
@@ -169,6 +171,7 @@ template <class F> HB_NOINLINE void pt_mul_2d_aff(jac<F>& r, const aff<F>& p, co
     jac<F> t; pt_from_aff(t, p); pt_add_mixed(t, t, p2);
     jac<F> acc; pt_set_inf(acc);
     for (int i = 31; i >= 0; i--) {
+        HB_USYNC();
         pt_dbl(acc, acc);
         const int sel = ((a >> i) & 1) | (((b >> i) & 1) << 1);
         if (sel == 3) pt_add(acc, acc, t);

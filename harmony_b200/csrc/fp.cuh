@@ -26,6 +26,17 @@
 #ifndef HB_OUTLINE_FP
 #define HB_OUTLINE_FP 0
 #endif
+// CTA-wide re-alignment points inside the uniform ladders / exponentiation loops of the thread-per-item kernels: with one
+// large CTA per SM all of its warps then walk the same instruction-cache lines (same idea as hb_lockstep in the pairing kernels).
+// Threads that left the kernel do not block a barrier; every call site is reached by whole CTAs in the common case.
+#ifndef HB_LOCKSTEP_T
+#define HB_LOCKSTEP_T 0
+#endif
+#if HB_LOCKSTEP_T && !defined(HB_HOST_EMU)
+#define HB_USYNC() __syncthreads()
+#else
+#define HB_USYNC() ((void)0)
+#endif
 #ifndef HB_OUTLINE_FP2
 #define HB_OUTLINE_FP2 1
 #endif

@@ -73,6 +73,15 @@ inline unsigned blocks_for(size_t n, unsigned tpb) { return (unsigned)((n + tpb 
 
 constexpr unsigned TPB = 64;      // heavy kernels: 64-thread CTAs
 // persistent launch geometry for the grid-stride kernels: at most `tpsm` resident threads per SM (HBLS_TPSM, default 384: measured 256: 267 ms, 384: 263 ms, 512: 280 ms per 303 104 rounds)
+// one large CTA per SM for the three big thread-per-round kernels when the library is built with HB_LOCKSTEP_T
+#if HB_LOCKSTEP_T
+static unsigned big_tpb() { static unsigned v = [] { const char* e = getenv("HBLS_TCTA"); return e ? (unsigned)atoi(e) : 384u; }(); return v; }
+static unsigned big_blocks(size_t n) { size_t need = (n + big_tpb() - 1) / big_tpb(); return (unsigned)(need < (size_t)g.sm_count ? need : (size_t)g.sm_count); }
+#else
+static unsigned big_tpb() { return TPB; }
+unsigned heavy_blocks(size_t n);
+static unsigned big_blocks(size_t n) { return heavy_blocks(n); }
+#endif
 unsigned heavy_blocks(size_t n) {
     static int tpsm = [] { const char* e = getenv("HBLS_TPSM"); int v = e ? atoi(e) : 384; return v < 64 ? 64 : v; }();
     size_t cap = (size_t)g.sm_count * (size_t)(tpsm / TPB);
@@ -120,13 +129,13 @@ static bool rlc_applies(size_t B, bool have_apk_jac) {
 void launch_verify_tail(size_t B, const VerifyBufs& v, const uint8_t* d_sig96, const uint8_t* d_msgs, uint32_t msg_len,
                         const uint8_t* ok_pk, uint8_t* d_results, cudaStream_t s, bool same_msg = false, const g1* apk_jac = nullptr) {
     STAGE_EV(2, s);
-    LAUNCH(k_g2_decode, heavy_blocks(B), TPB, s, B, d_sig96, v.sig, v.ok_sig, 1);
+    LAUNCH(k_g2_decode, big_blocks(B), big_tpb(), s, B, d_sig96, v.sig, v.ok_sig, 1);
     STAGE_EV(3, s);
     if (same_msg && B > 1) {
         LAUNCH(k_hash_to_g2, 1, TPB, s, (size_t)1, d_msgs, msg_len, v.hm, v.ok_hm);
         LAUNCH(k_broadcast_hm, blocks_for(B, 256), 256, s, B, v.hm, v.ok_hm);
     } else
-    LAUNCH(k_hash_to_g2, heavy_blocks(B), TPB, s, B, d_msgs, msg_len, v.hm, v.ok_hm);
+    LAUNCH(k_hash_to_g2, big_blocks(B), big_tpb(), s, B, d_msgs, msg_len, v.hm, v.ok_hm);
     STAGE_EV(4, s);
     static const int fuse_mode = [] { const char* e = getenv("HBLS_FUSE"); return e ? atoi(e) : -1; }();   // -1 auto, 0 split, 1 fused
     const bool fused = fuse_mode == 1 || (fuse_mode == -1 && B >= (size_t)g.sm_count * 256);
@@ -140,7 +149,7 @@ void launch_verify_tail(size_t B, const VerifyBufs& v, const uint8_t* d_sig96, c
         const size_t ng = B / G, nr = ng * G, tail = B - nr;
         const uint64_t s0 = g.rlc_seed[0] + 0x9e3779b97f4a7c15ull * (++g.rlc_calls), s1 = g.rlc_seed[1] ^ (g.rlc_calls << 32);
         cudaMemsetAsync(v.any_fail, 0, sizeof(int), s);
-        LAUNCH(k_rlc_scale, heavy_blocks(nr), TPB, s, nr, ng, apk_jac, v.sig, v.hm, v.ok_sig, v.ok_hm, s0, s1, v.pk_scaled, v.S, v.bad);
+        LAUNCH(k_rlc_scale, big_blocks(nr), big_tpb(), s, nr, ng, apk_jac, v.sig, v.hm, v.ok_sig, v.ok_hm, s0, s1, v.pk_scaled, v.S, v.bad);
         const bool full = 2 * ng >= (size_t)g.sm_count * HB_TPB_SPLIT;
         const unsigned pb = full ? split_blocks(2 * ng) : blocks_for(2 * ng, 64), pt = full ? HB_TPB_SPLIT : 64;
         if (G == 8) {
@@ -292,6 +301,8 @@ int hbls_init_device(int device) {
     cudaFuncSetAttribute(k_pairing_verify_split, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_hash_to_g2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_g2_decode, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    cudaFuncSetAttribute(k_rlc_scale, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    cudaFuncSetAttribute(k_mask_aggregate_serial, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_mask_aggregate, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     g.ready = true;
     return 0;

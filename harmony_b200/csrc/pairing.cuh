@@ -89,6 +89,9 @@ HB_DEV void miller_loop2(fp12& f, const g1a& p1, const g2a& q1, const g1a& p2, c
 // NP pairs at once with ONE shared accumulator: f = prod_k f_{|z|,Q_k}(P_k).  Used by the random-linear-combination
 // batch: rounds of a group contribute (-r_j apk_j, H(m_j)), the last pair is (B, sum_j r_j sigma_j).  P_k / Q_k stay in
 // global memory (read again at the five addition steps); only the running points T_k live in the thread.
+#ifndef HB_LOCKSTEP_PAIR
+#define HB_LOCKSTEP_PAIR 1
+#endif
 template <class E, int NP> HB_NOINLINE void miller_loop_multi(fp12_t<E>& f, const g1a* const* ps, const E* qx, const E* qy) {
     fp12_one(f);
     g2proj_t<E> T[NP];
@@ -97,11 +100,24 @@ template <class E, int NP> HB_NOINLINE void miller_loop_multi(fp12_t<E>& f, cons
     for (int i = 62; i >= 0; i--) {
         hb_lockstep<E>();
         fp12_sqr(f, f);
+#pragma unroll 1
         for (int k = 0; k < NP; k++) {
+            // long pair lists: re-align the CTA's warps inside the iteration too (instruction cache); measured on B200,
+            // 9 pairs: none 110 ms, every two pairs 97 ms
+#if HB_LOCKSTEP_PAIR == 1
+            if (NP > 4 && (k & 1) == 0 && k) hb_lockstep<E>();
+#elif HB_LOCKSTEP_PAIR >= 2
+            if (k) hb_lockstep<E>();
+#endif
             const fp px = ps[k]->x, py = ps[k]->y;          // staged into thread-local storage: field routines take local operands
-            ml_dbl(T[k], l0, l2, l3); fp2_mul_fp(l2, l2, px); fp2_mul_fp(l3, l3, py); fp12_mul_by_014(f, f, l0, l2, l3);
+            ml_dbl(T[k], l0, l2, l3); fp2_mul_fp(l2, l2, px); fp2_mul_fp(l3, l3, py);
+#if HB_LOCKSTEP_PAIR >= 3
+            hb_lockstep<E>();
+#endif
+            fp12_mul_by_014(f, f, l0, l2, l3);
         }
         if ((K_Z_ABS >> i) & 1) {
+#pragma unroll 1
             for (int k = 0; k < NP; k++) {
                 const fp px = ps[k]->x, py = ps[k]->y;
                 ml_add(T[k], qx[k], qy[k], l0, l2, l3); fp2_mul_fp(l2, l2, px); fp2_mul_fp(l3, l3, py); fp12_mul_by_014(f, f, l0, l2, l3);

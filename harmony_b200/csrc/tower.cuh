@@ -81,6 +81,7 @@ HB_NOINLINE void fp_pow(fp& r, const fp& a, const uint32_t* e) {
     bool started = false;
     for (int i = 95; i >= 0; i--) {
         uint32_t w = (e[i >> 3] >> (4 * (i & 7))) & 15u;
+        if ((i & 3) == 3) HB_USYNC();
         if (started) { fp_sqr(acc, acc); fp_sqr(acc, acc); fp_sqr(acc, acc); fp_sqr(acc, acc); }
         if (w) { if (started) fp_mul(acc, acc, tbl[w]); else { acc = tbl[w]; started = true; } }
     }
