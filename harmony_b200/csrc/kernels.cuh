@@ -252,7 +252,8 @@ __global__ void k_pairing_fixup(size_t B, const g2a* sig, const g1a* pk_neg, con
 // round that did not decode -- makes the exact per-round kernels run afterwards, so results stay exact booleans
 // (a bad round survives the batched test with probability 2^-64).
 #ifndef HB_RLC_G
-#define HB_RLC_G 4       // smallest group size (scratch is sized for it); the host picks 4 or 8 per call.  Measured best on B200 at 75 776 rounds/step (3: 76 ms, 4: 48 ms, 5: 68 ms, 7: 65 ms for the pairing stage)
+#define HB_RLC_G 4       // smallest group size (scratch is sized for it); the host picks 4 or 8 per call (hbls.cu).  At 75 776 rounds/step the
+                         // pairing stage measured 76 / 48 / 68 / 65 ms for G = 3 / 4 / 5 / 7: the group count must still fill the SMs
 #endif
 // Groups are STRIDED: group g = rounds {g, g + ng, g + 2 ng, ...}; the coefficient depends only on the position k inside the
 // group (r_k, fresh per call), so the 32 consecutive rounds of a warp share one scalar and the double-and-add ladders run

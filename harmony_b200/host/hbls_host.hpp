@@ -250,6 +250,8 @@ public:
     size_t BitmapLen() const { return (n_ + 7) >> 3; }
     const hbls_committee* handle() const { return h_; }
 };
+// batch entry points test large batches in random-linear-combination groups first (exact fallback); exactOnly forces the per-round algorithm
+inline void SetBatchMode(bool exactOnly) { hbls_set_batch_mode(exactOnly ? 0 : 1); }
 // == NewMask(pubKeys).SetMask(bitmap) ; aggSig.Deserialize ; aggSig.VerifyHash(mask.AggregatePublic, msg)
 inline int FastAggregateVerify(const Committee& c, const std::vector<uint8_t>& bitmap, const SerializedSignature& sig, const std::vector<uint8_t>& msg) {
     return hbls_aggregate_verify(c.handle(), bitmap.data(), bitmap.size(), sig.data(), msg.data(), msg.size());
@@ -359,5 +361,48 @@ public:
         return "";
     }
 };
+
+// ---- range form: engine.go:81-97 VerifyHeaders / stagedstreamsync/sig_verify.go:23-58 verify one header
+// signature per cgo round trip; here the block range of ONE committee epoch goes to the device in one call.
+struct HeaderSig {
+    bls::SerializedSignature commitSig; std::vector<uint8_t> commitBitmap; std::vector<uint8_t> commitPayload;   // payload = ConstructCommitPayload(...)
+};
+struct HeaderBatch {          // what hbls_aggregate_verify_batch consumes: same-length payloads, quorum-gated rounds only
+    size_t msgLen = 0; std::vector<size_t> index; std::vector<uint8_t> bitmaps, sigs, msgs;
+    size_t rounds() const { return index.size(); }
+};
+// Pure host step (no device): applies the checks of engine.go:619-634 that precede the pairing (bitmap length, quorum by
+// popcount) and packs the survivors by payload length (40 B pre-staking / 48 B staking eras never mix inside one call).
+inline std::vector<HeaderBatch> AssembleHeaderBatches(size_t committeeSize, const std::vector<HeaderSig>& headers, std::vector<std::string>& errs) {
+    const size_t blen = (committeeSize + 7) >> 3;
+    errs.assign(headers.size(), "");
+    std::vector<HeaderBatch> out;
+    for (size_t i = 0; i < headers.size(); i++) {
+        const HeaderSig& h = headers[i];
+        if (h.commitBitmap.size() != blen) { errs[i] = "deserialize signature and bitmap: mask.SetMask failed"; continue; }
+        if (quorum::CountOneBits(h.commitBitmap) < quorum::TwoThirdsSignersCount((int64_t)committeeSize)) { errs[i] = "not enough signature collected"; continue; }
+        if (h.commitPayload.empty() || h.commitPayload.size() > 64) { errs[i] = "invalid commit payload"; continue; }
+        HeaderBatch* b = nullptr;
+        for (auto& c : out) if (c.msgLen == h.commitPayload.size()) { b = &c; break; }
+        if (!b) { out.emplace_back(); b = &out.back(); b->msgLen = h.commitPayload.size(); }
+        b->index.push_back(i);
+        b->bitmaps.insert(b->bitmaps.end(), h.commitBitmap.begin(), h.commitBitmap.end());
+        b->sigs.insert(b->sigs.end(), h.commitSig.begin(), h.commitSig.end());
+        b->msgs.insert(b->msgs.end(), h.commitPayload.begin(), h.commitPayload.end());
+    }
+    return out;
+}
+// errs[i] == "" iff header i carries a valid quorum signature of the committee (same strings as verifySignature above)
+inline std::vector<std::string> VerifyHeaderSignatures(const bls::Committee& ec, const std::vector<HeaderSig>& headers) {
+    std::vector<std::string> errs;
+    for (auto& b : AssembleHeaderBatches(ec.Size(), headers, errs)) {
+        std::vector<uint8_t> res(b.rounds(), 0);
+        int rc = hbls_aggregate_verify_batch(ec.handle(), b.rounds(), b.bitmaps.data(), ec.BitmapLen(), b.sigs.data(), b.msgs.data(), b.msgLen, res.data());
+        for (size_t k = 0; k < b.rounds(); k++)
+            if (rc != 0) errs[b.index[k]] = "deserialize signature and bitmap";
+            else if (!res[k]) errs[b.index[k]] = "Unable to verify aggregated signature for block";
+    }
+    return errs;
+}
 }  // namespace chain
 }  // namespace harmony

@@ -30,6 +30,21 @@ int main() {
     CHECK(cache.Len() == 3 && !cache.Get("b", out) && cache.Get("c", out) && cache.Get("d", out) && out.v.d[0] == 4);
     std::vector<uint8_t> o; CHECK(bls::AggregateMasks({1, 2}, {4, 2}, o) && o == std::vector<uint8_t>({5, 2}) && !bls::AggregateMasks({1}, {1, 2}, o));
     bls::SerializedPublicKey z{}; CHECK(bls::IsEmpty(z) && bls::Hex(z).size() == 96);
+    // range form: quorum gate + packing by payload length (engine.go:619-634 checks before any pairing work)
+    {
+        std::vector<chain::HeaderSig> hs(5);
+        for (auto& x : hs) { x.commitBitmap.assign(1, 0x07); x.commitPayload.assign(48, 0x11); x.commitSig.fill(0x22); }   // committee of 4: quorum = 3 bits
+        hs[1].commitBitmap[0] = 0x03;                       // 2 of 4: below quorum
+        hs[2].commitBitmap.assign(2, 0xff);                 // wrong bitmap length
+        hs[3].commitPayload.assign(40, 0x33);               // pre-staking payload: its own batch
+        hs[4].commitSig.fill(0x44);
+        std::vector<std::string> errs;
+        auto batches = chain::AssembleHeaderBatches(4, hs, errs);
+        CHECK(errs[0].empty() && errs[1] == "not enough signature collected" && errs[2] == "deserialize signature and bitmap: mask.SetMask failed" && errs[3].empty() && errs[4].empty());
+        CHECK(batches.size() == 2 && batches[0].msgLen == 48 && batches[0].index == std::vector<size_t>({0, 4}) && batches[1].msgLen == 40 && batches[1].index == std::vector<size_t>({3}));
+        CHECK(batches[0].sigs.size() == 192 && batches[0].sigs[0] == 0x22 && batches[0].sigs[96] == 0x44 && batches[0].msgs.size() == 96 && batches[0].bitmaps.size() == 2);
+        CHECK(batches[1].msgs.size() == 40 && batches[1].msgs[0] == 0x33);
+    }
     // no CPU fallback: without blsInit (no device here) group operations fail instead of computing on the host
     bls_core::PublicKey q{}; std::vector<uint8_t> k48(48, 0); k48[0] = 1;
     CHECK(!q.Deserialize(k48));
