@@ -217,7 +217,7 @@ HB_NOINLINE bool g1_in_subgroup(const g1& p) {
 }
 
 // Batch-verification coefficient applied to one round: the 64-bit draw c = (b << 32 | a) stands for the scalar
-// s = a + b z^2 (mod r) -- 2^64 distinct values, and [z^2] is an endomorphism on both groups:
+// s = a + b z^2 (mod r) -- 2^63 distinct values (a is forced odd), and [z^2] is an endomorphism on both groups:
 //   G1: [z^2](x, y) = -phi(x, y) = (beta x, -y)      (g1_in_subgroup above: phi = -[z^2])
 //   G2: [z^2] = psi^2,  psi^2(x, y) = (N(cx) x, -y)   (psi = [p] = [z] on G2)
 // so both scalings are 32-step two-base ladders instead of 64-step ones.  Inputs must lie in G1 / G2 (the callers'

@@ -250,14 +250,14 @@ __global__ void k_pairing_fixup(size_t B, const g2a* sig, const g1a* pk_neg, con
 // prod_j [ e(B, sigma_j) e(-apk_j, H_j) ]^{r_j} == 1 with 64-bit r_j: the G rounds of a group share ONE Miller accumulator
 // (pairs (-r_j apk_j, H_j) plus (B, sum_j r_j sigma_j)) and ONE final exponentiation.  A group that fails -- or contains a
 // round that did not decode -- makes the exact per-round kernels run afterwards, so results stay exact booleans
-// (a bad round survives the batched test with probability 2^-64).
+// (a bad round survives the batched test with probability <= 2^-63).
 #ifndef HB_RLC_G
 #define HB_RLC_G 4       // smallest group size (scratch is sized for it); the host picks 4 or 8 per call (hbls.cu).  At 75 776 rounds/step the
                          // pairing stage measured 76 / 48 / 68 / 65 ms for G = 3 / 4 / 5 / 7: the group count must still fill the SMs
 #endif
 // Groups are STRIDED: group g = rounds {g, g + ng, g + 2 ng, ...}; the coefficient depends only on the position k inside the
 // group (r_k, fresh per call), so the 32 consecutive rounds of a warp share one scalar and the double-and-add ladders run
-// without divergence.  Sharing r_k across groups is sound: every group's test fails independently with probability 2^-64.
+// without divergence.  Sharing r_k across groups is sound: every group's test passes wrongly with probability <= 2^-63.
 HB_DEV uint64_t rlc_coeff(uint64_t s0, uint64_t s1, uint64_t j) {
     uint64_t x = j + s0;
     for (int r = 0; r < 2; r++) {

@@ -101,7 +101,7 @@ int hbls_aggregate_verify_batch(const hbls_committee* c, size_t B, const uint8_t
  * mode 1 (default): random-linear-combination groups -- 4 rounds share one Miller accumulator and one final exponentiation
  *   (prod_j [e(B, sigma_j) e(-apk_j, H_j)]^{r_j} == 1, fresh 64-bit r_j per call); if any group fails or holds an undecodable
  *   round, every round is recomputed exactly, so results are the exact booleans (a bad round survives the batched test
- *   with probability 2^-64).  Batches under 1024 rounds always use mode 0.
+ *   with probability <= 2^-63).  Batches under 1024 rounds always use mode 0.
  * mode 0: the exact per-round check only (identical semantics to N calls of hbls_aggregate_verify). */
 void hbls_set_batch_mode(int mode);
 int  hbls_get_batch_mode(void);
