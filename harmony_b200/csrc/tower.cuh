@@ -7,6 +7,10 @@
 #include "fp_wide.cuh"
 #include "hbls_constants.cuh"
 
+#ifdef HB_HOST_EMU
+#include <atomic>
+#include <thread>
+#endif
 namespace hb {
 // per-helper outlining switches (code size vs call overhead); -DHB_OL_<NAME>=0/1, default = HB_OUTLINE_FP2
 #ifndef HB_OL_ADD
@@ -281,9 +285,26 @@ HB_NOINLINE bool fp2_sqrt_anysign(fp2& r, const fp2& x) {
 // data-oblivious), because the exchanges use full-warp shuffles.
 struct fp2h { fp c; };
 #ifdef HB_HOST_EMU
-// host emulation runs one logical pair at a time: the partner component lives in a side slot
-struct fp2h_emu_ctx { int role; };
-static thread_local fp2h_emu_ctx hb_emu = {0};
+// host emulation (tests/emu): two host threads play the two lanes of ONE pair; role = lane parity, and a shuffle with the
+// partner lane is a rendezvous through a pair of slots (sequence numbers: publish, wait for the partner's value of the same
+// exchange, acknowledge so the partner may overwrite its slot at the next exchange)
+struct fp2h_emu_ctx { int role; uint64_t seq; };
+static thread_local fp2h_emu_ctx hb_emu = {0, 0};
+struct hb_emu_pair_t { std::atomic<uint32_t> slot[2]; std::atomic<uint64_t> pub[2], ack[2]; };
+static hb_emu_pair_t hb_emu_pair;
+static inline void hb_emu_pair_reset() { for (int i = 0; i < 2; i++) { hb_emu_pair.pub[i] = 0; hb_emu_pair.ack[i] = 0; } }
+static inline uint32_t hb_emu_exchange(uint32_t v) {
+    const int me = hb_emu.role, other = me ^ 1;
+    const uint64_t n = ++hb_emu.seq;
+    while (hb_emu_pair.ack[other].load(std::memory_order_acquire) < n - 1) std::this_thread::yield();   // partner consumed my previous value
+    hb_emu_pair.slot[me].store(v, std::memory_order_relaxed);
+    hb_emu_pair.pub[me].store(n, std::memory_order_release);
+    while (hb_emu_pair.pub[other].load(std::memory_order_acquire) < n) std::this_thread::yield();
+    const uint32_t got = hb_emu_pair.slot[other].load(std::memory_order_relaxed);
+    hb_emu_pair.ack[me].store(n, std::memory_order_release);
+    return got;
+}
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int) { return (T)hb_emu_exchange((uint32_t)v); }
 #endif
 HB_DEV int fp2h_role() {
 #ifdef HB_HOST_EMU
@@ -292,7 +313,6 @@ HB_DEV int fp2h_role() {
     return threadIdx.x & 1;
 #endif
 }
-#ifndef HB_HOST_EMU
 HB_DEV void fp2h_partner(fp& r, const fp& x) {
 #pragma unroll
     for (int j = 0; j < 12; j++) r.l[j] = __shfl_xor_sync(0xffffffffu, x.l[j], 1);
@@ -371,7 +391,6 @@ HB_NOINLINE void fp2_inv(fp2h& r, const fp2h& x) {
     fp t, m; fp_mul(t, x.c, n); fp_neg(m, t);
     r.c = t; fp_cmov(r.c, m, fp2h_role() == 1);
 }
-#endif  // !HB_HOST_EMU
 
 // Lock-step hint: with many resident warps the pairing is instruction-fetch bound (ncu: stall_no_instruction ~5 per
 // issue at 16 warps/SM) because warps drift through ~60 KB of hot code.  The lane-pair kernels keep every thread of a
@@ -457,7 +476,6 @@ template <class E> HB_DEV bool fp12_is_one(const fp12_t<E>& x) {
     const bool z3 = fp2_is_zero(x.c1.c0), z4 = fp2_is_zero(x.c1.c1), z5 = fp2_is_zero(x.c1.c2);
     return z0 & z1 & z2 & z3 & z4 & z5;
 }
-#ifndef HB_HOST_EMU
 // lane-pair carrier: each lane tests its own six components, ONE shuffle combines the pair's verdicts
 HB_DEV bool fp12_is_one(const fp12_t<fp2h>& x) {
     fp one; fp_one(one);
@@ -472,7 +490,6 @@ HB_DEV bool fp12_is_one(const fp12_t<fp2h>& x) {
     const int other = __shfl_xor_sync(0xffffffffu, mine, 1);
     return mine && other;
 }
-#endif
 template <class E> HB_NOINLINE void fp12_mul(fp12_t<E>& r, const fp12_t<E>& x, const fp12_t<E>& y) {
     hb_lockstep2<E>();
     fp6_t<E> v0, v1, s, t;

@@ -98,7 +98,7 @@ int hbls_aggregate_verify(const hbls_committee* c, const uint8_t* bitmap, size_t
 int hbls_aggregate_verify_batch(const hbls_committee* c, size_t B, const uint8_t* bitmaps, size_t blen,
                                 const uint8_t* sigs96, const uint8_t* msgs, size_t msg_len, uint8_t* results);
 /* How the two batch entries above check the pairing equations.
- * mode 1 (default): random-linear-combination groups -- 4 rounds share one Miller accumulator and one final exponentiation
+ * mode 1 (default): random-linear-combination groups -- 4 or 8 rounds share one Miller accumulator and one final exponentiation
  *   (prod_j [e(B, sigma_j) e(-apk_j, H_j)]^{r_j} == 1, fresh 64-bit r_j per call); if any group fails or holds an undecodable
  *   round, every round is recomputed exactly, so results are the exact booleans (a bad round survives the batched test
  *   with probability <= 2^-63).  Batches under 1024 rounds always use mode 0.

@@ -98,3 +98,64 @@ extern "C" int emu_legendre_check(const uint32_t* vals, int n) {
     for (int i = 0; i < n; i++) { fp a; for (int j = 0; j < 12; j++) a.l[j] = vals[12 * i + j]; if (fp_legendre(a) != fp_legendre_pow(a)) bad++; }
     return bad;
 }
+
+// ---- lane-pair (fp2h) code on two host threads: the same templates the split kernels instantiate, shuffles by rendezvous.
+// kind 0: exact round  -- miller_loop2<fp2h>(B, sig, -pk, H) + final_exp, compared with the single-thread fp2 form
+// kind 1: batched group of 4 -- miller_loop_multi<fp2h, 5> on the pairs produced by rlc_scale_pair, compared likewise
+// returns (split verdict) | (single-thread verdict << 1) | (Fp12 values identical << 2), or -1 on undecodable input
+extern "C" int emu_split_pairing(int kind, const uint8_t* pks48, const uint8_t* sigs96, const uint8_t* msgs, uint32_t len) {
+    const int G = kind ? 4 : 1, NPmax = 5;
+    g1a P[NPmax]; fp2 qx[NPmax], qy[NPmax]; const g1a* ps[NPmax];
+    int np;
+    if (kind == 0) {
+        g1 pk; g2 sg, h;
+        if (!g1_deserialize(pk, pks48, true) || !g2_deserialize(sg, sigs96, true) || !map_to_g2(h, msgs, len)) return -1;
+        g2a sa, ha; pt_to_aff(sa, sg); pt_to_aff(ha, h);
+        fp_set(P[0].x, K_G1_X); fp_set(P[0].y, K_G1_Y); qx[0] = sa.x; qy[0] = sa.y;
+        pt_to_aff(P[1], pk); fp_neg(P[1].y, P[1].y); qx[1] = ha.x; qy[1] = ha.y;
+        np = 2;
+    } else {
+        g2 acc; pt_set_inf(acc);
+        for (int k = 0; k < G; k++) {
+            g1 pk; g2 sg, h;
+            if (!g1_deserialize(pk, pks48 + 48 * k, true) || !g2_deserialize(sg, sigs96 + 96 * k, true) || !map_to_g2(h, msgs + len * k, len)) return -1;
+            g2a sa, ha; pt_to_aff(sa, sg); pt_to_aff(ha, h);
+            g1 rp; g2 rs; rlc_scale_pair(rp, rs, pk, sa, 0x9e3779b97f4a7c15ull * (k + 3));
+            pt_to_aff(P[k], rp); fp_neg(P[k].y, P[k].y); qx[k] = ha.x; qy[k] = ha.y; pt_add(acc, acc, rs);
+        }
+        g2a sga; pt_to_aff(sga, acc); qx[G] = sga.x; qy[G] = sga.y;
+        fp_set(P[G].x, K_G1_X); fp_set(P[G].y, K_G1_Y);
+        np = G + 1;
+    }
+    for (int k = 0; k < np; k++) ps[k] = &P[k];
+    // single-thread reference with the same templates over the plain Fp2 carrier
+    fp12 ref;
+    if (np == 2) { g2a q0, q1; q0.x = qx[0]; q0.y = qy[0]; q1.x = qx[1]; q1.y = qy[1]; miller_loop2(ref, P[0], q0, P[1], q1); }
+    else miller_loop_multi<fp2, 5>(ref, ps, qx, qy);
+    final_exp(ref, ref);
+    const int ref_one = fp12_is_one(ref) ? 1 : 0;
+    // the two lanes
+    fp12_t<fp2h> out[2]; int verdict[2] = {0, 0};
+    hb_emu_pair_reset();
+    auto lane = [&](int role) {
+        hb_emu.role = role; hb_emu.seq = 0;
+        fp2h hx[NPmax], hy[NPmax];
+        for (int k = 0; k < np; k++) { hx[k].c = role ? qx[k].b : qx[k].a; hy[k].c = role ? qy[k].b : qy[k].a; }
+        fp12_t<fp2h> m;
+        if (np == 2) miller_loop2<fp2h>(m, P[0], hx[0], hy[0], P[1], hx[1], hy[1], true, true);
+        else miller_loop_multi<fp2h, 5>(m, ps, hx, hy);
+        final_exp(m, m);
+        verdict[role] = fp12_is_one(m) ? 1 : 0;
+        out[role] = m;
+    };
+    std::thread t1(lane, 1); lane(0); t1.join();
+    hb_emu.role = 0;
+    // lane 0 holds the real parts, lane 1 the imaginary parts of the 6 Fp2 coefficients
+    const fp2* rc[6] = {&ref.c0.c0, &ref.c0.c1, &ref.c0.c2, &ref.c1.c0, &ref.c1.c1, &ref.c1.c2};
+    const fp2h* l0[6] = {&out[0].c0.c0, &out[0].c0.c1, &out[0].c0.c2, &out[0].c1.c0, &out[0].c1.c1, &out[0].c1.c2};
+    const fp2h* l1[6] = {&out[1].c0.c0, &out[1].c0.c1, &out[1].c0.c2, &out[1].c1.c0, &out[1].c1.c1, &out[1].c1.c2};
+    bool same = true;
+    for (int i = 0; i < 6; i++) same = same && fp_eq(rc[i]->a, l0[i]->c) && fp_eq(rc[i]->b, l1[i]->c);
+    if (verdict[0] != verdict[1]) return -2;
+    return verdict[0] | (ref_one << 1) | ((same ? 1 : 0) << 2);
+}
