@@ -22,7 +22,6 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     std::mutex mu;
     uint8_t* scratch = nullptr; size_t scratch_cap = 0;     // device bump arena
-    uint8_t* pinned = nullptr; size_t pinned_cap = 0;       // host staging (pinned)
     std::atomic<uint64_t> launches{0};
     bool stage_timing = false; bool stage_valid = false;
     int batch_mode = 1;                                     // 1: random-linear-combination groups + exact fallback, 0: exact per round
@@ -56,14 +55,6 @@ int reserve(size_t bytes) {
     size_t cap = bytes + bytes / 4;
     CK(cudaMalloc(&g.scratch, cap));
     g.scratch_cap = cap;
-    return 0;
-}
-int reserve_pinned(size_t bytes) {
-    if (bytes <= g.pinned_cap) return 0;
-    if (g.pinned) CK(cudaFreeHost(g.pinned));
-    g.pinned = nullptr; g.pinned_cap = 0;
-    CK(cudaMallocHost(&g.pinned, bytes + bytes / 4 + 4096));
-    g.pinned_cap = bytes + bytes / 4 + 4096;
     return 0;
 }
 unsigned split_blocks(size_t nthreads);
@@ -387,8 +378,7 @@ int blsVerifyHash(const blsSignature* sig, const blsPublicKey* pub, const void* 
     if (reserve(verify_scratch_bytes(1) + 4096)) return 0;
     Arena ar{g.scratch, 0, g.scratch_cap};
     VerifyBufs v = carve_verify(ar, 1);
-    g2* dsig = ar.take<g2>(1); g2a* dsiga = v.sig; uint8_t* dmsg = ar.take<uint8_t>(64); uint8_t* dres = ar.take<uint8_t>(1);
-    (void)dsiga;
+    g2* dsig = ar.take<g2>(1); uint8_t* dmsg = ar.take<uint8_t>(64); uint8_t* dres = ar.take<uint8_t>(1);
     cudaMemcpyAsync(v.apk, pub, 144, cudaMemcpyHostToDevice, g.stream);
     cudaMemcpyAsync(dsig, sig, 288, cudaMemcpyHostToDevice, g.stream);
     if (size) cudaMemcpyAsync(dmsg, h, size, cudaMemcpyHostToDevice, g.stream);
