@@ -1,0 +1,93 @@
+"""CPU-only: the __global__ kernels of harmony_b200/csrc/kernels.cuh run on the host (tests/emu/emu_kernels.cpp) in the launch
+order of hbls.cu's aggregate-verify pipeline -- complement-side mask sums, signature decode, hash-to-G2, batched groups of 4 with
+the lane-pair pairing kernel on two host threads, finish flags, exact fallback and tail -- against the oracle's per-round verdicts.
+Test infrastructure only: the product path has no CPU implementation (tests/test_capi_symbols.py)."""
+import ctypes, os, random, subprocess
+import pytest
+import oracle_lib
+from harmony_b200 import workload as wl
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+@pytest.fixture(scope="module")
+def emuk():
+    src = os.path.join(ROOT, "tests", "emu", "emu_kernels.cpp")
+    out = os.path.join(ROOT, "tests", "emu", "libhbls_emu_kernels.so")
+    csrc = os.path.join(ROOT, "harmony_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", out, src])
+    L = ctypes.CDLL(out)
+    L.emu_aggregate_verify_batch.argtypes = [ctypes.c_int, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t,
+                                             ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint64,
+                                             ctypes.c_char_p, ctypes.POINTER(ctypes.c_int), ctypes.c_char_p, ctypes.c_int]
+    return L
+
+@pytest.fixture(scope="module")
+def oracle():
+    return oracle_lib.load()
+
+def make_batch(oracle, n, B, seed):
+    """n-key committee, B rounds with distinct bitmaps (some above n/2: complement sums) and distinct 48-byte payloads."""
+    rng = random.Random(seed)
+    sks = [wl.seeded_sk("emuk", i) for i in range(n)]
+    pks = [oracle.get_public_key(wl.sk_bytes(k)) for k in sks]
+    blen = (n + 7) // 8
+    R = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
+    bitmaps, sigs, msgs = [], [], []
+    for j in range(B):
+        k = [n, n - 1, n // 2, 1, n - 2, 3][j % 6]
+        members = rng.sample(range(n), k)
+        bm = bytearray(blen)
+        for i in members: bm[i >> 3] |= 1 << (i & 7)
+        m = wl.commit_payload("emuk", j)
+        agg_sk = sum(sks[i] for i in members) % R
+        bitmaps.append(bytes(bm)); msgs.append(m); sigs.append(oracle.sign_hash(wl.sk_bytes(agg_sk), m))
+    return pks, blen, bitmaps, sigs, msgs
+
+def run(emuk, mode, pks, blen, bitmaps, sigs, msgs, seed=(0x1234, 0x9876), G=4):
+    B = len(sigs); res = ctypes.create_string_buffer(B); gok = ctypes.create_string_buffer(B // 4 + 1); af = ctypes.c_int(-1)
+    rc = emuk.emu_aggregate_verify_batch(mode, len(pks), b"".join(pks), B, b"".join(bitmaps), blen, b"".join(sigs), b"".join(msgs), 48,
+                                         seed[0], seed[1], res, ctypes.byref(af), gok, G)
+    assert rc == 0
+    return res.raw[:B], af.value, gok.raw[:B // G]
+
+def expected(oracle, pks, bitmaps, sigs, msgs):
+    h = oracle.committee(pks)
+    return bytes(1 if oracle.committee_aggregate_verify(h, bm, s, m) else 0 for bm, s, m in zip(bitmaps, sigs, msgs))
+
+def test_pipeline_all_valid_batched(emuk, oracle):
+    pks, blen, bitmaps, sigs, msgs = make_batch(oracle, 10, 9, seed=5)          # 2 groups of 4 (strided) + a tail of 1
+    res, any_fail, gok = run(emuk, 1, pks, blen, bitmaps, sigs, msgs)
+    assert res == b"\x01" * 9 and any_fail == 0 and gok == b"\x01\x01"
+    assert expected(oracle, pks, bitmaps, sigs, msgs) == res
+
+def test_pipeline_bad_rounds_fall_back_to_exact(emuk, oracle):
+    pks, blen, bitmaps, sigs, msgs = make_batch(oracle, 10, 9, seed=6)
+    sigs[5] = sigs[2]                                    # valid point, wrong round: group 1 (rounds 1, 3, 5, 7) must fail
+    sigs[8] = b"\xff" * 96                               # undecodable, in the exactly-verified tail
+    want = expected(oracle, pks, bitmaps, sigs, msgs)
+    assert want == b"\x01\x01\x01\x01\x01\x00\x01\x01\x00"
+    res, any_fail, gok = run(emuk, 1, pks, blen, bitmaps, sigs, msgs)
+    assert gok == b"\x01\x00" and any_fail == 1 and res == want
+    res0, _, _ = run(emuk, 0, pks, blen, bitmaps, sigs, msgs)                   # exact mode gives the same booleans
+    assert res0 == want
+
+def test_pipeline_irregular_rounds(emuk, oracle):
+    """Empty bitmap (identity aggregate key) and an all-zero signature: the batched form flags them, the exact pass
+    (lane-pair kernel result 0xFF -> k_pairing_fixup) decides exactly as the oracle does."""
+    pks, blen, bitmaps, sigs, msgs = make_batch(oracle, 10, 8, seed=7)
+    bitmaps[1] = bytes(blen)
+    sigs[6] = bytes(96)
+    want = expected(oracle, pks, bitmaps, sigs, msgs)
+    res, any_fail, gok = run(emuk, 1, pks, blen, bitmaps, sigs, msgs)
+    assert any_fail == 1 and res == want
+
+def test_pipeline_groups_of_eight(emuk, oracle):
+    pks, blen, bitmaps, sigs, msgs = make_batch(oracle, 12, 17, seed=8)         # 2 strided groups of 8 + a tail of 1
+    res, any_fail, gok = run(emuk, 1, pks, blen, bitmaps, sigs, msgs, G=8)
+    assert res == b"\x01" * 17 and any_fail == 0 and gok == b"\x01\x01"
+    msgs[4] = bytes([msgs[4][0] ^ 1]) + msgs[4][1:]      # round 4 = group 0 (even rounds): fails, exact pass sorts it out
+    want = expected(oracle, pks, bitmaps, sigs, msgs)
+    res, any_fail, gok = run(emuk, 1, pks, blen, bitmaps, sigs, msgs, G=8)
+    assert gok == b"\x00\x01" and any_fail == 1 and res == want and want[4] == 0 and sum(want) == 16
