@@ -119,6 +119,21 @@ template <class F> HB_NOINLINE void pt_to_aff(aff<F>& r, const jac<F>& p) {
     f_mul(r.x, p.x, zi2); f_mul(zi2, zi2, zi); f_mul(r.y, p.y, zi2);
 }
 
+// Montgomery's trick over K elements held by ONE thread: z[k] <- 1/z[k] with a single inversion (3 (K - 1) extra products);
+// entries flagged skip are left untouched.  A persistent thread that handles several items in turn shares their inversions.
+template <class F, int K> HB_NOINLINE void f_batch_inv(F* z, const bool* skip) {
+    F pre[K], acc; f_one(acc);
+    for (int k = 0; k < K; k++) { pre[k] = acc; if (!skip[k]) f_mul(acc, acc, z[k]); }
+    F inv; f_inv(inv, acc);
+    for (int k = K - 1; k >= 0; k--) if (!skip[k]) { F t; f_mul(t, inv, pre[k]); f_mul(inv, inv, z[k]); z[k] = t; }
+}
+// affine form of p given zi = 1 / p.z (identity -> the all-zero encoding)
+template <class F> HB_DEV void pt_to_aff_zinv(aff<F>& r, const jac<F>& p, const F& zi) {
+    if (pt_is_inf(p)) { f_zero(r.x); f_zero(r.y); return; }
+    F zi2; f_sqr(zi2, zi);
+    f_mul(r.x, p.x, zi2); f_mul(zi2, zi2, zi); f_mul(r.y, p.y, zi2);
+}
+
 // r = [k]p, k = nw little-endian 32-bit words; 4-bit fixed window, uniform control flow
 template <class F> HB_NOINLINE void pt_mul(jac<F>& r, const jac<F>& p, const uint32_t* k, int nw) {
     jac<F> tbl[16];
@@ -332,6 +347,42 @@ HB_NOINLINE bool sw_map_g2(g2& r, const fp2& t) {
     r.x = x; r.y = y; fp2_one(r.z);
     return true;
 }
+#if defined(HB_BATCH_INV) && HB_BATCH_INV
+// The same map in two halves around its single Fp2 inversion, so that a thread which maps several messages in turn can share
+// that inversion (f_batch_inv): pre() yields d = u * c1 t, post() continues from dinv = 1/d exactly as sw_map_g2 does.
+HB_NOINLINE bool sw_map_g2_pre(fp2& u, fp2& ct, fp2& d, const fp2& t) {
+    if (fp2_is_zero(t)) return false;
+    fp c1, one; fp2 bb; fp_set(c1, K_SW_C1); fp_one(one); fp2_const(bb, K_B2);
+    fp2_sqr(u, t); fp2_add(u, u, bb); fp_add(u.a, u.a, one);
+    if (fp2_is_zero(u)) return false;
+    fp2_mul_fp(ct, t, c1);
+    fp2_mul(d, u, ct);
+    return true;
+}
+HB_NOINLINE bool sw_map_g2_post(g2& r, const fp2& t, const fp2& u, const fp2& ct, const fp2& dinv) {
+    fp n, c2, one; fp2 w, x, y, g, bb;
+    fp_set(c2, K_SW_C2); fp_one(one); fp2_const(bb, K_B2);
+    bool negative = false;
+    if (!fp_is_zero(t.b)) { fp2_norm(n, t); negative = fp_legendre(n) < 0; }
+    fp2 x2, x3, g2v;
+    fp2_sqr(w, ct); fp2_mul(w, w, dinv);
+    fp2_sqr(x3, u); fp2_mul(x3, x3, dinv); fp2_sqr(x3, x3); fp_add(x3.a, x3.a, one);
+    fp2_mul(x, t, w); fp2_neg(x, x); fp_add(x.a, x.a, c2);
+    fp2_neg(x2, x); fp_sub(x2.a, x2.a, one);
+    fp2_sqr(g, x); fp2_mul(g, g, x); fp2_add(g, g, bb);
+    fp2_sqr(g2v, x2); fp2_mul(g2v, g2v, x2); fp2_add(g2v, g2v, bb);
+    fp n1, n2; fp2_norm(n1, g); fp2_norm(n2, g2v);
+    const bool sq1 = fp_legendre(n1) >= 0, sq2 = fp_legendre(n2) >= 0;
+    if (!sq1) {
+        if (sq2) { x = x2; g = g2v; }
+        else { x = x3; fp2_sqr(g, x); fp2_mul(g, g, x); fp2_add(g, g, bb); }
+    }
+    if (!fp2_sqrt(y, g)) return false;
+    if (negative) fp2_neg(y, y);
+    r.x = x; r.y = y; fp2_one(r.z);
+    return true;
+}
+#endif
 // Budroni-Pintore cofactor clearing: [z^2 - z - 1]P + psi([z - 1]P) + psi^2([2]P)   (plain h2 gives other bytes)
 HB_NOINLINE void g2_clear_cofactor(g2& r, const g2& p) {
     g2 zp, z2p, t1, t2, t3, np;

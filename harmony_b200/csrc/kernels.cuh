@@ -145,7 +145,45 @@ __global__ void __launch_bounds__(HB_SUM_THREADS) k_g2_sum(size_t n, const g2a* 
 }
 
 // ---- message -> G2 (hash part of R6/R7), affine output
+// HB_BATCH_INV (experimental, off): a persistent thread converts HB_BATCH_K of its items to affine with ONE inversion
+#ifndef HB_BATCH_INV
+#define HB_BATCH_INV 0
+#endif
+#ifndef HB_BATCH_K
+#define HB_BATCH_K 4
+#endif
 __global__ void k_hash_to_g2(size_t n, const uint8_t* msgs, uint32_t msg_len, g2a* out, uint8_t* ok) {
+#if HB_BATCH_INV
+  for (size_t i0 = HB_TID; i0 < n; i0 += (size_t)HB_BATCH_K * HB_STRIDE) {
+    g2 h[HB_BATCH_K]; fp2 z[HB_BATCH_K], t[HB_BATCH_K], u[HB_BATCH_K], ct[HB_BATCH_K]; bool skip[HB_BATCH_K], good[HB_BATCH_K];
+    for (int k = 0; k < HB_BATCH_K; k++) {
+        const size_t i = i0 + (size_t)k * HB_STRIDE;
+        good[k] = false; skip[k] = true;
+        if (i >= n) continue;
+        fp_zero(t[k].b); hash_to_fp(t[k].a, msgs + (size_t)msg_len * i, msg_len);
+        good[k] = sw_map_g2_pre(u[k], ct[k], z[k], t[k]);
+        skip[k] = !good[k];
+    }
+    f_batch_inv<fp2, HB_BATCH_K>(z, skip);                     // the maps' (u c1 t)^-1
+    for (int k = 0; k < HB_BATCH_K; k++) {
+        if (skip[k]) continue;
+        g2 a;
+        good[k] = sw_map_g2_post(a, t[k], u[k], ct[k], z[k]);
+        if (good[k]) g2_clear_cofactor(h[k], a);
+        skip[k] = !good[k] || pt_is_inf(h[k]);
+        if (!skip[k]) z[k] = h[k].z;
+    }
+    f_batch_inv<fp2, HB_BATCH_K>(z, skip);                     // -> affine
+    for (int k = 0; k < HB_BATCH_K; k++) {
+        const size_t i = i0 + (size_t)k * HB_STRIDE;
+        if (i >= n) continue;
+        g2a a;
+        if (skip[k]) { fp2_zero(a.x); fp2_zero(a.y); } else pt_to_aff_zinv(a, h[k], z[k]);
+        out[i] = a; ok[i] = good[k] ? 1 : 0;
+    }
+  }
+  return;
+#endif
   for (size_t i = HB_TID; i < n; i += HB_STRIDE) {
     g2 h; bool good = map_to_g2(h, msgs + (size_t)msg_len * i, msg_len);
     g2a a;
@@ -268,6 +306,32 @@ HB_DEV uint64_t rlc_coeff(uint64_t s0, uint64_t s1, uint64_t j) {
 // per round: P_j = -r_j apk_j (affine), S_j = r_j sigma_j (Jacobian), bad_j
 __global__ void k_rlc_scale(size_t B, size_t ng, const g1* apk, const g2a* sig, const g2a* hm, const uint8_t* ok_sig, const uint8_t* ok_hm,
                             uint64_t s0, uint64_t s1, g1a* pk_scaled_neg, g2* S, uint8_t* bad) {
+#if HB_BATCH_INV
+  for (size_t j0 = HB_TID; j0 < B; j0 += (size_t)HB_BATCH_K * HB_STRIDE) {
+    g1 ra[HB_BATCH_K]; fp z[HB_BATCH_K]; bool skip[HB_BATCH_K];
+    for (int k = 0; k < HB_BATCH_K; k++) {
+        const size_t j = j0 + (size_t)k * HB_STRIDE;
+        skip[k] = true;
+        if (j >= B) continue;
+        const uint64_t r = rlc_coeff(s0, s1, j / ng);
+        g1 a = apk[j]; g2a sg = sig[j]; g2a h = hm[j];
+        const bool b = !ok_sig[j] || !ok_hm[j] || pt_is_inf(a) || aff_is_inf(sg) || aff_is_inf(h);
+        g2 rs; rlc_scale_pair(ra[k], rs, a, sg, r);
+        S[j] = rs; bad[j] = b ? 1 : 0;
+        skip[k] = pt_is_inf(ra[k]);
+        if (!skip[k]) z[k] = ra[k].z;
+    }
+    f_batch_inv<fp, HB_BATCH_K>(z, skip);
+    for (int k = 0; k < HB_BATCH_K; k++) {
+        const size_t j = j0 + (size_t)k * HB_STRIDE;
+        if (j >= B) continue;
+        g1a pa;
+        if (skip[k]) { fp_zero(pa.x); fp_zero(pa.y); } else { pt_to_aff_zinv(pa, ra[k], z[k]); fp_neg(pa.y, pa.y); }
+        pk_scaled_neg[j] = pa;
+    }
+  }
+  return;
+#endif
   for (size_t j = HB_TID; j < B; j += HB_STRIDE) {
     const uint64_t r = rlc_coeff(s0, s1, j / ng);
     g1 a = apk[j]; g2a sg = sig[j]; g2a h = hm[j];

@@ -9,14 +9,18 @@ from harmony_b200 import workload as wl
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-@pytest.fixture(scope="module")
-def emuk():
+# "batch_inv" = the experimental HB_BATCH_INV build of the kernels (one shared inversion per 4 items of a persistent thread):
+# kept correct on the CPU so that a later round only has to time it on the GPU
+@pytest.fixture(scope="module", params=["default", "batch_inv"])
+def emuk(request):
+    variant = request.param
     src = os.path.join(ROOT, "tests", "emu", "emu_kernels.cpp")
-    out = os.path.join(ROOT, "tests", "emu", "libhbls_emu_kernels.so")
+    out = os.path.join(ROOT, "tests", "emu", "libhbls_emu_kernels.so" if variant == "default" else f"libhbls_emu_kernels_{variant}.so")
     csrc = os.path.join(ROOT, "harmony_b200", "csrc")
     deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-o", out, src])
+        flags = ["-DHB_BATCH_INV=1"] if variant == "batch_inv" else []
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread"] + flags + ["-o", out, src])
     L = ctypes.CDLL(out)
     L.emu_aggregate_verify_batch.argtypes = [ctypes.c_int, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t,
                                              ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint64,
