@@ -97,16 +97,26 @@ unsigned split_blocks(size_t nthreads) {
 // ------------------------------------------------------------------ one verification pass over device-resident inputs.
 // pk_neg: affine -apk (or -pk) per round; sig/hm decoded inside.  arena must hold verify_scratch_bytes(B).
 size_t verify_scratch_bytes(size_t B) {
+#if HB_FALLBACK_LIST
+    return B * (sizeof(g2a) * 2 + sizeof(g1a) * 2 + sizeof(g1) + sizeof(g2) + sizeof(fp12) * 2 + 16 + 4) + (B / HB_RLC_G + 1) * (sizeof(g2a) + 8) + 33 * 256;
+#endif
     return B * (sizeof(g2a) * 2 + sizeof(g1a) * 2 + sizeof(g1) + sizeof(g2) + sizeof(fp12) * 2 + 16) + (B / HB_RLC_G + 1) * (sizeof(g2a) + 8) + 32 * 256;
 }
 struct VerifyBufs { g2a* sig; g2a* hm; g1a* pkneg; g1* apk; fp12* f; uint8_t* ok_sig; uint8_t* ok_hm; uint8_t* ok_pk;
-                    g1a* pk_scaled; g2* S; uint8_t* bad; g2a* Sg; uint8_t* group_ok; int* any_fail; };
+                    g1a* pk_scaled; g2* S; uint8_t* bad; g2a* Sg; uint8_t* group_ok; int* any_fail;
+#if HB_FALLBACK_LIST
+                    uint32_t* fail_list; unsigned* fail_count;
+#endif
+};
 VerifyBufs carve_verify(Arena& ar, size_t B) {
     VerifyBufs v;
     v.sig = ar.take<g2a>(B); v.hm = ar.take<g2a>(B); v.pkneg = ar.take<g1a>(B); v.apk = ar.take<g1>(B);
     v.f = ar.take<fp12>(2 * B); v.ok_sig = ar.take<uint8_t>(B); v.ok_hm = ar.take<uint8_t>(B); v.ok_pk = ar.take<uint8_t>(B);
     v.pk_scaled = ar.take<g1a>(B); v.S = ar.take<g2>(B); v.bad = ar.take<uint8_t>(B);
     v.Sg = ar.take<g2a>(B / HB_RLC_G + 1); v.group_ok = ar.take<uint8_t>(B / HB_RLC_G + 1); v.any_fail = ar.take<int>(1);
+#if HB_FALLBACK_LIST
+    v.fail_list = ar.take<uint32_t>(B); v.fail_count = ar.take<unsigned>(1);
+#endif
     return v;
 }
 // batched (random-linear-combination) form applies: default mode, lane-pair kernels, Jacobian apk at hand, batch large enough
@@ -153,6 +163,18 @@ void launch_verify_tail(size_t B, const VerifyBufs& v, const uint8_t* d_sig96, c
             LAUNCH(k_rlc_pairing_split<4>, pb, pt, s, ng, v.pk_scaled, v.hm, v.Sg, v.bad, v.group_ok);
         }
         LAUNCH(k_rlc_finish, blocks_for(nr, 256), 256, s, nr, ng, v.group_ok, d_results, v.any_fail);
+#if HB_FALLBACK_LIST
+        // exact pass over the rounds of failed groups only (compacted on the device; the launches are sized for the worst case
+        // and return at once when the list is short or empty)
+        cudaMemsetAsync(v.fail_count, 0, sizeof(unsigned), s);
+        LAUNCH(k_rlc_collect_failed, blocks_for(nr, 256), 256, s, nr, ng, v.group_ok, v.fail_list, v.fail_count);
+        LAUNCH(k_g1_normalize_list, heavy_blocks(B), TPB, s, v.fail_count, v.fail_list, apk_jac, v.pkneg, 1);
+        if (2 * B >= (size_t)g.sm_count * HB_TPB_SPLIT)
+            LAUNCH(k_pairing_verify_split_list, split_blocks(2 * B), HB_TPB_SPLIT, s, v.fail_count, v.fail_list, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
+        else
+            LAUNCH(k_pairing_verify_split_list, blocks_for(2 * B, 64), 64, s, v.fail_count, v.fail_list, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
+        LAUNCH(k_pairing_fixup_list, heavy_blocks(B), TPB, s, v.fail_count, v.fail_list, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
+#else
         // exact per-round pass: returns immediately unless a group failed (then every round is recomputed exactly)
         LAUNCH(k_g1_normalize, blocks_for(B, TPB), TPB, s, B, apk_jac, v.pkneg, 1, (const int*)v.any_fail);
         if (2 * B >= (size_t)g.sm_count * HB_TPB_SPLIT)
@@ -160,6 +182,7 @@ void launch_verify_tail(size_t B, const VerifyBufs& v, const uint8_t* d_sig96, c
         else
             LAUNCH(k_pairing_verify_split, blocks_for(2 * B, 64), 64, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results, v.any_fail);
         LAUNCH(k_pairing_fixup, heavy_blocks(B), TPB, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results, v.any_fail);
+#endif
         if (tail) {       // the < G rounds that do not fill a group are always verified exactly
             LAUNCH(k_g1_normalize, 1, TPB, s, tail, apk_jac + nr, v.pkneg + nr, 1, (const int*)nullptr);
             LAUNCH(k_pairing_verify_split, blocks_for(2 * tail, 64), 64, s, tail, v.sig + nr, v.pkneg + nr, v.hm + nr, v.ok_sig + nr, v.ok_hm + nr,

@@ -389,6 +389,69 @@ __global__ void k_rlc_finish(size_t nrounds, size_t ngroups, const uint8_t* grou
     if (!ok) atomicOr(any_fail, 1);
 }
 
+// HB_FALLBACK_LIST (experimental, off): when groups fail, re-verify ONLY their rounds exactly (compacted index list) instead of
+// the whole batch -- one bad signature among 3*10^5 rounds then costs microseconds, not a second full pass.
+#ifndef HB_FALLBACK_LIST
+#define HB_FALLBACK_LIST 0
+#endif
+#if HB_FALLBACK_LIST
+__global__ void k_rlc_collect_failed(size_t nrounds, size_t ngroups, const uint8_t* group_ok, uint32_t* list, unsigned* count) {
+    size_t j = HB_TID; if (j >= nrounds) return;
+    if (!group_ok[j % ngroups]) list[atomicAdd(count, 1u)] = (uint32_t)j;
+}
+__global__ void k_g1_normalize_list(const unsigned* count, const uint32_t* list, const g1* in, g1a* out, int negate) {
+  const size_t n = *count;
+  for (size_t i = HB_TID; i < n; i += HB_STRIDE) {
+    const size_t j = list[i];
+    g1 p = in[j]; g1a a; pt_to_aff(a, p);
+    if (negate) fp_neg(a.y, a.y);
+    out[j] = a;
+  }
+}
+// k_pairing_verify_split over the listed rounds only (same body, indirect round index)
+__global__ void __launch_bounds__(HB_TPB_SPLIT, HB_MINBLOCKS_SPLIT) k_pairing_verify_split_list(const unsigned* count, const uint32_t* list, const g2a* sig, const g1a* pk_neg,
+                                 const g2a* hm, const uint8_t* ok_a, const uint8_t* ok_b, const uint8_t* ok_c, uint8_t* results) {
+    const size_t B = *count;
+    if (B == 0) return;
+    const int role = threadIdx.x & 1;
+    const size_t ppg = HB_STRIDE >> 1;
+    for (size_t it = 0; ; it++) {
+        const size_t warp_first = it * ppg + ((HB_TID & ~(size_t)31) >> 1);
+        if (warp_first >= B) break;
+        const size_t i = it * ppg + (HB_TID >> 1);
+        const bool valid = i < B;
+        const size_t jj = list[valid ? i : B - 1];
+        bool good = (!ok_a || ok_a[jj]) && (!ok_b || ok_b[jj]) && (!ok_c || ok_c[jj]);
+        g1a gen, p2 = pk_neg[jj];
+        fp_set(gen.x, K_G1_X); fp_set(gen.y, K_G1_Y);
+        const fp* s4 = reinterpret_cast<const fp*>(&sig[jj]);
+        const fp* h4 = reinterpret_cast<const fp*>(&hm[jj]);
+        fp2h q1x, q1y, q2x, q2y;
+        q1x.c = s4[role]; q1y.c = s4[2 + role]; q2x.c = h4[role]; q2y.c = h4[2 + role];
+        const bool z1x = fp2_is_zero(q1x), z1y = fp2_is_zero(q1y), z2x = fp2_is_zero(q2x), z2y = fp2_is_zero(q2y);
+        const bool irregular = (z1x & z1y) | (z2x & z2y) | (fp_is_zero(p2.x) & fp_is_zero(p2.y));
+        fp12_t<fp2h> m;
+        miller_loop2<fp2h>(m, gen, q1x, q1y, p2, q2x, q2y, true, true);
+        final_exp(m, m);
+        const bool one = fp12_is_one(m);
+        if (valid && role == 0) results[jj] = irregular ? 0xFF : ((good && one) ? 1 : 0);
+    }
+}
+__global__ void k_pairing_fixup_list(const unsigned* count, const uint32_t* list, const g2a* sig, const g1a* pk_neg, const g2a* hm,
+                                     const uint8_t* ok_a, const uint8_t* ok_b, const uint8_t* ok_c, uint8_t* results) {
+  const size_t n = *count;
+  for (size_t i = HB_TID; i < n; i += HB_STRIDE) {
+    const size_t j = list[i];
+    if (results[j] != 0xFF) continue;
+    bool good = (!ok_a || ok_a[j]) && (!ok_b || ok_b[j]) && (!ok_c || ok_c[j]);
+    g1a gen, p2 = pk_neg[j]; g2a q1 = sig[j], q2 = hm[j];
+    fp_set(gen.x, K_G1_X); fp_set(gen.y, K_G1_Y);
+    fp12 m; miller_loop2(m, gen, q1, p2, q2); final_exp(m, m);
+    results[j] = (good && fp12_is_one(m)) ? 1 : 0;
+  }
+}
+#endif
+
 // device self-test of the lane-pair Fp2 primitives against the single-thread ones on pseudo-random operands
 __global__ void k_selftest_fp2h(uint32_t n, uint32_t seed, uint32_t* mismatches) {
     const int role = threadIdx.x & 1;

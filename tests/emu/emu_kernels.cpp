@@ -66,7 +66,15 @@ template <int G> static int aggregate_verify_batch(int mode, uint32_t n, const u
         run_seq(1, 2, [&] { k_rlc_group_sum<G>(ng, S.data(), Sg.data()); });
         run_pair([&] { k_rlc_pairing_split<G>(ng, pk_scaled.data(), hm.data(), Sg.data(), bad.data(), group_ok.data()); });
         run_seq(1, (unsigned)nr, [&] { k_rlc_finish(nr, ng, group_ok.data(), results, &any_fail); });
+#if HB_FALLBACK_LIST
+        std::vector<uint32_t> list(B); unsigned count = 0;
+        run_seq(2, (unsigned)((nr + 1) / 2), [&] { k_rlc_collect_failed(nr, ng, group_ok.data(), list.data(), &count); });
+        run_seq(1, 3, [&] { k_g1_normalize_list(&count, list.data(), apk.data(), pkneg.data(), 1); });
+        run_pair([&] { k_pairing_verify_split_list(&count, list.data(), sig.data(), pkneg.data(), hm.data(), ok_sig.data(), ok_hm.data(), (const uint8_t*)nullptr, results); });
+        run_seq(1, 2, [&] { k_pairing_fixup_list(&count, list.data(), sig.data(), pkneg.data(), hm.data(), ok_sig.data(), ok_hm.data(), (const uint8_t*)nullptr, results); });
+#else
         exact(0, B, &any_fail);
+#endif
         if (tail) exact(nr, tail, nullptr);
         if (group_ok_out) std::memcpy(group_ok_out, group_ok.data(), ng);
     } else {

@@ -9,9 +9,10 @@ from harmony_b200 import workload as wl
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-# "batch_inv" = the experimental HB_BATCH_INV build of the kernels (one shared inversion per 4 items of a persistent thread):
-# kept correct on the CPU so that a later round only has to time it on the GPU
-@pytest.fixture(scope="module", params=["default", "batch_inv"])
+# "batch_inv" = the experimental HB_BATCH_INV build of the kernels (one shared inversion per 4 items of a persistent thread);
+# "fallback_list" = HB_FALLBACK_LIST (exact re-verification of the rounds of failed groups only, compacted index list).
+# Both are kept correct on the CPU so that a later round only has to time them on the GPU.
+@pytest.fixture(scope="module", params=["default", "batch_inv", "fallback_list"])
 def emuk(request):
     variant = request.param
     src = os.path.join(ROOT, "tests", "emu", "emu_kernels.cpp")
@@ -19,7 +20,7 @@ def emuk(request):
     csrc = os.path.join(ROOT, "harmony_b200", "csrc")
     deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
-        flags = ["-DHB_BATCH_INV=1"] if variant == "batch_inv" else []
+        flags = {"default": [], "batch_inv": ["-DHB_BATCH_INV=1"], "fallback_list": ["-DHB_FALLBACK_LIST=1"]}[variant]
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread"] + flags + ["-o", out, src])
     L = ctypes.CDLL(out)
     L.emu_aggregate_verify_batch.argtypes = [ctypes.c_int, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t,

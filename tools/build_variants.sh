@@ -10,6 +10,7 @@ FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
 build() { name=$1; shift; echo "building $name: $*"; $NVCC $FLAGS "$@" -o harmony_b200/lib/variants/libhbls_$name.so harmony_b200/csrc/hbls.cu & }
 build batchinv4 -DHB_BATCH_INV=1 -DHB_BATCH_K=4      # one shared Fp inversion per 4 items of a persistent thread (hash-to-G2: 2 per item -> 2 per 4)
 build batchinv8 -DHB_BATCH_INV=1 -DHB_BATCH_K=8
+build fallbacklist -DHB_FALLBACK_LIST=1               # exact re-verification of failed groups' rounds only (hostile-batch cost)
 build lockstep_t -DHB_LOCKSTEP_T=1                   # measured in round 1: 3-5 % slower (kept for re-checks)
 wait
 ls -la harmony_b200/lib/variants
