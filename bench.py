@@ -75,6 +75,22 @@ class ClockSampler:
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.maxmhz, "reasons": sorted(self.reasons), "samples": len(s)}
 
 # ------------------------------------------------------------------ CPU arm (oracle = restated reference path)
+def usable_cores():
+    """Host threads this process may actually use: sched affinity, capped by the cgroup CPU quota (cpu.max / cfs_quota)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    quota = None
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max": quota = float(q) / float(per)
+    except Exception:
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0: quota = q / per
+        except Exception: pass
+    info = {"affinity": n, "cgroup_quota": quota, "os_cpu_count": os.cpu_count()}
+    if quota: n = max(1, min(n, int(quota + 0.5)))
+    return n, info
+
 def oracle_lib():
     """The only place bench.py touches oracle/: cpu_baseline leg and --impl reference."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -100,19 +116,41 @@ def cpu_rounds_per_s(orc, pks, bitmaps, sigs, msgs, blen, budget_s, threads):
     dt = time.perf_counter() - t0
     return sum(done) / dt, sum(done), all(good)
 
-# executed work of the batched pairing stage: (Fp mul, Fp sqr) per GROUP of G rounds, counted by running the device code
-# compiled for the host (tests/emu: emu_rlc_stage_counts; pinned by tests/test_emu_logic.py::test_emu_rlc_stage_counts)
-RLC_EXEC_FP_OPS = {4: {"scale": (7856, 2576), "pairing": (34661, 764)},
-                   8: {"scale": (15046, 5094), "pairing": (54329, 764)}}
-NCU_DRAM_BYTES_PER_LAUNCH = {("k_rlc_pairing_split<8>", 303104): 28.78e9 + 109.09e9}
+# EXECUTED work per round = Fp multiplications / squarings the device code performs, counted by running the very same kernels on
+# the host (tests/emu/emu_kernels.cpp: emu_stage_counts for the thread-per-item stages, tests/emu/emu_main.cpp: emu_rlc_stage_counts
+# for the lane-pair pairing stage); pinned by tests/test_emu_kernels.py::test_stage_counts_pinned and tests/test_emu_logic.py.
+# (mul, sqr); "scale"/"pairing" are per GROUP of G rounds, the others per round of the 167/200/250-signer workload.
+EXEC_FP_OPS = {
+    False: {"mask": (357.3, 133.7), "decode": (1478.0, 756.0), "hash": (3172.6, 1524.0),
+            4: {"scale": (7150.0, 2892.8), "pairing": (34661, 764)}, 8: {"scale": (14753.6, 5427.2), "pairing": (54329, 764)}},
+    True:  {"mask": (357.3, 133.7), "decode": (1478.0, 756.0), "hash": (3048.0, 1014.7),                    # shared inversions (HB_BATCH_INV)
+            4: {"scale": (6882.0, 1879.6), "pairing": (34661, 764)}, 8: {"scale": (14217.6, 3400.0), "pairing": (54329, 764)}},
+}
+EXACT_PAIRING_FP_OPS = (20055, 497)      # exact mode: 2-pair Miller loop + final exponentiation per round (oracle counter, stages 4 + 5)
 def rlc_group_size(B, sm_count, tpb_split=512):
     """Mirror of the host's choice in hbls.cu launch_verify_tail: 8 when B/8 lane pairs still fill every SM, else 4."""
     env = os.environ.get("HBLS_RLC_G")
     if env in ("4", "8"): return int(env)
     return 8 if 2 * (B // 8) >= sm_count * tpb_split else 4
-def rlc_exec_mac32(G):
-    ops = RLC_EXEC_FP_OPS[G]
-    return tuple((ops[k][0] * 300 + ops[k][1] * 234) / G for k in ("scale", "pairing"))
+def mac32(ops): return ops[0] * MAC32_PER_MUL + ops[1] * MAC32_PER_SQR
+def executed_mac32_per_round(batch_inv, G):
+    t = EXEC_FP_OPS[bool(batch_inv)]
+    return [mac32(t["mask"]), 0.0, mac32(t["decode"]), mac32(t["hash"]), mac32(t[G]["scale"]) / G, mac32(t[G]["pairing"]) / G]
+def ncu_dram_bytes(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, read from the newest committed ncu summary
+    (profiles/r*_ncu_*.txt written by tools/ncu_summary.py) whose title names that kernel; None if there is none."""
+    import glob, re
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_*.txt"))):
+        try: txt = open(f).read()
+        except OSError: continue
+        if kernel_substr not in txt.splitlines()[0]: continue
+        vals = {}
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            m = re.search(r"^" + re.escape(key) + r"\s+([0-9.]+)\s+(\w+)", txt, re.M)
+            if m: vals[key] = float(m.group(1)) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}.get(m.group(2), 1)
+        if len(vals) == 2: best = (sum(vals.values()), os.path.relpath(f, ROOT))
+    return best
 
 def stage_mac32_per_round(orc, pks, bitmaps, sigs, msgs, blen, sample=12):
     """ALGORITHMIC work per round and per pipeline stage from the oracle's Fp mul/sqr counter."""
@@ -133,7 +171,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads, core_info = usable_cores()
     sks = make_committee_sks()
     orc = oracle_lib()
     pks = [orc.get_public_key(wl.sk_bytes(k)) for k in sks]
@@ -150,12 +188,14 @@ def run_reference(args):
         rates.append(r); ok &= g; rounds += d
     rps = float(np.mean(rates)); sig_per_round = nsig / S
     value = rps * sig_per_round
+    rps1, _, _ = cpu_rounds_per_s(orc, pks, bitmaps, sigs, msgs, blen, min(per, 3.0), 1)
     line = {"impl": "reference", "metric": "BLS aggregate-verify sigs/sec (250-validator FBFT commit batch)", "value": value, "unit": "sigs/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64 (6x64-bit Montgomery limbs)", "data": "synthetic",
             "config": {"workload": "FBFT commit-phase: 250-validator committee, FastAggregateVerify per round (SetMask + Deserialize + VerifyHash)",
                        "committee": N_COMMITTEE, "msg_len": MSG_LEN, "signers_per_round": "167/200/250 cycling"},
-            "cpu_baseline": {"value": value, "unit": "sigs/s", "cores": threads, "kind": "port",
+            "cpu_baseline": {"value": value, "unit": "sigs/s", "cores": threads, "kind": "port", "core_info": core_info,
+                             "single_thread_value": rps1 * sig_per_round, "thread_scaling": rps / rps1 if rps1 else None,
                              "sample": f"{rounds} rounds over {args.steps} x {per:.1f}s windows on {threads} threads; restated CPU path (oracle/hbls_oracle.c), real libbls not buildable here"},
             "e2e": {"value": value, "unit": "sigs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "all_correct": bool(ok)}
@@ -168,8 +208,7 @@ def run_gpu(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the BLS backend has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
-    os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep stdout to the single JSON line (no NCCL version banner)
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"): os.environ["NCCL_DEBUG"] = "WARN"
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # NCCL's own log (whatever NCCL_DEBUG asks for) goes to stderr: stdout stays one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from harmony_b200 import bls
@@ -239,17 +278,47 @@ def run_gpu(args):
     barrier()
     stage_ms /= n_stage
 
+    def timed_device(n_steps, bm=None, sg=None, ms=None, rounds=None):
+        """median CUDA-event time of one device-resident pass over the given (default: the step's) buffers, L2 flushed in between"""
+        bm = d_bm if bm is None else bm; sg = d_sig if sg is None else sg; ms = d_msg if ms is None else ms; rounds = B if rounds is None else rounds
+        evs2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
+        with torch.cuda.stream(stream):
+            for a_, b_ in [(None, None)] + evs2:          # first pass untimed
+                flush.zero_()
+                if a_ is not None: a_.record(stream)
+                rc = L.hbls_aggregate_verify_batch_device(com.h, rounds, bm.data_ptr(), blen, sg.data_ptr(), ms.data_ptr(), MSG_LEN, d_res.data_ptr(), stream.cuda_stream)
+                assert rc == 0, rc
+                if b_ is not None: b_.record(stream)
+        barrier()
+        return float(np.median([a_.elapsed_time(b_) for a_, b_ in evs2]))
+
     # the exact per-round algorithm (batch mode 0: one 2-pair Miller loop + final exponentiation per round) on the same batch
     bls.SetBatchMode(0)
-    ex_evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(3)]
-    with torch.cuda.stream(stream):
-        flush.zero_(); step_device()
-        for a, b in ex_evs:
-            flush.zero_(); a.record(stream); step_device(); b.record(stream)
-    barrier()
-    exact_ms = float(np.median([a.elapsed_time(b) for a, b in ex_evs]))
+    exact_ms = timed_device(3)
     assert int(d_res.sum().item()) == B
     bls.SetBatchMode(1)
+
+    # BASELINE C4 rule applied to the headline workload: 1 % of the rounds invalid (wrong payload / signature of another round /
+    # flipped participation bit / undecodable signature, seeded positions).  Results must be exactly "all but those"; the rounds of
+    # the groups that hold a bad round go through the exact pass (hbls_last_batch_info).
+    rng_bad = np.random.Generator(np.random.Philox(key=[99, rank]))
+    n_bad = max(1, B // 100)
+    bad_idx = np.sort(rng_bad.choice(B, size=n_bad, replace=False))
+    a_bm = np.frombuffer(bitmaps, dtype=np.uint8).reshape(B, blen).copy()
+    a_sg = np.frombuffer(sigs, dtype=np.uint8).reshape(B, 96).copy()
+    a_ms = np.frombuffer(msgs, dtype=np.uint8).reshape(B, MSG_LEN).copy()
+    kind = np.arange(n_bad) % 4
+    a_ms[bad_idx[kind == 0], 17] ^= 0x20
+    src = (bad_idx[kind == 1] + 1) % B; a_sg[bad_idx[kind == 1]] = np.frombuffer(sigs, dtype=np.uint8).reshape(B, 96)[src]
+    a_bm[bad_idx[kind == 2], 5] ^= 0x04
+    a_sg[bad_idx[kind == 3]] = 0xff
+    i_bm, i_sg, i_ms = (torch.from_numpy(x).cuda() for x in (a_bm, a_sg, a_ms))
+    inv_ms = timed_device(3, i_bm, i_sg, i_ms)
+    inv_info = bls.LastBatchInfo()
+    got_bad = np.flatnonzero(d_res.cpu().numpy() != 1)
+    assert np.array_equal(got_bad, bad_idx), "1 %-invalid leg: rejected rounds differ from the injected ones"
+    nsig_valid = float(np.unpackbits(a_bm, axis=1, bitorder="little")[:, :N_COMMITTEE].sum()) - float(np.unpackbits(a_bm[bad_idx], axis=1, bitorder="little")[:, :N_COMMITTEE].sum())
+    del i_bm, i_sg, i_ms
 
     # e2e: host buffers through the public C-ABI call, copies inside the timed region
     step_host(); torch.cuda.synchronize()
@@ -261,12 +330,21 @@ def run_gpu(args):
     e2e_s = time.perf_counter() - t0
     assert int(h_res.sum().item()) == B
     clocks = sampler.finish()
-    lat = []
-    for _ in range(5):
-        t0 = time.perf_counter()
-        rc = L.hbls_aggregate_verify_batch(com.h, 1, h_bm.data_ptr(), blen, h_sig.data_ptr(), h_msg.data_ptr(), MSG_LEN, h_res.data_ptr())
-        lat.append((time.perf_counter() - t0) * 1e3)
-    single_round_ms = float(np.median(lat))
+
+    # batch-size sweep (B in {1, 64, 1 024, 16 384} rounds in flight) through the host-buffer call: latency and sigs/s
+    sweep = {}
+    spr = nsig / B
+    for bsz in (1, 64, 1024, 16384):
+        if bsz > B: continue
+        lat = []
+        for _ in range(5 if bsz <= 1024 else 3):
+            t0 = time.perf_counter()
+            rc = L.hbls_aggregate_verify_batch(com.h, bsz, h_bm.data_ptr(), blen, h_sig.data_ptr(), h_msg.data_ptr(), MSG_LEN, h_res.data_ptr())
+            lat.append((time.perf_counter() - t0) * 1e3)
+        assert rc == 0 and int(h_res[:bsz].sum().item()) == bsz
+        ms_ = float(np.median(lat))
+        sweep[str(bsz)] = {"ms": ms_, "sigs_per_s": bsz * spr / (ms_ * 1e-3), "mode": bls.LastBatchInfo()["mode"]}
+    single_round_ms = sweep["1"]["ms"]
     # informational: the leader's commit-phase vote collection (R9, consensus/leader.go:227-290): 250 individual
     # signatures on ONE payload, one device call (single-bit bitmaps; H(m) computed once)
     vmsg = msgs[:MSG_LEN]
@@ -290,48 +368,57 @@ def run_gpu(args):
     value = nsig_total * args.steps / (dev_ms_max * 1e-3)
     e2e_value = nsig_total * args.steps / (e2e_ms_max * 1e-3)
 
-    # roofline of the dominant kernel: integer pipe (IMAD.WIDE) -- HBM is idle by construction
-    peak = bls.ProbeMac32PerS(8192)
-    orc = oracle_lib()
-    S = min(B, 64)
-    macs = stage_mac32_per_round(orc, pks, bitmaps, sigs, msgs, blen, sample=min(12, S))
-    names = list(bls.STAGE_NAMES)
+    # ---- roofline of the dominant kernel: the integer multiplier.  HBM is idle by construction.
+    # Denominator (calibrated in round 2, profiles/r2_probe_int.*): a 32x32+64 MAC is one IMAD.WIDE, and an IMAD.WIDE holds the
+    # FMA-heavy pipe of a scheduler for 4 cycles per warp (ncu: 4.0 pipe-cycles per instruction, carry-chained or not), so the chip
+    # peak is SMs x 4 schedulers x 8 MAC/clk x SM clock.  The live probe (the multiplier's own carry chains, nothing else) reaches ~90 % of it.
+    probe_macs, sm_clock_hz = bls.ProbeMac32PerS(8192)
     sm_count = torch.cuda.get_device_properties(local).multi_processor_count
+    peak = sm_count * 4 * 8 * sm_clock_hz
+    binfo = bls.BuildInfo()
+    names = list(bls.STAGE_NAMES)
     if B >= sm_count * 256: names[0] = "k_mask_aggregate_serial"
-    exact_macs = list(macs)                         # the oracle's per-round (exact) algorithm, stage by stage
-    rlc = bls.GetBatchMode() == 1 and B >= 1024 and os.environ.get("HBLS_RLC", "1") != "0"
+    rlc = bls.GetBatchMode() == 1 and B >= bls.GetParam("rlc_min")
+    G = rlc_group_size(B, sm_count)
     if rlc:
-        # batched form: slot 4 = coefficient scaling + group sums, slot 5 = (G+1)-pair Miller loop + ONE final exponentiation
-        # per group of G rounds (G = 8 when the batch fills the chip that way, else 4).  Executed Fp-mul/sqr counts of that algorithm come from the device code compiled
-        # for the host (tests/emu: emu_rlc_stage_counts; pinned by tests/test_emu_logic.py), x300 / x234 MAC32 each.
-        G = rlc_group_size(B, sm_count)
-        names[4], names[5] = "k_rlc_scale+k_rlc_group_sum", f"k_rlc_pairing_split<{G}>"
-        macs = macs[:4] + list(rlc_exec_mac32(G))
-    elif stage_ms[4] < 0.02 * stage_ms[5]:         # fused launch: Miller loops + final exponentiation in one kernel
-        macs = macs[:4] + [0.0, macs[4] + macs[5]]
-        names[5] = "k_pairing_verify_split" if os.environ.get("HBLS_SPLIT", "1") != "0" else "k_pairing_verify"
+        # batched form: slot 4 = coefficient scaling + group sums, slot 5 = (G+1)-pair Miller loop + ONE final exponentiation per group
+        names[5] = f"k_rlc_pairing_split<{G}>"
+        macs = executed_mac32_per_round(binfo["batch_inv"], G)
+    else:
+        t = EXEC_FP_OPS[bool(binfo["batch_inv"])]
+        names[4], names[5] = "(unused)", "k_pairing_verify_split"
+        macs = [mac32(t["mask"]), mac32((99, 381)), mac32(t["decode"]), mac32(t["hash"]), 0.0, mac32(EXACT_PAIRING_FP_OPS)]
     dom = int(np.argmax(stage_ms))
     achieved = macs[dom] * B / (stage_ms[dom] * 1e-3)
     total_macs = sum(macs)
     step_s = dev_ms / args.steps * 1e-3
     bytes_per_round = blen + 96 + MSG_LEN + 1
+    traffic = ncu_dram_bytes(names[dom].split("<")[0])
+    orc = oracle_lib()
+    S = min(B, 64)
+    exact_macs = stage_mac32_per_round(orc, pks, bitmaps, sigs, msgs, blen, sample=min(12, S))     # the reference algorithm, oracle counter
     roofline = {"bound": "int32-imad", "kernel": names[dom], "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TMAC32/s",
                 "frac": achieved / peak,
-                # DRAM bytes of ONE launch of the dominant kernel from the committed ncu --set full capture of this workload
-                # (profiles/r1_ncu_rlc_pairing_g8.txt): per-thread Fp12 temporaries spilling past L2, not input traffic
-                "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get((names[dom], B)),
-                "traffic_source": "profiles/r1_ncu_rlc_pairing_g8.txt (dram__bytes_read.sum + dram__bytes_write.sum)" if (names[dom], B) in NCU_DRAM_BYTES_PER_LAUNCH else None,
-                "peak_source": "hbls_probe_mac32_per_s: register-resident IMAD.WIDE.U32 probe measured live on this GPU",
-                "algorithm": (f"random-linear-combination batch check, groups of {G} rounds (exact per-round pass only when a group fails)"
+                "peak_source": f"FMA-heavy pipe: {sm_count} SMs x 4 schedulers x 8 IMAD.WIDE MAC/clk x {sm_clock_hz / 1e9:.3f} GHz (SM clock measured under the probe's load); "
+                               "4 pipe-cycles per IMAD.WIDE warp instruction measured with ncu (profiles/r2_probe_int_ncu.txt)",
+                "probe_achieved": probe_macs / 1e12, "probe_frac_of_peak": probe_macs / peak,
+                "probe": "hbls_probe_mac32_per_s: the field multiplier's own mad.lo.cc/madc.hi.cc rows (IMAD.WIDE.U32.X), 4 independent accumulator sets per thread, 512 threads/SM",
+                # DRAM bytes of ONE launch of the dominant kernel from the newest committed ncu --set full capture of this workload:
+                # per-thread Fp12 temporaries spilling past L2, not input traffic
+                "traffic": traffic[0] if traffic else None, "traffic_source": (traffic[1] + " (dram__bytes_read.sum + dram__bytes_write.sum)") if traffic else None,
+                "algorithm": (f"random-linear-combination batch check, groups of {G} rounds (exact pass over the rounds of failed groups only)"
                               if rlc else "exact per-round FastAggregateVerify"),
-                "work_counted": "Fp multiplications/squarings the kernel's algorithm performs (x300 / x234 MAC32), not instructions issued",
-                "algorithmic_mac32_per_round": total_macs, "kernel_mac32_per_round": macs[dom],
+                "work_counted": "EXECUTED Fp multiplications/squarings of the device code, all six stages (x300 / x234 MAC32 each; adds, shifts, selects not counted), "
+                                "from the same kernels run on the host: tests/emu emu_stage_counts / emu_rlc_stage_counts",
+                "kernel_mac32_per_round": macs[dom], "executed_mac32_per_round": total_macs,
                 "pipeline_frac": total_macs * B / step_s / peak,
-                "exact_algorithm_mac32_per_round": sum(exact_macs),
-                "pipeline_frac_exact_equivalent": sum(exact_macs) * B / step_s / peak,
+                "reference_algorithm_mac32_per_round": sum(exact_macs),
+                "algorithmic_saving_vs_reference": 1.0 - total_macs / sum(exact_macs),
                 "stage_ms_note": "per-kernel CUDA-event times from 3 extra passes after the timed region",
                 "stage_ms": {n: float(m) for n, m in zip(names, stage_ms)},
                 "stage_mac32_per_round": {n: m for n, m in zip(names, macs)},
+                "stage_frac_of_peak": {n: (m * B / (t_ * 1e-3) / peak if t_ > 0.05 else None) for n, m, t_ in zip(names, macs, stage_ms)},
+                "build": binfo,
                 "hbm_algorithmic_gbs": bytes_per_round * B / step_s / 1e9}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -339,15 +426,14 @@ def run_gpu(args):
     except Exception:
         roofline["hbm_peak_gbs_measured"] = None
 
-    threads = os.cpu_count() or 1
+    threads, core_info = usable_cores()
     cpu = None
     if world == 1:
         rps, done, good = cpu_rounds_per_s(orc, pks, bitmaps[:S * blen], sigs[:S * 96], msgs[:S * MSG_LEN], blen, 12.0, threads)
         rps1, done1, good1 = cpu_rounds_per_s(orc, pks, bitmaps[:S * blen], sigs[:S * 96], msgs[:S * MSG_LEN], blen, 4.0, 1)
-        spr = nsig / B
-        cpu = {"value": rps * spr, "unit": "sigs/s", "cores": threads, "kind": "port",
+        cpu = {"value": rps * spr, "unit": "sigs/s", "cores": threads, "kind": "port", "core_info": core_info,
                "sample": f"first {S} rounds of the same workload cycled for 12 s on {threads} threads ({done} rounds); restated CPU path oracle/hbls_oracle.c",
-               "single_thread_value": rps1 * spr, "all_correct": bool(good and good1),
+               "single_thread_value": rps1 * spr, "thread_scaling": rps / rps1 if rps1 else None, "all_correct": bool(good and good1),
                "reference_published_ms": {"VerifyHash": 1.5, "Sign.Deserialize": 0.52, "src": "reference test/chain/vrf/main.go:109-112, test/chain/reward/main.go:239-245 (hardware unspecified)"}}
 
     line = {"metric": "BLS aggregate-verify sigs/sec (250-validator FBFT commit batch)", "value": value, "unit": "sigs/s",
@@ -361,8 +447,13 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": "sigs/s", "h2d_bytes_per_step": B * (blen + 96 + MSG_LEN), "d2h_bytes_per_step": B,
                     "ms_per_step": e2e_ms_max / args.steps, "api": "hbls_aggregate_verify_batch (pinned host buffers)"},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "wall_s_timed_region": t_wall,
+            "value_1pct_invalid": nsig_valid / (inv_ms * 1e-3),
+            "one_pct_invalid": {"ms_per_step": inv_ms, "invalid_rounds": int(n_bad), "kinds": "wrong payload / other round's signature / flipped bitmap bit / undecodable signature",
+                                "value_this_rank": nsig_valid / (inv_ms * 1e-3), "unit": "sigs/s (constituent signatures of the rounds that verify)",
+                                "results_exact": True, "batch_info": inv_info},
             "exact_mode": {"ms_per_step": exact_ms, "value_this_rank": nsig / (exact_ms * 1e-3), "unit": "sigs/s",
                            "note": "hbls_set_batch_mode(0): every round verified on its own (no random linear combination), rank 0, 3 steps"},
+            "batch_sweep_e2e": sweep,
             "single_round_latency_ms": single_round_ms, "leader_250_votes_same_msg_latency_ms": votes250_ms}
     if cpu: line["cpu_baseline"] = cpu
     print(json.dumps(line), flush=True)

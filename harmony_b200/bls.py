@@ -29,6 +29,13 @@ _inited = False
 class HblsError(RuntimeError):
     pass
 
+class BatchInfo(ctypes.Structure):
+    """hbls_batch_info (include/hbls.h)."""
+    _fields_ = [("mode", ctypes.c_int32), ("group_size", ctypes.c_int32), ("rounds", ctypes.c_uint64), ("groups", ctypes.c_uint64),
+                ("groups_failed", ctypes.c_uint32), ("rounds_rechecked", ctypes.c_uint32), ("tail_rounds", ctypes.c_uint32),
+                ("cta_threads", ctypes.c_uint32)]
+    def as_dict(self): return {k: int(getattr(self, k)) for k, _ in self._fields_}
+
 class _Sec(ctypes.Structure):
     _fields_ = [("d", ctypes.c_uint64 * 4)]
 class _Pub(ctypes.Structure):
@@ -82,7 +89,27 @@ def lib():
         sig("hbls_map_to_g2", c.c_int, u8p, sz, vp)
         sig("hbls_fp_mul_batch", c.c_int, sz, vp, vp, vp)
         sig("hbls_kernel_launch_count", c.c_uint64)
-        sig("hbls_probe_mac32_per_s", c.c_double, c.c_int)
+        sig("hbls_build_info", c.c_int)
+        sig("hbls_probe_mac32_per_s", c.c_double, c.c_int, c.POINTER(c.c_double))
+        sig("hbls_get_address", c.c_int, c.POINTER(_Pub), vp)
+        sig("hbls_last_error", c.c_int, vp, sz)
+        sig("hbls_last_batch_info", c.c_int, c.POINTER(BatchInfo))
+        sig("hbls_set_param", c.c_int, u8p, c.c_longlong)
+        sig("hbls_get_param", c.c_longlong, u8p)
+        sig("hbls_aggregate_verify_items", c.c_int, sz, c.POINTER(vp), vp, vp, vp, sz, vp)
+        sig("hbls_verify_headers", c.c_int, vp, sz, vp, vp, sz, vp, sz, sz, vp)
+        sig("hbls_mask_create", c.c_int, c.POINTER(vp), vp)
+        sig("hbls_mask_destroy", None, vp)
+        sig("hbls_mask_set_mask", c.c_int, vp, vp, sz)
+        sig("hbls_mask_set_bit", c.c_int, vp, sz, c.c_int)
+        sig("hbls_mask_clear", c.c_int, vp)
+        sig("hbls_mask_count_enabled", c.c_int, vp)
+        sig("hbls_mask_get", c.c_int, vp, vp, sz, vp)
+        sig("hbls_mask_verify", c.c_int, vp, u8p, u8p, sz)
+        sig("hbls_ballot_box_create", c.c_int, c.POINTER(vp), vp)
+        sig("hbls_ballot_box_destroy", None, vp)
+        sig("hbls_ballot_box_add_vote", c.c_int, vp, u8p, sz, u8p)
+        sig("hbls_ballot_box_aggregate", c.c_int, vp, vp, vp, sz)
         sig("hbls_selftest_split", c.c_int, c.c_uint32)
         sig("hbls_set_batch_mode", None, c.c_int)
         sig("hbls_get_batch_mode", c.c_int)
@@ -144,6 +171,11 @@ class PublicKey:
     def Add(self, rhs): _need().blsPublicKeyAdd(ctypes.byref(self.v), ctypes.byref(rhs.v))
     def Sub(self, rhs): _need().blsPublicKeySub(ctypes.byref(self.v), ctypes.byref(rhs.v))
     def IsEqual(self, o): return _need().blsPublicKeyIsEqual(ctypes.byref(self.v), ctypes.byref(o.v)) == 1
+    def GetAddress(self) -> bytes:
+        """[20]byte (internal/utils/utils.go:77): first 20 bytes of SHA-256(Serialize())."""
+        out = ctypes.create_string_buffer(20)
+        if _need().hbls_get_address(ctypes.byref(self.v), out) != 0: raise HblsError("hbls_get_address failed")
+        return out.raw
 
 class Sign:
     """Zero value = identity (crypto/bls/mask.go:59)."""
@@ -242,6 +274,28 @@ class Committee:
         rc = _lib.hbls_aggregate_verify_batch(self.h, B, _buf(bitmaps), self.blen(), _buf(sigs96), _buf(msgs), msg_len, res)
         if rc != 0: raise HblsError(f"hbls_aggregate_verify_batch rc={rc}")
         return res.raw[:B]
+
+    def VerifyHeaders(self, sigs96: bytes, bitmaps: bytes, payloads: bytes, payload_len: int, quorum: int) -> bytes:
+        """Block-range form of engine.go:619-642 verifySignature: one status byte per header (HDR_* below)."""
+        n = len(sigs96) // 96
+        assert len(bitmaps) == n * self.blen() and len(payloads) == n * payload_len
+        st = ctypes.create_string_buffer(n if n else 1)
+        rc = _lib.hbls_verify_headers(self.h, n, _buf(sigs96), _buf(bitmaps), self.blen(), _buf(payloads), payload_len, quorum, st)
+        if rc != 0: raise HblsError(f"hbls_verify_headers rc={rc}")
+        return st.raw[:n]
+
+HDR_BAD_SIG, HDR_OK, HDR_NO_QUORUM, HDR_BAD_ENCODING = 0, 1, 2, 3
+
+def AggregateVerifyItems(committees, bitmaps, sigs96: bytes, msgs: bytes, msg_len: int) -> bytes:
+    """Multi-committee batch (BASELINE configs[2]; crosslinks engine.go:592-604): item j = (committees[j], bitmaps[j], sig_j, msg_j)."""
+    k = len(committees)
+    arr = (ctypes.c_void_p * k)(*[c.h for c in committees])
+    blob = b"".join(bytes(b) for b in bitmaps)
+    res = ctypes.create_string_buffer(k if k else 1)
+    rc = _need().hbls_aggregate_verify_items(k, arr, _buf(blob), _buf(sigs96), _buf(msgs), msg_len, res)
+    if rc == ERR_ARG: raise ValueError("hbls_aggregate_verify_items: bad argument")
+    if rc != 0: raise HblsError(f"hbls_aggregate_verify_items rc={rc}")
+    return res.raw[:k]
 
 def FastAggregateVerify(committee: Committee, bitmap: bytes, sig96: bytes, msg: bytes) -> bool:
     """BASELINE.json name; == Deserialize + Mask.SetMask + aggSig.VerifyHash(mask.AggregatePublic, msg)
@@ -365,10 +419,85 @@ def ConstructCommitPayload(is_staking: bool, block_hash: bytes, block_num: int, 
 def SelfTestSplit(iters: int = 16) -> int: return int(_need().hbls_selftest_split(iters))
 def SetBatchMode(mode: int): lib().hbls_set_batch_mode(int(mode))
 def GetBatchMode() -> int: return int(lib().hbls_get_batch_mode())
+def BuildInfo() -> dict:
+    v = int(lib().hbls_build_info()); return {"batch_inv": bool(v & 1), "batch_k": v >> 8}
 def KernelLaunchCount() -> int: return int(lib().hbls_kernel_launch_count())
-def ProbeMac32PerS(iters: int = 4096) -> float: return float(_need().hbls_probe_mac32_per_s(iters))
+def ProbeMac32PerS(iters: int = 4096):
+    """(achieved IMAD.WIDE MAC32/s of the carry-chain probe, SM clock in Hz measured under that load)."""
+    clk = ctypes.c_double(0.0)
+    v = float(_need().hbls_probe_mac32_per_s(iters, ctypes.byref(clk)))
+    return v, float(clk.value)
+def LastBatchInfo() -> dict:
+    bi = BatchInfo()
+    rc = lib().hbls_last_batch_info(ctypes.byref(bi))
+    if rc != 0: raise HblsError(f"hbls_last_batch_info rc={rc}")
+    return bi.as_dict()
+def SetParam(name: str, value: int):
+    if lib().hbls_set_param(name.encode(), int(value)) != 0: raise ValueError(f"hbls_set_param({name}, {value})")
+def GetParam(name: str) -> int: return int(lib().hbls_get_param(name.encode()))
+def LastError():
+    buf = ctypes.create_string_buffer(160)
+    return int(lib().hbls_last_error(buf, 160)), buf.value.decode()
 
-STAGE_NAMES = ["k_mask_aggregate", "k_g1_normalize", "k_g2_decode", "k_hash_to_g2", "k_miller_verify", "k_final_verify"]
+class DeviceMask:
+    """Persistent device Mask (hbls_mask_*): crypto/bls/mask.go semantics with the running aggregate key resident in HBM;
+    SetMask / SetBit apply only the delta (TODO(audit) consensus/consensus_service.go:318)."""
+    def __init__(self, committee: Committee):
+        self.c = committee; self.h = ctypes.c_void_p()
+        rc = _need().hbls_mask_create(ctypes.byref(self.h), committee.h)
+        if rc != 0: raise HblsError(f"hbls_mask_create rc={rc}")
+    def __del__(self):
+        try:
+            if self.h and _lib is not None: _lib.hbls_mask_destroy(self.h); self.h = None
+        except Exception: pass
+    def Len(self): return self.c.blen()
+    def SetMask(self, mask: bytes):
+        rc = _lib.hbls_mask_set_mask(self.h, _buf(mask), len(mask))
+        if rc == ERR_ARG: raise ValueError(f"mismatching bitmap lengths expectedBitmapLength {self.Len()} providedBitmapLength {len(mask)}")
+        if rc != 0: raise HblsError(f"hbls_mask_set_mask rc={rc}")
+    def SetBit(self, i: int, enable: bool):
+        rc = _lib.hbls_mask_set_bit(self.h, i, 1 if enable else 0)
+        if rc == ERR_ARG: raise IndexError("index out of range")
+        if rc != 0: raise HblsError(f"hbls_mask_set_bit rc={rc}")
+    def Clear(self):
+        if _lib.hbls_mask_clear(self.h) != 0: raise HblsError("hbls_mask_clear")
+    def CountEnabled(self) -> int: return int(_lib.hbls_mask_count_enabled(self.h))
+    def Mask(self) -> bytes:
+        out = ctypes.create_string_buffer(self.Len() if self.Len() else 1)
+        if _lib.hbls_mask_get(self.h, out, self.Len(), None) != 0: raise HblsError("hbls_mask_get")
+        return out.raw[:self.Len()]
+    def AggregatePublicBytes(self) -> bytes:
+        out = ctypes.create_string_buffer(48)
+        if _lib.hbls_mask_get(self.h, None, 0, out) != 0: raise HblsError("hbls_mask_get")
+        return out.raw
+    def VerifyHash(self, sig96: bytes, msg: bytes) -> bool:
+        rc = _lib.hbls_mask_verify(self.h, _buf(sig96), _buf(msg), len(msg))
+        if rc < 0: raise HblsError(f"hbls_mask_verify rc={rc}")
+        return rc == 1
+
+class BallotBox:
+    """Running vote aggregate (hbls_ballot_box_*): quorum.go:164-196 AggregateVotes with each vote decoded once on arrival."""
+    def __init__(self, committee: Committee):
+        self.c = committee; self.h = ctypes.c_void_p()
+        rc = _need().hbls_ballot_box_create(ctypes.byref(self.h), committee.h)
+        if rc != 0: raise HblsError(f"hbls_ballot_box_create rc={rc}")
+    def __del__(self):
+        try:
+            if self.h and _lib is not None: _lib.hbls_ballot_box_destroy(self.h); self.h = None
+        except Exception: pass
+    def AddVote(self, signer_bitmap: bytes, sig96: bytes) -> bool:
+        """True if counted, False if skipped (a signer was already collected); ValueError on an undecodable signature."""
+        rc = _lib.hbls_ballot_box_add_vote(self.h, _buf(signer_bitmap), len(signer_bitmap), _buf(sig96))
+        if rc == ERR_DECODE: raise ValueError("err blsSignatureDeserialize")
+        if rc < 0: raise HblsError(f"hbls_ballot_box_add_vote rc={rc}")
+        return rc == 0
+    def Aggregate(self):
+        sig = ctypes.create_string_buffer(96); bm = ctypes.create_string_buffer(self.c.blen() if self.c.blen() else 1)
+        rc = _lib.hbls_ballot_box_aggregate(self.h, sig, bm, self.c.blen())
+        if rc != 0: raise HblsError(f"hbls_ballot_box_aggregate rc={rc}")
+        return sig.raw, bm.raw[:self.c.blen()]
+
+STAGE_NAMES = ["k_mask_aggregate", "k_g1_normalize", "k_g2_decode", "k_hash_to_g2", "k_rlc_scale+k_rlc_group_sum", "pairing"]
 def StageTimingEnable(on: bool): lib().hbls_stage_timing_enable(1 if on else 0)
 def StageTimingGet():
     buf = (ctypes.c_float * 8)()

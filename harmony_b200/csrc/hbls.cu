@@ -1,11 +1,13 @@
 // harmony_b200/csrc/hbls.cu -- libhbls.so: C ABI (include/hbls.h) over the sm_100a kernels.
-// Host side = plumbing only (buffers, one stream, launches); every group/field operation runs on the GPU.
+// Host side = plumbing only (buffers, streams, launches); every group/field operation runs on the GPU.
 // No CPU fallback exists: without a usable CUDA device blsInit fails and every entry point returns HBLS_ERR_CUDA.
 #include <cuda_runtime.h>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <memory>
 #include <mutex>
 #include <vector>
 #include "../../include/hbls.h"
@@ -15,23 +17,41 @@ using namespace hb;
 
 namespace {
 
+// per-stream scratch: a bump arena + the timing events and the pinned counters of the last batch issued on that stream.
+// Calls on one stream are stream-ordered, so re-using its arena from offset 0 is safe; different streams never share one.
+struct Scratch {
+    uint8_t* base = nullptr; size_t cap = 0;
+    cudaEvent_t ev[8] = {}; bool ev_ok = false;
+    unsigned* h_counts = nullptr;            // pinned: [0] rounds re-verified exactly, [1] groups failed
+    cudaEvent_t done = nullptr;
+};
 struct Ctx {
     bool ready = false;
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
     std::mutex mu;
-    uint8_t* scratch = nullptr; size_t scratch_cap = 0;     // device bump arena
+    std::map<cudaStream_t, Scratch> scratch;
     std::atomic<uint64_t> launches{0};
-    bool stage_timing = false; bool stage_valid = false;
-    int batch_mode = 1;                                     // 1: random-linear-combination groups + exact fallback, 0: exact per round
-    uint64_t rlc_seed[2] = {0, 0}; uint64_t rlc_calls = 0;
-    cudaEvent_t ev[8] = {};
+    bool stage_timing = false; Scratch* stage_sc = nullptr;
+    int batch_mode = 1;                                     // 1: random-linear-combination groups + exact pass over failed groups, 0: exact per round
+    // tuning (hbls_set_param)
+    long long rlc_min = 1024, rlc_g = 0, tpsm = 384, tpsm_split = 512, tpsm_light = 1024;
+    // coefficient stream: ChaCha20 keyed from /dev/urandom, block counter = call number
+    uint32_t chacha_key[8] = {}; uint64_t rlc_calls = 0;
+    // last batch
+    hbls_batch_info info = {}; Scratch* info_sc = nullptr; bool info_valid = false;
+    // last error of a call that cannot return one
+    int last_err = 0; char last_err_msg[160] = {};
 };
 Ctx g;
 
-#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
-    fprintf(stderr, "[hbls] CUDA error %s at %s:%d: %s\n", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); return HBLS_ERR_CUDA; } } while (0)
+void note_error(cudaError_t e, const char* what, const char* file, int line) {
+    fprintf(stderr, "[hbls] CUDA error %s at %s:%d: %s\n", what, file, line, cudaGetErrorString(e));
+    g.last_err = (int)e;
+    snprintf(g.last_err_msg, sizeof g.last_err_msg, "%s: %s", what, cudaGetErrorString(e));
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { note_error(e_, #call, __FILE__, __LINE__); return HBLS_ERR_CUDA; } } while (0)
 
 int ensure_init() {
     if (g.ready) return 0;
@@ -47,175 +67,154 @@ struct Arena {
         return p;
     }
 };
-int reserve(size_t bytes) {
+// scratch of stream s, grown to `bytes` (growing frees the old block: cudaFree waits for the device, so no kernel still reads it)
+int reserve(cudaStream_t s, size_t bytes, Scratch** out) {
+    Scratch& sc = g.scratch[s];
     bytes += 4096;
-    if (bytes <= g.scratch_cap) return 0;
-    if (g.scratch) CK(cudaFree(g.scratch));
-    g.scratch = nullptr; g.scratch_cap = 0;
-    size_t cap = bytes + bytes / 4;
-    CK(cudaMalloc(&g.scratch, cap));
-    g.scratch_cap = cap;
+    if (bytes > sc.cap) {
+        if (sc.base) CK(cudaFree(sc.base));
+        sc.base = nullptr; sc.cap = 0;
+        size_t cap = bytes + bytes / 4;
+        CK(cudaMalloc(&sc.base, cap));
+        sc.cap = cap;
+    }
+    if (!sc.h_counts) { CK(cudaMallocHost(&sc.h_counts, 64)); sc.h_counts[0] = sc.h_counts[1] = 0; CK(cudaEventCreateWithFlags(&sc.done, cudaEventDisableTiming)); }
+    *out = &sc;
     return 0;
 }
-unsigned split_blocks(size_t nthreads);
-unsigned light_blocks(size_t n);
 inline unsigned blocks_for(size_t n, unsigned tpb) { return (unsigned)((n + tpb - 1) / tpb); }
 #define LAUNCH(kern, grid, block, strm, ...) do { kern<<<(grid), (block), 0, (strm)>>>(__VA_ARGS__); g.launches++; } while (0)
 
 constexpr unsigned TPB = 64;      // heavy kernels: 64-thread CTAs
-// persistent launch geometry for the grid-stride kernels: at most `tpsm` resident threads per SM (HBLS_TPSM, default 384: measured 256: 267 ms, 384: 263 ms, 512: 280 ms per 303 104 rounds)
-// one large CTA per SM for the three big thread-per-round kernels when the library is built with HB_LOCKSTEP_T
-#if HB_LOCKSTEP_T
-static unsigned big_tpb() { static unsigned v = [] { const char* e = getenv("HBLS_TCTA"); return e ? (unsigned)atoi(e) : 384u; }(); return v; }
-static unsigned big_blocks(size_t n) { size_t need = (n + big_tpb() - 1) / big_tpb(); return (unsigned)(need < (size_t)g.sm_count ? need : (size_t)g.sm_count); }
-#else
-static unsigned big_tpb() { return TPB; }
-unsigned heavy_blocks(size_t n);
-static unsigned big_blocks(size_t n) { return heavy_blocks(n); }
-#endif
-unsigned heavy_blocks(size_t n) {
-    static int tpsm = [] { const char* e = getenv("HBLS_TPSM"); int v = e ? atoi(e) : 384; return v < 64 ? 64 : v; }();
-    size_t cap = (size_t)g.sm_count * (size_t)(tpsm / TPB);
-    size_t need = (n + TPB - 1) / TPB;
+// persistent launch geometry for the grid-stride kernels: at most `tpsm` resident threads per SM (default 384: measured 256: 267 ms,
+// 384: 263 ms, 512: 280 ms per 303 104 rounds) so the per-thread stack (Fp12 temporaries) stays in L1/L2
+unsigned capped_blocks(size_t n, long long tpsm, unsigned tpb) {
+    size_t cap = (size_t)g.sm_count * (size_t)((tpsm < (long long)tpb ? tpb : tpsm) / tpb);
+    size_t need = (n + tpb - 1) / tpb;
     return (unsigned)(need < cap ? need : cap);
+}
+unsigned heavy_blocks(size_t n) { return capped_blocks(n, g.tpsm, TPB); }
+unsigned light_blocks(size_t n) { return capped_blocks(n, g.tpsm_light, TPB); }       // small-state kernels: the register count decides
+unsigned split_blocks(size_t nthreads) { return capped_blocks(nthreads, g.tpsm_split, HB_TPB_SPLIT); }
+
+// ------------------------------------------------------------------ coefficient stream (host): ChaCha20 block function, RFC 8439
+void chacha20_block(const uint32_t key[8], uint64_t counter, uint32_t out[16]) {
+    uint32_t st[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key[0], key[1], key[2], key[3], key[4], key[5], key[6], key[7],
+                       (uint32_t)counter, (uint32_t)(counter >> 32), 0x68626c73u /* "hbls" */, 0u};
+    uint32_t x[16]; memcpy(x, st, sizeof x);
+    auto rotl = [](uint32_t v, int c) { return (v << c) | (v >> (32 - c)); };
+    auto qr = [&](int a, int b, int c, int d) {
+        x[a] += x[b]; x[d] ^= x[a]; x[d] = rotl(x[d], 16); x[c] += x[d]; x[b] ^= x[c]; x[b] = rotl(x[b], 12);
+        x[a] += x[b]; x[d] ^= x[a]; x[d] = rotl(x[d], 8);  x[c] += x[d]; x[b] ^= x[c]; x[b] = rotl(x[b], 7);
+    };
+    for (int r = 0; r < 10; r++) { qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15); qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14); }
+    for (int i = 0; i < 16; i++) out[i] = x[i] + st[i];
+}
+// one fresh draw per position inside a group, per call (kernels.cuh: rlc_coeffs); the low bit of each half-scalar pair is forced
+// odd on the device (rlc_scale_pair), leaving 63 random bits per coefficient
+rlc_coeffs rlc_draw() {
+    uint32_t blk[16]; chacha20_block(g.chacha_key, ++g.rlc_calls, blk);
+    rlc_coeffs co;
+    for (int k = 0; k < HB_RLC_GMAX; k++) co.c[k] = ((uint64_t)blk[2 * k + 1] << 32) | blk[2 * k];
+    return co;
 }
 
-// small-state kernels (decode, hash): working set fits L1/L2 at any occupancy -> let the register count decide
-unsigned light_blocks(size_t n) {
-    static int tpsm = [] { const char* e = getenv("HBLS_TPSM_LIGHT"); int v = e ? atoi(e) : 1024; return v < 64 ? 64 : v; }();
-    size_t cap = (size_t)g.sm_count * (size_t)(tpsm / TPB);
-    size_t need = (n + TPB - 1) / TPB;
-    return (unsigned)(need < cap ? need : cap);
-}
-// lane-pair kernels: resident threads per SM from HBLS_TPSM_SPLIT (default 512)
-unsigned split_blocks(size_t nthreads) {
-    static int tpsm = [] { const char* e = getenv("HBLS_TPSM_SPLIT"); int v = e ? atoi(e) : 512; return v < 64 ? 64 : v; }();
-    size_t cap = (size_t)g.sm_count * (size_t)(tpsm / HB_TPB_SPLIT);
-    size_t need = (nthreads + HB_TPB_SPLIT - 1) / HB_TPB_SPLIT;
-    return (unsigned)(need < cap ? need : cap);
-}
 // ------------------------------------------------------------------ one verification pass over device-resident inputs.
-// pk_neg: affine -apk (or -pk) per round; sig/hm decoded inside.  arena must hold verify_scratch_bytes(B).
 size_t verify_scratch_bytes(size_t B) {
-#if HB_FALLBACK_LIST
-    return B * (sizeof(g2a) * 2 + sizeof(g1a) * 2 + sizeof(g1) + sizeof(g2) + sizeof(fp12) * 2 + 16 + 4) + (B / HB_RLC_G + 1) * (sizeof(g2a) + 8) + 33 * 256;
-#endif
-    return B * (sizeof(g2a) * 2 + sizeof(g1a) * 2 + sizeof(g1) + sizeof(g2) + sizeof(fp12) * 2 + 16) + (B / HB_RLC_G + 1) * (sizeof(g2a) + 8) + 32 * 256;
+    return B * (sizeof(g2a) * 2 + sizeof(g1a) * 2 + sizeof(g1) + sizeof(g2) + 16 + 4) + (B / HB_RLC_G + 1) * (sizeof(g2a) + 8) + 40 * 256;
 }
-struct VerifyBufs { g2a* sig; g2a* hm; g1a* pkneg; g1* apk; fp12* f; uint8_t* ok_sig; uint8_t* ok_hm; uint8_t* ok_pk;
-                    g1a* pk_scaled; g2* S; uint8_t* bad; g2a* Sg; uint8_t* group_ok; int* any_fail;
-#if HB_FALLBACK_LIST
-                    uint32_t* fail_list; unsigned* fail_count;
-#endif
-};
+struct VerifyBufs { g2a* sig; g2a* hm; g1a* pkneg; g1* apk; uint8_t* ok_sig; uint8_t* ok_hm; uint8_t* ok_pk;
+                    g1a* pk_scaled; g2* S; uint8_t* bad; g2a* Sg; uint8_t* group_ok; uint32_t* fail_list; unsigned* counts; };
 VerifyBufs carve_verify(Arena& ar, size_t B) {
     VerifyBufs v;
     v.sig = ar.take<g2a>(B); v.hm = ar.take<g2a>(B); v.pkneg = ar.take<g1a>(B); v.apk = ar.take<g1>(B);
-    v.f = ar.take<fp12>(2 * B); v.ok_sig = ar.take<uint8_t>(B); v.ok_hm = ar.take<uint8_t>(B); v.ok_pk = ar.take<uint8_t>(B);
+    v.ok_sig = ar.take<uint8_t>(B); v.ok_hm = ar.take<uint8_t>(B); v.ok_pk = ar.take<uint8_t>(B);
     v.pk_scaled = ar.take<g1a>(B); v.S = ar.take<g2>(B); v.bad = ar.take<uint8_t>(B);
-    v.Sg = ar.take<g2a>(B / HB_RLC_G + 1); v.group_ok = ar.take<uint8_t>(B / HB_RLC_G + 1); v.any_fail = ar.take<int>(1);
-#if HB_FALLBACK_LIST
-    v.fail_list = ar.take<uint32_t>(B); v.fail_count = ar.take<unsigned>(1);
-#endif
+    v.Sg = ar.take<g2a>(B / HB_RLC_G + 1); v.group_ok = ar.take<uint8_t>(B / HB_RLC_G + 1);
+    v.fail_list = ar.take<uint32_t>(B); v.counts = ar.take<unsigned>(2);
     return v;
 }
-// batched (random-linear-combination) form applies: default mode, lane-pair kernels, Jacobian apk at hand, batch large enough
-static bool rlc_applies(size_t B, bool have_apk_jac) {
-    static const int split_mode = [] { const char* e = getenv("HBLS_SPLIT"); return e ? atoi(e) : 1; }();
-    static const int rlc_env = [] { const char* e = getenv("HBLS_RLC"); return e ? atoi(e) : 1; }();
-    static const size_t rlc_min = [] { const char* e = getenv("HBLS_RLC_MIN"); return e ? (size_t)atol(e) : (size_t)1024; }();
-    return split_mode && rlc_env && g.batch_mode == 1 && have_apk_jac && B >= rlc_min;
-}
-#define STAGE_EV(i, strm) do { if (g.stage_timing) cudaEventRecord(g.ev[i], (strm)); } while (0)
-void launch_verify_tail(size_t B, const VerifyBufs& v, const uint8_t* d_sig96, const uint8_t* d_msgs, uint32_t msg_len,
-                        const uint8_t* ok_pk, uint8_t* d_results, cudaStream_t s, bool same_msg = false, const g1* apk_jac = nullptr) {
-    STAGE_EV(2, s);
-    LAUNCH(k_g2_decode, big_blocks(B), big_tpb(), s, B, d_sig96, v.sig, v.ok_sig, 1);
-    STAGE_EV(3, s);
+// batched (random-linear-combination) form applies: default mode and a batch large enough
+static bool rlc_applies(size_t B) { return g.batch_mode == 1 && (long long)B >= g.rlc_min && B >= 2 * HB_RLC_GMAX; }
+#define STAGE_EV(i, sc, strm) do { if (g.stage_timing && (sc)->ev_ok) cudaEventRecord((sc)->ev[i], (strm)); } while (0)
+// v.apk holds the Jacobian (aggregate) public key of every round; ok_pk (nullable) = per-round "key decoded" flags of the triple form
+void launch_verify_tail(size_t B, const VerifyBufs& v, Scratch* sc, const uint8_t* d_sig96, const uint8_t* d_msgs, uint32_t msg_len,
+                        const uint8_t* ok_pk, uint8_t* d_results, cudaStream_t s, bool same_msg) {
+    STAGE_EV(1, sc, s);
+    const bool rlc = rlc_applies(B);
+    // the batched check consumes the Jacobian sums directly; -apk in affine form is then only needed for the rounds of failed groups
+    if (!rlc) LAUNCH(k_g1_normalize, blocks_for(B, TPB), TPB, s, B, v.apk, v.pkneg, 1, (const int*)nullptr);
+    STAGE_EV(2, sc, s);
+    LAUNCH(k_g2_decode, heavy_blocks(B), TPB, s, B, d_sig96, v.sig, v.ok_sig, 1);
+    STAGE_EV(3, sc, s);
     if (same_msg && B > 1) {
         LAUNCH(k_hash_to_g2, 1, TPB, s, (size_t)1, d_msgs, msg_len, v.hm, v.ok_hm);
         LAUNCH(k_broadcast_hm, blocks_for(B, 256), 256, s, B, v.hm, v.ok_hm);
     } else
-    LAUNCH(k_hash_to_g2, big_blocks(B), big_tpb(), s, B, d_msgs, msg_len, v.hm, v.ok_hm);
-    STAGE_EV(4, s);
-    static const int fuse_mode = [] { const char* e = getenv("HBLS_FUSE"); return e ? atoi(e) : -1; }();   // -1 auto, 0 split, 1 fused
-    const bool fused = fuse_mode == 1 || (fuse_mode == -1 && B >= (size_t)g.sm_count * 256);
-    static const int split_mode = [] { const char* e = getenv("HBLS_SPLIT"); return e ? atoi(e) : 1; }();                // lane-pair pairing kernel
-    if (rlc_applies(B, apk_jac != nullptr)) {
-        // batched form (north-star "batched Miller loop + shared final exponentiation"): groups of HB_RLC_G rounds
-        // group size: 8 once that still gives every SM a full CTA of lane pairs (fewer Miller-loop pairs and final
-        // exponentiations per round), else 4
-        static const int g_env = [] { const char* e = getenv("HBLS_RLC_G"); return e ? atoi(e) : 0; }();
-        const size_t G = g_env == 4 || g_env == 8 ? (size_t)g_env : (2 * (B / 8) >= (size_t)g.sm_count * HB_TPB_SPLIT ? 8 : 4);
+        LAUNCH(k_hash_to_g2, heavy_blocks(B), TPB, s, B, d_msgs, msg_len, v.hm, v.ok_hm);
+    STAGE_EV(4, sc, s);
+    hbls_batch_info& bi = g.info;
+    bi = hbls_batch_info{}; bi.rounds = B; bi.mode = rlc ? 1 : 0;
+    cudaMemsetAsync(v.counts, 0, 2 * sizeof(unsigned), s);
+    if (rlc) {
+        // batched form (north-star "batched Miller loop + shared final exponentiation"): strided groups of G rounds; G = 8 once
+        // that still gives every SM a full CTA of lane pairs (fewer Miller-loop pairs and final exponentiations per round), else 4
+        const size_t G = (g.rlc_g == 4 || g.rlc_g == 8) ? (size_t)g.rlc_g : (2 * (B / 8) >= (size_t)g.sm_count * HB_TPB_SPLIT ? 8 : 4);
         const size_t ng = B / G, nr = ng * G, tail = B - nr;
-        const uint64_t s0 = g.rlc_seed[0] + 0x9e3779b97f4a7c15ull * (++g.rlc_calls), s1 = g.rlc_seed[1] ^ (g.rlc_calls << 32);
-        cudaMemsetAsync(v.any_fail, 0, sizeof(int), s);
-        LAUNCH(k_rlc_scale, big_blocks(nr), big_tpb(), s, nr, ng, apk_jac, v.sig, v.hm, v.ok_sig, v.ok_hm, s0, s1, v.pk_scaled, v.S, v.bad);
+        const rlc_coeffs co = rlc_draw();
+        LAUNCH(k_rlc_scale, heavy_blocks(nr), TPB, s, nr, ng, v.apk, v.sig, v.hm, v.ok_sig, v.ok_hm, ok_pk, co, v.pk_scaled, v.S, v.bad);
         const bool full = 2 * ng >= (size_t)g.sm_count * HB_TPB_SPLIT;
         const unsigned pb = full ? split_blocks(2 * ng) : blocks_for(2 * ng, 64), pt = full ? HB_TPB_SPLIT : 64;
         if (G == 8) {
             LAUNCH(k_rlc_group_sum<8>, heavy_blocks(ng), TPB, s, ng, v.S, v.Sg);
-            STAGE_EV(5, s);
+            STAGE_EV(5, sc, s);
             LAUNCH(k_rlc_pairing_split<8>, pb, pt, s, ng, v.pk_scaled, v.hm, v.Sg, v.bad, v.group_ok);
         } else {
             LAUNCH(k_rlc_group_sum<4>, heavy_blocks(ng), TPB, s, ng, v.S, v.Sg);
-            STAGE_EV(5, s);
+            STAGE_EV(5, sc, s);
             LAUNCH(k_rlc_pairing_split<4>, pb, pt, s, ng, v.pk_scaled, v.hm, v.Sg, v.bad, v.group_ok);
         }
-        LAUNCH(k_rlc_finish, blocks_for(nr, 256), 256, s, nr, ng, v.group_ok, d_results, v.any_fail);
-#if HB_FALLBACK_LIST
-        // exact pass over the rounds of failed groups only (compacted on the device; the launches are sized for the worst case
-        // and return at once when the list is short or empty)
-        cudaMemsetAsync(v.fail_count, 0, sizeof(unsigned), s);
-        LAUNCH(k_rlc_collect_failed, blocks_for(nr, 256), 256, s, nr, ng, v.group_ok, v.fail_list, v.fail_count);
-        LAUNCH(k_g1_normalize_list, heavy_blocks(B), TPB, s, v.fail_count, v.fail_list, apk_jac, v.pkneg, 1);
-        if (2 * B >= (size_t)g.sm_count * HB_TPB_SPLIT)
-            LAUNCH(k_pairing_verify_split_list, split_blocks(2 * B), HB_TPB_SPLIT, s, v.fail_count, v.fail_list, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
+        // exact pass over the rounds of failed groups only (compacted on the device; the launches are sized for the worst case and
+        // return at once when the list is short or empty)
+        LAUNCH(k_rlc_finish, blocks_for(nr, 256), 256, s, nr, ng, v.group_ok, d_results, v.fail_list, v.counts);
+        LAUNCH(k_g1_normalize_list, heavy_blocks(nr), TPB, s, v.counts, v.fail_list, v.apk, v.pkneg, 1);
+        if (2 * nr >= (size_t)g.sm_count * HB_TPB_SPLIT)
+            LAUNCH(k_pairing_verify_split_list, split_blocks(2 * nr), HB_TPB_SPLIT, s, v.counts, v.fail_list, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
         else
-            LAUNCH(k_pairing_verify_split_list, blocks_for(2 * B, 64), 64, s, v.fail_count, v.fail_list, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
-        LAUNCH(k_pairing_fixup_list, heavy_blocks(B), TPB, s, v.fail_count, v.fail_list, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
-#else
-        // exact per-round pass: returns immediately unless a group failed (then every round is recomputed exactly)
-        LAUNCH(k_g1_normalize, blocks_for(B, TPB), TPB, s, B, apk_jac, v.pkneg, 1, (const int*)v.any_fail);
-        if (2 * B >= (size_t)g.sm_count * HB_TPB_SPLIT)
-            LAUNCH(k_pairing_verify_split, split_blocks(2 * B), HB_TPB_SPLIT, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results, v.any_fail);
-        else
-            LAUNCH(k_pairing_verify_split, blocks_for(2 * B, 64), 64, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results, v.any_fail);
-        LAUNCH(k_pairing_fixup, heavy_blocks(B), TPB, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results, v.any_fail);
-#endif
+            LAUNCH(k_pairing_verify_split_list, blocks_for(2 * nr, 64), 64, s, v.counts, v.fail_list, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
+        LAUNCH(k_pairing_fixup_list, heavy_blocks(nr), TPB, s, v.counts, v.fail_list, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
         if (tail) {       // the < G rounds that do not fill a group are always verified exactly
-            LAUNCH(k_g1_normalize, 1, TPB, s, tail, apk_jac + nr, v.pkneg + nr, 1, (const int*)nullptr);
+            LAUNCH(k_g1_normalize, 1, TPB, s, tail, v.apk + nr, v.pkneg + nr, 1, (const int*)nullptr);
             LAUNCH(k_pairing_verify_split, blocks_for(2 * tail, 64), 64, s, tail, v.sig + nr, v.pkneg + nr, v.hm + nr, v.ok_sig + nr, v.ok_hm + nr,
-                   (const uint8_t*)nullptr, d_results + nr, (const int*)nullptr);
-            LAUNCH(k_pairing_fixup, 1, TPB, s, tail, v.sig + nr, v.pkneg + nr, v.hm + nr, v.ok_sig + nr, v.ok_hm + nr, (const uint8_t*)nullptr, d_results + nr, (const int*)nullptr);
+                   ok_pk ? ok_pk + nr : (const uint8_t*)nullptr, d_results + nr, (const int*)nullptr);
+            LAUNCH(k_pairing_fixup, 1, TPB, s, tail, v.sig + nr, v.pkneg + nr, v.hm + nr, v.ok_sig + nr, v.ok_hm + nr,
+                   ok_pk ? ok_pk + nr : (const uint8_t*)nullptr, d_results + nr, (const int*)nullptr);
         }
-    } else if (split_mode) {
-        // default at every batch size: a lane pair per round (half the per-thread state, half the single-round latency).
-        // Large batches use 512-thread lock-stepped CTAs (one per SM); small ones 64-thread CTAs spread over the SMs.
-        STAGE_EV(5, s);
-        if (2 * B >= (size_t)g.sm_count * HB_TPB_SPLIT)
+        bi.group_size = (int32_t)G; bi.groups = ng; bi.tail_rounds = (uint32_t)tail; bi.cta_threads = pt;
+    } else {
+        // exact form at every batch size: a lane pair per round.  Large batches use 512-thread lock-stepped CTAs (one per SM),
+        // small ones 64-thread CTAs spread over the SMs.
+        STAGE_EV(5, sc, s);
+        const bool full = 2 * B >= (size_t)g.sm_count * HB_TPB_SPLIT;
+        if (full)
             LAUNCH(k_pairing_verify_split, split_blocks(2 * B), HB_TPB_SPLIT, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results, (const int*)nullptr);
         else
             LAUNCH(k_pairing_verify_split, blocks_for(2 * B, 64), 64, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results, (const int*)nullptr);
         LAUNCH(k_pairing_fixup, heavy_blocks(B), TPB, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results, (const int*)nullptr);
-    } else if (fused) {
-        // batch alone fills the chip: one thread per round, 2-pair loop with shared squarings + final exponentiation
-        STAGE_EV(5, s);
-        LAUNCH(k_pairing_verify, heavy_blocks(B), TPB, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
-    } else {
-        // small batch: two threads per round for the Miller loops (more parallelism), then one for the exponentiation
-        LAUNCH(k_miller_verify, heavy_blocks(2 * B), TPB, s, B, v.sig, v.pkneg, v.hm, v.f);
-        STAGE_EV(5, s);
-        LAUNCH(k_final_verify, heavy_blocks(B), TPB, s, B, v.f, v.ok_sig, v.ok_hm, ok_pk, d_results);
+        bi.cta_threads = full ? HB_TPB_SPLIT : 64;
     }
-    STAGE_EV(6, s);
+    STAGE_EV(6, sc, s);
+    cudaMemcpyAsync(sc->h_counts, v.counts, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, s);
+    cudaEventRecord(sc->done, s);
+    g.info_sc = sc; g.info_valid = true;
+    if (g.stage_timing && sc->ev_ok) g.stage_sc = sc;
 }
 
 int single_op(int op, const void* a, size_t an, const void* b, size_t bn, void* out, size_t on, int* rc_out, uint32_t len = 0) {
     if (int e = ensure_init()) return e;
     std::lock_guard<std::mutex> lk(g.mu);
-    if (int e = reserve(an + bn + on + 4096)) return e;
-    Arena ar{g.scratch, 0, g.scratch_cap};
+    Scratch* sc; if (int e = reserve(g.stream, an + bn + on + 4096, &sc)) return e;
+    Arena ar{sc->base, 0, sc->cap};
     uint8_t* da = ar.take<uint8_t>(an ? an : 1); uint8_t* db = ar.take<uint8_t>(bn ? bn : 1);
     uint8_t* dout = ar.take<uint8_t>(on ? on : 1); int* drc = ar.take<int>(1);
     if (an) CK(cudaMemcpyAsync(da, a, an, cudaMemcpyHostToDevice, g.stream));
@@ -236,6 +235,40 @@ bool scalar_lt_r(const uint64_t k[4]) {
     for (int i = 3; i >= 0; i--) { if (k[i] < R_ORDER[i]) return true; if (k[i] > R_ORDER[i]) return false; }
     return false;
 }
+
+// SHA-256 (host; GetAddress = first 20 bytes of SHA-256 of the serialized key)
+struct Sha256 {
+    static uint32_t rotr(uint32_t x, int n) { return (x >> n) | (x << (32 - n)); }
+    static void digest(const uint8_t* msg, size_t len, uint8_t out[32]) {
+        static const uint32_t K[64] = {
+            0x428a2f98,0x71374491,0xb5c0fbcf,0xe9b5dba5,0x3956c25b,0x59f111f1,0x923f82a4,0xab1c5ed5,0xd807aa98,0x12835b01,0x243185be,0x550c7dc3,0x72be5d74,0x80deb1fe,0x9bdc06a7,0xc19bf174,
+            0xe49b69c1,0xefbe4786,0x0fc19dc6,0x240ca1cc,0x2de92c6f,0x4a7484aa,0x5cb0a9dc,0x76f988da,0x983e5152,0xa831c66d,0xb00327c8,0xbf597fc7,0xc6e00bf3,0xd5a79147,0x06ca6351,0x14292967,
+            0x27b70a85,0x2e1b2138,0x4d2c6dfc,0x53380d13,0x650a7354,0x766a0abb,0x81c2c92e,0x92722c85,0xa2bfe8a1,0xa81a664b,0xc24b8b70,0xc76c51a3,0xd192e819,0xd6990624,0xf40e3585,0x106aa070,
+            0x19a4c116,0x1e376c08,0x2748774c,0x34b0bcb5,0x391c0cb3,0x4ed8aa4a,0x5b9cca4f,0x682e6ff3,0x748f82ee,0x78a5636f,0x84c87814,0x8cc70208,0x90befffa,0xa4506ceb,0xbef9a3f7,0xc67178f2};
+        uint32_t h[8] = {0x6a09e667,0xbb67ae85,0x3c6ef372,0xa54ff53a,0x510e527f,0x9b05688c,0x1f83d9ab,0x5be0cd19};
+        std::vector<uint8_t> m(msg, msg + len);
+        m.push_back(0x80);
+        while (m.size() % 64 != 56) m.push_back(0);
+        uint64_t bits = (uint64_t)len * 8;
+        for (int i = 7; i >= 0; i--) m.push_back((uint8_t)(bits >> (8 * i)));
+        for (size_t off = 0; off < m.size(); off += 64) {
+            uint32_t w[64];
+            for (int i = 0; i < 16; i++) w[i] = ((uint32_t)m[off + 4 * i] << 24) | ((uint32_t)m[off + 4 * i + 1] << 16) | ((uint32_t)m[off + 4 * i + 2] << 8) | m[off + 4 * i + 3];
+            for (int i = 16; i < 64; i++) {
+                uint32_t s0 = rotr(w[i - 15], 7) ^ rotr(w[i - 15], 18) ^ (w[i - 15] >> 3), s1 = rotr(w[i - 2], 17) ^ rotr(w[i - 2], 19) ^ (w[i - 2] >> 10);
+                w[i] = w[i - 16] + s0 + w[i - 7] + s1;
+            }
+            uint32_t a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], gg = h[6], hh = h[7];
+            for (int i = 0; i < 64; i++) {
+                uint32_t S1 = rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25), ch = (e & f) ^ (~e & gg), t1 = hh + S1 + ch + K[i] + w[i];
+                uint32_t S0 = rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22), mj = (a & b) ^ (a & c) ^ (b & c), t2 = S0 + mj;
+                hh = gg; gg = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+            }
+            h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += gg; h[7] += hh;
+        }
+        for (int i = 0; i < 8; i++) for (int j = 0; j < 4; j++) out[4 * i + j] = (uint8_t)(h[i] >> (24 - 8 * j));
+    }
+};
 
 // SHA-512 (host; only for the test-only blsSign/blsVerify string API: mcl Fp::setHashOf)
 struct Sha512 {
@@ -287,7 +320,50 @@ struct hbls_committee {
     size_t n = 0;
     g1a* table = nullptr;       // device, affine, Montgomery
     g1* total = nullptr;        // device, sum of all rows (lets dense bitmaps be aggregated from their complement)
+    ~hbls_committee() { if (table) cudaFree(table); if (total) cudaFree(total); }
 };
+struct hbls_mask {
+    const hbls_committee* c = nullptr;
+    std::vector<uint8_t> bitmap;        // Mask.Bitmap (host)
+    g1* d_acc = nullptr;                // Mask.AggregatePublic (device, Jacobian)
+    ~hbls_mask() { if (d_acc) cudaFree(d_acc); }
+};
+struct hbls_ballot_box {
+    const hbls_committee* c = nullptr;
+    std::vector<uint8_t> collected;     // signers already counted
+    g2* d_sum = nullptr;                // running aggregate signature (device, Jacobian)
+    ~hbls_ballot_box() { if (d_sum) cudaFree(d_sum); }
+};
+
+namespace {
+int popcount_slots(const uint8_t* bm, size_t n) {          // set bits among slots i < n only (padding bits of the last byte never count)
+    int c = 0;
+    for (size_t i = 0; i < (n >> 3); i++) c += __builtin_popcount(bm[i]);
+    if (n & 7) c += __builtin_popcount(bm[n >> 3] & ((1u << (n & 7)) - 1u));
+    return c;
+}
+bool all_messages_equal(const uint8_t* msgs, size_t n, size_t msg_len) {
+    for (size_t i = 1; i < n; i++) if (memcmp(msgs, msgs + i * msg_len, msg_len) != 0) return false;
+    return n > 1;
+}
+// rounds against one committee, everything device-resident
+int agg_verify_device_locked(const hbls_committee* c, size_t B, const uint8_t* d_bitmaps, size_t blen, const uint8_t* d_sigs,
+                             const uint8_t* d_msgs, size_t msg_len, uint8_t* d_results, cudaStream_t s, Scratch* sc, Arena& ar, bool same_msg,
+                             VerifyBufs* v_out = nullptr) {
+    VerifyBufs v = carve_verify(ar, B);
+    STAGE_EV(0, sc, s);
+    if (B >= (size_t)g.sm_count * 256)
+        LAUNCH(k_mask_aggregate_serial, light_blocks(B), TPB, s, B, c->n, c->table, c->total, d_bitmaps, blen, v.apk);
+    else
+        LAUNCH(k_mask_aggregate, blocks_for(B * 32, 128), 128, s, B, c->n, c->table, d_bitmaps, blen, v.apk);
+    launch_verify_tail(B, v, sc, d_sigs, d_msgs, (uint32_t)msg_len, nullptr, d_results, s, same_msg);
+    if (v_out) *v_out = v;
+    return 0;
+}
+void ensure_stage_events(Scratch* sc) {
+    if (g.stage_timing && !sc->ev_ok) { for (int i = 0; i < 8; i++) cudaEventCreate(&sc->ev[i]); sc->ev_ok = true; }
+}
+}  // namespace
 
 extern "C" {
 
@@ -305,14 +381,15 @@ int hbls_init_device(int device) {
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
     g.device = device; g.sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-    { FILE* f = fopen("/dev/urandom", "rb"); if (!f || fread(g.rlc_seed, 1, 16, f) != 16) { if (f) fclose(f); fprintf(stderr, "[hbls] cannot read /dev/urandom\n"); return HBLS_ERR_CUDA; } fclose(f); }
+    { FILE* f = fopen("/dev/urandom", "rb"); if (!f || fread(g.chacha_key, 1, 32, f) != 32) { if (f) fclose(f); fprintf(stderr, "[hbls] cannot read /dev/urandom\n"); return HBLS_ERR_CUDA; } fclose(f); }
+    auto envll = [](const char* name, long long dflt) { const char* e = getenv(name); return e ? atoll(e) : dflt; };
+    g.rlc_min = envll("HBLS_RLC_MIN", 1024); g.rlc_g = envll("HBLS_RLC_G", 0);
+    g.tpsm = envll("HBLS_TPSM", 384); g.tpsm_split = envll("HBLS_TPSM_SPLIT", 512); g.tpsm_light = envll("HBLS_TPSM_LIGHT", 1024);
+    // the heavy kernels keep their Fp12 temporaries in per-thread local memory: give L1 the whole 228 KB
     cudaFuncSetAttribute(k_rlc_pairing_split<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_rlc_pairing_split<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
-    // the heavy kernels keep their Fp12 temporaries in per-thread local memory: give L1 the whole 228 KB
-    cudaFuncSetAttribute(k_miller_verify, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
-    cudaFuncSetAttribute(k_final_verify, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
-    cudaFuncSetAttribute(k_pairing_verify, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_pairing_verify_split, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    cudaFuncSetAttribute(k_pairing_verify_split_list, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_hash_to_g2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_g2_decode, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_rlc_scale, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
@@ -328,8 +405,41 @@ int blsInit(int curve, int compiledTimeVar) {
     return hbls_init_device(d ? atoi(d) : 0);
 }
 uint64_t hbls_kernel_launch_count(void) { return g.launches.load(); }
+int hbls_build_info(void) { return (HB_BATCH_INV ? 1 : 0) | (HB_BATCH_K << 8); }
 void hbls_set_batch_mode(int mode) { std::lock_guard<std::mutex> lk(g.mu); g.batch_mode = mode ? 1 : 0; }
 int hbls_get_batch_mode(void) { std::lock_guard<std::mutex> lk(g.mu); return g.batch_mode; }
+static long long* param_slot(const char* name) {
+    if (!name) return nullptr;
+    if (!strcmp(name, "rlc_min")) return &g.rlc_min;
+    if (!strcmp(name, "rlc_g")) return &g.rlc_g;
+    if (!strcmp(name, "tpsm")) return &g.tpsm;
+    if (!strcmp(name, "tpsm_split")) return &g.tpsm_split;
+    if (!strcmp(name, "tpsm_light")) return &g.tpsm_light;
+    return nullptr;
+}
+int hbls_set_param(const char* name, long long value) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    long long* p = param_slot(name);
+    if (!p || value < 0) return HBLS_ERR_ARG;
+    if (p == &g.rlc_g && value != 0 && value != 4 && value != 8) return HBLS_ERR_ARG;
+    *p = value; return 0;
+}
+long long hbls_get_param(const char* name) { std::lock_guard<std::mutex> lk(g.mu); long long* p = param_slot(name); return p ? *p : -1; }
+int hbls_last_error(char* msg, size_t msg_cap) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    int e = g.last_err;
+    if (msg && msg_cap) { strncpy(msg, g.last_err_msg, msg_cap - 1); msg[msg_cap - 1] = 0; }
+    g.last_err = 0; g.last_err_msg[0] = 0;
+    return e;
+}
+int hbls_last_batch_info(hbls_batch_info* out) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (!out || !g.info_valid || !g.info_sc) return HBLS_ERR_ARG;
+    CK(cudaEventSynchronize(g.info_sc->done));
+    *out = g.info;
+    out->rounds_rechecked = g.info_sc->h_counts[0]; out->groups_failed = g.info_sc->h_counts[1];
+    return 0;
+}
 
 // ------------------------------------------------------------------ secret keys (host bytes; no group arithmetic)
 int blsSecretKeySetByCSPRNG(blsSecretKey* sec) {
@@ -349,10 +459,11 @@ size_t blsSecretKeyDeserialize(blsSecretKey* sec, const void* buf, size_t bufSiz
 }
 int blsSecretKeyIsEqual(const blsSecretKey* l, const blsSecretKey* r) { return memcmp(l, r, 32) == 0; }
 
-// ------------------------------------------------------------------ single-element group ops
-void blsPublicKeyAdd(blsPublicKey* pub, const blsPublicKey* rhs) { int rc; single_op(OP_G1_ADD, pub, 144, rhs, 144, pub, 144, &rc); }
-void blsPublicKeySub(blsPublicKey* pub, const blsPublicKey* rhs) { int rc; single_op(OP_G1_SUB, pub, 144, rhs, 144, pub, 144, &rc); }
-void blsSignatureAdd(blsSignature* sig, const blsSignature* rhs) { int rc; single_op(OP_G2_ADD, sig, 288, rhs, 288, sig, 288, &rc); }
+// ------------------------------------------------------------------ single-element group ops.  The herumi signatures of Add / Sub /
+// GetPublicKey are void: on a CUDA failure the destination becomes the identity and the error is kept for hbls_last_error().
+void blsPublicKeyAdd(blsPublicKey* pub, const blsPublicKey* rhs) { int rc; if (single_op(OP_G1_ADD, pub, 144, rhs, 144, pub, 144, &rc)) memset(pub, 0, sizeof *pub); }
+void blsPublicKeySub(blsPublicKey* pub, const blsPublicKey* rhs) { int rc; if (single_op(OP_G1_SUB, pub, 144, rhs, 144, pub, 144, &rc)) memset(pub, 0, sizeof *pub); }
+void blsSignatureAdd(blsSignature* sig, const blsSignature* rhs) { int rc; if (single_op(OP_G2_ADD, sig, 288, rhs, 288, sig, 288, &rc)) memset(sig, 0, sizeof *sig); }
 int blsPublicKeyIsEqual(const blsPublicKey* l, const blsPublicKey* r) { int rc = 0; if (single_op(OP_G1_EQ, l, 144, r, 144, nullptr, 0, &rc)) return 0; return rc; }
 int blsSignatureIsEqual(const blsSignature* l, const blsSignature* r) { int rc = 0; if (single_op(OP_G2_EQ, l, 288, r, 288, nullptr, 0, &rc)) return 0; return rc; }
 size_t blsPublicKeySerialize(void* buf, size_t maxBufSize, const blsPublicKey* pub) {
@@ -364,26 +475,35 @@ size_t blsPublicKeyDeserialize(blsPublicKey* pub, const void* buf, size_t bufSiz
 size_t blsSignatureDeserialize(blsSignature* sig, const void* buf, size_t bufSize) {
     if (bufSize < 96) return 0; int rc = 0; if (single_op(OP_G2_DES, buf, 96, nullptr, 0, sig, 288, &rc)) return 0; return rc == 96 ? 96 : 0; }
 int hbls_map_to_g2(const void* msg, size_t msg_len, uint8_t out96[96]) {
-    if (msg_len > 64) msg_len = 64;      // only the first 48 bytes matter
+    if (msg_len > 48) msg_len = 48;      // only the first 48 bytes matter
     int rc = -1; if (int e = single_op(OP_MAP_SER, msg, msg_len, nullptr, 0, out96, 96, &rc, (uint32_t)msg_len)) return e; return rc; }
+int hbls_get_address(const blsPublicKey* pub, uint8_t out20[20]) {
+    uint8_t ser[48], dg[32];
+    if (blsPublicKeySerialize(ser, 48, pub) != 48) return HBLS_ERR_CUDA;
+    Sha256::digest(ser, 48, dg); memcpy(out20, dg, 20); return 0;
+}
 
 void blsGetPublicKey(blsPublicKey* pub, const blsSecretKey* sec) {
-    if (ensure_init()) { memset(pub, 0, sizeof *pub); return; }
+    memset(pub, 0, sizeof *pub);
+    if (ensure_init()) return;
     std::lock_guard<std::mutex> lk(g.mu);
-    if (reserve(4096)) return;
-    Arena ar{g.scratch, 0, g.scratch_cap};
+    Scratch* sc; if (reserve(g.stream, 4096, &sc)) return;
+    Arena ar{sc->base, 0, sc->cap};
     uint8_t* dsk = ar.take<uint8_t>(32); g1* dout = ar.take<g1>(1);
-    cudaMemcpyAsync(dsk, sec->d, 32, cudaMemcpyHostToDevice, g.stream);
+    blsPublicKey tmp;
+    cudaError_t e = cudaMemcpyAsync(dsk, sec->d, 32, cudaMemcpyHostToDevice, g.stream);
     LAUNCH(k_g1_mul_gen, 1, 32, g.stream, (size_t)1, dsk, dout);
-    cudaMemcpyAsync(pub, dout, 144, cudaMemcpyDeviceToHost, g.stream);
-    cudaStreamSynchronize(g.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&tmp, dout, 144, cudaMemcpyDeviceToHost, g.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+    if (e != cudaSuccess) { note_error(e, "blsGetPublicKey", __FILE__, __LINE__); return; }
+    *pub = tmp;
 }
 int blsSignHash(blsSignature* sig, const blsSecretKey* sec, const void* h, size_t size) {
     if (int e = ensure_init()) return e;
     std::lock_guard<std::mutex> lk(g.mu);
-    if (size > 64) size = 64;
-    if (int e = reserve(4096)) return e;
-    Arena ar{g.scratch, 0, g.scratch_cap};
+    if (size > 48) size = 48;
+    Scratch* sc; if (int e = reserve(g.stream, 4096, &sc)) return e;
+    Arena ar{sc->base, 0, sc->cap};
     uint8_t* dsk = ar.take<uint8_t>(32); uint8_t* dmsg = ar.take<uint8_t>(64); g2* dout = ar.take<g2>(1); uint8_t* dok = ar.take<uint8_t>(1);
     CK(cudaMemcpyAsync(dsk, sec->d, 32, cudaMemcpyHostToDevice, g.stream));
     if (size) CK(cudaMemcpyAsync(dmsg, h, size, cudaMemcpyHostToDevice, g.stream));
@@ -394,27 +514,38 @@ int blsSignHash(blsSignature* sig, const blsSecretKey* sec, const void* h, size_
     CK(cudaStreamSynchronize(g.stream));
     return ok ? 0 : -1;
 }
+// VerifyHash on already-decoded structs: d_apk (device Jacobian key) or host pub; returns 1 / 0, <0 on error.  Caller holds g.mu.
+static int verify_hash_locked(const blsSignature* sig, const blsPublicKey* pub, const g1* d_apk, const uint8_t* sig96, const void* h, size_t size) {
+    if (size > 48) size = 48;
+    Scratch* sc; if (int e = reserve(g.stream, verify_scratch_bytes(1) + 4096, &sc)) return e;
+    Arena ar{sc->base, 0, sc->cap};
+    VerifyBufs v = carve_verify(ar, 1);
+    g2* dsig = ar.take<g2>(1); uint8_t* dsig96 = ar.take<uint8_t>(96); uint8_t* dmsg = ar.take<uint8_t>(64); uint8_t* dres = ar.take<uint8_t>(1);
+    if (d_apk) CK(cudaMemcpyAsync(v.apk, d_apk, 144, cudaMemcpyDeviceToDevice, g.stream));
+    else CK(cudaMemcpyAsync(v.apk, pub, 144, cudaMemcpyHostToDevice, g.stream));
+    if (size) CK(cudaMemcpyAsync(dmsg, h, size, cudaMemcpyHostToDevice, g.stream));
+    LAUNCH(k_g1_normalize, 1, 32, g.stream, (size_t)1, v.apk, v.pkneg, 1, (const int*)nullptr);
+    const uint8_t* ok_sig = nullptr;
+    if (sig96) {          // serialized signature: decode (+ subgroup check) on the device
+        CK(cudaMemcpyAsync(dsig96, sig96, 96, cudaMemcpyHostToDevice, g.stream));
+        LAUNCH(k_g2_decode, 1, 32, g.stream, (size_t)1, dsig96, v.sig, v.ok_sig, 1);
+        ok_sig = v.ok_sig;
+    } else {              // struct inputs are already-decoded Jacobian points: normalise instead of decoding
+        CK(cudaMemcpyAsync(dsig, sig, 288, cudaMemcpyHostToDevice, g.stream));
+        LAUNCH(k_g2_normalize, 1, 32, g.stream, (size_t)1, dsig, v.sig);
+    }
+    LAUNCH(k_hash_to_g2, 1, 32, g.stream, (size_t)1, dmsg, (uint32_t)size, v.hm, v.ok_hm);
+    LAUNCH(k_pairing_verify_split, 1, 64, g.stream, (size_t)1, v.sig, v.pkneg, v.hm, (const uint8_t*)v.ok_hm, ok_sig, (const uint8_t*)nullptr, dres, (const int*)nullptr);
+    LAUNCH(k_pairing_fixup, 1, 32, g.stream, (size_t)1, v.sig, v.pkneg, v.hm, (const uint8_t*)v.ok_hm, ok_sig, (const uint8_t*)nullptr, dres, (const int*)nullptr);
+    uint8_t res = 0;
+    CK(cudaMemcpyAsync(&res, dres, 1, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return res ? 1 : 0;
+}
 int blsVerifyHash(const blsSignature* sig, const blsPublicKey* pub, const void* h, size_t size) {
     if (ensure_init()) return 0;
     std::lock_guard<std::mutex> lk(g.mu);
-    if (size > 64) size = 64;
-    if (reserve(verify_scratch_bytes(1) + 4096)) return 0;
-    Arena ar{g.scratch, 0, g.scratch_cap};
-    VerifyBufs v = carve_verify(ar, 1);
-    g2* dsig = ar.take<g2>(1); uint8_t* dmsg = ar.take<uint8_t>(64); uint8_t* dres = ar.take<uint8_t>(1);
-    cudaMemcpyAsync(v.apk, pub, 144, cudaMemcpyHostToDevice, g.stream);
-    cudaMemcpyAsync(dsig, sig, 288, cudaMemcpyHostToDevice, g.stream);
-    if (size) cudaMemcpyAsync(dmsg, h, size, cudaMemcpyHostToDevice, g.stream);
-    // struct inputs are already-decoded Jacobian points: normalise instead of decoding
-    LAUNCH(k_g1_normalize, 1, 32, g.stream, (size_t)1, v.apk, v.pkneg, 1, (const int*)nullptr);
-    LAUNCH(k_g2_normalize, 1, 32, g.stream, (size_t)1, dsig, v.sig);
-    LAUNCH(k_hash_to_g2, 1, 32, g.stream, (size_t)1, dmsg, (uint32_t)size, v.hm, v.ok_hm);
-    LAUNCH(k_pairing_verify_split, 1, 64, g.stream, (size_t)1, v.sig, v.pkneg, v.hm, (const uint8_t*)v.ok_hm, (const uint8_t*)nullptr, (const uint8_t*)nullptr, dres, (const int*)nullptr);
-    LAUNCH(k_pairing_fixup, 1, 32, g.stream, (size_t)1, v.sig, v.pkneg, v.hm, (const uint8_t*)v.ok_hm, (const uint8_t*)nullptr, (const uint8_t*)nullptr, dres, (const int*)nullptr);
-    uint8_t res = 0;
-    cudaMemcpyAsync(&res, dres, 1, cudaMemcpyDeviceToHost, g.stream);
-    if (cudaStreamSynchronize(g.stream) != cudaSuccess) return 0;
-    return res ? 1 : 0;
+    return verify_hash_locked(sig, pub, nullptr, nullptr, h, size) == 1 ? 1 : 0;
 }
 void blsSign(blsSignature* sig, const blsSecretKey* sec, const void* m, size_t size) {
     uint8_t dg[64]; Sha512::digest((const uint8_t*)m, size, dg);
@@ -430,11 +561,11 @@ int hbls_committee_create(hbls_committee** out, const uint8_t* pk48, size_t n, s
     if (int e = ensure_init()) return e;
     if (!out) return HBLS_ERR_ARG;
     std::lock_guard<std::mutex> lk(g.mu);
-    hbls_committee* c = new hbls_committee; c->n = n;
+    std::unique_ptr<hbls_committee> c(new hbls_committee); c->n = n;       // freed (with its device tables) on every early return
     size_t nn = n ? n : 1;
     CK(cudaMalloc(&c->table, nn * sizeof(g1a)));
-    if (int e = reserve(nn * 49 + 4096)) return e;
-    Arena ar{g.scratch, 0, g.scratch_cap};
+    Scratch* sc; if (int e = reserve(g.stream, nn * 49 + 4096, &sc)) return e;
+    Arena ar{sc->base, 0, sc->cap};
     uint8_t* din = ar.take<uint8_t>(nn * 48); uint8_t* dok = ar.take<uint8_t>(nn);
     std::vector<uint8_t> ok(nn, 1);
     if (n) {
@@ -445,21 +576,18 @@ int hbls_committee_create(hbls_committee** out, const uint8_t* pk48, size_t n, s
         CK(cudaMemcpyAsync(ok.data(), dok, n, cudaMemcpyDeviceToHost, g.stream));
         CK(cudaStreamSynchronize(g.stream));
     }
-    for (size_t i = 0; i < n; i++) if (!ok[i]) {
-        if (bad_index) *bad_index = i;
-        cudaFree(c->table); cudaFree(c->total); delete c; return HBLS_ERR_DECODE;
-    }
-    *out = c; return 0;
+    for (size_t i = 0; i < n; i++) if (!ok[i]) { if (bad_index) *bad_index = i; return HBLS_ERR_DECODE; }
+    *out = c.release(); return 0;
 }
-void hbls_committee_destroy(hbls_committee* c) { if (!c) return; std::lock_guard<std::mutex> lk(g.mu); cudaFree(c->table); cudaFree(c->total); delete c; }
+void hbls_committee_destroy(hbls_committee* c) { if (!c) return; std::lock_guard<std::mutex> lk(g.mu); cudaDeviceSynchronize(); delete c; }
 size_t hbls_committee_size(const hbls_committee* c) { return c ? c->n : 0; }
 
 int hbls_mask_aggregate(const hbls_committee* c, const uint8_t* bitmap, size_t blen, uint8_t out_pk48[48]) {
     if (int e = ensure_init()) return e;
     if (!c || blen != ((c->n + 7) >> 3)) return HBLS_ERR_ARG;
     std::lock_guard<std::mutex> lk(g.mu);
-    if (int e = reserve(blen + 4096)) return e;
-    Arena ar{g.scratch, 0, g.scratch_cap};
+    Scratch* sc; if (int e = reserve(g.stream, blen + 4096, &sc)) return e;
+    Arena ar{sc->base, 0, sc->cap};
     uint8_t* dbm = ar.take<uint8_t>(blen ? blen : 1); g1* dacc = ar.take<g1>(1); uint8_t* dout = ar.take<uint8_t>(48);
     if (blen) CK(cudaMemcpyAsync(dbm, bitmap, blen, cudaMemcpyHostToDevice, g.stream));
     LAUNCH(k_mask_aggregate, 1, 32, g.stream, (size_t)1, c->n, c->table, dbm, blen, dacc);
@@ -473,8 +601,8 @@ int hbls_aggregate_sigs(const uint8_t* sig96, size_t n, uint8_t out96[96]) {
     if (int e = ensure_init()) return e;
     std::lock_guard<std::mutex> lk(g.mu);
     size_t nn = n ? n : 1;
-    if (int e = reserve(nn * (96 + sizeof(g2a) + 1) + 4096)) return e;
-    Arena ar{g.scratch, 0, g.scratch_cap};
+    Scratch* sc; if (int e = reserve(g.stream, nn * (96 + sizeof(g2a) + 1) + 4096, &sc)) return e;
+    Arena ar{sc->base, 0, sc->cap};
     uint8_t* din = ar.take<uint8_t>(nn * 96); g2a* dpts = ar.take<g2a>(nn); uint8_t* dok = ar.take<uint8_t>(nn);
     g2* dsum = ar.take<g2>(1); uint8_t* dout = ar.take<uint8_t>(96);
     std::vector<uint8_t> ok(nn, 1);
@@ -492,92 +620,255 @@ int hbls_aggregate_sigs(const uint8_t* sig96, size_t n, uint8_t out96[96]) {
 }
 
 // ------------------------------------------------------------------ aggregate verification
-static bool all_messages_equal(const uint8_t* msgs, size_t n, size_t msg_len) {
-    for (size_t i = 1; i < n; i++) if (memcmp(msgs, msgs + i * msg_len, msg_len) != 0) return false;
-    return n > 1;
-}
-static int agg_verify_device_locked(const hbls_committee* c, size_t B, const uint8_t* d_bitmaps, size_t blen, const uint8_t* d_sigs,
-                                    const uint8_t* d_msgs, size_t msg_len, uint8_t* d_results, cudaStream_t s, Arena& ar, bool same_msg = false) {
-    VerifyBufs v = carve_verify(ar, B);
-    STAGE_EV(0, s);
-    if (B >= (size_t)g.sm_count * 256)
-        LAUNCH(k_mask_aggregate_serial, light_blocks(B), TPB, s, B, c->n, c->table, c->total, d_bitmaps, blen, v.apk);
-    else
-        LAUNCH(k_mask_aggregate, blocks_for(B * 32, 128), 128, s, B, c->n, c->table, d_bitmaps, blen, v.apk);
-    STAGE_EV(1, s);
-    // the batched check consumes the Jacobian sums directly; -apk in affine form is then only needed if a group fails
-    if (!rlc_applies(B, true)) LAUNCH(k_g1_normalize, blocks_for(B, TPB), TPB, s, B, v.apk, v.pkneg, 1, (const int*)nullptr);
-    launch_verify_tail(B, v, d_sigs, d_msgs, (uint32_t)msg_len, nullptr, d_results, s, same_msg, v.apk);
-    if (g.stage_timing) g.stage_valid = true;
-    return 0;
-}
 int hbls_aggregate_verify_batch_device(const hbls_committee* c, size_t B, const void* d_bitmaps, size_t blen, const void* d_sigs96,
                                        const void* d_msgs, size_t msg_len, void* d_results, void* stream) {
     if (int e = ensure_init()) return e;
-    if (!c || blen != ((c->n + 7) >> 3) || msg_len > 64) return HBLS_ERR_ARG;
+    if (!c || blen != ((c->n + 7) >> 3)) return HBLS_ERR_ARG;
     if (B == 0) return 0;
     std::lock_guard<std::mutex> lk(g.mu);
-    if (int e = reserve(verify_scratch_bytes(B))) return e;
-    Arena ar{g.scratch, 0, g.scratch_cap};
     cudaStream_t s = stream ? (cudaStream_t)stream : g.stream;
-    int rc = agg_verify_device_locked(c, B, (const uint8_t*)d_bitmaps, blen, (const uint8_t*)d_sigs96, (const uint8_t*)d_msgs, msg_len, (uint8_t*)d_results, s, ar);
+    Scratch* sc; if (int e = reserve(s, verify_scratch_bytes(B), &sc)) return e;
+    ensure_stage_events(sc);
+    Arena ar{sc->base, 0, sc->cap};
+    int rc = agg_verify_device_locked(c, B, (const uint8_t*)d_bitmaps, blen, (const uint8_t*)d_sigs96, (const uint8_t*)d_msgs, msg_len, (uint8_t*)d_results, s, sc, ar, false);
     CK(cudaGetLastError());
     return rc;
+}
+// host-buffer form shared by the batch entry and the header-range entry: flags_out (nullable) receives the decode flags per round
+static int agg_verify_host_locked(const hbls_committee* c, size_t B, const uint8_t* bitmaps, size_t blen, const uint8_t* sigs96,
+                                  const uint8_t* msgs, size_t msg_len, uint8_t* results, uint8_t* flags_out) {
+    size_t in_bytes = B * (blen + 96 + msg_len);
+    Scratch* sc; if (int e = reserve(g.stream, verify_scratch_bytes(B) + in_bytes + 2 * B + 4096, &sc)) return e;
+    ensure_stage_events(sc);
+    Arena ar{sc->base, 0, sc->cap};
+    uint8_t* dbm = ar.take<uint8_t>(B * blen + 1); uint8_t* dsig = ar.take<uint8_t>(B * 96); uint8_t* dmsg = ar.take<uint8_t>(B * msg_len + 1);
+    uint8_t* dres = ar.take<uint8_t>(B); uint8_t* dflags = ar.take<uint8_t>(B);
+    if (blen) CK(cudaMemcpyAsync(dbm, bitmaps, B * blen, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(dsig, sigs96, B * 96, cudaMemcpyHostToDevice, g.stream));
+    if (msg_len) CK(cudaMemcpyAsync(dmsg, msgs, B * msg_len, cudaMemcpyHostToDevice, g.stream));
+    VerifyBufs v;
+    agg_verify_device_locked(c, B, dbm, blen, dsig, dmsg, msg_len, dres, g.stream, sc, ar, all_messages_equal(msgs, B, msg_len), &v);
+    CK(cudaMemcpyAsync(results, dres, B, cudaMemcpyDeviceToHost, g.stream));
+    if (flags_out) {
+        LAUNCH(k_pack_flags, blocks_for(B, 256), 256, g.stream, B, v.ok_sig, v.ok_hm, (const uint8_t*)nullptr, dflags);
+        CK(cudaMemcpyAsync(flags_out, dflags, B, cudaMemcpyDeviceToHost, g.stream));
+    }
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
 }
 int hbls_aggregate_verify_batch(const hbls_committee* c, size_t B, const uint8_t* bitmaps, size_t blen, const uint8_t* sigs96,
                                 const uint8_t* msgs, size_t msg_len, uint8_t* results) {
     if (int e = ensure_init()) return e;
-    if (!c || blen != ((c->n + 7) >> 3) || msg_len > 64) return HBLS_ERR_ARG;
+    if (!c || blen != ((c->n + 7) >> 3)) return HBLS_ERR_ARG;
     if (B == 0) return 0;
     std::lock_guard<std::mutex> lk(g.mu);
-    size_t in_bytes = B * (blen + 96 + msg_len);
-    if (int e = reserve(verify_scratch_bytes(B) + in_bytes + B + 4096)) return e;
-    Arena ar{g.scratch, 0, g.scratch_cap};
-    uint8_t* dbm = ar.take<uint8_t>(B * blen + 1); uint8_t* dsig = ar.take<uint8_t>(B * 96); uint8_t* dmsg = ar.take<uint8_t>(B * msg_len + 1);
-    uint8_t* dres = ar.take<uint8_t>(B);
-    if (blen) CK(cudaMemcpyAsync(dbm, bitmaps, B * blen, cudaMemcpyHostToDevice, g.stream));
-    CK(cudaMemcpyAsync(dsig, sigs96, B * 96, cudaMemcpyHostToDevice, g.stream));
-    if (msg_len) CK(cudaMemcpyAsync(dmsg, msgs, B * msg_len, cudaMemcpyHostToDevice, g.stream));
-    agg_verify_device_locked(c, B, dbm, blen, dsig, dmsg, msg_len, dres, g.stream, ar, all_messages_equal(msgs, B, msg_len));
-    CK(cudaMemcpyAsync(results, dres, B, cudaMemcpyDeviceToHost, g.stream));
-    CK(cudaStreamSynchronize(g.stream));
-    return 0;
+    return agg_verify_host_locked(c, B, bitmaps, blen, sigs96, msgs, msg_len, results, nullptr);
 }
 int hbls_aggregate_verify(const hbls_committee* c, const uint8_t* bitmap, size_t blen, const uint8_t sig96[96], const void* msg, size_t msg_len) {
-    if (msg_len > 64) msg_len = 64;       // only the first 48 bytes enter the map
     uint8_t res = 0;
     int rc = hbls_aggregate_verify_batch(c, 1, bitmap, blen, sig96, (const uint8_t*)msg, msg_len, &res);
     if (rc) return rc;
     return res ? 1 : 0;
 }
+int hbls_verify_headers(const hbls_committee* c, size_t n, const uint8_t* sigs96, const uint8_t* bitmaps, size_t blen,
+                        const uint8_t* payloads, size_t payload_len, size_t quorum, uint8_t* status) {
+    if (int e = ensure_init()) return e;
+    if (!c || blen != ((c->n + 7) >> 3) || !status) return HBLS_ERR_ARG;        // DecodeSigBitmap: mask.SetMask length error (sig.go:43)
+    if (n == 0) return 0;
+    std::lock_guard<std::mutex> lk(g.mu);
+    std::vector<uint8_t> res(n), flags(n);
+    if (int e = agg_verify_host_locked(c, n, bitmaps, blen, sigs96, payloads, payload_len, res.data(), flags.data())) return e;
+    for (size_t i = 0; i < n; i++) {
+        // engine.go:630-640: DecodeSigBitmap (signature deserialise) -> IsQuorumAchievedByMask -> VerifyHash
+        if (!(flags[i] & 1)) status[i] = HBLS_HDR_BAD_ENCODING;
+        else if (quorum && (size_t)popcount_slots(bitmaps + i * blen, c->n) < quorum) status[i] = HBLS_HDR_NO_QUORUM;
+        else status[i] = res[i] ? HBLS_HDR_OK : HBLS_HDR_BAD_SIG;
+    }
+    return 0;
+}
+
+int hbls_aggregate_verify_items(size_t k, const hbls_committee* const* committees, const uint8_t* bitmaps, const uint8_t* sigs96,
+                                const uint8_t* msgs, size_t msg_len, uint8_t* results) {
+    if (int e = ensure_init()) return e;
+    if (k == 0) return 0;
+    if (!committees || !results) return HBLS_ERR_ARG;
+    size_t bm_bytes = 0;
+    for (size_t j = 0; j < k; j++) { if (!committees[j]) return HBLS_ERR_ARG; bm_bytes += (committees[j]->n + 7) >> 3; }
+    std::lock_guard<std::mutex> lk(g.mu);
+    Scratch* sc; if (int e = reserve(g.stream, verify_scratch_bytes(k) + bm_bytes + k * (96 + msg_len + 1 + sizeof(mask_item)) + 4096, &sc)) return e;
+    ensure_stage_events(sc);
+    Arena ar{sc->base, 0, sc->cap};
+    VerifyBufs v = carve_verify(ar, k);
+    uint8_t* dbm = ar.take<uint8_t>(bm_bytes + 1); uint8_t* dsig = ar.take<uint8_t>(k * 96); uint8_t* dmsg = ar.take<uint8_t>(k * msg_len + 1);
+    uint8_t* dres = ar.take<uint8_t>(k); mask_item* ditems = ar.take<mask_item>(k);
+    std::vector<mask_item> items(k); size_t off = 0;
+    for (size_t j = 0; j < k; j++) { items[j].table = committees[j]->table; items[j].bitmap = dbm + off; items[j].n = committees[j]->n; off += (committees[j]->n + 7) >> 3; }
+    if (bm_bytes) CK(cudaMemcpyAsync(dbm, bitmaps, bm_bytes, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(dsig, sigs96, k * 96, cudaMemcpyHostToDevice, g.stream));
+    if (msg_len) CK(cudaMemcpyAsync(dmsg, msgs, k * msg_len, cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(ditems, items.data(), k * sizeof(mask_item), cudaMemcpyHostToDevice, g.stream));
+    STAGE_EV(0, sc, g.stream);
+    LAUNCH(k_mask_aggregate_items, blocks_for(k * 32, 128), 128, g.stream, k, ditems, v.apk);
+    launch_verify_tail(k, v, sc, dsig, dmsg, (uint32_t)msg_len, nullptr, dres, g.stream, all_messages_equal(msgs, k, msg_len));
+    CK(cudaMemcpyAsync(results, dres, k, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));          // items[] (pageable source of an async copy) stays alive until here
+    return 0;
+}
 
 int hbls_verify_batch(size_t k, const uint8_t* pk48, const uint8_t* sig96, const uint8_t* msgs, size_t msg_len, uint8_t* results) {
     if (int e = ensure_init()) return e;
-    if (msg_len > 64) return HBLS_ERR_ARG;
     if (k == 0) return 0;
     std::lock_guard<std::mutex> lk(g.mu);
-    if (int e = reserve(verify_scratch_bytes(k) + k * (48 + 96 + msg_len + 1) + 4096)) return e;
-    Arena ar{g.scratch, 0, g.scratch_cap};
+    Scratch* sc; if (int e = reserve(g.stream, verify_scratch_bytes(k) + k * (48 + 96 + msg_len + 1) + 4096, &sc)) return e;
+    ensure_stage_events(sc);
+    Arena ar{sc->base, 0, sc->cap};
     VerifyBufs v = carve_verify(ar, k);
     uint8_t* dpk = ar.take<uint8_t>(k * 48); uint8_t* dsig = ar.take<uint8_t>(k * 96); uint8_t* dmsg = ar.take<uint8_t>(k * msg_len + 1);
     uint8_t* dres = ar.take<uint8_t>(k);
     CK(cudaMemcpyAsync(dpk, pk48, k * 48, cudaMemcpyHostToDevice, g.stream));
     CK(cudaMemcpyAsync(dsig, sig96, k * 96, cudaMemcpyHostToDevice, g.stream));
     if (msg_len) CK(cudaMemcpyAsync(dmsg, msgs, k * msg_len, cudaMemcpyHostToDevice, g.stream));
-    LAUNCH(k_g1_decode, blocks_for(k, TPB), TPB, g.stream, k, dpk, v.pkneg, v.ok_pk, 1, 1);
-    launch_verify_tail(k, v, dsig, dmsg, (uint32_t)msg_len, v.ok_pk, dres, g.stream, all_messages_equal(msgs, k, msg_len));
+    STAGE_EV(0, sc, g.stream);
+    // keys stay Jacobian (z = 1): the same tail as a mask aggregate, so independent triples also go through the batched groups
+    LAUNCH(k_g1_decode_jac, heavy_blocks(k), TPB, g.stream, k, dpk, v.apk, v.ok_pk, 1);
+    launch_verify_tail(k, v, sc, dsig, dmsg, (uint32_t)msg_len, v.ok_pk, dres, g.stream, all_messages_equal(msgs, k, msg_len));
     CK(cudaMemcpyAsync(results, dres, k, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
     return 0;
 }
 
+// ------------------------------------------------------------------ persistent Mask / running vote aggregate
+int hbls_mask_create(hbls_mask** out, const hbls_committee* c) {
+    if (int e = ensure_init()) return e;
+    if (!out || !c) return HBLS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g.mu);
+    std::unique_ptr<hbls_mask> m(new hbls_mask); m->c = c; m->bitmap.assign((c->n + 7) >> 3, 0);
+    CK(cudaMalloc(&m->d_acc, sizeof(g1)));
+    CK(cudaMemsetAsync(m->d_acc, 0, sizeof(g1), g.stream));          // all-zero struct = identity (mask.go:88)
+    CK(cudaStreamSynchronize(g.stream));
+    *out = m.release(); return 0;
+}
+void hbls_mask_destroy(hbls_mask* m) { if (!m) return; std::lock_guard<std::mutex> lk(g.mu); cudaDeviceSynchronize(); delete m; }
+int hbls_mask_clear(hbls_mask* m) {
+    if (int e = ensure_init()) return e;
+    if (!m) return HBLS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g.mu);
+    std::fill(m->bitmap.begin(), m->bitmap.end(), 0);
+    CK(cudaMemsetAsync(m->d_acc, 0, sizeof(g1), g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+int hbls_mask_set_mask(hbls_mask* m, const uint8_t* bitmap, size_t blen) {
+    if (int e = ensure_init()) return e;
+    if (!m || blen != m->bitmap.size()) return HBLS_ERR_ARG;          // mask.go:114-120 "mismatching bitmap lengths"
+    std::lock_guard<std::mutex> lk(g.mu);
+    const size_t n = m->c->n;
+    std::vector<uint8_t> delta(2 * blen + 2, 0);                       // row 0: bits to Add (0 -> 1), row 1: bits to Sub (1 -> 0)
+    bool any = false;
+    for (size_t i = 0; i < n; i++) {                                   // only slots i < n exist (mask.go:121: for i := range m.Publics)
+        const uint8_t msk = (uint8_t)(1u << (i & 7)); const bool was = m->bitmap[i >> 3] & msk, now = bitmap[i >> 3] & msk;
+        if (!was && now) { delta[i >> 3] |= msk; any = true; }
+        if (was && !now) { delta[blen + (i >> 3)] |= msk; any = true; }
+    }
+    if (!any) return 0;
+    Scratch* sc; if (int e = reserve(g.stream, 2 * blen + 4096, &sc)) return e;
+    Arena ar{sc->base, 0, sc->cap};
+    uint8_t* dbm = ar.take<uint8_t>(2 * blen + 2); g1* dtmp = ar.take<g1>(2); int* drc = ar.take<int>(1);
+    CK(cudaMemcpyAsync(dbm, delta.data(), 2 * blen, cudaMemcpyHostToDevice, g.stream));
+    LAUNCH(k_mask_aggregate, 1, 64, g.stream, (size_t)2, n, m->c->table, dbm, blen, dtmp);
+    LAUNCH(k_single, 1, 32, g.stream, (int)OP_G1_ADD, (const void*)m->d_acc, (const void*)(dtmp + 0), (void*)m->d_acc, drc, 0u);
+    LAUNCH(k_single, 1, 32, g.stream, (int)OP_G1_SUB, (const void*)m->d_acc, (const void*)(dtmp + 1), (void*)m->d_acc, drc, 0u);
+    CK(cudaStreamSynchronize(g.stream));
+    for (size_t i = 0; i < n; i++) {
+        const uint8_t msk = (uint8_t)(1u << (i & 7));
+        m->bitmap[i >> 3] = (uint8_t)((m->bitmap[i >> 3] & ~msk) | (bitmap[i >> 3] & msk));
+    }
+    return 0;
+}
+int hbls_mask_set_bit(hbls_mask* m, size_t index, int enable) {
+    if (!m || index >= m->c->n) return HBLS_ERR_ARG;                   // mask.go:138-140 "index out of range"
+    std::vector<uint8_t> bm;
+    { std::lock_guard<std::mutex> lk(g.mu); bm = m->bitmap; }
+    const uint8_t msk = (uint8_t)(1u << (index & 7));
+    if (enable) bm[index >> 3] |= msk; else bm[index >> 3] &= (uint8_t)~msk;
+    return hbls_mask_set_mask(m, bm.data(), bm.size());
+}
+int hbls_mask_count_enabled(const hbls_mask* m) {
+    if (!m) return HBLS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g.mu);
+    return popcount_slots(m->bitmap.data(), m->c->n);
+}
+int hbls_mask_get(const hbls_mask* m, uint8_t* bitmap_out, size_t blen, uint8_t pk48_out[48]) {
+    if (int e = ensure_init()) return e;
+    if (!m || (bitmap_out && blen != m->bitmap.size())) return HBLS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (bitmap_out) memcpy(bitmap_out, m->bitmap.data(), blen);
+    if (pk48_out) {
+        Scratch* sc; if (int e = reserve(g.stream, 4096, &sc)) return e;
+        Arena ar{sc->base, 0, sc->cap};
+        uint8_t* dout = ar.take<uint8_t>(48);
+        LAUNCH(k_g1_serialize, 1, 32, g.stream, (size_t)1, (const g1*)m->d_acc, dout);
+        CK(cudaMemcpyAsync(pk48_out, dout, 48, cudaMemcpyDeviceToHost, g.stream));
+        CK(cudaStreamSynchronize(g.stream));
+    }
+    return 0;
+}
+int hbls_mask_verify(const hbls_mask* m, const uint8_t sig96[96], const void* msg, size_t msg_len) {
+    if (int e = ensure_init()) return e;
+    if (!m || !sig96) return HBLS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g.mu);
+    return verify_hash_locked(nullptr, nullptr, m->d_acc, sig96, msg, msg_len);
+}
+int hbls_ballot_box_create(hbls_ballot_box** out, const hbls_committee* c) {
+    if (int e = ensure_init()) return e;
+    if (!out || !c) return HBLS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g.mu);
+    std::unique_ptr<hbls_ballot_box> b(new hbls_ballot_box); b->c = c; b->collected.assign((c->n + 7) >> 3, 0);
+    CK(cudaMalloc(&b->d_sum, sizeof(g2)));
+    CK(cudaMemsetAsync(b->d_sum, 0, sizeof(g2), g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    *out = b.release(); return 0;
+}
+void hbls_ballot_box_destroy(hbls_ballot_box* b) { if (!b) return; std::lock_guard<std::mutex> lk(g.mu); cudaDeviceSynchronize(); delete b; }
+int hbls_ballot_box_add_vote(hbls_ballot_box* b, const uint8_t* signer_bitmap, size_t blen, const uint8_t sig96[96]) {
+    if (int e = ensure_init()) return e;
+    if (!b || !signer_bitmap || blen != b->collected.size()) return HBLS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g.mu);
+    const size_t n = b->c->n;
+    for (size_t i = 0; i < n; i++)                                      // quorum.go:168-181: skip a ballot that shares a signer with a collected one
+        if ((signer_bitmap[i >> 3] >> (i & 7)) & 1 && (b->collected[i >> 3] >> (i & 7)) & 1) return 1;
+    Scratch* sc; if (int e = reserve(g.stream, 4096, &sc)) return e;
+    Arena ar{sc->base, 0, sc->cap};
+    uint8_t* dsig = ar.take<uint8_t>(96); int* drc = ar.take<int>(1);
+    CK(cudaMemcpyAsync(dsig, sig96, 96, cudaMemcpyHostToDevice, g.stream));
+    LAUNCH(k_single, 1, 32, g.stream, (int)OP_G2_DES_ADD, (const void*)dsig, (const void*)nullptr, (void*)b->d_sum, drc, 0u);
+    int rc = 0;
+    CK(cudaMemcpyAsync(&rc, drc, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    if (rc != 96) return HBLS_ERR_DECODE;
+    for (size_t i = 0; i < n; i++) if ((signer_bitmap[i >> 3] >> (i & 7)) & 1) b->collected[i >> 3] |= (uint8_t)(1u << (i & 7));
+    return 0;
+}
+int hbls_ballot_box_aggregate(const hbls_ballot_box* b, uint8_t out_sig96[96], uint8_t* bitmap_out, size_t blen) {
+    if (int e = ensure_init()) return e;
+    if (!b || !out_sig96 || (bitmap_out && blen != b->collected.size())) return HBLS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g.mu);
+    Scratch* sc; if (int e = reserve(g.stream, 4096, &sc)) return e;
+    Arena ar{sc->base, 0, sc->cap};
+    uint8_t* dout = ar.take<uint8_t>(96);
+    LAUNCH(k_g2_serialize, 1, 32, g.stream, (size_t)1, (const g2*)b->d_sum, dout);
+    CK(cudaMemcpyAsync(out_sig96, dout, 96, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    if (bitmap_out) memcpy(bitmap_out, b->collected.data(), blen);
+    return 0;
+}
+
 int hbls_sign_hash_batch(size_t k, const uint8_t* sk32, const uint8_t* msgs, size_t msg_len, uint8_t* sig96_out, uint8_t* ok) {
     if (int e = ensure_init()) return e;
-    if (msg_len > 64) return HBLS_ERR_ARG;
     if (k == 0) return 0;
     std::lock_guard<std::mutex> lk(g.mu);
-    if (int e = reserve(k * (32 + msg_len + sizeof(g2) + 96 + 1) + 4096)) return e;
-    Arena ar{g.scratch, 0, g.scratch_cap};
+    Scratch* sc; if (int e = reserve(g.stream, k * (32 + msg_len + sizeof(g2) + 96 + 1) + 4096, &sc)) return e;
+    Arena ar{sc->base, 0, sc->cap};
     uint8_t* dsk = ar.take<uint8_t>(k * 32); uint8_t* dmsg = ar.take<uint8_t>(k * msg_len + 1); g2* dpts = ar.take<g2>(k);
     uint8_t* dout = ar.take<uint8_t>(k * 96); uint8_t* dok = ar.take<uint8_t>(k);
     CK(cudaMemcpyAsync(dsk, sk32, k * 32, cudaMemcpyHostToDevice, g.stream));
@@ -593,8 +884,8 @@ int hbls_get_public_key_batch(size_t k, const uint8_t* sk32, uint8_t* pk48_out) 
     if (int e = ensure_init()) return e;
     if (k == 0) return 0;
     std::lock_guard<std::mutex> lk(g.mu);
-    if (int e = reserve(k * (32 + sizeof(g1) + 48) + 4096)) return e;
-    Arena ar{g.scratch, 0, g.scratch_cap};
+    Scratch* sc; if (int e = reserve(g.stream, k * (32 + sizeof(g1) + 48) + 4096, &sc)) return e;
+    Arena ar{sc->base, 0, sc->cap};
     uint8_t* dsk = ar.take<uint8_t>(k * 32); g1* dpts = ar.take<g1>(k); uint8_t* dout = ar.take<uint8_t>(k * 48);
     CK(cudaMemcpyAsync(dsk, sk32, k * 32, cudaMemcpyHostToDevice, g.stream));
     LAUNCH(k_g1_mul_gen, blocks_for(k, TPB), TPB, g.stream, k, dsk, dpts);
@@ -604,14 +895,12 @@ int hbls_get_public_key_batch(size_t k, const uint8_t* sk32, uint8_t* pk48_out) 
     return 0;
 }
 
-int hbls_debug_g2(const uint8_t sig96[96], uint8_t out512[512]) {
-    int rc = -1; if (int e = single_op(OP_DBG_G2, sig96, 96, nullptr, 0, out512, 512, &rc)) return e; return rc; }
 int hbls_fp_mul_batch(size_t n, const uint8_t* a48, const uint8_t* b48, uint8_t* out48) {
     if (int e = ensure_init()) return e;
     if (n == 0) return 0;
     std::lock_guard<std::mutex> lk(g.mu);
-    if (int e = reserve(n * 144 + 4096)) return e;
-    Arena ar{g.scratch, 0, g.scratch_cap};
+    Scratch* sc; if (int e = reserve(g.stream, n * 144 + 4096, &sc)) return e;
+    Arena ar{sc->base, 0, sc->cap};
     uint8_t* da = ar.take<uint8_t>(n * 48); uint8_t* db = ar.take<uint8_t>(n * 48); uint8_t* dout = ar.take<uint8_t>(n * 48);
     CK(cudaMemcpyAsync(da, a48, n * 48, cudaMemcpyHostToDevice, g.stream));
     CK(cudaMemcpyAsync(db, b48, n * 48, cudaMemcpyHostToDevice, g.stream));
@@ -623,22 +912,22 @@ int hbls_fp_mul_batch(size_t n, const uint8_t* a48, const uint8_t* b48, uint8_t*
 
 void hbls_stage_timing_enable(int on) {
     std::lock_guard<std::mutex> lk(g.mu);
-    if (on && !g.ev[0]) for (int i = 0; i < 8; i++) cudaEventCreate(&g.ev[i]);
-    g.stage_timing = on != 0; g.stage_valid = false;
+    g.stage_timing = on != 0; g.stage_sc = nullptr;
 }
 int hbls_stage_timing_get(float* ms_out, int max_stages) {
     std::lock_guard<std::mutex> lk(g.mu);
-    if (!g.stage_valid) return 0;
-    if (cudaEventSynchronize(g.ev[6]) != cudaSuccess) return 0;
+    Scratch* sc = g.stage_sc;
+    if (!sc || !sc->ev_ok) return 0;
+    if (cudaEventSynchronize(sc->ev[6]) != cudaSuccess) return 0;
     int n = max_stages < 6 ? max_stages : 6;
-    for (int i = 0; i < n; i++) { float ms = 0; cudaEventElapsedTime(&ms, g.ev[i], g.ev[i + 1]); ms_out[i] = ms; }
+    for (int i = 0; i < n; i++) { float ms = 0; cudaEventElapsedTime(&ms, sc->ev[i], sc->ev[i + 1]); ms_out[i] = ms; }
     return n;
 }
 int hbls_selftest_split(uint32_t iters) {
     if (int e = ensure_init()) return e;
     std::lock_guard<std::mutex> lk(g.mu);
-    if (int e = reserve(4096)) return e;
-    uint32_t* d = reinterpret_cast<uint32_t*>(g.scratch);
+    Scratch* sc; if (int e = reserve(g.stream, 4096, &sc)) return e;
+    uint32_t* d = reinterpret_cast<uint32_t*>(sc->base);
     CK(cudaMemsetAsync(d, 0, 4, g.stream));
     LAUNCH(k_selftest_fp2h, 8, 64, g.stream, iters, 20240922u, d);
     uint32_t bad = 0;
@@ -646,22 +935,26 @@ int hbls_selftest_split(uint32_t iters) {
     CK(cudaStreamSynchronize(g.stream));
     return (int)bad;
 }
-double hbls_probe_mac32_per_s(int iters) {
+double hbls_probe_mac32_per_s(int iters, double* sm_clock_hz) {
     if (ensure_init()) return -1.0;
     std::lock_guard<std::mutex> lk(g.mu);
-    if (reserve(4096)) return -1.0;
-    uint64_t* sink = reinterpret_cast<uint64_t*>(g.scratch);
-    constexpr int ILP = 8;
-    const int threads = 256, blocks = g.sm_count * 8;
+    Scratch* sc; if (reserve(g.stream, 4096, &sc)) return -1.0;
+    uint32_t* sink = reinterpret_cast<uint32_t*>(sc->base);
+    unsigned long long* cyc = reinterpret_cast<unsigned long long*>(sc->base + 256);
+    constexpr int K = 4;
+    const int threads = 256, blocks = g.sm_count * 2;                  // one wave: 2 x 256 threads x 94 registers per SM
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    LAUNCH(k_probe_imad<ILP>, blocks, threads, g.stream, iters / 8 + 1, 12345u, sink);     // warm-up
+    LAUNCH(k_probe_carry<K>, blocks, threads, g.stream, iters / 8 + 1, 12345u, sink, cyc);     // warm-up
     cudaEventRecord(e0, g.stream);
-    LAUNCH(k_probe_imad<ILP>, blocks, threads, g.stream, iters, 12345u, sink);
+    LAUNCH(k_probe_carry<K>, blocks, threads, g.stream, iters, 12345u, sink, cyc);
     cudaEventRecord(e1, g.stream);
+    unsigned long long cycles = 0;
+    cudaMemcpyAsync(&cycles, cyc, sizeof cycles, cudaMemcpyDeviceToHost, g.stream);
     if (cudaStreamSynchronize(g.stream) != cudaSuccess) return -1.0;
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    double macs = (double)blocks * threads * (double)iters * ILP;
+    if (sm_clock_hz) *sm_clock_hz = (double)cycles / (ms * 1e-3);      // thread 0's loop spans (nearly) the whole launch
+    double macs = (double)blocks * threads * (double)iters * K * 6.0;  // lane_mad = 6 IMAD.WIDE
     return macs / (ms * 1e-3);
 }
 

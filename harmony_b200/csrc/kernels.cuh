@@ -37,6 +37,14 @@ __global__ void k_g1_decode(size_t n, const uint8_t* in, g1a* out, uint8_t* ok, 
     else { a.x = p.x; a.y = p.y; if (negate) fp_neg(a.y, a.y); }      // deserialize returns z == 1
     out[i] = a; ok[i] = good ? 1 : 0;
 }
+// triples (hbls_verify_batch): the key feeds the same pipeline as a mask aggregate, so it is kept Jacobian (z = 1; identity on failure)
+__global__ void k_g1_decode_jac(size_t n, const uint8_t* in, g1* out, uint8_t* ok, int check_order) {
+  for (size_t i = HB_TID; i < n; i += HB_STRIDE) {
+    g1 p; bool good = g1_deserialize(p, in + 48 * i, check_order != 0);
+    if (!good) pt_set_inf(p);
+    out[i] = p; ok[i] = good ? 1 : 0;
+  }
+}
 __global__ void k_g2_decode(size_t n, const uint8_t* in, g2a* out, uint8_t* ok, int check_order) {
   for (size_t i = HB_TID; i < n; i += HB_STRIDE) {
     g2 p; bool good = g2_deserialize(p, in + 96 * i, check_order != 0);
@@ -70,6 +78,23 @@ __global__ void k_mask_aggregate(size_t B, size_t n, const g1a* __restrict__ tab
     }
     if (lane == 0) out[warp] = acc;
 }
+// multi-committee form (crosslinks / multi-shard block seal: internal/chain/engine.go:592-604, node/harmony/node_cross_link.go:69-90):
+// every item names its own committee table; one warp per item
+struct mask_item { const g1a* table; const uint8_t* bitmap; uint64_t n; };
+__global__ void k_mask_aggregate_items(size_t B, const mask_item* __restrict__ items, g1* out) {
+    size_t warp = HB_TID >> 5; int lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    const mask_item it = items[warp];
+    g1 acc; pt_set_inf(acc);
+    for (size_t i = lane; i < it.n; i += 32) {
+        if (it.bitmap[i >> 3] & (1u << (i & 7))) { g1a q = it.table[i]; pt_add_mixed(acc, acc, q); }
+    }
+    for (int off = 16; off >= 1; off >>= 1) {
+        g1 other; shfl_down_struct(other, acc, off);
+        if (lane < off) pt_add(acc, acc, other);
+    }
+    if (lane == 0) out[warp] = acc;
+}
 // large-batch form: one thread per round.  Quorum bitmaps are dense (167..250 of 250 set), so the thread sums whichever
 // side is SMALLER -- the set bits, or the unset bits subtracted from the committee total (computed once at
 // hbls_committee_create) -- from a compacted index list: ~44 point additions per round instead of ~206, and the
@@ -81,9 +106,10 @@ __global__ void k_mask_aggregate_serial(size_t B, size_t n, const g1a* __restric
     const uint8_t* bm = bitmaps + j * blen;
     uint32_t k = 0;
     for (size_t i = 0; i < n; i++) k += (bm[i >> 3] >> (i & 7)) & 1u;
-    const bool comp = (2 * (size_t)k > n) && (n - k) <= HB_MASK_LIST && total != nullptr;     // sum the unset side
+    const bool fits = n <= 65536;                                                             // idx[] holds 16-bit row numbers
+    const bool comp = fits && (2 * (size_t)k > n) && (n - k) <= HB_MASK_LIST && total != nullptr;     // sum the unset side
     g1 acc; pt_set_inf(acc);
-    if (comp || k <= HB_MASK_LIST) {
+    if (comp || (fits && k <= HB_MASK_LIST)) {
         uint16_t idx[HB_MASK_LIST]; uint32_t cnt = 0;
         const uint32_t want = comp ? 0u : 1u;
         for (size_t i = 0; i < n; i++) if (((bm[i >> 3] >> (i & 7)) & 1u) == want) idx[cnt++] = (uint16_t)i;
@@ -199,43 +225,9 @@ __global__ void k_broadcast_hm(size_t n, g2a* hm, uint8_t* ok) {
     hm[i] = hm[0]; ok[i] = ok[0];
 }
 
-// ---- verification (R7/R8): two Miller loops per round, one thread each:
-//      t even: f = ML(B, sig_j)        t odd: f = ML(-pk_j, H(m_j))
-__global__ void __launch_bounds__(64, HB_MINBLOCKS) k_miller_verify(size_t B, const g2a* sig, const g1a* pk_neg, const g2a* hm, fp12* f) {
-  for (size_t t = HB_TID; t < 2 * B; t += HB_STRIDE) {
-    size_t j = t >> 1;
-    g1a p; g2a q;
-    if (t & 1) { p = pk_neg[j]; q = hm[j]; }
-    else { fp_set(p.x, K_G1_X); fp_set(p.y, K_G1_Y); q = sig[j]; }
-    fp12 r; miller_loop(r, p, q);
-    f[t] = r;
-  }
-}
-// result_j = ok flags && FE(f_2j * f_2j+1) == 1
-__global__ void __launch_bounds__(64, HB_MINBLOCKS) k_final_verify(size_t B, const fp12* f, const uint8_t* ok_a, const uint8_t* ok_b, const uint8_t* ok_c, uint8_t* results) {
-  for (size_t j = HB_TID; j < B; j += HB_STRIDE) {
-    bool good = (!ok_a || ok_a[j]) && (!ok_b || ok_b[j]) && (!ok_c || ok_c[j]);
-    fp12 m, a = f[2 * j], b = f[2 * j + 1];
-    fp12_mul(m, a, b); final_exp(m, m);
-    results[j] = (good && fp12_is_one(m)) ? 1 : 0;
-  }
-}
-
-// fused form used when the batch alone fills the chip: one thread per round runs the 2-pair Miller loop (shared
-// squarings) and the final exponentiation back to back -- no Fp12 round trip through HBM
-__global__ void __launch_bounds__(64, HB_MINBLOCKS) k_pairing_verify(size_t B, const g2a* sig, const g1a* pk_neg, const g2a* hm,
-                                 const uint8_t* ok_a, const uint8_t* ok_b, const uint8_t* ok_c, uint8_t* results) {
-  for (size_t j = HB_TID; j < B; j += HB_STRIDE) {
-    bool good = (!ok_a || ok_a[j]) && (!ok_b || ok_b[j]) && (!ok_c || ok_c[j]);
-    g1a gen, p2 = pk_neg[j]; g2a q1 = sig[j], q2 = hm[j];
-    fp_set(gen.x, K_G1_X); fp_set(gen.y, K_G1_Y);
-    fp12 m; miller_loop2(m, gen, q1, p2, q2); final_exp(m, m);
-    results[j] = (good && fp12_is_one(m)) ? 1 : 0;
-  }
-}
-
+// ---- verification (R7/R8)
 // ---- lane-pair form: lanes (2k, 2k+1) co-own round j (even lane = real parts, odd lane = imaginary parts of every Fp2).
-// Half the per-thread state of k_pairing_verify => twice the warps for the same L1/L2 footprint.  Control flow is
+// Half the per-thread state of a thread-per-round pairing => twice the warps for the same L1/L2 footprint.  Control flow is
 // data-oblivious; rounds with an identity operand (never the case for honest input) are flagged 0xFF and recomputed by
 // k_pairing_fixup with the thread-per-round code.
 #ifndef HB_TPB_SPLIT
@@ -272,6 +264,13 @@ __global__ void __launch_bounds__(HB_TPB_SPLIT, HB_MINBLOCKS_SPLIT) k_pairing_ve
         if (valid && role == 0) results[j] = irregular ? 0xFF : ((good && one) ? 1 : 0);
     }
 }
+// rounds with an identity operand (thread-per-round code path).  An identity public key never verifies (include/hbls.h: a
+// zero key would make the zero signature "valid" for every message); an identity signature is checked like any other point.
+HB_NOINLINE bool verify_irregular(const g1a& gen, const g2a& q1, const g1a& p2, const g2a& q2) {
+    if (aff_is_inf(p2)) return false;
+    fp12 m; miller_loop2(m, gen, q1, p2, q2); final_exp(m, m);
+    return fp12_is_one(m);
+}
 __global__ void k_pairing_fixup(size_t B, const g2a* sig, const g1a* pk_neg, const g2a* hm,
                                 const uint8_t* ok_a, const uint8_t* ok_b, const uint8_t* ok_c, uint8_t* results, const int* run_if) {
   if (run_if && *run_if == 0) return;
@@ -280,32 +279,27 @@ __global__ void k_pairing_fixup(size_t B, const g2a* sig, const g1a* pk_neg, con
     bool good = (!ok_a || ok_a[j]) && (!ok_b || ok_b[j]) && (!ok_c || ok_c[j]);
     g1a gen, p2 = pk_neg[j]; g2a q1 = sig[j], q2 = hm[j];
     fp_set(gen.x, K_G1_X); fp_set(gen.y, K_G1_Y);
-    fp12 m; miller_loop2(m, gen, q1, p2, q2); final_exp(m, m);
-    results[j] = (good && fp12_is_one(m)) ? 1 : 0;
+    results[j] = (good && verify_irregular(gen, q1, p2, q2)) ? 1 : 0;
   }
 }
 // ------------------------------------------------------------------ random-linear-combination batch (R9 / R10 GPU form)
 // prod_j [ e(B, sigma_j) e(-apk_j, H_j) ]^{r_j} == 1 with 64-bit r_j: the G rounds of a group share ONE Miller accumulator
-// (pairs (-r_j apk_j, H_j) plus (B, sum_j r_j sigma_j)) and ONE final exponentiation.  A group that fails -- or contains a
-// round that did not decode -- makes the exact per-round kernels run afterwards, so results stay exact booleans
-// (a bad round survives the batched test with probability <= 2^-63).
+// (pairs (-r_j apk_j, H_j) plus (B, sum_j r_j sigma_j)) and ONE final exponentiation.  The rounds of a group that fails -- or
+// holds a round that did not decode -- are re-verified exactly afterwards (compacted list, k_pairing_verify_split_list), so
+// results stay exact booleans (a bad round survives the batched test with probability <= 2^-63).
 #ifndef HB_RLC_G
 #define HB_RLC_G 4       // smallest group size (scratch is sized for it); the host picks 4 or 8 per call (hbls.cu).  At 75 776 rounds/step the
                          // pairing stage measured 76 / 48 / 68 / 65 ms for G = 3 / 4 / 5 / 7: the group count must still fill the SMs
 #endif
+#define HB_RLC_GMAX 8
 // Groups are STRIDED: group g = rounds {g, g + ng, g + 2 ng, ...}; the coefficient depends only on the position k inside the
-// group (r_k, fresh per call), so the 32 consecutive rounds of a warp share one scalar and the double-and-add ladders run
-// without divergence.  Sharing r_k across groups is sound: every group's test passes wrongly with probability <= 2^-63.
-HB_DEV uint64_t rlc_coeff(uint64_t s0, uint64_t s1, uint64_t j) {
-    uint64_t x = j + s0;
-    for (int r = 0; r < 2; r++) {
-        x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31; x ^= s1; x += 0x9e3779b97f4a7c15ull;
-    }
-    return x | 1ull;
-}
+// group (c[k], fresh per call from the host's keyed ChaCha20 stream: hbls.cu rlc_draw), so the 32 consecutive rounds of a warp
+// share one scalar and the double-and-add ladders run without divergence.  Sharing c[k] across groups is sound: every group's
+// test passes wrongly with probability <= 2^-63 over the draw, whatever the (non-adaptive) input.
+struct rlc_coeffs { uint64_t c[HB_RLC_GMAX]; };
 // per round: P_j = -r_j apk_j (affine), S_j = r_j sigma_j (Jacobian), bad_j
 __global__ void k_rlc_scale(size_t B, size_t ng, const g1* apk, const g2a* sig, const g2a* hm, const uint8_t* ok_sig, const uint8_t* ok_hm,
-                            uint64_t s0, uint64_t s1, g1a* pk_scaled_neg, g2* S, uint8_t* bad) {
+                            const uint8_t* ok_pk, rlc_coeffs co, g1a* pk_scaled_neg, g2* S, uint8_t* bad) {
 #if HB_BATCH_INV
   for (size_t j0 = HB_TID; j0 < B; j0 += (size_t)HB_BATCH_K * HB_STRIDE) {
     g1 ra[HB_BATCH_K]; fp z[HB_BATCH_K]; bool skip[HB_BATCH_K];
@@ -313,9 +307,9 @@ __global__ void k_rlc_scale(size_t B, size_t ng, const g1* apk, const g2a* sig, 
         const size_t j = j0 + (size_t)k * HB_STRIDE;
         skip[k] = true;
         if (j >= B) continue;
-        const uint64_t r = rlc_coeff(s0, s1, j / ng);
+        const uint64_t r = co.c[j / ng];
         g1 a = apk[j]; g2a sg = sig[j]; g2a h = hm[j];
-        const bool b = !ok_sig[j] || !ok_hm[j] || pt_is_inf(a) || aff_is_inf(sg) || aff_is_inf(h);
+        const bool b = !ok_sig[j] || !ok_hm[j] || (ok_pk && !ok_pk[j]) || pt_is_inf(a) || aff_is_inf(sg) || aff_is_inf(h);
         g2 rs; rlc_scale_pair(ra[k], rs, a, sg, r);
         S[j] = rs; bad[j] = b ? 1 : 0;
         skip[k] = pt_is_inf(ra[k]);
@@ -333,9 +327,9 @@ __global__ void k_rlc_scale(size_t B, size_t ng, const g1* apk, const g2a* sig, 
   return;
 #endif
   for (size_t j = HB_TID; j < B; j += HB_STRIDE) {
-    const uint64_t r = rlc_coeff(s0, s1, j / ng);
+    const uint64_t r = co.c[j / ng];
     g1 a = apk[j]; g2a sg = sig[j]; g2a h = hm[j];
-    const bool b = !ok_sig[j] || !ok_hm[j] || pt_is_inf(a) || aff_is_inf(sg) || aff_is_inf(h);
+    const bool b = !ok_sig[j] || !ok_hm[j] || (ok_pk && !ok_pk[j]) || pt_is_inf(a) || aff_is_inf(sg) || aff_is_inf(h);
     g1 ra; g2 rs; rlc_scale_pair(ra, rs, a, sg, r);
     g1a pa; pt_to_aff(pa, ra); fp_neg(pa.y, pa.y);
     pk_scaled_neg[j] = pa; S[j] = rs; bad[j] = b ? 1 : 0;
@@ -382,22 +376,16 @@ template <int G> __global__ void __launch_bounds__(HB_TPB_SPLIT, HB_MINBLOCKS_SP
         if (valid && role == 0) group_ok[g] = (one && !anybad) ? 1 : 0;
     }
 }
-__global__ void k_rlc_finish(size_t nrounds, size_t ngroups, const uint8_t* group_ok, uint8_t* results, int* any_fail) {
+// verdicts of the groups -> per-round results; the rounds of failed groups are compacted into `list` for the exact pass.
+// counts[0] = rounds listed, counts[1] = groups that failed (hbls_last_batch_info)
+__global__ void k_rlc_finish(size_t nrounds, size_t ngroups, const uint8_t* group_ok, uint8_t* results, uint32_t* list, unsigned* counts) {
     size_t j = HB_TID; if (j >= nrounds) return;
     const uint8_t ok = group_ok[j % ngroups];
     results[j] = ok;
-    if (!ok) atomicOr(any_fail, 1);
-}
-
-// HB_FALLBACK_LIST (experimental, off): when groups fail, re-verify ONLY their rounds exactly (compacted index list) instead of
-// the whole batch -- one bad signature among 3*10^5 rounds then costs microseconds, not a second full pass.
-#ifndef HB_FALLBACK_LIST
-#define HB_FALLBACK_LIST 0
-#endif
-#if HB_FALLBACK_LIST
-__global__ void k_rlc_collect_failed(size_t nrounds, size_t ngroups, const uint8_t* group_ok, uint32_t* list, unsigned* count) {
-    size_t j = HB_TID; if (j >= nrounds) return;
-    if (!group_ok[j % ngroups]) list[atomicAdd(count, 1u)] = (uint32_t)j;
+    if (!ok) {
+        list[atomicAdd(&counts[0], 1u)] = (uint32_t)j;
+        if (j < ngroups) atomicAdd(&counts[1], 1u);
+    }
 }
 __global__ void k_g1_normalize_list(const unsigned* count, const uint32_t* list, const g1* in, g1a* out, int negate) {
   const size_t n = *count;
@@ -446,11 +434,15 @@ __global__ void k_pairing_fixup_list(const unsigned* count, const uint32_t* list
     bool good = (!ok_a || ok_a[j]) && (!ok_b || ok_b[j]) && (!ok_c || ok_c[j]);
     g1a gen, p2 = pk_neg[j]; g2a q1 = sig[j], q2 = hm[j];
     fp_set(gen.x, K_G1_X); fp_set(gen.y, K_G1_Y);
-    fp12 m; miller_loop2(m, gen, q1, p2, q2); final_exp(m, m);
-    results[j] = (good && fp12_is_one(m)) ? 1 : 0;
+    results[j] = (good && verify_irregular(gen, q1, p2, q2)) ? 1 : 0;
   }
 }
-#endif
+// headers / items callers want to tell "signature bytes do not decode" from "pairing check failed" (engine.go:630-640 returns
+// different errors): flags[j] bit0 = signature decoded, bit1 = message mapped to a point, bit2 = public key decoded
+__global__ void k_pack_flags(size_t n, const uint8_t* ok_sig, const uint8_t* ok_hm, const uint8_t* ok_pk, uint8_t* flags) {
+    size_t j = HB_TID; if (j >= n) return;
+    flags[j] = (ok_sig[j] ? 1 : 0) | (ok_hm[j] ? 2 : 0) | ((!ok_pk || ok_pk[j]) ? 4 : 0);
+}
 
 // device self-test of the lane-pair Fp2 primitives against the single-thread ones on pseudo-random operands
 __global__ void k_selftest_fp2h(uint32_t n, uint32_t seed, uint32_t* mismatches) {
@@ -496,7 +488,7 @@ __global__ void k_sign_hash(size_t n, const uint8_t* sk32, const uint8_t* msgs, 
 }
 
 // ---- single-element ops behind the herumi-shaped C ABI (one thread; latency is launch-bound)
-enum { OP_G1_ADD = 1, OP_G1_SUB, OP_G2_ADD, OP_G1_EQ, OP_G2_EQ, OP_G1_SER, OP_G2_SER, OP_G1_DES, OP_G2_DES, OP_MAP_SER, OP_DBG_G2 };
+enum { OP_G1_ADD = 1, OP_G1_SUB, OP_G2_ADD, OP_G1_EQ, OP_G2_EQ, OP_G1_SER, OP_G2_SER, OP_G1_DES, OP_G2_DES, OP_MAP_SER, OP_G2_DES_ADD };
 __global__ void k_single(int op, const void* a, const void* b, void* out, int* rc, uint32_t len) {
     if (HB_TID != 0) return;
     switch (op) {
@@ -511,40 +503,42 @@ __global__ void k_single(int op, const void* a, const void* b, void* out, int* r
     case OP_G1_DES: { g1 x; bool g = g1_deserialize(x, (const uint8_t*)a, true); if (g) *(g1*)out = x; *rc = g ? 48 : 0; break; }
     case OP_G2_DES: { g2 x; bool g = g2_deserialize(x, (const uint8_t*)a, true); if (g) *(g2*)out = x; *rc = g ? 96 : 0; break; }
     case OP_MAP_SER: { g2 h; bool g = map_to_g2(h, (const uint8_t*)a, len); if (g) g2_serialize((uint8_t*)out, h); *rc = g ? 0 : -1; break; }
-    case OP_DBG_G2: {   // step-by-step G2 decode probe (debug aid): flags in out[0..31], four serialized points after
-        uint8_t* o = (uint8_t*)out; const uint8_t* in = (const uint8_t*)a;
-        fp va, vb; load_words(va.l, in, 12); load_words(vb.l, in + 48, 12);
-        bool odd = (vb.l[11] >> 31) != 0; vb.l[11] &= 0x7fffffffu;
-        fp2 x, y, t, b2; fp_from_int(x.a, va); fp_from_int(x.b, vb);
-        fp2_sqr(t, x); fp2_mul(t, t, x); fp2_const(b2, K_B2); fp2_add(t, t, b2);
-        o[0] = fp2_sqrt(y, t) ? 1 : 0;
-        o[1] = fp_is_odd(y.a) ? 1 : 0; o[2] = odd ? 1 : 0;
-        if ((o[1] != 0) != odd) fp2_neg(y, y);
-        o[3] = fp_is_odd(y.a) ? 1 : 0;
-        g2 P; P.x = x; P.y = y; fp2_one(P.z);
-        g2 A, B, C, D; g2_psi(A, P); pt_mul_zabs(B, P); pt_neg(C, B); D = B; pt_neg(D, D);
-        o[4] = pt_eq(A, C) ? 1 : 0; o[5] = pt_eq(A, D) ? 1 : 0; o[6] = pt_eq(C, D) ? 1 : 0; o[7] = g2_in_subgroup(P) ? 1 : 0;
-        g2_serialize(o + 32, A); g2_serialize(o + 128, B); g2_serialize(o + 224, C); g2_serialize(o + 320, D); g2_serialize(o + 416, P);
-        *rc = 0; break; }
+    case OP_G2_DES_ADD: {   // ballot box: out (Jacobian running sum) += decode(a); rc = 96 ok / 0 undecodable (sum untouched)
+        g2 x; bool g = g2_deserialize(x, (const uint8_t*)a, true);
+        if (g) { g2 acc = *(const g2*)out; pt_add(acc, acc, x); *(g2*)out = acc; }
+        *rc = g ? 96 : 0; break; }
     default: *rc = -1;
     }
 }
 
-// ---- integer-pipe roofline probe: ILP independent IMAD.WIDE.U32 chains per thread, register resident
-template <int ILP> __global__ void k_probe_imad(int iters, uint32_t seed, uint64_t* sink) {
-    uint64_t acc[ILP];
-    uint32_t a = seed ^ (uint32_t)HB_TID, b = seed * 2654435761u + threadIdx.x;
+// ---- integer-pipe roofline probe: K independent accumulator sets per thread, each fed by lane_mad -- the exact
+// mad.lo.cc / madc.hi.cc chains of the field multiplier (SASS: IMAD.WIDE.U32(.X), 6 per lane_mad).  Round 1 probed two loop
+// invariants with a plain mad.wide; ptxas hoisted the product and the loop became IADD3 pairs, so the "18 TMAC32/s" it
+// reported was half the ALU add rate.  Measured on B200 (tools/probe_int.cu, profiles/r2_probe_int.*): an IMAD.WIDE occupies the
+// FMA-heavy pipe for 4 cycles per warp (a 32-bit IMAD for 2), i.e. 8 wide MACs per clock per scheduler.
+template <int K> __global__ void k_probe_carry(int iters, uint32_t seed, uint32_t* sink, unsigned long long* cycles) {
+    uint32_t acc[K][14], a[12];
+    uint32_t t = seed ^ (uint32_t)HB_TID;
 #pragma unroll
-    for (int k = 0; k < ILP; k++) acc[k] = (uint64_t)(k + 1) * 0x9e3779b97f4a7c15ull + a;
+    for (int j = 0; j < 12; j++) { t = t * 1664525u + 1013904223u; a[j] = t; }
+#pragma unroll
+    for (int k = 0; k < K; k++)
+#pragma unroll
+        for (int j = 0; j < 14; j++) { t = t * 1664525u + 1013904223u; acc[k][j] = t; }
+    const uint32_t b = t | 1u;
+    const long long c0 = clock64();
     for (int i = 0; i < iters; i++) {
 #pragma unroll
-        for (int k = 0; k < ILP; k++)
-            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[k]) : "r"(a), "r"(b));
+        for (int k = 0; k < K; k++) lane_mad(acc[k], a, b);
     }
-    uint64_t s = 0;
+    const long long c1 = clock64();
+    uint32_t s = 0;
 #pragma unroll
-    for (int k = 0; k < ILP; k++) s ^= acc[k];
-    if (s == 0x1234567ull) sink[0] = s;      // never true in practice: keeps the chains alive
+    for (int k = 0; k < K; k++)
+#pragma unroll
+        for (int j = 0; j < 14; j++) s ^= acc[k][j];
+    if (s == 0x12345u) sink[0] = s;                // never true in practice: keeps the chains alive
+    if (HB_TID == 0) cycles[0] = (unsigned long long)(c1 - c0);
 }
 
 }  // namespace hb

@@ -59,6 +59,7 @@ struct PublicKey {
     void Add(const PublicKey* rhs) { blsPublicKeyAdd(&v, &rhs->v); }
     void Sub(const PublicKey* rhs) { blsPublicKeySub(&v, &rhs->v); }
     bool IsEqual(const PublicKey* rhs) const { return blsPublicKeyIsEqual(&v, &rhs->v) == 1; }
+    std::array<uint8_t, 20> GetAddress() const { std::array<uint8_t, 20> a{}; hbls_get_address(&v, a.data()); return a; }      // internal/utils/utils.go:77
 };
 
 struct Sign {
@@ -310,9 +311,18 @@ inline std::string DecodeSigBitmap(const bls::SerializedSignature& sigBytes, con
 namespace quorum {     // == consensus/quorum, uniform (one-node-one-vote) policy + ballot aggregation
 inline int64_t TwoThirdsSignersCount(int64_t participants) { return participants * 2 / 3 + 1; }       // quorum.go:409-411
 inline int64_t CountOneBits(const std::vector<uint8_t>& bm) { int64_t c = 0; for (uint8_t b : bm) c += __builtin_popcount(b); return c; }
+// Set bits among the committee's n slots only.  The reference counts mask.Bitmap AFTER SetMask, which never sets a bit i >= n
+// (crypto/bls/mask.go:121-133), so the padding bits of the last byte of a RAW header bitmap must not count: with n = 250 an
+// attacker could otherwise add 6 phantom votes and pass the 167 threshold with 161 real signers.
+inline int64_t CountSlotBits(const std::vector<uint8_t>& bm, size_t n) {
+    int64_t c = 0;
+    for (size_t i = 0; i < (n >> 3) && i < bm.size(); i++) c += __builtin_popcount(bm[i]);
+    if ((n & 7) && (n >> 3) < bm.size()) c += __builtin_popcount(bm[n >> 3] & ((1u << (n & 7)) - 1u));
+    return c;
+}
 inline bool IsQuorumAchievedByMask(const bls::Mask* mask, int64_t participants) {                      // one-node-one-vote.go:57-72
     if (!mask) return false;
-    return CountOneBits(mask->Bitmap) >= TwoThirdsSignersCount(participants);
+    return CountOneBits(mask->Bitmap) >= TwoThirdsSignersCount(participants);                          // Mask.Bitmap never holds padding bits
 }
 struct Ballot { std::vector<bls::SerializedPublicKey> SignerPubKeys; std::vector<uint8_t> Signature; };
 // quorum.go:164-196: skip ballots sharing a signer with an already collected ballot, re-decode each stored signature, fold Add.
@@ -335,20 +345,29 @@ inline std::shared_ptr<bls_core::Sign> AggregateVotes(const std::vector<Ballot>&
 }  // namespace quorum
 
 namespace chain {
+inline const char* headerStatusError(uint8_t st) {          // the Go error strings of engine.go:619-642 / sig.go:37-49
+    switch (st) {
+    case HBLS_HDR_OK: return "";
+    case HBLS_HDR_BAD_ENCODING: return "deserialize signature and bitmap: unable to deserialize multi-signature from payload";
+    case HBLS_HDR_NO_QUORUM: return "not enough signature collected";
+    default: return "Unable to verify aggregated signature for block";
+    }
+}
 // engine.go:619-642 over a device-resident committee, with the 100-entry verified-signature cache of engine.go:606-617
 class SignatureVerifier {
     std::list<std::string> order_; std::set<std::string> seen_; size_t cap_;
 public:
     explicit SignatureVerifier(size_t cap = 100) : cap_(cap) {}
-    // "" on success or the Go error string
+    // "" on success or the Go error string.  Order of checks as in engine.go:630-640: DecodeSigBitmap (signature deserialise,
+    // SetMask length) -> IsQuorumAchievedByMask over the committee's slots -> VerifyHash; one device call (hbls_verify_headers, n = 1).
     std::string verifySignature(const bls::Committee& ec, const bls::SerializedSignature& commitSig, const std::vector<uint8_t>& commitBitmap,
                                 const std::vector<uint8_t>& commitPayload) {
         if (commitBitmap.size() != ec.BitmapLen()) return "deserialize signature and bitmap: mask.SetMask failed";
-        if (quorum::CountOneBits(commitBitmap) < quorum::TwoThirdsSignersCount((int64_t)ec.Size())) return "not enough signature collected";
-        int rc = bls::FastAggregateVerify(ec, commitBitmap, commitSig, commitPayload);
-        if (rc < 0) return "deserialize signature and bitmap";
-        if (rc != 1) return "Unable to verify aggregated signature for block";
-        return "";
+        uint8_t st = 0;
+        int rc = hbls_verify_headers(ec.handle(), 1, commitSig.data(), commitBitmap.data(), commitBitmap.size(), commitPayload.data(), commitPayload.size(),
+                                     (size_t)quorum::TwoThirdsSignersCount((int64_t)ec.Size()), &st);
+        if (rc != 0) return "deserialize signature and bitmap";
+        return headerStatusError(st);
     }
     std::string verifySignatureCached(const bls::Committee& ec, const std::array<uint8_t, 32>& blockHash, const bls::SerializedSignature& sig,
                                       const std::vector<uint8_t>& bitmap, const std::vector<uint8_t>& payload) {
@@ -363,16 +382,17 @@ public:
 };
 
 // ---- range form: engine.go:81-97 VerifyHeaders / stagedstreamsync/sig_verify.go:23-58 verify one header
-// signature per cgo round trip; here the block range of ONE committee epoch goes to the device in one call.
+// signature per cgo round trip; here the block range of ONE committee epoch goes to the device in one call (hbls_verify_headers).
 struct HeaderSig {
     bls::SerializedSignature commitSig; std::vector<uint8_t> commitBitmap; std::vector<uint8_t> commitPayload;   // payload = ConstructCommitPayload(...)
 };
-struct HeaderBatch {          // what hbls_aggregate_verify_batch consumes: same-length payloads, quorum-gated rounds only
+struct HeaderBatch {          // what hbls_verify_headers consumes: same-length payloads, well-formed bitmaps
     size_t msgLen = 0; std::vector<size_t> index; std::vector<uint8_t> bitmaps, sigs, msgs;
     size_t rounds() const { return index.size(); }
 };
-// Pure host step (no device): applies the checks of engine.go:619-634 that precede the pairing (bitmap length, quorum by
-// popcount) and packs the survivors by payload length (40 B pre-staking / 48 B staking eras never mix inside one call).
+// Pure host step (no device): rejects malformed records (bitmap length: sig.go:43 mask.SetMask error; empty payload) and packs the
+// rest by payload length (40 B pre-staking / 48 B staking eras never mix inside one call).  Quorum and signature checks happen in
+// hbls_verify_headers, in the reference's order.
 inline std::vector<HeaderBatch> AssembleHeaderBatches(size_t committeeSize, const std::vector<HeaderSig>& headers, std::vector<std::string>& errs) {
     const size_t blen = (committeeSize + 7) >> 3;
     errs.assign(headers.size(), "");
@@ -380,8 +400,7 @@ inline std::vector<HeaderBatch> AssembleHeaderBatches(size_t committeeSize, cons
     for (size_t i = 0; i < headers.size(); i++) {
         const HeaderSig& h = headers[i];
         if (h.commitBitmap.size() != blen) { errs[i] = "deserialize signature and bitmap: mask.SetMask failed"; continue; }
-        if (quorum::CountOneBits(h.commitBitmap) < quorum::TwoThirdsSignersCount((int64_t)committeeSize)) { errs[i] = "not enough signature collected"; continue; }
-        if (h.commitPayload.empty() || h.commitPayload.size() > 64) { errs[i] = "invalid commit payload"; continue; }
+        if (h.commitPayload.empty()) { errs[i] = "invalid commit payload"; continue; }
         HeaderBatch* b = nullptr;
         for (auto& c : out) if (c.msgLen == h.commitPayload.size()) { b = &c; break; }
         if (!b) { out.emplace_back(); b = &out.back(); b->msgLen = h.commitPayload.size(); }
@@ -395,12 +414,11 @@ inline std::vector<HeaderBatch> AssembleHeaderBatches(size_t committeeSize, cons
 // errs[i] == "" iff header i carries a valid quorum signature of the committee (same strings as verifySignature above)
 inline std::vector<std::string> VerifyHeaderSignatures(const bls::Committee& ec, const std::vector<HeaderSig>& headers) {
     std::vector<std::string> errs;
+    const size_t quorum = (size_t)quorum::TwoThirdsSignersCount((int64_t)ec.Size());
     for (auto& b : AssembleHeaderBatches(ec.Size(), headers, errs)) {
-        std::vector<uint8_t> res(b.rounds(), 0);
-        int rc = hbls_aggregate_verify_batch(ec.handle(), b.rounds(), b.bitmaps.data(), ec.BitmapLen(), b.sigs.data(), b.msgs.data(), b.msgLen, res.data());
-        for (size_t k = 0; k < b.rounds(); k++)
-            if (rc != 0) errs[b.index[k]] = "deserialize signature and bitmap";
-            else if (!res[k]) errs[b.index[k]] = "Unable to verify aggregated signature for block";
+        std::vector<uint8_t> st(b.rounds(), 0);
+        int rc = hbls_verify_headers(ec.handle(), b.rounds(), b.sigs.data(), b.bitmaps.data(), ec.BitmapLen(), b.msgs.data(), b.msgLen, quorum, st.data());
+        for (size_t k = 0; k < b.rounds(); k++) errs[b.index[k]] = rc != 0 ? "deserialize signature and bitmap" : headerStatusError(st[k]);
     }
     return errs;
 }

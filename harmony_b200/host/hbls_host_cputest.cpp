@@ -23,6 +23,9 @@ int main() {
     CHECK(!bls::SeparateSigAndMask(std::vector<uint8_t>(10), a, m));
     CHECK(quorum::TwoThirdsSignersCount(250) == 167 && quorum::TwoThirdsSignersCount(4) == 3 && quorum::TwoThirdsSignersCount(1000) == 667);
     CHECK(quorum::CountOneBits({0xff, 0x01, 0x80}) == 10);
+    // only the committee's slots count: 250 slots = 31 full bytes + 2 bits; the 6 padding bits of byte 31 are not votes
+    { std::vector<uint8_t> bm(32, 0); bm[31] = 0xff; CHECK(quorum::CountSlotBits(bm, 250) == 2 && quorum::CountSlotBits(bm, 256) == 8 && quorum::CountOneBits(bm) == 8);
+      bm.assign(32, 0xff); CHECK(quorum::CountSlotBits(bm, 250) == 250 && quorum::CountSlotBits(bm, 6) == 6); }
     bls::PubKeyCache cache(3); bls_core::PublicKey pk{}; pk.v.d[0] = 1;
     cache.Add("a", pk); pk.v.d[0] = 2; cache.Add("b", pk); pk.v.d[0] = 3; cache.Add("c", pk);
     bls_core::PublicKey out{}; CHECK(cache.Get("a", out) && out.v.d[0] == 1);          // "a" becomes most recent
@@ -30,7 +33,8 @@ int main() {
     CHECK(cache.Len() == 3 && !cache.Get("b", out) && cache.Get("c", out) && cache.Get("d", out) && out.v.d[0] == 4);
     std::vector<uint8_t> o; CHECK(bls::AggregateMasks({1, 2}, {4, 2}, o) && o == std::vector<uint8_t>({5, 2}) && !bls::AggregateMasks({1}, {1, 2}, o));
     bls::SerializedPublicKey z{}; CHECK(bls::IsEmpty(z) && bls::Hex(z).size() == 96);
-    // range form: quorum gate + packing by payload length (engine.go:619-634 checks before any pairing work)
+    // range form: malformed records are rejected on the host, the rest is packed by payload length; quorum and signature checks run
+    // in hbls_verify_headers in the reference's order (engine.go:630-640)
     {
         std::vector<chain::HeaderSig> hs(5);
         for (auto& x : hs) { x.commitBitmap.assign(1, 0x07); x.commitPayload.assign(48, 0x11); x.commitSig.fill(0x22); }   // committee of 4: quorum = 3 bits
@@ -40,9 +44,10 @@ int main() {
         hs[4].commitSig.fill(0x44);
         std::vector<std::string> errs;
         auto batches = chain::AssembleHeaderBatches(4, hs, errs);
-        CHECK(errs[0].empty() && errs[1] == "not enough signature collected" && errs[2] == "deserialize signature and bitmap: mask.SetMask failed" && errs[3].empty() && errs[4].empty());
-        CHECK(batches.size() == 2 && batches[0].msgLen == 48 && batches[0].index == std::vector<size_t>({0, 4}) && batches[1].msgLen == 40 && batches[1].index == std::vector<size_t>({3}));
-        CHECK(batches[0].sigs.size() == 192 && batches[0].sigs[0] == 0x22 && batches[0].sigs[96] == 0x44 && batches[0].msgs.size() == 96 && batches[0].bitmaps.size() == 2);
+        CHECK(errs[0].empty() && errs[1].empty() && errs[2] == "deserialize signature and bitmap: mask.SetMask failed" && errs[3].empty() && errs[4].empty());
+        CHECK(batches.size() == 2 && batches[0].msgLen == 48 && batches[0].index == std::vector<size_t>({0, 1, 4}) && batches[1].msgLen == 40 && batches[1].index == std::vector<size_t>({3}));
+        CHECK(batches[0].sigs.size() == 288 && batches[0].sigs[0] == 0x22 && batches[0].sigs[192] == 0x44 && batches[0].msgs.size() == 144 && batches[0].bitmaps.size() == 3);
+        CHECK(std::string(chain::headerStatusError(HBLS_HDR_NO_QUORUM)) == "not enough signature collected" && std::string(chain::headerStatusError(HBLS_HDR_OK)).empty());
         CHECK(batches[1].msgs.size() == 40 && batches[1].msgs[0] == 0x33);
     }
     // no CPU fallback: without blsInit (no device here) group operations fail instead of computing on the host

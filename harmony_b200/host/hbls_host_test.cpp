@@ -85,6 +85,30 @@ static void test_quorum_votes() {
     CHECK(chain::DecodeSigBitmap(s96, bitmap, pubs, dsig, dmask).empty() && dsig->VerifyHash(dmask->AggregatePublic.get(), hash));
     CHECK(chain::DecodeSigBitmap(s96, {0x3f, 0x00}, pubs, dsig, dmask) == "mask.SetMask failed");
     CHECK(bls::FastAggregateVerify(com, bitmap, s96, hash) == 1 && bls::VerifyAggregateSig(com, {0x1f}, s96, hash) == 0);
+    // padding bits are not votes: 6-key committee (1-byte bitmap, quorum 5).  4 real signers + the two padding bits give a raw
+    // popcount of 6, and the aggregate of the 4 verifies -- the reference counts mask.Bitmap after SetMask (4 < 5) and rejects.
+    {
+        std::vector<bls::PublicKeyWrapper> six(pubs.begin(), pubs.begin() + 6);
+        bls::Committee c6; CHECK(c6.Load(six).empty());
+        bls::SerializedSignature s4; auto b4 = a4->Serialize(); std::copy(b4.begin(), b4.end(), s4.begin());
+        CHECK(bls::FastAggregateVerify(c6, {0xcf}, s4, hash) == 1);                               // the device ignores the padding bits
+        CHECK(eng.verifySignature(c6, s4, {0xcf}, hash) == "not enough signature collected");
+        CHECK(eng.verifySignature(c6, s4, {0x0f}, hash) == "not enough signature collected");
+        // header range: valid / below quorum (padding attack) / wrong payload / undecodable signature / valid
+        bls::SerializedSignature s6; auto b6 = a6->Serialize(); std::copy(b6.begin(), b6.end(), s6.begin());
+        std::vector<chain::HeaderSig> hs(5);
+        for (auto& x : hs) { x.commitSig = s6; x.commitBitmap = {0x3f}; x.commitPayload = hash; }
+        hs[1].commitSig = s4; hs[1].commitBitmap = {0xcf};
+        hs[2].commitPayload[3] ^= 1;
+        hs[3].commitSig.fill(0xff);
+        auto errs = chain::VerifyHeaderSignatures(c6, hs);
+        CHECK(errs[0].empty() && errs[4].empty());
+        CHECK(errs[1] == "not enough signature collected");
+        CHECK(errs[2] == "Unable to verify aggregated signature for block");
+        CHECK(errs[3] == "deserialize signature and bitmap: unable to deserialize multi-signature from payload");
+    }
+    // GetAddress (internal/utils/utils.go:77): 20 bytes, deterministic, differs between keys
+    CHECK(pubs[0].Object->GetAddress() == pubs[0].Object->GetAddress() && pubs[0].Object->GetAddress() != pubs[1].Object->GetAddress());
 }
 
 static void test_codecs_multibls_payload() {

@@ -605,6 +605,8 @@ API int ho_sig_add(const u8 a[96], const u8 b[96], u8 out[96]) {
     g2_add(&p, &p, &q); g2_serialize(out, &p); return 0;
 }
 static int verify_core(const g2 *sig, const g1 *pk, const u8 *msg, size_t len) {
+    /* identity public key never verifies (include/hbls.h; unpinned by the reference; current herumi rejects a zero key) */
+    if (g1_is_inf(pk)) return 0;
     g2 h; if (!map_to_g2(&h, msg, len)) return 0;
     g1 ps[2]; g2 qs[2];
     g1_generator(&ps[0]); qs[0] = *sig; g1_neg(&ps[1], pk); qs[1] = h;

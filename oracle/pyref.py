@@ -450,6 +450,7 @@ def sign_hash(sk: int, h: bytes):
 
 def verify_hash(sig, pk, h: bytes) -> bool:
     """Sign.VerifyHash(pk, h): e(B, sig) == e(pk, H(h))."""
+    if pt_is_inf(FP, pk): return False       # identity public key never verifies (include/hbls.h; unpinned: SURVEY A.7)
     Hm = map_to_g2(h)
     if Hm is None: return False
     return pairing_product_is_one([(G1_GEN, sig), (pt_neg(FP, pk), Hm)])

@@ -1,7 +1,7 @@
 // tests/emu/emu_kernels.cpp -- TEST HARNESS ONLY: runs the __global__ kernels of harmony_b200/csrc/kernels.cuh on the host
 // (HB_HOST_EMU: software carry flags; thread-per-item kernels one "thread" after the other, the lane-pair kernels as a
 // 2-thread CTA on two host threads with shuffles / barriers by rendezvous) in the launch order of hbls.cu's
-// aggregate-verify pipeline, so the device LOGIC -- mask complement sums, strided batch groups, fallback flags, result
+// aggregate-verify pipeline, so the device LOGIC -- mask complement sums, strided batch groups, failed-group lists, result
 // codes -- is diffed against the oracle on the GPU-less build box.  Never linked into libhbls.so; the product has no CPU path.
 #define HB_HOST_EMU 1
 #include <cstring>
@@ -16,8 +16,8 @@ static thread_local hb_dim3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDi
 #define __launch_bounds__(...)
 #include "../../harmony_b200/csrc/pairing.cuh"
 static inline void __syncthreads() { if (blockDim.x == 2) hb::hb_emu_exchange(0); }       // 2-thread CTA: rendezvous; 1-thread: nothing
-static inline int atomicOr(int* p, int v) { int o = *p; *p |= v; return o; }
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p += v; return o; }
+static inline long long clock64() { return 0; }
 template <class T> static inline T __shfl_down_sync(unsigned, T v, int) { return v; }       // warp-cooperative kernels are not run here
 #include "../../harmony_b200/csrc/kernels.cuh"
 using namespace hb;
@@ -42,7 +42,7 @@ template <class F> static void run_pair(F f) {                 // one CTA of two
 // mode 1: batched groups + exact fallback, mode 0: exact only.  Returns 0, or -3 if a committee key does not decode.
 template <int G> static int aggregate_verify_batch(int mode, uint32_t n, const uint8_t* pks48, size_t B, const uint8_t* bitmaps, size_t blen,
                                           const uint8_t* sigs96, const uint8_t* msgs, uint32_t msg_len, uint64_t s0, uint64_t s1,
-                                          uint8_t* results, int* any_fail_out, uint8_t* group_ok_out) {
+                                          uint8_t* results, int* any_fail_out, uint8_t* group_ok_out, int* groups_failed_out) {
     std::vector<g1a> table(n), pkneg(B), pk_scaled(B); std::vector<uint8_t> okk(n), ok_sig(B), ok_hm(B), bad(B), group_ok(B / G + 1);
     std::vector<g1> apk(B); std::vector<g2a> sig(B), hm(B), Sg(B / G + 1); std::vector<g2> S(B);
     run_seq(1, n, [&] { k_g1_decode(n, pks48, table.data(), okk.data(), 1, 0); });
@@ -62,19 +62,18 @@ template <int G> static int aggregate_verify_batch(int mode, uint32_t n, const u
     };
     if (mode == 1 && B >= (size_t)G) {
         const size_t ng = B / G, nr = ng * G, tail = B - nr;
-        run_seq(2, 2, [&] { k_rlc_scale(nr, ng, apk.data(), sig.data(), hm.data(), ok_sig.data(), ok_hm.data(), s0, s1, pk_scaled.data(), S.data(), bad.data()); });
+        rlc_coeffs co;                                          // stands in for the host's ChaCha20 draw (hbls.cu rlc_draw)
+        for (int k = 0; k < HB_RLC_GMAX; k++) { uint64_t x = s0 + 0x9e3779b97f4a7c15ull * (uint64_t)(k + 1); x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x ^= s1; co.c[k] = x; }
+        run_seq(2, 2, [&] { k_rlc_scale(nr, ng, apk.data(), sig.data(), hm.data(), ok_sig.data(), ok_hm.data(), (const uint8_t*)nullptr, co, pk_scaled.data(), S.data(), bad.data()); });
         run_seq(1, 2, [&] { k_rlc_group_sum<G>(ng, S.data(), Sg.data()); });
         run_pair([&] { k_rlc_pairing_split<G>(ng, pk_scaled.data(), hm.data(), Sg.data(), bad.data(), group_ok.data()); });
-        run_seq(1, (unsigned)nr, [&] { k_rlc_finish(nr, ng, group_ok.data(), results, &any_fail); });
-#if HB_FALLBACK_LIST
-        std::vector<uint32_t> list(B); unsigned count = 0;
-        run_seq(2, (unsigned)((nr + 1) / 2), [&] { k_rlc_collect_failed(nr, ng, group_ok.data(), list.data(), &count); });
-        run_seq(1, 3, [&] { k_g1_normalize_list(&count, list.data(), apk.data(), pkneg.data(), 1); });
-        run_pair([&] { k_pairing_verify_split_list(&count, list.data(), sig.data(), pkneg.data(), hm.data(), ok_sig.data(), ok_hm.data(), (const uint8_t*)nullptr, results); });
-        run_seq(1, 2, [&] { k_pairing_fixup_list(&count, list.data(), sig.data(), pkneg.data(), hm.data(), ok_sig.data(), ok_hm.data(), (const uint8_t*)nullptr, results); });
-#else
-        exact(0, B, &any_fail);
-#endif
+        std::vector<uint32_t> list(B); unsigned counts[2] = {0, 0};
+        run_seq(2, (unsigned)((nr + 1) / 2), [&] { k_rlc_finish(nr, ng, group_ok.data(), results, list.data(), counts); });
+        run_seq(1, 3, [&] { k_g1_normalize_list(&counts[0], list.data(), apk.data(), pkneg.data(), 1); });
+        run_pair([&] { k_pairing_verify_split_list(&counts[0], list.data(), sig.data(), pkneg.data(), hm.data(), ok_sig.data(), ok_hm.data(), (const uint8_t*)nullptr, results); });
+        run_seq(1, 2, [&] { k_pairing_fixup_list(&counts[0], list.data(), sig.data(), pkneg.data(), hm.data(), ok_sig.data(), ok_hm.data(), (const uint8_t*)nullptr, results); });
+        any_fail = counts[0] != 0;
+        if (groups_failed_out) *groups_failed_out = (int)counts[1];
         if (tail) exact(nr, tail, nullptr);
         if (group_ok_out) std::memcpy(group_ok_out, group_ok.data(), ng);
     } else {
@@ -85,7 +84,31 @@ template <int G> static int aggregate_verify_batch(int mode, uint32_t n, const u
 }
 extern "C" int emu_aggregate_verify_batch(int mode, uint32_t n, const uint8_t* pks48, size_t B, const uint8_t* bitmaps, size_t blen,
                                           const uint8_t* sigs96, const uint8_t* msgs, uint32_t msg_len, uint64_t s0, uint64_t s1,
-                                          uint8_t* results, int* any_fail_out, uint8_t* group_ok_out, int G) {
-    return G == 8 ? aggregate_verify_batch<8>(mode, n, pks48, B, bitmaps, blen, sigs96, msgs, msg_len, s0, s1, results, any_fail_out, group_ok_out)
-                  : aggregate_verify_batch<4>(mode, n, pks48, B, bitmaps, blen, sigs96, msgs, msg_len, s0, s1, results, any_fail_out, group_ok_out);
+                                          uint8_t* results, int* any_fail_out, uint8_t* group_ok_out, int G, int* groups_failed_out) {
+    return G == 8 ? aggregate_verify_batch<8>(mode, n, pks48, B, bitmaps, blen, sigs96, msgs, msg_len, s0, s1, results, any_fail_out, group_ok_out, groups_failed_out)
+                  : aggregate_verify_batch<4>(mode, n, pks48, B, bitmaps, blen, sigs96, msgs, msg_len, s0, s1, results, any_fail_out, group_ok_out, groups_failed_out);
+}
+
+// Executed Fp multiplications / squarings of the thread-per-item stages (mask aggregation from the complement side, signature
+// decode, hash-to-G2, coefficient scaling + group sums), summed over B rounds: out[2 s] = mul, out[2 s + 1] = sqr for stage s in
+// that order.  bench.py's roofline uses these per-round figures (x300 / x234 MAC32); tests/test_emu_kernels.py pins them.
+extern "C" int emu_stage_counts(uint32_t n, const uint8_t* pks48, size_t B, const uint8_t* bitmaps, size_t blen, const uint8_t* sigs96,
+                                const uint8_t* msgs, uint32_t msg_len, int G, uint64_t* out) {
+    std::vector<g1a> table(n), pk_scaled(B); std::vector<uint8_t> okk(n), ok_sig(B), ok_hm(B), bad(B);
+    std::vector<g1> apk(B); std::vector<g2a> sig(B), hm(B), Sg(B / G + 1); std::vector<g2> S(B);
+    run_seq(1, n, [&] { k_g1_decode(n, pks48, table.data(), okk.data(), 1, 0); });
+    for (uint32_t i = 0; i < n; i++) if (!okk[i]) return -3;
+    g1 total; pt_set_inf(total);
+    for (uint32_t i = 0; i < n; i++) pt_add_mixed(total, total, table[i]);
+    uint64_t m0 = hb_emu_cnt_mul, s0 = hb_emu_cnt_sqr; int st = 0;
+    auto mark = [&] { out[2 * st] = hb_emu_cnt_mul - m0; out[2 * st + 1] = hb_emu_cnt_sqr - s0; m0 = hb_emu_cnt_mul; s0 = hb_emu_cnt_sqr; st++; };
+    run_seq(1, 4, [&] { k_mask_aggregate_serial(B, n, table.data(), &total, bitmaps, blen, apk.data()); }); mark();
+    run_seq(1, 4, [&] { k_g2_decode(B, sigs96, sig.data(), ok_sig.data(), 1); }); mark();
+    run_seq(1, 4, [&] { k_hash_to_g2(B, msgs, msg_len, hm.data(), ok_hm.data()); }); mark();
+    const size_t ng = B / G, nr = ng * G;
+    rlc_coeffs co; for (int k = 0; k < HB_RLC_GMAX; k++) co.c[k] = 0x9e3779b97f4a7c15ull * (uint64_t)(k + 3) ^ 0x5851f42d4c957f2dull;
+    run_seq(1, 4, [&] { k_rlc_scale(nr, ng, apk.data(), sig.data(), hm.data(), ok_sig.data(), ok_hm.data(), (const uint8_t*)nullptr, co, pk_scaled.data(), S.data(), bad.data()); });
+    if (G == 8) run_seq(1, 2, [&] { k_rlc_group_sum<8>(ng, S.data(), Sg.data()); }); else run_seq(1, 2, [&] { k_rlc_group_sum<4>(ng, S.data(), Sg.data()); });
+    mark();
+    return 0;
 }

@@ -9,10 +9,8 @@ from harmony_b200 import workload as wl
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-# "batch_inv" = the experimental HB_BATCH_INV build of the kernels (one shared inversion per 4 items of a persistent thread);
-# "fallback_list" = HB_FALLBACK_LIST (exact re-verification of the rounds of failed groups only, compacted index list).
-# Both are kept correct on the CPU so that a later round only has to time them on the GPU.
-@pytest.fixture(scope="module", params=["default", "batch_inv", "fallback_list"])
+# "batch_inv" = the HB_BATCH_INV build of the kernels (one shared inversion per 4 items of a persistent thread)
+@pytest.fixture(scope="module", params=["default", "batch_inv"])
 def emuk(request):
     variant = request.param
     src = os.path.join(ROOT, "tests", "emu", "emu_kernels.cpp")
@@ -20,12 +18,12 @@ def emuk(request):
     csrc = os.path.join(ROOT, "harmony_b200", "csrc")
     deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
-        flags = {"default": [], "batch_inv": ["-DHB_BATCH_INV=1"], "fallback_list": ["-DHB_FALLBACK_LIST=1"]}[variant]
+        flags = {"default": ["-DHB_BATCH_INV=0"], "batch_inv": ["-DHB_BATCH_INV=1"]}[variant]
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread"] + flags + ["-o", out, src])
     L = ctypes.CDLL(out)
     L.emu_aggregate_verify_batch.argtypes = [ctypes.c_int, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t,
                                              ctypes.c_char_p, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint64,
-                                             ctypes.c_char_p, ctypes.POINTER(ctypes.c_int), ctypes.c_char_p, ctypes.c_int]
+                                             ctypes.c_char_p, ctypes.POINTER(ctypes.c_int), ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
     return L
 
 @pytest.fixture(scope="module")
@@ -51,9 +49,9 @@ def make_batch(oracle, n, B, seed):
     return pks, blen, bitmaps, sigs, msgs
 
 def run(emuk, mode, pks, blen, bitmaps, sigs, msgs, seed=(0x1234, 0x9876), G=4):
-    B = len(sigs); res = ctypes.create_string_buffer(B); gok = ctypes.create_string_buffer(B // 4 + 1); af = ctypes.c_int(-1)
+    B = len(sigs); res = ctypes.create_string_buffer(B); gok = ctypes.create_string_buffer(B // 4 + 1); af = ctypes.c_int(-1); gf = ctypes.c_int(-1)
     rc = emuk.emu_aggregate_verify_batch(mode, len(pks), b"".join(pks), B, b"".join(bitmaps), blen, b"".join(sigs), b"".join(msgs), 48,
-                                         seed[0], seed[1], res, ctypes.byref(af), gok, G)
+                                         seed[0], seed[1], res, ctypes.byref(af), gok, G, ctypes.byref(gf))
     assert rc == 0
     return res.raw[:B], af.value, gok.raw[:B // G]
 
@@ -96,3 +94,26 @@ def test_pipeline_groups_of_eight(emuk, oracle):
     want = expected(oracle, pks, bitmaps, sigs, msgs)
     res, any_fail, gok = run(emuk, 1, pks, blen, bitmaps, sigs, msgs, G=8)
     assert gok == b"\x00\x01" and any_fail == 1 and res == want and want[4] == 0 and sum(want) == 16
+
+def test_stage_counts_pinned(emuk, oracle, request):
+    """bench.py's roofline counts EXECUTED Fp multiplications / squarings per round for every stage; the figures are those of the
+    device kernels themselves, run here on the host over rounds of the benchmark's workload (250 keys, 167/200/250 signers)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py")); bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    batch_inv = "batch_inv" in request.node.name
+    sks = bench.make_committee_sks()
+    pks = [oracle.get_public_key(wl.sk_bytes(k)) for k in sks]
+    B = 24
+    bitmaps, agg_sk, msgs, nsig = bench.make_rounds(sks, B, seed=2024)
+    sigs = b"".join(oracle.sign_hash(agg_sk[32 * j:32 * j + 32], msgs[48 * j:48 * j + 48]) for j in range(B))
+    emuk.emu_stage_counts.argtypes = [ctypes.c_uint32, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_char_p,
+                                      ctypes.c_uint32, ctypes.c_int, ctypes.POINTER(ctypes.c_uint64)]
+    t = bench.EXEC_FP_OPS[batch_inv]
+    for G in (8, 4):
+        out = (ctypes.c_uint64 * 8)()
+        assert emuk.emu_stage_counts(250, b"".join(pks), B, bitmaps, 32, sigs, msgs, 48, G, out) == 0
+        got = [(out[2 * i] / B, out[2 * i + 1] / B) for i in range(4)]
+        want = [t["mask"], t["decode"], t["hash"], (t[G]["scale"][0] / G, t[G]["scale"][1] / G)]
+        for (gm, gs), (wm, ws) in zip(got, want):
+            assert abs(gm - wm) <= 0.02 * wm and abs(gs - ws) <= 0.02 * ws, (G, got, want)

@@ -130,9 +130,9 @@ def test_emu_rlc_stage_counts(emu, oracle):
         msgs = [wl.commit_payload("cnt", i) for i in range(G)]; sigs = [oracle.sign_hash(s, m) for s, m in zip(sks, msgs)]
         out = (ctypes.c_uint64 * 4)()
         assert emu.emu_rlc_stage_counts(G, b"".join(pks), b"".join(sigs), b"".join(msgs), 48, out) == 1
-        assert (out[2], out[3]) == bench.RLC_EXEC_FP_OPS[G]["pairing"]
-        sm, ss = bench.RLC_EXEC_FP_OPS[G]["scale"]                # depends on the coefficients' bit pattern: within 5 %
-        assert abs(out[0] - sm) <= 0.05 * sm and abs(out[1] - ss) <= 0.05 * ss
+        assert (out[2], out[3]) == bench.EXEC_FP_OPS[False][G]["pairing"] == bench.EXEC_FP_OPS[True][G]["pairing"]
+        # (the coefficient-scaling stage depends on the operands' form and the coefficients' bit pattern: pinned on the benchmark's
+        #  own workload by tests/test_emu_kernels.py::test_stage_counts_pinned)
     assert bench.rlc_group_size(303104, 148) == 8 and bench.rlc_group_size(151552, 148) == 4
 
 

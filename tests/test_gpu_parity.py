@@ -410,3 +410,267 @@ def test_batch_mode_rlc_equals_exact(gbls):
             assert [j for j in range(B) if out[1][j] == 0] == bad
     finally:
         gbls.SetBatchMode(1)
+
+# ---------------------------------------------------------------------------------------------------------------- round 2
+def _bench_committee(gbls):
+    import bench
+    sks = bench.make_committee_sks()
+    pks_blob = gbls.GetPublicKeyBatch(b"".join(wl.sk_bytes(k) for k in sks))
+    pks = [pks_blob[48 * i:48 * i + 48] for i in range(len(sks))]
+    return sks, pks, gbls.Committee(pks)
+
+def test_headline_configuration_rejects_bad_rounds(gbls, oracle):
+    """The benchmark's own configuration -- B = 303 104 rounds = 37 888 strided groups of 8, k_rlc_pairing_split<8> in 512-thread
+    lock-stepped persistent CTAs -- with >= 30 seeded bad rounds of five kinds.  Per-round booleans equal the oracle's on every
+    bad round and on a 2 000-round random sample; hbls_last_batch_info shows that the G = 8 kernel itself rejected exactly the
+    groups that hold a bad round, and that only their rounds went through the exact pass."""
+    import bench
+    n, B = 250, 303104
+    sks, pks, com = _bench_committee(gbls)
+    bitmaps, agg_sk, msgs, nsig = bench.make_rounds(sks, B, seed=2025)
+    sigs, ok = gbls.SignHashBatch(agg_sk, msgs, 48)
+    assert ok == b"\x01" * B
+    rng = random.Random(77)
+    bad = sorted(rng.sample(range(B), 35))
+    bm = bytearray(bitmaps); mm = bytearray(msgs); sg = bytearray(sigs)
+    kinds = {}
+    for t, j in enumerate(bad):
+        kind = ["wrong_msg", "swapped_sig", "flipped_bitmap_bit", "undecodable_sig", "identity_sig", "empty_bitmap", "zero_msg"][t % 7]
+        kinds[j] = kind
+        if kind == "wrong_msg": mm[48 * j + 17] ^= 0x20
+        elif kind == "swapped_sig":
+            o = (j + 1) % B; sg[96 * j:96 * j + 96] = sigs[96 * o:96 * o + 96]
+        elif kind == "flipped_bitmap_bit": bm[32 * j + (t % 31)] ^= 0x04
+        elif kind == "undecodable_sig": sg[96 * j:96 * j + 96] = b"\xff" * 96
+        elif kind == "identity_sig": sg[96 * j:96 * j + 96] = bytes(96)
+        elif kind == "empty_bitmap": bm[32 * j:32 * j + 32] = bytes(32)
+        elif kind == "zero_msg": mm[48 * j:48 * j + 48] = bytes(48)
+    res = com.AggregateVerifyBatch(bytes(bm), bytes(sg), bytes(mm), 48)
+    info = gbls.LastBatchInfo()
+    assert info["mode"] == 1 and info["group_size"] == 8 and info["cta_threads"] == 512 and info["groups"] == B // 8 and info["tail_rounds"] == 0
+    ng = B // 8
+    bad_groups = {j % ng for j in bad}
+    assert info["groups_failed"] == len(bad_groups) and info["rounds_rechecked"] == 8 * len(bad_groups)
+    och = oracle.committee(pks)
+    check = set(bad) | set(rng.sample(range(B), 2000)) | {g + k * ng for g in list(bad_groups)[:8] for k in range(8)}
+    for j in sorted(check):
+        exp = oracle.committee_aggregate_verify(och, bytes(bm[32 * j:32 * j + 32]), bytes(sg[96 * j:96 * j + 96]), bytes(mm[48 * j:48 * j + 48])) == 1
+        assert (res[j] == 1) == exp, (j, kinds.get(j), res[j])
+    assert all(res[j] == 0 for j in bad)
+    assert sum(res) == B - len(bad)
+    # an all-valid batch of the same size: nothing fails, nothing is re-verified
+    res2 = com.AggregateVerifyBatch(bitmaps, sigs, msgs, 48)
+    info2 = gbls.LastBatchInfo()
+    assert res2 == b"\x01" * B and info2["groups_failed"] == 0 and info2["rounds_rechecked"] == 0
+
+def test_rlc_groups_of_eight_forced_small(gbls, oracle):
+    """G = 8 forced at a small batch (hbls_set_param rlc_g / rlc_min): bad, undecodable and identity rounds in several positions
+    of the strided groups, a partial tail; booleans equal the exact mode's and the oracle's."""
+    n = 250
+    sks, pks, com = _bench_committee(gbls)
+    och = oracle.committee(pks)
+    B = 8 * 9 + 5
+    bms = [wl.bitmap_with_k("g8", j, n, [167, 200, 250][j % 3]) for j in range(B)]
+    msgs = [wl.commit_payload("g8", j) for j in range(B)]
+    sigs_blob, ok = gbls.SignHashBatch(b"".join(wl.sk_bytes(wl.round_signer_sum(sks, bm)) for bm in bms), b"".join(msgs), 48)
+    sigs = [bytearray(sigs_blob[96 * j:96 * j + 96]) for j in range(B)]
+    msgs = [bytearray(m) for m in msgs]; bms = [bytearray(b) for b in bms]
+    msgs[0][3] ^= 1                      # group 0, position 0
+    sigs[9 + 4] = bytearray(b"\xff" * 96)  # group 4, position 1: undecodable
+    sigs[7 * 9 + 8] = bytearray(96)      # group 8, position 7: identity signature
+    bms[3 * 9 + 2] = bytearray(32)       # group 2, position 3: empty bitmap -> identity key
+    msgs[B - 1][40] ^= 2                 # tail round
+    old = (gbls.GetParam("rlc_g"), gbls.GetParam("rlc_min"))
+    try:
+        gbls.SetParam("rlc_g", 8); gbls.SetParam("rlc_min", 16)
+        out = {}
+        for mode in (1, 0):
+            gbls.SetBatchMode(mode)
+            out[mode] = com.AggregateVerifyBatch(b"".join(bytes(b) for b in bms), b"".join(bytes(s) for s in sigs), b"".join(bytes(m) for m in msgs), 48)
+            if mode == 1:
+                info = gbls.LastBatchInfo()
+                assert info["mode"] == 1 and info["group_size"] == 8 and info["groups"] == 9 and info["tail_rounds"] == 5
+                assert info["groups_failed"] == 4 and info["rounds_rechecked"] == 32
+        exp = bytes(1 if oracle.committee_aggregate_verify(och, bytes(bms[j]), bytes(sigs[j]), bytes(msgs[j])) == 1 else 0 for j in range(B))
+        assert out[1] == out[0] == exp
+        assert [j for j in range(B) if exp[j] == 0] == [0, 13, 29, 71, B - 1]
+    finally:
+        gbls.SetBatchMode(1); gbls.SetParam("rlc_g", old[0]); gbls.SetParam("rlc_min", old[1])
+
+def test_config4_ten_thousand_triples_one_percent_invalid(gbls, oracle):
+    """BASELINE configs[3] at full size on one GPU: 10 000 independent (pk, msg, sig) triples from 10 000 distinct keys, 1 % invalid
+    (bit-flipped signature byte, wrong message, wrong key, undecodable key) at seeded positions.  Goes through the batched groups
+    (triple form: P_j = -s_j pk_j) with the exact pass over failed groups; 10 000 booleans equal the oracle's on every invalid item,
+    every item that shares a group with one, and a random sample."""
+    k = 10000
+    sks = b"".join(wl.sk_bytes(wl.seeded_sk("c4full", i)) for i in range(k))
+    msgs = b"".join(wl.seeded_bytes("c4full/m", i, 32) for i in range(k))
+    pks = gbls.GetPublicKeyBatch(sks)
+    sigs, ok = gbls.SignHashBatch(sks, msgs, 32)
+    assert ok == b"\x01" * k
+    rng = random.Random(404)
+    bad = sorted(rng.sample(range(k), 100))
+    pk = bytearray(pks); sg = bytearray(sigs); mm = bytearray(msgs)
+    for t, i in enumerate(bad):
+        kind = t % 4
+        if kind == 0: sg[96 * i + 11] ^= 0x01
+        elif kind == 1: mm[32 * i + 5] ^= 0x80
+        elif kind == 2: o = (i + 7) % k; pk[48 * i:48 * i + 48] = pks[48 * o:48 * o + 48]
+        else: pk[48 * i:48 * i + 48] = b"\xff" * 48
+    res = gbls.VerifyBatch(bytes(pk), bytes(sg), bytes(mm), 32)
+    info = gbls.LastBatchInfo()
+    assert info["mode"] == 1 and info["group_size"] == 4 and info["groups"] == k // 4
+    ng = k // 4
+    check = set(bad) | {g % ng + q * ng for g in bad for q in range(4)} | set(rng.sample(range(k), 300))
+    for i in sorted(check):
+        exp = oracle.verify_hash(bytes(sg[96 * i:96 * i + 96]), bytes(pk[48 * i:48 * i + 48]), bytes(mm[32 * i:32 * i + 32]))
+        assert (res[i] == 1) == exp, i
+    assert all(res[i] == 0 for i in bad) and sum(res) == k - len(bad)
+    gbls.SetBatchMode(0)
+    try: assert gbls.VerifyBatch(bytes(pk), bytes(sg), bytes(mm), 32) == res
+    finally: gbls.SetBatchMode(1)
+
+def test_config3_four_committees_one_call(gbls, oracle):
+    """BASELINE configs[2]: 4 shards x 250 validators, 4 distinct messages, ONE device call (hbls_aggregate_verify_items);
+    then with shard 2 corrupted, and a 64-item multi-committee batch through the batched groups."""
+    n = 250
+    coms, ochs, bms, sigs, msgs, skss = [], [], [], [], [], []
+    for sh in range(4):
+        sks = [wl.seeded_sk(f"c3i/{sh}", i) for i in range(n)]
+        blob = gbls.GetPublicKeyBatch(b"".join(wl.sk_bytes(k) for k in sks))
+        pks = [blob[48 * i:48 * i + 48] for i in range(n)]
+        coms.append(gbls.Committee(pks)); ochs.append(oracle.committee(pks)); skss.append(sks)
+        bm = wl.bitmap_with_k(f"c3i/{sh}", 0, n, [167, 200, 250, 180][sh]); bms.append(bm)
+        m = wl.commit_payload(f"c3i/{sh}", 0); msgs.append(m)
+        sigs.append(oracle.sign_hash(wl.sk_bytes(wl.round_signer_sum(sks, bm)), m))
+    assert gbls.AggregateVerifyItems(coms, bms, b"".join(sigs), b"".join(msgs), 48) == b"\x01\x01\x01\x01"
+    m2 = list(msgs); m2[2] = bytes([m2[2][0] ^ 4]) + m2[2][1:]
+    res = gbls.AggregateVerifyItems(coms, bms, b"".join(sigs), b"".join(m2), 48)
+    exp = bytes(1 if oracle.committee_aggregate_verify(ochs[j], bms[j], sigs[j], m2[j]) == 1 else 0 for j in range(4))
+    assert res == exp == b"\x01\x01\x00\x01"
+    # 64 items cycling over the 4 committees, two bad, through the batched groups (rlc_min lowered)
+    K = 64; items = [j % 4 for j in range(K)]
+    ibm = [wl.bitmap_with_k(f"c3i/b{j}", j, n, 167 + j) for j in range(K)]
+    imsg = [wl.commit_payload("c3i/m", j) for j in range(K)]
+    isig = [oracle.sign_hash(wl.sk_bytes(wl.round_signer_sum(skss[items[j]], ibm[j])), imsg[j]) for j in range(K)]
+    isig[5] = isig[6]; imsg[40] = bytes([imsg[40][9] ^ 1]).join([imsg[40][:9], imsg[40][10:]])
+    old = gbls.GetParam("rlc_min")
+    try:
+        gbls.SetParam("rlc_min", 16)
+        res = gbls.AggregateVerifyItems([coms[s] for s in items], ibm, b"".join(isig), b"".join(imsg), 48)
+        assert gbls.LastBatchInfo()["mode"] == 1
+    finally: gbls.SetParam("rlc_min", old)
+    exp = bytes(1 if oracle.committee_aggregate_verify(ochs[items[j]], ibm[j], isig[j], imsg[j]) == 1 else 0 for j in range(K))
+    assert res == exp and [j for j in range(K) if res[j] == 0] == [5, 40]
+
+def test_verify_headers_range(gbls, oracle):
+    """SURVEY 8f.1 (stagedstreamsync/sig_verify.go:23-58, engine.go:619-642): a block range of one committee epoch in one call.
+    Mixed valid / wrong payload / below quorum / quorum reached only through padding bits / undecodable signature; statuses follow
+    the reference's order of checks."""
+    n = 250
+    sks, pks, com = _bench_committee(gbls)
+    och = oracle.committee(pks)
+    N = 40; q = wl.quorum_k(n)
+    bms = [bytearray(wl.bitmap_with_k("hdr", j, n, [167, 200, 250][j % 3])) for j in range(N)]
+    msgs = [bytearray(wl.commit_payload("hdr", j)) for j in range(N)]
+    sig_blob, ok = gbls.SignHashBatch(b"".join(wl.sk_bytes(wl.round_signer_sum(sks, bytes(b))) for b in bms), b"".join(bytes(m) for m in msgs), 48)
+    sigs = [bytearray(sig_blob[96 * j:96 * j + 96]) for j in range(N)]
+    msgs[3][12] ^= 1                                                    # wrong payload
+    bms[7] = bytearray(wl.bitmap_with_k("hdr/low", 7, n, 160))            # 160 < 167 signers, correctly signed
+    sigs[7] = bytearray(oracle.sign_hash(wl.sk_bytes(wl.round_signer_sum(sks, bytes(bms[7]))), bytes(msgs[7])))
+    bms[11] = bytearray(wl.bitmap_with_k("hdr/pad", 11, n, 161))          # 161 real signers + the 6 padding bits of byte 31 = 167 raw bits
+    sigs[11] = bytearray(oracle.sign_hash(wl.sk_bytes(wl.round_signer_sum(sks, bytes(bms[11]))), bytes(msgs[11])))
+    bms[11][31] |= 0xfc
+    sigs[20] = bytearray(b"\xff" * 96)                                   # undecodable
+    sigs[21] = bytearray(b"\xff" * 96); bms[21] = bytearray(wl.bitmap_with_k("hdr/low", 21, n, 10))   # undecodable AND below quorum: decode error first
+    st = com.VerifyHeaders(b"".join(bytes(s) for s in sigs), b"".join(bytes(b) for b in bms), b"".join(bytes(m) for m in msgs), 48, q)
+    exp = []
+    for j in range(N):
+        if not oracle.sig_check(bytes(sigs[j])): exp.append(gbls.HDR_BAD_ENCODING); continue
+        cnt = sum(1 for i in range(n) if bms[j][i >> 3] >> (i & 7) & 1)
+        if cnt < q: exp.append(gbls.HDR_NO_QUORUM); continue
+        exp.append(gbls.HDR_OK if oracle.committee_aggregate_verify(och, bytes(bms[j]), bytes(sigs[j]), bytes(msgs[j])) == 1 else gbls.HDR_BAD_SIG)
+    assert list(st) == exp
+    assert st[3] == gbls.HDR_BAD_SIG and st[7] == gbls.HDR_NO_QUORUM and st[11] == gbls.HDR_NO_QUORUM and st[20] == st[21] == gbls.HDR_BAD_ENCODING
+    assert sum(1 for s in st if s == gbls.HDR_OK) == N - 5
+    # quorum = 0 skips the gate (staked-vote deciders apply their own): the correctly signed low-participation header verifies
+    st0 = com.VerifyHeaders(b"".join(bytes(s) for s in sigs), b"".join(bytes(b) for b in bms), b"".join(bytes(m) for m in msgs), 48, 0)
+    assert st0[7] == gbls.HDR_OK and st0[11] == gbls.HDR_OK and st0[3] == gbls.HDR_BAD_SIG
+
+def test_persistent_device_mask_and_ballot_box(gbls, oracle):
+    """device-resident Mask (delta Add/Sub like mask.go:121-133,137-155) and running vote aggregate
+    (quorum.go:164-196 with each vote decoded once).  Bytes equal the oracle's from-scratch results."""
+    n = 250
+    sks, pks, com = _bench_committee(gbls)
+    och = oracle.committee(pks)
+    m = gbls.DeviceMask(com)
+    assert m.AggregatePublicBytes() == bytes(48) and m.CountEnabled() == 0
+    with pytest.raises(ValueError): m.SetMask(b"\x01")
+    with pytest.raises(IndexError): m.SetBit(250, True)
+    b1 = wl.bitmap_with_k("dm", 1, n, 200); b2 = wl.bitmap_with_k("dm", 2, n, 170)
+    m.SetMask(b1); assert m.AggregatePublicBytes() == oracle.committee_mask_aggregate(och, b1) and m.CountEnabled() == 200
+    m.SetMask(b2); assert m.AggregatePublicBytes() == oracle.committee_mask_aggregate(och, b2) and m.Mask() == b2     # mixed Add / Sub delta
+    extra = next(i for i in range(n) if not b2[i >> 3] >> (i & 7) & 1)
+    m.SetBit(extra, True); b3 = bytearray(b2); b3[extra >> 3] |= 1 << (extra & 7)
+    assert m.AggregatePublicBytes() == oracle.committee_mask_aggregate(och, bytes(b3)) and m.CountEnabled() == 171
+    m.SetBit(extra, True); assert m.CountEnabled() == 171                   # idempotent: no second Add
+    m.SetBit(extra, False); assert m.AggregatePublicBytes() == oracle.committee_mask_aggregate(och, b2)
+    pad = bytearray(b2); pad[31] |= 0xfc; m.SetMask(bytes(pad))               # padding bits are ignored (mask.go:121 ranges over Publics)
+    assert m.Mask() == b2 and m.CountEnabled() == 170
+    msg = wl.commit_payload("dm", 9)
+    sig = oracle.sign_hash(wl.sk_bytes(wl.round_signer_sum(sks, b2)), msg)
+    assert m.VerifyHash(sig, msg) and not m.VerifyHash(sig, bytes([msg[0] ^ 1]) + msg[1:]) and not m.VerifyHash(b"\xff" * 96, msg)
+    m.Clear(); assert m.AggregatePublicBytes() == bytes(48) and not m.VerifyHash(bytes(96), msg)      # identity key never verifies
+    # ballot box
+    box = gbls.BallotBox(com)
+    vmsg = wl.commit_payload("box", 0)
+    vs, _ = gbls.SignHashBatch(b"".join(wl.sk_bytes(k) for k in sks[:12]), vmsg * 12, 48)
+    one = lambda i: bytes(bytearray((1 << (i & 7)) if b == i >> 3 else 0 for b in range(32)))
+    for i in range(10): assert box.AddVote(one(i), vs[96 * i:96 * i + 96]) is True
+    assert box.AddVote(one(3), vs[96 * 3:96 * 4]) is False                    # signer 3 already collected
+    multi = bytearray(32); multi[1] |= 0x0c                                   # keys 10 and 11 in one multi-key vote
+    assert box.AddVote(bytes(multi), oracle.aggregate_sigs([vs[96 * 10:96 * 11], vs[96 * 11:96 * 12]])) is True
+    with pytest.raises(ValueError): box.AddVote(one(20), b"\xff" * 96)
+    agg, bm = box.Aggregate()
+    assert agg == oracle.aggregate_sigs([vs[96 * i:96 * i + 96] for i in range(12)]) and bm == bytes([0xff, 0x0f] + [0] * 30)
+    assert com.AggregateVerify(bm, agg, vmsg)
+
+def test_get_address_and_identity_key(gbls, oracle):
+    import hashlib
+    sk = gbls.SecretKey(); sk.Deserialize(wl.sk_bytes(wl.seeded_sk("addr", 0)))
+    pk = sk.GetPublicKey()
+    assert pk.GetAddress() == hashlib.sha256(pk.Serialize()).digest()[:20]
+    # identity operands (include/hbls.h): zero key + zero signature is NOT a valid signature of anything
+    z_pk, z_sig = gbls.PublicKey(), gbls.Sign()
+    assert not z_sig.VerifyHash(z_pk, b"\x01" * 32) and not oracle.verify_hash(bytes(96), bytes(48), b"\x01" * 32)
+    assert gbls.VerifyBatch(bytes(48), bytes(96), b"\x01" * 32, 32) == b"\x00"
+    assert gbls.LastError()[0] == 0
+
+def test_device_entry_on_two_streams(gbls):
+    """hbls_aggregate_verify_batch_device is asynchronous on the caller's stream; scratch is per stream, so two pipelines in flight
+    on different streams do not clobber each other's intermediates (one batch all valid, the other with rejected rounds)."""
+    import torch
+    n = 250
+    sks, pks, com = _bench_committee(gbls)
+    B = 2048
+    L = gbls.lib()
+    def mk(tag, bad):
+        bms = [wl.bitmap_with_k(tag, j % 8, n, [167, 200, 250][j % 3]) for j in range(8)]
+        agg = [wl.sk_bytes(wl.round_signer_sum(sks, bm)) for bm in bms]
+        msgs = [wl.commit_payload(tag, j) for j in range(B)]
+        sigs, ok = gbls.SignHashBatch(b"".join(agg[j % 8] for j in range(B)), b"".join(msgs), 48)
+        msgs = [bytes([m[8] ^ 1]).join([m[:8], m[9:]]) if j in bad else m for j, m in enumerate(msgs)]
+        dev = lambda b: torch.frombuffer(bytearray(b), dtype=torch.uint8).cuda()
+        return dev(b"".join(bms[j % 8] for j in range(B))), dev(sigs), dev(b"".join(msgs)), torch.full((B,), 7, dtype=torch.uint8, device="cuda")
+    bad = {5, 900, 2047}
+    A, Bt = mk("s0", set()), mk("s1", bad)
+    s0, s1 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    for _ in range(3):
+        for (bm, sg, ms, rs), st in ((A, s0), (Bt, s1)):
+            rc = L.hbls_aggregate_verify_batch_device(com.h, B, bm.data_ptr(), 32, sg.data_ptr(), ms.data_ptr(), 48, rs.data_ptr(), st.cuda_stream)
+            assert rc == 0
+    torch.cuda.synchronize()
+    assert A[3].cpu().numpy().tobytes() == b"\x01" * B
+    r = Bt[3].cpu().numpy().tobytes()
+    assert {j for j in range(B) if r[j] == 0} == bad
