@@ -36,7 +36,7 @@ struct Ctx {
     bool stage_timing = false; Scratch* stage_sc = nullptr;
     int batch_mode = 1;                                     // 1: random-linear-combination groups + exact pass over failed groups, 0: exact per round
     // tuning (hbls_set_param)
-    long long rlc_min = 1024, rlc_g = 0, tpsm = 384, tpsm_split = 512, tpsm_light = 1024;
+    long long rlc_min = 16384, rlc_g = 0, tpsm = 384, tpsm_split = 512, tpsm_light = 1024, coop_max = 16383;
     // coefficient stream: ChaCha20 keyed from /dev/urandom, block counter = call number
     uint32_t chacha_key[8] = {}; uint64_t rlc_calls = 0;
     // last batch
@@ -196,12 +196,15 @@ void launch_verify_tail(size_t B, const VerifyBufs& v, Scratch* sc, const uint8_
         // small ones 64-thread CTAs spread over the SMs.
         STAGE_EV(5, sc, s);
         const bool full = 2 * B >= (size_t)g.sm_count * HB_TPB_SPLIT;
-        if (full)
+        const bool coop = (long long)B <= g.coop_max;        // latency form: one warp per round (vm.cuh), 9 resident rounds per SM
+        if (coop)
+            LAUNCH(k_pairing_coop, (unsigned)(B < (size_t)g.sm_count * 9 ? B : (size_t)g.sm_count * 9), 32, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
+        else if (full)
             LAUNCH(k_pairing_verify_split, split_blocks(2 * B), HB_TPB_SPLIT, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results, (const int*)nullptr);
         else
             LAUNCH(k_pairing_verify_split, blocks_for(2 * B, 64), 64, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results, (const int*)nullptr);
         LAUNCH(k_pairing_fixup, heavy_blocks(B), TPB, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results, (const int*)nullptr);
-        bi.cta_threads = full ? HB_TPB_SPLIT : 64;
+        bi.cta_threads = coop ? 32 : (full ? HB_TPB_SPLIT : 64);
     }
     STAGE_EV(6, sc, s);
     cudaMemcpyAsync(sc->h_counts, v.counts, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, s);
@@ -383,7 +386,7 @@ int hbls_init_device(int device) {
     CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     { FILE* f = fopen("/dev/urandom", "rb"); if (!f || fread(g.chacha_key, 1, 32, f) != 32) { if (f) fclose(f); fprintf(stderr, "[hbls] cannot read /dev/urandom\n"); return HBLS_ERR_CUDA; } fclose(f); }
     auto envll = [](const char* name, long long dflt) { const char* e = getenv(name); return e ? atoll(e) : dflt; };
-    g.rlc_min = envll("HBLS_RLC_MIN", 1024); g.rlc_g = envll("HBLS_RLC_G", 0);
+    g.rlc_min = envll("HBLS_RLC_MIN", 16384); g.rlc_g = envll("HBLS_RLC_G", 0); g.coop_max = envll("HBLS_COOP_MAX", 16383);
     g.tpsm = envll("HBLS_TPSM", 384); g.tpsm_split = envll("HBLS_TPSM_SPLIT", 512); g.tpsm_light = envll("HBLS_TPSM_LIGHT", 1024);
     // the heavy kernels keep their Fp12 temporaries in per-thread local memory: give L1 the whole 228 KB
     cudaFuncSetAttribute(k_rlc_pairing_split<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
@@ -415,6 +418,7 @@ static long long* param_slot(const char* name) {
     if (!strcmp(name, "tpsm")) return &g.tpsm;
     if (!strcmp(name, "tpsm_split")) return &g.tpsm_split;
     if (!strcmp(name, "tpsm_light")) return &g.tpsm_light;
+    if (!strcmp(name, "coop_max")) return &g.coop_max;
     return nullptr;
 }
 int hbls_set_param(const char* name, long long value) {
@@ -535,7 +539,8 @@ static int verify_hash_locked(const blsSignature* sig, const blsPublicKey* pub, 
         LAUNCH(k_g2_normalize, 1, 32, g.stream, (size_t)1, dsig, v.sig);
     }
     LAUNCH(k_hash_to_g2, 1, 32, g.stream, (size_t)1, dmsg, (uint32_t)size, v.hm, v.ok_hm);
-    LAUNCH(k_pairing_verify_split, 1, 64, g.stream, (size_t)1, v.sig, v.pkneg, v.hm, (const uint8_t*)v.ok_hm, ok_sig, (const uint8_t*)nullptr, dres, (const int*)nullptr);
+    if (g.coop_max >= 1) LAUNCH(k_pairing_coop, 1, 32, g.stream, (size_t)1, v.sig, v.pkneg, v.hm, (const uint8_t*)v.ok_hm, ok_sig, (const uint8_t*)nullptr, dres);
+    else LAUNCH(k_pairing_verify_split, 1, 64, g.stream, (size_t)1, v.sig, v.pkneg, v.hm, (const uint8_t*)v.ok_hm, ok_sig, (const uint8_t*)nullptr, dres, (const int*)nullptr);
     LAUNCH(k_pairing_fixup, 1, 32, g.stream, (size_t)1, v.sig, v.pkneg, v.hm, (const uint8_t*)v.ok_hm, ok_sig, (const uint8_t*)nullptr, dres, (const int*)nullptr);
     uint8_t res = 0;
     CK(cudaMemcpyAsync(&res, dres, 1, cudaMemcpyDeviceToHost, g.stream));

@@ -9,6 +9,7 @@
 // launch geometry therefore only aims at filling 148 SMs x 4 schedulers with independent IMAD chains.
 #pragma once
 #include "pairing.cuh"
+#include "vm.cuh"
 
 namespace hb {
 
@@ -282,6 +283,43 @@ __global__ void k_pairing_fixup(size_t B, const g2a* sig, const g1a* pk_neg, con
     results[j] = (good && verify_irregular(gen, q1, p2, q2)) ? 1 : 0;
   }
 }
+// ---- latency form (vm.cuh): ONE WARP per round runs the 2-pair Miller loop + final exponentiation as step programs over
+// shared-memory slots, 16 lane pairs wide.  Same inputs, flags and result protocol as k_pairing_verify_split (0xFF = a round with an
+// identity operand, decided afterwards by k_pairing_fixup).  Small batches: a single round is ~10x faster than on one lane pair.
+__global__ void __launch_bounds__(32) k_pairing_coop(size_t B, const g2a* sig, const g1a* pk_neg, const g2a* hm,
+                                 const uint8_t* ok_a, const uint8_t* ok_b, const uint8_t* ok_c, uint8_t* results) {
+    __shared__ uint32_t slots[VM_SMEM_WORDS];
+    const int lane = threadIdx.x & 31;
+    vm_load_consts(slots);
+    for (size_t j = blockIdx.x; j < B; j += gridDim.x) {
+        const bool good = (!ok_a || ok_a[j]) && (!ok_b || ok_b[j]) && (!ok_c || ok_c[j]);
+        // lanes 0..7 stage one operand each: P1 = generator, Q1 = signature, P2 = -pk, Q2 = H(m)
+        bool zero = true;
+        if (lane < 8) {
+            fp2 v; fp2_zero(v);
+            const g1a pk = pk_neg[j];
+            switch (lane) {
+            case 0: fp_set(v.a, K_G1_X); break;
+            case 1: fp_set(v.a, K_G1_Y); break;
+            case 2: v = sig[j].x; break;
+            case 3: v = sig[j].y; break;
+            case 4: v.a = pk.x; break;
+            case 5: v.a = pk.y; break;
+            case 6: v = hm[j].x; break;
+            default: v = hm[j].y; break;
+            }
+            vm_set_fp2(slots, VM_R_P1X + lane, v);
+            zero = fp_is_zero(v.a) & fp_is_zero(v.b);
+        }
+        const unsigned zmask = __ballot_sync(0xffffffffu, zero);            // bit l: operand l is zero
+        const bool irregular = ((zmask & 0x0c) == 0x0c) | ((zmask & 0x30) == 0x30) | ((zmask & 0xc0) == 0xc0);
+        bool one = false;
+        if (!irregular) one = vm_pairing_check(slots);                        // warp-uniform branch
+        if (lane == 0) results[j] = irregular ? 0xFF : ((good && one) ? 1 : 0);
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------ random-linear-combination batch (R9 / R10 GPU form)
 // prod_j [ e(B, sigma_j) e(-apk_j, H_j) ]^{r_j} == 1 with 64-bit r_j: the G rounds of a group share ONE Miller accumulator
 // (pairs (-r_j apk_j, H_j) plus (B, sum_j r_j sigma_j)) and ONE final exponentiation.  The rounds of a group that fails -- or

@@ -116,7 +116,8 @@ int hbls_aggregate_verify_batch(const hbls_committee* c, size_t B, const uint8_t
  *   (prod_j [e(B, sigma_j) e(-apk_j, H_j)]^{r_j} == 1; r_j = a_j + b_j z^2 from a fresh 64-bit draw per group position and call out of
  *   a ChaCha20 stream keyed from /dev/urandom at blsInit).  The rounds of every group that fails or holds an undecodable round are
  *   re-verified exactly (those rounds only), so results are the exact booleans; a bad round survives the batched test with
- *   probability <= 2^-63.  Batches under `rlc_min` rounds (default 1024, hbls_set_param) always use mode 0.
+ *   probability <= 2^-63.  Batches under `rlc_min` rounds (default 16 384, hbls_set_param) always use mode 0, and up to `coop_max`
+ *   rounds the exact check runs one WARP per round (latency form, csrc/vm.cuh) instead of one lane pair.
  * mode 0: the exact per-round check only (identical semantics to N calls of hbls_aggregate_verify). */
 void hbls_set_batch_mode(int mode);
 int  hbls_get_batch_mode(void);
@@ -133,8 +134,9 @@ typedef struct {
     uint32_t cta_threads;       /* threads per CTA of the pairing kernel (512 = lock-stepped persistent CTAs) */
 } hbls_batch_info;
 int hbls_last_batch_info(hbls_batch_info* out);
-/* tuning knobs (tests, sweeps): "rlc_min" (rounds), "rlc_g" (0 auto / 4 / 8), "tpsm" (resident threads per SM of the
- * thread-per-item kernels), "tpsm_split" (lane-pair kernels), "tpsm_light".  Defaults come from HBLS_RLC_MIN, HBLS_RLC_G,
+/* tuning knobs (tests, sweeps): "rlc_min" (rounds from which mode 1 batches in groups), "rlc_g" (0 auto / 4 / 8), "coop_max" (exact
+ * checks of at most this many rounds use the warp-per-round latency kernel, 0 = never), "tpsm" (resident threads per SM of the
+ * thread-per-item kernels), "tpsm_split" (lane-pair kernels), "tpsm_light".  Defaults come from HBLS_RLC_MIN, HBLS_RLC_G, HBLS_COOP_MAX,
  * HBLS_TPSM, HBLS_TPSM_SPLIT, HBLS_TPSM_LIGHT at blsInit.  0 ok, HBLS_ERR_ARG for an unknown name / bad value. */
 int hbls_set_param(const char* name, long long value);
 long long hbls_get_param(const char* name);

@@ -99,6 +99,19 @@ extern "C" int emu_legendre_check(const uint32_t* vals, int n) {
     return bad;
 }
 
+// binary-GCD inversion against the Fermat exponentiation on n values (Montgomery limbs in, 12 words each); returns mismatches
+extern "C" int emu_inv_gcd_check(const uint32_t* vals, int n) {
+    int bad = 0;
+    for (int i = 0; i < n; i++) {
+        fp a, x, y; for (int j = 0; j < 12; j++) a.l[j] = vals[12 * i + j];
+        fp_inv_gcd(x, a); fp_inv(y, a);
+        if (!fp_eq(x, y)) bad++;
+        fp one, t; fp_one(one); fp_mul(t, x, a);
+        if (!fp_is_zero(a) && !fp_eq(t, one)) bad++;
+    }
+    return bad;
+}
+
 // ---- lane-pair (fp2h) code on two host threads: the same templates the split kernels instantiate, shuffles by rendezvous.
 // kind 0: exact round  -- miller_loop2<fp2h>(B, sig, -pk, H) + final_exp, compared with the single-thread fp2 form
 // kind 1: batched group of 4 -- miller_loop_multi<fp2h, 5> on the pairs produced by rlc_scale_pair, compared likewise

@@ -117,3 +117,14 @@ def test_stage_counts_pinned(emuk, oracle, request):
         want = [t["mask"], t["decode"], t["hash"], (t[G]["scale"][0] / G, t[G]["scale"][1] / G)]
         for (gm, gs), (wm, ws) in zip(got, want):
             assert abs(gm - wm) <= 0.02 * wm and abs(gs - ws) <= 0.02 * ws, (G, got, want)
+
+def test_vm_pairing_device_decoders(emuk, oracle):
+    """Latency-mode pairing (csrc/vm.cuh): the generated step programs executed with the device's own instruction decoders
+    (vm_mul / vm_sqr / vm_lin over the 25-word slots) give the oracle's verdicts -- valid, wrong message, wrong key."""
+    sk = wl.sk_bytes(wl.seeded_sk("vm", 0)); sk2 = wl.sk_bytes(wl.seeded_sk("vm", 1))
+    pk, pk2 = oracle.get_public_key(sk), oracle.get_public_key(sk2)
+    m = wl.commit_payload("vm", 0); m2 = wl.commit_payload("vm", 1)
+    sig = oracle.sign_hash(sk, m)
+    for (p_, s_, msg) in ((pk, sig, m), (pk, sig, m2), (pk2, sig, m)):
+        assert emuk.emu_vm_pairing(p_, s_, msg, 48) == (1 if oracle.verify_hash(s_, p_, msg) else 0)
+    assert emuk.emu_vm_pairing(pk, sig, m, 48) == 1 and emuk.emu_vm_pairing(pk, sig, m2, 48) == 0

@@ -147,6 +147,17 @@ def test_emu_legendre_jacobi(emu):
     assert emu.emu_legendre_check(arr, len(vals)) == 0
 
 
+def test_emu_inv_gcd(emu):
+    """fp_inv_gcd (binary extended Euclid, used on the latency path) == a^(p-2) on edge values and random ones."""
+    p = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+    rng = random.Random(10)
+    vals = [0, 1, 2, 3, p - 1, p - 2, (p - 1) // 2, (p + 1) // 2, 1 << 380, (1 << 380) - 1, 0xffffffff, 1 << 32] + [rng.randrange(p) for _ in range(300)]
+    arr = (ctypes.c_uint32 * (12 * len(vals)))()
+    for i, v in enumerate(vals):
+        for j in range(12): arr[12 * i + j] = (v >> (32 * j)) & 0xffffffff
+    assert emu.emu_inv_gcd_check(arr, len(vals)) == 0
+
+
 def test_emu_lane_pair_pairing(emu, oracle):
     """The lane-pair (fp2h) Miller loop + final exponentiation -- the code of k_pairing_verify_split / k_rlc_pairing_split --
     run on two host threads (shuffles by rendezvous) must produce the same Fp12 value and verdict as the single-thread

@@ -1,8 +1,9 @@
 // tools/probe_int.cu -- integer-pipe calibration probes for the roofline denominator.
 //
 // Measures, on the whole chip, the issue rate of the instruction forms the field arithmetic is built from:
-//   plain      IMAD.WIDE.U32 Rd, Ra, Rb, Rc            (64-bit accumulate, no carry flags)          -- the r1 probe
-//   carry      IMAD.WIDE.U32(.X) chains = mad.lo.cc / madc.hi.cc exactly as fp.cuh: lane_mad emits them
+//   wide+add64 mad.wide.u32 with a 64-bit addend, no carry flags (ptxas: IMAD.WIDE.U32 Rd, Ra, Rb, RZ + IADD3 / IADD3.X)
+//   carry      IMAD.WIDE.U32(.X) chains = mad.lo.cc / madc.hi.cc exactly as fp.cuh: lane_mad emits them (6 IMAD.WIDE per row)
+//   imad32 / iadd   32-bit IMAD and IADD3 alone (the FMA-heavy and ALU pipes' instruction rates)
 //   mul32x12   the shipped 12 x 32-bit Montgomery product (fp_mul_regs), register resident, dependent products
 //   mul28x14   a carry-free 14 x 28-bit Montgomery product (64-bit column accumulators, plain IMAD.WIDE only)
 // and cross-checks mul28x14 against mul32x12 on the same canonical operands.
@@ -275,10 +276,11 @@ int main(int argc, char** argv) {
     const int sms = prop.multiProcessorCount;
     void* sink; CK(cudaMalloc(&sink, 4096));
     printf("{\"device\": \"%s\", \"sms\": %d, \"clock_khz\": %d", prop.name, sms, prop.clockRate);
-    const char* names[11] = {"plain_ilp8", "carry_k1", "carry_k2", "carry_k4", "plain_rows_k4", "plain_plus_iadd_ilp8", "", "", "", "iadd_only_ilp8", "imad32_ilp8"};
+    // wide_plus_add64: ptxas lowers a plain (carry-free) mad.wide.u32 with a 64-bit addend to IMAD.WIDE(RZ) + IADD3 / IADD3.X
+    const char* names[11] = {"wide_plus_add64_ilp8", "carry_k1", "carry_k2", "carry_k4", "", "wide_plus_add64_plus_iadd_ilp8", "", "", "", "iadd_only_ilp8", "imad32_ilp8"};
     const double mac_per_iter[11] = {8, 6, 12, 24, 24, 8, 0, 0, 0, 8, 8};      // lane_mad = 6 wide MACs (each mad.lo.cc/madc.hi.cc pair is ONE IMAD.WIDE)
     for (int v = 0; v < 11; v++) {
-        if (v >= 6 && v <= 8) continue;
+        if ((v >= 6 && v <= 8) || v == 4) continue;
         if (only >= 0 && only != v) continue;
         for (int tpsm = 256; tpsm <= 1024; tpsm *= 2) {
             L l{sms * (tpsm / 256), 256, 4096, sink, nullptr, v};

@@ -1,0 +1,492 @@
+#!/usr/bin/env python
+"""tools/vmgen.py -- build-time generator of harmony_b200/csrc/vm_programs.cuh: the warp-cooperative ("latency mode") pairing.
+
+One warp = 16 lane pairs verifies ONE round.  The Miller loop and the final exponentiation are straight-line programs over Fp2
+values that live in shared-memory slots; a program is a list of STEPS, and in every step each lane pair executes at most one Fp2
+operation (pair p runs instruction p of the step), so up to 16 independent Fp2 products run side by side:
+    MUL   dst = a * b                     (lane-pair product: 2 wide products + 1 reduction per lane, tower.cuh fp2h)
+    SQR   dst = a * a                     (1 wide product + 1 reduction per lane)
+    LIN   dst = sum_{k<4} M_k * src_k     (M_k = 2x2 small-integer matrices over (re, im): add, sub, conj, xi*, i*, 2x, 3x ...)
+This file holds the formulas (the same tower / Miller-loop / final-exponentiation formulas as tower.cuh and pairing.cuh, written once
+over an abstract Fp2 type), a tracer that turns them into a dependency graph, a list scheduler (<= 16 operations of one class per
+step, linear combinations folded so that at most one LIN level sits between two MUL levels), a slot allocator, the C emitter and
+a reference interpreter (`run_program`) that tests/test_vm_programs.py uses to check every program against the CPU oracle.
+
+Run:  python tools/vmgen.py            (rewrites harmony_b200/csrc/vm_programs.cuh; the generated header is committed)
+"""
+import os, sys
+
+P = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+Z_ABS = 0xd201000000010000
+NPAIR = 16
+MAXT = 4            # terms per LIN instruction
+CMAX = 7            # |matrix entry| limit of a LIN term (4-bit signed field)
+
+# ------------------------------------------------------------------ concrete Fp2 (reference semantics of the VM)
+def f2(a, b=0): return (a % P, b % P)
+def f2_add(x, y): return ((x[0] + y[0]) % P, (x[1] + y[1]) % P)
+def f2_mul(x, y): return ((x[0] * y[0] - x[1] * y[1]) % P, (x[0] * y[1] + x[1] * y[0]) % P)
+def f2_apply(M, x): return ((M[0] * x[0] + M[1] * x[1]) % P, (M[2] * x[0] + M[3] * x[1]) % P)
+def f2_pow(x, e):
+    r = (1, 0)
+    while e:
+        if e & 1: r = f2_mul(r, x)
+        x = f2_mul(x, x); e >>= 1
+    return r
+XI = (1, 1)
+CONSTS = {"ONE": (1, 0), "B3": (12, 12), "INV2": (pow(2, -1, P), 0)}
+for k in range(6):
+    CONSTS[f"FROB1_{k}"] = f2_pow(XI, k * (P - 1) // 6)
+    g2 = f2_pow(XI, k * (P * P - 1) // 6); assert g2[1] == 0
+    CONSTS[f"FROB2_{k}"] = g2
+
+# ------------------------------------------------------------------ tracer
+I2 = (1, 0, 0, 1)
+def m_mul(A, B): return (A[0] * B[0] + A[1] * B[2], A[0] * B[1] + A[1] * B[3], A[2] * B[0] + A[3] * B[2], A[2] * B[1] + A[3] * B[3])
+def m_add(A, B): return tuple(a + b for a, b in zip(A, B))
+M_CONJ, M_XI, M_NEG = (1, 0, 0, -1), (1, -1, 1, 1), (-1, 0, 0, -1)
+
+class Graph:
+    """nodes: ('in', name) | ('const', name) | ('mul', a, b) | ('sqr', a) | ('lin', ((node, M), ...))"""
+    def __init__(self, name):
+        self.name = name; self.nodes = []; self.cse = {}; self.outputs = []; self.inputs = {}
+    def add(self, node):
+        key = node
+        if key in self.cse: return self.cse[key]
+        self.nodes.append(node); self.cse[key] = len(self.nodes) - 1
+        return len(self.nodes) - 1
+    def inp(self, reg):
+        i = self.add(("in", reg)); self.inputs[reg] = i
+        return V(self, {i: I2})
+    def const(self, name): return V(self, {self.add(("const", name)): I2})
+    def out(self, reg, v): self.outputs.append((reg, v.node()))
+
+class V:
+    """symbolic Fp2 value = sum of M_n * node_n"""
+    def __init__(self, g, terms): self.g = g; self.t = {n: M for n, M in terms.items() if M != (0, 0, 0, 0)}
+    def _lin(self, M): return V(self.g, {n: m_mul(M, X) for n, X in self.t.items()})
+    def __add__(self, o):
+        t = dict(self.t)
+        for n, M in o.t.items(): t[n] = m_add(t[n], M) if n in t else M
+        return V(self.g, t)
+    def __neg__(self): return self._lin(M_NEG)
+    def __sub__(self, o): return self + (-o)
+    def scale(self, k): return self._lin((k, 0, 0, k))
+    def dbl(self): return self.scale(2)
+    def conj(self): return self._lin(M_CONJ)
+    def xi(self): return self._lin(M_XI)
+    def node(self):
+        """materialise: a node index holding exactly this value"""
+        g = self.g
+        if len(self.t) == 1:
+            (n, M), = self.t.items()
+            if M == I2: return n
+        items = sorted(self.t.items())
+        if not items: items = [(g.add(("const", "ONE")), (0, 0, 0, 0))]
+        # split so that every LIN instruction has <= MAXT terms with entries within +-CMAX
+        def fits(M): return all(abs(c) <= CMAX for c in M)
+        for n, M in items:
+            if not fits(M): raise ValueError(f"{g.name}: coefficient out of range {M}")
+        while len(items) > MAXT:
+            head, items = items[:MAXT], items[MAXT:]
+            items.insert(0, (g.add(("lin", tuple(head))), I2))
+        return g.add(("lin", tuple(items)))
+    def __mul__(self, o):
+        a, b = self.node(), o.node()
+        if a == b: return V(self.g, {self.g.add(("sqr", a)): I2})
+        if a > b: a, b = b, a
+        return V(self.g, {self.g.add(("mul", a, b)): I2})
+    def sqr(self): return self * self
+
+class C:
+    """concrete twin of V (same interface) used to validate formulas and the interpreter"""
+    def __init__(self, v): self.v = (v[0] % P, v[1] % P)
+    def __add__(self, o): return C(f2_add(self.v, o.v))
+    def __neg__(self): return C((-self.v[0], -self.v[1]))
+    def __sub__(self, o): return self + (-o)
+    def scale(self, k): return C((self.v[0] * k, self.v[1] * k))
+    def dbl(self): return self.scale(2)
+    def conj(self): return C((self.v[0], -self.v[1]))
+    def xi(self): return C(f2_apply(M_XI, self.v))
+    def __mul__(self, o): return C(f2_mul(self.v, o.v))
+    def sqr(self): return self * self
+
+# ------------------------------------------------------------------ formulas over the abstract Fp2 type (V or C).  k(name) = constant
+# Fp6 = (c0, c1, c2) over v^3 = xi; Fp12 = (c0, c1) over w^2 = v; fp12 as a 6-tuple in tower order (c0.c0, c0.c1, c0.c2, c1.c0, c1.c1, c1.c2)
+def fp6_add(x, y): return tuple(a + b for a, b in zip(x, y))
+def fp6_sub(x, y): return tuple(a - b for a, b in zip(x, y))
+def fp6_neg(x): return tuple(-a for a in x)
+def fp6_mul_v(x): return (x[2].xi(), x[0], x[1])
+def fp6_mul(x, y):
+    v0, v1, v2 = x[0] * y[0], x[1] * y[1], x[2] * y[2]
+    t0 = ((x[1] + x[2]) * (y[1] + y[2]) - v1 - v2).xi() + v0
+    t1 = (x[0] + x[1]) * (y[0] + y[1]) - v0 - v1 + v2.xi()
+    t2 = (x[0] + x[2]) * (y[0] + y[2]) - v0 - v2 + v1
+    return (t0, t1, t2)
+def fp6_mul_by_01(x, b0, b1):
+    v0, v1 = x[0] * b0, x[1] * b1
+    t0 = (x[2] * b1).xi() + v0
+    t1 = (x[0] + x[1]) * (b0 + b1) - v0 - v1
+    t2 = x[2] * b0 + v1
+    return (t0, t1, t2)
+def fp6_mul_by_1(x, b1): return ((x[2] * b1).xi(), x[0] * b1, x[1] * b1)
+def fp6_inv_parts(x):
+    """(t0, t1, t2, d): x^-1 = (t0, t1, t2) / d with d in Fp2"""
+    t0 = x[0].sqr() - (x[1] * x[2]).xi()
+    t1 = x[2].sqr().xi() - x[0] * x[1]
+    t2 = x[1].sqr() - x[0] * x[2]
+    d = (x[2] * t1 + x[1] * t2).xi() + x[0] * t0
+    return t0, t1, t2, d
+def fp12_split(f): return f[0:3], f[3:6]
+def fp12_mul(x, y):
+    x0, x1 = fp12_split(x); y0, y1 = fp12_split(y)
+    v0, v1 = fp6_mul(x0, y0), fp6_mul(x1, y1)
+    s = fp6_sub(fp6_sub(fp6_mul(fp6_add(x0, x1), fp6_add(y0, y1)), v0), v1)
+    return fp6_add(v0, fp6_mul_v(v1)) + s
+def fp12_sqr(x):
+    x0, x1 = fp12_split(x)
+    ab = fp6_mul(x0, x1)
+    s = fp6_mul(fp6_add(x0, x1), fp6_add(fp6_mul_v(x1), x0))
+    c0 = fp6_sub(fp6_sub(s, ab), fp6_mul_v(ab))
+    return c0 + fp6_add(ab, ab)
+def fp12_conj(x): return tuple(x[0:3]) + fp6_neg(x[3:6])
+def fp12_mul_by_014(x, o0, o1, o4):
+    x0, x1 = fp12_split(x)
+    aa = fp6_mul_by_01(x0, o0, o1)
+    bb = fp6_mul_by_1(x1, o4)
+    s = fp6_sub(fp6_sub(fp6_mul_by_01(fp6_add(x0, x1), o0, o1 + o4), aa), bb)
+    return fp6_add(aa, fp6_mul_v(bb)) + s
+# coefficient of w^k (k = 2i + j) <-> tower slot index
+SLOT_OF_W = [0, 3, 1, 4, 2, 5]
+def fp12_frob(x, k):
+    r = list(x)
+    for w in range(6):
+        i = SLOT_OF_W[w]; r[i] = x[i].conj() * k(f"FROB1_{w}")
+    return tuple(r)
+def fp12_frob2(x, k):
+    r = list(x)
+    for w in range(6):
+        i = SLOT_OF_W[w]; r[i] = x[i] * k(f"FROB2_{w}")
+    return tuple(r)
+def fp4_sqr(a, b):
+    t0, t1 = a.sqr(), b.sqr()
+    return t1.xi() + t0, (a + b).sqr() - t0 - t1
+def fp12_cyc_sqr(x):
+    z0, z4, z3, z2, z1, z5 = x
+    t0, t1 = fp4_sqr(z0, z1)
+    z0 = (t0 - z0).dbl() + t0; z1 = (t1 + z1).dbl() + t1
+    t0, t1 = fp4_sqr(z2, z3); t2, t3 = fp4_sqr(z4, z5)
+    z4 = (t0 - z4).dbl() + t0; z5 = (t1 + z5).dbl() + t1
+    t0 = t3.xi()
+    z2 = (t0 + z2).dbl() + t0; z3 = (t2 - z3).dbl() + t2
+    return (z0, z4, z3, z2, z1, z5)
+def ml_dbl(T, k):
+    x, y, z = T
+    A = (x * y) * k("INV2")
+    B, Cc = y.sqr(), z.sqr()
+    E = k("B3") * Cc
+    F = E.scale(3)
+    H = (y + z).sqr() - B - Cc
+    l0 = B - E
+    l2 = -(x.sqr().scale(3))
+    l3 = H
+    x3 = (B - F) * A
+    y3 = ((B + F) * k("INV2")).sqr() - E.sqr().scale(3)
+    return (x3, y3, B * H), (l0, l2, l3)
+def ml_add(T, qx, qy):
+    x, y, z = T
+    th = y - qy * z
+    mu = x - qx * z
+    l0 = th * qx - mu * qy
+    Cc, D = th.sqr(), mu.sqr()
+    E = mu * D; F = z * Cc; G = x * D
+    H = E + F - G.dbl()
+    x3 = mu * H
+    y3 = (G - H) * th - E * y
+    return (x3, y3, z * E), (l0, -th, mu)
+def line_at(l, px, py): return l[0], l[1] * px, l[2] * py
+
+# ------------------------------------------------------------------ programs.  Persistent registers (fixed slots, shared by all programs)
+REG_CONST = ["ONE", "B3", "INV2"] + [f"FROB1_{k}" for k in range(6)] + [f"FROB2_{k}" for k in range(6)]
+REG_IN = ["P1X", "P1Y", "Q1X", "Q1Y", "P2X", "P2Y", "Q2X", "Q2Y"]
+def r6(n): return [f"{n}{i}" for i in range(6)]
+REG_STATE = ["T1X", "T1Y", "T1Z", "T2X", "T2Y", "T2Z"] + r6("F") + r6("M") + r6("X") + r6("ACC") + r6("A") + r6("B") + r6("C") + \
+            ["IT0", "IT1", "IT2", "ID", "NORM", "NINV"]
+REGS = REG_CONST + REG_IN + REG_STATE
+SLOT = {r: i for i, r in enumerate(REGS)}
+NSLOTS = 232        # slots per warp (100 B each): registers + temporaries
+
+def build_programs(make_graph):
+    """every program as a function of a fresh graph; returns {name: graph}"""
+    progs = {}
+    def prog(fn):
+        g = make_graph(fn.__name__[2:].upper()); k = g.const
+        fn(g, k); progs[g.name] = g
+        return fn
+    def get6(g, n): return tuple(g.inp(r) for r in r6(n))
+    def put6(g, n, v):
+        for r, x in zip(r6(n), v): g.out(r, x)
+    @prog
+    def p_ml_init(g, k):
+        one = k("ONE")
+        for t, q in (("T1", "Q1"), ("T2", "Q2")):
+            g.out(t + "X", g.inp(q + "X")); g.out(t + "Y", g.inp(q + "Y")); g.out(t + "Z", one)
+        put6(g, "F", (one,) + tuple(one.scale(0) for _ in range(5)))
+    @prog
+    def p_ml_dbl(g, k):
+        f = fp12_sqr(get6(g, "F"))
+        for t, pp in (("T1", "P1"), ("T2", "P2")):
+            T, l = ml_dbl((g.inp(t + "X"), g.inp(t + "Y"), g.inp(t + "Z")), k)
+            f = fp12_mul_by_014(f, *line_at(l, g.inp(pp + "X"), g.inp(pp + "Y")))
+            g.out(t + "X", T[0]); g.out(t + "Y", T[1]); g.out(t + "Z", T[2])
+        put6(g, "F", f)
+    @prog
+    def p_ml_add(g, k):
+        f = get6(g, "F")
+        for t, pp, q in (("T1", "P1", "Q1"), ("T2", "P2", "Q2")):
+            T, l = ml_add((g.inp(t + "X"), g.inp(t + "Y"), g.inp(t + "Z")), g.inp(q + "X"), g.inp(q + "Y"))
+            f = fp12_mul_by_014(f, *line_at(l, g.inp(pp + "X"), g.inp(pp + "Y")))
+            g.out(t + "X", T[0]); g.out(t + "Y", T[1]); g.out(t + "Z", T[2])
+        put6(g, "F", f)
+    # final exponentiation, easy part: m = conj(f) * f^-1, m = frob2(m) * m.  The Fp12 inverse goes down to ONE Fp inversion
+    # (of NORM = N(d), d in Fp2), which a single lane computes between FE_INV_A and FE_INV_B.
+    @prog
+    def p_fe_inv_a(g, k):
+        f = get6(g, "F"); f0, f1 = fp12_split(f)
+        t = fp6_sub(fp6_mul(f0, f0), fp6_mul_v(fp6_mul(f1, f1)))        # f0^2 - v f1^2 in Fp6
+        t0, t1, t2, d = fp6_inv_parts(t)
+        g.out("IT0", t0); g.out("IT1", t1); g.out("IT2", t2); g.out("ID", d)
+        g.out("NORM", d * d.conj())                                      # (re^2 + im^2, 0)
+    @prog
+    def p_fe_inv_b(g, k):
+        f = get6(g, "F"); f0, f1 = fp12_split(f)
+        dinv = g.inp("ID").conj() * g.inp("NINV")                        # d^-1 = conj(d) / N(d)
+        tinv = tuple(g.inp(r) * dinv for r in ("IT0", "IT1", "IT2"))     # (f0^2 - v f1^2)^-1
+        finv = fp6_mul(f0, tinv) + fp6_neg(fp6_mul(f1, tinv))
+        m = fp12_mul(fp12_conj(f), finv)
+        m = fp12_mul(fp12_frob2(m, k), m)
+        put6(g, "M", m); put6(g, "X", m); put6(g, "ACC", m)
+    @prog
+    def p_cycsqr(g, k): put6(g, "ACC", fp12_cyc_sqr(get6(g, "ACC")))
+    @prog
+    def p_mulx(g, k): put6(g, "ACC", fp12_mul(get6(g, "ACC"), get6(g, "X")))
+    # hard part (pairing.cuh final_exp): a = m^(z-1), b = a^(z-1), c = b^(z+p), d = c^(z^2+p^2-1), result d * m^3.
+    # exp_z(x) = conj(x^|z|); the kernel runs the 63-step square-and-multiply loop on (X, ACC) between these glue programs.
+    @prog
+    def p_glue1(g, k):
+        a = fp12_mul(fp12_conj(get6(g, "ACC")), fp12_conj(get6(g, "M")))
+        put6(g, "A", a); put6(g, "X", a); put6(g, "ACC", a)
+    @prog
+    def p_glue2(g, k):
+        b = fp12_mul(fp12_conj(get6(g, "ACC")), fp12_conj(get6(g, "A")))
+        put6(g, "B", b); put6(g, "X", b); put6(g, "ACC", b)
+    @prog
+    def p_glue3(g, k):
+        c = fp12_mul(fp12_conj(get6(g, "ACC")), fp12_frob(get6(g, "B"), k))
+        put6(g, "C", c); put6(g, "X", c); put6(g, "ACC", c)
+    @prog
+    def p_glue4(g, k):
+        t = fp12_conj(get6(g, "ACC"))
+        put6(g, "X", t); put6(g, "ACC", t)
+    @prog
+    def p_glue5(g, k):
+        c = get6(g, "C"); m = get6(g, "M")
+        d = fp12_mul(fp12_mul(fp12_conj(get6(g, "ACC")), fp12_frob2(c, k)), fp12_conj(c))
+        r = fp12_mul(d, fp12_mul(fp12_cyc_sqr(m), m))
+        put6(g, "ACC", r)
+    return progs
+
+# ------------------------------------------------------------------ scheduling + slot allocation
+OP_MUL, OP_SQR, OP_LIN = 1, 2, 3
+class Program:
+    def __init__(self, name): self.name = name; self.steps = []      # step = (cls, [instr...]); instr = (dst, a, b) | (dst, ((slot, M), ...))
+
+def compile_graph(g):
+    nodes = g.nodes
+    # live nodes (reachable from the outputs)
+    need = set(); stack = [n for _, n in g.outputs]
+    def deps(n):
+        nd = nodes[n]
+        if nd[0] == "mul": return [nd[1], nd[2]]
+        if nd[0] == "sqr": return [nd[1]]
+        if nd[0] == "lin": return [s for s, _ in nd[1]]
+        return []
+    while stack:
+        n = stack.pop()
+        if n in need: continue
+        need.add(n); stack += deps(n)
+    ops = [n for n in sorted(need) if nodes[n][0] in ("mul", "sqr", "lin")]
+    users = {n: [] for n in need}
+    for n in ops:
+        for d in deps(n): users[d].append(n)
+    # critical-path priority (MUL/SQR weigh 8, LIN 1)
+    w = {n: (8 if nodes[n][0] != "lin" else 1) for n in ops}
+    prio = {}
+    for n in reversed(ops): prio[n] = w[n] + max([prio[u] for u in users[n]] + [0])
+    done = set(n for n in need if nodes[n][0] in ("in", "const"))
+    pending = set(ops); steps = []
+    while pending:
+        ready = [n for n in pending if all(d in done for d in deps(n))]
+        lin = sorted([n for n in ready if nodes[n][0] == "lin"], key=lambda n: -prio[n])
+        mul = sorted([n for n in ready if nodes[n][0] != "lin"], key=lambda n: -prio[n])
+        if lin:                                   # cheap steps first: they unlock products
+            chosen = lin[:NPAIR]; cls = OP_LIN
+        else:
+            chosen = mul[:NPAIR]
+            cls = OP_SQR if all(nodes[n][0] == "sqr" for n in chosen) else OP_MUL
+        steps.append((cls, chosen)); done |= set(chosen); pending -= set(chosen)
+    # final move step(s): outputs into their registers (a register may still be read as an input until the very end)
+    # slot allocation over steps: value of node n lives from its defining step to its last use
+    nstep = len(steps)
+    defstep = {n: -1 for n in done if nodes[n][0] in ("in", "const")}
+    for si, (_, ch) in enumerate(steps):
+        for n in ch: defstep[n] = si
+    lastuse = {n: defstep[n] for n in need}
+    for n in ops:
+        for d in deps(n): lastuse[d] = max(lastuse[d], defstep[n])
+    for _, n in g.outputs: lastuse[n] = nstep            # read by the move step
+    slot = {}
+    for n in need:
+        if nodes[n][0] in ("in", "const"): slot[n] = SLOT[nodes[n][1]]
+    free = list(range(len(REGS), NSLOTS)); release = {}   # step -> slots that become free AFTER that step
+    for si, (_, ch) in enumerate(steps):
+        for s in release.pop(si - 1, []): free.append(s)
+        for n in ch:
+            if not free: raise RuntimeError(f"{g.name}: out of slots")
+            slot[n] = free.pop(0)
+            release.setdefault(lastuse[n], []).append(slot[n])
+    prog = Program(g.name)
+    for cls, ch in steps:
+        ins = []
+        for n in ch:
+            nd = nodes[n]
+            if nd[0] == "mul": ins.append((slot[n], slot[nd[1]], slot[nd[2]]))
+            elif nd[0] == "sqr": ins.append((slot[n], slot[nd[1]], slot[nd[1]]))
+            else: ins.append((slot[n], tuple((slot[s], M) for s, M in nd[1])))
+        prog.steps.append((cls, ins))
+    moves = [(SLOT[reg], ((slot[n], I2),)) for reg, n in g.outputs if SLOT[reg] != slot[n]]
+    for i in range(0, len(moves), NPAIR): prog.steps.append((OP_LIN, moves[i:i + NPAIR]))
+    # the moves read temporaries (or registers that no move writes) and write registers: no read-after-write hazard inside or across
+    # the move steps (pairs of one step are not ordered against each other on the device)
+    srcs = {t[0][0] for _, t in moves}; dsts = {d for d, _ in moves}
+    if srcs & dsts: raise RuntimeError(f"{g.name}: move hazard on slots {sorted(srcs & dsts)}")
+    # and no step may write a slot that the same step reads
+    for cls, ins in prog.steps:
+        rd = set()
+        for i in ins: rd |= ({s_ for s_, _ in i[1]} if cls == OP_LIN else {i[1], i[2]})
+        if rd & {i[0] for i in ins}: raise RuntimeError(f"{g.name}: a step writes a slot it reads")
+    return prog
+
+def run_program(prog, slots):
+    """reference interpreter: slots = list of (re, im) ints mod P (plain, not Montgomery).  All instructions of a step read
+    before any writes (the device separates steps by __syncwarp and never lets a step write a slot it reads)."""
+    for cls, ins in prog.steps:
+        res = []
+        for i in ins:
+            if cls == OP_LIN:
+                acc = (0, 0)
+                for s, M in i[1]: acc = f2_add(acc, f2_apply(M, slots[s]))
+                res.append((i[0], acc))
+            else: res.append((i[0], f2_mul(slots[i[1]], slots[i[2]])))
+        for d, v in res: slots[d] = v
+    return slots
+
+def compile_all():
+    graphs = build_programs(Graph)
+    return {n: compile_graph(g) for n, g in graphs.items()}
+
+# ------------------------------------------------------------------ whole pairing check with the reference interpreter (tests)
+def fresh_slots():
+    s = [(0, 0)] * NSLOTS
+    for r in REG_CONST: s[SLOT[r]] = CONSTS[r]
+    return s
+def fp_inv(a): return pow(a, P - 2, P)
+def vm_pairing_is_one(progs, p1, q1, p2, q2):
+    """e(p1, q1) e(p2, q2) == 1 via the VM programs; p = (x, y) in Fp, q = ((x0, x1), (y0, y1)) in Fp2 (affine, not identity)"""
+    s = fresh_slots()
+    for reg, v in (("P1X", (p1[0], 0)), ("P1Y", (p1[1], 0)), ("Q1X", q1[0]), ("Q1Y", q1[1]), ("P2X", (p2[0], 0)), ("P2Y", (p2[1], 0)), ("Q2X", q2[0]), ("Q2Y", q2[1])):
+        s[SLOT[reg]] = (v[0] % P, v[1] % P)
+    run_program(progs["ML_INIT"], s)
+    for i in range(62, -1, -1):
+        run_program(progs["ML_DBL"], s)
+        if (Z_ABS >> i) & 1: run_program(progs["ML_ADD"], s)
+    final_exp_vm(progs, s)
+    return [s[SLOT[r]] for r in r6("ACC")] == [(1, 0)] + [(0, 0)] * 5
+def final_exp_vm(progs, s):
+    run_program(progs["FE_INV_A"], s)
+    n = s[SLOT["NORM"]]; assert n[1] == 0
+    s[SLOT["NINV"]] = (fp_inv(n[0]), 0)
+    run_program(progs["FE_INV_B"], s)
+    def expz():
+        for i in range(62, -1, -1):
+            run_program(progs["CYCSQR"], s)
+            if (Z_ABS >> i) & 1: run_program(progs["MULX"], s)
+    expz(); run_program(progs["GLUE1"], s)
+    expz(); run_program(progs["GLUE2"], s)
+    expz(); run_program(progs["GLUE3"], s)
+    expz(); run_program(progs["GLUE4"], s)
+    expz(); run_program(progs["GLUE5"], s)
+
+# ------------------------------------------------------------------ emitter
+def enc_lin(dst, terms):
+    """128-bit LIN instruction as 4 x u32: w0 = dst | nterms << 8; then per term 24 bits: slot | 4 x 4-bit two's-complement entries"""
+    tw = []
+    for s, M in terms:
+        e = 0
+        for j, c in enumerate(M): e |= (c & 0xf) << (4 * j)
+        tw.append(s | (e << 8))
+    tw += [0] * (MAXT - len(tw))
+    w0 = dst | (len(terms) << 8) | ((tw[0] & 0xffff) << 16)
+    w1 = (tw[0] >> 16) | (tw[1] << 8)
+    w2 = tw[2] | ((tw[3] & 0xff) << 24)
+    w3 = tw[3] >> 8
+    return [w0 & 0xffffffff, w1 & 0xffffffff, w2 & 0xffffffff, w3 & 0xffffffff]
+def enc_mul(dst, a, b): return [dst | (a << 8) | (b << 16), 0, 0, 0]
+NOP = [0xff, 0, 0, 0]          # dst 0xff = no operation
+
+def emit(progs, path):
+    order = ["ML_INIT", "ML_DBL", "ML_ADD", "FE_INV_A", "FE_INV_B", "CYCSQR", "MULX", "GLUE1", "GLUE2", "GLUE3", "GLUE4", "GLUE5"]
+    L = []
+    A = L.append
+    A("// GENERATED by tools/vmgen.py -- do not edit.  Step programs of the warp-cooperative pairing (see tools/vmgen.py for the format).")
+    A("#ifndef HBLS_VM_PROGRAMS_CUH\n#define HBLS_VM_PROGRAMS_CUH\n#include <stdint.h>")
+    A(f"#define VM_NSLOTS {NSLOTS}\n#define VM_OP_MUL {OP_MUL}\n#define VM_OP_SQR {OP_SQR}\n#define VM_OP_LIN {OP_LIN}")
+    for r in REGS: A(f"#define VM_R_{r} {SLOT[r]}")
+    hdr = []; ins = []; table = []
+    for pi, name in enumerate(order):
+        p = progs[name]; first = len(hdr)
+        for cls, instrs in p.steps:
+            hdr.append(cls)
+            row = []
+            for i in instrs: row += enc_lin(i[0], i[1]) if cls == OP_LIN else enc_mul(*i)
+            row += NOP * (NPAIR - len(instrs))
+            ins += row
+        table.append((name, first, len(p.steps)))
+        A(f"#define VM_P_{name} {pi}")
+    A(f"#define VM_NPROG {len(order)}")
+    A("static __device__ const uint16_t VM_PROG_FIRST[VM_NPROG] = {" + ", ".join(str(t[1]) for t in table) + "};")
+    A("static __device__ const uint16_t VM_PROG_STEPS[VM_NPROG] = {" + ", ".join(str(t[2]) for t in table) + "};")
+    A(f"// steps per program: " + ", ".join(f"{t[0]}={t[2]}" for t in table))
+    A(f"static __device__ const uint8_t VM_STEP_CLASS[{len(hdr)}] = {{" + ", ".join(str(h) for h in hdr) + "};")
+    A(f"static __device__ const uint4 VM_INS[{len(ins) // 4}] = {{")
+    for i in range(0, len(ins), 16):
+        A("    " + " ".join("{0x%08xu, 0x%08xu, 0x%08xu, 0x%08xu}," % tuple(ins[j:j + 4]) for j in range(i, min(i + 16, len(ins)), 4)))
+    A("};\n#endif")
+    open(path, "w").write("\n".join(L) + "\n")
+    return table, len(hdr)
+
+def stats(progs):
+    out = {}
+    for n, p in progs.items():
+        c = {OP_MUL: 0, OP_SQR: 0, OP_LIN: 0}; fill = {OP_MUL: 0, OP_SQR: 0, OP_LIN: 0}
+        for cls, ins in p.steps: c[cls] += 1; fill[cls] += len(ins)
+        out[n] = {"steps": len(p.steps), "mul_steps": c[OP_MUL], "sqr_steps": c[OP_SQR], "lin_steps": c[OP_LIN],
+                  "mul_ops": fill[OP_MUL], "sqr_ops": fill[OP_SQR], "lin_ops": fill[OP_LIN]}
+    return out
+
+if __name__ == "__main__":
+    progs = compile_all()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    table, nsteps = emit(progs, os.path.join(root, "harmony_b200", "csrc", "vm_programs.cuh"))
+    for n, s in stats(progs).items(): print(f"{n:10s} {s}")
+    print("total steps stored:", nsteps)
