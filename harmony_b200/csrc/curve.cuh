@@ -34,6 +34,20 @@ HB_DEV void f_zero(fp2& r) { fp2_zero(r); }
 HB_DEV void f_one(fp2& r) { fp2_one(r); }
 HB_DEV void f_cmov(fp2& r, const fp2& a, bool c) { fp2_cmov(r, a, c); }
 
+// lane-pair carrier (tower.cuh fp2h): the same point arithmetic with every Fp2 coordinate split over two lanes
+HB_DEV void f_add(fp2h& r, const fp2h& a, const fp2h& b) { fp2_add(r, a, b); }
+HB_DEV void f_sub(fp2h& r, const fp2h& a, const fp2h& b) { fp2_sub(r, a, b); }
+HB_DEV void f_dbl(fp2h& r, const fp2h& a) { fp2_dbl(r, a); }
+HB_DEV void f_neg(fp2h& r, const fp2h& a) { fp2_neg(r, a); }
+HB_DEV void f_mul(fp2h& r, const fp2h& a, const fp2h& b) { fp2_mul(r, a, b); }
+HB_DEV void f_sqr(fp2h& r, const fp2h& a) { fp2_sqr(r, a); }
+HB_DEV void f_inv(fp2h& r, const fp2h& a) { fp2_inv(r, a); }
+HB_DEV bool f_is_zero(const fp2h& a) { return fp2_is_zero(a); }
+HB_DEV bool f_eq(const fp2h& a, const fp2h& b) { return fp2_eq(a, b); }
+HB_DEV void f_zero(fp2h& r) { fp2_zero(r); }
+HB_DEV void f_one(fp2h& r) { fp2_one(r); }
+HB_DEV void f_cmov(fp2h& r, const fp2h& a, bool c) { fp2_cmov(r, a, c); }
+
 template <class F> struct jac { F x, y, z; };     // Jacobian: (X/Z^2, Y/Z^3); z == 0 <=> identity
 template <class F> struct aff { F x, y; };        // affine; x == y == 0 encodes the identity (not on either curve)
 typedef jac<fp> g1; typedef jac<fp2> g2;
@@ -204,22 +218,22 @@ HB_DEV void g2_psi_aff(g2a& r, const g2a& a) {
     fp2 t; fp2_conj(t, a.x); fp2_mul(r.x, t, cx);
     fp2_conj(t, a.y); fp2_mul(r.y, t, cy);
 }
-// Jacobian form: psi(X, Y, Z) = (conj(X) cx, conj(Y) cy, conj(Z)) -- no inversion
-HB_DEV void g2_psi(g2& r, const g2& p) {
-    fp2 cx, cy; fp2_const(cx, K_PSI_CX); fp2_const(cy, K_PSI_CY);
-    fp2 t; fp2_conj(t, p.x); fp2_mul(r.x, t, cx);
+// Jacobian form: psi(X, Y, Z) = (conj(X) cx, conj(Y) cy, conj(Z)) -- no inversion.  E = fp2 or the lane-pair carrier fp2h.
+template <class E> HB_DEV void g2_psi(jac<E>& r, const jac<E>& p) {
+    E cx, cy; fp2_const(cx, K_PSI_CX); fp2_const(cy, K_PSI_CY);
+    E t; fp2_conj(t, p.x); fp2_mul(r.x, t, cx);
     fp2_conj(t, p.y); fp2_mul(r.y, t, cy);
     fp2_conj(r.z, p.z);
 }
 // psi^2(X, Y, Z) = (X * N(cx), -Y, Z)
-HB_DEV void g2_psi2(g2& r, const g2& p) {
+template <class E> HB_DEV void g2_psi2(jac<E>& r, const jac<E>& p) {
     fp c; fp_set(c, K_PSI2_CX);
     fp2_mul_fp(r.x, p.x, c); fp2_neg(r.y, p.y); r.z = p.z;
 }
 // Q in G2  <=>  psi(Q) == [z]Q   (same boolean as [r]Q == O)
-HB_NOINLINE bool g2_in_subgroup(const g2& p) {
+template <class E> HB_NOINLINE bool g2_in_subgroup(const jac<E>& p) {
     if (pt_is_inf(p)) return true;
-    g2 a, b; g2_psi(a, p); pt_mul_zabs(b, p); pt_neg(b, b);
+    jac<E> a, b; g2_psi(a, p); pt_mul_zabs(b, p); pt_neg(b, b);
     return pt_eq(a, b);
 }
 // P in G1  <=>  phi(P) == -[z^2]P, phi(x, y) = (beta x, y)
@@ -384,8 +398,8 @@ HB_NOINLINE bool sw_map_g2_post(g2& r, const fp2& t, const fp2& u, const fp2& ct
 }
 #endif
 // Budroni-Pintore cofactor clearing: [z^2 - z - 1]P + psi([z - 1]P) + psi^2([2]P)   (plain h2 gives other bytes)
-HB_NOINLINE void g2_clear_cofactor(g2& r, const g2& p) {
-    g2 zp, z2p, t1, t2, t3, np;
+template <class E> HB_NOINLINE void g2_clear_cofactor(jac<E>& r, const jac<E>& p) {
+    jac<E> zp, z2p, t1, t2, t3, np;
     pt_mul_zabs(zp, p); pt_neg(zp, zp);
     pt_mul_zabs(z2p, zp); pt_neg(z2p, z2p);
     pt_neg(np, p);

@@ -145,12 +145,18 @@ void launch_verify_tail(size_t B, const VerifyBufs& v, Scratch* sc, const uint8_
     // the batched check consumes the Jacobian sums directly; -apk in affine form is then only needed for the rounds of failed groups
     if (!rlc) LAUNCH(k_g1_normalize, blocks_for(B, TPB), TPB, s, B, v.apk, v.pkneg, 1, (const int*)nullptr);
     STAGE_EV(2, sc, s);
-    LAUNCH(k_g2_decode, heavy_blocks(B), TPB, s, B, d_sig96, v.sig, v.ok_sig, 1);
+    // small batches (latency path): one item per lane pair; large ones: one per thread, persistent
+    const bool pairs = !rlc && (long long)B <= g.coop_max;
+    if (pairs) LAUNCH(k_g2_decode_pair, blocks_for(2 * B, 32), 32, s, B, d_sig96, v.sig, v.ok_sig, 1);
+    else LAUNCH(k_g2_decode, heavy_blocks(B), TPB, s, B, d_sig96, v.sig, v.ok_sig, 1);
     STAGE_EV(3, sc, s);
     if (same_msg && B > 1) {
-        LAUNCH(k_hash_to_g2, 1, TPB, s, (size_t)1, d_msgs, msg_len, v.hm, v.ok_hm);
+        if (pairs) LAUNCH(k_hash_to_g2_pair, 1, 32, s, (size_t)1, d_msgs, msg_len, v.hm, v.ok_hm);
+        else LAUNCH(k_hash_to_g2, 1, TPB, s, (size_t)1, d_msgs, msg_len, v.hm, v.ok_hm);
         LAUNCH(k_broadcast_hm, blocks_for(B, 256), 256, s, B, v.hm, v.ok_hm);
-    } else
+    } else if (pairs)
+        LAUNCH(k_hash_to_g2_pair, blocks_for(2 * B, 32), 32, s, B, d_msgs, msg_len, v.hm, v.ok_hm);
+    else
         LAUNCH(k_hash_to_g2, heavy_blocks(B), TPB, s, B, d_msgs, msg_len, v.hm, v.ok_hm);
     STAGE_EV(4, sc, s);
     hbls_batch_info& bi = g.info;
@@ -532,13 +538,13 @@ static int verify_hash_locked(const blsSignature* sig, const blsPublicKey* pub, 
     const uint8_t* ok_sig = nullptr;
     if (sig96) {          // serialized signature: decode (+ subgroup check) on the device
         CK(cudaMemcpyAsync(dsig96, sig96, 96, cudaMemcpyHostToDevice, g.stream));
-        LAUNCH(k_g2_decode, 1, 32, g.stream, (size_t)1, dsig96, v.sig, v.ok_sig, 1);
+        LAUNCH(k_g2_decode_pair, 1, 32, g.stream, (size_t)1, dsig96, v.sig, v.ok_sig, 1);
         ok_sig = v.ok_sig;
     } else {              // struct inputs are already-decoded Jacobian points: normalise instead of decoding
         CK(cudaMemcpyAsync(dsig, sig, 288, cudaMemcpyHostToDevice, g.stream));
         LAUNCH(k_g2_normalize, 1, 32, g.stream, (size_t)1, dsig, v.sig);
     }
-    LAUNCH(k_hash_to_g2, 1, 32, g.stream, (size_t)1, dmsg, (uint32_t)size, v.hm, v.ok_hm);
+    LAUNCH(k_hash_to_g2_pair, 1, 32, g.stream, (size_t)1, dmsg, (uint32_t)size, v.hm, v.ok_hm);
     if (g.coop_max >= 1) LAUNCH(k_pairing_coop, 1, 32, g.stream, (size_t)1, v.sig, v.pkneg, v.hm, (const uint8_t*)v.ok_hm, ok_sig, (const uint8_t*)nullptr, dres);
     else LAUNCH(k_pairing_verify_split, 1, 64, g.stream, (size_t)1, v.sig, v.pkneg, v.hm, (const uint8_t*)v.ok_hm, ok_sig, (const uint8_t*)nullptr, dres, (const int*)nullptr);
     LAUNCH(k_pairing_fixup, 1, 32, g.stream, (size_t)1, v.sig, v.pkneg, v.hm, (const uint8_t*)v.ok_hm, ok_sig, (const uint8_t*)nullptr, dres, (const int*)nullptr);

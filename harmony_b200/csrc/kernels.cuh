@@ -219,6 +219,39 @@ __global__ void k_hash_to_g2(size_t n, const uint8_t* msgs, uint32_t msg_len, g2
   }
 }
 
+// ---- lane-pair forms of decode / hash for small batches (latency path, hbls.cu: B <= coop_max): one item per LANE PAIR.  The Fp-only
+// chains (square roots, Jacobi symbols, the SW map) run redundantly on both lanes; the long G2 ladders -- subgroup test, cofactor
+// clearing -- run on the split carrier (an Fp2 product costs one product-time per lane instead of three), inversions by binary GCD.
+__global__ void k_g2_decode_pair(size_t n, const uint8_t* in, g2a* out, uint8_t* ok, int check_order) {
+    const size_t i = HB_TID >> 1; if (i >= n) return;                    // a pair leaves together
+    g2 p; bool good = g2_deserialize(p, in + 96 * i, false);
+    if (good && check_order && !pt_is_inf(p)) {
+        jac<fp2h> q; fp2h_pack(q.x, p.x); fp2h_pack(q.y, p.y); fp2h_pack(q.z, p.z);
+        good = g2_in_subgroup(q);
+    }
+    if ((threadIdx.x & 1) == 0) {
+        g2a a;
+        if (!good || pt_is_inf(p)) { fp2_zero(a.x); fp2_zero(a.y); } else { a.x = p.x; a.y = p.y; }
+        out[i] = a; ok[i] = good ? 1 : 0;
+    }
+}
+__global__ void k_hash_to_g2_pair(size_t n, const uint8_t* msgs, uint32_t msg_len, g2a* out, uint8_t* ok) {
+    const size_t i = HB_TID >> 1; if (i >= n) return;
+    fp2 t; hash_to_fp(t.a, msgs + (size_t)msg_len * i, msg_len); fp_zero(t.b);
+    g2 a; bool good = sw_map_g2(a, t);                                    // Fp-heavy: both lanes compute the same point
+    g2a res; fp2_zero(res.x); fp2_zero(res.y);
+    if (good) {
+        jac<fp2h> A, H; fp2h_pack(A.x, a.x); fp2h_pack(A.y, a.y); fp2h_pack(A.z, a.z);
+        g2_clear_cofactor(H, A);
+        if (!pt_is_inf(H)) {
+            fp2h zi, zi2, hx, hy; fp2_inv_gcd(zi, H.z); fp2_sqr(zi2, zi);
+            fp2_mul(hx, H.x, zi2); fp2_mul(zi2, zi2, zi); fp2_mul(hy, H.y, zi2);
+            fp2h_unpack(res.x, hx); fp2h_unpack(res.y, hy);
+        }
+    }
+    if ((threadIdx.x & 1) == 0) { out[i] = res; ok[i] = good ? 1 : 0; }
+}
+
 // same-message batches (the leader's prepare / commit vote collection, consensus/leader.go:127-290: every vote signs
 // the same block hash / commit payload): H(m) is computed once and replicated
 __global__ void k_broadcast_hm(size_t n, g2a* hm, uint8_t* ok) {

@@ -388,6 +388,13 @@ static inline uint32_t hb_emu_exchange(uint32_t v) {
 }
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int) { return (T)hb_emu_exchange((uint32_t)v); }
 #endif
+// Exchanges between the two lanes of a pair name only those two lanes in the shuffle mask: pairs of one warp may then diverge
+// (data-dependent branches of the point arithmetic on hostile inputs) without leaving a shuffle short of participants.
+#ifdef HB_HOST_EMU
+#define HB_PAIR_MASK 0u
+#else
+#define HB_PAIR_MASK (3u << (threadIdx.x & 30u))
+#endif
 HB_DEV int fp2h_role() {
 #ifdef HB_HOST_EMU
     return hb_emu.role;
@@ -397,16 +404,30 @@ HB_DEV int fp2h_role() {
 }
 HB_DEV void fp2h_partner(fp& r, const fp& x) {
 #pragma unroll
-    for (int j = 0; j < 12; j++) r.l[j] = __shfl_xor_sync(0xffffffffu, x.l[j], 1);
+    for (int j = 0; j < 12; j++) r.l[j] = __shfl_xor_sync(HB_PAIR_MASK, x.l[j], 1);
 }
 HB_DEV void fp2_zero(fp2h& r) { fp_zero(r.c); }
 HB_DEV void fp2_one(fp2h& r) { fp o; fp_one(o); fp z; fp_zero(z); r.c = z; fp_cmov(r.c, o, fp2h_role() == 0); }
 HB_DEV bool fp2_is_zero(const fp2h& x) {
     bool mine = fp_is_zero(x.c);
-    bool other = __shfl_xor_sync(0xffffffffu, mine ? 1 : 0, 1) != 0;
+    bool other = __shfl_xor_sync(HB_PAIR_MASK, mine ? 1 : 0, 1) != 0;
     return mine && other;
 }
 HB_DEV void fp2_const(fp2h& r, const uint32_t k[2][12]) { fp_set(r.c, k[fp2h_role()]); }
+HB_DEV bool fp2_eq(const fp2h& x, const fp2h& y) {
+    const int mine = fp_eq(x.c, y.c) ? 1 : 0;
+    return mine && __shfl_xor_sync(HB_PAIR_MASK, mine, 1) != 0;
+}
+HB_DEV void fp2_cmov(fp2h& r, const fp2h& x, bool c) { fp_cmov(r.c, x.c, c); }
+// whole value <-> the pair's halves (both lanes end up holding the full Fp2 element / each lane keeps its own half)
+HB_DEV void fp2h_unpack(fp2& r, const fp2h& x) {
+    fp o; 
+#pragma unroll
+    for (int j = 0; j < 12; j++) o.l[j] = __shfl_xor_sync(HB_PAIR_MASK, x.c.l[j], 1);
+    const bool im = fp2h_role() == 1;
+    r.a = im ? o : x.c; r.b = im ? x.c : o;
+}
+HB_DEV void fp2h_pack(fp2h& r, const fp2& x) { r.c = fp2h_role() == 1 ? x.b : x.a; }
 #ifndef HB_SPLIT_INLINE
 #define HB_SPLIT_INLINE 1
 #endif
@@ -436,7 +457,7 @@ HB_NOINLINE void fp2_mul(fp2h& r, const fp2h& x, const fp2h& y) {
 #pragma unroll
     for (int j = 0; j < 12; j++) { xo[j] = x.c.l[j]; yo[j] = y.c.l[j]; }
 #pragma unroll
-    for (int j = 0; j < 12; j++) { xp[j] = __shfl_xor_sync(0xffffffffu, xo[j], 1); yp[j] = __shfl_xor_sync(0xffffffffu, yo[j], 1); }
+    for (int j = 0; j < 12; j++) { xp[j] = __shfl_xor_sync(HB_PAIR_MASK, xo[j], 1); yp[j] = __shfl_xor_sync(HB_PAIR_MASK, yo[j], 1); }
     uint32_t ny[12];                                   // p - yp in (0, p]
     sub_cc(ny[0], HB_P0, yp[0]);
 #pragma unroll
@@ -456,7 +477,7 @@ HB_NOINLINE void fp2_sqr(fp2h& r, const fp2h& x) {
 #pragma unroll
     for (int j = 0; j < 12; j++) xo[j] = x.c.l[j];
 #pragma unroll
-    for (int j = 0; j < 12; j++) xp[j] = __shfl_xor_sync(0xffffffffu, xo[j], 1);
+    for (int j = 0; j < 12; j++) xp[j] = __shfl_xor_sync(HB_PAIR_MASK, xo[j], 1);
     limbs_add12(s, xo, xp);            // < 2p
     limbs_sub12_plus_p(d, xo, xp);     // in (0, 2p)
     limbs_add12(t, xp, xp);            // 2 xp < 2p
@@ -470,6 +491,14 @@ HB_NOINLINE void fp2_sqr(fp2h& r, const fp2h& x) {
 HB_NOINLINE void fp2_inv(fp2h& r, const fp2h& x) {
     fp sq, o, n; fp_sqr(sq, x.c); fp2h_partner(o, sq); fp_add(n, sq, o);      // a^2 + b^2 (both lanes)
     fp_inv(n, n);
+    fp t, m; fp_mul(t, x.c, n); fp_neg(m, t);
+    r.c = t; fp_cmov(r.c, m, fp2h_role() == 1);
+}
+
+// latency-path inversion: same as fp2_inv with the binary-GCD Fp inverse
+HB_NOINLINE void fp2_inv_gcd(fp2h& r, const fp2h& x) {
+    fp sq, o, n; fp_sqr(sq, x.c); fp2h_partner(o, sq); fp_add(n, sq, o);
+    fp_inv_gcd(n, n);
     fp t, m; fp_mul(t, x.c, n); fp_neg(m, t);
     r.c = t; fp_cmov(r.c, m, fp2h_role() == 1);
 }
@@ -569,7 +598,7 @@ HB_DEV bool fp12_is_one(const fp12_t<fp2h>& x) {
         acc |= x.c0.c1.c.l[j] | x.c0.c2.c.l[j] | x.c1.c0.c.l[j] | x.c1.c1.c.l[j] | x.c1.c2.c.l[j];
     }
     const int mine = acc == 0;
-    const int other = __shfl_xor_sync(0xffffffffu, mine, 1);
+    const int other = __shfl_xor_sync(HB_PAIR_MASK, mine, 1);
     return mine && other;
 }
 template <class E> HB_NOINLINE void fp12_mul(fp12_t<E>& r, const fp12_t<E>& x, const fp12_t<E>& y) {

@@ -170,3 +170,19 @@ extern "C" int emu_vm_pairing(const uint8_t* pk48, const uint8_t* sig96, const u
     }
     return diff == 0 ? 1 : 0;
 }
+
+// lane-pair decode / hash kernels (latency path) on two host threads against the thread-per-item kernels: bit 0 = decoded
+// signature identical (point and ok flag), bit 1 = H(m) identical; n items one after the other (pair 0 of a 2-thread CTA)
+extern "C" int emu_pair_decode_hash(size_t n, const uint8_t* sigs96, const uint8_t* msgs, uint32_t len) {
+    std::vector<g2a> s1(n), s2(n), h1(n), h2(n); std::vector<uint8_t> o1(n), o2(n), k1(n), k2(n);
+    run_seq(1, (unsigned)n, [&] { k_g2_decode(n, sigs96, s1.data(), o1.data(), 1); });
+    run_seq(1, (unsigned)n, [&] { k_hash_to_g2(n, msgs, len, h1.data(), k1.data()); });
+    int res = 3;
+    for (size_t i = 0; i < n; i++) {
+        run_pair([&] { k_g2_decode_pair(1, sigs96 + 96 * i, &s2[i], &o2[i], 1); });
+        run_pair([&] { k_hash_to_g2_pair(1, msgs + (size_t)len * i, len, &h2[i], &k2[i]); });
+        if (o1[i] != o2[i] || std::memcmp(&s1[i], &s2[i], sizeof(g2a)) != 0) res &= ~1;
+        if (k1[i] != k2[i] || std::memcmp(&h1[i], &h2[i], sizeof(g2a)) != 0) res &= ~2;
+    }
+    return res;
+}

@@ -128,3 +128,15 @@ def test_vm_pairing_device_decoders(emuk, oracle):
     for (p_, s_, msg) in ((pk, sig, m), (pk, sig, m2), (pk2, sig, m)):
         assert emuk.emu_vm_pairing(p_, s_, msg, 48) == (1 if oracle.verify_hash(s_, p_, msg) else 0)
     assert emuk.emu_vm_pairing(pk, sig, m, 48) == 1 and emuk.emu_vm_pairing(pk, sig, m2, 48) == 0
+
+def test_lane_pair_decode_and_hash_kernels(emuk, oracle):
+    """k_g2_decode_pair / k_hash_to_g2_pair (item per lane pair, latency path) == the thread-per-item kernels: valid signatures,
+    a point outside the subgroup / undecodable bytes / the identity, messages incl. one that maps to no point."""
+    import random
+    rng = random.Random(3)
+    sks = [wl.sk_bytes(wl.seeded_sk("lp2", i)) for i in range(3)]
+    msgs = [wl.commit_payload("lp2", i) for i in range(3)] + [bytes(48), rng.randbytes(48), rng.randbytes(48)]
+    sigs = [oracle.sign_hash(s, m) for s, m in zip(sks, msgs)]
+    junk = bytearray(rng.randbytes(96)); junk[95] &= 0x19; junk[47] &= 0x19
+    sigs += [bytes(96), b"\xff" * 96, bytes(junk)]
+    assert emuk.emu_pair_decode_hash(len(sigs), b"".join(sigs), b"".join(msgs), 48) == 3

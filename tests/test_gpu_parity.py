@@ -394,6 +394,7 @@ def test_batch_mode_rlc_equals_exact(gbls):
     pks_blob = gbls.GetPublicKeyBatch(b"".join(wl.sk_bytes(k) for k in sks))
     com = gbls.Committee([pks_blob[48 * i:48 * i + 48] for i in range(n)])
     B = 1024 + 3                                                  # 256 strided groups of 4 + 3 tail rounds
+    old_min = gbls.GetParam("rlc_min"); gbls.SetParam("rlc_min", 1024)
     bms = [wl.bitmap_with_k("rlc", j, n, [167, 200, 250][j % 3]) for j in range(16)]
     agg = [wl.sk_bytes(wl.round_signer_sum(sks, bm)) for bm in bms]
     msgs = [wl.commit_payload("rlc", j) for j in range(B)]
@@ -409,7 +410,7 @@ def test_batch_mode_rlc_equals_exact(gbls):
             assert out[1] == out[0]
             assert [j for j in range(B) if out[1][j] == 0] == bad
     finally:
-        gbls.SetBatchMode(1)
+        gbls.SetBatchMode(1); gbls.SetParam("rlc_min", old_min)
 
 # ---------------------------------------------------------------------------------------------------------------- round 2
 def _bench_committee(gbls):
@@ -517,9 +518,14 @@ def test_config4_ten_thousand_triples_one_percent_invalid(gbls, oracle):
         elif kind == 1: mm[32 * i + 5] ^= 0x80
         elif kind == 2: o = (i + 7) % k; pk[48 * i:48 * i + 48] = pks[48 * o:48 * o + 48]
         else: pk[48 * i:48 * i + 48] = b"\xff" * 48
-    res = gbls.VerifyBatch(bytes(pk), bytes(sg), bytes(mm), 32)
-    info = gbls.LastBatchInfo()
+    old = gbls.GetParam("rlc_min")
+    try:
+        gbls.SetParam("rlc_min", 1024)               # batched groups (default threshold 16 384: below it the warp-per-item exact kernel is faster)
+        res = gbls.VerifyBatch(bytes(pk), bytes(sg), bytes(mm), 32)
+        info = gbls.LastBatchInfo()
+    finally: gbls.SetParam("rlc_min", old)
     assert info["mode"] == 1 and info["group_size"] == 4 and info["groups"] == k // 4
+    assert gbls.VerifyBatch(bytes(pk), bytes(sg), bytes(mm), 32) == res and gbls.LastBatchInfo()["cta_threads"] == 32     # default path: warp per item
     ng = k // 4
     check = set(bad) | {g % ng + q * ng for g in bad for q in range(4)} | set(rng.sample(range(k), 300))
     for i in sorted(check):
