@@ -121,10 +121,10 @@ def cpu_rounds_per_s(orc, pks, bitmaps, sigs, msgs, blen, budget_s, threads):
 # for the lane-pair pairing stage); pinned by tests/test_emu_kernels.py::test_stage_counts_pinned and tests/test_emu_logic.py.
 # (mul, sqr); "scale"/"pairing" are per GROUP of G rounds, the others per round of the 167/200/250-signer workload.
 EXEC_FP_OPS = {
-    False: {"mask": (357.3, 133.7), "decode": (1478.0, 756.0), "hash": (3172.6, 1524.0),
-            4: {"scale": (7150.0, 2892.8), "pairing": (34661, 764)}, 8: {"scale": (14753.6, 5427.2), "pairing": (54329, 764)}},
-    True:  {"mask": (357.3, 133.7), "decode": (1478.0, 756.0), "hash": (3048.0, 1014.7),                    # shared inversions (HB_BATCH_INV)
-            4: {"scale": (6882.0, 1879.6), "pairing": (34661, 764)}, 8: {"scale": (14217.6, 3400.0), "pairing": (54329, 764)}},
+    False: {"mask": (368.5, 137.8), "decode": (1478.0, 756.0), "hash": (3173.4, 1524.0),
+            4: {"scale": (7150.0, 2893.0), "pairing": (34661, 764)}, 8: {"scale": (14754.0, 5427.0), "pairing": (54329, 764)}},
+    True: {"mask": (368.5, 137.8), "decode": (1478.0, 756.0), "hash": (3004.2, 855.5),
+            4: {"scale": (6794.5, 1563.0), "pairing": (34661, 764)}, 8: {"scale": (14043.0, 2767.0), "pairing": (54329, 764)}},      # shared inversions (HB_BATCH_INV, 8 items per inversion)
 }
 EXACT_PAIRING_FP_OPS = (20055, 497)      # exact mode: 2-pair Miller loop + final exponentiation per round (oracle counter, stages 4 + 5)
 def rlc_group_size(B, sm_count, tpb_split=512):
@@ -372,8 +372,9 @@ def run_gpu(args):
     # Denominator (calibrated in round 2, profiles/r2_probe_int.*): a 32x32+64 MAC is one IMAD.WIDE, and an IMAD.WIDE holds the
     # FMA-heavy pipe of a scheduler for 4 cycles per warp (ncu: 4.0 pipe-cycles per instruction, carry-chained or not), so the chip
     # peak is SMs x 4 schedulers x 8 MAC/clk x SM clock.  The live probe (the multiplier's own carry chains, nothing else) reaches ~90 % of it.
-    probe_macs, sm_clock_hz = bls.ProbeMac32PerS(8192)
+    probe_macs, max_clock_hz = bls.ProbeMac32PerS(8192)
     sm_count = torch.cuda.get_device_properties(local).multi_processor_count
+    sm_clock_hz = min(max_clock_hz, clocks["sm_mhz"] * 1e6) if clocks.get("sm_mhz") else max_clock_hz     # median SM clock sampled during the timed region
     peak = sm_count * 4 * 8 * sm_clock_hz
     binfo = bls.BuildInfo()
     names = list(bls.STAGE_NAMES)
@@ -399,7 +400,7 @@ def run_gpu(args):
     exact_macs = stage_mac32_per_round(orc, pks, bitmaps, sigs, msgs, blen, sample=min(12, S))     # the reference algorithm, oracle counter
     roofline = {"bound": "int32-imad", "kernel": names[dom], "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TMAC32/s",
                 "frac": achieved / peak,
-                "peak_source": f"FMA-heavy pipe: {sm_count} SMs x 4 schedulers x 8 IMAD.WIDE MAC/clk x {sm_clock_hz / 1e9:.3f} GHz (SM clock measured under the probe's load); "
+                "peak_source": f"FMA-heavy pipe: {sm_count} SMs x 4 schedulers x 8 IMAD.WIDE MAC/clk x {sm_clock_hz / 1e9:.3f} GHz (median SM clock nvidia-smi reported during the timed region); "
                                "4 pipe-cycles per IMAD.WIDE warp instruction measured with ncu (profiles/r2_probe_int_ncu.txt)",
                 "probe_achieved": probe_macs / 1e12, "probe_frac_of_peak": probe_macs / peak,
                 "probe": "hbls_probe_mac32_per_s: the field multiplier's own mad.lo.cc/madc.hi.cc rows (IMAD.WIDE.U32.X), 4 independent accumulator sets per thread, 512 threads/SM",

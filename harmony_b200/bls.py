@@ -98,6 +98,8 @@ def lib():
         sig("hbls_get_param", c.c_longlong, u8p)
         sig("hbls_aggregate_verify_items", c.c_int, sz, c.POINTER(vp), vp, vp, vp, sz, vp)
         sig("hbls_verify_headers", c.c_int, vp, sz, vp, vp, sz, vp, sz, sz, vp)
+        sig("hbls_rlc_partial", c.c_int, sz, vp, vp, vp, sz, vp)
+        sig("hbls_rlc_fold", c.c_int, sz, vp)
         sig("hbls_mask_create", c.c_int, c.POINTER(vp), vp)
         sig("hbls_mask_destroy", None, vp)
         sig("hbls_mask_set_mask", c.c_int, vp, vp, sz)
@@ -318,6 +320,21 @@ def VerifyBatch(pks48: bytes, sigs96: bytes, msgs: bytes, msg_len: int) -> bytes
     rc = _need().hbls_verify_batch(k, _buf(pks48), _buf(sigs96), _buf(msgs), msg_len, res)
     if rc != 0: raise HblsError(f"hbls_verify_batch rc={rc}")
     return res.raw[:k]
+
+PARTIAL_BYTES = 872
+def RlcPartial(pks48: bytes, sigs96: bytes, msgs: bytes, msg_len: int) -> bytes:
+    """Partial record of a slice of triples (hbls_rlc_partial): what a rank contributes to the all-gather of a batch split over GPUs."""
+    k = len(sigs96) // 96
+    rec = ctypes.create_string_buffer(PARTIAL_BYTES)
+    rc = _need().hbls_rlc_partial(k, _buf(pks48), _buf(sigs96), _buf(msgs), msg_len, rec)
+    if rc != 0: raise HblsError(f"hbls_rlc_partial rc={rc}")
+    return rec.raw
+def RlcFold(records) -> bool:
+    """True iff the gathered records prove every item of every slice valid (hbls_rlc_fold)."""
+    blob = b"".join(bytes(r) for r in records)
+    rc = _need().hbls_rlc_fold(len(blob) // PARTIAL_BYTES, _buf(blob))
+    if rc < 0: raise HblsError(f"hbls_rlc_fold rc={rc}")
+    return rc == 1
 
 def SignHashBatch(sks32: bytes, msgs: bytes, msg_len: int):
     k = len(sks32) // 32

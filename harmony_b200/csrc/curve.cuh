@@ -361,7 +361,6 @@ HB_NOINLINE bool sw_map_g2(g2& r, const fp2& t) {
     r.x = x; r.y = y; fp2_one(r.z);
     return true;
 }
-#if defined(HB_BATCH_INV) && HB_BATCH_INV
 // The same map in two halves around its single Fp2 inversion, so that a thread which maps several messages in turn can share
 // that inversion (f_batch_inv): pre() yields d = u * c1 t, post() continues from dinv = 1/d exactly as sw_map_g2 does.
 HB_NOINLINE bool sw_map_g2_pre(fp2& u, fp2& ct, fp2& d, const fp2& t) {
@@ -396,7 +395,6 @@ HB_NOINLINE bool sw_map_g2_post(g2& r, const fp2& t, const fp2& u, const fp2& ct
     r.x = x; r.y = y; fp2_one(r.z);
     return true;
 }
-#endif
 // Budroni-Pintore cofactor clearing: [z^2 - z - 1]P + psi([z - 1]P) + psi^2([2]P)   (plain h2 gives other bytes)
 template <class E> HB_NOINLINE void g2_clear_cofactor(jac<E>& r, const jac<E>& p) {
     jac<E> zp, z2p, t1, t2, t3, np;

@@ -98,9 +98,9 @@ unsigned light_blocks(size_t n) { return capped_blocks(n, g.tpsm_light, TPB); } 
 unsigned split_blocks(size_t nthreads) { return capped_blocks(nthreads, g.tpsm_split, HB_TPB_SPLIT); }
 
 // ------------------------------------------------------------------ coefficient stream (host): ChaCha20 block function, RFC 8439
-void chacha20_block(const uint32_t key[8], uint64_t counter, uint32_t out[16]) {
+void chacha20_block(const uint32_t key[8], uint64_t counter, uint32_t out[16], uint32_t block = 0) {
     uint32_t st[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key[0], key[1], key[2], key[3], key[4], key[5], key[6], key[7],
-                       (uint32_t)counter, (uint32_t)(counter >> 32), 0x68626c73u /* "hbls" */, 0u};
+                       (uint32_t)counter, (uint32_t)(counter >> 32), 0x68626c73u /* "hbls" */, block};
     uint32_t x[16]; memcpy(x, st, sizeof x);
     auto rotl = [](uint32_t v, int c) { return (v << c) | (v >> (32 - c)); };
     auto qr = [&](int a, int b, int c, int d) {
@@ -117,6 +117,16 @@ rlc_coeffs rlc_draw() {
     rlc_coeffs co;
     for (int k = 0; k < HB_RLC_GMAX; k++) co.c[k] = ((uint64_t)blk[2 * k + 1] << 32) | blk[2 * k];
     return co;
+}
+
+// one independent draw per item (the single combined check of hbls_rlc_partial / hbls_rlc_fold)
+std::vector<uint64_t> rlc_draw_items(size_t k) {
+    std::vector<uint64_t> c(k); const uint64_t call = ++g.rlc_calls; uint32_t blk[16];
+    for (size_t j = 0; j < k; j++) {
+        if ((j & 7) == 0) chacha20_block(g.chacha_key, call, blk, (uint32_t)(j >> 3) + 1);
+        c[j] = ((uint64_t)blk[2 * (j & 7) + 1] << 32) | blk[2 * (j & 7)];
+    }
+    return c;
 }
 
 // ------------------------------------------------------------------ one verification pass over device-resident inputs.
@@ -168,7 +178,7 @@ void launch_verify_tail(size_t B, const VerifyBufs& v, Scratch* sc, const uint8_
         const size_t G = (g.rlc_g == 4 || g.rlc_g == 8) ? (size_t)g.rlc_g : (2 * (B / 8) >= (size_t)g.sm_count * HB_TPB_SPLIT ? 8 : 4);
         const size_t ng = B / G, nr = ng * G, tail = B - nr;
         const rlc_coeffs co = rlc_draw();
-        LAUNCH(k_rlc_scale, heavy_blocks(nr), TPB, s, nr, ng, v.apk, v.sig, v.hm, v.ok_sig, v.ok_hm, ok_pk, co, v.pk_scaled, v.S, v.bad);
+        LAUNCH(k_rlc_scale, heavy_blocks(nr), TPB, s, nr, ng, v.apk, v.sig, v.hm, v.ok_sig, v.ok_hm, ok_pk, co, (const uint64_t*)nullptr, v.pk_scaled, v.S, v.bad);
         const bool full = 2 * ng >= (size_t)g.sm_count * HB_TPB_SPLIT;
         const unsigned pb = full ? split_blocks(2 * ng) : blocks_for(2 * ng, 64), pt = full ? HB_TPB_SPLIT : 64;
         if (G == 8) {
@@ -874,6 +884,71 @@ int hbls_ballot_box_aggregate(const hbls_ballot_box* b, uint8_t out_sig96[96], u
     return 0;
 }
 
+// ------------------------------------------------------------------ ONE batch split over several GPUs (BASELINE configs[3])
+struct PartialRecord { g2 S; fp2 f[6]; uint32_t n_items; uint32_t n_bad; };
+static_assert(sizeof(PartialRecord) == HBLS_PARTIAL_BYTES, "partial record layout");
+int hbls_rlc_partial(size_t k, const uint8_t* pk48, const uint8_t* sig96, const uint8_t* msgs, size_t msg_len, uint8_t record[HBLS_PARTIAL_BYTES]) {
+    if (int e = ensure_init()) return e;
+    if (!record) return HBLS_ERR_ARG;
+    PartialRecord rec; memset(&rec, 0, sizeof rec);
+    std::lock_guard<std::mutex> lk(g.mu);
+    const size_t kk = k ? k : 1;
+    const unsigned W = (unsigned)(kk < (size_t)g.sm_count * 2 ? kk : (size_t)g.sm_count * 2);      // warps that multiply Miller values into partial products
+    Scratch* sc; if (int e = reserve(g.stream, verify_scratch_bytes(kk) + kk * (48 + 96 + msg_len + 8) + (W + 2) * 6 * sizeof(fp2) + sizeof(g2) + 8192, &sc)) return e;
+    Arena ar{sc->base, 0, sc->cap};
+    VerifyBufs v = carve_verify(ar, kk);
+    uint8_t* dpk = ar.take<uint8_t>(kk * 48); uint8_t* dsig = ar.take<uint8_t>(kk * 96); uint8_t* dmsg = ar.take<uint8_t>(kk * msg_len + 1);
+    uint64_t* dco = ar.take<uint64_t>(kk); fp2* dpart = ar.take<fp2>((size_t)W * 6); fp2* dprod = ar.take<fp2>(6); g2* dS = ar.take<g2>(1);
+    if (k) {
+        const std::vector<uint64_t> co = rlc_draw_items(k);
+        CK(cudaMemcpyAsync(dpk, pk48, k * 48, cudaMemcpyHostToDevice, g.stream));
+        CK(cudaMemcpyAsync(dsig, sig96, k * 96, cudaMemcpyHostToDevice, g.stream));
+        if (msg_len) CK(cudaMemcpyAsync(dmsg, msgs, k * msg_len, cudaMemcpyHostToDevice, g.stream));
+        CK(cudaMemcpyAsync(dco, co.data(), k * 8, cudaMemcpyHostToDevice, g.stream));
+        CK(cudaStreamSynchronize(g.stream));                    // co is a local: the copy must have read it before it goes out of scope
+    }
+    CK(cudaMemsetAsync(v.counts, 0, 2 * sizeof(unsigned), g.stream));
+    LAUNCH(k_g1_decode_jac, heavy_blocks(kk), TPB, g.stream, k, dpk, v.apk, v.ok_pk, 1);
+    const bool pairs = (long long)k <= g.coop_max;
+    if (pairs) { LAUNCH(k_g2_decode_pair, blocks_for(2 * kk, 32), 32, g.stream, k, dsig, v.sig, v.ok_sig, 1); LAUNCH(k_hash_to_g2_pair, blocks_for(2 * kk, 32), 32, g.stream, k, dmsg, (uint32_t)msg_len, v.hm, v.ok_hm); }
+    else { LAUNCH(k_g2_decode, heavy_blocks(kk), TPB, g.stream, k, dsig, v.sig, v.ok_sig, 1); LAUNCH(k_hash_to_g2, heavy_blocks(kk), TPB, g.stream, k, dmsg, (uint32_t)msg_len, v.hm, v.ok_hm); }
+    rlc_coeffs none{};
+    LAUNCH(k_rlc_scale, heavy_blocks(kk), TPB, g.stream, k, (size_t)1, v.apk, v.sig, v.hm, v.ok_sig, v.ok_hm, (const uint8_t*)v.ok_pk, none, (const uint64_t*)dco, v.pk_scaled, v.S, v.bad);
+    LAUNCH(k_rlc_partial_coop, W, 32, g.stream, k, v.pk_scaled, v.hm, v.bad, dpart, v.counts);
+    LAUNCH(k_rlc_reduce_coop, 1, 32, g.stream, (size_t)W, dpart, dprod);
+    LAUNCH(k_g2_sum_jac, 1, HB_SUM_THREADS, g.stream, k, v.S, dS);
+    unsigned counts[2] = {0, 0};
+    CK(cudaMemcpyAsync(&rec.S, dS, sizeof(g2), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaMemcpyAsync(rec.f, dprod, 6 * sizeof(fp2), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaMemcpyAsync(counts, v.counts, sizeof counts, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    rec.n_items = (uint32_t)k; rec.n_bad = counts[0];
+    memcpy(record, &rec, sizeof rec);
+    return 0;
+}
+int hbls_rlc_fold(size_t n, const uint8_t* records) {
+    if (int e = ensure_init()) return e;
+    if (!records) return HBLS_ERR_ARG;
+    size_t items = 0, bad = 0;
+    for (size_t p = 0; p < n; p++) { PartialRecord r; memcpy(&r, records + p * sizeof r, sizeof r); items += r.n_items; bad += r.n_bad; }
+    if (bad || items == 0) return 0;                                  // an undecodable / identity item somewhere, or nothing to prove: callers verify exactly
+    std::lock_guard<std::mutex> lk(g.mu);
+    Scratch* sc; if (int e = reserve(g.stream, n * (sizeof(g2) + 6 * sizeof(fp2)) + sizeof(g2) + sizeof(g2a) + 4096, &sc)) return e;
+    Arena ar{sc->base, 0, sc->cap};
+    g2* dS = ar.take<g2>(n); fp2* dparts = ar.take<fp2>(n * 6); g2* dsum = ar.take<g2>(1); g2a* dsg = ar.take<g2a>(1); uint8_t* dres = ar.take<uint8_t>(1);
+    std::vector<g2> hs(n); std::vector<fp2> hf(n * 6);
+    for (size_t p = 0; p < n; p++) { PartialRecord r; memcpy(&r, records + p * sizeof r, sizeof r); hs[p] = r.S; for (int i = 0; i < 6; i++) hf[6 * p + i] = r.f[i]; }
+    CK(cudaMemcpyAsync(dS, hs.data(), n * sizeof(g2), cudaMemcpyHostToDevice, g.stream));
+    CK(cudaMemcpyAsync(dparts, hf.data(), n * 6 * sizeof(fp2), cudaMemcpyHostToDevice, g.stream));
+    LAUNCH(k_g2_sum_jac, 1, HB_SUM_THREADS, g.stream, n, dS, dsum);
+    LAUNCH(k_g2_normalize, 1, 32, g.stream, (size_t)1, dsum, dsg);
+    LAUNCH(k_rlc_fold_coop, 1, 32, g.stream, n, dparts, dsg, dres);
+    uint8_t res = 0;
+    CK(cudaMemcpyAsync(&res, dres, 1, cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));                              // hs / hf stay alive until the copies are done
+    return res ? 1 : 0;
+}
+
 int hbls_sign_hash_batch(size_t k, const uint8_t* sk32, const uint8_t* msgs, size_t msg_len, uint8_t* sig96_out, uint8_t* ok) {
     if (int e = ensure_init()) return e;
     if (k == 0) return 0;
@@ -959,12 +1034,10 @@ double hbls_probe_mac32_per_s(int iters, double* sm_clock_hz) {
     cudaEventRecord(e0, g.stream);
     LAUNCH(k_probe_carry<K>, blocks, threads, g.stream, iters, 12345u, sink, cyc);
     cudaEventRecord(e1, g.stream);
-    unsigned long long cycles = 0;
-    cudaMemcpyAsync(&cycles, cyc, sizeof cycles, cudaMemcpyDeviceToHost, g.stream);
     if (cudaStreamSynchronize(g.stream) != cudaSuccess) return -1.0;
     float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    if (sm_clock_hz) *sm_clock_hz = (double)cycles / (ms * 1e-3);      // thread 0's loop spans (nearly) the whole launch
+    if (sm_clock_hz) { int khz = 0; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, g.device); *sm_clock_hz = khz * 1e3; }   // maximum SM clock
     double macs = (double)blocks * threads * (double)iters * K * 6.0;  // lane_mad = 6 IMAD.WIDE
     return macs / (ms * 1e-3);
 }

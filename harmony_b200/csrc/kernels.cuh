@@ -172,12 +172,14 @@ __global__ void __launch_bounds__(HB_SUM_THREADS) k_g2_sum(size_t n, const g2a* 
 }
 
 // ---- message -> G2 (hash part of R6/R7), affine output
-// HB_BATCH_INV (experimental, off): a persistent thread converts HB_BATCH_K of its items to affine with ONE inversion
+// HB_BATCH_INV: a persistent thread shares ONE inversion among HB_BATCH_K of its items (Montgomery's trick) -- both inversions of
+// hash-to-G2 and the affine conversion of the coefficient-scaling stage.  Measured on B200 at 303 104 rounds/step (profiles/
+// r2_stage_times.txt): off 251.3 ms, K = 4 248.2 ms, K = 8 243.2 ms per step.
 #ifndef HB_BATCH_INV
-#define HB_BATCH_INV 0
+#define HB_BATCH_INV 1
 #endif
 #ifndef HB_BATCH_K
-#define HB_BATCH_K 4
+#define HB_BATCH_K 8
 #endif
 __global__ void k_hash_to_g2(size_t n, const uint8_t* msgs, uint32_t msg_len, g2a* out, uint8_t* ok) {
 #if HB_BATCH_INV
@@ -209,14 +211,14 @@ __global__ void k_hash_to_g2(size_t n, const uint8_t* msgs, uint32_t msg_len, g2
         out[i] = a; ok[i] = good[k] ? 1 : 0;
     }
   }
-  return;
-#endif
+#else
   for (size_t i = HB_TID; i < n; i += HB_STRIDE) {
     g2 h; bool good = map_to_g2(h, msgs + (size_t)msg_len * i, msg_len);
     g2a a;
     if (!good) { fp2_zero(a.x); fp2_zero(a.y); } else pt_to_aff(a, h);
     out[i] = a; ok[i] = good ? 1 : 0;
   }
+#endif
 }
 
 // ---- lane-pair forms of decode / hash for small batches (latency path, hbls.cu: B <= coop_max): one item per LANE PAIR.  The Fp-only
@@ -353,6 +355,94 @@ __global__ void __launch_bounds__(32) k_pairing_coop(size_t B, const g2a* sig, c
     }
 }
 
+// ---- ONE batch split over several GPUs (BASELINE configs[3]): every rank turns its slice into a fixed-size partial record
+// { sum_j r_j sigma_j (G2) , prod_j f_{|z|, H_j}(-r_j pk_j) (Fp12, no final exponentiation) , bad count }; the records are all-gathered
+// (NCCL) and every rank folds them identically: prod of the partial products x Miller(B, sum of the partial sums), ONE final
+// exponentiation.  EC addition / Fp12 multiplication are not NCCL reduction operators, hence all-gather + local fold.
+// A warp multiplies the Miller values of its items (w, w + W, ...) into the VM register A; bad / identity items only count.
+__global__ void __launch_bounds__(32) k_rlc_partial_coop(size_t n, const g1a* pk_scaled_neg, const g2a* hm, const uint8_t* bad,
+                                                         fp2* partial /* 6 per warp, tower order */, unsigned* bad_count) {
+    __shared__ uint32_t slots[VM_SMEM_WORDS];
+    const int lane = threadIdx.x & 31;
+    vm_load_consts(slots);
+    vm_run(VM_P_A_ONE, slots);
+    for (size_t j = blockIdx.x; j < n; j += gridDim.x) {
+        bool zero = true;
+        if (lane < 4) {
+            fp2 v; fp2_zero(v);
+            const g1a pk = pk_scaled_neg[j];
+            if (lane == 0) v.a = pk.x; else if (lane == 1) v.a = pk.y; else if (lane == 2) v = hm[j].x; else v = hm[j].y;
+            vm_set_fp2(slots, VM_R_P2X + lane, v);
+            zero = fp_is_zero(v.a) & fp_is_zero(v.b);
+        }
+        const unsigned zmask = __ballot_sync(0xffffffffu, zero);
+        const bool skip = bad[j] != 0 || (zmask & 0x3) == 0x3 || (zmask & 0xc) == 0xc;
+        if (skip) { if (lane == 0) atomicAdd(bad_count, 1u); __syncwarp(); continue; }
+        vm_run(VM_P_ML1_INIT, slots);
+        for (int i = 62; i >= 0; i--) {
+            vm_run(VM_P_ML1_DBL, slots);
+            if ((K_Z_ABS >> i) & 1) vm_run(VM_P_ML1_ADD, slots);
+        }
+        vm_run(VM_P_AMULF, slots);
+    }
+    if (lane < 12) vm_ld(reinterpret_cast<fp*>(&partial[6 * (size_t)blockIdx.x + (lane >> 1)])[lane & 1].l, slots, VM_R_A0 + (lane >> 1), lane & 1);
+}
+// product of W partial products (one warp)
+__global__ void __launch_bounds__(32) k_rlc_reduce_coop(size_t W, const fp2* partial, fp2* out) {
+    __shared__ uint32_t slots[VM_SMEM_WORDS];
+    const int lane = threadIdx.x & 31;
+    vm_load_consts(slots);
+    vm_run(VM_P_A_ONE, slots);
+    for (size_t w = 0; w < W; w++) {
+        if (lane < 12) vm_st(slots, VM_R_F0 + (lane >> 1), lane & 1, reinterpret_cast<const fp*>(&partial[6 * w + (lane >> 1)])[lane & 1].l);
+        __syncwarp();
+        vm_run(VM_P_AMULF, slots);
+    }
+    if (lane < 12) vm_ld(reinterpret_cast<fp*>(&out[lane >> 1])[lane & 1].l, slots, VM_R_A0 + (lane >> 1), lane & 1);
+}
+// fold: verdict = FE( prod_p parts[p] * Miller(B, Sg) ) == 1, Sg = affine sum of the partial signature sums (not the identity)
+__global__ void __launch_bounds__(32) k_rlc_fold_coop(size_t nparts, const fp2* parts, const g2a* Sg, uint8_t* result) {
+    __shared__ uint32_t slots[VM_SMEM_WORDS];
+    const int lane = threadIdx.x & 31;
+    vm_load_consts(slots);
+    vm_run(VM_P_A_ONE, slots);
+    for (size_t w = 0; w < nparts; w++) {
+        if (lane < 12) vm_st(slots, VM_R_F0 + (lane >> 1), lane & 1, reinterpret_cast<const fp*>(&parts[6 * w + (lane >> 1)])[lane & 1].l);
+        __syncwarp();
+        vm_run(VM_P_AMULF, slots);
+    }
+    bool zero = true;
+    if (lane < 4) {
+        fp2 v; fp2_zero(v);
+        if (lane == 0) fp_set(v.a, K_G1_X); else if (lane == 1) fp_set(v.a, K_G1_Y); else if (lane == 2) v = Sg->x; else v = Sg->y;
+        vm_set_fp2(slots, VM_R_P2X + lane, v);
+        zero = fp_is_zero(v.a) & fp_is_zero(v.b);
+    }
+    const unsigned zmask = __ballot_sync(0xffffffffu, zero);
+    if ((zmask & 0xc) == 0xc) { if (lane == 0) *result = 0; return; }       // empty / cancelling signature sum: not proven, callers fall back
+    vm_run(VM_P_ML1_INIT, slots);
+    for (int i = 62; i >= 0; i--) {
+        vm_run(VM_P_ML1_DBL, slots);
+        if ((K_Z_ABS >> i) & 1) vm_run(VM_P_ML1_ADD, slots);
+    }
+    vm_run(VM_P_FMULA, slots);
+    const bool one = vm_final_exp_is_one(slots);
+    if (lane == 0) *result = one ? 1 : 0;
+}
+// Jacobian G2 sum, single CTA (the partial signature sums)
+__global__ void __launch_bounds__(HB_SUM_THREADS) k_g2_sum_jac(size_t n, const g2* in, g2* out) {
+    __shared__ g2 sm[HB_SUM_THREADS];
+    g2 acc; pt_set_inf(acc);
+    for (size_t i = threadIdx.x; i < n; i += HB_SUM_THREADS) { g2 q = in[i]; pt_add(acc, acc, q); }
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = HB_SUM_THREADS / 2; off >= 1; off >>= 1) {
+        if ((int)threadIdx.x < off) { g2 o = sm[threadIdx.x + off]; pt_add(acc, acc, o); sm[threadIdx.x] = acc; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[0] = acc;
+}
+
 // ------------------------------------------------------------------ random-linear-combination batch (R9 / R10 GPU form)
 // prod_j [ e(B, sigma_j) e(-apk_j, H_j) ]^{r_j} == 1 with 64-bit r_j: the G rounds of a group share ONE Miller accumulator
 // (pairs (-r_j apk_j, H_j) plus (B, sum_j r_j sigma_j)) and ONE final exponentiation.  The rounds of a group that fails -- or
@@ -370,7 +460,9 @@ __global__ void __launch_bounds__(32) k_pairing_coop(size_t B, const g2a* sig, c
 struct rlc_coeffs { uint64_t c[HB_RLC_GMAX]; };
 // per round: P_j = -r_j apk_j (affine), S_j = r_j sigma_j (Jacobian), bad_j
 __global__ void k_rlc_scale(size_t B, size_t ng, const g1* apk, const g2a* sig, const g2a* hm, const uint8_t* ok_sig, const uint8_t* ok_hm,
-                            const uint8_t* ok_pk, rlc_coeffs co, g1a* pk_scaled_neg, g2* S, uint8_t* bad) {
+                            const uint8_t* ok_pk, rlc_coeffs co, const uint64_t* per_item, g1a* pk_scaled_neg, g2* S, uint8_t* bad) {
+  // per_item (nullable): one independent coefficient per round -- needed when ALL rounds enter one combined check (the split of a
+  // single batch over several GPUs, k_rlc_partial_coop); the grouped form shares co.c[position in group] across groups
 #if HB_BATCH_INV
   for (size_t j0 = HB_TID; j0 < B; j0 += (size_t)HB_BATCH_K * HB_STRIDE) {
     g1 ra[HB_BATCH_K]; fp z[HB_BATCH_K]; bool skip[HB_BATCH_K];
@@ -378,7 +470,7 @@ __global__ void k_rlc_scale(size_t B, size_t ng, const g1* apk, const g2a* sig, 
         const size_t j = j0 + (size_t)k * HB_STRIDE;
         skip[k] = true;
         if (j >= B) continue;
-        const uint64_t r = co.c[j / ng];
+        const uint64_t r = per_item ? per_item[j] : co.c[j / ng];
         g1 a = apk[j]; g2a sg = sig[j]; g2a h = hm[j];
         const bool b = !ok_sig[j] || !ok_hm[j] || (ok_pk && !ok_pk[j]) || pt_is_inf(a) || aff_is_inf(sg) || aff_is_inf(h);
         g2 rs; rlc_scale_pair(ra[k], rs, a, sg, r);
@@ -395,16 +487,16 @@ __global__ void k_rlc_scale(size_t B, size_t ng, const g1* apk, const g2a* sig, 
         pk_scaled_neg[j] = pa;
     }
   }
-  return;
-#endif
+#else
   for (size_t j = HB_TID; j < B; j += HB_STRIDE) {
-    const uint64_t r = co.c[j / ng];
+    const uint64_t r = per_item ? per_item[j] : co.c[j / ng];
     g1 a = apk[j]; g2a sg = sig[j]; g2a h = hm[j];
     const bool b = !ok_sig[j] || !ok_hm[j] || (ok_pk && !ok_pk[j]) || pt_is_inf(a) || aff_is_inf(sg) || aff_is_inf(h);
     g1 ra; g2 rs; rlc_scale_pair(ra, rs, a, sg, r);
     g1a pa; pt_to_aff(pa, ra); fp_neg(pa.y, pa.y);
     pk_scaled_neg[j] = pa; S[j] = rs; bad[j] = b ? 1 : 0;
   }
+#endif
 }
 // per group: affine sum of its S_j
 template <int G> __global__ void k_rlc_group_sum(size_t ngroups, const g2* S, g2a* Sg) {

@@ -114,7 +114,7 @@ HB_DEV void vm_set_fp2(uint32_t* slots, int s, const fp2& v) { vm_st(slots, s, 0
 HB_DEV void vm_load_consts(uint32_t* slots) {
     const int lane = threadIdx.x & 31;
     if (lane == 0) { fp o; fp_one(o); vm_set_fp(slots, VM_R_ONE, o); }
-    if (lane == 1) { fp2 b; fp2_const(b, K_B2_3); vm_set_fp2(slots, VM_R_B3, b); }
+    if (lane == 1) { fp2 b; fp2_const(b, K_B2_3); vm_set_fp2(slots, VM_R_TWIST3B, b); }
     if (lane == 2) { fp h; fp_set(h, K_INV2); vm_set_fp(slots, VM_R_INV2, h); }
     if (lane >= 3 && lane < 9) { fp2 g; fp2_const(g, K_FROB1[lane - 3]); vm_set_fp2(slots, VM_R_FROB1_0 + (lane - 3), g); }
     if (lane >= 9 && lane < 15) { fp g; fp_set(g, K_FROB2[lane - 9]); vm_set_fp(slots, VM_R_FROB2_0 + (lane - 9), g); }
@@ -127,15 +127,10 @@ HB_DEV void vm_expz(uint32_t* slots) {
         if ((K_Z_ABS >> i) & 1) vm_run(VM_P_MULX, slots);
     }
 }
-// e(P1, Q1) e(P2, Q2) == 1 ?  Inputs already in the slots P1X .. Q2Y (affine, none the identity); returns the verdict to every lane.
-HB_NOINLINE bool vm_pairing_check(uint32_t* slots) {
+// F^(3 (p^12 - 1) / r) == 1 ?  Verdict to every lane.  Easy part around ONE Fp inversion (binary GCD on one lane), hard part = five
+// x^|z| chains.
+HB_NOINLINE bool vm_final_exp_is_one(uint32_t* slots) {
     const int lane = threadIdx.x & 31;
-    vm_run(VM_P_ML_INIT, slots);
-    for (int i = 62; i >= 0; i--) {
-        vm_run(VM_P_ML_DBL, slots);
-        if ((K_Z_ABS >> i) & 1) vm_run(VM_P_ML_ADD, slots);
-    }
-    // final exponentiation: easy part around ONE Fp inversion (binary GCD on one lane), hard part = five x^|z| chains
     vm_run(VM_P_FE_INV_A, slots);
     if (lane == 0) {
         fp n, ni; vm_ld(n.l, slots, VM_R_NORM, 0);
@@ -158,6 +153,15 @@ HB_NOINLINE bool vm_pairing_check(uint32_t* slots) {
         for (int j = 0; j < 12; j++) diff |= v.l[j] ^ (lane == 0 ? one.l[j] : 0u);
     }
     return __ballot_sync(0xffffffffu, diff != 0) == 0;
+}
+// e(P1, Q1) e(P2, Q2) == 1 ?  Inputs already in the slots P1X .. Q2Y (affine, none the identity); returns the verdict to every lane.
+HB_NOINLINE bool vm_pairing_check(uint32_t* slots) {
+    vm_run(VM_P_ML_INIT, slots);
+    for (int i = 62; i >= 0; i--) {
+        vm_run(VM_P_ML_DBL, slots);
+        if ((K_Z_ABS >> i) & 1) vm_run(VM_P_ML_ADD, slots);
+    }
+    return vm_final_exp_is_one(slots);
 }
 
 }  // namespace hb

@@ -199,6 +199,18 @@ int  hbls_ballot_box_add_vote(hbls_ballot_box* b, const uint8_t* signer_bitmap, 
 /* aggregate signature of the collected votes + their bitmap (construct.go:158-175 constructQuorumSigAndBitmap) */
 int  hbls_ballot_box_aggregate(const hbls_ballot_box* b, uint8_t out_sig96[96], uint8_t* bitmap_out, size_t blen);
 
+/* ONE batch split over several GPUs (BASELINE configs[3] "sharded across 8 x B200 with NCCL G1/G2 partial-sum allreduce").
+ * Rank g turns its slice of independent (pk, msg, sig) triples into a fixed-size partial record
+ *     { sum_j r_j sigma_j (G2 Jacobian, 288 B) ; prod_j Miller(-r_j pk_j, H(m_j)) (Fp12, 576 B, no final exponentiation) ; item / bad counts }
+ * with one fresh 64-bit coefficient per item; the ranks all-gather the records (EC addition and Fp12 multiplication are not NCCL
+ * reduction operators, so the "allreduce" is an all-gather + identical local fold: harmony_b200/shard.py) and hbls_rlc_fold
+ * multiplies the partial products, adds Miller(B, sum of the partial sums) and runs ONE final exponentiation.
+ * fold returns 1 = every item of every slice is valid (error probability <= 2^-63), 0 = not proven (some item is invalid or did not
+ * decode: every rank then verifies its own slice exactly with hbls_verify_batch), < 0 error. */
+#define HBLS_PARTIAL_BYTES 872
+int hbls_rlc_partial(size_t k, const uint8_t* pk48, const uint8_t* sig96, const uint8_t* msgs, size_t msg_len, uint8_t record[HBLS_PARTIAL_BYTES]);
+int hbls_rlc_fold(size_t n_records, const uint8_t* records);
+
 /* batched SignHash / GetPublicKey (consensus/construct.go:97-114 with multibls keys) ; ok[j] = 1/0 */
 int hbls_sign_hash_batch(size_t k, const uint8_t* sk32, const uint8_t* msgs, size_t msg_len, uint8_t* sig96_out, uint8_t* ok);
 int hbls_get_public_key_batch(size_t k, const uint8_t* sk32, uint8_t* pk48_out);
@@ -225,9 +237,10 @@ void hbls_stage_timing_enable(int on);
 int hbls_stage_timing_get(float* ms_out, int max_stages);
 /* integer-pipe probe: every thread of a chip-filling grid runs `iters` rounds of the field multiplier's own carry-chained
  * mad.lo.cc / madc.hi.cc rows (IMAD.WIDE.U32.X, 4 independent accumulator sets) and the call returns the achieved 32x32+64
- * MACs per second; *sm_clock_hz (nullable) receives the SM clock measured under that load (clock64 / CUDA-event time).
+ * MACs per second; *sm_clock_hz (nullable) receives the device's maximum SM clock (cudaDevAttrClockRate).
  * Roofline denominator: an IMAD.WIDE holds the FMA-heavy pipe for 4 cycles per warp (profiles/r2_probe_int.*), so the
- * pipe peak is sm_count * 4 schedulers * 8 MAC/clk * sm_clock_hz; the probe itself reaches about 90 % of it.  <0 on error */
+ * pipe peak is sm_count * 4 schedulers * 8 MAC/clk * SM clock (bench.py uses the clock nvidia-smi reports under load);
+ * the probe itself reaches about 90 % of it.  <0 on error */
 double hbls_probe_mac32_per_s(int iters, double* sm_clock_hz);
 
 #ifdef __cplusplus

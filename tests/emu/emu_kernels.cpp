@@ -67,7 +67,7 @@ template <int G> static int aggregate_verify_batch(int mode, uint32_t n, const u
         const size_t ng = B / G, nr = ng * G, tail = B - nr;
         rlc_coeffs co;                                          // stands in for the host's ChaCha20 draw (hbls.cu rlc_draw)
         for (int k = 0; k < HB_RLC_GMAX; k++) { uint64_t x = s0 + 0x9e3779b97f4a7c15ull * (uint64_t)(k + 1); x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x ^= s1; co.c[k] = x; }
-        run_seq(2, 2, [&] { k_rlc_scale(nr, ng, apk.data(), sig.data(), hm.data(), ok_sig.data(), ok_hm.data(), (const uint8_t*)nullptr, co, pk_scaled.data(), S.data(), bad.data()); });
+        run_seq(2, 2, [&] { k_rlc_scale(nr, ng, apk.data(), sig.data(), hm.data(), ok_sig.data(), ok_hm.data(), (const uint8_t*)nullptr, co, (const uint64_t*)nullptr, pk_scaled.data(), S.data(), bad.data()); });
         run_seq(1, 2, [&] { k_rlc_group_sum<G>(ng, S.data(), Sg.data()); });
         run_pair([&] { k_rlc_pairing_split<G>(ng, pk_scaled.data(), hm.data(), Sg.data(), bad.data(), group_ok.data()); });
         std::vector<uint32_t> list(B); unsigned counts[2] = {0, 0};
@@ -110,7 +110,7 @@ extern "C" int emu_stage_counts(uint32_t n, const uint8_t* pks48, size_t B, cons
     run_seq(1, 4, [&] { k_hash_to_g2(B, msgs, msg_len, hm.data(), ok_hm.data()); }); mark();
     const size_t ng = B / G, nr = ng * G;
     rlc_coeffs co; for (int k = 0; k < HB_RLC_GMAX; k++) co.c[k] = 0x9e3779b97f4a7c15ull * (uint64_t)(k + 3) ^ 0x5851f42d4c957f2dull;
-    run_seq(1, 4, [&] { k_rlc_scale(nr, ng, apk.data(), sig.data(), hm.data(), ok_sig.data(), ok_hm.data(), (const uint8_t*)nullptr, co, pk_scaled.data(), S.data(), bad.data()); });
+    run_seq(1, 4, [&] { k_rlc_scale(nr, ng, apk.data(), sig.data(), hm.data(), ok_sig.data(), ok_hm.data(), (const uint8_t*)nullptr, co, (const uint64_t*)nullptr, pk_scaled.data(), S.data(), bad.data()); });
     if (G == 8) run_seq(1, 2, [&] { k_rlc_group_sum<8>(ng, S.data(), Sg.data()); }); else run_seq(1, 2, [&] { k_rlc_group_sum<4>(ng, S.data(), Sg.data()); });
     mark();
     return 0;

@@ -104,7 +104,7 @@ def test_stage_counts_pinned(emuk, oracle, request):
     batch_inv = "batch_inv" in request.node.name
     sks = bench.make_committee_sks()
     pks = [oracle.get_public_key(wl.sk_bytes(k)) for k in sks]
-    B = 24
+    B = 32
     bitmaps, agg_sk, msgs, nsig = bench.make_rounds(sks, B, seed=2024)
     sigs = b"".join(oracle.sign_hash(agg_sk[32 * j:32 * j + 32], msgs[48 * j:48 * j + 48]) for j in range(B))
     emuk.emu_stage_counts.argtypes = [ctypes.c_uint32, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_char_p,

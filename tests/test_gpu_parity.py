@@ -680,3 +680,36 @@ def test_device_entry_on_two_streams(gbls):
     assert A[3].cpu().numpy().tobytes() == b"\x01" * B
     r = Bt[3].cpu().numpy().tobytes()
     assert {j for j in range(B) if r[j] == 0} == bad
+
+def test_split_batch_partial_records_fold(gbls, oracle):
+    """SURVEY 8e / BASELINE configs[3]: ONE batch split over ranks.  Two slices processed one after the other on this GPU stand for
+    two ranks: their 872-byte partial records { sum r sigma, product of Miller values } fold to "all valid" exactly when every triple
+    of both slices verifies; a wrong message, a swapped key or an undecodable signature in either slice makes the fold fail, and the
+    single-rank protocol (shard.verify_triples_split) then returns the exact per-item booleans."""
+    from harmony_b200 import shard
+    k = 96
+    sks = b"".join(wl.sk_bytes(wl.seeded_sk("split", i)) for i in range(k))
+    msgs = b"".join(wl.seeded_bytes("split/m", i, 32) for i in range(k))
+    pks = gbls.GetPublicKeyBatch(sks)
+    sigs, ok = gbls.SignHashBatch(sks, msgs, 32)
+    cut = 41
+    def recs(p, s, m): return [gbls.RlcPartial(p[:48 * cut], s[:96 * cut], m[:32 * cut], 32), gbls.RlcPartial(p[48 * cut:], s[96 * cut:], m[32 * cut:], 32)]
+    r = recs(pks, sigs, msgs)
+    assert all(len(x) == gbls.PARTIAL_BYTES for x in r)
+    assert gbls.RlcFold(r) is True and gbls.RlcFold([r[0]]) is True and gbls.RlcFold([r[1]]) is True
+    assert gbls.RlcFold(recs(pks, sigs, msgs)) is True                                 # fresh coefficients every call
+    m2 = bytearray(msgs); m2[32 * 70 + 3] ^= 1
+    assert gbls.RlcFold(recs(pks, sigs, bytes(m2))) is False
+    p2 = bytearray(pks); p2[48 * 5:48 * 6] = pks[48 * 6:48 * 7]
+    assert gbls.RlcFold(recs(bytes(p2), sigs, msgs)) is False
+    s2 = bytearray(sigs); s2[96 * 90:96 * 91] = b"\xff" * 96
+    assert gbls.RlcFold(recs(pks, bytes(s2), msgs)) is False
+    # errors that cancel under EQUAL coefficients do not cancel here: swap two signatures (sum of signatures unchanged)
+    s3 = bytearray(sigs); s3[96 * 10:96 * 11], s3[96 * 11:96 * 12] = sigs[96 * 11:96 * 12], sigs[96 * 10:96 * 11]
+    assert gbls.RlcFold(recs(pks, bytes(s3), msgs)) is False
+    # the protocol on one rank
+    res, settled = shard.verify_triples_split(pks, sigs, msgs, 32)
+    assert res == b"\x01" * k and settled is True
+    res, settled = shard.verify_triples_split(pks, bytes(s3), bytes(m2), 32)
+    assert settled is False and [i for i in range(k) if res[i] == 0] == [10, 11, 70]
+    assert res == bytes(1 if oracle.verify_hash(bytes(s3[96 * i:96 * i + 96]), pks[48 * i:48 * i + 48], bytes(m2[32 * i:32 * i + 32])) else 0 for i in range(k))

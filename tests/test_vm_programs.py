@@ -34,6 +34,27 @@ def test_vm_pairing_valid_and_invalid(vm, progs):
     _, _, npk2, _ = _instance(0x77, b"vm-test-message-0123456789abcdef")
     assert vm.vm_pairing_is_one(progs, gen, sa, npk2, ha) is False
 
+def test_vm_slots_reused_across_rounds(vm, progs):
+    """A warp verifies many rounds on the same slots: no program may depend on what an earlier round left behind (a register
+    named like a constant once made the second round of every warp fail)."""
+    a = _instance(0x123, b"m1..............................")
+    b = _instance(0x456, b"m2..............................")
+    s = vm.fresh_slots()
+    def run(p1, q1, p2, q2):
+        for reg, v in (("P1X", (p1[0], 0)), ("P1Y", (p1[1], 0)), ("Q1X", q1[0]), ("Q1Y", q1[1]), ("P2X", (p2[0], 0)), ("P2Y", (p2[1], 0)), ("Q2X", q2[0]), ("Q2Y", q2[1])):
+            s[vm.SLOT[reg]] = (v[0] % vm.P, v[1] % vm.P)
+        vm.run_program(progs["ML_INIT"], s)
+        for i in range(62, -1, -1):
+            vm.run_program(progs["ML_DBL"], s)
+            if (vm.Z_ABS >> i) & 1: vm.run_program(progs["ML_ADD"], s)
+        vm.final_exp_vm(progs, s)
+        return [s[vm.SLOT[r]] for r in vm.r6("ACC")] == [(1, 0)] + [(0, 0)] * 5
+    assert [run(*a), run(*b), run(a[0], a[1], b[2], b[3]), run(*a)] == [True, True, False, True]
+    ro = {vm.SLOT[r] for r in vm.REG_CONST + vm.REG_IN}
+    for p in progs.values():
+        for cls, ins in p.steps:
+            assert not ({i[0] for i in ins} & ro), "a program writes a constant / input register"
+
 def test_vm_final_exp_matches_oracle_value(vm, progs):
     """The Fp12 value after the VM's final exponentiation equals the oracle's f^(3 (p^12 - 1) / r) on a Miller-loop output
     (same cube-of-the-pairing convention as pairing.cuh), checked through  r_vm == 1  <=>  r_oracle == 1 and by cubing."""
@@ -72,3 +93,19 @@ def test_vm_header_is_current(vm, progs, tmp_path):
     out = tmp_path / "vm_programs.cuh"
     vm.emit(progs, str(out))
     assert out.read_text() == open(os.path.join(ROOT, "harmony_b200", "csrc", "vm_programs.cuh")).read(), "run python tools/vmgen.py"
+
+def test_vm_split_product(vm, progs):
+    """Single-pair Miller programs + running product (the multi-GPU split of one batch): two parts of pairs whose overall product
+    is 1 -- e(B, s1 + s2) e(-pk1, H1) e(-pk2, H2) -- and the same with one wrong message."""
+    import pyref as o
+    inst = [(0x1111, b"split-message-one................"), (0x2222, b"split-message-two................")]
+    sigs = [o.sign_hash(sk, m) for sk, m in inst]
+    ssum = o.pt_affine(o.FP2, o.pt_add(o.FP2, sigs[0], sigs[1]))
+    gen = o.pt_affine(o.FP, o.G1_GEN)
+    def neg_pk(sk): return o.pt_affine(o.FP, o.pt_neg(o.FP, o.get_public_key(sk)))
+    def hm(m): return o.pt_affine(o.FP2, o.map_to_g2(m))
+    part0 = [(neg_pk(inst[0][0]), hm(inst[0][1]))]
+    part1 = [(neg_pk(inst[1][0]), hm(inst[1][1])), (gen, ssum)]
+    assert vm.vm_product_is_one(progs, [part0, part1]) is True
+    bad1 = [(neg_pk(inst[1][0]), hm(b"split-message-XXX................")), (gen, ssum)]
+    assert vm.vm_product_is_one(progs, [part0, bad1]) is False

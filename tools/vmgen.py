@@ -34,7 +34,7 @@ def f2_pow(x, e):
         x = f2_mul(x, x); e >>= 1
     return r
 XI = (1, 1)
-CONSTS = {"ONE": (1, 0), "B3": (12, 12), "INV2": (pow(2, -1, P), 0)}
+CONSTS = {"ONE": (1, 0), "TWIST3B": (12, 12), "INV2": (pow(2, -1, P), 0)}       # TWIST3B = 3 b' = 3 * 4(1 + i)
 for k in range(6):
     CONSTS[f"FROB1_{k}"] = f2_pow(XI, k * (P - 1) // 6)
     g2 = f2_pow(XI, k * (P * P - 1) // 6); assert g2[1] == 0
@@ -184,7 +184,7 @@ def ml_dbl(T, k):
     x, y, z = T
     A = (x * y) * k("INV2")
     B, Cc = y.sqr(), z.sqr()
-    E = k("B3") * Cc
+    E = k("TWIST3B") * Cc
     F = E.scale(3)
     H = (y + z).sqr() - B - Cc
     l0 = B - E
@@ -207,12 +207,13 @@ def ml_add(T, qx, qy):
 def line_at(l, px, py): return l[0], l[1] * px, l[2] * py
 
 # ------------------------------------------------------------------ programs.  Persistent registers (fixed slots, shared by all programs)
-REG_CONST = ["ONE", "B3", "INV2"] + [f"FROB1_{k}" for k in range(6)] + [f"FROB2_{k}" for k in range(6)]
+REG_CONST = ["ONE", "TWIST3B", "INV2"] + [f"FROB1_{k}" for k in range(6)] + [f"FROB2_{k}" for k in range(6)]
 REG_IN = ["P1X", "P1Y", "Q1X", "Q1Y", "P2X", "P2Y", "Q2X", "Q2Y"]
 def r6(n): return [f"{n}{i}" for i in range(6)]
 REG_STATE = ["T1X", "T1Y", "T1Z", "T2X", "T2Y", "T2Z"] + r6("F") + r6("M") + r6("X") + r6("ACC") + r6("A") + r6("B") + r6("C") + \
             ["IT0", "IT1", "IT2", "ID", "NORM", "NINV"]
 REGS = REG_CONST + REG_IN + REG_STATE
+assert len(set(REGS)) == len(REGS), "duplicate register name"
 SLOT = {r: i for i, r in enumerate(REGS)}
 NSLOTS = 232        # slots per warp (100 B each): registers + temporaries
 
@@ -248,6 +249,32 @@ def build_programs(make_graph):
             f = fp12_mul_by_014(f, *line_at(l, g.inp(pp + "X"), g.inp(pp + "Y")))
             g.out(t + "X", T[0]); g.out(t + "Y", T[1]); g.out(t + "Z", T[2])
         put6(g, "F", f)
+    # single-pair forms on the pair-2 registers and a running Fp12 product in A: the multi-GPU split of ONE batch lets
+    # every warp multiply the Miller values of its items into A (no final exponentiation per item); the fold multiplies the gathered
+    # partial products into F before ONE final exponentiation.
+    @prog
+    def p_ml1_init(g, k):
+        one = k("ONE")
+        g.out("T2X", g.inp("Q2X")); g.out("T2Y", g.inp("Q2Y")); g.out("T2Z", one)
+        put6(g, "F", (one,) + tuple(one.scale(0) for _ in range(5)))
+    @prog
+    def p_ml1_dbl(g, k):
+        f = fp12_sqr(get6(g, "F"))
+        T, l = ml_dbl((g.inp("T2X"), g.inp("T2Y"), g.inp("T2Z")), k)
+        f = fp12_mul_by_014(f, *line_at(l, g.inp("P2X"), g.inp("P2Y")))
+        g.out("T2X", T[0]); g.out("T2Y", T[1]); g.out("T2Z", T[2]); put6(g, "F", f)
+    @prog
+    def p_ml1_add(g, k):
+        T, l = ml_add((g.inp("T2X"), g.inp("T2Y"), g.inp("T2Z")), g.inp("Q2X"), g.inp("Q2Y"))
+        f = fp12_mul_by_014(get6(g, "F"), *line_at(l, g.inp("P2X"), g.inp("P2Y")))
+        g.out("T2X", T[0]); g.out("T2Y", T[1]); g.out("T2Z", T[2]); put6(g, "F", f)
+    @prog
+    def p_a_one(g, k):
+        one = k("ONE"); put6(g, "A", (one,) + tuple(one.scale(0) for _ in range(5)))
+    @prog
+    def p_amulf(g, k): put6(g, "A", fp12_mul(get6(g, "A"), get6(g, "F")))
+    @prog
+    def p_fmula(g, k): put6(g, "F", fp12_mul(get6(g, "F"), get6(g, "A")))
     # final exponentiation, easy part: m = conj(f) * f^-1, m = frob2(m) * m.  The Fp12 inverse goes down to ONE Fp inversion
     # (of NORM = N(d), d in Fp2), which a single lane computes between FE_INV_A and FE_INV_B.
     @prog
@@ -412,6 +439,27 @@ def vm_pairing_is_one(progs, p1, q1, p2, q2):
         if (Z_ABS >> i) & 1: run_program(progs["ML_ADD"], s)
     final_exp_vm(progs, s)
     return [s[SLOT[r]] for r in r6("ACC")] == [(1, 0)] + [(0, 0)] * 5
+def vm_miller1(progs, s, p, q):
+    """F <- f_{|z|,q}(p) (single pair on the pair-2 registers)"""
+    for reg, v in (("P2X", (p[0], 0)), ("P2Y", (p[1], 0)), ("Q2X", q[0]), ("Q2Y", q[1])): s[SLOT[reg]] = (v[0] % P, v[1] % P)
+    run_program(progs["ML1_INIT"], s)
+    for i in range(62, -1, -1):
+        run_program(progs["ML1_DBL"], s)
+        if (Z_ABS >> i) & 1: run_program(progs["ML1_ADD"], s)
+def vm_product_is_one(progs, pairs_per_part):
+    """the split protocol: every part multiplies the Miller values of its pairs into A; the fold multiplies the parts' A into F"""
+    parts = []
+    for pairs in pairs_per_part:
+        s = fresh_slots(); run_program(progs["A_ONE"], s)
+        for p, q in pairs: vm_miller1(progs, s, p, q); run_program(progs["AMULF"], s)
+        parts.append([s[SLOT[r]] for r in r6("A")])
+    s = fresh_slots()
+    for i, r in enumerate(r6("F")): s[SLOT[r]] = (1, 0) if i == 0 else (0, 0)
+    for a in parts:
+        for r, v in zip(r6("A"), a): s[SLOT[r]] = v
+        run_program(progs["FMULA"], s)
+    final_exp_vm(progs, s)
+    return [s[SLOT[r]] for r in r6("ACC")] == [(1, 0)] + [(0, 0)] * 5
 def final_exp_vm(progs, s):
     run_program(progs["FE_INV_A"], s)
     n = s[SLOT["NORM"]]; assert n[1] == 0
@@ -445,7 +493,8 @@ def enc_mul(dst, a, b): return [dst | (a << 8) | (b << 16), 0, 0, 0]
 NOP = [0xff, 0, 0, 0]          # dst 0xff = no operation
 
 def emit(progs, path):
-    order = ["ML_INIT", "ML_DBL", "ML_ADD", "FE_INV_A", "FE_INV_B", "CYCSQR", "MULX", "GLUE1", "GLUE2", "GLUE3", "GLUE4", "GLUE5"]
+    order = ["ML_INIT", "ML_DBL", "ML_ADD", "FE_INV_A", "FE_INV_B", "CYCSQR", "MULX", "GLUE1", "GLUE2", "GLUE3", "GLUE4", "GLUE5",
+             "ML1_INIT", "ML1_DBL", "ML1_ADD", "A_ONE", "AMULF", "FMULA"]
     L = []
     A = L.append
     A("// GENERATED by tools/vmgen.py -- do not edit.  Step programs of the warp-cooperative pairing (see tools/vmgen.py for the format).")
