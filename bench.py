@@ -166,6 +166,106 @@ def stage_mac32_per_round(orc, pks, bitmaps, sigs, msgs, blen, sample=12):
     acc /= sample
     return [float(acc[2 * s] * MAC32_PER_MUL + acc[2 * s + 1] * MAC32_PER_SQR) for s in range(6)]
 
+# ------------------------------------------------------------------ the other BASELINE configs (C3 / C4 / C5), short legs reported beside the headline
+def _median_ms(fn, reps=3):
+    ts = []
+    for _ in range(reps):
+        t0 = time.perf_counter(); out = fn(); ts.append((time.perf_counter() - t0) * 1e3)
+    return float(np.median(ts)), out
+
+def other_configs(bls, world, rank, dist, device):
+    """C3: 4 shards x 250 validators, 4 distinct messages, one call (+ a 1 024-item multi-committee batch);
+    C4: 10 000 independent triples, 1 % invalid -- one GPU through hbls_verify_batch, and split over the ranks (partial records,
+        NCCL all-gather, fold; exact per-slice pass when the fold does not settle it);
+    C5: 1 000-validator committee: sign 1 000, aggregate 1 000, aggregate-verify at 64 / 256 / 1 024 rounds.
+    Host-buffer calls, wall-clock medians (these legs are latency-like: copies and launches included)."""
+    from harmony_b200 import shard
+    out = {}
+    rng = np.random.Generator(np.random.Philox(key=[31337, 0]))
+    if rank == 0:
+        # ---- C3
+        n = N_COMMITTEE; coms, skss = [], []
+        for sh in range(4):
+            sks = [wl.seeded_sk(f"bench-c3/{sh}", i) for i in range(n)]
+            blob = bls.GetPublicKeyBatch(b"".join(wl.sk_bytes(k) for k in sks))
+            coms.append(bls.Committee([blob[48 * i:48 * i + 48] for i in range(n)])); skss.append(sks)
+        def items(K):
+            idx = [j % 4 for j in range(K)]
+            bms = [wl.bitmap_with_k("bench-c3/bm", j, n, [167, 200, 250, 180][j % 4]) for j in range(K)]
+            msgs = b"".join(wl.commit_payload("bench-c3/m", j) for j in range(K))
+            agg = b"".join(wl.sk_bytes(wl.round_signer_sum(skss[idx[j]], bms[j])) for j in range(K))
+            sigs, ok = bls.SignHashBatch(agg, msgs, MSG_LEN)
+            return [coms[i] for i in idx], bms, sigs, msgs, sum(sum(bin(b).count("1") for b in bm) for bm in bms)
+        for K in (4, 1024):
+            cs, bms, sigs, msgs, nsig = items(K)
+            ms, res = _median_ms(lambda: bls.AggregateVerifyItems(cs, bms, sigs, msgs, MSG_LEN), 5 if K == 4 else 3)
+            assert res == b"\x01" * K
+            out[f"c3_items_{K}"] = {"ms": ms, "sigs_per_s": nsig / (ms * 1e-3), "committees": 4, "mode": bls.LastBatchInfo()["mode"]}
+        # ---- C5
+        n5 = 1000
+        sks5 = [wl.seeded_sk("bench-c5", i) for i in range(n5)]
+        sk_blob = b"".join(wl.sk_bytes(k) for k in sks5)
+        ms_pk, pk_blob = _median_ms(lambda: bls.GetPublicKeyBatch(sk_blob), 1)
+        com5 = bls.Committee([pk_blob[48 * i:48 * i + 48] for i in range(n5)])
+        m5 = wl.commit_payload("bench-c5", 0)
+        ms_sign, (sigs5, ok5) = _median_ms(lambda: bls.SignHashBatch(sk_blob, m5 * n5, MSG_LEN))
+        ms_agg, agg5 = _median_ms(lambda: bls.AggregateSigBytes([sigs5[96 * i:96 * i + 96] for i in range(n5)]))
+        full_bm = bytes([0xff] * (n5 // 8))
+        assert com5.AggregateVerify(full_bm, agg5, m5)
+        c5 = {"committee": n5, "sign_1000_ms": ms_sign, "aggregate_1000_sigs_ms": ms_agg, "verify": {}}
+        for Bv in (64, 256, 1024):
+            bms = [wl.bitmap_with_k("bench-c5/bm", j % 16, n5, [667, 800, 1000][j % 3]) for j in range(Bv)]
+            msgs = b"".join(wl.commit_payload("bench-c5/m", j) for j in range(Bv))
+            agg = b"".join(wl.sk_bytes(wl.round_signer_sum(sks5, bms[j])) for j in range(Bv))
+            sigs, ok = bls.SignHashBatch(agg, msgs, MSG_LEN)
+            ms, res = _median_ms(lambda: com5.AggregateVerifyBatch(b"".join(bms), sigs, msgs, MSG_LEN))
+            assert res == b"\x01" * Bv
+            nsig = sum(sum(bin(b).count("1") for b in bm) for bm in bms)
+            c5["verify"][str(Bv)] = {"ms": ms, "sigs_per_s": nsig / (ms * 1e-3)}
+        out["c5_super_committee"] = c5
+    # ---- C4 (every rank takes part in the split form)
+    k = 10000
+    sks4 = b"".join(wl.sk_bytes(wl.seeded_sk("bench-c4", i)) for i in range(k))
+    msgs4 = b"".join(wl.seeded_bytes("bench-c4/m", i, 32) for i in range(k))
+    pks4 = bls.GetPublicKeyBatch(sks4)
+    sigs4, ok4 = bls.SignHashBatch(sks4, msgs4, 32)
+    bad = np.sort(np.random.Generator(np.random.Philox(key=[4, 4])).choice(k, size=k // 100, replace=False))
+    a_sg = np.frombuffer(sigs4, dtype=np.uint8).reshape(k, 96).copy(); a_ms = np.frombuffer(msgs4, dtype=np.uint8).reshape(k, 32).copy()
+    a_sg[bad[0::2], 11] ^= 1; a_ms[bad[1::2], 5] ^= 0x80
+    sig_bad, msg_bad = a_sg.tobytes(), a_ms.tobytes()
+    want = bytearray(b"\x01" * k)
+    for i in bad: want[i] = 0
+    c4 = {"triples": k, "invalid": int(len(bad))}
+    if rank == 0:
+        ms, res = _median_ms(lambda: bls.VerifyBatch(pks4, sig_bad, msg_bad, 32))
+        assert res == bytes(want)
+        c4["one_gpu_verify_batch"] = {"ms": ms, "triples_per_s": k / (ms * 1e-3), "results_exact": True, "batch_info": bls.LastBatchInfo()}
+        ms, res = _median_ms(lambda: bls.VerifyBatch(pks4, sigs4, msgs4, 32))
+        assert res == b"\x01" * k
+        c4["one_gpu_verify_batch_all_valid"] = {"ms": ms, "triples_per_s": k / (ms * 1e-3)}
+    def split(sg, ms_):
+        if world > 1: dist.barrier()
+        t0 = time.perf_counter()
+        res, settled = shard.verify_triples_split(pks4, sg, ms_, 32, device=device)
+        dt = (time.perf_counter() - t0) * 1e3
+        if world > 1:
+            import torch
+            t = torch.tensor([dt], dtype=torch.float64, device=device); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t[0])
+        return dt, res, settled
+    split(sigs4, msgs4)                                   # warm-up (allocations, NCCL channel set-up)
+    v = [split(sigs4, msgs4) for _ in range(3)]
+    assert all(r == b"\x01" * k and s for _, r, s in v)
+    ms_ok = float(np.median([d for d, _, _ in v]))
+    v = [split(sig_bad, msg_bad) for _ in range(3)]
+    assert all(r == bytes(want) and not s for _, r, s in v)
+    ms_bad = float(np.median([d for d, _, _ in v]))
+    c4["split_over_ranks"] = {"ranks": world, "scaling": "strong", "collective": "all-gather of one 872-byte partial record per rank + identical local fold",
+                              "all_valid": {"ms": ms_ok, "triples_per_s": k / (ms_ok * 1e-3), "settled_by_fold": True},
+                              "one_pct_invalid": {"ms": ms_bad, "triples_per_s": k / (ms_bad * 1e-3), "settled_by_fold": False,
+                                                  "note": "fold fails by construction; every rank then verifies its slice exactly and the result bytes are all-gathered"}}
+    out["c4_view_change_storm"] = c4
+    return out
+
 # ------------------------------------------------------------------ main arms
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -359,6 +459,9 @@ def run_gpu(args):
     assert vres == b"\x01" * N_COMMITTEE
     votes250_ms = float(np.median(vlat))
 
+    others = None
+    if not args.no_other_configs:
+        others = other_configs(bls, world, rank, dist, "cuda")
     from harmony_b200 import shard
     dev_ms_max, e2e_ms_max, nsig_total = shard.reduce_step_stats(dev_ms, e2e_s * 1e3, float(nsig), device="cuda")
     if rank != 0:
@@ -457,6 +560,7 @@ def run_gpu(args):
             "batch_sweep_e2e": sweep,
             "single_round_latency_ms": single_round_ms, "leader_250_votes_same_msg_latency_ms": votes250_ms}
     if cpu: line["cpu_baseline"] = cpu
+    if others: line["other_configs"] = others
     print(json.dumps(line), flush=True)
     if world > 1: dist.destroy_process_group()
 
@@ -467,6 +571,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--rounds", type=int, default=303104, help="rounds per step per GPU (default: 37 888 groups of 8 = one lane pair per group on 148 SMs x 512 threads)")
     ap.add_argument("--impl", default="hbls", choices=["hbls", "reference"])
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short C3 / C4 / C5 legs (BASELINE configs[2..4]) reported beside the headline")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "hbls":
         log("note: warm-up < 3 steps requested")
