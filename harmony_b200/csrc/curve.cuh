@@ -328,7 +328,8 @@ HB_DEV void hash_to_fp(fp& t, const uint8_t* msg, uint32_t len) {
     fp_from_int(t, v);
 }
 // mcl MapTo::calcBN over Fp2 (Shallue-van de Woestijne / Fouque-Tibouchi); false when the map is undefined (t = 0)
-HB_NOINLINE bool sw_map_g2(g2& r, const fp2& t) {
+// GCD = true: the one inversion of the map by binary GCD (latency path)
+template <bool GCD = false> HB_NOINLINE bool sw_map_g2(g2& r, const fp2& t) {
     if (fp2_is_zero(t)) return false;
     fp n, c1, c2, one; fp2 w, x, y, g, bb;
     fp_set(c1, K_SW_C1); fp_set(c2, K_SW_C2); fp_one(one); fp2_const(bb, K_B2);
@@ -343,7 +344,8 @@ HB_NOINLINE bool sw_map_g2(g2& r, const fp2& t) {
     fp2_sqr(u, t); fp2_add(u, u, bb); fp_add(u.a, u.a, one);        // u = t^2 + b + 1
     if (fp2_is_zero(u)) return false;
     fp2_mul_fp(ct, t, c1);                                          // c1 t
-    fp2_mul(d, u, ct); fp2_inv(d, d);                               // (u c1 t)^-1
+    fp2_mul(d, u, ct);
+    if (GCD) fp2_inv_gcd(d, d); else fp2_inv(d, d);                 // (u c1 t)^-1
     fp2_sqr(w, ct); fp2_mul(w, w, d);                               // w = c1 t / u
     fp2_sqr(x3, u); fp2_mul(x3, x3, d); fp2_sqr(x3, x3); fp_add(x3.a, x3.a, one);   // x3 = 1 + 1/w^2
     fp2_mul(x, t, w); fp2_neg(x, x); fp_add(x.a, x.a, c2);          // x1 = c2 - t w

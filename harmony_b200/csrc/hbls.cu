@@ -24,19 +24,21 @@ struct Scratch {
     cudaEvent_t ev[8] = {}; bool ev_ok = false;
     unsigned* h_counts = nullptr;            // pinned: [0] rounds re-verified exactly, [1] groups failed
     cudaEvent_t done = nullptr;
+    cudaEvent_t fork = nullptr, join[2] = {}; bool forked = false;      // small batches: decode / hash on two auxiliary streams
 };
 struct Ctx {
     bool ready = false;
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t aux[2] = {nullptr, nullptr};               // latency path: signature decode and hash-to-G2 run beside the mask aggregation
     std::mutex mu;
     std::map<cudaStream_t, Scratch> scratch;
     std::atomic<uint64_t> launches{0};
     bool stage_timing = false; Scratch* stage_sc = nullptr;
     int batch_mode = 1;                                     // 1: random-linear-combination groups + exact pass over failed groups, 0: exact per round
     // tuning (hbls_set_param)
-    long long rlc_min = 16384, rlc_g = 0, tpsm = 384, tpsm_split = 512, tpsm_light = 1024, coop_max = 16383;
+    long long rlc_min = 16384, rlc_g = 0, tpsm = 384, tpsm_split = 512, tpsm_light = 1024, coop_max = 16383, overlap = 1;
     // coefficient stream: ChaCha20 keyed from /dev/urandom, block counter = call number
     uint32_t chacha_key[8] = {}; uint64_t rlc_calls = 0;
     // last batch
@@ -78,7 +80,12 @@ int reserve(cudaStream_t s, size_t bytes, Scratch** out) {
         CK(cudaMalloc(&sc.base, cap));
         sc.cap = cap;
     }
-    if (!sc.h_counts) { CK(cudaMallocHost(&sc.h_counts, 64)); sc.h_counts[0] = sc.h_counts[1] = 0; CK(cudaEventCreateWithFlags(&sc.done, cudaEventDisableTiming)); }
+    if (!sc.h_counts) {
+        CK(cudaMallocHost(&sc.h_counts, 64)); sc.h_counts[0] = sc.h_counts[1] = 0;
+        CK(cudaEventCreateWithFlags(&sc.done, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&sc.fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&sc.join[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&sc.join[1], cudaEventDisableTiming));
+    }
+    sc.forked = false;
     *out = &sc;
     return 0;
 }
@@ -144,8 +151,16 @@ VerifyBufs carve_verify(Arena& ar, size_t B) {
     v.fail_list = ar.take<uint32_t>(B); v.counts = ar.take<unsigned>(2);
     return v;
 }
+// Small batches (latency path): the inputs are on the device from here on -- signature decode and hash-to-G2 may start on the
+// auxiliary streams while the caller's stream still aggregates the public keys (launch_verify_tail joins them before the pairing).
+static bool latency_path(size_t B);
+void fork_point(size_t B, Scratch* sc, cudaStream_t s) {
+    if (!latency_path(B) || !g.overlap || g.stage_timing) return;
+    if (cudaEventRecord(sc->fork, s) == cudaSuccess) sc->forked = true;
+}
 // batched (random-linear-combination) form applies: default mode and a batch large enough
 static bool rlc_applies(size_t B) { return g.batch_mode == 1 && (long long)B >= g.rlc_min && B >= 2 * HB_RLC_GMAX; }
+static bool latency_path(size_t B) { return !rlc_applies(B) && (long long)B <= g.coop_max; }
 #define STAGE_EV(i, sc, strm) do { if (g.stage_timing && (sc)->ev_ok) cudaEventRecord((sc)->ev[i], (strm)); } while (0)
 // v.apk holds the Jacobian (aggregate) public key of every round; ok_pk (nullable) = per-round "key decoded" flags of the triple form
 void launch_verify_tail(size_t B, const VerifyBufs& v, Scratch* sc, const uint8_t* d_sig96, const uint8_t* d_msgs, uint32_t msg_len,
@@ -153,21 +168,31 @@ void launch_verify_tail(size_t B, const VerifyBufs& v, Scratch* sc, const uint8_
     STAGE_EV(1, sc, s);
     const bool rlc = rlc_applies(B);
     // the batched check consumes the Jacobian sums directly; -apk in affine form is then only needed for the rounds of failed groups
-    if (!rlc) LAUNCH(k_g1_normalize, blocks_for(B, TPB), TPB, s, B, v.apk, v.pkneg, 1, (const int*)nullptr);
+    // small batches (latency path): one item per lane pair, binary-GCD inversions; large ones: one item per thread, persistent
+    const bool pairs = latency_path(B);
+    if (!rlc) {
+        if (pairs) LAUNCH(k_g1_normalize_lat, blocks_for(B, 32), 32, s, B, v.apk, v.pkneg, 1);
+        else LAUNCH(k_g1_normalize, blocks_for(B, TPB), TPB, s, B, v.apk, v.pkneg, 1, (const int*)nullptr);
+    }
     STAGE_EV(2, sc, s);
-    // small batches (latency path): one item per lane pair; large ones: one per thread, persistent
-    const bool pairs = !rlc && (long long)B <= g.coop_max;
-    if (pairs) LAUNCH(k_g2_decode_pair, blocks_for(2 * B, 32), 32, s, B, d_sig96, v.sig, v.ok_sig, 1);
+    const bool forked = pairs && sc->forked;              // decode on aux[0], hash on aux[1], concurrently with the work above
+    cudaStream_t sd = forked ? g.aux[0] : s, sh = forked ? g.aux[1] : s;
+    if (forked) { cudaStreamWaitEvent(sd, sc->fork, 0); cudaStreamWaitEvent(sh, sc->fork, 0); }
+    if (pairs) LAUNCH(k_g2_decode_pair, blocks_for(2 * B, 32), 32, sd, B, d_sig96, v.sig, v.ok_sig, 1);
     else LAUNCH(k_g2_decode, heavy_blocks(B), TPB, s, B, d_sig96, v.sig, v.ok_sig, 1);
     STAGE_EV(3, sc, s);
     if (same_msg && B > 1) {
-        if (pairs) LAUNCH(k_hash_to_g2_pair, 1, 32, s, (size_t)1, d_msgs, msg_len, v.hm, v.ok_hm);
+        if (pairs) LAUNCH(k_hash_to_g2_pair, 1, 32, sh, (size_t)1, d_msgs, msg_len, v.hm, v.ok_hm);
         else LAUNCH(k_hash_to_g2, 1, TPB, s, (size_t)1, d_msgs, msg_len, v.hm, v.ok_hm);
-        LAUNCH(k_broadcast_hm, blocks_for(B, 256), 256, s, B, v.hm, v.ok_hm);
+        LAUNCH(k_broadcast_hm, blocks_for(B, 256), 256, sh, B, v.hm, v.ok_hm);
     } else if (pairs)
-        LAUNCH(k_hash_to_g2_pair, blocks_for(2 * B, 32), 32, s, B, d_msgs, msg_len, v.hm, v.ok_hm);
+        LAUNCH(k_hash_to_g2_pair, blocks_for(2 * B, 32), 32, sh, B, d_msgs, msg_len, v.hm, v.ok_hm);
     else
         LAUNCH(k_hash_to_g2, heavy_blocks(B), TPB, s, B, d_msgs, msg_len, v.hm, v.ok_hm);
+    if (forked) {
+        cudaEventRecord(sc->join[0], sd); cudaEventRecord(sc->join[1], sh);
+        cudaStreamWaitEvent(s, sc->join[0], 0); cudaStreamWaitEvent(s, sc->join[1], 0);
+    }
     STAGE_EV(4, sc, s);
     hbls_batch_info& bi = g.info;
     bi = hbls_batch_info{}; bi.rounds = B; bi.mode = rlc ? 1 : 0;
@@ -370,6 +395,7 @@ int agg_verify_device_locked(const hbls_committee* c, size_t B, const uint8_t* d
                              const uint8_t* d_msgs, size_t msg_len, uint8_t* d_results, cudaStream_t s, Scratch* sc, Arena& ar, bool same_msg,
                              VerifyBufs* v_out = nullptr) {
     VerifyBufs v = carve_verify(ar, B);
+    fork_point(B, sc, s);
     STAGE_EV(0, sc, s);
     if (B >= (size_t)g.sm_count * 256)
         LAUNCH(k_mask_aggregate_serial, light_blocks(B), TPB, s, B, c->n, c->table, c->total, d_bitmaps, blen, v.apk);
@@ -400,6 +426,7 @@ int hbls_init_device(int device) {
     cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, device));
     g.device = device; g.sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&g.aux[0], cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&g.aux[1], cudaStreamNonBlocking));
     { FILE* f = fopen("/dev/urandom", "rb"); if (!f || fread(g.chacha_key, 1, 32, f) != 32) { if (f) fclose(f); fprintf(stderr, "[hbls] cannot read /dev/urandom\n"); return HBLS_ERR_CUDA; } fclose(f); }
     auto envll = [](const char* name, long long dflt) { const char* e = getenv(name); return e ? atoll(e) : dflt; };
     g.rlc_min = envll("HBLS_RLC_MIN", 16384); g.rlc_g = envll("HBLS_RLC_G", 0); g.coop_max = envll("HBLS_COOP_MAX", 16383);
@@ -435,6 +462,7 @@ static long long* param_slot(const char* name) {
     if (!strcmp(name, "tpsm_split")) return &g.tpsm_split;
     if (!strcmp(name, "tpsm_light")) return &g.tpsm_light;
     if (!strcmp(name, "coop_max")) return &g.coop_max;
+    if (!strcmp(name, "overlap")) return &g.overlap;
     return nullptr;
 }
 int hbls_set_param(const char* name, long long value) {
@@ -544,7 +572,7 @@ static int verify_hash_locked(const blsSignature* sig, const blsPublicKey* pub, 
     if (d_apk) CK(cudaMemcpyAsync(v.apk, d_apk, 144, cudaMemcpyDeviceToDevice, g.stream));
     else CK(cudaMemcpyAsync(v.apk, pub, 144, cudaMemcpyHostToDevice, g.stream));
     if (size) CK(cudaMemcpyAsync(dmsg, h, size, cudaMemcpyHostToDevice, g.stream));
-    LAUNCH(k_g1_normalize, 1, 32, g.stream, (size_t)1, v.apk, v.pkneg, 1, (const int*)nullptr);
+    LAUNCH(k_g1_normalize_lat, 1, 32, g.stream, (size_t)1, v.apk, v.pkneg, 1);
     const uint8_t* ok_sig = nullptr;
     if (sig96) {          // serialized signature: decode (+ subgroup check) on the device
         CK(cudaMemcpyAsync(dsig96, sig96, 96, cudaMemcpyHostToDevice, g.stream));
@@ -728,6 +756,7 @@ int hbls_aggregate_verify_items(size_t k, const hbls_committee* const* committee
     CK(cudaMemcpyAsync(dsig, sigs96, k * 96, cudaMemcpyHostToDevice, g.stream));
     if (msg_len) CK(cudaMemcpyAsync(dmsg, msgs, k * msg_len, cudaMemcpyHostToDevice, g.stream));
     CK(cudaMemcpyAsync(ditems, items.data(), k * sizeof(mask_item), cudaMemcpyHostToDevice, g.stream));
+    fork_point(k, sc, g.stream);
     STAGE_EV(0, sc, g.stream);
     LAUNCH(k_mask_aggregate_items, blocks_for(k * 32, 128), 128, g.stream, k, ditems, v.apk);
     launch_verify_tail(k, v, sc, dsig, dmsg, (uint32_t)msg_len, nullptr, dres, g.stream, all_messages_equal(msgs, k, msg_len));
@@ -749,6 +778,7 @@ int hbls_verify_batch(size_t k, const uint8_t* pk48, const uint8_t* sig96, const
     CK(cudaMemcpyAsync(dpk, pk48, k * 48, cudaMemcpyHostToDevice, g.stream));
     CK(cudaMemcpyAsync(dsig, sig96, k * 96, cudaMemcpyHostToDevice, g.stream));
     if (msg_len) CK(cudaMemcpyAsync(dmsg, msgs, k * msg_len, cudaMemcpyHostToDevice, g.stream));
+    fork_point(k, sc, g.stream);
     STAGE_EV(0, sc, g.stream);
     // keys stay Jacobian (z = 1): the same tail as a mask aggregate, so independent triples also go through the batched groups
     LAUNCH(k_g1_decode_jac, heavy_blocks(k), TPB, g.stream, k, dpk, v.apk, v.ok_pk, 1);

@@ -142,6 +142,18 @@ __global__ void k_g1_normalize(size_t n, const g1* in, g1a* out, int negate, con
     if (negate) fp_neg(a.y, a.y);
     out[i] = a;
 }
+// latency path: affine -apk with the binary-GCD inverse
+__global__ void k_g1_normalize_lat(size_t n, const g1* in, g1a* out, int negate) {
+    size_t i = HB_TID; if (i >= n) return;
+    g1 p = in[i]; g1a a;
+    if (pt_is_inf(p)) { fp_zero(a.x); fp_zero(a.y); }
+    else {
+        fp zi, zi2; fp_inv_gcd(zi, p.z); fp_sqr(zi2, zi);
+        fp_mul(a.x, p.x, zi2); fp_mul(zi2, zi2, zi); fp_mul(a.y, p.y, zi2);
+        if (negate) fp_neg(a.y, a.y);
+    }
+    out[i] = a;
+}
 __global__ void k_g2_normalize(size_t n, const g2* in, g2a* out) {
     size_t i = HB_TID; if (i >= n) return;
     g2 p = in[i]; g2a a; pt_to_aff(a, p);
@@ -240,7 +252,7 @@ __global__ void k_g2_decode_pair(size_t n, const uint8_t* in, g2a* out, uint8_t*
 __global__ void k_hash_to_g2_pair(size_t n, const uint8_t* msgs, uint32_t msg_len, g2a* out, uint8_t* ok) {
     const size_t i = HB_TID >> 1; if (i >= n) return;
     fp2 t; hash_to_fp(t.a, msgs + (size_t)msg_len * i, msg_len); fp_zero(t.b);
-    g2 a; bool good = sw_map_g2(a, t);                                    // Fp-heavy: both lanes compute the same point
+    g2 a; bool good = sw_map_g2<true>(a, t);                              // Fp-heavy: both lanes compute the same point
     g2a res; fp2_zero(res.x); fp2_zero(res.y);
     if (good) {
         jac<fp2h> A, H; fp2h_pack(A.x, a.x); fp2h_pack(A.y, a.y); fp2h_pack(A.z, a.z);

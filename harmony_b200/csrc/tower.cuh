@@ -496,6 +496,10 @@ HB_NOINLINE void fp2_inv(fp2h& r, const fp2h& x) {
 }
 
 // latency-path inversion: same as fp2_inv with the binary-GCD Fp inverse
+HB_NOINLINE void fp2_inv_gcd(fp2& r, const fp2& x) {
+    fp n; fp2_norm(n, x); fp_inv_gcd(n, n);
+    fp_mul(r.a, x.a, n); fp_mul(r.b, x.b, n); fp_neg(r.b, r.b);
+}
 HB_NOINLINE void fp2_inv_gcd(fp2h& r, const fp2h& x) {
     fp sq, o, n; fp_sqr(sq, x.c); fp2h_partner(o, sq); fp_add(n, sq, o);
     fp_inv_gcd(n, n);

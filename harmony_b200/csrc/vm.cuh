@@ -6,6 +6,8 @@
 // Fp2 values held in shared memory (vm_programs.cuh, generated and CPU-verified by tools/vmgen.py): in every step each of the 16
 // lane pairs of the warp executes one Fp2 operation -- a product, a squaring, or a small-integer linear combination -- so up to 16
 // independent Fp2 products are in flight.  The whole working set (232 slots x 100 B) stays in shared memory: no local-memory stack.
+// Linear combinations are stored per lane role as lists of atoms (+- m x one half of one slot) so that all 32 lanes of a step run
+// the same branch-free loop and reduce once.
 //
 // Slot layout: slot s = 25 words at s * 25: real part (12 Montgomery limbs), imaginary part (12), 1 pad word (odd stride: the 16
 // pairs of a step read 16 different slots without systematic bank conflicts).  Lane 2k is the "real" lane of pair k, lane 2k+1 the
@@ -58,47 +60,83 @@ HB_NOINLINE void vm_sqr(uint32_t* slots, int dst, int a, int im) {
     redc_wide(rr, T);
     vm_st(slots, dst, im, rr);
 }
-// acc += c * v for a small signed c (|c| <= 7), all values canonical
-HB_DEV void vm_axpy(fp& acc, int c, const fp& v) {
-    if (c == 0) return;
-    const int m = c < 0 ? -c : c;
-    fp t = v, sum; bool have = false;
-    for (int bit = 0; bit < 3; bit++) {
-        if (m & (1 << bit)) { if (have) fp_add(sum, sum, t); else { sum = t; have = true; } }
-        if ((m >> (bit + 1)) == 0) break;
-        fp_dbl(t, t);
+// k * p as 13 little-endian words, k = 1, 2, 4, 8, 16 (reduction ladder of vm_lin)
+__device__ __constant__ const uint32_t VM_KP[5][13] = {
+    {0xffffaaabu, 0xb9feffffu, 0xb153ffffu, 0x1eabfffeu, 0xf6b0f624u, 0x6730d2a0u, 0xf38512bfu, 0x64774b84u, 0x434bacd7u, 0x4b1ba7b6u, 0x397fe69au, 0x1a0111eau, 0x00000000u},
+    {0xffff5556u, 0x73fdffffu, 0x62a7ffffu, 0x3d57fffdu, 0xed61ec48u, 0xce61a541u, 0xe70a257eu, 0xc8ee9709u, 0x869759aeu, 0x96374f6cu, 0x72ffcd34u, 0x340223d4u, 0x00000000u},
+    {0xfffeaaacu, 0xe7fbffffu, 0xc54ffffeu, 0x7aaffffau, 0xdac3d890u, 0x9cc34a83u, 0xce144afdu, 0x91dd2e13u, 0x0d2eb35du, 0x2c6e9ed9u, 0xe5ff9a69u, 0x680447a8u, 0x00000000u},
+    {0xfffd5558u, 0xcff7ffffu, 0x8a9ffffdu, 0xf55ffff5u, 0xb587b120u, 0x39869507u, 0x9c2895fbu, 0x23ba5c27u, 0x1a5d66bbu, 0x58dd3db2u, 0xcbff34d2u, 0xd0088f51u, 0x00000000u},
+    {0xfffaaab0u, 0x9fefffffu, 0x153ffffbu, 0xeabfffebu, 0x6b0f6241u, 0x730d2a0fu, 0x38512bf6u, 0x4774b84fu, 0x34bacd76u, 0xb1ba7b64u, 0x97fe69a4u, 0xa0111ea3u, 0x00000001u}};
+// dst = sum_k M_k src_k, stored per lane role as <= 8 atoms (slot, half, sign, multiplier 1..4): every lane of the step runs the same
+// `natoms` iterations (its unused atoms point at the ZERO slot), accumulating plain 13-limb integers (< 32 p), then ONE reduction.
+HB_NOINLINE void vm_lin(uint32_t* slots, int dst, const uint4 row, int natoms, int im) {
+    uint32_t acc[13];
+#pragma unroll
+    for (int j = 0; j < 13; j++) acc[j] = 0;
+    const uint32_t rw[4] = {row.x, row.y, row.z, row.w};
+#pragma unroll 1
+    for (int a = 0; a < natoms; a++) {
+        const uint32_t at = (rw[a >> 1] >> (16 * (a & 1))) & 0xffffu;
+        const int s = at & 0xff, half = (at >> 8) & 1, sh = (at >> 10) & 3;             // multiplier m = sh + 1
+        const uint32_t neg = 0u - ((at >> 9) & 1u);
+        uint32_t v[12], w[12];
+        vm_ld(v, slots, s, half);
+        // w = neg ? p - v : v   (in [0, p])
+        sub_cc(w[0], HB_P0, v[0]);
+#pragma unroll
+        for (int j = 1; j < 11; j++) subc_cc(w[j], p_limb(j), v[j]);
+        subc(w[11], HB_P11, v[11]);
+#pragma unroll
+        for (int j = 0; j < 12; j++) w[j] = (w[j] & neg) | (v[j] & ~neg);
+        // acc += m * w:  m = 1, 2, 4 -> one shifted addend; m = 3 -> 2 w + w
+        const int shift = sh == 3 ? 2 : (sh == 0 ? 0 : 1);                               // sh: 0 -> x1, 1 -> x2, 2 -> x3 (= x2 + x1), 3 -> x4
+        uint32_t t[13];
+        t[0] = w[0] << shift;
+#pragma unroll
+        for (int j = 1; j < 12; j++) t[j] = __funnelshift_l(w[j - 1], w[j], shift);
+        t[12] = __funnelshift_l(w[11], 0u, shift);
+        add_cc(acc[0], acc[0], t[0]);
+#pragma unroll
+        for (int j = 1; j < 12; j++) addc_cc(acc[j], acc[j], t[j]);
+        addc(acc[12], acc[12], t[12]);
+        const uint32_t extra = sh == 2 ? 0xffffffffu : 0u;                               // x3: one more w
+        add_cc(acc[0], acc[0], w[0] & extra);
+#pragma unroll
+        for (int j = 1; j < 12; j++) addc_cc(acc[j], acc[j], w[j] & extra);
+        addc(acc[12], acc[12], 0u);
     }
-    if (c > 0) fp_add(acc, acc, sum); else fp_sub(acc, acc, sum);
-}
-// dst = sum_k M_k src_k, M_k = 2 x 2 integer matrix on (re, im): this lane evaluates its own row
-HB_NOINLINE void vm_lin(uint32_t* slots, const uint4 ins, int im) {
-    const int dst = ins.x & 0xff, nt = (ins.x >> 8) & 0xff;
-    uint32_t tw[4];
-    tw[0] = (ins.x >> 16) | ((ins.y & 0xffu) << 16); tw[1] = ins.y >> 8; tw[2] = ins.z & 0xffffffu; tw[3] = (ins.z >> 24) | ((ins.w & 0xffffu) << 8);
-    fp acc; fp_zero(acc);
-    for (int k = 0; k < nt; k++) {
-        const int s = tw[k] & 0xff;
-        const uint32_t e = tw[k] >> 8;                                  // four 4-bit two's-complement entries m00 m01 m10 m11
-        const int sh = im ? 8 : 0;
-        const int c_re = ((int)((e >> sh) & 0xf) ^ 8) - 8, c_im = ((int)((e >> (sh + 4)) & 0xf) ^ 8) - 8;
-        fp v;
-        if (c_re) { vm_ld(v.l, slots, s, 0); vm_axpy(acc, c_re, v); }
-        if (c_im) { vm_ld(v.l, slots, s, 1); vm_axpy(acc, c_im, v); }
+    // acc < 32 p: subtract 16 p, 8 p, 4 p, 2 p, p, p where it fits
+#pragma unroll
+    for (int k = 5; k >= 0; k--) {
+        const int row_k = k == 0 ? 0 : k - 1;                                              // ladder 16p, 8p, 4p, 2p, p, p
+        uint32_t d[13], bw;
+        sub_cc(d[0], acc[0], VM_KP[row_k][0]);
+#pragma unroll
+        for (int j = 1; j < 13; j++) subc_cc(d[j], acc[j], VM_KP[row_k][j]);
+        subc(bw, 0, 0);                                                                    // all-ones when acc < k p
+#pragma unroll
+        for (int j = 0; j < 13; j++) acc[j] = (acc[j] & bw) | (d[j] & ~bw);
     }
-    vm_st(slots, dst, im, acc.l);
+    vm_st(slots, dst, im, acc);
 }
-// run one step program; every lane of the warp must call it (steps end in __syncwarp)
+// run one step program; every lane of the warp must call it (steps end in __syncwarp).  The instruction words of the next step
+// are fetched while the current one executes.
 HB_NOINLINE void vm_run(int prog, uint32_t* slots) {
     const int lane = threadIdx.x & 31, pair = lane >> 1, im = lane & 1;
     const int first = VM_PROG_FIRST[prog], n = VM_PROG_STEPS[prog];
-    for (int st = first; st < first + n; st++) {
-        const int cls = VM_STEP_CLASS[st];
-        const uint4 ins = VM_INS[st * 16 + pair];
-        const int dst = ins.x & 0xff;
+    const uint4* ip = VM_INS + ((size_t)first * 16 + pair) * (VM_INS_WORDS / 4);
+    uint32_t hdr = VM_STEP_HDR[first]; uint32_t w0 = ip[0].x; uint4 row = ip[1 + im];
+    for (int st = 0; st < n; st++) {
+        const uint32_t c_hdr = hdr, c_w0 = w0; const uint4 c_row = row;
+        if (st + 1 < n) {
+            ip += 16 * (VM_INS_WORDS / 4);
+            hdr = VM_STEP_HDR[first + st + 1]; w0 = ip[0].x; row = ip[1 + im];
+        }
+        const int cls = c_hdr & 0xff, dst = c_w0 & 0xff;
         if (dst != 0xff) {
-            if (cls == VM_OP_LIN) vm_lin(slots, ins, im);
-            else if (cls == VM_OP_SQR) vm_sqr(slots, dst, (ins.x >> 8) & 0xff, im);
-            else vm_mul(slots, dst, (ins.x >> 8) & 0xff, (ins.x >> 16) & 0xff, im);
+            if (cls == VM_OP_LIN) vm_lin(slots, dst, c_row, (int)(c_hdr >> 8), im);
+            else if (cls == VM_OP_SQR) vm_sqr(slots, dst, (c_w0 >> 8) & 0xff, im);
+            else vm_mul(slots, dst, (c_w0 >> 8) & 0xff, (c_w0 >> 16) & 0xff, im);
         }
         __syncwarp();
     }
@@ -110,9 +148,10 @@ HB_DEV void vm_set_fp(uint32_t* slots, int s, const fp& re) {        // slot = (
     vm_st(slots, s, 0, re.l); vm_st(slots, s, 1, z);
 }
 HB_DEV void vm_set_fp2(uint32_t* slots, int s, const fp2& v) { vm_st(slots, s, 0, v.a.l); vm_st(slots, s, 1, v.b.l); }
-// constants of the programs (ONE, 3 b', 1/2, Frobenius coefficients): lanes share the 15 slots
+// constants of the programs (0, 1, 3 b', 1/2, Frobenius coefficients): lanes share the 16 slots
 HB_DEV void vm_load_consts(uint32_t* slots) {
     const int lane = threadIdx.x & 31;
+    if (lane == 15) { fp z; fp_zero(z); vm_set_fp(slots, VM_R_ZERO, z); }
     if (lane == 0) { fp o; fp_one(o); vm_set_fp(slots, VM_R_ONE, o); }
     if (lane == 1) { fp2 b; fp2_const(b, K_B2_3); vm_set_fp2(slots, VM_R_TWIST3B, b); }
     if (lane == 2) { fp h; fp_set(h, K_INV2); vm_set_fp(slots, VM_R_INV2, h); }
@@ -120,12 +159,22 @@ HB_DEV void vm_load_consts(uint32_t* slots) {
     if (lane >= 9 && lane < 15) { fp g; fp_set(g, K_FROB2[lane - 9]); vm_set_fp(slots, VM_R_FROB2_0 + (lane - 9), g); }
     __syncwarp();
 }
-// x^|z| on (X, ACC) by square-and-multiply, |z| = 0xd201000000010000 (ACC = X on entry = bit 63)
+// x^|z| on (X, ACC) by square-and-multiply, |z| = 0xd201000000010000 (ACC = X on entry = bit 63).  The runs of squarings between
+// the set bits (1, 2, 3, 9, 32, then 16 trailing) go through the run programs CYCSQR16 / 8 / 4 / 2 / 1.
+HB_DEV void vm_cycsqr_run(uint32_t* slots, int run) {
+    while (run >= 16) { vm_run(VM_P_CYCSQR16, slots); run -= 16; }
+    if (run & 8) vm_run(VM_P_CYCSQR8, slots);
+    if (run & 4) vm_run(VM_P_CYCSQR4, slots);
+    if (run & 2) vm_run(VM_P_CYCSQR2, slots);
+    if (run & 1) vm_run(VM_P_CYCSQR, slots);
+}
 HB_DEV void vm_expz(uint32_t* slots) {
+    int run = 0;
     for (int i = 62; i >= 0; i--) {
-        vm_run(VM_P_CYCSQR, slots);
-        if ((K_Z_ABS >> i) & 1) vm_run(VM_P_MULX, slots);
+        run++;
+        if ((K_Z_ABS >> i) & 1) { vm_cycsqr_run(slots, run); run = 0; vm_run(VM_P_MULX, slots); }
     }
+    vm_cycsqr_run(slots, run);
 }
 // F^(3 (p^12 - 1) / r) == 1 ?  Verdict to every lane.  Easy part around ONE Fp inversion (binary GCD on one lane), hard part = five
 // x^|z| chains.
@@ -157,9 +206,10 @@ HB_NOINLINE bool vm_final_exp_is_one(uint32_t* slots) {
 // e(P1, Q1) e(P2, Q2) == 1 ?  Inputs already in the slots P1X .. Q2Y (affine, none the identity); returns the verdict to every lane.
 HB_NOINLINE bool vm_pairing_check(uint32_t* slots) {
     vm_run(VM_P_ML_INIT, slots);
-    for (int i = 62; i >= 0; i--) {
-        vm_run(VM_P_ML_DBL, slots);
-        if ((K_Z_ABS >> i) & 1) vm_run(VM_P_ML_ADD, slots);
+    for (int i = 62; i >= 0; ) {
+        if ((K_Z_ABS >> i) & 1) { vm_run(VM_P_ML_DBL, slots); vm_run(VM_P_ML_ADD, slots); i--; }
+        else if (i >= 1 && !((K_Z_ABS >> (i - 1)) & 1)) { vm_run(VM_P_ML_DBL2, slots); i -= 2; }      // two doubling iterations in one program
+        else { vm_run(VM_P_ML_DBL, slots); i--; }
     }
     return vm_final_exp_is_one(slots);
 }

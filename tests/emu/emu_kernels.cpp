@@ -16,6 +16,7 @@ static thread_local hb_dim3 threadIdx = {0, 0, 0}, blockIdx = {0, 0, 0}, blockDi
 #define __launch_bounds__(...)
 struct uint4 { unsigned x, y, z, w; };
 static inline void __syncwarp() {}
+static inline unsigned __funnelshift_l(unsigned lo, unsigned hi, unsigned sh) { sh &= 31; return sh ? (hi << sh) | (lo >> (32 - sh)) : hi; }
 static inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }      // k_pairing_coop itself is not run here (see emu_vm_pairing)
 #include "../../harmony_b200/csrc/pairing.cuh"
 static inline void __syncthreads() { if (blockDim.x == 2) hb::hb_emu_exchange(0); }       // 2-thread CTA: rendezvous; 1-thread: nothing
@@ -122,23 +123,33 @@ extern "C" int emu_stage_counts(uint32_t n, const uint8_t* pks48, size_t B, cons
 static void emu_vm_run(int prog, uint32_t* slots) {
     const int first = VM_PROG_FIRST[prog], n = VM_PROG_STEPS[prog];
     for (int st = first; st < first + n; st++) {
-        const int cls = VM_STEP_CLASS[st];
+        const uint32_t hdr = VM_STEP_HDR[st]; const int cls = hdr & 0xff;
         // every lane reads before any lane's result becomes visible: stage the stores
         std::vector<uint32_t> snap(slots, slots + VM_SMEM_WORDS), next(slots, slots + VM_SMEM_WORDS);
         for (int lane = 0; lane < 32; lane++) {
-            const uint4 ins = VM_INS[st * 16 + (lane >> 1)]; const int dst = ins.x & 0xff, im = lane & 1;
+            const uint4* ip = VM_INS + ((size_t)st * 16 + (lane >> 1)) * (VM_INS_WORDS / 4);
+            const uint32_t w0 = ip[0].x; const int dst = w0 & 0xff, im = lane & 1;
             if (dst == 0xff) continue;
             std::vector<uint32_t> work(snap);
-            if (cls == VM_OP_LIN) vm_lin(work.data(), ins, im);
-            else if (cls == VM_OP_SQR) vm_sqr(work.data(), dst, (ins.x >> 8) & 0xff, im);
-            else vm_mul(work.data(), dst, (ins.x >> 8) & 0xff, (ins.x >> 16) & 0xff, im);
+            if (cls == VM_OP_LIN) vm_lin(work.data(), dst, ip[1 + im], (int)(hdr >> 8), im);
+            else if (cls == VM_OP_SQR) vm_sqr(work.data(), dst, (w0 >> 8) & 0xff, im);
+            else vm_mul(work.data(), dst, (w0 >> 8) & 0xff, (w0 >> 16) & 0xff, im);
             for (int j = 0; j < 12; j++) next[dst * VM_SLOT_WORDS + im * 12 + j] = work[dst * VM_SLOT_WORDS + im * 12 + j];
         }
         std::memcpy(slots, next.data(), VM_SMEM_WORDS * 4);
     }
 }
+static void emu_cycsqr_run(uint32_t* slots, int run) {
+    while (run >= 16) { emu_vm_run(VM_P_CYCSQR16, slots); run -= 16; }
+    if (run & 8) emu_vm_run(VM_P_CYCSQR8, slots);
+    if (run & 4) emu_vm_run(VM_P_CYCSQR4, slots);
+    if (run & 2) emu_vm_run(VM_P_CYCSQR2, slots);
+    if (run & 1) emu_vm_run(VM_P_CYCSQR, slots);
+}
 static void emu_vm_expz(uint32_t* slots) {
-    for (int i = 62; i >= 0; i--) { emu_vm_run(VM_P_CYCSQR, slots); if ((K_Z_ABS >> i) & 1) emu_vm_run(VM_P_MULX, slots); }
+    int run = 0;
+    for (int i = 62; i >= 0; i--) { run++; if ((K_Z_ABS >> i) & 1) { emu_cycsqr_run(slots, run); run = 0; emu_vm_run(VM_P_MULX, slots); } }
+    emu_cycsqr_run(slots, run);
 }
 // 1 / 0 = verdict of e(B, sig) e(-pk, H(msg)) == 1 through the VM; -1 undecodable input
 extern "C" int emu_vm_pairing(const uint8_t* pk48, const uint8_t* sig96, const uint8_t* msg, uint32_t len) {
@@ -146,7 +157,7 @@ extern "C" int emu_vm_pairing(const uint8_t* pk48, const uint8_t* sig96, const u
     if (!g1_deserialize(pk, pk48, true) || !g2_deserialize(sg, sig96, true) || !map_to_g2(h, msg, len)) return -1;
     g1a pa; g2a sa, ha; pt_to_aff(pa, pk); fp_neg(pa.y, pa.y); pt_to_aff(sa, sg); pt_to_aff(ha, h);
     std::vector<uint32_t> sl(VM_SMEM_WORDS, 0); uint32_t* slots = sl.data();
-    for (unsigned lane = 0; lane < 15; lane++) { threadIdx = {lane, 0, 0}; vm_load_consts(slots); }
+    for (unsigned lane = 0; lane < 16; lane++) { threadIdx = {lane, 0, 0}; vm_load_consts(slots); }
     threadIdx = {0, 0, 0};
     fp2 v; fp2_zero(v);
     fp_set(v.a, K_G1_X); vm_set_fp2(slots, VM_R_P1X, v); fp_set(v.a, K_G1_Y); vm_set_fp2(slots, VM_R_P1Y, v);
@@ -154,7 +165,11 @@ extern "C" int emu_vm_pairing(const uint8_t* pk48, const uint8_t* sig96, const u
     v.a = pa.x; vm_set_fp2(slots, VM_R_P2X, v); v.a = pa.y; vm_set_fp2(slots, VM_R_P2Y, v);
     vm_set_fp2(slots, VM_R_Q2X, ha.x); vm_set_fp2(slots, VM_R_Q2Y, ha.y);
     emu_vm_run(VM_P_ML_INIT, slots);
-    for (int i = 62; i >= 0; i--) { emu_vm_run(VM_P_ML_DBL, slots); if ((K_Z_ABS >> i) & 1) emu_vm_run(VM_P_ML_ADD, slots); }
+    for (int i = 62; i >= 0; ) {
+        if ((K_Z_ABS >> i) & 1) { emu_vm_run(VM_P_ML_DBL, slots); emu_vm_run(VM_P_ML_ADD, slots); i--; }
+        else if (i >= 1 && !((K_Z_ABS >> (i - 1)) & 1)) { emu_vm_run(VM_P_ML_DBL2, slots); i -= 2; }
+        else { emu_vm_run(VM_P_ML_DBL, slots); i--; }
+    }
     emu_vm_run(VM_P_FE_INV_A, slots);
     { fp n, ni; vm_ld(n.l, slots, VM_R_NORM, 0); fp_inv_gcd(ni, n); vm_set_fp(slots, VM_R_NINV, ni); }
     emu_vm_run(VM_P_FE_INV_B, slots);

@@ -43,10 +43,7 @@ def test_vm_slots_reused_across_rounds(vm, progs):
     def run(p1, q1, p2, q2):
         for reg, v in (("P1X", (p1[0], 0)), ("P1Y", (p1[1], 0)), ("Q1X", q1[0]), ("Q1Y", q1[1]), ("P2X", (p2[0], 0)), ("P2Y", (p2[1], 0)), ("Q2X", q2[0]), ("Q2Y", q2[1])):
             s[vm.SLOT[reg]] = (v[0] % vm.P, v[1] % vm.P)
-        vm.run_program(progs["ML_INIT"], s)
-        for i in range(62, -1, -1):
-            vm.run_program(progs["ML_DBL"], s)
-            if (vm.Z_ABS >> i) & 1: vm.run_program(progs["ML_ADD"], s)
+        vm.miller2_vm(progs, s)
         vm.final_exp_vm(progs, s)
         return [s[vm.SLOT[r]] for r in vm.r6("ACC")] == [(1, 0)] + [(0, 0)] * 5
     assert [run(*a), run(*b), run(a[0], a[1], b[2], b[3]), run(*a)] == [True, True, False, True]
@@ -63,10 +60,7 @@ def test_vm_final_exp_matches_oracle_value(vm, progs):
     s = vm.fresh_slots()
     for reg, v in (("P1X", (gen[0], 0)), ("P1Y", (gen[1], 0)), ("Q1X", sa[0]), ("Q1Y", sa[1]), ("P2X", (npk[0], 0)), ("P2Y", (npk[1], 0)), ("Q2X", ha[0]), ("Q2Y", ha[1])):
         s[vm.SLOT[reg]] = v
-    vm.run_program(progs["ML_INIT"], s)
-    for i in range(62, -1, -1):
-        vm.run_program(progs["ML_DBL"], s)
-        if (vm.Z_ABS >> i) & 1: vm.run_program(progs["ML_ADD"], s)
+    vm.miller2_vm(progs, s)
     # tower order (c0.c0, c0.c1, c0.c2, c1.c0, c1.c1, c1.c2) -> the oracle's w-power order (w^0 .. w^5)
     f_t = [s[vm.SLOT[r]] for r in vm.r6("F")]
     f_w = tuple(f_t[vm.SLOT_OF_W[k]] for k in range(6))
@@ -85,7 +79,8 @@ def test_vm_encoding_limits(vm, progs):
             for i in ins:
                 assert 0 <= i[0] < vm.NSLOTS < 255
                 if cls == vm.OP_LIN:
-                    assert 1 <= len(i[1]) <= vm.MAXT
+                    rows = vm.lin_rows(i[1])
+                    for r in rows: assert len(r) <= vm.MAXA and sum(((a >> 10) & 3) + 1 for a in r) <= vm.MAXW
                     for sl, M in i[1]: assert 0 <= sl < vm.NSLOTS and all(abs(c) <= vm.CMAX for c in M)
                 else: assert 0 <= i[1] < vm.NSLOTS and 0 <= i[2] < vm.NSLOTS
 

@@ -6,7 +6,9 @@ values that live in shared-memory slots; a program is a list of STEPS, and in ev
 operation (pair p runs instruction p of the step), so up to 16 independent Fp2 products run side by side:
     MUL   dst = a * b                     (lane-pair product: 2 wide products + 1 reduction per lane, tower.cuh fp2h)
     SQR   dst = a * a                     (1 wide product + 1 reduction per lane)
-    LIN   dst = sum_{k<4} M_k * src_k     (M_k = 2x2 small-integer matrices over (re, im): add, sub, conj, xi*, i*, 2x, 3x ...)
+    LIN   dst = sum_k M_k * src_k         (M_k = 2x2 small-integer matrices over (re, im): add, sub, conj, xi*, i*, 2x, 3x ...;
+                                           stored per lane role as a list of <= 8 ATOMS (slot, half, sign) that the lane adds up, so
+                                           that all 32 lanes of a step run the same branch-free loop)
 This file holds the formulas (the same tower / Miller-loop / final-exponentiation formulas as tower.cuh and pairing.cuh, written once
 over an abstract Fp2 type), a tracer that turns them into a dependency graph, a list scheduler (<= 16 operations of one class per
 step, linear combinations folded so that at most one LIN level sits between two MUL levels), a slot allocator, the C emitter and
@@ -19,8 +21,9 @@ import os, sys
 P = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
 Z_ABS = 0xd201000000010000
 NPAIR = 16
-MAXT = 4            # terms per LIN instruction
-CMAX = 7            # |matrix entry| limit of a LIN term (4-bit signed field)
+MAXA = 8            # atoms per row (re / im) of a LIN instruction: an atom adds or subtracts m x ONE half of ONE slot, m in 1..4
+MAXW = 24           # total weight (sum of the m) of a row: the lane accumulates plain integers < 32 p (13 limbs) before ONE reduction
+CMAX = 7            # |matrix entry| limit of a LIN term (5, 6, 7 take two atoms)
 
 # ------------------------------------------------------------------ concrete Fp2 (reference semantics of the VM)
 def f2(a, b=0): return (a % P, b % P)
@@ -34,7 +37,7 @@ def f2_pow(x, e):
         x = f2_mul(x, x); e >>= 1
     return r
 XI = (1, 1)
-CONSTS = {"ONE": (1, 0), "TWIST3B": (12, 12), "INV2": (pow(2, -1, P), 0)}       # TWIST3B = 3 b' = 3 * 4(1 + i)
+CONSTS = {"ZERO": (0, 0), "ONE": (1, 0), "TWIST3B": (12, 12), "INV2": (pow(2, -1, P), 0)}       # TWIST3B = 3 b' = 3 * 4(1 + i)
 for k in range(6):
     CONSTS[f"FROB1_{k}"] = f2_pow(XI, k * (P - 1) // 6)
     g2 = f2_pow(XI, k * (P * P - 1) // 6); assert g2[1] == 0
@@ -83,12 +86,19 @@ class V:
             if M == I2: return n
         items = sorted(self.t.items())
         if not items: items = [(g.add(("const", "ONE")), (0, 0, 0, 0))]
-        # split so that every LIN instruction has <= MAXT terms with entries within +-CMAX
+        # split so that both rows (re: m00, m01; im: m10, m11) of every LIN instruction stay within MAXA atoms
         def fits(M): return all(abs(c) <= CMAX for c in M)
         for n, M in items:
             if not fits(M): raise ValueError(f"{g.name}: coefficient out of range {M}")
-        while len(items) > MAXT:
-            head, items = items[:MAXT], items[MAXT:]
+        def na(c): return 0 if c == 0 else (1 if abs(c) <= 4 else 2)
+        def cost(ts):      # (atoms, weight) of the heavier row
+            return (max(sum(na(M[0]) + na(M[1]) for _, M in ts), sum(na(M[2]) + na(M[3]) for _, M in ts)),
+                    max(sum(abs(M[0]) + abs(M[1]) for _, M in ts), sum(abs(M[2]) + abs(M[3]) for _, M in ts)))
+        def ok(ts): a, w = cost(ts); return a <= MAXA and w <= MAXW
+        while not ok(items):
+            head = []
+            while items and ok(head + [items[0]]): head.append(items.pop(0))
+            if not head or (len(head) == 1 and head[0][1] == I2): raise ValueError(f"{g.name}: cannot split a linear combination into LIN instructions")
             items.insert(0, (g.add(("lin", tuple(head))), I2))
         return g.add(("lin", tuple(items)))
     def __mul__(self, o):
@@ -171,8 +181,19 @@ def fp12_frob2(x, k):
 def fp4_sqr(a, b):
     t0, t1 = a.sqr(), b.sqr()
     return t1.xi() + t0, (a + b).sqr() - t0 - t1
-def fp12_cyc_sqr(x):
+def fp12_cyc_sqr(x, xn=None):
+    """xn (optional): the same six values as single materialised nodes.  Squarings and the (a + b) sums use x (expansions in terms
+    of the previous squarings, so that they sit ONE linear level after them); the 3 t -+ 2 z outputs use xn (small coefficients)."""
     z0, z4, z3, z2, z1, z5 = x
+    if xn is not None:
+        n0, n4, n3, n2, n1, n5 = xn
+        t0, t1 = fp4_sqr(z0, z1)
+        r0 = (t0 - n0).dbl() + t0; r1 = (t1 + n1).dbl() + t1
+        t0, t1 = fp4_sqr(z2, z3); t2, t3 = fp4_sqr(z4, z5)
+        r4 = (t0 - n4).dbl() + t0; r5 = (t1 + n5).dbl() + t1
+        t0 = t3.xi()
+        r2 = (t0 + n2).dbl() + t0; r3 = (t2 - n3).dbl() + t2
+        return (r0, r4, r3, r2, r1, r5)
     t0, t1 = fp4_sqr(z0, z1)
     z0 = (t0 - z0).dbl() + t0; z1 = (t1 + z1).dbl() + t1
     t0, t1 = fp4_sqr(z2, z3); t2, t3 = fp4_sqr(z4, z5)
@@ -207,7 +228,7 @@ def ml_add(T, qx, qy):
 def line_at(l, px, py): return l[0], l[1] * px, l[2] * py
 
 # ------------------------------------------------------------------ programs.  Persistent registers (fixed slots, shared by all programs)
-REG_CONST = ["ONE", "TWIST3B", "INV2"] + [f"FROB1_{k}" for k in range(6)] + [f"FROB2_{k}" for k in range(6)]
+REG_CONST = ["ZERO", "ONE", "TWIST3B", "INV2"] + [f"FROB1_{k}" for k in range(6)] + [f"FROB2_{k}" for k in range(6)]
 REG_IN = ["P1X", "P1Y", "Q1X", "Q1Y", "P2X", "P2Y", "Q2X", "Q2Y"]
 def r6(n): return [f"{n}{i}" for i in range(6)]
 REG_STATE = ["T1X", "T1Y", "T1Z", "T2X", "T2Y", "T2Z"] + r6("F") + r6("M") + r6("X") + r6("ACC") + r6("A") + r6("B") + r6("C") + \
@@ -240,6 +261,18 @@ def build_programs(make_graph):
             T, l = ml_dbl((g.inp(t + "X"), g.inp(t + "Y"), g.inp(t + "Z")), k)
             f = fp12_mul_by_014(f, *line_at(l, g.inp(pp + "X"), g.inp(pp + "Y")))
             g.out(t + "X", T[0]); g.out(t + "Y", T[1]); g.out(t + "Z", T[2])
+        put6(g, "F", f)
+    @prog
+    def p_ml_dbl2(g, k):          # two doubling iterations in one program (no add step between them)
+        f = get6(g, "F"); T = {t: (g.inp(t + "X"), g.inp(t + "Y"), g.inp(t + "Z")) for t in ("T1", "T2")}
+        for _ in range(2):
+            f = fp12_sqr(f)
+            for t, pp in (("T1", "P1"), ("T2", "P2")):
+                T[t], l = ml_dbl(T[t], k)
+                f = fp12_mul_by_014(f, *line_at(l, g.inp(pp + "X"), g.inp(pp + "Y")))
+            f = tuple(V(g, {x.node(): I2}) for x in f); T = {t: tuple(V(g, {x.node(): I2}) for x in T[t]) for t in T}
+        for t in ("T1", "T2"):
+            g.out(t + "X", T[t][0]); g.out(t + "Y", T[t][1]); g.out(t + "Z", T[t][2])
         put6(g, "F", f)
     @prog
     def p_ml_add(g, k):
@@ -295,6 +328,17 @@ def build_programs(make_graph):
         put6(g, "M", m); put6(g, "X", m); put6(g, "ACC", m)
     @prog
     def p_cycsqr(g, k): put6(g, "ACC", fp12_cyc_sqr(get6(g, "ACC")))
+    # runs of squarings between the set bits of |z| as ONE program each: the linear steps between consecutive squarings fold into one
+    def cyc_run(n):
+        def f(g, k):
+            a = get6(g, "ACC")
+            an = a
+            for _ in range(n):
+                a = fp12_cyc_sqr(a, an)
+                an = tuple(V(g, {x.node(): I2}) for x in a)          # the materialised twins keep the coefficients small
+            put6(g, "ACC", a)
+        f.__name__ = f"p_cycsqr{n}"; return f
+    for n in (2, 4, 8, 16): prog(cyc_run(n))
     @prog
     def p_mulx(g, k): put6(g, "ACC", fp12_mul(get6(g, "ACC"), get6(g, "X")))
     # hard part (pairing.cuh final_exp): a = m^(z-1), b = a^(z-1), c = b^(z+p), d = c^(z^2+p^2-1), result d * m^3.
@@ -350,18 +394,26 @@ def compile_graph(g):
     w = {n: (8 if nodes[n][0] != "lin" else 1) for n in ops}
     prio = {}
     for n in reversed(ops): prio[n] = w[n] + max([prio[u] for u in users[n]] + [0])
+    def schedule(mul_first):
+        done = set(n for n in need if nodes[n][0] in ("in", "const"))
+        pending = set(ops); steps = []
+        while pending:
+            ready = [n for n in pending if all(d in done for d in deps(n))]
+            lin = sorted([n for n in ready if nodes[n][0] == "lin"], key=lambda n: -prio[n])
+            mul = sorted([n for n in ready if nodes[n][0] != "lin"], key=lambda n: -prio[n])
+            # mul_first: products as soon as any is ready, so that the linear work in between piles up into few steps;
+            # otherwise cheap steps first (they unlock products and fill the product steps better)
+            if mul and (mul_first or not lin):
+                chosen = mul[:NPAIR]
+                cls = OP_SQR if all(nodes[n][0] == "sqr" for n in chosen) else OP_MUL
+            else:
+                chosen = lin[:NPAIR]; cls = OP_LIN
+            steps.append((cls, chosen)); done |= set(chosen); pending -= set(chosen)
+        return steps
+    def cost(steps):        # rough step times on the device (us): product 1.45, squaring 1.0, linear 0.6
+        return sum({OP_MUL: 1.45, OP_SQR: 1.0, OP_LIN: 0.6}[c] for c, _ in steps)
+    steps = min((schedule(False), schedule(True)), key=cost)
     done = set(n for n in need if nodes[n][0] in ("in", "const"))
-    pending = set(ops); steps = []
-    while pending:
-        ready = [n for n in pending if all(d in done for d in deps(n))]
-        lin = sorted([n for n in ready if nodes[n][0] == "lin"], key=lambda n: -prio[n])
-        mul = sorted([n for n in ready if nodes[n][0] != "lin"], key=lambda n: -prio[n])
-        if lin:                                   # cheap steps first: they unlock products
-            chosen = lin[:NPAIR]; cls = OP_LIN
-        else:
-            chosen = mul[:NPAIR]
-            cls = OP_SQR if all(nodes[n][0] == "sqr" for n in chosen) else OP_MUL
-        steps.append((cls, chosen)); done |= set(chosen); pending -= set(chosen)
     # final move step(s): outputs into their registers (a register may still be read as an input until the very end)
     # slot allocation over steps: value of node n lives from its defining step to its last use
     nstep = len(steps)
@@ -433,12 +485,17 @@ def vm_pairing_is_one(progs, p1, q1, p2, q2):
     s = fresh_slots()
     for reg, v in (("P1X", (p1[0], 0)), ("P1Y", (p1[1], 0)), ("Q1X", q1[0]), ("Q1Y", q1[1]), ("P2X", (p2[0], 0)), ("P2Y", (p2[1], 0)), ("Q2X", q2[0]), ("Q2Y", q2[1])):
         s[SLOT[reg]] = (v[0] % P, v[1] % P)
-    run_program(progs["ML_INIT"], s)
-    for i in range(62, -1, -1):
-        run_program(progs["ML_DBL"], s)
-        if (Z_ABS >> i) & 1: run_program(progs["ML_ADD"], s)
+    miller2_vm(progs, s)
     final_exp_vm(progs, s)
     return [s[SLOT[r]] for r in r6("ACC")] == [(1, 0)] + [(0, 0)] * 5
+def miller2_vm(progs, s):
+    """the device's loop (vm.cuh vm_pairing_check): doubling iterations in pairs where no addition step separates them"""
+    run_program(progs["ML_INIT"], s)
+    i = 62
+    while i >= 0:
+        if (Z_ABS >> i) & 1: run_program(progs["ML_DBL"], s); run_program(progs["ML_ADD"], s); i -= 1
+        elif i >= 1 and not (Z_ABS >> (i - 1)) & 1: run_program(progs["ML_DBL2"], s); i -= 2
+        else: run_program(progs["ML_DBL"], s); i -= 1
 def vm_miller1(progs, s, p, q):
     """F <- f_{|z|,q}(p) (single pair on the pair-2 registers)"""
     for reg, v in (("P2X", (p[0], 0)), ("P2Y", (p[1], 0)), ("Q2X", q[0]), ("Q2Y", q[1])): s[SLOT[reg]] = (v[0] % P, v[1] % P)
@@ -460,15 +517,24 @@ def vm_product_is_one(progs, pairs_per_part):
         run_program(progs["FMULA"], s)
     final_exp_vm(progs, s)
     return [s[SLOT[r]] for r in r6("ACC")] == [(1, 0)] + [(0, 0)] * 5
+def expz_schedule():
+    """x^|z| by square-and-multiply from bit 62 down: [(number of squarings, multiply afterwards?), ...]"""
+    out = []; run = 0
+    for i in range(62, -1, -1):
+        run += 1
+        if (Z_ABS >> i) & 1: out.append((run, True)); run = 0
+    if run: out.append((run, False))
+    return out
 def final_exp_vm(progs, s):
     run_program(progs["FE_INV_A"], s)
     n = s[SLOT["NORM"]]; assert n[1] == 0
     s[SLOT["NINV"]] = (fp_inv(n[0]), 0)
     run_program(progs["FE_INV_B"], s)
     def expz():
-        for i in range(62, -1, -1):
-            run_program(progs["CYCSQR"], s)
-            if (Z_ABS >> i) & 1: run_program(progs["MULX"], s)
+        for run, mul in expz_schedule():
+            for n in (16, 8, 4, 2, 1):
+                while run >= n: run_program(progs["CYCSQR" if n == 1 else f"CYCSQR{n}"], s); run -= n
+            if mul: run_program(progs["MULX"], s)
     expz(); run_program(progs["GLUE1"], s)
     expz(); run_program(progs["GLUE2"], s)
     expz(); run_program(progs["GLUE3"], s)
@@ -476,36 +542,50 @@ def final_exp_vm(progs, s):
     expz(); run_program(progs["GLUE5"], s)
 
 # ------------------------------------------------------------------ emitter
+# Instruction = 12 x u32 per (step, pair):
+#   w0        MUL / SQR: dst | a << 8 | b << 16          LIN: dst | (atoms in the re row) << 8 | (atoms in the im row) << 12
+#   w4 .. w7  LIN: the re row, 8 atoms of 16 bits (slot | half << 8 | negate << 9 | (m - 1) << 10: adds (+-) m x that half, m = 1..4),
+#             unused atoms = the ZERO slot
+#   w8 .. w11 LIN: the im row
+# dst = 0xff: no operation.  A lane reads w0 and the uint4 of its own row.  Step header = class | (longest row of the step) << 8.
+INS_WORDS = 12
+def lin_rows(terms):
+    rows = ([], [])
+    for s_, M in terms:
+        for r in (0, 1):
+            for half in (0, 1):
+                c = M[2 * r + half]; m = abs(c)
+                for part in ([m] if m <= 4 else [4, m - 4]):
+                    if part: rows[r].append(s_ | (half << 8) | ((1 if c < 0 else 0) << 9) | ((part - 1) << 10))
+    return rows
 def enc_lin(dst, terms):
-    """128-bit LIN instruction as 4 x u32: w0 = dst | nterms << 8; then per term 24 bits: slot | 4 x 4-bit two's-complement entries"""
-    tw = []
-    for s, M in terms:
-        e = 0
-        for j, c in enumerate(M): e |= (c & 0xf) << (4 * j)
-        tw.append(s | (e << 8))
-    tw += [0] * (MAXT - len(tw))
-    w0 = dst | (len(terms) << 8) | ((tw[0] & 0xffff) << 16)
-    w1 = (tw[0] >> 16) | (tw[1] << 8)
-    w2 = tw[2] | ((tw[3] & 0xff) << 24)
-    w3 = tw[3] >> 8
-    return [w0 & 0xffffffff, w1 & 0xffffffff, w2 & 0xffffffff, w3 & 0xffffffff]
-def enc_mul(dst, a, b): return [dst | (a << 8) | (b << 16), 0, 0, 0]
-NOP = [0xff, 0, 0, 0]          # dst 0xff = no operation
+    rows = lin_rows(terms)
+    assert len(rows[0]) <= MAXA and len(rows[1]) <= MAXA
+    w = [dst | (len(rows[0]) << 8) | (len(rows[1]) << 12), 0, 0, 0]
+    for r in (0, 1):
+        at = rows[r] + [SLOT["ZERO"]] * (MAXA - len(rows[r]))
+        w += [at[2 * i] | (at[2 * i + 1] << 16) for i in range(4)]
+    return w
+def enc_mul(dst, a, b): return [dst | (a << 8) | (b << 16)] + [0] * (INS_WORDS - 1)
+NOP = [0xff] + [0] * (INS_WORDS - 1)          # dst 0xff = no operation
+PROGRAM_ORDER = ["ML_INIT", "ML_DBL", "ML_DBL2", "ML_ADD", "FE_INV_A", "FE_INV_B", "CYCSQR", "CYCSQR2", "CYCSQR4", "CYCSQR8", "CYCSQR16", "MULX",
+                 "GLUE1", "GLUE2", "GLUE3", "GLUE4", "GLUE5", "ML1_INIT", "ML1_DBL", "ML1_ADD", "A_ONE", "AMULF", "FMULA"]
 
 def emit(progs, path):
-    order = ["ML_INIT", "ML_DBL", "ML_ADD", "FE_INV_A", "FE_INV_B", "CYCSQR", "MULX", "GLUE1", "GLUE2", "GLUE3", "GLUE4", "GLUE5",
-             "ML1_INIT", "ML1_DBL", "ML1_ADD", "A_ONE", "AMULF", "FMULA"]
+    order = PROGRAM_ORDER
+    assert set(order) == set(progs)
     L = []
     A = L.append
     A("// GENERATED by tools/vmgen.py -- do not edit.  Step programs of the warp-cooperative pairing (see tools/vmgen.py for the format).")
     A("#ifndef HBLS_VM_PROGRAMS_CUH\n#define HBLS_VM_PROGRAMS_CUH\n#include <stdint.h>")
-    A(f"#define VM_NSLOTS {NSLOTS}\n#define VM_OP_MUL {OP_MUL}\n#define VM_OP_SQR {OP_SQR}\n#define VM_OP_LIN {OP_LIN}")
+    A(f"#define VM_NSLOTS {NSLOTS}\n#define VM_OP_MUL {OP_MUL}\n#define VM_OP_SQR {OP_SQR}\n#define VM_OP_LIN {OP_LIN}\n#define VM_INS_WORDS {INS_WORDS}")
     for r in REGS: A(f"#define VM_R_{r} {SLOT[r]}")
     hdr = []; ins = []; table = []
     for pi, name in enumerate(order):
         p = progs[name]; first = len(hdr)
         for cls, instrs in p.steps:
-            hdr.append(cls)
+            longest = max([max(len(r) for r in lin_rows(i[1])) for i in instrs]) if cls == OP_LIN else 0
+            hdr.append(cls | (longest << 8))
             row = []
             for i in instrs: row += enc_lin(i[0], i[1]) if cls == OP_LIN else enc_mul(*i)
             row += NOP * (NPAIR - len(instrs))
@@ -516,10 +596,10 @@ def emit(progs, path):
     A("static __device__ const uint16_t VM_PROG_FIRST[VM_NPROG] = {" + ", ".join(str(t[1]) for t in table) + "};")
     A("static __device__ const uint16_t VM_PROG_STEPS[VM_NPROG] = {" + ", ".join(str(t[2]) for t in table) + "};")
     A(f"// steps per program: " + ", ".join(f"{t[0]}={t[2]}" for t in table))
-    A(f"static __device__ const uint8_t VM_STEP_CLASS[{len(hdr)}] = {{" + ", ".join(str(h) for h in hdr) + "};")
+    A(f"static __device__ const uint16_t VM_STEP_HDR[{len(hdr)}] = {{" + ", ".join(str(h) for h in hdr) + "};")
     A(f"static __device__ const uint4 VM_INS[{len(ins) // 4}] = {{")
-    for i in range(0, len(ins), 16):
-        A("    " + " ".join("{0x%08xu, 0x%08xu, 0x%08xu, 0x%08xu}," % tuple(ins[j:j + 4]) for j in range(i, min(i + 16, len(ins)), 4)))
+    for i in range(0, len(ins), 12):
+        A("    " + " ".join("{0x%08xu, 0x%08xu, 0x%08xu, 0x%08xu}," % tuple(ins[j:j + 4]) for j in range(i, i + 12, 4)))
     A("};\n#endif")
     open(path, "w").write("\n".join(L) + "\n")
     return table, len(hdr)
