@@ -263,7 +263,14 @@ HB_DEV void rlc_scale_pair(g1& ra, g2& rs, const g1& apk, const g2a& sig, uint64
 
 // ------------------------------------------------------------------ codecs (reference crypto/bls/bls.go:67-71,109-118)
 // bytes are little-endian; the 12 u32 words of a canonical coordinate ARE its 48 bytes on this little-endian target
+// serialized inputs sit in the library's own device buffers (256-byte aligned, item strides 32 / 48 / 96 bytes): word loads
+// (LDG.E, vectorised by the compiler when n is a constant); unaligned caller pointers (device-pointer entry) fall back to bytes
 HB_DEV void load_words(uint32_t* w, const uint8_t* b, int n) {
+    if ((reinterpret_cast<uintptr_t>(b) & 3u) == 0) {
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(b);
+        for (int i = 0; i < n; i++) w[i] = p[i];
+        return;
+    }
     for (int i = 0; i < n; i++) w[i] = (uint32_t)b[4 * i] | ((uint32_t)b[4 * i + 1] << 8) | ((uint32_t)b[4 * i + 2] << 16) | ((uint32_t)b[4 * i + 3] << 24);
 }
 HB_DEV void store_words(uint8_t* b, const uint32_t* w, int n) {

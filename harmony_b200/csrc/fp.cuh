@@ -260,6 +260,12 @@ static thread_local uint64_t hb_emu_cnt_mul = 0, hb_emu_cnt_sqr = 0;      // exe
 #else
 #define HB_EMU_COUNT(x) ((void)0)
 #endif
+#ifndef HB_KARATSUBA
+#define HB_KARATSUBA 0
+#endif
+#if HB_KARATSUBA
+HB_NOINLINE void fp_mul(fp& r, const fp& a, const fp& b);      // fp_wide.cuh: Karatsuba product + separate reduction
+#else
 HB_NOINLINE void fp_mul(fp& r, const fp& a, const fp& b) {
     HB_EMU_COUNT(hb_emu_cnt_mul);
     uint32_t ra[12], rb[12], rr[12];
@@ -269,6 +275,7 @@ HB_NOINLINE void fp_mul(fp& r, const fp& a, const fp& b) {
 #pragma unroll
     for (int j = 0; j < 12; j++) r.l[j] = rr[j];
 }
+#endif
 // fp_sqr lives in fp_wide.cuh (dedicated 78-product squaring + one reduction)
 
 }  // namespace hb

@@ -11,6 +11,7 @@
 
 namespace hb {
 
+template <int N> HB_DEV void lane_mad_n(uint32_t* acc, const uint32_t* a, uint32_t b);
 // T[0..23] = a * b (plain integer product of two 12-limb values, any a, b < 2^384)
 HB_DEV void mul_wide(uint32_t* T, const uint32_t* a, const uint32_t* b) {
     uint32_t x[26], y[26];          // x: 64-bit lanes at even limb positions, y: lanes at odd positions (absolute)
@@ -28,6 +29,74 @@ HB_DEV void mul_wide(uint32_t* T, const uint32_t* a, const uint32_t* b) {
 #pragma unroll
     for (int j = 2; j < 23; j++) addc_cc(T[j], x[j], y[j]);
     addc(T[23], x[23], y[23]);
+}
+
+// T[0..11] = a * b for 6-limb operands (same even / odd lane scheme as mul_wide): 36 IMAD.WIDE
+HB_DEV void mul_wide6(uint32_t* T, const uint32_t* a, const uint32_t* b) {
+    uint32_t x[14], y[14];
+#pragma unroll
+    for (int i = 0; i < 14; i++) { x[i] = 0; y[i] = 0; }
+#pragma unroll
+    for (int i = 0; i < 6; i += 2) {
+        lane_mad_n<3>(x + i, a, b[i]);
+        lane_mad_n<3>(y + i + 1, a + 1, b[i]);
+        lane_mad_n<3>(y + i + 1, a, b[i + 1]);
+        lane_mad_n<3>(x + i + 2, a + 1, b[i + 1]);
+    }
+    T[0] = x[0];
+    add_cc(T[1], x[1], y[1]);
+#pragma unroll
+    for (int j = 2; j < 11; j++) addc_cc(T[j], x[j], y[j]);
+    addc(T[11], x[11], y[11]);
+}
+// T[0..23] = a * b by one level of Karatsuba over the 6-limb halves: 3 x 36 = 108 IMAD.WIDE instead of 144, paid with ~85 adds /
+// selects on the ALU pipe (which idles at ~1/3 while the FMA-heavy pipe is the bound: profiles/r2_probe_int.txt).
+HB_DEV void mul_wide_k(uint32_t* T, const uint32_t* a, const uint32_t* b) {
+    uint32_t z0[12], z2[12], s[6], t[6], m[12], z1[13];
+    mul_wide6(z0, a, b);
+    mul_wide6(z2, a + 6, b + 6);
+    uint32_t cs, ct;
+    add_cc(s[0], a[0], a[6]);
+#pragma unroll
+    for (int j = 1; j < 6; j++) addc_cc(s[j], a[j], a[6 + j]);
+    addc(cs, 0, 0);
+    add_cc(t[0], b[0], b[6]);
+#pragma unroll
+    for (int j = 1; j < 6; j++) addc_cc(t[j], b[j], b[6 + j]);
+    addc(ct, 0, 0);
+    mul_wide6(m, s, t);
+    // z1 = (s + cs 2^192)(t + ct 2^192) - z0 - z2 = a0 b1 + a1 b0 < 2^385: 13 limbs
+    const uint32_t ms = 0u - cs, mt = 0u - ct;
+#pragma unroll
+    for (int j = 0; j < 6; j++) z1[j] = m[j];
+    add_cc(z1[6], m[6], t[0] & ms);
+#pragma unroll
+    for (int j = 1; j < 6; j++) addc_cc(z1[6 + j], m[6 + j], t[j] & ms);
+    addc(z1[12], cs & ct, 0);
+    add_cc(z1[6], z1[6], s[0] & mt);
+#pragma unroll
+    for (int j = 1; j < 6; j++) addc_cc(z1[6 + j], z1[6 + j], s[j] & mt);
+    addc(z1[12], z1[12], 0);
+    sub_cc(z1[0], z1[0], z0[0]);
+#pragma unroll
+    for (int j = 1; j < 12; j++) subc_cc(z1[j], z1[j], z0[j]);
+    subc(z1[12], z1[12], 0);
+    sub_cc(z1[0], z1[0], z2[0]);
+#pragma unroll
+    for (int j = 1; j < 12; j++) subc_cc(z1[j], z1[j], z2[j]);
+    subc(z1[12], z1[12], 0);
+    // T = z0 + z1 2^192 + z2 2^384
+#pragma unroll
+    for (int j = 0; j < 6; j++) T[j] = z0[j];
+    add_cc(T[6], z0[6], z1[0]);
+#pragma unroll
+    for (int j = 1; j < 6; j++) addc_cc(T[6 + j], z0[6 + j], z1[j]);
+#pragma unroll
+    for (int j = 0; j < 6; j++) addc_cc(T[12 + j], z2[j], z1[6 + j]);
+    addc_cc(T[18], z2[6], z1[12]);
+#pragma unroll
+    for (int j = 7; j < 11; j++) addc_cc(T[12 + j], z2[j], 0);
+    addc(T[23], z2[11], 0);
 }
 
 // T[0..23] = a1 * b1 + a2 * b2 accumulated in ONE pair of lane accumulators (one merge instead of two + a wide add);
@@ -54,6 +123,25 @@ HB_DEV void mul_wide2(uint32_t* T, const uint32_t* a1, const uint32_t* b1, const
     addc(T[23], x[23], y[23]);
 }
 
+#ifndef HB_KARATSUBA
+#define HB_KARATSUBA 0      // 1: products through mul_wide_k (108 IMAD.WIDE) + a separate reduction instead of the interleaved 288 + 12 form
+#endif
+// T = a1 * b1 + a2 * b2 from two Karatsuba products (sum < 2^768 by the caller's contract)
+HB_DEV void mul_wide2_k(uint32_t* T, const uint32_t* a1, const uint32_t* b1, const uint32_t* a2, const uint32_t* b2) {
+    uint32_t U[24];
+    mul_wide_k(T, a1, b1); mul_wide_k(U, a2, b2);
+    add_cc(T[0], T[0], U[0]);
+#pragma unroll
+    for (int j = 1; j < 23; j++) addc_cc(T[j], T[j], U[j]);
+    addc(T[23], T[23], U[23]);
+}
+#if HB_KARATSUBA
+#define HB_MUL_WIDE mul_wide_k
+#define HB_MUL_WIDE2 mul_wide2_k
+#else
+#define HB_MUL_WIDE mul_wide
+#define HB_MUL_WIDE2 mul_wide2
+#endif
 // r[0..11] = T / 2^384 mod p for T < p * 2^384; result canonical in [0, p).  T is consumed.
 HB_DEV void redc_wide(uint32_t* r, const uint32_t* T) {
     uint32_t x[28], y[28];
@@ -188,6 +276,18 @@ HB_DEV void limbs_sub12_plus_p(uint32_t* r, const uint32_t* a, const uint32_t* b
     addc(r[11], t[11], HB_P11);
 }
 
+#if HB_KARATSUBA
+HB_NOINLINE void fp_mul(fp& r, const fp& a, const fp& b) {
+    HB_EMU_COUNT(hb_emu_cnt_mul);
+    uint32_t ra[12], rb[12], T[24], rr[12];
+#pragma unroll
+    for (int j = 0; j < 12; j++) { ra[j] = a.l[j]; rb[j] = b.l[j]; }
+    mul_wide_k(T, ra, rb);
+    redc_wide(rr, T);
+#pragma unroll
+    for (int j = 0; j < 12; j++) r.l[j] = rr[j];
+}
+#endif
 // r = a^2 / R mod p: 78 + 156 = 234 IMAD.WIDE (the exponentiation chains of sqrt / inverse / Legendre are ~80% squarings)
 HB_NOINLINE void fp_sqr(fp& r, const fp& a) {
     HB_EMU_COUNT(hb_emu_cnt_sqr);

@@ -91,6 +91,7 @@ int reserve(cudaStream_t s, size_t bytes, Scratch** out) {
 }
 inline unsigned blocks_for(size_t n, unsigned tpb) { return (unsigned)((n + tpb - 1) / tpb); }
 #define LAUNCH(kern, grid, block, strm, ...) do { kern<<<(grid), (block), 0, (strm)>>>(__VA_ARGS__); g.launches++; } while (0)
+#define LAUNCH_SMEM(kern, grid, block, smem, strm, ...) do { kern<<<(grid), (block), (smem), (strm)>>>(__VA_ARGS__); g.launches++; } while (0)
 
 constexpr unsigned TPB = 64;      // heavy kernels: 64-thread CTAs
 // persistent launch geometry for the grid-stride kernels: at most `tpsm` resident threads per SM (default 384: measured 256: 267 ms,
@@ -209,11 +210,11 @@ void launch_verify_tail(size_t B, const VerifyBufs& v, Scratch* sc, const uint8_
         if (G == 8) {
             LAUNCH(k_rlc_group_sum<8>, heavy_blocks(ng), TPB, s, ng, v.S, v.Sg);
             STAGE_EV(5, sc, s);
-            LAUNCH(k_rlc_pairing_split<8>, pb, pt, s, ng, v.pk_scaled, v.hm, v.Sg, v.bad, v.group_ok);
+            LAUNCH_SMEM(k_rlc_pairing_split<8>, pb, pt, HB_SMEM_F ? pt * HB_SMEM_F_WORDS * 4 : 0, s, ng, v.pk_scaled, v.hm, v.Sg, v.bad, v.group_ok);
         } else {
             LAUNCH(k_rlc_group_sum<4>, heavy_blocks(ng), TPB, s, ng, v.S, v.Sg);
             STAGE_EV(5, sc, s);
-            LAUNCH(k_rlc_pairing_split<4>, pb, pt, s, ng, v.pk_scaled, v.hm, v.Sg, v.bad, v.group_ok);
+            LAUNCH_SMEM(k_rlc_pairing_split<4>, pb, pt, HB_SMEM_F ? pt * HB_SMEM_F_WORDS * 4 : 0, s, ng, v.pk_scaled, v.hm, v.Sg, v.bad, v.group_ok);
         }
         // exact pass over the rounds of failed groups only (compacted on the device; the launches are sized for the worst case and
         // return at once when the list is short or empty)
@@ -432,8 +433,13 @@ int hbls_init_device(int device) {
     g.rlc_min = envll("HBLS_RLC_MIN", 16384); g.rlc_g = envll("HBLS_RLC_G", 0); g.coop_max = envll("HBLS_COOP_MAX", 16383);
     g.tpsm = envll("HBLS_TPSM", 384); g.tpsm_split = envll("HBLS_TPSM_SPLIT", 512); g.tpsm_light = envll("HBLS_TPSM_LIGHT", 1024);
     // the heavy kernels keep their Fp12 temporaries in per-thread local memory: give L1 the whole 228 KB
+#if HB_SMEM_F
+    cudaFuncSetAttribute(k_rlc_pairing_split<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, HB_TPB_SPLIT * HB_SMEM_F_WORDS * 4);
+    cudaFuncSetAttribute(k_rlc_pairing_split<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, HB_TPB_SPLIT * HB_SMEM_F_WORDS * 4);
+#else
     cudaFuncSetAttribute(k_rlc_pairing_split<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_rlc_pairing_split<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+#endif
     cudaFuncSetAttribute(k_pairing_verify_split, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_pairing_verify_split_list, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_hash_to_g2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);

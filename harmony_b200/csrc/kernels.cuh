@@ -518,6 +518,10 @@ template <int G> __global__ void k_rlc_group_sum(size_t ngroups, const g2* S, g2
     g2a a; pt_to_aff(a, acc); Sg[g] = a;
   }
 }
+#ifndef HB_SMEM_F
+#define HB_SMEM_F 0       // 1: keep each lane's Fp12 accumulator in dynamic shared memory (experiment: profiles/r2_stage_times.txt)
+#endif
+#define HB_SMEM_F_WORDS 73
 // lane pair per group: (G + 1)-pair Miller loop, final exponentiation, verdict
 template <int G> __global__ void __launch_bounds__(HB_TPB_SPLIT, HB_MINBLOCKS_SPLIT) k_rlc_pairing_split(size_t ngroups, const g1a* pk_scaled_neg, const g2a* hm, const g2a* Sg,
                                  const uint8_t* bad, uint8_t* group_ok) {
@@ -544,7 +548,13 @@ template <int G> __global__ void __launch_bounds__(HB_TPB_SPLIT, HB_MINBLOCKS_SP
         ps[G] = &gen_sh;
         const fp* s4 = reinterpret_cast<const fp*>(&Sg[gg]);
         qx[G].c = s4[role]; qy[G].c = s4[2 + role];
+#if HB_SMEM_F
+        // the Miller accumulator / exponentiation value of this lane in shared memory (73-word stride: conflict-free), not on the stack
+        extern __shared__ uint32_t hb_dyn_smem[];
+        fp12_t<fp2h>& m = *reinterpret_cast<fp12_t<fp2h>*>(hb_dyn_smem + (size_t)threadIdx.x * HB_SMEM_F_WORDS);
+#else
         fp12_t<fp2h> m;
+#endif
         miller_loop_multi<fp2h, G + 1>(m, ps, qx, qy);
         final_exp(m, m);
         const bool one = fp12_is_one(m);

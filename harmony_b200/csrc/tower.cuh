@@ -465,7 +465,7 @@ HB_NOINLINE void fp2_mul(fp2h& r, const fp2h& x, const fp2h& y) {
     subc(ny[11], HB_P11, yp[11]);
 #pragma unroll
     for (int j = 0; j < 12; j++) { A[j] = im ? yp[j] : yo[j]; B[j] = im ? yo[j] : ny[j]; }
-    mul_wide2(T, xo, A, xp, B);                        // < 2 p^2 < p R
+    HB_MUL_WIDE2(T, xo, A, xp, B);                     // < 2 p^2 < p R
     redc_wide(rr, T);
 #pragma unroll
     for (int j = 0; j < 12; j++) r.c.l[j] = rr[j];
@@ -483,7 +483,7 @@ HB_NOINLINE void fp2_sqr(fp2h& r, const fp2h& x) {
     limbs_add12(t, xp, xp);            // 2 xp < 2p
 #pragma unroll
     for (int j = 0; j < 12; j++) { A[j] = im ? xo[j] : s[j]; B[j] = im ? t[j] : d[j]; }
-    mul_wide(T, A, B);                 // < 4 p^2 < p R
+    HB_MUL_WIDE(T, A, B);              // < 4 p^2 < p R
     redc_wide(rr, T);
 #pragma unroll
     for (int j = 0; j < 12; j++) r.c.l[j] = rr[j];

@@ -43,7 +43,7 @@ HB_NOINLINE void vm_mul(uint32_t* slots, int dst, int a, int b, int im) {
     subc(nbi[11], HB_P11, bi[11]);
 #pragma unroll
     for (int j = 0; j < 12; j++) { y1[j] = im ? bi[j] : br[j]; y2[j] = im ? br[j] : nbi[j]; }
-    mul_wide2(T, ar, y1, ai, y2);                      // < 2 p^2 < p R
+    HB_MUL_WIDE2(T, ar, y1, ai, y2);                   // < 2 p^2 < p R
     redc_wide(rr, T);
     vm_st(slots, dst, im, rr);
 }
@@ -56,7 +56,7 @@ HB_NOINLINE void vm_sqr(uint32_t* slots, int dst, int a, int im) {
     limbs_add12(t, ai, ai);            // < 2p
 #pragma unroll
     for (int j = 0; j < 12; j++) { A[j] = im ? ar[j] : s[j]; B[j] = im ? t[j] : d[j]; }
-    mul_wide(T, A, B);                 // < 4 p^2 < p R
+    HB_MUL_WIDE(T, A, B);              // < 4 p^2 < p R
     redc_wide(rr, T);
     vm_st(slots, dst, im, rr);
 }

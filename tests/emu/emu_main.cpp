@@ -99,6 +99,16 @@ extern "C" int emu_legendre_check(const uint32_t* vals, int n) {
     return bad;
 }
 
+// Karatsuba wide product against the schoolbook one on n operand pairs (12 words each, any values); returns mismatches
+extern "C" int emu_mul_wide_k_check(const uint32_t* a, const uint32_t* b, int n) {
+    int bad = 0;
+    for (int i = 0; i < n; i++) {
+        uint32_t T1[24], T2[24];
+        mul_wide(T1, a + 12 * i, b + 12 * i); mul_wide_k(T2, a + 12 * i, b + 12 * i);
+        for (int j = 0; j < 24; j++) if (T1[j] != T2[j]) { bad++; break; }
+    }
+    return bad;
+}
 // binary-GCD inversion against the Fermat exponentiation on n values (Montgomery limbs in, 12 words each); returns mismatches
 extern "C" int emu_inv_gcd_check(const uint32_t* vals, int n) {
     int bad = 0;

@@ -9,8 +9,9 @@ from harmony_b200 import workload as wl
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-# "batch_inv" = the HB_BATCH_INV build of the kernels (one shared inversion per 4 items of a persistent thread)
-@pytest.fixture(scope="module", params=["default", "batch_inv"])
+# "default" = the shipped build (shared inversions: one per 8 items of a persistent thread); "plain" = one inversion per item
+# (round-1 behaviour, -DHB_BATCH_INV=0); "karatsuba" = products through mul_wide_k (-DHB_KARATSUBA=1, timed variant)
+@pytest.fixture(scope="module", params=["default", "plain", "karatsuba"])
 def emuk(request):
     variant = request.param
     src = os.path.join(ROOT, "tests", "emu", "emu_kernels.cpp")
@@ -18,7 +19,7 @@ def emuk(request):
     csrc = os.path.join(ROOT, "harmony_b200", "csrc")
     deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
-        flags = {"default": ["-DHB_BATCH_INV=0"], "batch_inv": ["-DHB_BATCH_INV=1"]}[variant]
+        flags = {"default": [], "plain": ["-DHB_BATCH_INV=0"], "karatsuba": ["-DHB_KARATSUBA=1"]}[variant]
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread"] + flags + ["-o", out, src])
     L = ctypes.CDLL(out)
     L.emu_aggregate_verify_batch.argtypes = [ctypes.c_int, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_size_t,
@@ -101,7 +102,7 @@ def test_stage_counts_pinned(emuk, oracle, request):
     import importlib.util
     spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py")); bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
-    batch_inv = "batch_inv" in request.node.name
+    batch_inv = "plain" not in request.node.name
     sks = bench.make_committee_sks()
     pks = [oracle.get_public_key(wl.sk_bytes(k)) for k in sks]
     B = 32

@@ -147,6 +147,20 @@ def test_emu_legendre_jacobi(emu):
     assert emu.emu_legendre_check(arr, len(vals)) == 0
 
 
+def test_emu_karatsuba_wide_product(emu):
+    """mul_wide_k (one Karatsuba level over 6-limb halves) == the schoolbook 12 x 12 product on random and extreme operands
+    (all-ones halves exercise the carry bits of a0 + a1 and b0 + b1)."""
+    rng = random.Random(12)
+    F = (1 << 384) - 1; H = (1 << 192) - 1
+    vals = [(0, 0), (F, F), (H, H), (F, H), (H << 192, H << 192), (F, 1), (1 << 383, 1 << 383), ((H << 192) | 1, (H << 192) | (1 << 191))]
+    vals += [(rng.getrandbits(384), rng.getrandbits(384)) for _ in range(400)]
+    n = len(vals)
+    A = (ctypes.c_uint32 * (12 * n))(); Bv = (ctypes.c_uint32 * (12 * n))()
+    for i, (x, y) in enumerate(vals):
+        for j in range(12): A[12 * i + j] = (x >> (32 * j)) & 0xffffffff; Bv[12 * i + j] = (y >> (32 * j)) & 0xffffffff
+    assert emu.emu_mul_wide_k_check(A, Bv, n) == 0
+
+
 def test_emu_inv_gcd(emu):
     """fp_inv_gcd (binary extended Euclid, used on the latency path) == a^(p-2) on edge values and random ones."""
     p = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab

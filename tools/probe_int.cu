@@ -220,6 +220,21 @@ __global__ void k_chain32(int iters, const uint32_t* in, uint32_t* out) {
 #pragma unroll
     for (int j = 0; j < 12; j++) out[12 * i + j] = x[j];
 }
+// the shipped limbs with ONE Karatsuba level in the product (fp_wide.cuh mul_wide_k) + a separate reduction: 108 + 156 IMAD instead of 300
+__device__ __forceinline__ void fp_mul_k(uint32_t* r, const uint32_t* a, const uint32_t* b) { uint32_t T[24]; mul_wide_k(T, a, b); redc_wide(r, T); }
+__device__ __forceinline__ void fp_mul_w(uint32_t* r, const uint32_t* a, const uint32_t* b) { uint32_t T[24]; mul_wide(T, a, b); redc_wide(r, T); }
+template <int K> __global__ void k_chain32w(int iters, const uint32_t* in, uint32_t* out) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t x[12], y[12], r2[12], one[12];
+#pragma unroll
+    for (int j = 0; j < 12; j++) { x[j] = in[24 * i + j]; y[j] = in[24 * i + 12 + j]; r2[j] = K_R2[j]; one[j] = j == 0; }
+    fp_mul_regs(x, x, r2); fp_mul_regs(y, y, r2);
+#pragma unroll 1
+    for (int k = 0; k < iters; k++) { if (K) { fp_mul_k(x, x, y); fp_mul_k(y, y, x); } else { fp_mul_w(x, x, y); fp_mul_w(y, y, x); } }
+    fp_mul_regs(x, x, one);
+#pragma unroll
+    for (int j = 0; j < 12; j++) out[12 * i + j] = x[j];
+}
 template <int V> __global__ void k_chain28(int iters, const uint32_t* in, uint32_t* out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t w[12], x[14], y[14], r2[14], one[14];
@@ -267,6 +282,8 @@ static void do_launch(void* c) {
     case 6: k_chain32<<<l->blocks, l->threads>>>(l->iters, (const uint32_t*)l->p0, (uint32_t*)l->p1); break;
     case 7: k_chain28<0><<<l->blocks, l->threads>>>(l->iters, (const uint32_t*)l->p0, (uint32_t*)l->p1); break;
     case 8: k_chain28<1><<<l->blocks, l->threads>>>(l->iters, (const uint32_t*)l->p0, (uint32_t*)l->p1); break;
+    case 11: k_chain32w<0><<<l->blocks, l->threads>>>(l->iters, (const uint32_t*)l->p0, (uint32_t*)l->p1); break;
+    case 12: k_chain32w<1><<<l->blocks, l->threads>>>(l->iters, (const uint32_t*)l->p0, (uint32_t*)l->p1); break;
     }
 }
 
@@ -298,13 +315,14 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&din, h.size() * 4)); CK(cudaMalloc(&d32, 12 * (size_t)maxthreads * 4)); CK(cudaMalloc(&d28, 12 * (size_t)maxthreads * 4)); CK(cudaMalloc(&d28v, 12 * (size_t)maxthreads * 4));
     CK(cudaMemcpy(din, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
     const int iters = 512;
-    for (int v = 6; v < 9; v++) {
+    uint32_t *dw, *dk; CK(cudaMalloc(&dw, 12 * (size_t)maxthreads * 4)); CK(cudaMalloc(&dk, 12 * (size_t)maxthreads * 4));
+    for (int v : {6, 7, 8, 11, 12}) {
         if (only >= 0 && only != v) continue;
         for (int tpsm = 128; tpsm <= 1024; tpsm *= 2) {
-            L l{sms * (tpsm / 128), 128, iters, din, v == 6 ? d32 : (v == 7 ? d28 : d28v), v};
+            L l{sms * (tpsm / 128), 128, iters, din, v == 6 ? d32 : (v == 7 ? d28 : (v == 8 ? d28v : (v == 11 ? dw : dk))), v};
             float ms = time_ms(0, do_launch, &l);
             double muls = (double)l.blocks * l.threads * (2.0 * iters + 3);
-            printf(", \"%s_t%d_Gmulps\": %.3f", v == 6 ? "mul32x12" : (v == 7 ? "mul28x14" : "mul28x14_volatile"), tpsm, muls / (ms * 1e-3) / 1e9);
+            printf(", \"%s_t%d_Gmulps\": %.3f", v == 6 ? "mul32x12" : (v == 7 ? "mul28x14" : (v == 8 ? "mul28x14_volatile" : (v == 11 ? "mul32x12_wide_plus_redc" : "mul32x12_karatsuba_plus_redc"))), tpsm, muls / (ms * 1e-3) / 1e9);
         }
     }
     if (only < 0) {
@@ -315,7 +333,12 @@ int main(int argc, char** argv) {
         for (size_t i = 0; i < a.size(); i++) { bad += a[i] != b[i]; nz += a[i] != 0; }
         CK(cudaMemcpy(b.data(), d28v, b.size() * 4, cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < a.size(); i++) badv += a[i] != b[i];
-        printf(", \"mul28_vs_mul32_mismatching_words\": %zu, \"mul28v_vs_mul32_mismatching_words\": %zu, \"nonzero_words\": %zu", bad, badv, nz);
+        size_t badw = 0, badk = 0;
+        CK(cudaMemcpy(b.data(), dw, b.size() * 4, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < a.size(); i++) badw += a[i] != b[i];
+        CK(cudaMemcpy(b.data(), dk, b.size() * 4, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < a.size(); i++) badk += a[i] != b[i];
+        printf(", \"mul28_vs_mul32_mismatching_words\": %zu, \"mul28v_vs_mul32_mismatching_words\": %zu, \"wide_vs_mul32_mismatching_words\": %zu, \"karatsuba_vs_mul32_mismatching_words\": %zu, \"nonzero_words\": %zu", bad, badv, badw, badk, nz);
     }
     printf("}\n");
     return 0;
