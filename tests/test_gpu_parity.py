@@ -520,7 +520,7 @@ def test_config4_ten_thousand_triples_one_percent_invalid(gbls, oracle):
         else: pk[48 * i:48 * i + 48] = b"\xff" * 48
     old = gbls.GetParam("rlc_min")
     try:
-        gbls.SetParam("rlc_min", 1024)               # batched groups (default threshold 16 384: below it the warp-per-item exact kernel is faster)
+        gbls.SetParam("rlc_min", 1024)               # batched groups (default threshold 6 144: below it the warp-per-item exact kernel is faster)
         res = gbls.VerifyBatch(bytes(pk), bytes(sg), bytes(mm), 32)
         info = gbls.LastBatchInfo()
     finally: gbls.SetParam("rlc_min", old)
