@@ -139,10 +139,12 @@ std::vector<uint64_t> rlc_draw_items(size_t k) {
 
 // ------------------------------------------------------------------ one verification pass over device-resident inputs.
 size_t verify_scratch_bytes(size_t B) {
-    return B * (sizeof(g2a) * 2 + sizeof(g1a) * 2 + sizeof(g1) + sizeof(g2) + 16 + 4) + (B / HB_RLC_G + 1) * (sizeof(g2a) + 8) + 40 * 256;
+    return B * (sizeof(g2a) * 2 + sizeof(g1a) * 2 + sizeof(g1) + sizeof(g2) + 16 + 4) + (B / HB_RLC_G + 1) * (sizeof(g2a) + 8) + 40 * 256
+           + (B <= 8192 ? B * (6 * sizeof(fp2) + 1) + 512 : 0);                 // latency path: Miller values of (B, sigma)
 }
 struct VerifyBufs { g2a* sig; g2a* hm; g1a* pkneg; g1* apk; uint8_t* ok_sig; uint8_t* ok_hm; uint8_t* ok_pk;
-                    g1a* pk_scaled; g2* S; uint8_t* bad; g2a* Sg; uint8_t* group_ok; uint32_t* fail_list; unsigned* counts; };
+                    g1a* pk_scaled; g2* S; uint8_t* bad; g2a* Sg; uint8_t* group_ok; uint32_t* fail_list; unsigned* counts;
+                    fp2* f1; uint8_t* irr1; };
 VerifyBufs carve_verify(Arena& ar, size_t B) {
     VerifyBufs v;
     v.sig = ar.take<g2a>(B); v.hm = ar.take<g2a>(B); v.pkneg = ar.take<g1a>(B); v.apk = ar.take<g1>(B);
@@ -150,6 +152,8 @@ VerifyBufs carve_verify(Arena& ar, size_t B) {
     v.pk_scaled = ar.take<g1a>(B); v.S = ar.take<g2>(B); v.bad = ar.take<uint8_t>(B);
     v.Sg = ar.take<g2a>(B / HB_RLC_G + 1); v.group_ok = ar.take<uint8_t>(B / HB_RLC_G + 1);
     v.fail_list = ar.take<uint32_t>(B); v.counts = ar.take<unsigned>(2);
+    v.f1 = nullptr; v.irr1 = nullptr;
+    if (B <= 8192) { v.f1 = ar.take<fp2>(6 * B); v.irr1 = ar.take<uint8_t>(B); }
     return v;
 }
 // Small batches (latency path): the inputs are on the device from here on -- signature decode and hash-to-G2 may start on the
@@ -179,8 +183,11 @@ void launch_verify_tail(size_t B, const VerifyBufs& v, Scratch* sc, const uint8_
     const bool forked = pairs && sc->forked;              // decode on aux[0], hash on aux[1], concurrently with the work above
     cudaStream_t sd = forked ? g.aux[0] : s, sh = forked ? g.aux[1] : s;
     if (forked) { cudaStreamWaitEvent(sd, sc->fork, 0); cudaStreamWaitEvent(sh, sc->fork, 0); }
+    const unsigned coop_grid = (unsigned)(B < (size_t)g.sm_count * 9 ? B : (size_t)g.sm_count * 9);
+    const bool split_ml = forked && v.f1 != nullptr;       // Miller value of (B, sigma) on the decode stream, beside hash-to-G2
     if (pairs) LAUNCH(k_g2_decode_pair, blocks_for(2 * B, 32), 32, sd, B, d_sig96, v.sig, v.ok_sig, 1);
     else LAUNCH(k_g2_decode, heavy_blocks(B), TPB, s, B, d_sig96, v.sig, v.ok_sig, 1);
+    if (split_ml) LAUNCH(k_miller1_coop, coop_grid, 32, sd, B, v.sig, v.ok_sig, v.f1, v.irr1);
     STAGE_EV(3, sc, s);
     if (same_msg && B > 1) {
         if (pairs) LAUNCH(k_hash_to_g2_pair, 1, 32, sh, (size_t)1, d_msgs, msg_len, v.hm, v.ok_hm);
@@ -239,8 +246,10 @@ void launch_verify_tail(size_t B, const VerifyBufs& v, Scratch* sc, const uint8_
         STAGE_EV(5, sc, s);
         const bool full = 2 * B >= (size_t)g.sm_count * HB_TPB_SPLIT;
         const bool coop = (long long)B <= g.coop_max;        // latency form: one warp per round (vm.cuh), 9 resident rounds per SM
-        if (coop)
-            LAUNCH(k_pairing_coop, (unsigned)(B < (size_t)g.sm_count * 9 ? B : (size_t)g.sm_count * 9), 32, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
+        if (coop && split_ml)
+            LAUNCH(k_pairing_coop2, coop_grid, 32, s, B, v.f1, v.irr1, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
+        else if (coop)
+            LAUNCH(k_pairing_coop, coop_grid, 32, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
         else if (full)
             LAUNCH(k_pairing_verify_split, split_blocks(2 * B), HB_TPB_SPLIT, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results, (const int*)nullptr);
         else

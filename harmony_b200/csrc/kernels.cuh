@@ -455,6 +455,68 @@ __global__ void __launch_bounds__(HB_SUM_THREADS) k_g2_sum_jac(size_t n, const g
     if (threadIdx.x == 0) out[0] = acc;
 }
 
+// ---- latency form, split in two: the Miller value of (B, sigma) only needs the decoded signature, so it is computed on the decode
+// stream while hash-to-G2 (the long pole of a single check) still runs; the second kernel adds the pair (-apk, H(m)) and the final
+// exponentiation.  f1: 6 Fp2 per round (tower order); irr1[j] = 1 when the signature is the identity / did not decode.
+__global__ void __launch_bounds__(32) k_miller1_coop(size_t B, const g2a* sig, const uint8_t* ok_sig, fp2* f1, uint8_t* irr1) {
+    __shared__ uint32_t slots[VM_SMEM_WORDS];
+    const int lane = threadIdx.x & 31;
+    vm_load_consts(slots);
+    for (size_t j = blockIdx.x; j < B; j += gridDim.x) {
+        bool zero = true;
+        if (lane < 4) {
+            fp2 v; fp2_zero(v);
+            if (lane == 0) fp_set(v.a, K_G1_X); else if (lane == 1) fp_set(v.a, K_G1_Y); else if (lane == 2) v = sig[j].x; else v = sig[j].y;
+            vm_set_fp2(slots, VM_R_P2X + lane, v);
+            zero = fp_is_zero(v.a) & fp_is_zero(v.b);
+        }
+        const unsigned zmask = __ballot_sync(0xffffffffu, zero);
+        const bool skip = (ok_sig && !ok_sig[j]) || (zmask & 0xc) == 0xc;
+        if (lane == 0) irr1[j] = skip ? 1 : 0;
+        if (skip) { __syncwarp(); continue; }
+        vm_run(VM_P_ML1_INIT, slots);
+        for (int i = 62; i >= 0; i--) {
+            vm_run(VM_P_ML1_DBL, slots);
+            if ((K_Z_ABS >> i) & 1) vm_run(VM_P_ML1_ADD, slots);
+        }
+        if (lane < 12) vm_ld(reinterpret_cast<fp*>(&f1[6 * j + (lane >> 1)])[lane & 1].l, slots, VM_R_F0 + (lane >> 1), lane & 1);
+        __syncwarp();
+    }
+}
+__global__ void __launch_bounds__(32) k_pairing_coop2(size_t B, const fp2* f1, const uint8_t* irr1, const g1a* pk_neg, const g2a* hm,
+                                  const uint8_t* ok_a, const uint8_t* ok_b, const uint8_t* ok_c, uint8_t* results) {
+    __shared__ uint32_t slots[VM_SMEM_WORDS];
+    const int lane = threadIdx.x & 31;
+    vm_load_consts(slots);
+    for (size_t j = blockIdx.x; j < B; j += gridDim.x) {
+        const bool good = (!ok_a || ok_a[j]) && (!ok_b || ok_b[j]) && (!ok_c || ok_c[j]);
+        bool zero = true;
+        if (lane < 4) {
+            fp2 v; fp2_zero(v);
+            const g1a pk = pk_neg[j];
+            if (lane == 0) v.a = pk.x; else if (lane == 1) v.a = pk.y; else if (lane == 2) v = hm[j].x; else v = hm[j].y;
+            vm_set_fp2(slots, VM_R_P2X + lane, v);
+            zero = fp_is_zero(v.a) & fp_is_zero(v.b);
+        }
+        const unsigned zmask = __ballot_sync(0xffffffffu, zero);
+        const bool irregular = irr1[j] != 0 || (zmask & 0x3) == 0x3 || (zmask & 0xc) == 0xc;
+        bool one = false;
+        if (!irregular) {
+            if (lane < 12) vm_st(slots, VM_R_A0 + (lane >> 1), lane & 1, reinterpret_cast<const fp*>(&f1[6 * j + (lane >> 1)])[lane & 1].l);
+            __syncwarp();
+            vm_run(VM_P_ML1_INIT, slots);
+            for (int i = 62; i >= 0; i--) {
+                vm_run(VM_P_ML1_DBL, slots);
+                if ((K_Z_ABS >> i) & 1) vm_run(VM_P_ML1_ADD, slots);
+            }
+            vm_run(VM_P_FMULA, slots);
+            one = vm_final_exp_is_one(slots);
+        }
+        if (lane == 0) results[j] = irregular ? 0xFF : ((good && one) ? 1 : 0);
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------ random-linear-combination batch (R9 / R10 GPU form)
 // prod_j [ e(B, sigma_j) e(-apk_j, H_j) ]^{r_j} == 1 with 64-bit r_j: the G rounds of a group share ONE Miller accumulator
 // (pairs (-r_j apk_j, H_j) plus (B, sum_j r_j sigma_j)) and ONE final exponentiation.  The rounds of a group that fails -- or

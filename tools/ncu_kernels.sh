@@ -1,6 +1,16 @@
-# tools/ncu_kernels.sh -- one `ncu --set full` capture per big kernel of the aggregate-verify step (run on the GPU box):
-#   gpurun -- 'bash tools/ncu_kernels.sh'   -> gpurun_out/r2_<kernel>.ncu-rep ; summarise here with tools/ncu_summary.py
-for k in k_hash_to_g2 k_g2_decode k_rlc_scale k_mask_aggregate_serial; do
-  timeout 500 ncu --set full --import-source on --clock-control none -k regex:^$k -c 1 -o gpurun_out/r2_$k python tools/profile_target.py 303104 1 > gpurun_out/r2_ncu_$k.log 2>&1
-done
-HBLS_COOP_MAX=100000 HBLS_RLC_MIN=1000000 timeout 500 ncu --set full --import-source on --clock-control none -k regex:k_pairing_coop -c 1 -o gpurun_out/r2_k_pairing_coop python tools/profile_target.py 1332 1 > gpurun_out/r2_ncu_coop.log 2>&1
+# tools/ncu_kernels.sh -- one `ncu --set full` capture per big kernel of the aggregate-verify step (run on the GPU box); the reports
+# are turned into the two CSV pages tools/ncu_summary.py reads (the .ncu-rep files themselves exceed gpurun's 64 MiB return limit):
+#   gpurun -- 'bash tools/ncu_kernels.sh'   then here:  python tools/ncu_summary.py gpurun_out/r2_<k>_raw.csv gpurun_out/r2_<k>_src.csv "<title>"
+cap() {  # name regex rounds [env...]
+  name=$1; rx=$2; rounds=$3
+  timeout 500 ncu --set full --import-source on --clock-control none -k regex:$rx -c 1 -o /tmp/r2_$name python tools/profile_target.py $rounds 1 > gpurun_out/r2_ncu_$name.log 2>&1
+  ncu -i /tmp/r2_$name.ncu-rep --page raw --csv > gpurun_out/r2_${name}_raw.csv 2>/dev/null
+  ncu -i /tmp/r2_$name.ncu-rep --page source --csv > gpurun_out/r2_${name}_src.csv 2>/dev/null
+  rm -f /tmp/r2_$name.ncu-rep
+}
+cap k_hash_to_g2 '^k_hash_to_g2$|hb::k_hash_to_g2\(' 303104
+cap k_g2_decode 'k_g2_decode\(' 303104
+cap k_rlc_scale 'k_rlc_scale' 303104
+cap k_mask_aggregate_serial 'k_mask_aggregate_serial' 303104
+export HBLS_COOP_MAX=100000 HBLS_RLC_MIN=1000000
+cap k_pairing_coop 'k_pairing_coop' 1332
