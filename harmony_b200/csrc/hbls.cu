@@ -38,7 +38,7 @@ struct Ctx {
     bool stage_timing = false; Scratch* stage_sc = nullptr;
     int batch_mode = 1;                                     // 1: random-linear-combination groups + exact pass over failed groups, 0: exact per round
     // tuning (hbls_set_param)
-    long long rlc_min = 6144, rlc_g = 0, tpsm = 384, tpsm_split = 512, tpsm_light = 1024, coop_max = 6143, overlap = 1;
+    long long rlc_min = 6144, rlc_g = 0, tpsm = 384, tpsm_split = 512, tpsm_light = 1024, coop_max = 6143, overlap = 1, coop_wpsm = 14;
     // coefficient stream: ChaCha20 keyed from /dev/urandom, block counter = call number
     uint32_t chacha_key[8] = {}; uint64_t rlc_calls = 0;
     // last batch
@@ -183,7 +183,8 @@ void launch_verify_tail(size_t B, const VerifyBufs& v, Scratch* sc, const uint8_
     const bool forked = pairs && sc->forked;              // decode on aux[0], hash on aux[1], concurrently with the work above
     cudaStream_t sd = forked ? g.aux[0] : s, sh = forked ? g.aux[1] : s;
     if (forked) { cudaStreamWaitEvent(sd, sc->fork, 0); cudaStreamWaitEvent(sh, sc->fork, 0); }
-    const unsigned coop_grid = (unsigned)(B < (size_t)g.sm_count * 9 ? B : (size_t)g.sm_count * 9);
+    const size_t coop_cap = (size_t)g.sm_count * (size_t)(g.coop_wpsm > 0 ? g.coop_wpsm : 1);      // resident warps (one round each)
+    const unsigned coop_grid = (unsigned)(B < coop_cap ? B : coop_cap);
     const bool split_ml = forked && v.f1 != nullptr;       // Miller value of (B, sigma) on the decode stream, beside hash-to-G2
     if (pairs) LAUNCH(k_g2_decode_pair, blocks_for(2 * B, 32), 32, sd, B, d_sig96, v.sig, v.ok_sig, 1);
     else LAUNCH(k_g2_decode, heavy_blocks(B), TPB, s, B, d_sig96, v.sig, v.ok_sig, 1);
@@ -245,7 +246,7 @@ void launch_verify_tail(size_t B, const VerifyBufs& v, Scratch* sc, const uint8_
         // small ones 64-thread CTAs spread over the SMs.
         STAGE_EV(5, sc, s);
         const bool full = 2 * B >= (size_t)g.sm_count * HB_TPB_SPLIT;
-        const bool coop = (long long)B <= g.coop_max;        // latency form: one warp per round (vm.cuh), 9 resident rounds per SM
+        const bool coop = (long long)B <= g.coop_max;        // latency form: one warp per round (vm.cuh), up to 14 resident rounds per SM (14.4 KB of slots, 138 registers)
         if (coop && split_ml)
             LAUNCH(k_pairing_coop2, coop_grid, 32, s, B, v.f1, v.irr1, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
         else if (coop)
@@ -478,6 +479,7 @@ static long long* param_slot(const char* name) {
     if (!strcmp(name, "tpsm_light")) return &g.tpsm_light;
     if (!strcmp(name, "coop_max")) return &g.coop_max;
     if (!strcmp(name, "overlap")) return &g.overlap;
+    if (!strcmp(name, "coop_wpsm")) return &g.coop_wpsm;
     return nullptr;
 }
 int hbls_set_param(const char* name, long long value) {

@@ -5,7 +5,7 @@
 // ~10^4 dependent field products long.  Here the Miller loop and the final exponentiation run as straight-line STEP PROGRAMS over
 // Fp2 values held in shared memory (vm_programs.cuh, generated and CPU-verified by tools/vmgen.py): in every step each of the 16
 // lane pairs of the warp executes one Fp2 operation -- a product, a squaring, or a small-integer linear combination -- so up to 16
-// independent Fp2 products are in flight.  The whole working set (232 slots x 100 B) stays in shared memory: no local-memory stack.
+// independent Fp2 products are in flight.  The whole working set (144 slots x 100 B) stays in shared memory: no local-memory stack.
 // Linear combinations are stored per lane role as lists of atoms (+- m x one half of one slot) so that all 32 lanes of a step run
 // the same branch-free loop and reduce once.
 //
@@ -192,7 +192,7 @@ HB_NOINLINE bool vm_final_exp_is_one(uint32_t* slots) {
     vm_expz(slots); vm_run(VM_P_GLUE2, slots);
     vm_expz(slots); vm_run(VM_P_GLUE3, slots);
     vm_expz(slots); vm_run(VM_P_GLUE4, slots);
-    vm_expz(slots); vm_run(VM_P_GLUE5, slots);
+    vm_expz(slots); vm_run(VM_P_GLUE5, slots); vm_run(VM_P_GLUE6, slots);
     // result in ACC0..5: lanes 0..11 compare one half each against 1
     uint32_t diff = 0;
     if (lane < 12) {

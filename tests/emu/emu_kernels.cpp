@@ -177,7 +177,7 @@ extern "C" int emu_vm_pairing(const uint8_t* pk48, const uint8_t* sig96, const u
     emu_vm_expz(slots); emu_vm_run(VM_P_GLUE2, slots);
     emu_vm_expz(slots); emu_vm_run(VM_P_GLUE3, slots);
     emu_vm_expz(slots); emu_vm_run(VM_P_GLUE4, slots);
-    emu_vm_expz(slots); emu_vm_run(VM_P_GLUE5, slots);
+    emu_vm_expz(slots); emu_vm_run(VM_P_GLUE5, slots); emu_vm_run(VM_P_GLUE6, slots);
     fp one; fp_one(one); uint32_t diff = 0;
     for (int lane = 0; lane < 12; lane++) {
         fp x; vm_ld(x.l, slots, VM_R_ACC0 + (lane >> 1), lane & 1);

@@ -236,7 +236,7 @@ REG_STATE = ["T1X", "T1Y", "T1Z", "T2X", "T2Y", "T2Z"] + r6("F") + r6("M") + r6(
 REGS = REG_CONST + REG_IN + REG_STATE
 assert len(set(REGS)) == len(REGS), "duplicate register name"
 SLOT = {r: i for i, r in enumerate(REGS)}
-NSLOTS = 232        # slots per warp (100 B each): registers + temporaries
+NSLOTS = 144        # slots per warp (100 B each): 78 registers + temporaries; lowest-free-first allocation keeps every program under it (14.4 KB per warp)
 
 def build_programs(make_graph):
     """every program as a function of a fresh graph; returns {name: graph}"""
@@ -360,11 +360,13 @@ def build_programs(make_graph):
         t = fp12_conj(get6(g, "ACC"))
         put6(g, "X", t); put6(g, "ACC", t)
     @prog
-    def p_glue5(g, k):
-        c = get6(g, "C"); m = get6(g, "M")
-        d = fp12_mul(fp12_mul(fp12_conj(get6(g, "ACC")), fp12_frob2(c, k)), fp12_conj(c))
-        r = fp12_mul(d, fp12_mul(fp12_cyc_sqr(m), m))
-        put6(g, "ACC", r)
+    def p_glue5(g, k):            # d = c^(z^2) * frob2(c) * conj(c), kept in B
+        c = get6(g, "C")
+        put6(g, "B", fp12_mul(fp12_mul(fp12_conj(get6(g, "ACC")), fp12_frob2(c, k)), fp12_conj(c)))
+    @prog
+    def p_glue6(g, k):            # result = d * m^3  (two short programs instead of one: the slot working set stays under 128)
+        m = get6(g, "M")
+        put6(g, "ACC", fp12_mul(get6(g, "B"), fp12_mul(fp12_cyc_sqr(m), m)))
     return progs
 
 # ------------------------------------------------------------------ scheduling + slot allocation
@@ -427,12 +429,13 @@ def compile_graph(g):
     slot = {}
     for n in need:
         if nodes[n][0] in ("in", "const"): slot[n] = SLOT[nodes[n][1]]
-    free = list(range(len(REGS), NSLOTS)); release = {}   # step -> slots that become free AFTER that step
+    import heapq
+    free = list(range(len(REGS), NSLOTS)); heapq.heapify(free); release = {}   # step -> slots that become free AFTER that step
     for si, (_, ch) in enumerate(steps):
-        for s in release.pop(si - 1, []): free.append(s)
+        for s in release.pop(si - 1, []): heapq.heappush(free, s)
         for n in ch:
             if not free: raise RuntimeError(f"{g.name}: out of slots")
-            slot[n] = free.pop(0)
+            slot[n] = heapq.heappop(free)                   # lowest free slot: the working set stays compact
             release.setdefault(lastuse[n], []).append(slot[n])
     prog = Program(g.name)
     for cls, ch in steps:
@@ -539,7 +542,7 @@ def final_exp_vm(progs, s):
     expz(); run_program(progs["GLUE2"], s)
     expz(); run_program(progs["GLUE3"], s)
     expz(); run_program(progs["GLUE4"], s)
-    expz(); run_program(progs["GLUE5"], s)
+    expz(); run_program(progs["GLUE5"], s); run_program(progs["GLUE6"], s)
 
 # ------------------------------------------------------------------ emitter
 # Instruction = 12 x u32 per (step, pair):
@@ -569,7 +572,7 @@ def enc_lin(dst, terms):
 def enc_mul(dst, a, b): return [dst | (a << 8) | (b << 16)] + [0] * (INS_WORDS - 1)
 NOP = [0xff] + [0] * (INS_WORDS - 1)          # dst 0xff = no operation
 PROGRAM_ORDER = ["ML_INIT", "ML_DBL", "ML_DBL2", "ML_ADD", "FE_INV_A", "FE_INV_B", "CYCSQR", "CYCSQR2", "CYCSQR4", "CYCSQR8", "CYCSQR16", "MULX",
-                 "GLUE1", "GLUE2", "GLUE3", "GLUE4", "GLUE5", "ML1_INIT", "ML1_DBL", "ML1_ADD", "A_ONE", "AMULF", "FMULA"]
+                 "GLUE1", "GLUE2", "GLUE3", "GLUE4", "GLUE5", "GLUE6", "ML1_INIT", "ML1_DBL", "ML1_ADD", "A_ONE", "AMULF", "FMULA"]
 
 def emit(progs, path):
     order = PROGRAM_ORDER
