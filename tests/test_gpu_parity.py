@@ -525,7 +525,13 @@ def test_config4_ten_thousand_triples_one_percent_invalid(gbls, oracle):
         info = gbls.LastBatchInfo()
     finally: gbls.SetParam("rlc_min", old)
     assert info["mode"] == 1 and info["group_size"] == 4 and info["groups"] == k // 4
-    assert gbls.VerifyBatch(bytes(pk), bytes(sg), bytes(mm), 32) == res and gbls.LastBatchInfo()["cta_threads"] == 32     # default path: warp per item
+    # default thresholds: 10 000 items >= rlc_min (6 144) -> batched groups as well; forcing the exact warp-per-item path must agree
+    assert gbls.VerifyBatch(bytes(pk), bytes(sg), bytes(mm), 32) == res and gbls.LastBatchInfo()["mode"] == (1 if k >= old else 0)
+    old_c = gbls.GetParam("coop_max")
+    try:
+        gbls.SetParam("rlc_min", 1 << 30); gbls.SetParam("coop_max", 1 << 30)
+        assert gbls.VerifyBatch(bytes(pk), bytes(sg), bytes(mm), 32) == res and gbls.LastBatchInfo()["cta_threads"] == 32      # warp per item
+    finally: gbls.SetParam("rlc_min", old); gbls.SetParam("coop_max", old_c)
     ng = k // 4
     check = set(bad) | {g % ng + q * ng for g in bad for q in range(4)} | set(rng.sample(range(k), 300))
     for i in sorted(check):
