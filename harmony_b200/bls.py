@@ -115,6 +115,8 @@ def lib():
         sig("hbls_selftest_split", c.c_int, c.c_uint32)
         sig("hbls_set_batch_mode", None, c.c_int)
         sig("hbls_get_batch_mode", c.c_int)
+        sig("hbls_hash_prefetch", c.c_int, u8p, sz)
+        sig("hbls_hash_cache_stats", c.c_int, c.POINTER(c.c_uint64), c.POINTER(c.c_uint64))
         sig("hbls_stage_timing_enable", None, c.c_int)
         sig("hbls_stage_timing_get", c.c_int, c.POINTER(c.c_float), c.c_int)
         _lib = L
@@ -342,6 +344,17 @@ def SignHashBatch(sks32: bytes, msgs: bytes, msg_len: int):
     rc = _need().hbls_sign_hash_batch(k, _buf(sks32), _buf(msgs), msg_len, out, ok)
     if rc != 0: raise HblsError(f"hbls_sign_hash_batch rc={rc}")
     return out.raw[:96 * k], ok.raw[:k]
+
+def HashPrefetch(msg: bytes):
+    """Enqueue H(msg) into the library's device-resident H(m) cache and return at once (include/hbls.h: e.g. on ANNOUNCE, when the
+    block hash / commit payload the node will sign and later verify becomes known)."""
+    rc = _need().hbls_hash_prefetch(_buf(msg), len(msg))
+    if rc != 0: raise HblsError(f"hbls_hash_prefetch rc={rc}")
+
+def HashCacheStats():
+    h = ctypes.c_uint64(0); m = ctypes.c_uint64(0)
+    _need().hbls_hash_cache_stats(ctypes.byref(h), ctypes.byref(m))
+    return {"hits": h.value, "misses": m.value}
 
 def GetPublicKeyBatch(sks32: bytes) -> bytes:
     k = len(sks32) // 32

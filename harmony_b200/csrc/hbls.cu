@@ -25,6 +25,7 @@ struct Scratch {
     unsigned* h_counts = nullptr;            // pinned: [0] rounds re-verified exactly, [1] groups failed
     cudaEvent_t done = nullptr;
     cudaEvent_t fork = nullptr, join[2] = {}; bool forked = false;      // small batches: decode / hash on two auxiliary streams
+    cudaEvent_t mid = nullptr, join2 = nullptr;                          // H(m) cached: "signature decoded" / "subgroup test done"
 };
 struct Ctx {
     bool ready = false;
@@ -45,6 +46,16 @@ struct Ctx {
     hbls_batch_info info = {}; Scratch* info_sc = nullptr; bool info_valid = false;
     // last error of a call that cannot return one
     int last_err = 0; char last_err_msg[160] = {};
+    // H(m) cache (device-resident, LRU): the messages a node hashes again and again -- the block hash / commit payload it SIGNS
+    // itself (consensus/validator.go: prepare / commit votes) and then VERIFIES in PREPARED / COMMITTED (validator.go:219-236,
+    // engine.go:630-640), the one message of a leader's vote collection (leader.go:127-290).  Keyed by the 48 zero-padded bytes
+    // hash_to_fp reads (A.3: longer inputs are truncated).  Mirrors the reference's own caches on this path (BLSPubKeyCache LRU,
+    // crypto/bls/mask.go:35-55; epochCtx committee cache, engine.go:727-761).
+    struct HmEntry { uint8_t key[48] = {}; uint64_t stamp = 0; bool used = false, has_reader = false; cudaEvent_t filled = nullptr, read_done = nullptr; };
+    static constexpr int HM_N = 64;
+    g2a* hm_slots = nullptr; uint8_t* hm_ok = nullptr; HmEntry hm[HM_N];
+    uint64_t hm_clock = 0, hm_hits = 0, hm_misses = 0;
+    long long hm_cache = 1;                                 // hbls_set_param("hm_cache", 0) turns it off (cold-path measurements)
 };
 Ctx g;
 
@@ -84,12 +95,47 @@ int reserve(cudaStream_t s, size_t bytes, Scratch** out) {
         CK(cudaMallocHost(&sc.h_counts, 64)); sc.h_counts[0] = sc.h_counts[1] = 0;
         CK(cudaEventCreateWithFlags(&sc.done, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&sc.fork, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&sc.join[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&sc.join[1], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&sc.mid, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&sc.join2, cudaEventDisableTiming));
     }
     sc.forked = false;
     *out = &sc;
     return 0;
 }
 inline unsigned blocks_for(size_t n, unsigned tpb) { return (unsigned)((n + tpb - 1) / tpb); }
+
+// ------------------------------------------------------------------ H(m) cache.  Caller holds g.mu.  Entries are filled and read on
+// whatever stream the call runs on; `filled` orders readers after the fill, `read_done` orders a later overwrite after the readers.
+void hm_key(uint8_t key[48], const void* msg, size_t len) { memset(key, 0, 48); if (len) memcpy(key, msg, len > 48 ? 48 : len); }
+bool hm_enabled() { return g.hm_cache != 0 && g.hm_slots != nullptr; }
+// hit: stream st copies the cached point into dst / dst_ok and true is returned
+bool hm_fetch(const uint8_t key[48], g2a* dst, uint8_t* dst_ok, cudaStream_t st) {
+    for (int i = 0; i < Ctx::HM_N; i++) {
+        Ctx::HmEntry& e = g.hm[i];
+        if (!e.used || memcmp(e.key, key, 48) != 0) continue;
+        cudaStreamWaitEvent(st, e.filled, 0);
+        cudaMemcpyAsync(dst, g.hm_slots + i, sizeof(g2a), cudaMemcpyDeviceToDevice, st);
+        cudaMemcpyAsync(dst_ok, g.hm_ok + i, 1, cudaMemcpyDeviceToDevice, st);
+        cudaEventRecord(e.read_done, st); e.has_reader = true;
+        e.stamp = ++g.hm_clock; g.hm_hits++;
+        return true;
+    }
+    g.hm_misses++;
+    return false;
+}
+// after stream st has produced H(key) in src / src_ok: keep a copy in the least recently used slot
+void hm_store(const uint8_t key[48], const g2a* src, const uint8_t* src_ok, cudaStream_t st) {
+    int victim = 0;
+    for (int i = 0; i < Ctx::HM_N; i++) {
+        if (!g.hm[i].used) { victim = i; break; }
+        if (g.hm[i].stamp < g.hm[victim].stamp) victim = i;
+    }
+    Ctx::HmEntry& e = g.hm[victim];
+    if (e.used) { cudaStreamWaitEvent(st, e.filled, 0); if (e.has_reader) cudaStreamWaitEvent(st, e.read_done, 0); }
+    cudaMemcpyAsync(g.hm_slots + victim, src, sizeof(g2a), cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(g.hm_ok + victim, src_ok, 1, cudaMemcpyDeviceToDevice, st);
+    cudaEventRecord(e.filled, st);
+    memcpy(e.key, key, 48); e.used = true; e.has_reader = false; e.stamp = ++g.hm_clock;
+}
 #define LAUNCH(kern, grid, block, strm, ...) do { kern<<<(grid), (block), 0, (strm)>>>(__VA_ARGS__); g.launches++; } while (0)
 #define LAUNCH_SMEM(kern, grid, block, smem, strm, ...) do { kern<<<(grid), (block), (smem), (strm)>>>(__VA_ARGS__); g.launches++; } while (0)
 
@@ -140,11 +186,11 @@ std::vector<uint64_t> rlc_draw_items(size_t k) {
 // ------------------------------------------------------------------ one verification pass over device-resident inputs.
 size_t verify_scratch_bytes(size_t B) {
     return B * (sizeof(g2a) * 2 + sizeof(g1a) * 2 + sizeof(g1) + sizeof(g2) + 16 + 4) + (B / HB_RLC_G + 1) * (sizeof(g2a) + 8) + 40 * 256
-           + (B <= 8192 ? B * (6 * sizeof(fp2) + 1) + 512 : 0);                 // latency path: Miller values of (B, sigma)
+           + (B <= 8192 ? B * (12 * sizeof(fp2) + 3) + 1024 : 0);               // latency path: Miller values of (B, sigma) and (-apk, H(m))
 }
 struct VerifyBufs { g2a* sig; g2a* hm; g1a* pkneg; g1* apk; uint8_t* ok_sig; uint8_t* ok_hm; uint8_t* ok_pk;
                     g1a* pk_scaled; g2* S; uint8_t* bad; g2a* Sg; uint8_t* group_ok; uint32_t* fail_list; unsigned* counts;
-                    fp2* f1; uint8_t* irr1; };
+                    fp2* f1; uint8_t* irr1; fp2* f2; uint8_t* irr2; uint8_t* ok_sub; };
 VerifyBufs carve_verify(Arena& ar, size_t B) {
     VerifyBufs v;
     v.sig = ar.take<g2a>(B); v.hm = ar.take<g2a>(B); v.pkneg = ar.take<g1a>(B); v.apk = ar.take<g1>(B);
@@ -152,8 +198,8 @@ VerifyBufs carve_verify(Arena& ar, size_t B) {
     v.pk_scaled = ar.take<g1a>(B); v.S = ar.take<g2>(B); v.bad = ar.take<uint8_t>(B);
     v.Sg = ar.take<g2a>(B / HB_RLC_G + 1); v.group_ok = ar.take<uint8_t>(B / HB_RLC_G + 1);
     v.fail_list = ar.take<uint32_t>(B); v.counts = ar.take<unsigned>(2);
-    v.f1 = nullptr; v.irr1 = nullptr;
-    if (B <= 8192) { v.f1 = ar.take<fp2>(6 * B); v.irr1 = ar.take<uint8_t>(B); }
+    v.f1 = v.f2 = nullptr; v.irr1 = v.irr2 = v.ok_sub = nullptr;
+    if (B <= 8192) { v.f1 = ar.take<fp2>(6 * B); v.irr1 = ar.take<uint8_t>(B); v.f2 = ar.take<fp2>(6 * B); v.irr2 = ar.take<uint8_t>(B); v.ok_sub = ar.take<uint8_t>(B); }
     return v;
 }
 // Small batches (latency path): the inputs are on the device from here on -- signature decode and hash-to-G2 may start on the
@@ -168,8 +214,10 @@ static bool rlc_applies(size_t B) { return g.batch_mode == 1 && (long long)B >= 
 static bool latency_path(size_t B) { return !rlc_applies(B) && (long long)B <= g.coop_max; }
 #define STAGE_EV(i, sc, strm) do { if (g.stage_timing && (sc)->ev_ok) cudaEventRecord((sc)->ev[i], (strm)); } while (0)
 // v.apk holds the Jacobian (aggregate) public key of every round; ok_pk (nullable) = per-round "key decoded" flags of the triple form
+// h_msg (nullable): host copy of THE message when the call has a single one (one round, or a same-message batch) -- the key of the
+// H(m) cache
 void launch_verify_tail(size_t B, const VerifyBufs& v, Scratch* sc, const uint8_t* d_sig96, const uint8_t* d_msgs, uint32_t msg_len,
-                        const uint8_t* ok_pk, uint8_t* d_results, cudaStream_t s, bool same_msg) {
+                        const uint8_t* ok_pk, uint8_t* d_results, cudaStream_t s, bool same_msg, const uint8_t* h_msg = nullptr) {
     STAGE_EV(1, sc, s);
     const bool rlc = rlc_applies(B);
     // the batched check consumes the Jacobian sums directly; -apk in affine form is then only needed for the rounds of failed groups
@@ -186,19 +234,42 @@ void launch_verify_tail(size_t B, const VerifyBufs& v, Scratch* sc, const uint8_
     const size_t coop_cap = (size_t)g.sm_count * (size_t)(g.coop_wpsm > 0 ? g.coop_wpsm : 1);      // resident warps (one round each)
     const unsigned coop_grid = (unsigned)(B < coop_cap ? B : coop_cap);
     const bool split_ml = forked && v.f1 != nullptr;       // Miller value of (B, sigma) on the decode stream, beside hash-to-G2
-    if (pairs) LAUNCH(k_g2_decode_pair, blocks_for(2 * B, 32), 32, sd, B, d_sig96, v.sig, v.ok_sig, 1);
+    // one message (one round, or a same-message batch): H(m) once -- from the cache when this node has hashed it before (it signed
+    // it, verified it, or prefetched it)
+    const bool one_msg = (same_msg && B > 1) || (B == 1 && h_msg);
+    const bool use_cache = one_msg && h_msg != nullptr && hm_enabled();
+    uint8_t key[48]; bool hit = false;
+    if (use_cache) { hm_key(key, h_msg, msg_len); hit = hm_fetch(key, v.hm, v.ok_hm, sh); }
+    // H(m) known up front: the two Miller values do not depend on each other -- (-apk, H(m)) starts right after the key aggregation
+    // on the caller's stream, (B, sigma) after the decode on the decode stream with the signature's subgroup test beside it
+    const bool warm = hit && split_ml;
+    if (pairs) LAUNCH(k_g2_decode_pair, blocks_for(2 * B, 32), 32, sd, B, d_sig96, v.sig, v.ok_sig, warm ? 0 : 1);
     else LAUNCH(k_g2_decode, heavy_blocks(B), TPB, s, B, d_sig96, v.sig, v.ok_sig, 1);
-    if (split_ml) LAUNCH(k_miller1_coop, coop_grid, 32, sd, B, v.sig, v.ok_sig, v.f1, v.irr1);
+    if (warm) {
+        cudaEventRecord(sc->mid, sd);
+        LAUNCH(k_miller_pq_coop, coop_grid, 32, sd, B, (const g1a*)nullptr, v.sig, v.ok_sig, v.f1, v.irr1);
+    } else if (split_ml) LAUNCH(k_miller1_coop, coop_grid, 32, sd, B, v.sig, v.ok_sig, v.f1, v.irr1);
     STAGE_EV(3, sc, s);
-    if (same_msg && B > 1) {
-        if (pairs) LAUNCH(k_hash_to_g2_pair, 1, 32, sh, (size_t)1, d_msgs, msg_len, v.hm, v.ok_hm);
-        else LAUNCH(k_hash_to_g2, 1, TPB, s, (size_t)1, d_msgs, msg_len, v.hm, v.ok_hm);
-        LAUNCH(k_broadcast_hm, blocks_for(B, 256), 256, sh, B, v.hm, v.ok_hm);
+    if (one_msg) {
+        if (!hit) {
+            if (pairs) LAUNCH(k_hash_to_g2_pair, 1, 32, sh, (size_t)1, d_msgs, msg_len, v.hm, v.ok_hm);
+            else LAUNCH(k_hash_to_g2, 1, TPB, sh, (size_t)1, d_msgs, msg_len, v.hm, v.ok_hm);
+            if (use_cache) hm_store(key, v.hm, v.ok_hm, sh);
+        }
+        if (B > 1) LAUNCH(k_broadcast_hm, blocks_for(B, 256), 256, sh, B, v.hm, v.ok_hm);
     } else if (pairs)
         LAUNCH(k_hash_to_g2_pair, blocks_for(2 * B, 32), 32, sh, B, d_msgs, msg_len, v.hm, v.ok_hm);
     else
         LAUNCH(k_hash_to_g2, heavy_blocks(B), TPB, s, B, d_msgs, msg_len, v.hm, v.ok_hm);
-    if (forked) {
+    if (warm) {
+        cudaEventRecord(sc->join[1], sh); cudaStreamWaitEvent(s, sc->join[1], 0);
+        LAUNCH(k_miller_pq_coop, coop_grid, 32, s, B, (const g1a*)v.pkneg, v.hm, (const uint8_t*)v.ok_hm, v.f2, v.irr2);
+        cudaStreamWaitEvent(sh, sc->mid, 0);
+        LAUNCH(k_g2_subgroup_pair, blocks_for(2 * B, 32), 32, sh, B, v.sig, v.ok_sig, v.ok_sub);
+        cudaEventRecord(sc->join2, sh); cudaEventRecord(sc->join[0], sd);
+        cudaStreamWaitEvent(s, sc->join[0], 0); cudaStreamWaitEvent(s, sc->join2, 0);
+        cudaMemcpyAsync(v.ok_sig, v.ok_sub, B, cudaMemcpyDeviceToDevice, s);          // decode flag := decoded AND in the subgroup
+    } else if (forked) {
         cudaEventRecord(sc->join[0], sd); cudaEventRecord(sc->join[1], sh);
         cudaStreamWaitEvent(s, sc->join[0], 0); cudaStreamWaitEvent(s, sc->join[1], 0);
     }
@@ -247,7 +318,9 @@ void launch_verify_tail(size_t B, const VerifyBufs& v, Scratch* sc, const uint8_
         STAGE_EV(5, sc, s);
         const bool full = 2 * B >= (size_t)g.sm_count * HB_TPB_SPLIT;
         const bool coop = (long long)B <= g.coop_max;        // latency form: one warp per round (vm.cuh), up to 14 resident rounds per SM (14.4 KB of slots, 138 registers)
-        if (coop && split_ml)
+        if (coop && warm)
+            LAUNCH(k_fe2_coop, coop_grid, 32, s, B, v.f1, v.irr1, v.f2, v.irr2, v.ok_sig, v.ok_hm, ok_pk, (const uint8_t*)nullptr, d_results);
+        else if (coop && split_ml)
             LAUNCH(k_pairing_coop2, coop_grid, 32, s, B, v.f1, v.irr1, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
         else if (coop)
             LAUNCH(k_pairing_coop, coop_grid, 32, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
@@ -404,7 +477,7 @@ bool all_messages_equal(const uint8_t* msgs, size_t n, size_t msg_len) {
 // rounds against one committee, everything device-resident
 int agg_verify_device_locked(const hbls_committee* c, size_t B, const uint8_t* d_bitmaps, size_t blen, const uint8_t* d_sigs,
                              const uint8_t* d_msgs, size_t msg_len, uint8_t* d_results, cudaStream_t s, Scratch* sc, Arena& ar, bool same_msg,
-                             VerifyBufs* v_out = nullptr) {
+                             VerifyBufs* v_out = nullptr, const uint8_t* h_msg = nullptr) {
     VerifyBufs v = carve_verify(ar, B);
     fork_point(B, sc, s);
     STAGE_EV(0, sc, s);
@@ -412,7 +485,7 @@ int agg_verify_device_locked(const hbls_committee* c, size_t B, const uint8_t* d
         LAUNCH(k_mask_aggregate_serial, light_blocks(B), TPB, s, B, c->n, c->table, c->total, d_bitmaps, blen, v.apk);
     else
         LAUNCH(k_mask_aggregate, blocks_for(B * 32, 128), 128, s, B, c->n, c->table, d_bitmaps, blen, v.apk);
-    launch_verify_tail(B, v, sc, d_sigs, d_msgs, (uint32_t)msg_len, nullptr, d_results, s, same_msg);
+    launch_verify_tail(B, v, sc, d_sigs, d_msgs, (uint32_t)msg_len, nullptr, d_results, s, same_msg, h_msg);
     if (v_out) *v_out = v;
     return 0;
 }
@@ -457,6 +530,11 @@ int hbls_init_device(int device) {
     cudaFuncSetAttribute(k_rlc_scale, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_mask_aggregate_serial, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_mask_aggregate, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    CK(cudaMalloc(&g.hm_slots, Ctx::HM_N * sizeof(g2a))); CK(cudaMalloc(&g.hm_ok, Ctx::HM_N));
+    for (int i = 0; i < Ctx::HM_N; i++) {
+        CK(cudaEventCreateWithFlags(&g.hm[i].filled, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&g.hm[i].read_done, cudaEventDisableTiming));
+    }
+    g.hm_cache = envll("HBLS_HM_CACHE", 1);
     g.ready = true;
     return 0;
 }
@@ -480,6 +558,7 @@ static long long* param_slot(const char* name) {
     if (!strcmp(name, "coop_max")) return &g.coop_max;
     if (!strcmp(name, "overlap")) return &g.overlap;
     if (!strcmp(name, "coop_wpsm")) return &g.coop_wpsm;
+    if (!strcmp(name, "hm_cache")) return &g.hm_cache;
     return nullptr;
 }
 int hbls_set_param(const char* name, long long value) {
@@ -542,6 +621,32 @@ size_t blsSignatureDeserialize(blsSignature* sig, const void* buf, size_t bufSiz
 int hbls_map_to_g2(const void* msg, size_t msg_len, uint8_t out96[96]) {
     if (msg_len > 48) msg_len = 48;      // only the first 48 bytes matter
     int rc = -1; if (int e = single_op(OP_MAP_SER, msg, msg_len, nullptr, 0, out96, 96, &rc, (uint32_t)msg_len)) return e; return rc; }
+// asynchronous: enqueues H(msg) on the hash stream and returns; a later SignHash / VerifyHash / aggregate-verify of that message
+// finds the point in the cache (stream-ordered after the fill).  0 ok (also when already cached or the cache is off).
+int hbls_hash_prefetch(const void* msg, size_t msg_len) {
+    if (int e = ensure_init()) return e;
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (!hm_enabled()) return 0;
+    if (msg_len > 48) msg_len = 48;
+    uint8_t key[48]; hm_key(key, msg, msg_len);
+    for (int i = 0; i < Ctx::HM_N; i++) if (g.hm[i].used && memcmp(g.hm[i].key, key, 48) == 0) { g.hm[i].stamp = ++g.hm_clock; return 0; }
+    cudaStream_t st = g.aux[1];
+    Scratch* sc; if (int e = reserve(st, 4096, &sc)) return e;
+    Arena ar{sc->base, 0, sc->cap};
+    uint8_t* dmsg = ar.take<uint8_t>(64); g2a* dhm = ar.take<g2a>(1); uint8_t* dok = ar.take<uint8_t>(1);
+    // the 48 key bytes ARE the bytes hash_to_fp reads (pageable source: the runtime stages it before cudaMemcpyAsync returns)
+    CK(cudaMemcpyAsync(dmsg, key, 48, cudaMemcpyHostToDevice, st));
+    LAUNCH(k_hash_to_g2_pair, 1, 32, st, (size_t)1, dmsg, (uint32_t)48, dhm, dok);
+    hm_store(key, dhm, dok, st);
+    CK(cudaGetLastError());
+    return 0;
+}
+int hbls_hash_cache_stats(uint64_t* hits, uint64_t* misses) {
+    std::lock_guard<std::mutex> lk(g.mu);
+    if (hits) *hits = g.hm_hits;
+    if (misses) *misses = g.hm_misses;
+    return 0;
+}
 int hbls_get_address(const blsPublicKey* pub, uint8_t out20[20]) {
     uint8_t ser[48], dg[32];
     if (blsPublicKeySerialize(ser, 48, pub) != 48) return HBLS_ERR_CUDA;
@@ -570,9 +675,18 @@ int blsSignHash(blsSignature* sig, const blsSecretKey* sec, const void* h, size_
     Scratch* sc; if (int e = reserve(g.stream, 4096, &sc)) return e;
     Arena ar{sc->base, 0, sc->cap};
     uint8_t* dsk = ar.take<uint8_t>(32); uint8_t* dmsg = ar.take<uint8_t>(64); g2* dout = ar.take<g2>(1); uint8_t* dok = ar.take<uint8_t>(1);
+    g2a* dhm = ar.take<g2a>(1); uint8_t* dhm_ok = ar.take<uint8_t>(1);
     CK(cudaMemcpyAsync(dsk, sec->d, 32, cudaMemcpyHostToDevice, g.stream));
     if (size) CK(cudaMemcpyAsync(dmsg, h, size, cudaMemcpyHostToDevice, g.stream));
-    LAUNCH(k_sign_hash, 1, 32, g.stream, (size_t)1, dsk, dmsg, (uint32_t)size, dout, dok);
+    // H(m) on a lane pair (kept in the H(m) cache: the validator verifies the aggregate over the very message it signs here), then
+    // the 255-bit ladder sk * H on the split carrier
+    uint8_t key[48]; bool hit = false;
+    if (hm_enabled()) { hm_key(key, h, size); hit = hm_fetch(key, dhm, dhm_ok, g.stream); }
+    if (!hit) {
+        LAUNCH(k_hash_to_g2_pair, 1, 32, g.stream, (size_t)1, dmsg, (uint32_t)size, dhm, dhm_ok);
+        if (hm_enabled()) hm_store(key, dhm, dhm_ok, g.stream);
+    }
+    LAUNCH(k_sign_hm_pair, 1, 32, g.stream, (size_t)1, dsk, dhm, dhm_ok, (size_t)0, dout, dok);
     uint8_t ok = 0;
     CK(cudaMemcpyAsync(sig, dout, 288, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaMemcpyAsync(&ok, dok, 1, cudaMemcpyDeviceToHost, g.stream));
@@ -599,7 +713,14 @@ static int verify_hash_locked(const blsSignature* sig, const blsPublicKey* pub, 
         CK(cudaMemcpyAsync(dsig, sig, 288, cudaMemcpyHostToDevice, g.stream));
         LAUNCH(k_g2_normalize, 1, 32, g.stream, (size_t)1, dsig, v.sig);
     }
-    LAUNCH(k_hash_to_g2_pair, 1, 32, g.stream, (size_t)1, dmsg, (uint32_t)size, v.hm, v.ok_hm);
+    {   // H(m): cached when this node has hashed the message before (its own SignHash, a prefetch, an earlier check)
+        uint8_t key[48]; bool hit = false;
+        if (hm_enabled()) { hm_key(key, h, size); hit = hm_fetch(key, v.hm, v.ok_hm, g.stream); }
+        if (!hit) {
+            LAUNCH(k_hash_to_g2_pair, 1, 32, g.stream, (size_t)1, dmsg, (uint32_t)size, v.hm, v.ok_hm);
+            if (hm_enabled()) hm_store(key, v.hm, v.ok_hm, g.stream);
+        }
+    }
     if (g.coop_max >= 1) LAUNCH(k_pairing_coop, 1, 32, g.stream, (size_t)1, v.sig, v.pkneg, v.hm, (const uint8_t*)v.ok_hm, ok_sig, (const uint8_t*)nullptr, dres);
     else LAUNCH(k_pairing_verify_split, 1, 64, g.stream, (size_t)1, v.sig, v.pkneg, v.hm, (const uint8_t*)v.ok_hm, ok_sig, (const uint8_t*)nullptr, dres, (const int*)nullptr);
     LAUNCH(k_pairing_fixup, 1, 32, g.stream, (size_t)1, v.sig, v.pkneg, v.hm, (const uint8_t*)v.ok_hm, ok_sig, (const uint8_t*)nullptr, dres, (const int*)nullptr);
@@ -713,7 +834,8 @@ static int agg_verify_host_locked(const hbls_committee* c, size_t B, const uint8
     CK(cudaMemcpyAsync(dsig, sigs96, B * 96, cudaMemcpyHostToDevice, g.stream));
     if (msg_len) CK(cudaMemcpyAsync(dmsg, msgs, B * msg_len, cudaMemcpyHostToDevice, g.stream));
     VerifyBufs v;
-    agg_verify_device_locked(c, B, dbm, blen, dsig, dmsg, msg_len, dres, g.stream, sc, ar, all_messages_equal(msgs, B, msg_len), &v);
+    const bool same = all_messages_equal(msgs, B, msg_len);
+    agg_verify_device_locked(c, B, dbm, blen, dsig, dmsg, msg_len, dres, g.stream, sc, ar, same, &v, (same || B == 1) ? msgs : nullptr);
     CK(cudaMemcpyAsync(results, dres, B, cudaMemcpyDeviceToHost, g.stream));
     if (flags_out) {
         LAUNCH(k_pack_flags, blocks_for(B, 256), 256, g.stream, B, v.ok_sig, v.ok_hm, (const uint8_t*)nullptr, dflags);

@@ -483,6 +483,70 @@ __global__ void __launch_bounds__(32) k_miller1_coop(size_t B, const g2a* sig, c
         __syncwarp();
     }
 }
+// ---- latency form with H(m) already known (the library's H(m) cache, hbls.cu): BOTH Miller values are independent of each other --
+// (B, sigma) waits for the signature decode, (-apk, H(m)) only for the key aggregation -- so they run on two streams and a third
+// kernel multiplies them and does the final exponentiation.  P = nullptr: the generator.  irr[j] = 1: an operand is the identity /
+// did not decode (the round is then decided by k_pairing_fixup, like in the other forms).
+__global__ void __launch_bounds__(32) k_miller_pq_coop(size_t B, const g1a* P, const g2a* Q, const uint8_t* ok_q, fp2* f, uint8_t* irr) {
+    __shared__ uint32_t slots[VM_SMEM_WORDS];
+    const int lane = threadIdx.x & 31;
+    vm_load_consts(slots);
+    for (size_t j = blockIdx.x; j < B; j += gridDim.x) {
+        bool zero = true;
+        if (lane < 4) {
+            fp2 v; fp2_zero(v);
+            if (lane < 2) { if (P) v.a = lane == 0 ? P[j].x : P[j].y; else fp_set(v.a, lane == 0 ? K_G1_X : K_G1_Y); }
+            else v = lane == 2 ? Q[j].x : Q[j].y;
+            vm_set_fp2(slots, VM_R_P2X + lane, v);
+            zero = fp_is_zero(v.a) & fp_is_zero(v.b);
+        }
+        const unsigned zmask = __ballot_sync(0xffffffffu, zero);
+        const bool skip = (ok_q && !ok_q[j]) || (zmask & 0x3) == 0x3 || (zmask & 0xc) == 0xc;
+        if (lane == 0) irr[j] = skip ? 1 : 0;
+        if (skip) { __syncwarp(); continue; }
+        vm_run(VM_P_ML1_INIT, slots);
+        for (int i = 62; i >= 0; i--) {
+            vm_run(VM_P_ML1_DBL, slots);
+            if ((K_Z_ABS >> i) & 1) vm_run(VM_P_ML1_ADD, slots);
+        }
+        if (lane < 12) vm_ld(reinterpret_cast<fp*>(&f[6 * j + (lane >> 1)])[lane & 1].l, slots, VM_R_F0 + (lane >> 1), lane & 1);
+        __syncwarp();
+    }
+}
+// verdict = FE(f1 f2) == 1; ok_sub (nullable): the signature's subgroup test, run beside its Miller loop
+__global__ void __launch_bounds__(32) k_fe2_coop(size_t B, const fp2* f1, const uint8_t* irr1, const fp2* f2, const uint8_t* irr2,
+                             const uint8_t* ok_a, const uint8_t* ok_b, const uint8_t* ok_c, const uint8_t* ok_sub, uint8_t* results) {
+    __shared__ uint32_t slots[VM_SMEM_WORDS];
+    const int lane = threadIdx.x & 31;
+    vm_load_consts(slots);
+    for (size_t j = blockIdx.x; j < B; j += gridDim.x) {
+        const bool good = (!ok_a || ok_a[j]) && (!ok_b || ok_b[j]) && (!ok_c || ok_c[j]) && (!ok_sub || ok_sub[j]);
+        const bool irregular = irr1[j] != 0 || irr2[j] != 0;
+        bool one = false;
+        if (!irregular) {
+            if (lane < 12) {
+                vm_st(slots, VM_R_A0 + (lane >> 1), lane & 1, reinterpret_cast<const fp*>(&f1[6 * j + (lane >> 1)])[lane & 1].l);
+                vm_st(slots, VM_R_F0 + (lane >> 1), lane & 1, reinterpret_cast<const fp*>(&f2[6 * j + (lane >> 1)])[lane & 1].l);
+            }
+            __syncwarp();
+            vm_run(VM_P_FMULA, slots);
+            one = vm_final_exp_is_one(slots);
+        }
+        if (lane == 0) results[j] = irregular ? 0xFF : ((good && one) ? 1 : 0);
+        __syncwarp();
+    }
+}
+// subgroup test of already-decoded affine signatures, one item per lane pair (the second half of k_g2_decode_pair)
+__global__ void k_g2_subgroup_pair(size_t n, const g2a* pts, const uint8_t* ok_in, uint8_t* ok_out) {
+    const size_t i = HB_TID >> 1; if (i >= n) return;
+    const g2a a = pts[i];
+    bool good = ok_in[i] != 0;
+    if (good && !aff_is_inf(a)) {
+        jac<fp2h> q; fp2h_pack(q.x, a.x); fp2h_pack(q.y, a.y); fp2_one(q.z);
+        good = g2_in_subgroup(q);
+    }
+    if ((threadIdx.x & 1) == 0) ok_out[i] = good ? 1 : 0;
+}
 __global__ void __launch_bounds__(32) k_pairing_coop2(size_t B, const fp2* f1, const uint8_t* irr1, const g1a* pk_neg, const g2a* hm,
                                   const uint8_t* ok_a, const uint8_t* ok_b, const uint8_t* ok_c, uint8_t* results) {
     __shared__ uint32_t slots[VM_SMEM_WORDS];
@@ -732,6 +796,19 @@ __global__ void k_sign_hash(size_t n, const uint8_t* sk32, const uint8_t* msgs, 
     g2 h, r; bool good = map_to_g2(h, msgs + (size_t)msg_len * i, msg_len);
     if (good) pt_mul(r, h, k, 8); else pt_set_inf(r);
     out[i] = r; ok[i] = good ? 1 : 0;
+}
+// sigma = sk * H for an already-mapped H(m) (the library's H(m) cache, hbls.cu): one item per LANE PAIR, the 255-bit ladder on the
+// split carrier.  hm_stride = 0: every item signs the same point.  Output Jacobian (the layout of blsSignature).
+__global__ void k_sign_hm_pair(size_t n, const uint8_t* sk32, const g2a* hm, const uint8_t* ok_hm, size_t hm_stride, g2* out, uint8_t* ok) {
+    const size_t i = HB_TID >> 1; if (i >= n) return;
+    uint32_t k[8]; load_words(k, sk32 + 32 * i, 8);
+    const g2a h = hm[i * hm_stride];
+    const bool good = ok_hm[i * hm_stride] != 0 && !aff_is_inf(h);
+    jac<fp2h> H, R; fp2h_pack(H.x, h.x); fp2h_pack(H.y, h.y); fp2_one(H.z);
+    pt_mul(R, H, k, 8);
+    g2 r; fp2h_unpack(r.x, R.x); fp2h_unpack(r.y, R.y); fp2h_unpack(r.z, R.z);
+    if (!good) pt_set_inf(r);
+    if ((threadIdx.x & 1) == 0) { out[i] = r; ok[i] = good ? 1 : 0; }
 }
 
 // ---- single-element ops behind the herumi-shaped C ABI (one thread; latency is launch-bound)

@@ -719,3 +719,52 @@ def test_split_batch_partial_records_fold(gbls, oracle):
     res, settled = shard.verify_triples_split(pks, bytes(s3), bytes(m2), 32)
     assert settled is False and [i for i in range(k) if res[i] == 0] == [10, 11, 70]
     assert res == bytes(1 if oracle.verify_hash(bytes(s3[96 * i:96 * i + 96]), pks[48 * i:48 * i + 48], bytes(m2[32 * i:32 * i + 32])) else 0 for i in range(k))
+
+def test_hash_cache_sign_then_verify(gbls, oracle):
+    """H(m) cache (include/hbls.h): the validator signs a block hash / commit payload and later verifies the aggregate over the same
+    bytes (consensus/validator.go:219-236).  Cached and uncached paths give the oracle's bytes / booleans; a hit never leaks to
+    another message; > 48-byte inputs share the entry of their 48-byte prefix (A.3 truncation); eviction keeps results exact."""
+    n = 16
+    sks = [wl.seeded_sk("hmc", i) for i in range(n)]
+    pks_blob = gbls.GetPublicKeyBatch(b"".join(wl.sk_bytes(k) for k in sks))
+    pks = [pks_blob[48 * i:48 * i + 48] for i in range(n)]
+    com = gbls.Committee(pks); och = oracle.committee(pks)
+    bm = wl.bitmap_with_k("hmc", 0, n, 11)
+    agg = wl.sk_bytes(wl.round_signer_sum(sks, bm))
+    m1 = wl.commit_payload("hmc", 1); m2 = wl.commit_payload("hmc", 2)
+    old = gbls.GetParam("hm_cache")
+    try:
+        gbls.SetParam("hm_cache", 0)
+        sk = gbls.SecretKey(); sk.Deserialize(agg)
+        cold_sig = sk.SignHash(m1).Serialize()
+        assert cold_sig == oracle.sign_hash(agg, m1)
+        cold = com.AggregateVerify(bm, cold_sig, m1)
+        gbls.SetParam("hm_cache", 1)
+        st0 = gbls.HashCacheStats()
+        warm_sig = sk.SignHash(m1).Serialize()                       # miss: fills the entry
+        assert warm_sig == cold_sig
+        assert com.AggregateVerify(bm, warm_sig, m1) == cold == True      # hit
+        assert com.AggregateVerify(bm, warm_sig, m2) is False             # other message: miss, rejected
+        assert com.AggregateVerify(bm, warm_sig, m2) is False             # ... and rejected again from the cache
+        st1 = gbls.HashCacheStats()
+        assert st1["hits"] - st0["hits"] == 2 and st1["misses"] - st0["misses"] == 2
+        # truncation: 60-byte input = its first 48 bytes
+        long_msg = m1 + b"\x55" * 12
+        assert sk.SignHash(long_msg).Serialize() == cold_sig
+        assert gbls.HashCacheStats()["hits"] - st1["hits"] == 1
+        # prefetch, then 70 more distinct messages evict it; every check still exact
+        gbls.HashPrefetch(m2)
+        sig2 = sk.SignHash(m2).Serialize()
+        assert sig2 == oracle.sign_hash(agg, m2)
+        for t in range(70): gbls.HashPrefetch(wl.commit_payload("hmc/evict", t))
+        assert com.AggregateVerify(bm, sig2, m2) is True and com.AggregateVerify(bm, sig2, m1) is False
+        assert oracle.committee_aggregate_verify(och, bm, sig2, m2) == 1
+        # same-message vote batch (leader): H(m) from the cache, booleans unchanged
+        votes, ok = gbls.SignHashBatch(b"".join(wl.sk_bytes(k) for k in sks), m1 * n, 48)
+        sb = b"".join(bytes([1 << (i & 7) if j == i >> 3 else 0 for j in range(2)]) for i in range(n))
+        bad = bytearray(votes); bad[96 * 5 + 3] ^= 1
+        r1 = com.AggregateVerifyBatch(sb, bytes(bad), m1 * n, 48)
+        gbls.SetParam("hm_cache", 0)
+        assert com.AggregateVerifyBatch(sb, bytes(bad), m1 * n, 48) == r1 and sum(r1) == n - 1 and r1[5] == 0
+    finally:
+        gbls.SetParam("hm_cache", old)
