@@ -68,7 +68,75 @@ __device__ __constant__ const uint32_t VM_KP[5][13] = {
     {0xfffd5558u, 0xcff7ffffu, 0x8a9ffffdu, 0xf55ffff5u, 0xb587b120u, 0x39869507u, 0x9c2895fbu, 0x23ba5c27u, 0x1a5d66bbu, 0x58dd3db2u, 0xcbff34d2u, 0xd0088f51u, 0x00000000u},
     {0xfffaaab0u, 0x9fefffffu, 0x153ffffbu, 0xeabfffebu, 0x6b0f6241u, 0x730d2a0fu, 0x38512bf6u, 0x4774b84fu, 0x34bacd76u, 0xb1ba7b64u, 0x97fe69a4u, 0xa0111ea3u, 0x00000001u}};
 // dst = sum_k M_k src_k, stored per lane role as <= 8 atoms (slot, half, sign, multiplier 1..4): every lane of the step runs the same
-// `natoms` iterations (its unused atoms point at the ZERO slot), accumulating plain 13-limb integers (< 32 p), then ONE reduction.
+// `natoms` iterations (its unused atoms point at the ZERO slot).
+//
+// Latency form (one warp is alone on its scheduler, so DEPENDENT instruction chains are what costs): the atoms are accumulated
+// WITHOUT carry chains -- each 32-bit limb of a source is split into its 16-bit halves and multiplied into 24 independent 32-bit
+// accumulators (IMAD by the signed multiplier) -- and only then folded into 13 limbs with one carry chain.  The accumulators start
+// at INIT = 2^22 + (16-bit digits of X), X = 631 p - 2^22 * sum_k 2^(16 k): 2^22 absorbs the negative atoms (|sum| <= 8 * 4 * 65535
+// < 2^21 per accumulator) and the whole offset is exactly 631 p, so the folded value is (sum + 631 p) in (599 p, 663 p).  It is
+// reduced by one quotient estimate from the top 42 bits (floor(top / (p_11 + 1)) never overshoots and leaves < 2 p) and two trial
+// subtractions.  Measured (tools/lat_probe.cu, profiles/r2_lat_probe.txt): 4-atom step 1 759 -> 1 332 cycles, 8-atom step 2 871 -> 1 750; a Miller doubling
+// iteration (14 steps) 42.5k -> 35.6k cycles.
+#ifndef HB_VM_LIN_V1
+#define HB_VM_LIN_V1 0
+#endif
+#if !HB_VM_LIN_V1
+HB_NOINLINE void vm_lin(uint32_t* slots, int dst, const uint4 row, int natoms, int im) {
+    uint32_t lo[12] = {0x40ab7du, 0x40ffbfu, 0x40ff13u, 0x40fc87u, 0x40b2c7u, 0x402a80u, 0x403587u, 0x402474u, 0x4006a8u, 0x4061ffu, 0x40660fu, 0x402813u};
+    uint32_t hi[12] = {0x40feedu, 0x407348u, 0x4015cbu, 0x4099b3u, 0x400deeu, 0x405917u, 0x403cc1u, 0x40a1cbu, 0x40df47u, 0x4020eau, 0x40ba01u, 0x401863u};
+    const uint32_t rw[4] = {row.x, row.y, row.z, row.w};
+#pragma unroll 2
+    for (int a = 0; a < natoms; a++) {
+        const uint32_t at = (rw[a >> 1] >> (16 * (a & 1))) & 0xffffu;
+        const int s = at & 0xff, half = (at >> 8) & 1;
+        const uint32_t m = ((at >> 10) & 3u) + 1u;
+        const uint32_t sm = ((at >> 9) & 1u) ? 0u - m : m;              // signed multiplier, two's complement (wrap-around arithmetic)
+        uint32_t v[12];
+        vm_ld(v, slots, s, half);
+#pragma unroll
+        for (int j = 0; j < 12; j++) { lo[j] += sm * (v[j] & 0xffffu); hi[j] += sm * (v[j] >> 16); }
+    }
+    // fold: u_j = lo_j + 2^16 hi_j (< 2^40), value = sum_j u_j 2^(32 j)
+    uint32_t low[12], high[12], acc[13];
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+        low[j] = lo[j] + (hi[j] << 16);
+        high[j] = (hi[j] >> 16) + (low[j] < lo[j] ? 1u : 0u);
+    }
+    acc[0] = low[0];
+    add_cc(acc[1], low[1], high[0]);
+#pragma unroll
+    for (int j = 2; j < 12; j++) addc_cc(acc[j], low[j], high[j - 1]);
+    addc(acc[12], high[11], 0u);
+    // quotient estimate from the top 42 bits: q <= floor(value / p), value - q p < 2 p
+    const uint64_t top = ((uint64_t)acc[12] << 32) | acc[11];
+    const uint32_t q = (uint32_t)(top / 0x1a0111ebull);               // p_11 + 1 (constant divisor: multiply-high + shift)
+    uint32_t pl[12], ph[12], qp[13];
+#pragma unroll
+    for (int j = 0; j < 12; j++) { pl[j] = q * p_limb(j); ph[j] = (uint32_t)(((uint64_t)q * p_limb(j)) >> 32); }
+    qp[0] = pl[0];
+    add_cc(qp[1], pl[1], ph[0]);
+#pragma unroll
+    for (int j = 2; j < 12; j++) addc_cc(qp[j], pl[j], ph[j - 1]);
+    addc(qp[12], ph[11], 0u);
+    sub_cc(acc[0], acc[0], qp[0]);
+#pragma unroll
+    for (int j = 1; j < 12; j++) subc_cc(acc[j], acc[j], qp[j]);
+    subc(acc[12], acc[12], qp[12]);
+#pragma unroll
+    for (int k = 0; k < 2; k++) {                                     // < 2 p (+ rounding of the estimate): p, p
+        uint32_t d[13], bw;
+        sub_cc(d[0], acc[0], VM_KP[0][0]);
+#pragma unroll
+        for (int j = 1; j < 13; j++) subc_cc(d[j], acc[j], VM_KP[0][j]);
+        subc(bw, 0, 0);                                               // all-ones when acc < p
+#pragma unroll
+        for (int j = 0; j < 13; j++) acc[j] = (acc[j] & bw) | (d[j] & ~bw);
+    }
+    vm_st(slots, dst, im, acc);
+}
+#else
 HB_NOINLINE void vm_lin(uint32_t* slots, int dst, const uint4 row, int natoms, int im) {
     uint32_t acc[13];
 #pragma unroll
@@ -119,6 +187,7 @@ HB_NOINLINE void vm_lin(uint32_t* slots, int dst, const uint4 row, int natoms, i
     }
     vm_st(slots, dst, im, acc);
 }
+#endif
 // run one step program; every lane of the warp must call it (steps end in __syncwarp).  The instruction words of the next step
 // are fetched while the current one executes.
 HB_NOINLINE void vm_run(int prog, uint32_t* slots) {
