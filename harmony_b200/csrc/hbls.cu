@@ -39,7 +39,7 @@ struct Ctx {
     bool stage_timing = false; Scratch* stage_sc = nullptr;
     int batch_mode = 1;                                     // 1: random-linear-combination groups + exact pass over failed groups, 0: exact per round
     // tuning (hbls_set_param)
-    long long rlc_min = 6144, rlc_g = 0, tpsm = 384, tpsm_split = 512, tpsm_light = 1024, coop_max = 6143, overlap = 1, coop_wpsm = 14;
+    long long rlc_min = 6144, rlc_g = 0, tpsm = 384, tpsm_split = 512, tpsm_light = 1024, coop_max = 6143, overlap = 1, coop_wpsm = 14, hash_coop_max = 592;
     // coefficient stream: ChaCha20 keyed from /dev/urandom, block counter = call number
     uint32_t chacha_key[8] = {}; uint64_t rlc_calls = 0;
     // last batch
@@ -151,6 +151,13 @@ unsigned heavy_blocks(size_t n) { return capped_blocks(n, g.tpsm, TPB); }
 unsigned light_blocks(size_t n) { return capped_blocks(n, g.tpsm_light, TPB); }       // small-state kernels: the register count decides
 unsigned split_blocks(size_t nthreads) { return capped_blocks(nthreads, g.tpsm_split, HB_TPB_SPLIT); }
 
+// hash-to-G2 of a small batch (latency path): one WARP per message while that still leaves every warp its own scheduler's worth of
+// an SM (the cofactor clearing runs as VM step programs: 2.7 instead of 3.7 ms for one message), else one message per lane pair
+void launch_hash_small(cudaStream_t st, size_t n, const uint8_t* d_msgs, uint32_t msg_len, g2a* hm, uint8_t* ok_hm) {
+    if ((long long)n <= g.hash_coop_max) LAUNCH(k_hash_to_g2_coop, (unsigned)n, 32, st, n, d_msgs, msg_len, hm, ok_hm);
+    else LAUNCH(k_hash_to_g2_pair, blocks_for(2 * n, 32), 32, st, n, d_msgs, msg_len, hm, ok_hm);
+}
+
 // ------------------------------------------------------------------ coefficient stream (host): ChaCha20 block function, RFC 8439
 void chacha20_block(const uint32_t key[8], uint64_t counter, uint32_t out[16], uint32_t block = 0) {
     uint32_t st[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key[0], key[1], key[2], key[3], key[4], key[5], key[6], key[7],
@@ -252,13 +259,13 @@ void launch_verify_tail(size_t B, const VerifyBufs& v, Scratch* sc, const uint8_
     STAGE_EV(3, sc, s);
     if (one_msg) {
         if (!hit) {
-            if (pairs) LAUNCH(k_hash_to_g2_pair, 1, 32, sh, (size_t)1, d_msgs, msg_len, v.hm, v.ok_hm);
+            if (pairs) launch_hash_small(sh, 1, d_msgs, msg_len, v.hm, v.ok_hm);
             else LAUNCH(k_hash_to_g2, 1, TPB, sh, (size_t)1, d_msgs, msg_len, v.hm, v.ok_hm);
             if (use_cache) hm_store(key, v.hm, v.ok_hm, sh);
         }
         if (B > 1) LAUNCH(k_broadcast_hm, blocks_for(B, 256), 256, sh, B, v.hm, v.ok_hm);
     } else if (pairs)
-        LAUNCH(k_hash_to_g2_pair, blocks_for(2 * B, 32), 32, sh, B, d_msgs, msg_len, v.hm, v.ok_hm);
+        launch_hash_small(sh, B, d_msgs, msg_len, v.hm, v.ok_hm);
     else
         LAUNCH(k_hash_to_g2, heavy_blocks(B), TPB, s, B, d_msgs, msg_len, v.hm, v.ok_hm);
     if (warm) {
@@ -317,7 +324,7 @@ void launch_verify_tail(size_t B, const VerifyBufs& v, Scratch* sc, const uint8_
         // small ones 64-thread CTAs spread over the SMs.
         STAGE_EV(5, sc, s);
         const bool full = 2 * B >= (size_t)g.sm_count * HB_TPB_SPLIT;
-        const bool coop = (long long)B <= g.coop_max;        // latency form: one warp per round (vm.cuh), up to 14 resident rounds per SM (14.4 KB of slots, 138 registers)
+        const bool coop = (long long)B <= g.coop_max;        // latency form: one warp per round (vm.cuh), up to 14 resident rounds per SM (15 KB of slots each)
         if (coop && warm)
             LAUNCH(k_fe2_coop, coop_grid, 32, s, B, v.f1, v.irr1, v.f2, v.irr2, v.ok_sig, v.ok_hm, ok_pk, (const uint8_t*)nullptr, d_results);
         else if (coop && split_ml)
@@ -559,6 +566,7 @@ static long long* param_slot(const char* name) {
     if (!strcmp(name, "overlap")) return &g.overlap;
     if (!strcmp(name, "coop_wpsm")) return &g.coop_wpsm;
     if (!strcmp(name, "hm_cache")) return &g.hm_cache;
+    if (!strcmp(name, "hash_coop_max")) return &g.hash_coop_max;
     return nullptr;
 }
 int hbls_set_param(const char* name, long long value) {
@@ -636,7 +644,7 @@ int hbls_hash_prefetch(const void* msg, size_t msg_len) {
     uint8_t* dmsg = ar.take<uint8_t>(64); g2a* dhm = ar.take<g2a>(1); uint8_t* dok = ar.take<uint8_t>(1);
     // the 48 key bytes ARE the bytes hash_to_fp reads (pageable source: the runtime stages it before cudaMemcpyAsync returns)
     CK(cudaMemcpyAsync(dmsg, key, 48, cudaMemcpyHostToDevice, st));
-    LAUNCH(k_hash_to_g2_pair, 1, 32, st, (size_t)1, dmsg, (uint32_t)48, dhm, dok);
+    launch_hash_small(st, 1, dmsg, 48, dhm, dok);
     hm_store(key, dhm, dok, st);
     CK(cudaGetLastError());
     return 0;
@@ -683,7 +691,7 @@ int blsSignHash(blsSignature* sig, const blsSecretKey* sec, const void* h, size_
     uint8_t key[48]; bool hit = false;
     if (hm_enabled()) { hm_key(key, h, size); hit = hm_fetch(key, dhm, dhm_ok, g.stream); }
     if (!hit) {
-        LAUNCH(k_hash_to_g2_pair, 1, 32, g.stream, (size_t)1, dmsg, (uint32_t)size, dhm, dhm_ok);
+        launch_hash_small(g.stream, 1, dmsg, (uint32_t)size, dhm, dhm_ok);
         if (hm_enabled()) hm_store(key, dhm, dhm_ok, g.stream);
     }
     LAUNCH(k_sign_hm_pair, 1, 32, g.stream, (size_t)1, dsk, dhm, dhm_ok, (size_t)0, dout, dok);
@@ -717,7 +725,7 @@ static int verify_hash_locked(const blsSignature* sig, const blsPublicKey* pub, 
         uint8_t key[48]; bool hit = false;
         if (hm_enabled()) { hm_key(key, h, size); hit = hm_fetch(key, v.hm, v.ok_hm, g.stream); }
         if (!hit) {
-            LAUNCH(k_hash_to_g2_pair, 1, 32, g.stream, (size_t)1, dmsg, (uint32_t)size, v.hm, v.ok_hm);
+            launch_hash_small(g.stream, 1, dmsg, (uint32_t)size, v.hm, v.ok_hm);
             if (hm_enabled()) hm_store(key, v.hm, v.ok_hm, g.stream);
         }
     }
@@ -1079,7 +1087,7 @@ int hbls_rlc_partial(size_t k, const uint8_t* pk48, const uint8_t* sig96, const 
     CK(cudaMemsetAsync(v.counts, 0, 2 * sizeof(unsigned), g.stream));
     LAUNCH(k_g1_decode_jac, heavy_blocks(kk), TPB, g.stream, k, dpk, v.apk, v.ok_pk, 1);
     const bool pairs = (long long)k <= g.coop_max;
-    if (pairs) { LAUNCH(k_g2_decode_pair, blocks_for(2 * kk, 32), 32, g.stream, k, dsig, v.sig, v.ok_sig, 1); LAUNCH(k_hash_to_g2_pair, blocks_for(2 * kk, 32), 32, g.stream, k, dmsg, (uint32_t)msg_len, v.hm, v.ok_hm); }
+    if (pairs) { LAUNCH(k_g2_decode_pair, blocks_for(2 * kk, 32), 32, g.stream, k, dsig, v.sig, v.ok_sig, 1); launch_hash_small(g.stream, k, dmsg, (uint32_t)msg_len, v.hm, v.ok_hm); }
     else { LAUNCH(k_g2_decode, heavy_blocks(kk), TPB, g.stream, k, dsig, v.sig, v.ok_sig, 1); LAUNCH(k_hash_to_g2, heavy_blocks(kk), TPB, g.stream, k, dmsg, (uint32_t)msg_len, v.hm, v.ok_hm); }
     rlc_coeffs none{};
     LAUNCH(k_rlc_scale, heavy_blocks(kk), TPB, g.stream, k, (size_t)1, v.apk, v.sig, v.hm, v.ok_sig, v.ok_hm, (const uint8_t*)v.ok_pk, none, (const uint64_t*)dco, v.pk_scaled, v.S, v.bad);

@@ -265,6 +265,37 @@ __global__ void k_hash_to_g2_pair(size_t n, const uint8_t* msgs, uint32_t msg_le
     }
     if ((threadIdx.x & 1) == 0) { out[i] = res; ok[i] = good ? 1 : 0; }
 }
+// ---- latency form of hash-to-G2 (vm.cuh): ONE WARP per message.  The Shallue-van de Woestijne map (Fp chains: one inversion, two
+// Legendre symbols, the Fp2 square root) runs on every lane alike; the cofactor clearing -- two 63-doubling chains of G2, 52 % of a
+// lane pair's hash time (profiles/r2_lat_probe.txt) -- runs as VM step programs with the 3 independent products of a doubling level
+// side by side.  Falls back to the complete lane-pair code when the generic formulas degenerate.
+__global__ void __launch_bounds__(32) k_hash_to_g2_coop(size_t n, const uint8_t* msgs, uint32_t msg_len, g2a* out, uint8_t* ok) {
+    __shared__ uint32_t slots[VM_SMEM_WORDS];
+    const int lane = threadIdx.x & 31;
+    vm_load_consts(slots);
+    for (size_t i = blockIdx.x; i < n; i += gridDim.x) {
+        fp2 t; hash_to_fp(t.a, msgs + (size_t)msg_len * i, msg_len); fp_zero(t.b);
+        g2 a; const bool good = sw_map_g2<true>(a, t);                       // warp-uniform: every lane maps the same message
+        g2a res; fp2_zero(res.x); fp2_zero(res.y);
+        if (good) {
+            if (lane == 0) { vm_set_fp2(slots, VM_R_Q2X, a.x); vm_set_fp2(slots, VM_R_Q2Y, a.y); }
+            __syncwarp();
+            if (vm_hash_cofactor(slots)) {
+                if (lane == 0) { vm_ld(res.x.a.l, slots, VM_R_HX, 0); vm_ld(res.x.b.l, slots, VM_R_HX, 1); vm_ld(res.y.a.l, slots, VM_R_HY, 0); vm_ld(res.y.b.l, slots, VM_R_HY, 1); }
+            } else if (lane < 2) {
+                jac<fp2h> A, H; fp2h_pack(A.x, a.x); fp2h_pack(A.y, a.y); fp2h_pack(A.z, a.z);
+                g2_clear_cofactor(H, A);
+                if (!pt_is_inf(H)) {
+                    fp2h zi, zi2, hx, hy; fp2_inv_gcd(zi, H.z); fp2_sqr(zi2, zi);
+                    fp2_mul(hx, H.x, zi2); fp2_mul(zi2, zi2, zi); fp2_mul(hy, H.y, zi2);
+                    fp2h_unpack(res.x, hx); fp2h_unpack(res.y, hy);
+                }
+            }
+        }
+        if (lane == 0) { out[i] = res; ok[i] = good ? 1 : 0; }
+        __syncwarp();
+    }
+}
 
 // same-message batches (the leader's prepare / commit vote collection, consensus/leader.go:127-290: every vote signs
 // the same block hash / commit payload): H(m) is computed once and replicated

@@ -5,7 +5,7 @@
 // ~10^4 dependent field products long.  Here the Miller loop and the final exponentiation run as straight-line STEP PROGRAMS over
 // Fp2 values held in shared memory (vm_programs.cuh, generated and CPU-verified by tools/vmgen.py): in every step each of the 16
 // lane pairs of the warp executes one Fp2 operation -- a product, a squaring, or a small-integer linear combination -- so up to 16
-// independent Fp2 products are in flight.  The whole working set (144 slots x 100 B) stays in shared memory: no local-memory stack.
+// independent Fp2 products are in flight.  The whole working set (150 slots x 100 B) stays in shared memory: no local-memory stack.
 // Linear combinations are stored per lane role as lists of atoms (+- m x one half of one slot) so that all 32 lanes of a step run
 // the same branch-free loop and reduce once.
 //
@@ -226,6 +226,9 @@ HB_DEV void vm_load_consts(uint32_t* slots) {
     if (lane == 2) { fp h; fp_set(h, K_INV2); vm_set_fp(slots, VM_R_INV2, h); }
     if (lane >= 3 && lane < 9) { fp2 g; fp2_const(g, K_FROB1[lane - 3]); vm_set_fp2(slots, VM_R_FROB1_0 + (lane - 3), g); }
     if (lane >= 9 && lane < 15) { fp g; fp_set(g, K_FROB2[lane - 9]); vm_set_fp(slots, VM_R_FROB2_0 + (lane - 9), g); }
+    if (lane == 16) { fp2 c; fp2_const(c, K_PSI_CX); vm_set_fp2(slots, VM_R_PSI_CX, c); }
+    if (lane == 17) { fp2 c; fp2_const(c, K_PSI_CY); vm_set_fp2(slots, VM_R_PSI_CY, c); }
+    if (lane == 18) { fp c; fp_set(c, K_PSI2_CX); vm_set_fp(slots, VM_R_PSI2_CX, c); }
     __syncwarp();
 }
 // x^|z| on (X, ACC) by square-and-multiply, |z| = 0xd201000000010000 (ACC = X on entry = bit 63).  The runs of squarings between
@@ -244,6 +247,42 @@ HB_DEV void vm_expz(uint32_t* slots) {
         if ((K_Z_ABS >> i) & 1) { vm_cycsqr_run(slots, run); run = 0; vm_run(VM_P_MULX, slots); }
     }
     vm_cycsqr_run(slots, run);
+}
+// ---- hash-to-G2 cofactor clearing on the VM (tools/vmgen.py: G2_INIT .. G2_AFF).  T1 = [|z|] T2 (T1 == T2 on entry): 63 doublings in
+// runs of 16 / 8 / 4 / 2 / 1 + an addition of T2 at the five lower set bits of |z|.
+HB_DEV void vm_g2_dbl_run(uint32_t* slots, int run) {
+    while (run >= 16) { vm_run(VM_P_G2DBL16, slots); run -= 16; }
+    if (run & 8) vm_run(VM_P_G2DBL8, slots);
+    if (run & 4) vm_run(VM_P_G2DBL4, slots);
+    if (run & 2) vm_run(VM_P_G2DBL2, slots);
+    if (run & 1) vm_run(VM_P_G2DBL, slots);
+}
+HB_DEV void vm_g2_zmul(uint32_t* slots) {
+    int run = 0;
+    for (int i = 62; i >= 0; i--) {
+        run++;
+        if ((K_Z_ABS >> i) & 1) { vm_g2_dbl_run(slots, run); run = 0; vm_run(VM_P_G2_ADD, slots); }
+    }
+    vm_g2_dbl_run(slots, run);
+}
+// in: (Q2X, Q2Y) = the affine Shallue-van de Woestijne point.  out: (HX, HY) = h(P) affine (Budroni-Pintore, the bytes of
+// curve.cuh g2_clear_cofactor).  false: the generic group law degenerated somewhere (Z = 0: equal / opposite operands or an
+// identity -- never for an honest map output); the caller redoes the message with the complete lane-pair code.
+HB_NOINLINE bool vm_hash_cofactor(uint32_t* slots) {
+    const int lane = threadIdx.x & 31;
+    vm_run(VM_P_G2_INIT, slots); vm_g2_zmul(slots);
+    vm_run(VM_P_HC_MID, slots); vm_g2_zmul(slots);
+    vm_run(VM_P_HC_FIN, slots); vm_run(VM_P_G2_NORM, slots);
+    bool zero = false;
+    if (lane == 0) {
+        fp n, ni; vm_ld(n.l, slots, VM_R_NORM, 0);
+        zero = fp_is_zero(n);
+        fp_inv_gcd(ni, n);
+        vm_set_fp(slots, VM_R_NINV, ni);
+    }
+    if (__ballot_sync(0xffffffffu, zero) & 1u) return false;
+    vm_run(VM_P_G2_AFF, slots);
+    return true;
 }
 // F^(3 (p^12 - 1) / r) == 1 ?  Verdict to every lane.  Easy part around ONE Fp inversion (binary GCD on one lane), hard part = five
 // x^|z| chains.

@@ -157,7 +157,7 @@ extern "C" int emu_vm_pairing(const uint8_t* pk48, const uint8_t* sig96, const u
     if (!g1_deserialize(pk, pk48, true) || !g2_deserialize(sg, sig96, true) || !map_to_g2(h, msg, len)) return -1;
     g1a pa; g2a sa, ha; pt_to_aff(pa, pk); fp_neg(pa.y, pa.y); pt_to_aff(sa, sg); pt_to_aff(ha, h);
     std::vector<uint32_t> sl(VM_SMEM_WORDS, 0); uint32_t* slots = sl.data();
-    for (unsigned lane = 0; lane < 16; lane++) { threadIdx = {lane, 0, 0}; vm_load_consts(slots); }
+    for (unsigned lane = 0; lane < 32; lane++) { threadIdx = {lane, 0, 0}; vm_load_consts(slots); }
     threadIdx = {0, 0, 0};
     fp2 v; fp2_zero(v);
     fp_set(v.a, K_G1_X); vm_set_fp2(slots, VM_R_P1X, v); fp_set(v.a, K_G1_Y); vm_set_fp2(slots, VM_R_P1Y, v);
@@ -184,6 +184,40 @@ extern "C" int emu_vm_pairing(const uint8_t* pk48, const uint8_t* sig96, const u
         for (int j = 0; j < 12; j++) diff |= x.l[j] ^ (lane == 0 ? one.l[j] : 0u);
     }
     return diff == 0 ? 1 : 0;
+}
+
+// hash-to-G2 with the cofactor clearing on the VM (k_hash_to_g2_coop's arithmetic: G2_INIT .. G2_AFF through the device decoders)
+// against the thread-per-item kernel: 1 identical point, 0 different, -1 the map is undefined for this message, -2 degenerate
+static void emu_g2_dbl_run(uint32_t* slots, int run) {
+    while (run >= 16) { emu_vm_run(VM_P_G2DBL16, slots); run -= 16; }
+    if (run & 8) emu_vm_run(VM_P_G2DBL8, slots);
+    if (run & 4) emu_vm_run(VM_P_G2DBL4, slots);
+    if (run & 2) emu_vm_run(VM_P_G2DBL2, slots);
+    if (run & 1) emu_vm_run(VM_P_G2DBL, slots);
+}
+static void emu_g2_zmul(uint32_t* slots) {
+    int run = 0;
+    for (int i = 62; i >= 0; i--) { run++; if ((K_Z_ABS >> i) & 1) { emu_g2_dbl_run(slots, run); run = 0; emu_vm_run(VM_P_G2_ADD, slots); } }
+    emu_g2_dbl_run(slots, run);
+}
+extern "C" int emu_vm_hash(const uint8_t* msg, uint32_t len) {
+    g2a want; uint8_t okw = 0;
+    run_seq(1, 1, [&] { k_hash_to_g2(1, msg, len, &want, &okw); });
+    fp2 t; hash_to_fp(t.a, msg, len); fp_zero(t.b);
+    g2 a; if (!sw_map_g2<true>(a, t)) return okw ? 0 : -1;
+    std::vector<uint32_t> sl(VM_SMEM_WORDS, 0); uint32_t* slots = sl.data();
+    for (unsigned lane = 0; lane < 32; lane++) { threadIdx = {lane, 0, 0}; vm_load_consts(slots); }
+    threadIdx = {0, 0, 0};
+    vm_set_fp2(slots, VM_R_Q2X, a.x); vm_set_fp2(slots, VM_R_Q2Y, a.y);
+    emu_vm_run(VM_P_G2_INIT, slots); emu_g2_zmul(slots);
+    emu_vm_run(VM_P_HC_MID, slots); emu_g2_zmul(slots);
+    emu_vm_run(VM_P_HC_FIN, slots); emu_vm_run(VM_P_G2_NORM, slots);
+    fp n, ni; vm_ld(n.l, slots, VM_R_NORM, 0);
+    if (fp_is_zero(n)) return -2;
+    fp_inv_gcd(ni, n); vm_set_fp(slots, VM_R_NINV, ni);
+    emu_vm_run(VM_P_G2_AFF, slots);
+    g2a got; vm_ld(got.x.a.l, slots, VM_R_HX, 0); vm_ld(got.x.b.l, slots, VM_R_HX, 1); vm_ld(got.y.a.l, slots, VM_R_HY, 0); vm_ld(got.y.b.l, slots, VM_R_HY, 1);
+    return (okw && std::memcmp(&got, &want, sizeof(g2a)) == 0) ? 1 : 0;
 }
 
 // lane-pair decode / hash kernels (latency path) on two host threads against the thread-per-item kernels: bit 0 = decoded

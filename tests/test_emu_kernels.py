@@ -130,6 +130,14 @@ def test_vm_pairing_device_decoders(emuk, oracle):
         assert emuk.emu_vm_pairing(p_, s_, msg, 48) == (1 if oracle.verify_hash(s_, p_, msg) else 0)
     assert emuk.emu_vm_pairing(pk, sig, m, 48) == 1 and emuk.emu_vm_pairing(pk, sig, m2, 48) == 0
 
+def test_vm_hash_cofactor_device_decoders(emuk):
+    """Warp-per-message hash-to-G2 (k_hash_to_g2_coop): the Budroni-Pintore cofactor clearing as VM step programs (G2 doubling runs,
+    additions, psi / psi^2, one inversion), executed with the device decoders, gives the point of the thread-per-item kernel."""
+    for i in range(3):
+        assert emuk.emu_vm_hash(wl.commit_payload("vmh", i), 48) == 1
+    assert emuk.emu_vm_hash(wl.seeded_bytes("vmh/32", 7, 32), 32) == 1
+    assert emuk.emu_vm_hash(bytes(48), 48) == -1                      # t = 0: the map is undefined (SignHash returns nil)
+
 def test_lane_pair_decode_and_hash_kernels(emuk, oracle):
     """k_g2_decode_pair / k_hash_to_g2_pair (item per lane pair, latency path) == the thread-per-item kernels: valid signatures,
     a point outside the subgroup / undecodable bytes / the identity, messages incl. one that maps to no point."""

@@ -38,6 +38,10 @@ def f2_pow(x, e):
     return r
 XI = (1, 1)
 CONSTS = {"ZERO": (0, 0), "ONE": (1, 0), "TWIST3B": (12, 12), "INV2": (pow(2, -1, P), 0)}       # TWIST3B = 3 b' = 3 * 4(1 + i)
+# psi endomorphism of E'(Fp2) (oracle/pyref.py PSI_CX / PSI_CY; curve.cuh g2_psi): psi(x, y) = (conj(x) cx, conj(y) cy)
+def f2_inv(x): return f2_pow(x, P * P - 2)
+CONSTS["PSI_CX"] = f2_inv(f2_pow(XI, (P - 1) // 3)); CONSTS["PSI_CY"] = f2_inv(f2_pow(XI, (P - 1) // 2))
+CONSTS["PSI2_CX"] = f2_mul(CONSTS["PSI_CX"], (CONSTS["PSI_CX"][0], -CONSTS["PSI_CX"][1])); assert CONSTS["PSI2_CX"][1] == 0
 for k in range(6):
     CONSTS[f"FROB1_{k}"] = f2_pow(XI, k * (P - 1) // 6)
     g2 = f2_pow(XI, k * (P * P - 1) // 6); assert g2[1] == 0
@@ -226,17 +230,43 @@ def ml_add(T, qx, qy):
     y3 = (G - H) * th - E * y
     return (x3, y3, z * E), (l0, -th, mu)
 def line_at(l, px, py): return l[0], l[1] * px, l[2] * py
+# ---- G2 group law in Jacobian coordinates (a = 0): the cofactor clearing of hash-to-G2 on the VM (curve.cuh g2_clear_cofactor).
+# Generic formulas: a degenerate addition (equal / opposite operands, an identity) yields Z = 0, which stays 0 through every later
+# operation -- the kernel then redoes the message with the complete lane-pair code.
+def g2_dbl(T):
+    x, y, z = T
+    A, B = x.sqr(), y.sqr()
+    Cc, C4 = B.sqr(), B.dbl().sqr()                  # Y^4 and 4 Y^4 (coefficients of a linear combination stay <= 7)
+    S = (x + B).sqr()
+    E = A.scale(3); F = E.sqr()
+    x3 = F - S.scale(4) + A.scale(4) + C4              # F - 2 D,  D = 2 (S - A - C)
+    W = S.scale(6) - A.scale(6) - Cc.scale(6) - F      # D - x3 = 3 D - F
+    return (x3, E * W - C4.dbl(), (y * z).dbl())
+def g2_add(T, Q):
+    x1, y1, z1 = T; x2, y2, z2 = Q
+    z1z1, z2z2 = z1.sqr(), z2.sqr()
+    u1, u2 = x1 * z2z2, x2 * z1z1
+    s1, s2 = (y1 * z2) * z2z2, (y2 * z1) * z1z1
+    h = u2 - u1
+    i = h.dbl().sqr(); j = h * i
+    r = (s2 - s1).dbl()
+    v = u1 * i
+    x3 = r.sqr() - j - v.dbl()
+    return (x3, r * (v - x3) - (s1 * j).dbl(), ((z1 + z2).sqr() - z1z1 - z2z2) * h)
+def g2_neg(T): return (T[0], -T[1], T[2])
+def g2_psi(T, k): return (T[0].conj() * k("PSI_CX"), T[1].conj() * k("PSI_CY"), T[2].conj())
+def g2_psi2(T, k): return (T[0] * k("PSI2_CX"), -T[1], T[2])
 
 # ------------------------------------------------------------------ programs.  Persistent registers (fixed slots, shared by all programs)
-REG_CONST = ["ZERO", "ONE", "TWIST3B", "INV2"] + [f"FROB1_{k}" for k in range(6)] + [f"FROB2_{k}" for k in range(6)]
+REG_CONST = ["ZERO", "ONE", "TWIST3B", "INV2"] + [f"FROB1_{k}" for k in range(6)] + [f"FROB2_{k}" for k in range(6)] + ["PSI_CX", "PSI_CY", "PSI2_CX"]
 REG_IN = ["P1X", "P1Y", "Q1X", "Q1Y", "P2X", "P2Y", "Q2X", "Q2Y"]
 def r6(n): return [f"{n}{i}" for i in range(6)]
 REG_STATE = ["T1X", "T1Y", "T1Z", "T2X", "T2Y", "T2Z"] + r6("F") + r6("M") + r6("X") + r6("ACC") + r6("A") + r6("B") + r6("C") + \
-            ["IT0", "IT1", "IT2", "ID", "NORM", "NINV"]
+            ["IT0", "IT1", "IT2", "ID", "NORM", "NINV", "HX", "HY"]
 REGS = REG_CONST + REG_IN + REG_STATE
 assert len(set(REGS)) == len(REGS), "duplicate register name"
 SLOT = {r: i for i, r in enumerate(REGS)}
-NSLOTS = 144        # slots per warp (100 B each): 78 registers + temporaries; lowest-free-first allocation keeps every program under it (14.4 KB per warp)
+NSLOTS = 150        # slots per warp (100 B each): 83 registers + temporaries; lowest-free-first allocation keeps every program under it (15 KB per warp)
 
 def build_programs(make_graph):
     """every program as a function of a fresh graph; returns {name: graph}"""
@@ -367,6 +397,47 @@ def build_programs(make_graph):
     def p_glue6(g, k):            # result = d * m^3  (two short programs instead of one: the slot working set stays under 128)
         m = get6(g, "M")
         put6(g, "ACC", fp12_mul(get6(g, "B"), fp12_mul(fp12_cyc_sqr(m), m)))
+    # ---- hash-to-G2 cofactor clearing (Budroni-Pintore, curve.cuh g2_clear_cofactor): h(P) = [z^2 - z - 1]P + psi([z - 1]P) + psi^2([2]P)
+    # with P = (Q2X, Q2Y) the affine Shallue-van de Woestijne point.  [|z|] = 63 doublings of T1 (run programs like the cyclotomic
+    # squarings) + 5 additions of T2.  Result affine in (HX, HY) around ONE Fp inversion (NORM -> NINV, like the final exponentiation).
+    def getT(g, t): return (g.inp(t + "X"), g.inp(t + "Y"), g.inp(t + "Z"))
+    def putT(g, t, v):
+        for c, x in zip("XYZ", v): g.out(t + c, x)
+    @prog
+    def p_g2_init(g, k):
+        pt = (g.inp("Q2X"), g.inp("Q2Y"), k("ONE")); putT(g, "T1", pt); putT(g, "T2", pt)
+    def g2_dbl_run(n):
+        def f(g, k):
+            T = getT(g, "T1")
+            for _ in range(n):
+                T = g2_dbl(T); T = tuple(V(g, {x.node(): I2}) for x in T)
+            putT(g, "T1", T)
+        f.__name__ = "p_g2dbl" + (str(n) if n > 1 else ""); return f
+    for n in (1, 2, 4, 8, 16): prog(g2_dbl_run(n))
+    @prog
+    def p_g2_add(g, k): putT(g, "T1", g2_add(getT(g, "T1"), getT(g, "T2")))
+    @prog
+    def p_hc_mid(g, k):           # T1 = [|z|]P  ->  zp = [z]P = -T1 (z < 0), kept in M0..2; next chain starts from zp
+        zp = g2_neg(getT(g, "T1"))
+        for r, x in zip(("M0", "M1", "M2"), zp): g.out(r, x)
+        putT(g, "T1", zp); putT(g, "T2", zp)
+    @prog
+    def p_hc_fin(g, k):           # T1 = [|z|]zp -> z2p = -T1
+        z2p = g2_neg(getT(g, "T1"))
+        zp = (g.inp("M0"), g.inp("M1"), g.inp("M2"))
+        pt = (g.inp("Q2X"), g.inp("Q2Y"), k("ONE")); npt = g2_neg(pt)
+        def mat(T): return tuple(V(g, {x.node(): I2}) for x in T)
+        t1 = mat(g2_add(mat(g2_add(z2p, npt)), g2_neg(zp)))
+        t2 = mat(g2_psi(mat(g2_add(zp, npt)), k))
+        t3 = mat(g2_psi2(mat(g2_dbl(pt)), k))
+        putT(g, "T1", g2_add(mat(g2_add(t1, t2)), t3))
+    @prog
+    def p_g2_norm(g, k):
+        z = g.inp("T1Z"); g.out("NORM", z * z.conj())
+    @prog
+    def p_g2_aff(g, k):
+        zi = g.inp("T1Z").conj() * g.inp("NINV"); zi2 = zi.sqr()
+        g.out("HX", g.inp("T1X") * zi2); g.out("HY", g.inp("T1Y") * (zi2 * zi))
     return progs
 
 # ------------------------------------------------------------------ scheduling + slot allocation
@@ -520,6 +591,24 @@ def vm_product_is_one(progs, pairs_per_part):
         run_program(progs["FMULA"], s)
     final_exp_vm(progs, s)
     return [s[SLOT[r]] for r in r6("ACC")] == [(1, 0)] + [(0, 0)] * 5
+def vm_clear_cofactor(progs, pt):
+    """hash-to-G2 cofactor clearing on the VM programs: pt = affine ((x0, x1), (y0, y1)) -> affine h(pt), or None when the generic
+    formulas degenerate (Z = 0)"""
+    s = fresh_slots()
+    s[SLOT["Q2X"]], s[SLOT["Q2Y"]] = pt
+    def zmul():
+        for run, add in expz_schedule():
+            for n in (16, 8, 4, 2, 1):
+                while run >= n: run_program(progs["G2DBL" if n == 1 else f"G2DBL{n}"], s); run -= n
+            if add: run_program(progs["G2_ADD"], s)
+    run_program(progs["G2_INIT"], s); zmul()
+    run_program(progs["HC_MID"], s); zmul()
+    run_program(progs["HC_FIN"], s); run_program(progs["G2_NORM"], s)
+    n = s[SLOT["NORM"]]; assert n[1] == 0
+    if n[0] == 0: return None
+    s[SLOT["NINV"]] = (fp_inv(n[0]), 0)
+    run_program(progs["G2_AFF"], s)
+    return s[SLOT["HX"]], s[SLOT["HY"]]
 def expz_schedule():
     """x^|z| by square-and-multiply from bit 62 down: [(number of squarings, multiply afterwards?), ...]"""
     out = []; run = 0
@@ -572,7 +661,8 @@ def enc_lin(dst, terms):
 def enc_mul(dst, a, b): return [dst | (a << 8) | (b << 16)] + [0] * (INS_WORDS - 1)
 NOP = [0xff] + [0] * (INS_WORDS - 1)          # dst 0xff = no operation
 PROGRAM_ORDER = ["ML_INIT", "ML_DBL", "ML_DBL2", "ML_ADD", "FE_INV_A", "FE_INV_B", "CYCSQR", "CYCSQR2", "CYCSQR4", "CYCSQR8", "CYCSQR16", "MULX",
-                 "GLUE1", "GLUE2", "GLUE3", "GLUE4", "GLUE5", "GLUE6", "ML1_INIT", "ML1_DBL", "ML1_ADD", "A_ONE", "AMULF", "FMULA"]
+                 "GLUE1", "GLUE2", "GLUE3", "GLUE4", "GLUE5", "GLUE6", "ML1_INIT", "ML1_DBL", "ML1_ADD", "A_ONE", "AMULF", "FMULA",
+                 "G2_INIT", "G2DBL", "G2DBL2", "G2DBL4", "G2DBL8", "G2DBL16", "G2_ADD", "HC_MID", "HC_FIN", "G2_NORM", "G2_AFF"]
 
 def emit(progs, path):
     order = PROGRAM_ORDER
