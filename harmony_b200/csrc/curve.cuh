@@ -209,6 +209,63 @@ template <class F> HB_NOINLINE void pt_mul_2d_aff(jac<F>& r, const aff<F>& p, co
     r = acc;
 }
 
+// ---- the same two-base ladders over the JOINT SPARSE FORM of (a, b) (Solinas): signed digits u0_i, u1_i in {-1, 0, 1}, <= 33 digit
+// pairs of which on average 16.8 are non-zero (24 of 32 for the plain binary pairs above) -- 6 additions fewer per ladder after the
+// one extra table entry P - P2.  The digits depend on the coefficient only, which a warp's 32 rounds share: control flow stays uniform.
+// Bit i of nz0 / ng0 (nz1 / ng1): digit i of a (of b) is non-zero / negative.  Returns the number of digits.
+HB_DEV int jsf_pack(uint32_t a, uint32_t b, uint64_t& nz0, uint64_t& ng0, uint64_t& nz1, uint64_t& ng1) {
+    uint64_t k0 = a, k1 = b; uint32_t d0 = 0, d1 = 0; int n = 0;
+    nz0 = ng0 = nz1 = ng1 = 0;
+    while (k0 + d0 != 0 || k1 + d1 != 0) {
+        const uint32_t l0 = (uint32_t)((k0 + d0) & 7u), l1 = (uint32_t)((k1 + d1) & 7u);
+        int u0 = 0, u1 = 0;
+        if (l0 & 1u) { u0 = (l0 & 3u) == 1u ? 1 : -1; if ((l0 == 3u || l0 == 5u) && (l1 & 3u) == 2u) u0 = -u0; }
+        if (l1 & 1u) { u1 = (l1 & 3u) == 1u ? 1 : -1; if ((l1 == 3u || l1 == 5u) && (l0 & 3u) == 2u) u1 = -u1; }
+        if (2 * (int)d0 == 1 + u0) d0 = 1u - d0;
+        if (2 * (int)d1 == 1 + u1) d1 = 1u - d1;
+        k0 >>= 1; k1 >>= 1;
+        if (u0) { nz0 |= 1ull << n; if (u0 < 0) ng0 |= 1ull << n; }
+        if (u1) { nz1 |= 1ull << n; if (u1 < 0) ng1 |= 1ull << n; }
+        n++;
+    }
+    return n;
+}
+template <class F> HB_NOINLINE void pt_mul_2d_jsf(jac<F>& r, const jac<F>& p, const jac<F>& p2, uint32_t a, uint32_t b) {
+    uint64_t nz0, ng0, nz1, ng1; const int n = jsf_pack(a, b, nz0, ng0, nz1, ng1);
+    jac<F> t, m, q; pt_add(t, p, p2); pt_neg(q, p2); pt_add(m, p, q);          // P + P2, P - P2
+    jac<F> acc; pt_set_inf(acc);
+    for (int i = n - 1; i >= 0; i--) {
+        HB_USYNC();
+        pt_dbl(acc, acc);
+        const bool z0 = (nz0 >> i) & 1, z1 = (nz1 >> i) & 1, n0 = (ng0 >> i) & 1, n1 = (ng1 >> i) & 1;
+        if (!z0 && !z1) continue;
+        // +-P, +-P2, +-(P + P2) when the signs agree, +-(P - P2) when they differ; the overall sign is that of the a-digit (or of
+        // the b-digit when a's is zero)
+        const bool neg = z0 ? n0 : n1;
+        q = (z0 && z1) ? (n0 == n1 ? t : m) : (z0 ? p : p2);
+        if (neg) pt_neg(q, q);
+        pt_add(acc, acc, q);
+    }
+    r = acc;
+}
+template <class F> HB_NOINLINE void pt_mul_2d_aff_jsf(jac<F>& r, const aff<F>& p, const aff<F>& p2, uint32_t a, uint32_t b) {
+    uint64_t nz0, ng0, nz1, ng1; const int n = jsf_pack(a, b, nz0, ng0, nz1, ng1);
+    jac<F> t, m, q; aff<F> w;
+    pt_from_aff(t, p); pt_add_mixed(t, t, p2);
+    w = p2; f_neg(w.y, w.y); pt_from_aff(m, p); pt_add_mixed(m, m, w);
+    jac<F> acc; pt_set_inf(acc);
+    for (int i = n - 1; i >= 0; i--) {
+        HB_USYNC();
+        pt_dbl(acc, acc);
+        const bool z0 = (nz0 >> i) & 1, z1 = (nz1 >> i) & 1, n0 = (ng0 >> i) & 1, n1 = (ng1 >> i) & 1;
+        if (!z0 && !z1) continue;
+        const bool neg = z0 ? n0 : n1;
+        if (z0 && z1) { q = n0 == n1 ? t : m; if (neg) pt_neg(q, q); pt_add(acc, acc, q); }
+        else { w = z0 ? p : p2; if (neg) f_neg(w.y, w.y); pt_add_mixed(acc, acc, w); }
+    }
+    r = acc;
+}
+
 HB_DEV void g1_generator(g1& r) { fp_set(r.x, K_G1_X); fp_set(r.y, K_G1_Y); fp_one(r.z); }
 
 // ------------------------------------------------------------------ endomorphisms and subgroup membership
@@ -255,10 +312,21 @@ HB_DEV void rlc_scale_pair(g1& ra, g2& rs, const g1& apk, const g2a& sig, uint64
     const uint32_t a = (uint32_t)c | 1u, b = (uint32_t)(c >> 32);
     g1 p2; fp beta; fp_set(beta, K_BETA);
     fp_mul(p2.x, apk.x, beta); fp_neg(p2.y, apk.y); p2.z = apk.z;
+#ifndef HB_JSF
+#define HB_JSF 1
+#endif
+#if HB_JSF
+    pt_mul_2d_jsf(ra, apk, p2, a, b);
+#else
     pt_mul_2d(ra, apk, p2, a, b);
+#endif
     g2a q2; fp cx; fp_set(cx, K_PSI2_CX);
     fp2_mul_fp(q2.x, sig.x, cx); fp2_neg(q2.y, sig.y);
+#if HB_JSF
+    pt_mul_2d_aff_jsf(rs, sig, q2, a, b);
+#else
     pt_mul_2d_aff(rs, sig, q2, a, b);
+#endif
 }
 
 // ------------------------------------------------------------------ codecs (reference crypto/bls/bls.go:67-71,109-118)

@@ -639,10 +639,15 @@ __global__ void k_rlc_scale(size_t B, size_t ng, const g1* apk, const g2a* sig, 
         const size_t j = j0 + (size_t)k * HB_STRIDE;
         skip[k] = true;
         if (j >= B) continue;
-        const uint64_t r = per_item ? per_item[j] : co.c[j / ng];
+        // grouped form: the FIRST round of every group keeps coefficient 1 (no ladders at all: a warp-uniform branch, since the 32
+        // rounds of a warp share their position).  Sound: a group holding a bad round passes only if prod_j delta_j^{s_j} = 1 with
+        // some delta_j != 1; if that j is 0 alone the product is delta_0 != 1, otherwise one of the random s_j (j >= 1) must hit
+        // the single value mod r that cancels the rest -- probability <= 2^-63, as before.
+        const uint64_t r = per_item ? per_item[j] : (j < ng ? 1ull : co.c[j / ng]);
         g1 a = apk[j]; g2a sg = sig[j]; g2a h = hm[j];
         const bool b = !ok_sig[j] || !ok_hm[j] || (ok_pk && !ok_pk[j]) || pt_is_inf(a) || aff_is_inf(sg) || aff_is_inf(h);
-        g2 rs; rlc_scale_pair(ra[k], rs, a, sg, r);
+        g2 rs;
+        if (r == 1ull && !per_item) { ra[k] = a; pt_from_aff(rs, sg); } else rlc_scale_pair(ra[k], rs, a, sg, r);
         S[j] = rs; bad[j] = b ? 1 : 0;
         skip[k] = pt_is_inf(ra[k]);
         if (!skip[k]) z[k] = ra[k].z;
@@ -658,10 +663,11 @@ __global__ void k_rlc_scale(size_t B, size_t ng, const g1* apk, const g2a* sig, 
   }
 #else
   for (size_t j = HB_TID; j < B; j += HB_STRIDE) {
-    const uint64_t r = per_item ? per_item[j] : co.c[j / ng];
+    const uint64_t r = per_item ? per_item[j] : (j < ng ? 1ull : co.c[j / ng]);
     g1 a = apk[j]; g2a sg = sig[j]; g2a h = hm[j];
     const bool b = !ok_sig[j] || !ok_hm[j] || (ok_pk && !ok_pk[j]) || pt_is_inf(a) || aff_is_inf(sg) || aff_is_inf(h);
-    g1 ra; g2 rs; rlc_scale_pair(ra, rs, a, sg, r);
+    g1 ra; g2 rs;
+    if (r == 1ull && !per_item) { ra = a; pt_from_aff(rs, sg); } else rlc_scale_pair(ra, rs, a, sg, r);
     g1a pa; pt_to_aff(pa, ra); fp_neg(pa.y, pa.y);
     pk_scaled_neg[j] = pa; S[j] = rs; bad[j] = b ? 1 : 0;
   }

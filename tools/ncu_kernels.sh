@@ -12,5 +12,9 @@ cap k_hash_to_g2 '^k_hash_to_g2$|hb::k_hash_to_g2\(' 303104
 cap k_g2_decode 'k_g2_decode\(' 303104
 cap k_rlc_scale 'k_rlc_scale' 303104
 cap k_mask_aggregate_serial 'k_mask_aggregate_serial' 303104
-export HBLS_COOP_MAX=100000 HBLS_RLC_MIN=1000000
-cap k_pairing_coop 'k_pairing_coop' 1332
+# latency path: ONE round (a warp per kernel): the Miller value of (B, sigma), hash-to-G2 with the cofactor clearing on the VM, and the
+# product + final exponentiation of the H(m)-cached form
+export HBLS_HM_CACHE=0
+cap k_pairing_coop2 'k_pairing_coop2' 1
+cap k_hash_to_g2_coop 'k_hash_to_g2_coop' 1
+cap k_g2_decode_pair 'k_g2_decode_pair' 1
