@@ -9,7 +9,7 @@ cap() {  # name regex rounds [env...]
   rm -f /tmp/r2_$name.ncu-rep
 }
 cap k_hash_to_g2 '^k_hash_to_g2$|hb::k_hash_to_g2\(' 303104
-cap k_g2_decode 'k_g2_decode\(' 303104
+cap k_g2_decode '^k_g2_decode$' 303104
 cap k_rlc_scale 'k_rlc_scale' 303104
 cap k_mask_aggregate_serial 'k_mask_aggregate_serial' 303104
 # latency path: ONE round (a warp per kernel): the Miller value of (B, sigma), hash-to-G2 with the cofactor clearing on the VM, and the
