@@ -39,7 +39,7 @@ struct Ctx {
     bool stage_timing = false; Scratch* stage_sc = nullptr;
     int batch_mode = 1;                                     // 1: random-linear-combination groups + exact pass over failed groups, 0: exact per round
     // tuning (hbls_set_param)
-    long long rlc_min = 6144, rlc_g = 0, tpsm = 384, tpsm_split = 512, tpsm_light = 1024, coop_max = 6143, overlap = 1, coop_wpsm = 14, hash_coop_max = 592;
+    long long rlc_min = 6144, rlc_g = 0, tpsm = 384, tpsm_split = 512, tpsm_light = 1024, coop_max = 6143, overlap = 1, coop_wpsm = 14, hash_coop_max = 592, mask_sort = 1;
     // coefficient stream: ChaCha20 keyed from /dev/urandom, block counter = call number
     uint32_t chacha_key[8] = {}; uint64_t rlc_calls = 0;
     // last batch
@@ -192,12 +192,13 @@ std::vector<uint64_t> rlc_draw_items(size_t k) {
 
 // ------------------------------------------------------------------ one verification pass over device-resident inputs.
 size_t verify_scratch_bytes(size_t B) {
-    return B * (sizeof(g2a) * 2 + sizeof(g1a) * 2 + sizeof(g1) + sizeof(g2) + 16 + 4) + (B / HB_RLC_G + 1) * (sizeof(g2a) + 8) + 40 * 256
+    return B * (sizeof(g2a) * 2 + sizeof(g1a) * 2 + sizeof(g1) + sizeof(g2) + 16 + 4 + 6) + HB_MASK_BINS * 4 + (B / HB_RLC_G + 1) * (sizeof(g2a) + 8) + 44 * 256
            + (B <= 8192 ? B * (12 * sizeof(fp2) + 3) + 1024 : 0);               // latency path: Miller values of (B, sigma) and (-apk, H(m))
 }
 struct VerifyBufs { g2a* sig; g2a* hm; g1a* pkneg; g1* apk; uint8_t* ok_sig; uint8_t* ok_hm; uint8_t* ok_pk;
                     g1a* pk_scaled; g2* S; uint8_t* bad; g2a* Sg; uint8_t* group_ok; uint32_t* fail_list; unsigned* counts;
-                    fp2* f1; uint8_t* irr1; fp2* f2; uint8_t* irr2; uint8_t* ok_sub; };
+                    fp2* f1; uint8_t* irr1; fp2* f2; uint8_t* irr2; uint8_t* ok_sub;
+                    uint16_t* mask_cost; unsigned* mask_hist; uint32_t* mask_order; };
 VerifyBufs carve_verify(Arena& ar, size_t B) {
     VerifyBufs v;
     v.sig = ar.take<g2a>(B); v.hm = ar.take<g2a>(B); v.pkneg = ar.take<g1a>(B); v.apk = ar.take<g1>(B);
@@ -205,6 +206,7 @@ VerifyBufs carve_verify(Arena& ar, size_t B) {
     v.pk_scaled = ar.take<g1a>(B); v.S = ar.take<g2>(B); v.bad = ar.take<uint8_t>(B);
     v.Sg = ar.take<g2a>(B / HB_RLC_G + 1); v.group_ok = ar.take<uint8_t>(B / HB_RLC_G + 1);
     v.fail_list = ar.take<uint32_t>(B); v.counts = ar.take<unsigned>(2);
+    v.mask_cost = ar.take<uint16_t>(B); v.mask_hist = ar.take<unsigned>(HB_MASK_BINS); v.mask_order = ar.take<uint32_t>(B);
     v.f1 = v.f2 = nullptr; v.irr1 = v.irr2 = v.ok_sub = nullptr;
     if (B <= 8192) { v.f1 = ar.take<fp2>(6 * B); v.irr1 = ar.take<uint8_t>(B); v.f2 = ar.take<fp2>(6 * B); v.irr2 = ar.take<uint8_t>(B); v.ok_sub = ar.take<uint8_t>(B); }
     return v;
@@ -489,7 +491,18 @@ int agg_verify_device_locked(const hbls_committee* c, size_t B, const uint8_t* d
     fork_point(B, sc, s);
     STAGE_EV(0, sc, s);
     if (B >= (size_t)g.sm_count * 256)
-        LAUNCH(k_mask_aggregate_serial, light_blocks(B), TPB, s, B, c->n, c->table, c->total, d_bitmaps, blen, v.apk);
+    {
+        // rounds sorted by the number of point additions they need (device counting sort), so that the lanes of a warp finish together
+        const uint32_t* order = nullptr;
+        if (g.mask_sort && B <= 0xffffffffull) {
+            cudaMemsetAsync(v.mask_hist, 0, HB_MASK_BINS * sizeof(unsigned), s);
+            LAUNCH(k_mask_count, blocks_for(B, 256), 256, s, B, c->n, d_bitmaps, blen, v.mask_cost, v.mask_hist);
+            LAUNCH(k_mask_scan, 1, 32, s, v.mask_hist);
+            LAUNCH(k_mask_scatter, blocks_for(B, 256), 256, s, B, v.mask_cost, v.mask_hist, v.mask_order);
+            order = v.mask_order;
+        }
+        LAUNCH(k_mask_aggregate_serial, light_blocks(B), TPB, s, B, c->n, c->table, c->total, d_bitmaps, blen, v.apk, order);
+    }
     else
         LAUNCH(k_mask_aggregate, blocks_for(B * 32, 128), 128, s, B, c->n, c->table, d_bitmaps, blen, v.apk);
     launch_verify_tail(B, v, sc, d_sigs, d_msgs, (uint32_t)msg_len, nullptr, d_results, s, same_msg, h_msg);
@@ -541,7 +554,7 @@ int hbls_init_device(int device) {
     for (int i = 0; i < Ctx::HM_N; i++) {
         CK(cudaEventCreateWithFlags(&g.hm[i].filled, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&g.hm[i].read_done, cudaEventDisableTiming));
     }
-    g.hm_cache = envll("HBLS_HM_CACHE", 1);
+    g.hm_cache = envll("HBLS_HM_CACHE", 1); g.mask_sort = envll("HBLS_MASK_SORT", 1); g.hash_coop_max = envll("HBLS_HASH_COOP_MAX", 592);
     g.ready = true;
     return 0;
 }
@@ -567,6 +580,7 @@ static long long* param_slot(const char* name) {
     if (!strcmp(name, "coop_wpsm")) return &g.coop_wpsm;
     if (!strcmp(name, "hm_cache")) return &g.hm_cache;
     if (!strcmp(name, "hash_coop_max")) return &g.hash_coop_max;
+    if (!strcmp(name, "mask_sort")) return &g.mask_sort;
     return nullptr;
 }
 int hbls_set_param(const char* name, long long value) {

@@ -101,9 +101,32 @@ __global__ void k_mask_aggregate_items(size_t B, const mask_item* __restrict__ i
 // hbls_committee_create) -- from a compacted index list: ~44 point additions per round instead of ~206, and the
 // loop trip counts of the 32 lanes are short and similar.  Group arithmetic only; Serialize normalises.
 #define HB_MASK_LIST 512
+// The 32 lanes of a warp run as long as the lane with the most additions (167 / 200 / 250 signers of 250 = 83 / 50 / 0 additions:
+// ncu showed the multiplier 82 % busy for work worth 43 %).  `order` (nullable) = the rounds sorted by the number of additions they
+// need (counting sort on the device: k_mask_count -> k_mask_scan -> k_mask_scatter), so that neighbouring lanes get equal trip counts.
+#define HB_MASK_BINS 1024
+__global__ void k_mask_count(size_t B, size_t n, const uint8_t* __restrict__ bitmaps, size_t blen, uint16_t* cost, unsigned* hist) {
+    const size_t j = HB_TID; if (j >= B) return;
+    const uint8_t* bm = bitmaps + j * blen;
+    uint32_t k = 0;
+    for (size_t i = 0; i < n; i++) k += (bm[i >> 3] >> (i & 7)) & 1u;
+    uint32_t c = (2 * (size_t)k > n) ? (uint32_t)(n - k) : k;            // the side k_mask_aggregate_serial will sum
+    if (c >= HB_MASK_BINS) c = HB_MASK_BINS - 1;
+    cost[j] = (uint16_t)c; atomicAdd(&hist[c], 1u);
+}
+__global__ void k_mask_scan(unsigned* hist) {                             // exclusive prefix sum of the bins, one thread (1 024 adds)
+    if (HB_TID != 0) return;
+    unsigned acc = 0;
+    for (int i = 0; i < HB_MASK_BINS; i++) { const unsigned h = hist[i]; hist[i] = acc; acc += h; }
+}
+__global__ void k_mask_scatter(size_t B, const uint16_t* cost, unsigned* hist, uint32_t* order) {
+    const size_t j = HB_TID; if (j >= B) return;
+    order[atomicAdd(&hist[cost[j]], 1u)] = (uint32_t)j;
+}
 __global__ void k_mask_aggregate_serial(size_t B, size_t n, const g1a* __restrict__ table, const g1* __restrict__ total,
-                                        const uint8_t* __restrict__ bitmaps, size_t blen, g1* out) {
-  for (size_t j = HB_TID; j < B; j += HB_STRIDE) {
+                                        const uint8_t* __restrict__ bitmaps, size_t blen, g1* out, const uint32_t* __restrict__ order = nullptr) {
+  for (size_t jt = HB_TID; jt < B; jt += HB_STRIDE) {
+    const size_t j = order ? order[jt] : jt;
     const uint8_t* bm = bitmaps + j * blen;
     uint32_t k = 0;
     for (size_t i = 0; i < n; i++) k += (bm[i >> 3] >> (i & 7)) & 1u;
