@@ -39,7 +39,7 @@ struct Ctx {
     bool stage_timing = false; Scratch* stage_sc = nullptr;
     int batch_mode = 1;                                     // 1: random-linear-combination groups + exact pass over failed groups, 0: exact per round
     // tuning (hbls_set_param)
-    long long rlc_min = 6144, rlc_g = 0, tpsm = 384, tpsm_split = 512, tpsm_light = 1024, coop_max = 6143, overlap = 1, coop_wpsm = 14, hash_coop_max = 592, mask_sort = 1;
+    long long rlc_min = 6144, rlc_g = 0, tpsm = 384, tpsm_split = 512, tpsm_light = 1024, coop_max = 6143, overlap = 1, coop_wpsm = 14, hash_coop_max = 592, mask_sort = 1, hash_split = 1, tpsm_sw = 512;
     // coefficient stream: ChaCha20 keyed from /dev/urandom, block counter = call number
     uint32_t chacha_key[8] = {}; uint64_t rlc_calls = 0;
     // last batch
@@ -268,7 +268,10 @@ void launch_verify_tail(size_t B, const VerifyBufs& v, Scratch* sc, const uint8_
         if (B > 1) LAUNCH(k_broadcast_hm, blocks_for(B, 256), 256, sh, B, v.hm, v.ok_hm);
     } else if (pairs)
         launch_hash_small(sh, B, d_msgs, msg_len, v.hm, v.ok_hm);
-    else
+    else if (g.hash_split && HB_BATCH_INV) {
+        LAUNCH(k_hash_sw, capped_blocks(B, g.tpsm_sw, TPB), TPB, s, B, d_msgs, msg_len, v.hm, v.ok_hm);
+        LAUNCH(k_hash_cofactor, heavy_blocks(B), TPB, s, B, v.hm, (const uint8_t*)v.ok_hm);
+    } else
         LAUNCH(k_hash_to_g2, heavy_blocks(B), TPB, s, B, d_msgs, msg_len, v.hm, v.ok_hm);
     if (warm) {
         cudaEventRecord(sc->join[1], sh); cudaStreamWaitEvent(s, sc->join[1], 0);
@@ -555,6 +558,9 @@ int hbls_init_device(int device) {
         CK(cudaEventCreateWithFlags(&g.hm[i].filled, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&g.hm[i].read_done, cudaEventDisableTiming));
     }
     g.hm_cache = envll("HBLS_HM_CACHE", 1); g.mask_sort = envll("HBLS_MASK_SORT", 1); g.hash_coop_max = envll("HBLS_HASH_COOP_MAX", 592);
+    g.hash_split = envll("HBLS_HASH_SPLIT", 1); g.tpsm_sw = envll("HBLS_TPSM_SW", 512);
+    cudaFuncSetAttribute(k_hash_sw, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    cudaFuncSetAttribute(k_hash_cofactor, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     g.ready = true;
     return 0;
 }
@@ -581,6 +587,8 @@ static long long* param_slot(const char* name) {
     if (!strcmp(name, "hm_cache")) return &g.hm_cache;
     if (!strcmp(name, "hash_coop_max")) return &g.hash_coop_max;
     if (!strcmp(name, "mask_sort")) return &g.mask_sort;
+    if (!strcmp(name, "hash_split")) return &g.hash_split;
+    if (!strcmp(name, "tpsm_sw")) return &g.tpsm_sw;
     return nullptr;
 }
 int hbls_set_param(const char* name, long long value) {

@@ -256,6 +256,57 @@ __global__ void k_hash_to_g2(size_t n, const uint8_t* msgs, uint32_t msg_len, g2
 #endif
 }
 
+// ---- the same hash in two kernels (large batches, hbls.cu "hash_split"): the Shallue-van de Woestijne map is Fp-only work (square-
+// root exponentiation chains, Jacobi symbols, the shared inversion) with a small register and instruction-cache footprint, the
+// cofactor clearing is G2 ladders over Fp2.  Separate kernels let the first run with more resident warps and keep each kernel's hot
+// code small (ncu on the fused kernel: stall_no_instruction 0.78 per issue, 3 warps per scheduler).
+#ifndef HB_SW_MINBLOCKS
+#define HB_SW_MINBLOCKS 8         // x 64 threads = 512 resident threads per SM (<= 128 registers); measured 64.6 -> 62.4 ms per 303 104 messages
+#endif
+__global__ void __launch_bounds__(64, HB_SW_MINBLOCKS) k_hash_sw(size_t n, const uint8_t* msgs, uint32_t msg_len, g2a* pts, uint8_t* ok) {
+  for (size_t i0 = HB_TID; i0 < n; i0 += (size_t)HB_BATCH_K * HB_STRIDE) {
+    fp2 z[HB_BATCH_K], t[HB_BATCH_K], u[HB_BATCH_K], ct[HB_BATCH_K]; bool skip[HB_BATCH_K];
+    for (int k = 0; k < HB_BATCH_K; k++) {
+        const size_t i = i0 + (size_t)k * HB_STRIDE;
+        skip[k] = true;
+        if (i >= n) continue;
+        fp_zero(t[k].b); hash_to_fp(t[k].a, msgs + (size_t)msg_len * i, msg_len);
+        skip[k] = !sw_map_g2_pre(u[k], ct[k], z[k], t[k]);
+    }
+    f_batch_inv<fp2, HB_BATCH_K>(z, skip);
+    for (int k = 0; k < HB_BATCH_K; k++) {
+        const size_t i = i0 + (size_t)k * HB_STRIDE;
+        if (i >= n) continue;
+        g2 a; g2a o; fp2_zero(o.x); fp2_zero(o.y);
+        const bool good = !skip[k] && sw_map_g2_post(a, t[k], u[k], ct[k], z[k]);
+        if (good) { o.x = a.x; o.y = a.y; }
+        pts[i] = o; ok[i] = good ? 1 : 0;
+    }
+  }
+}
+__global__ void k_hash_cofactor(size_t n, g2a* pts, const uint8_t* ok) {
+  for (size_t i0 = HB_TID; i0 < n; i0 += (size_t)HB_BATCH_K * HB_STRIDE) {
+    g2 h[HB_BATCH_K]; fp2 z[HB_BATCH_K]; bool skip[HB_BATCH_K];
+    for (int k = 0; k < HB_BATCH_K; k++) {
+        const size_t i = i0 + (size_t)k * HB_STRIDE;
+        skip[k] = true;
+        if (i >= n || !ok[i]) continue;
+        g2 a; const g2a p = pts[i]; a.x = p.x; a.y = p.y; fp2_one(a.z);
+        g2_clear_cofactor(h[k], a);
+        skip[k] = pt_is_inf(h[k]);
+        if (!skip[k]) z[k] = h[k].z;
+    }
+    f_batch_inv<fp2, HB_BATCH_K>(z, skip);
+    for (int k = 0; k < HB_BATCH_K; k++) {
+        const size_t i = i0 + (size_t)k * HB_STRIDE;
+        if (i >= n) continue;
+        g2a a;
+        if (skip[k]) { fp2_zero(a.x); fp2_zero(a.y); } else pt_to_aff_zinv(a, h[k], z[k]);
+        pts[i] = a;
+    }
+  }
+}
+
 // ---- lane-pair forms of decode / hash for small batches (latency path, hbls.cu: B <= coop_max): one item per LANE PAIR.  The Fp-only
 // chains (square roots, Jacobi symbols, the SW map) run redundantly on both lanes; the long G2 ladders -- subgroup test, cofactor
 // clearing -- run on the split carrier (an Fp2 product costs one product-time per lane instead of three), inversions by binary GCD.
