@@ -25,6 +25,7 @@
 #include <unordered_map>
 #include <vector>
 #include "../../include/hbls.h"
+#include "hbls_keyfile.hpp"
 
 namespace harmony {
 namespace bls_core {   // == github.com/harmony-one/bls/ffi/go/bls
@@ -423,4 +424,20 @@ inline std::vector<std::string> VerifyHeaderSignatures(const bls::Committee& ec,
     return errs;
 }
 }  // namespace chain
+namespace blsgen {     // == internal/blsgen/lib.go (key files; codec in hbls_keyfile.hpp)
+// LoadBLSKeyWithPassPhrase (lib.go:51-71) on the file's content: nullptr + err on a wrong passphrase / damaged file / bad key
+inline std::shared_ptr<bls_core::SecretKey> LoadBLSKeyWithPassPhrase(const std::string& fileName, const std::string& fileContent, const std::string& passphrase, std::string* err = nullptr) {
+    std::string skHex;
+    if (!LoadBLSKeyHexWithPassPhrase(fileContent, passphrase, skHex, err)) return nullptr;
+    auto sk = std::make_shared<bls_core::SecretKey>();
+    if (!sk->DeserializeHexStr(skHex)) { if (err) *err = "could not deserialize byte content of " + fileName + " as BLS secret key"; return nullptr; }
+    return sk;
+}
+// GenBLSKeyWithPassPhrase's file (lib.go:20-34): name = hex(pk) + ".key", content = encrypt(hex(sk), passphrase)
+inline std::pair<std::string, std::string> KeyFileFor(const bls_core::SecretKey& sk, const std::string& passphrase, const uint8_t nonce[12]) {
+    std::unique_ptr<bls_core::PublicKey> pk(sk.GetPublicKey());
+    return {pk->SerializeToHexStr() + ".key", encrypt(sk.SerializeToHexStr(), passphrase, nonce)};
+}
+}  // namespace blsgen
+
 }  // namespace harmony

@@ -50,6 +50,27 @@ int main() {
         CHECK(std::string(chain::headerStatusError(HBLS_HDR_NO_QUORUM)) == "not enough signature collected" && std::string(chain::headerStatusError(HBLS_HDR_OK)).empty());
         CHECK(batches[1].msgs.size() == 40 && batches[1].msgs[0] == 0x33);
     }
+    // key files (internal/blsgen/lib.go): the reference's own vectors, internal/blsgen/utils_test.go:30-43
+    {
+        CHECK(blsgen::hex_of(blsgen::md5((const uint8_t*)"", 0).data(), 16) == "d41d8cd98f00b204e9800998ecf8427e");
+        CHECK(blsgen::hex_of(blsgen::md5((const uint8_t*)"harmony", 7).data(), 16).size() == 32);
+        const uint8_t k0[32] = {0}, z[16] = {0}; uint8_t ct[16]; blsgen::Aes256(k0).encrypt(z, ct);
+        CHECK(blsgen::hex_of(ct, 16) == "dc95c078a2408989ad48a21492842087");            // FIPS 197 / SP 800-38A all-zero AES-256 block
+        struct { const char *sk, *pass, *blob; } v[2] = {
+            {"78c88c331195591b396e3205830071901a7a79e14fd0ede7f06bfb4c5e9f3473", "",
+             "1d97f32175d8875f251e15805fd08f0cda794d827cb02d2de7b10d10f36f951d68347bef1e7a3018bd865c6966219cd9c4d20b055c50f8e09a6a3a1666b7c112450f643cc3c175f541fae75da8a843d47993fe89ec85788fd6ea2e98"},
+            {"c20fa8de733d08e27e3101436d41f6a3207b8bedad7525c6e91a77ae2a49cf56", "harmony",
+             "194a2d68c37f037f36b28a560402d64ab007f949313b63d9a08f5adb55a061681c70d9119df2d2cdcae5da6e484550c03bad63aae7c1332a3647ce633999ac4ddbb4a40e213c7e88e604784fef40da9d2f28b392c9fb2462f5e51e9c"}};
+        for (auto& t : v) {
+            std::string sk, err;
+            CHECK(blsgen::LoadBLSKeyHexWithPassPhrase(t.blob, std::string(" ") + t.pass + "\n", sk, &err) && sk == t.sk);     // passphrase is trimmed
+            CHECK(!blsgen::LoadBLSKeyHexWithPassPhrase(t.blob, std::string(t.pass) + "x", sk, &err) && err == "cipher: message authentication failed");
+            std::vector<uint8_t> raw; blsgen::unhex_to(t.blob, raw);
+            CHECK(blsgen::encrypt(t.sk, t.pass, raw.data()) == t.blob);                                                       // same nonce -> same bytes
+            CHECK(blsgen::LoadBLSKeyHexWithPassPhrase(std::string(raw.begin(), raw.end()), t.pass, sk, &err) && sk == t.sk);   // binary form fall-back
+        }
+        std::string sk, err; CHECK(!blsgen::LoadBLSKeyHexWithPassPhrase("", "", sk, &err) && !blsgen::LoadBLSKeyHexWithPassPhrase("zz", "", sk, &err));
+    }
     // no CPU fallback: without blsInit (no device here) group operations fail instead of computing on the host
     bls_core::PublicKey q{}; std::vector<uint8_t> k48(48, 0); k48[0] = 1;
     CHECK(!q.Deserialize(k48));

@@ -61,6 +61,7 @@ def keccak256(data: bytes) -> bytes:
 def main():
     assert keccak256(b"").hex() == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470"
     sk_pk = []
+    keyfiles = []          # encrypted blobs themselves: pins of the key-file codec (internal/blsgen/lib.go:20-159)
     seen = set()
     def add(sk, pk, src):
         if (sk, pk) in seen: return
@@ -73,6 +74,7 @@ def main():
         pk, sk, pw, blob = m.groups()
         add(sk, pk, "internal/blsgen/utils_test.go:30-43")
         assert decrypt_keyfile(blob, pw) == sk
+        keyfiles.append({"pk": pk, "pass": pw, "blob": blob, "src": "internal/blsgen/utils_test.go:30-43"})
     nfiles = 0
     for path in sorted(glob.glob(f"{REF}/.hmy/**/*.key", recursive=True)):
         nfiles += 1
@@ -84,6 +86,7 @@ def main():
         sk = decrypt_keyfile(open(path).read(), pw)
         if sk is None or not re.fullmatch(r"[0-9a-f]{64}", sk): continue
         add(sk, pk, os.path.relpath(path, REF))
+        if len(keyfiles) < 10: keyfiles.append({"pk": pk, "pass": pw, "blob": open(path).read().strip(), "src": os.path.relpath(path, REF)})
     # valid pubkeys (decode-only pins): genesis account tables
     pks = set()
     for path in sorted(glob.glob(f"{REF}/internal/genesis/*.go")):
@@ -94,6 +97,7 @@ def main():
     out = {
         "generated_by": "tests/golden/make_golden.py",
         "sk_pk": sk_pk,
+        "keyfiles": keyfiles,
         "sig_vectors": [{
             "sk": "c6d7603520311f7a4e6aac0b26701fc433b75b38df504cd416ef2b900cd66205",
             "pk": "30b2c38b1316da91e068ac3bd8751c0901ef6c02a1d58bc712104918302c6ed03d5894671d0c816dad2b4d303320f202",
