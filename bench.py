@@ -471,6 +471,16 @@ def run_gpu(args):
             t0 = time.perf_counter(); fn(); wl_.append((time.perf_counter() - t0) * 1e3)
         warm[name + "_hm_cached_ms"] = float(np.median(wl_))
     assert int(h_res[:1].sum().item()) == 1
+    # SignHash of one key on one message (consensus/construct.go:101,110: the validator's prepare / commit vote): H(m) + the 255-bit ladder
+    sk1 = bls.SecretKey(); sk1.Deserialize(wl.sk_bytes(sks[0]))
+    def sign_ms(msg_of):
+        ts = []
+        for r in range(5):
+            m_ = msg_of(r); t0 = time.perf_counter(); sg = sk1.SignHash(m_); ts.append((time.perf_counter() - t0) * 1e3)
+            assert sg is not None
+        return float(np.median(ts))
+    warm["sign_hash_ms"] = sign_ms(lambda r: wl.commit_payload("bench/sign", r))                 # fresh message every call
+    warm["sign_hash_hm_cached_ms"] = sign_ms(lambda r: bytes(msgs[:MSG_LEN]))
     warm["hash_cache"] = bls.HashCacheStats()
 
     others = None

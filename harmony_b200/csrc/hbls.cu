@@ -369,6 +369,19 @@ int single_op(int op, const void* a, size_t an, const void* b, size_t bn, void* 
     return 0;
 }
 
+// sk (little-endian u64 x 4, < r < Z^4) -> its four base-Z digits, Z = |z| = 0xd201000000010000 (plain long division on the host)
+bool sk_digits_base_z(const uint64_t sk[4], uint64_t dig[4]) {
+    const uint64_t Z = 0xd201000000010000ull;
+    uint64_t v[4] = {sk[0], sk[1], sk[2], sk[3]};
+    for (int k = 0; k < 3; k++) {
+        unsigned __int128 rem = 0;
+        for (int i = 3; i >= 0; i--) { const unsigned __int128 cur = (rem << 64) | v[i]; v[i] = (uint64_t)(cur / Z); rem = cur % Z; }
+        dig[k] = (uint64_t)rem;
+    }
+    dig[3] = v[0];
+    return (v[1] | v[2] | v[3]) == 0;                 // always for sk < r < Z^4; a hand-filled struct >= Z^4 takes the plain ladder
+}
+
 // r (BLS12-381 group order), little-endian u64
 const uint64_t R_ORDER[4] = {0xffffffff00000001ull, 0x53bda402fffe5bfeull, 0x3339d80809a1d805ull, 0x73eda753299d7d48ull};
 bool scalar_lt_r(const uint64_t k[4]) {
@@ -716,7 +729,14 @@ int blsSignHash(blsSignature* sig, const blsSecretKey* sec, const void* h, size_
         launch_hash_small(g.stream, 1, dmsg, (uint32_t)size, dhm, dhm_ok);
         if (hm_enabled()) hm_store(key, dhm, dhm_ok, g.stream);
     }
-    LAUNCH(k_sign_hm_pair, 1, 32, g.stream, (size_t)1, dsk, dhm, dhm_ok, (size_t)0, dout, dok);
+    // sk in base |z| (four 64-bit digits): the ladder runs over psi (kernels.cuh k_sign_hm_gls_pair)
+    uint64_t dig[4];
+    if (sk_digits_base_z(sec->d, dig)) {
+        uint64_t* ddig = ar.take<uint64_t>(4);
+        CK(cudaMemcpyAsync(ddig, dig, sizeof dig, cudaMemcpyHostToDevice, g.stream));
+        LAUNCH(k_sign_hm_gls_pair, 1, 32, g.stream, (size_t)1, ddig, dhm, dhm_ok, (size_t)0, dout, dok);
+    } else
+        LAUNCH(k_sign_hm_pair, 1, 32, g.stream, (size_t)1, dsk, dhm, dhm_ok, (size_t)0, dout, dok);
     uint8_t ok = 0;
     CK(cudaMemcpyAsync(sig, dout, 288, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaMemcpyAsync(&ok, dok, 1, cudaMemcpyDeviceToHost, g.stream));

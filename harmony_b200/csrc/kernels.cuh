@@ -921,6 +921,31 @@ __global__ void k_sign_hm_pair(size_t n, const uint8_t* sk32, const g2a* hm, con
     if (!good) pt_set_inf(r);
     if ((threadIdx.x & 1) == 0) { out[i] = r; ok[i] = good ? 1 : 0; }
 }
+// The same signature through the psi endomorphism (latency path of blsSignHash): the host writes sk = d0 + d1 Z + d2 Z^2 + d3 Z^3 in
+// base Z = |z| (four 64-bit digits: sk < r < Z^4); on G2 psi acts as [z] = [-Z], so  sk H = d0 H - d1 psi(H) + d2 psi^2(H) - d3 psi^3(H)
+// is ONE 64-step ladder over a 15-entry table of subset sums (64 doublings + <= 64 additions instead of 255 + 64 + 14).
+__global__ void k_sign_hm_gls_pair(size_t n, const uint64_t* digits, const g2a* hm, const uint8_t* ok_hm, size_t hm_stride, g2* out, uint8_t* ok) {
+    const size_t i = HB_TID >> 1; if (i >= n) return;
+    const uint64_t d0 = digits[4 * i], d1 = digits[4 * i + 1], d2 = digits[4 * i + 2], d3 = digits[4 * i + 3];
+    const g2a h = hm[i * hm_stride];
+    const bool good = ok_hm[i * hm_stride] != 0 && !aff_is_inf(h);
+    jac<fp2h> T[16], R;
+    pt_set_inf(T[0]);
+    fp2h_pack(T[1].x, h.x); fp2h_pack(T[1].y, h.y); fp2_one(T[1].z);          // H
+    g2_psi(T[2], T[1]); pt_neg(T[2], T[2]);                                    // -psi(H)
+    g2_psi2(T[4], T[1]);                                                       // psi^2(H)
+    g2_psi(T[8], T[4]); pt_neg(T[8], T[8]);                                    // -psi^3(H)
+    for (int m = 3; m < 16; m++) if (m & (m - 1)) pt_add(T[m], T[m & (m - 1)], T[m & -m]);
+    pt_set_inf(R);
+    for (int b = 63; b >= 0; b--) {
+        pt_dbl(R, R);
+        const int m = (int)((d0 >> b) & 1) | (int)((d1 >> b) & 1) << 1 | (int)((d2 >> b) & 1) << 2 | (int)((d3 >> b) & 1) << 3;
+        if (m) pt_add(R, R, T[m]);
+    }
+    g2 r; fp2h_unpack(r.x, R.x); fp2h_unpack(r.y, R.y); fp2h_unpack(r.z, R.z);
+    if (!good) pt_set_inf(r);
+    if ((threadIdx.x & 1) == 0) { out[i] = r; ok[i] = good ? 1 : 0; }
+}
 
 // ---- single-element ops behind the herumi-shaped C ABI (one thread; latency is launch-bound)
 enum { OP_G1_ADD = 1, OP_G1_SUB, OP_G2_ADD, OP_G1_EQ, OP_G2_EQ, OP_G1_SER, OP_G2_SER, OP_G1_DES, OP_G2_DES, OP_MAP_SER, OP_G2_DES_ADD };

@@ -220,6 +220,28 @@ extern "C" int emu_vm_hash(const uint8_t* msg, uint32_t len) {
     return (okw && std::memcmp(&got, &want, sizeof(g2a)) == 0) ? 1 : 0;
 }
 
+// blsSignHash's ladder over psi (k_sign_hm_gls_pair, base-|z| digits of the key) on two host threads against the plain 255-bit ladder of
+// k_sign_hash: 1 = the same group element, 0 = different, -1 = the message maps to no point
+extern "C" int emu_sign_gls(const uint8_t* sk32, const uint8_t* msg, uint32_t len) {
+    g2 want; uint8_t okw = 0;
+    run_seq(1, 1, [&] { k_sign_hash(1, sk32, msg, len, &want, &okw); });
+    if (!okw) return -1;
+    g2a hm; uint8_t okh = 0;
+    run_seq(1, 1, [&] { k_hash_to_g2(1, msg, len, &hm, &okh); });
+    uint64_t v[4], dig[4]; std::memcpy(v, sk32, 32);
+    const uint64_t Z = 0xd201000000010000ull;
+    for (int k = 0; k < 3; k++) {
+        unsigned __int128 rem = 0;
+        for (int i = 3; i >= 0; i--) { const unsigned __int128 cur = (rem << 64) | v[i]; v[i] = (uint64_t)(cur / Z); rem = cur % Z; }
+        dig[k] = (uint64_t)rem;
+    }
+    dig[3] = v[0];
+    if (v[1] | v[2] | v[3]) return -2;
+    g2 got; uint8_t okg = 0;
+    run_pair([&] { k_sign_hm_gls_pair(1, dig, &hm, &okh, 0, &got, &okg); });
+    return (okg && pt_eq(got, want)) ? 1 : 0;
+}
+
 // lane-pair decode / hash kernels (latency path) on two host threads against the thread-per-item kernels: bit 0 = decoded
 // signature identical (point and ok flag), bit 1 = H(m) identical; n items one after the other (pair 0 of a 2-thread CTA)
 extern "C" int emu_pair_decode_hash(size_t n, const uint8_t* sigs96, const uint8_t* msgs, uint32_t len) {

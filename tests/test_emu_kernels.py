@@ -138,6 +138,14 @@ def test_vm_hash_cofactor_device_decoders(emuk):
     assert emuk.emu_vm_hash(wl.seeded_bytes("vmh/32", 7, 32), 32) == 1
     assert emuk.emu_vm_hash(bytes(48), 48) == -1                      # t = 0: the map is undefined (SignHash returns nil)
 
+def test_sign_ladder_over_psi(emuk):
+    """blsSignHash's 4-dimensional ladder (sk in base |z|, psi = [z] on G2) == the plain 255-bit ladder, for ordinary keys and the
+    edge digits: sk = 1, |z|, |z|^3, r - 1."""
+    R = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001; Z = 0xd201000000010000
+    keys = [wl.seeded_sk("gls", i) for i in range(3)] + [1, Z, Z ** 3, Z ** 3 + Z - 1, R - 1]
+    for k in keys:
+        assert emuk.emu_sign_gls(wl.sk_bytes(k), wl.commit_payload("gls", k & 7), 48) == 1, hex(k)
+
 def test_lane_pair_decode_and_hash_kernels(emuk, oracle):
     """k_g2_decode_pair / k_hash_to_g2_pair (item per lane pair, latency path) == the thread-per-item kernels: valid signatures,
     a point outside the subgroup / undecodable bytes / the identity, messages incl. one that maps to no point."""
