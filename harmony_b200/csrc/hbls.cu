@@ -39,7 +39,7 @@ struct Ctx {
     bool stage_timing = false; Scratch* stage_sc = nullptr;
     int batch_mode = 1;                                     // 1: random-linear-combination groups + exact pass over failed groups, 0: exact per round
     // tuning (hbls_set_param)
-    long long rlc_min = 6144, rlc_g = 0, tpsm = 384, tpsm_split = 512, tpsm_light = 1024, coop_max = 6143, overlap = 1, coop_wpsm = 14, hash_coop_max = 592, mask_sort = 1, hash_split = 1, tpsm_sw = 512;
+    long long rlc_min = 6144, rlc_g = 0, tpsm = 384, tpsm_split = 512, tpsm_light = 1024, coop_max = 6143, overlap = 1, coop_wpsm = 14, hash_coop_max = 592, mask_sort = 1, hash_split = 1, tpsm_sw = 512, hash_fallback = 0;
     // coefficient stream: ChaCha20 keyed from /dev/urandom, block counter = call number
     uint32_t chacha_key[8] = {}; uint64_t rlc_calls = 0;
     // last batch
@@ -154,7 +154,7 @@ unsigned split_blocks(size_t nthreads) { return capped_blocks(nthreads, g.tpsm_s
 // hash-to-G2 of a small batch (latency path): one WARP per message while that still leaves every warp its own scheduler's worth of
 // an SM (the cofactor clearing runs as VM step programs: 2.7 instead of 3.7 ms for one message), else one message per lane pair
 void launch_hash_small(cudaStream_t st, size_t n, const uint8_t* d_msgs, uint32_t msg_len, g2a* hm, uint8_t* ok_hm) {
-    if ((long long)n <= g.hash_coop_max) LAUNCH(k_hash_to_g2_coop, (unsigned)n, 32, st, n, d_msgs, msg_len, hm, ok_hm);
+    if ((long long)n <= g.hash_coop_max) LAUNCH(k_hash_to_g2_coop, (unsigned)n, 32, st, n, d_msgs, msg_len, hm, ok_hm, (int)g.hash_fallback);
     else LAUNCH(k_hash_to_g2_pair, blocks_for(2 * n, 32), 32, st, n, d_msgs, msg_len, hm, ok_hm);
 }
 
@@ -601,6 +601,7 @@ static long long* param_slot(const char* name) {
     if (!strcmp(name, "hash_coop_max")) return &g.hash_coop_max;
     if (!strcmp(name, "mask_sort")) return &g.mask_sort;
     if (!strcmp(name, "hash_split")) return &g.hash_split;
+    if (!strcmp(name, "hash_fallback")) return &g.hash_fallback;
     if (!strcmp(name, "tpsm_sw")) return &g.tpsm_sw;
     return nullptr;
 }

@@ -343,7 +343,7 @@ __global__ void k_hash_to_g2_pair(size_t n, const uint8_t* msgs, uint32_t msg_le
 // Legendre symbols, the Fp2 square root) runs on every lane alike; the cofactor clearing -- two 63-doubling chains of G2, 52 % of a
 // lane pair's hash time (profiles/r2_lat_probe.txt) -- runs as VM step programs with the 3 independent products of a doubling level
 // side by side.  Falls back to the complete lane-pair code when the generic formulas degenerate.
-__global__ void __launch_bounds__(32) k_hash_to_g2_coop(size_t n, const uint8_t* msgs, uint32_t msg_len, g2a* out, uint8_t* ok) {
+__global__ void __launch_bounds__(32) k_hash_to_g2_coop(size_t n, const uint8_t* msgs, uint32_t msg_len, g2a* out, uint8_t* ok, int force_fallback) {
     __shared__ uint32_t slots[VM_SMEM_WORDS];
     const int lane = threadIdx.x & 31;
     vm_load_consts(slots);
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(32) k_hash_to_g2_coop(size_t n, const uint8_t*
         if (good) {
             if (lane == 0) { vm_set_fp2(slots, VM_R_Q2X, a.x); vm_set_fp2(slots, VM_R_Q2Y, a.y); }
             __syncwarp();
-            if (vm_hash_cofactor(slots)) {
+            if (vm_hash_cofactor(slots) && !force_fallback) {             // force_fallback: test hook (hbls_set_param "hash_fallback")
                 if (lane == 0) { vm_ld(res.x.a.l, slots, VM_R_HX, 0); vm_ld(res.x.b.l, slots, VM_R_HX, 1); vm_ld(res.y.a.l, slots, VM_R_HY, 0); vm_ld(res.y.b.l, slots, VM_R_HY, 1); }
             } else if (lane < 2) {
                 jac<fp2h> A, H; fp2h_pack(A.x, a.x); fp2h_pack(A.y, a.y); fp2h_pack(A.z, a.z);

@@ -768,3 +768,32 @@ def test_hash_cache_sign_then_verify(gbls, oracle):
         assert com.AggregateVerifyBatch(sb, bytes(bad), m1 * n, 48) == r1 and sum(r1) == n - 1 and r1[5] == 0
     finally:
         gbls.SetParam("hm_cache", old)
+
+def test_hash_paths_agree(gbls, oracle):
+    """hash-to-G2 has four device forms: thread per item (large batches; one kernel or map + cofactor kernels), lane pair per item,
+    warp per message with the cofactor clearing on the VM, and that kernel's fall-back for degenerate group-law cases (forced here).
+    All give the oracle's bytes through SignHash, and the same verdicts through a 40-round batch."""
+    n = 8
+    sks = [wl.seeded_sk("hp", i) for i in range(n)]
+    pks_blob = gbls.GetPublicKeyBatch(b"".join(wl.sk_bytes(k) for k in sks))
+    com = gbls.Committee([pks_blob[48 * i:48 * i + 48] for i in range(n)])
+    B = 40
+    bms = [wl.bitmap_with_k("hp", j, n, 6 + (j % 3)) for j in range(B)]
+    msgs = [wl.commit_payload("hp", j) for j in range(B)]
+    agg = [wl.sk_bytes(wl.round_signer_sum(sks, bm)) for bm in bms]
+    sigs, ok = gbls.SignHashBatch(b"".join(agg), b"".join(msgs), 48)
+    assert ok == b"\x01" * B and sigs[:96] == oracle.sign_hash(agg[0], msgs[0])
+    bad = bytearray(b"".join(msgs)); bad[48 * 7] ^= 1
+    names = ("hm_cache", "hash_coop_max", "hash_fallback", "hash_split")
+    old = {k: gbls.GetParam(k) for k in names}
+    res = {}
+    try:
+        gbls.SetParam("hm_cache", 0)
+        for tag, coop_max, fb in (("warp+vm", 592, 0), ("warp+fallback", 592, 1), ("lane pair", 0, 0)):
+            gbls.SetParam("hash_coop_max", coop_max); gbls.SetParam("hash_fallback", fb)
+            sk = gbls.SecretKey(); sk.Deserialize(agg[3])
+            assert sk.SignHash(msgs[3]).Serialize() == sigs[96 * 3:96 * 4] == oracle.sign_hash(agg[3], msgs[3]), tag
+            res[tag] = com.AggregateVerifyBatch(b"".join(bms), sigs, bytes(bad), 48)
+        assert res["warp+vm"] == res["warp+fallback"] == res["lane pair"] and res["lane pair"][7] == 0 and sum(res["lane pair"]) == B - 1
+    finally:
+        for k, v in old.items(): gbls.SetParam(k, v)
