@@ -126,6 +126,7 @@ EXEC_FP_OPS = {
     True: {"mask": (368.5, 137.8), "decode": (1478.0, 756.0), "hash": (3004.2, 855.5),
             4: {"scale": (4571.5, 1257.0), "pairing": (34661, 764)}, 8: {"scale": (10544.0, 2372.0), "pairing": (54329, 764)}},      # shared inversions (HB_BATCH_INV, 8 items per inversion)
 }
+EXEC_FP_OPS_LINES = {4: (11105, 0), 8: (19989, 0)}     # the line kernel's share of "pairing" in the two-kernel form (k_rlc_lines_split; tests/test_emu_logic.py)
 EXACT_PAIRING_FP_OPS = (20055, 497)      # exact mode: 2-pair Miller loop + final exponentiation per round (oracle counter, stages 4 + 5)
 def rlc_group_size(B, sm_count, tpb_split=512):
     """Mirror of the host's choice in hbls.cu launch_verify_tail: 8 when B/8 lane pairs still fill every SM, else 4."""
@@ -369,12 +370,14 @@ def run_gpu(args):
     assert int(d_res.sum().item()) == B
     # per-kernel durations: separate passes with event records between the kernels (kept out of the timed region)
     bls.StageTimingEnable(True)
-    n_stage = 3
+    n_stage = 3; lines_ms = 0.0
     with torch.cuda.stream(stream):
         for i in range(n_stage):
             flush.zero_(); step_device()
             st = bls.StageTimingGet(); stage_ms += np.array(st if len(st) == 6 else [0] * 6)
+            lines_ms += bls.StageTimingLinesMs()
     bls.StageTimingEnable(False)
+    lines_ms /= n_stage
     barrier()
     stage_ms /= n_stage
 
@@ -517,15 +520,27 @@ def run_gpu(args):
         names[4], names[5] = "(unused)", "k_pairing_verify_split"
         macs = [mac32(t["mask"]), mac32((99, 381)), mac32(t["decode"]), mac32(t["hash"]), 0.0, mac32(EXACT_PAIRING_FP_OPS)]
     dom = int(np.argmax(stage_ms))
-    achieved = macs[dom] * B / (stage_ms[dom] * 1e-3)
+    dom_name, dom_macs, dom_ms = names[dom], macs[dom], stage_ms[dom]
+    two_kernels = None
+    if rlc and dom == 5 and lines_ms > 0:
+        # the batched pairing stage ran as two kernels (running points + lines | accumulator + final exponentiation): the roofline is
+        # that of the larger one, with its own executed work and its own CUDA-event time
+        lm = mac32(EXEC_FP_OPS_LINES[G]) / G; am = macs[5] - lm; a_ms = stage_ms[5] - lines_ms
+        two_kernels = {f"k_rlc_lines_split<{G}>": {"ms": lines_ms, "mac32_per_round": lm, "frac_of_peak": None},
+                       f"k_rlc_accum_split<{G}>": {"ms": a_ms, "mac32_per_round": am, "frac_of_peak": None}}
+        names[5] = f"k_rlc_lines_split<{G}>+k_rlc_accum_split<{G}>"
+        dom_name, dom_macs, dom_ms = (f"k_rlc_accum_split<{G}>", am, a_ms) if a_ms >= lines_ms else (f"k_rlc_lines_split<{G}>", lm, lines_ms)
+    achieved = dom_macs * B / (dom_ms * 1e-3)
     total_macs = sum(macs)
     step_s = dev_ms / args.steps * 1e-3
     bytes_per_round = blen + 96 + MSG_LEN + 1
-    traffic = ncu_dram_bytes(names[dom].split("<")[0])
+    traffic = ncu_dram_bytes(dom_name.split("<")[0])
     orc = oracle_lib()
     S = min(B, 64)
     exact_macs = stage_mac32_per_round(orc, pks, bitmaps, sigs, msgs, blen, sample=min(12, S))     # the reference algorithm, oracle counter
-    roofline = {"bound": "int32-imad", "kernel": names[dom], "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TMAC32/s",
+    if two_kernels:
+        for kk in two_kernels.values(): kk["frac_of_peak"] = kk["mac32_per_round"] * B / (kk["ms"] * 1e-3) / peak
+    roofline = {"bound": "int32-imad", "kernel": dom_name, "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TMAC32/s",
                 "frac": achieved / peak,
                 "peak_source": f"FMA-heavy pipe: {sm_count} SMs x 4 schedulers x 8 IMAD.WIDE MAC/clk x {sm_clock_hz / 1e9:.3f} GHz (median SM clock nvidia-smi reported during the timed region); "
                                "4 pipe-cycles per IMAD.WIDE warp instruction measured with ncu (profiles/r2_probe_int_ncu.txt)",
@@ -538,7 +553,7 @@ def run_gpu(args):
                               if rlc else "exact per-round FastAggregateVerify"),
                 "work_counted": "EXECUTED Fp multiplications/squarings of the device code, all six stages (x300 / x234 MAC32 each; adds, shifts, selects not counted), "
                                 "from the same kernels run on the host: tests/emu emu_stage_counts / emu_rlc_stage_counts",
-                "kernel_mac32_per_round": macs[dom], "executed_mac32_per_round": total_macs,
+                "kernel_mac32_per_round": dom_macs, "kernel_ms": dom_ms, "pairing_stage_kernels": two_kernels, "executed_mac32_per_round": total_macs,
                 "pipeline_frac": total_macs * B / step_s / peak,
                 "reference_algorithm_mac32_per_round": sum(exact_macs),
                 "algorithmic_saving_vs_reference": 1.0 - total_macs / sum(exact_macs),

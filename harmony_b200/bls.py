@@ -530,6 +530,12 @@ class BallotBox:
 STAGE_NAMES = ["k_mask_aggregate", "k_g1_normalize", "k_g2_decode", "k_hash_to_g2", "k_rlc_scale+k_rlc_group_sum", "pairing"]
 def StageTimingEnable(on: bool): lib().hbls_stage_timing_enable(1 if on else 0)
 def StageTimingGet():
+    """six stage times (ms) of the last aggregate-verify pipeline issued with stage timing on"""
+    buf = (ctypes.c_float * 8)()
+    n = lib().hbls_stage_timing_get(buf, 6)
+    return [float(buf[i]) for i in range(n)]
+def StageTimingLinesMs():
+    """the line kernel's share of stage 5 (ms) when the batched pairing ran as two kernels, else 0"""
     buf = (ctypes.c_float * 8)()
     n = lib().hbls_stage_timing_get(buf, 8)
-    return [float(buf[i]) for i in range(n)]
+    return float(buf[6]) if n >= 7 else 0.0

@@ -21,7 +21,7 @@ namespace {
 // Calls on one stream are stream-ordered, so re-using its arena from offset 0 is safe; different streams never share one.
 struct Scratch {
     uint8_t* base = nullptr; size_t cap = 0;
-    cudaEvent_t ev[8] = {}; bool ev_ok = false;
+    cudaEvent_t ev[8] = {}; bool ev_ok = false, ev7_set = false;
     unsigned* h_counts = nullptr;            // pinned: [0] rounds re-verified exactly, [1] groups failed
     cudaEvent_t done = nullptr;
     cudaEvent_t fork = nullptr, join[2] = {}; bool forked = false;      // small batches: decode / hash on two auxiliary streams
@@ -39,7 +39,7 @@ struct Ctx {
     bool stage_timing = false; Scratch* stage_sc = nullptr;
     int batch_mode = 1;                                     // 1: random-linear-combination groups + exact pass over failed groups, 0: exact per round
     // tuning (hbls_set_param)
-    long long rlc_min = 6144, rlc_g = 0, tpsm = 384, tpsm_split = 512, tpsm_light = 1024, coop_max = 6143, overlap = 1, coop_wpsm = 14, hash_coop_max = 592, mask_sort = 1, hash_split = 1, tpsm_sw = 512, hash_fallback = 0;
+    long long rlc_min = 6144, rlc_g = 0, tpsm = 384, tpsm_split = 512, tpsm_light = 1024, coop_max = 6143, overlap = 1, coop_wpsm = 14, hash_coop_max = 592, mask_sort = 1, hash_split = 1, tpsm_sw = 512, hash_fallback = 0, rlc_two_phase = 1, tpsm_lines = 512, tpsm_accum = 512;
     // coefficient stream: ChaCha20 keyed from /dev/urandom, block counter = call number
     uint32_t chacha_key[8] = {}; uint64_t rlc_calls = 0;
     // last batch
@@ -97,7 +97,7 @@ int reserve(cudaStream_t s, size_t bytes, Scratch** out) {
         CK(cudaEventCreateWithFlags(&sc.join[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&sc.join[1], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&sc.mid, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&sc.join2, cudaEventDisableTiming));
     }
-    sc.forked = false;
+    sc.forked = false; sc.ev7_set = false;
     *out = &sc;
     return 0;
 }
@@ -191,14 +191,27 @@ std::vector<uint64_t> rlc_draw_items(size_t k) {
 }
 
 // ------------------------------------------------------------------ one verification pass over device-resident inputs.
+// batched form: groups of 8 once that still gives every SM a full CTA of lane pairs (fewer Miller-loop pairs and final exponentiations
+// per round), else 4
+size_t rlc_group_size(size_t B) {
+    return (g.rlc_g == 4 || g.rlc_g == 8) ? (size_t)g.rlc_g : (2 * (B / 8) >= (size_t)g.sm_count * HB_TPB_SPLIT ? 8 : 4);
+}
+constexpr size_t RLC_CHUNK_GROUPS = 37888;             // two-phase form: groups per pass (148 SMs x 256 lane pairs)
+static bool rlc_applies(size_t B);
+size_t rlc_lines_bytes(size_t B) {
+    if (!g.rlc_two_phase || !rlc_applies(B)) return 0;
+    const size_t G = rlc_group_size(B), ng = B / G, ngc = ng < RLC_CHUNK_GROUPS ? ng : RLC_CHUNK_GROUPS;
+    return (size_t)HB_ML_STEPS * 3 * (G + 1) * ngc * 2 * sizeof(fp) + 256;
+}
 size_t verify_scratch_bytes(size_t B) {
     return B * (sizeof(g2a) * 2 + sizeof(g1a) * 2 + sizeof(g1) + sizeof(g2) + 16 + 4 + 6) + HB_MASK_BINS * 4 + (B / HB_RLC_G + 1) * (sizeof(g2a) + 8) + 44 * 256
-           + (B <= 8192 ? B * (12 * sizeof(fp2) + 3) + 1024 : 0);               // latency path: Miller values of (B, sigma) and (-apk, H(m))
+           + (B <= 8192 ? B * (12 * sizeof(fp2) + 3) + 1024 : 0)                // latency path: Miller values of (B, sigma) and (-apk, H(m))
+           + (B >= 2 * HB_RLC_GMAX ? rlc_lines_bytes(B) : 0);                    // two-phase batched form: the line functions of one chunk
 }
 struct VerifyBufs { g2a* sig; g2a* hm; g1a* pkneg; g1* apk; uint8_t* ok_sig; uint8_t* ok_hm; uint8_t* ok_pk;
                     g1a* pk_scaled; g2* S; uint8_t* bad; g2a* Sg; uint8_t* group_ok; uint32_t* fail_list; unsigned* counts;
                     fp2* f1; uint8_t* irr1; fp2* f2; uint8_t* irr2; uint8_t* ok_sub;
-                    uint16_t* mask_cost; unsigned* mask_hist; uint32_t* mask_order; };
+                    uint16_t* mask_cost; unsigned* mask_hist; uint32_t* mask_order; fp* lines; };
 VerifyBufs carve_verify(Arena& ar, size_t B) {
     VerifyBufs v;
     v.sig = ar.take<g2a>(B); v.hm = ar.take<g2a>(B); v.pkneg = ar.take<g1a>(B); v.apk = ar.take<g1>(B);
@@ -207,6 +220,8 @@ VerifyBufs carve_verify(Arena& ar, size_t B) {
     v.Sg = ar.take<g2a>(B / HB_RLC_G + 1); v.group_ok = ar.take<uint8_t>(B / HB_RLC_G + 1);
     v.fail_list = ar.take<uint32_t>(B); v.counts = ar.take<unsigned>(2);
     v.mask_cost = ar.take<uint16_t>(B); v.mask_hist = ar.take<unsigned>(HB_MASK_BINS); v.mask_order = ar.take<uint32_t>(B);
+    v.lines = nullptr;
+    if (B >= 2 * HB_RLC_GMAX && rlc_lines_bytes(B)) v.lines = reinterpret_cast<fp*>(ar.take<uint8_t>(rlc_lines_bytes(B)));
     v.f1 = v.f2 = nullptr; v.irr1 = v.irr2 = v.ok_sub = nullptr;
     if (B <= 8192) { v.f1 = ar.take<fp2>(6 * B); v.irr1 = ar.take<uint8_t>(B); v.f2 = ar.take<fp2>(6 * B); v.irr2 = ar.take<uint8_t>(B); v.ok_sub = ar.take<uint8_t>(B); }
     return v;
@@ -292,21 +307,34 @@ void launch_verify_tail(size_t B, const VerifyBufs& v, Scratch* sc, const uint8_
     if (rlc) {
         // batched form (north-star "batched Miller loop + shared final exponentiation"): strided groups of G rounds; G = 8 once
         // that still gives every SM a full CTA of lane pairs (fewer Miller-loop pairs and final exponentiations per round), else 4
-        const size_t G = (g.rlc_g == 4 || g.rlc_g == 8) ? (size_t)g.rlc_g : (2 * (B / 8) >= (size_t)g.sm_count * HB_TPB_SPLIT ? 8 : 4);
+        const size_t G = rlc_group_size(B);
         const size_t ng = B / G, nr = ng * G, tail = B - nr;
         const rlc_coeffs co = rlc_draw();
         LAUNCH(k_rlc_scale, heavy_blocks(nr), TPB, s, nr, ng, v.apk, v.sig, v.hm, v.ok_sig, v.ok_hm, ok_pk, co, (const uint64_t*)nullptr, v.pk_scaled, v.S, v.bad);
         const bool full = 2 * ng >= (size_t)g.sm_count * HB_TPB_SPLIT;
         const unsigned pb = full ? split_blocks(2 * ng) : blocks_for(2 * ng, 64), pt = full ? HB_TPB_SPLIT : 64;
-        if (G == 8) {
-            LAUNCH(k_rlc_group_sum<8>, heavy_blocks(ng), TPB, s, ng, v.S, v.Sg);
-            STAGE_EV(5, sc, s);
+        const bool two_phase = g.rlc_two_phase && v.lines != nullptr && full;
+        if (G == 8) LAUNCH(k_rlc_group_sum<8>, heavy_blocks(ng), TPB, s, ng, v.S, v.Sg);
+        else LAUNCH(k_rlc_group_sum<4>, heavy_blocks(ng), TPB, s, ng, v.S, v.Sg);
+        STAGE_EV(5, sc, s);
+        if (two_phase) {
+            // running points in their own kernel (lines to HBM, read once), accumulator + final exponentiation in the second
+            for (size_t g0 = 0; g0 < ng; g0 += RLC_CHUNK_GROUPS) {
+                const size_t ngc = ng - g0 < RLC_CHUNK_GROUPS ? ng - g0 : RLC_CHUNK_GROUPS;
+                // one lock-stepped CTA per SM, its size = the resident threads wanted for that kernel (multiple of 64, <= 512)
+                auto cta = [](long long t) { t = t < 64 ? 64 : (t > HB_TPB_SPLIT ? HB_TPB_SPLIT : t); return (unsigned)(t & ~63ll); };
+                const unsigned lt = cta(g.tpsm_lines), at = cta(g.tpsm_accum);
+                const unsigned lb = capped_blocks(2 * (G + 1) * ngc, lt, lt), ab = capped_blocks(2 * ngc, at, at);
+                if (G == 8) LAUNCH(k_rlc_lines_split<8>, lb, lt, s, ng, g0, ngc, v.pk_scaled, v.hm, v.Sg, v.lines);
+                else LAUNCH(k_rlc_lines_split<4>, lb, lt, s, ng, g0, ngc, v.pk_scaled, v.hm, v.Sg, v.lines);
+                if (g0 == 0) { STAGE_EV(7, sc, s); sc->ev7_set = g.stage_timing && sc->ev_ok; }       // line kernel | accumulator kernel (first chunk)
+                if (G == 8) LAUNCH(k_rlc_accum_split<8>, ab, at, s, ng, g0, ngc, (const fp*)v.lines, v.bad, v.group_ok);
+                else LAUNCH(k_rlc_accum_split<4>, ab, at, s, ng, g0, ngc, (const fp*)v.lines, v.bad, v.group_ok);
+            }
+        } else if (G == 8)
             LAUNCH_SMEM(k_rlc_pairing_split<8>, pb, pt, HB_SMEM_F ? pt * HB_SMEM_F_WORDS * 4 : 0, s, ng, v.pk_scaled, v.hm, v.Sg, v.bad, v.group_ok);
-        } else {
-            LAUNCH(k_rlc_group_sum<4>, heavy_blocks(ng), TPB, s, ng, v.S, v.Sg);
-            STAGE_EV(5, sc, s);
+        else
             LAUNCH_SMEM(k_rlc_pairing_split<4>, pb, pt, HB_SMEM_F ? pt * HB_SMEM_F_WORDS * 4 : 0, s, ng, v.pk_scaled, v.hm, v.Sg, v.bad, v.group_ok);
-        }
         // exact pass over the rounds of failed groups only (compacted on the device; the launches are sized for the worst case and
         // return at once when the list is short or empty)
         LAUNCH(k_rlc_finish, blocks_for(nr, 256), 256, s, nr, ng, v.group_ok, d_results, v.fail_list, v.counts);
@@ -559,6 +587,10 @@ int hbls_init_device(int device) {
     cudaFuncSetAttribute(k_rlc_pairing_split<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_rlc_pairing_split<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
 #endif
+    cudaFuncSetAttribute(k_rlc_lines_split<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    cudaFuncSetAttribute(k_rlc_lines_split<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    cudaFuncSetAttribute(k_rlc_accum_split<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    cudaFuncSetAttribute(k_rlc_accum_split<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_pairing_verify_split, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_pairing_verify_split_list, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_hash_to_g2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
@@ -571,6 +603,7 @@ int hbls_init_device(int device) {
         CK(cudaEventCreateWithFlags(&g.hm[i].filled, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&g.hm[i].read_done, cudaEventDisableTiming));
     }
     g.hm_cache = envll("HBLS_HM_CACHE", 1); g.mask_sort = envll("HBLS_MASK_SORT", 1); g.hash_coop_max = envll("HBLS_HASH_COOP_MAX", 592);
+    g.rlc_two_phase = envll("HBLS_RLC_2P", 1); g.tpsm_lines = envll("HBLS_TPSM_LINES", 512); g.tpsm_accum = envll("HBLS_TPSM_ACCUM", 512);
     g.hash_split = envll("HBLS_HASH_SPLIT", 1); g.tpsm_sw = envll("HBLS_TPSM_SW", 512);
     cudaFuncSetAttribute(k_hash_sw, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_hash_cofactor, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
@@ -602,6 +635,9 @@ static long long* param_slot(const char* name) {
     if (!strcmp(name, "mask_sort")) return &g.mask_sort;
     if (!strcmp(name, "hash_split")) return &g.hash_split;
     if (!strcmp(name, "hash_fallback")) return &g.hash_fallback;
+    if (!strcmp(name, "rlc_two_phase")) return &g.rlc_two_phase;
+    if (!strcmp(name, "tpsm_lines")) return &g.tpsm_lines;
+    if (!strcmp(name, "tpsm_accum")) return &g.tpsm_accum;
     if (!strcmp(name, "tpsm_sw")) return &g.tpsm_sw;
     return nullptr;
 }
@@ -1227,6 +1263,8 @@ int hbls_stage_timing_get(float* ms_out, int max_stages) {
     if (cudaEventSynchronize(sc->ev[6]) != cudaSuccess) return 0;
     int n = max_stages < 6 ? max_stages : 6;
     for (int i = 0; i < n; i++) { float ms = 0; cudaEventElapsedTime(&ms, sc->ev[i], sc->ev[i + 1]); ms_out[i] = ms; }
+    // 7th value: the line kernel's part of stage 5 when the batched pairing ran as two kernels (first chunk), else 0
+    if (max_stages >= 7) { float ms = 0; if (sc->ev7_set) cudaEventElapsedTime(&ms, sc->ev[5], sc->ev[7]); ms_out[6] = ms; n = 7; }
     return n;
 }
 int hbls_selftest_split(uint32_t iters) {

@@ -798,6 +798,112 @@ template <int G> __global__ void __launch_bounds__(HB_TPB_SPLIT, HB_MINBLOCKS_SP
         if (valid && role == 0) group_ok[g] = (one && !anybad) ? 1 : 0;
     }
 }
+// ---- the same check in TWO kernels (hbls.cu "rlc_two_phase").  The fused kernel above keeps G + 1 running points, the Fp12 accumulator
+// and their temporaries per lane pair (4.5 KB of local memory per thread: 340 MB per launch, more than L2 -- ncu: 148 GB of DRAM traffic).
+// Here the running points live in their OWN kernel: k_rlc_lines_split walks ONE pair (P, Q) per lane pair through the 63 doubling and
+// 5 addition steps and writes the 68 line functions, already evaluated at P, to HBM (3 Fp2 per step: 19.6 KB per pair, read once);
+// k_rlc_accum_split keeps only the accumulator: f <- f^2 * prod_k line_k per iteration, then the final exponentiation.
+// Line layout: fp index ((step * 3 + c) * npairs + p) * 2 + role, p = k * ngroups + g: a warp's 32 lanes touch 1.5 KB contiguously.
+#define HB_ML_STEPS 68                 // 63 doublings + 5 additions (bits 62, 60, 57, 48, 16 of |z|)
+// the lines are written once and read once: streaming (evict-first) accesses keep them from pushing the kernels' own temporaries
+// (local memory, which lives in L1 / L2) out of L2.  fp = 48 bytes at 16-byte aligned offsets: three 128-bit accesses.
+HB_DEV void line_store(fp* dst, const fp& v) {
+#ifdef HB_HOST_EMU
+    *dst = v;
+#else
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    __stcs(d, make_uint4(v.l[0], v.l[1], v.l[2], v.l[3])); __stcs(d + 1, make_uint4(v.l[4], v.l[5], v.l[6], v.l[7])); __stcs(d + 2, make_uint4(v.l[8], v.l[9], v.l[10], v.l[11]));
+#endif
+}
+HB_DEV void line_load(fp& v, const fp* src) {
+#ifdef HB_HOST_EMU
+    v = *src;
+#else
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+    const uint4 a = __ldcs(s), b = __ldcs(s + 1), c = __ldcs(s + 2);
+    v.l[0] = a.x; v.l[1] = a.y; v.l[2] = a.z; v.l[3] = a.w; v.l[4] = b.x; v.l[5] = b.y; v.l[6] = b.z; v.l[7] = b.w; v.l[8] = c.x; v.l[9] = c.y; v.l[10] = c.z; v.l[11] = c.w;
+#endif
+}
+template <int G> __global__ void __launch_bounds__(HB_TPB_SPLIT, HB_MINBLOCKS_SPLIT) k_rlc_lines_split(size_t ngtot, size_t g0, size_t ngroups, const g1a* pk_scaled_neg, const g2a* hm,
+                                 const g2a* Sg, fp* lines) {
+    // groups g0 .. g0 + ngroups - 1 of ngtot (a chunk: the line buffer is sized for <= 37 888 groups); round of (k, g) = k * ngtot + g
+    const int role = threadIdx.x & 1;
+    const size_t ppg = HB_STRIDE >> 1, npairs = (size_t)(G + 1) * ngroups;
+    for (size_t it = 0; ; it++) {
+        const size_t warp_first = it * ppg + ((HB_TID & ~(size_t)31) >> 1);
+        if (warp_first >= npairs) break;
+        const size_t p = it * ppg + (HB_TID >> 1);
+        const bool valid = p < npairs;
+        const size_t pp = valid ? p : npairs - 1, k = pp / ngroups, g = pp - k * ngroups;
+        g1a P; const fp* q4;
+        if (k < (size_t)G) { P = pk_scaled_neg[k * ngtot + g0 + g]; q4 = reinterpret_cast<const fp*>(&hm[k * ngtot + g0 + g]); }
+        else { fp_set(P.x, K_G1_X); fp_set(P.y, K_G1_Y); q4 = reinterpret_cast<const fp*>(&Sg[g0 + g]); }
+        fp2h qx, qy; qx.c = q4[role]; qy.c = q4[2 + role];
+        g2proj_t<fp2h> T; T.x = qx; T.y = qy; fp2_one(T.z);
+        fp2h l0, l2, l3;
+        size_t st = 0;
+        for (int i = 62; i >= 0; i--) {
+#ifndef HB_LINES_SYNC
+#define HB_LINES_SYNC 1
+#endif
+            if (HB_LINES_SYNC) hb_lockstep<fp2h>();
+            ml_dbl(T, l0, l2, l3); fp2_mul_fp(l2, l2, P.x); fp2_mul_fp(l3, l3, P.y);
+            if (valid) { fp* o = lines + ((st * 3) * npairs + pp) * 2 + role; line_store(o, l0.c); line_store(o + 2 * npairs, l2.c); line_store(o + 4 * npairs, l3.c); }
+            st++;
+            if ((K_Z_ABS >> i) & 1) {
+                ml_add(T, qx, qy, l0, l2, l3); fp2_mul_fp(l2, l2, P.x); fp2_mul_fp(l3, l3, P.y);
+                if (valid) { fp* o = lines + ((st * 3) * npairs + pp) * 2 + role; line_store(o, l0.c); line_store(o + 2 * npairs, l2.c); line_store(o + 4 * npairs, l3.c); }
+                st++;
+            }
+        }
+    }
+}
+template <int G> __global__ void __launch_bounds__(HB_TPB_SPLIT, HB_MINBLOCKS_SPLIT) k_rlc_accum_split(size_t ngtot, size_t g0, size_t ngroups, const fp* lines, const uint8_t* bad, uint8_t* group_ok) {
+    const int role = threadIdx.x & 1;
+    const size_t ppg = HB_STRIDE >> 1, npairs = (size_t)(G + 1) * ngroups;
+    for (size_t it = 0; ; it++) {
+        const size_t warp_first = it * ppg + ((HB_TID & ~(size_t)31) >> 1);
+        if (warp_first >= ngroups) break;
+        const size_t g = it * ppg + (HB_TID >> 1);
+        const bool valid = g < ngroups;
+        const size_t gg = valid ? g : ngroups - 1;
+        bool anybad = false;
+        for (int k = 0; k < G; k++) anybad |= bad[(size_t)k * ngtot + g0 + gg] != 0;
+        fp12_t<fp2h> m; fp12_one(m);
+        size_t st = 0;
+#ifndef HB_LINE_PAIRS
+#define HB_LINE_PAIRS 0          // 1: lines are multiplied two by two before they touch the accumulator (23 instead of 26 Fp2 products):
+#endif                           // measured 99.1 vs 96.9 ms -- the extra temporaries cost more than the 10 % fewer products save
+#ifndef HB_ACCUM_SYNC
+#define HB_ACCUM_SYNC 0          // CTA re-alignment every this many lines inside an iteration (0: only once per iteration, -1: never);
+                                 // measured (pairing stage, 303 104 rounds): every 2 lines 98.5, every 4 96.9, per iteration only 95.7, never 100.5 ms
+#endif
+        auto mul_lines = [&](size_t step) {
+            const fp* base = lines + ((step * 3) * npairs + gg) * 2 + role;
+#pragma unroll 1
+            for (int k = 0; k <= G; k += HB_LINE_PAIRS ? 2 : 1) {
+                if (HB_ACCUM_SYNC > 0 && G > 4 && (k % (HB_ACCUM_SYNC > 0 ? HB_ACCUM_SYNC : 1)) == 0 && k) hb_lockstep<fp2h>();
+                const fp* o = base + (size_t)k * ngroups * 2;
+                fp2h l0, l2, l3; line_load(l0.c, o); line_load(l2.c, o + 2 * npairs); line_load(l3.c, o + 4 * npairs);
+                if (HB_LINE_PAIRS && k + 1 <= G) {
+                    const fp* o2 = o + ngroups * 2;
+                    fp2h n0, n2, n3; line_load(n0.c, o2); line_load(n2.c, o2 + 2 * npairs); line_load(n3.c, o2 + 4 * npairs);
+                    fp12_mul_by_two_lines(m, m, l0, l2, l3, n0, n2, n3);
+                } else
+                    fp12_mul_by_014(m, m, l0, l2, l3);
+            }
+        };
+        for (int i = 62; i >= 0; i--) {
+            if (HB_ACCUM_SYNC >= 0) hb_lockstep<fp2h>();
+            fp12_sqr(m, m);
+            mul_lines(st++);
+            if ((K_Z_ABS >> i) & 1) mul_lines(st++);
+        }
+        final_exp(m, m);
+        const bool one = fp12_is_one(m);
+        if (valid && role == 0) group_ok[g0 + g] = (one && !anybad) ? 1 : 0;
+    }
+}
 // verdicts of the groups -> per-round results; the rounds of failed groups are compacted into `list` for the exact pass.
 // counts[0] = rounds listed, counts[1] = groups that failed (hbls_last_batch_info)
 __global__ void k_rlc_finish(size_t nrounds, size_t ngroups, const uint8_t* group_ok, uint8_t* results, uint32_t* list, unsigned* counts) {

@@ -639,6 +639,37 @@ template <class E> HB_NOINLINE void fp12_mul_by_014(fp12_t<E>& r, const fp12_t<E
     fp6_sub(s, s, aa); fp6_sub(s, s, bb);
     fp6_mul_v(bb, bb); fp6_add(r.c0, aa, bb); r.c1 = s;
 }
+// x * (d1 v + d2 v^2): 5 products
+template <class E> HB_NOINLINE void fp6_mul_by_12(fp6_t<E>& r, const fp6_t<E>& x, const E& d1, const E& d2) {
+    E m1, m2, m12, s, t, u0, u1;
+    fp2_mul(m1, x.c1, d1); fp2_mul(m2, x.c2, d2);
+    fp2_add(s, x.c1, x.c2); fp2_add(t, d1, d2); fp2_mul(m12, s, t); fp2_sub(m12, m12, m1); fp2_sub(m12, m12, m2);      // x1 d2 + x2 d1
+    fp2_mul(u0, x.c0, d1); fp2_mul(u1, x.c0, d2);
+    fp2_mul_xi(r.c0, m12);
+    fp2_mul_xi(s, m2); fp2_add(r.c1, u0, s);
+    fp2_add(r.c2, u1, m1);
+}
+// x * (la * lb) for two Miller lines la = (a0 + a1 v) + (a4 v) w, lb likewise: the product of the lines first (6 products: it has five
+// non-zero coefficients), then ONE multiplication by it (17) -- 23 Fp2 products instead of 2 x 13
+template <class E> HB_NOINLINE void fp12_mul_by_two_lines(fp12_t<E>& r, const fp12_t<E>& x, const E& a0, const E& a1, const E& a4, const E& b0, const E& b1, const E& b4) {
+    hb_lockstep2<E>();
+    E t00, t11, t44, s, t, d1, d2;
+    fp6_t<E> C0;
+    fp2_mul(t00, a0, b0); fp2_mul(t11, a1, b1); fp2_mul(t44, a4, b4);
+    fp2_add(s, a0, a1); fp2_add(t, b0, b1); fp2_mul(C0.c1, s, t); fp2_sub(C0.c1, C0.c1, t00); fp2_sub(C0.c1, C0.c1, t11);   // a0 b1 + a1 b0
+    fp2_add(s, a0, a4); fp2_add(t, b0, b4); fp2_mul(d1, s, t); fp2_sub(d1, d1, t00); fp2_sub(d1, d1, t44);                  // a0 b4 + a4 b0
+    fp2_add(s, a1, a4); fp2_add(t, b1, b4); fp2_mul(d2, s, t); fp2_sub(d2, d2, t11); fp2_sub(d2, d2, t44);                  // a1 b4 + a4 b1
+    fp2_mul_xi(s, t44); fp2_add(C0.c0, t00, s); C0.c2 = t11;
+    // x * (C0 + (d1 v + d2 v^2) w)
+    fp6_t<E> v0, v1, sx, sc;
+    fp6_mul(v0, x.c0, C0);
+    fp6_mul_by_12(v1, x.c1, d1, d2);
+    fp6_add(sx, x.c0, x.c1);
+    sc.c0 = C0.c0; fp2_add(sc.c1, C0.c1, d1); fp2_add(sc.c2, C0.c2, d2);
+    fp6_mul(sx, sx, sc);
+    fp6_sub(sx, sx, v0); fp6_sub(sx, sx, v1);
+    fp6_mul_v(sc, v1); fp6_add(r.c0, v0, sc); r.c1 = sx;
+}
 // coefficient of w^k (k = 2i + j) <-> tower slot
 template <class E> HB_DEV E& fp12_slot(fp12_t<E>& x, int k) {
     fp6_t<E>& h = (k & 1) ? x.c1 : x.c0;

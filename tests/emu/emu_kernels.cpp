@@ -71,6 +71,17 @@ template <int G> static int aggregate_verify_batch(int mode, uint32_t n, const u
         run_seq(2, 2, [&] { k_rlc_scale(nr, ng, apk.data(), sig.data(), hm.data(), ok_sig.data(), ok_hm.data(), (const uint8_t*)nullptr, co, (const uint64_t*)nullptr, pk_scaled.data(), S.data(), bad.data()); });
         run_seq(1, 2, [&] { k_rlc_group_sum<G>(ng, S.data(), Sg.data()); });
         run_pair([&] { k_rlc_pairing_split<G>(ng, pk_scaled.data(), hm.data(), Sg.data(), bad.data(), group_ok.data()); });
+        {   // the two-kernel form (lines to memory, then the accumulator) must give the same verdicts -- in two chunks, like a large batch
+            std::vector<uint8_t> gok2(ng + 1, 0xee);
+            const size_t half = ng / 2 ? ng / 2 : ng;
+            for (size_t g0 = 0; g0 < ng; g0 += half) {
+                const size_t ngc = ng - g0 < half ? ng - g0 : half;
+                std::vector<fp> lines((size_t)HB_ML_STEPS * 3 * (G + 1) * ngc * 2);
+                run_pair([&] { k_rlc_lines_split<G>(ng, g0, ngc, pk_scaled.data(), hm.data(), Sg.data(), lines.data()); });
+                run_pair([&] { k_rlc_accum_split<G>(ng, g0, ngc, lines.data(), bad.data(), gok2.data()); });
+            }
+            if (std::memcmp(gok2.data(), group_ok.data(), ng) != 0) return -9;
+        }
         std::vector<uint32_t> list(B); unsigned counts[2] = {0, 0};
         run_seq(2, (unsigned)((nr + 1) / 2), [&] { k_rlc_finish(nr, ng, group_ok.data(), results, list.data(), counts); });
         run_seq(1, 3, [&] { k_g1_normalize_list(&counts[0], list.data(), apk.data(), pkneg.data(), 1); });

@@ -77,6 +77,18 @@ template <int G> static int rlc_stage_counts(const uint8_t* pks48, const uint8_t
     fp_set(P[G].x, K_G1_X); fp_set(P[G].y, K_G1_Y); ps[G] = &P[G];
     fp12 m; miller_loop_multi<fp2, G + 1>(m, ps, qx, qy); final_exp(m, m);
     out[2] = hb_emu_cnt_mul - m0; out[3] = hb_emu_cnt_sqr - s0;
+    // the share of the line kernel of the two-kernel form (k_rlc_lines_split: running points + lines evaluated at P, G + 1 pairs):
+    // out[4..5]; the accumulator kernel (k_rlc_accum_split) executes the rest of out[2..3] minus the group sum
+    m0 = hb_emu_cnt_mul; s0 = hb_emu_cnt_sqr;
+    for (int k = 0; k <= G; k++) {
+        g2proj T; T.x = qx[k]; T.y = qy[k]; fp2_one(T.z);
+        fp2 l0, l2, l3;
+        for (int i = 62; i >= 0; i--) {
+            ml_dbl(T, l0, l2, l3); fp2_mul_fp(l2, l2, ps[k]->x); fp2_mul_fp(l3, l3, ps[k]->y);
+            if ((K_Z_ABS >> i) & 1) { ml_add(T, qx[k], qy[k], l0, l2, l3); fp2_mul_fp(l2, l2, ps[k]->x); fp2_mul_fp(l3, l3, ps[k]->y); }
+        }
+    }
+    out[4] = hb_emu_cnt_mul - m0; out[5] = hb_emu_cnt_sqr - s0;
     return fp12_is_one(m) ? 1 : 0;
 }
 extern "C" int emu_rlc_stage_counts(int G, const uint8_t* pks48, const uint8_t* sigs96, const uint8_t* msgs, uint32_t len, uint64_t* out) {

@@ -128,9 +128,10 @@ def test_emu_rlc_stage_counts(emu, oracle):
     for G in (4, 8):
         sks = [wl.sk_bytes(wl.seeded_sk("cnt", i)) for i in range(G)]; pks = [oracle.get_public_key(s) for s in sks]
         msgs = [wl.commit_payload("cnt", i) for i in range(G)]; sigs = [oracle.sign_hash(s, m) for s, m in zip(sks, msgs)]
-        out = (ctypes.c_uint64 * 4)()
+        out = (ctypes.c_uint64 * 6)()
         assert emu.emu_rlc_stage_counts(G, b"".join(pks), b"".join(sigs), b"".join(msgs), 48, out) == 1
         assert (out[2], out[3]) == bench.EXEC_FP_OPS[False][G]["pairing"] == bench.EXEC_FP_OPS[True][G]["pairing"]
+        assert (out[4], out[5]) == bench.EXEC_FP_OPS_LINES[G]          # the line kernel's share in the two-kernel form
         # (the coefficient-scaling stage depends on the operands' form and the coefficients' bit pattern: pinned on the benchmark's
         #  own workload by tests/test_emu_kernels.py::test_stage_counts_pinned)
     assert bench.rlc_group_size(303104, 148) == 8 and bench.rlc_group_size(151552, 148) == 4

@@ -8,7 +8,11 @@ cap() {  # name regex rounds [env...]
   ncu -i /tmp/r2_$name.ncu-rep --page source --csv > gpurun_out/r2_${name}_src.csv 2>/dev/null
   rm -f /tmp/r2_$name.ncu-rep
 }
-cap k_hash_to_g2 '^k_hash_to_g2$|hb::k_hash_to_g2\(' 303104
+cap k_rlc_accum_split 'k_rlc_accum_split' 303104
+cap k_rlc_lines_split 'k_rlc_lines_split' 303104
+cap k_hash_sw '^k_hash_sw$' 303104
+cap k_hash_cofactor '^k_hash_cofactor$' 303104
+HBLS_HASH_SPLIT=0 cap k_hash_to_g2 '^k_hash_to_g2$|hb::k_hash_to_g2\(' 303104
 cap k_g2_decode '^k_g2_decode$' 303104
 cap k_rlc_scale 'k_rlc_scale' 303104
 cap k_mask_aggregate_serial 'k_mask_aggregate_serial' 303104
