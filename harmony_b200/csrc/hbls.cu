@@ -39,7 +39,7 @@ struct Ctx {
     bool stage_timing = false; Scratch* stage_sc = nullptr;
     int batch_mode = 1;                                     // 1: random-linear-combination groups + exact pass over failed groups, 0: exact per round
     // tuning (hbls_set_param)
-    long long rlc_min = 6144, rlc_g = 0, tpsm = 384, tpsm_split = 512, tpsm_light = 1024, coop_max = 6143, overlap = 1, coop_wpsm = 14, hash_coop_max = 592, mask_sort = 1, hash_split = 1, tpsm_sw = 512, hash_fallback = 0, rlc_two_phase = 1, tpsm_lines = 512, tpsm_accum = 512;
+    long long rlc_min = 6144, rlc_g = 0, tpsm = 384, tpsm_split = 512, tpsm_light = 1024, coop_max = 6143, overlap = 1, coop_wpsm = 14, hash_coop_max = 592, mask_sort = 1, hash_split = 2, tpsm_sw = 512, hash_fallback = 0, rlc_two_phase = 1, tpsm_lines = 512, tpsm_accum = 512;
     // coefficient stream: ChaCha20 keyed from /dev/urandom, block counter = call number
     uint32_t chacha_key[8] = {}; uint64_t rlc_calls = 0;
     // last batch
@@ -285,7 +285,11 @@ void launch_verify_tail(size_t B, const VerifyBufs& v, Scratch* sc, const uint8_
         launch_hash_small(sh, B, d_msgs, msg_len, v.hm, v.ok_hm);
     else if (g.hash_split && HB_BATCH_INV) {
         LAUNCH(k_hash_sw, capped_blocks(B, g.tpsm_sw, TPB), TPB, s, B, d_msgs, msg_len, v.hm, v.ok_hm);
-        LAUNCH(k_hash_cofactor, heavy_blocks(B), TPB, s, B, v.hm, (const uint8_t*)v.ok_hm);
+        if (g.hash_split >= 2) {        // three kernels: map | cofactor clearing (Jacobian, into the S buffer the scaling stage fills later) | affine
+            LAUNCH(k_hash_cofactor_jac, heavy_blocks(B), TPB, s, B, (const g2a*)v.hm, (const uint8_t*)v.ok_hm, v.S);
+            LAUNCH(k_g2_normalize_batch, heavy_blocks(B), TPB, s, B, (const g2*)v.S, v.hm);
+        } else
+            LAUNCH(k_hash_cofactor, heavy_blocks(B), TPB, s, B, v.hm, (const uint8_t*)v.ok_hm);
     } else
         LAUNCH(k_hash_to_g2, heavy_blocks(B), TPB, s, B, d_msgs, msg_len, v.hm, v.ok_hm);
     if (warm) {
@@ -604,9 +608,11 @@ int hbls_init_device(int device) {
     }
     g.hm_cache = envll("HBLS_HM_CACHE", 1); g.mask_sort = envll("HBLS_MASK_SORT", 1); g.hash_coop_max = envll("HBLS_HASH_COOP_MAX", 592);
     g.rlc_two_phase = envll("HBLS_RLC_2P", 1); g.tpsm_lines = envll("HBLS_TPSM_LINES", 512); g.tpsm_accum = envll("HBLS_TPSM_ACCUM", 512);
-    g.hash_split = envll("HBLS_HASH_SPLIT", 1); g.tpsm_sw = envll("HBLS_TPSM_SW", 512);
+    g.hash_split = envll("HBLS_HASH_SPLIT", 2); g.tpsm_sw = envll("HBLS_TPSM_SW", 512);
     cudaFuncSetAttribute(k_hash_sw, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_hash_cofactor, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    cudaFuncSetAttribute(k_hash_cofactor_jac, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    cudaFuncSetAttribute(k_g2_normalize_batch, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     g.ready = true;
     return 0;
 }

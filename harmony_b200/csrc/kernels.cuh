@@ -284,6 +284,34 @@ __global__ void __launch_bounds__(64, HB_SW_MINBLOCKS) k_hash_sw(size_t n, const
     }
   }
 }
+// cofactor clearing alone, Jacobian result (no per-thread arrays of pending items: the frame is the group law's own temporaries), and
+// the shared-inversion affine conversion as its own small kernel
+__global__ void k_hash_cofactor_jac(size_t n, const g2a* pts, const uint8_t* ok, g2* out) {
+  for (size_t i = HB_TID; i < n; i += HB_STRIDE) {
+    g2 h; pt_set_inf(h);
+    if (ok[i]) { g2 a; const g2a p = pts[i]; a.x = p.x; a.y = p.y; fp2_one(a.z); g2_clear_cofactor(h, a); }
+    out[i] = h;
+  }
+}
+__global__ void k_g2_normalize_batch(size_t n, const g2* in, g2a* out) {
+  for (size_t i0 = HB_TID; i0 < n; i0 += (size_t)HB_BATCH_K * HB_STRIDE) {
+    fp2 z[HB_BATCH_K]; bool skip[HB_BATCH_K];
+    for (int k = 0; k < HB_BATCH_K; k++) {
+        const size_t i = i0 + (size_t)k * HB_STRIDE;
+        skip[k] = true;
+        if (i >= n) continue;
+        z[k] = in[i].z; skip[k] = fp2_is_zero(z[k]);
+    }
+    f_batch_inv<fp2, HB_BATCH_K>(z, skip);
+    for (int k = 0; k < HB_BATCH_K; k++) {
+        const size_t i = i0 + (size_t)k * HB_STRIDE;
+        if (i >= n) continue;
+        g2a a;
+        if (skip[k]) { fp2_zero(a.x); fp2_zero(a.y); } else { const g2 h = in[i]; pt_to_aff_zinv(a, h, z[k]); }
+        out[i] = a;
+    }
+  }
+}
 __global__ void k_hash_cofactor(size_t n, g2a* pts, const uint8_t* ok) {
   for (size_t i0 = HB_TID; i0 < n; i0 += (size_t)HB_BATCH_K * HB_STRIDE) {
     g2 h[HB_BATCH_K]; fp2 z[HB_BATCH_K]; bool skip[HB_BATCH_K];
