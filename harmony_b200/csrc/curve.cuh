@@ -308,18 +308,21 @@ HB_NOINLINE bool g1_in_subgroup(const g1& p) {
 //   G2: [z^2] = psi^2,  psi^2(x, y) = (N(cx) x, -y)   (psi = [p] = [z] on G2)
 // so both scalings are 32-step two-base ladders instead of 64-step ones.  Inputs must lie in G1 / G2 (the callers'
 // points are sums of subgroup-checked keys and subgroup-checked signatures).
-HB_DEV void rlc_scale_pair(g1& ra, g2& rs, const g1& apk, const g2a& sig, uint64_t c) {
-    const uint32_t a = (uint32_t)c | 1u, b = (uint32_t)(c >> 32);
-    g1 p2; fp beta; fp_set(beta, K_BETA);
-    fp_mul(p2.x, apk.x, beta); fp_neg(p2.y, apk.y); p2.z = apk.z;
 #ifndef HB_JSF
 #define HB_JSF 1
 #endif
+HB_DEV void rlc_scale_g1(g1& ra, const g1& apk, uint64_t c) {
+    const uint32_t a = (uint32_t)c | 1u, b = (uint32_t)(c >> 32);
+    g1 p2; fp beta; fp_set(beta, K_BETA);
+    fp_mul(p2.x, apk.x, beta); fp_neg(p2.y, apk.y); p2.z = apk.z;
 #if HB_JSF
     pt_mul_2d_jsf(ra, apk, p2, a, b);
 #else
     pt_mul_2d(ra, apk, p2, a, b);
 #endif
+}
+HB_DEV void rlc_scale_g2(g2& rs, const g2a& sig, uint64_t c) {
+    const uint32_t a = (uint32_t)c | 1u, b = (uint32_t)(c >> 32);
     g2a q2; fp cx; fp_set(cx, K_PSI2_CX);
     fp2_mul_fp(q2.x, sig.x, cx); fp2_neg(q2.y, sig.y);
 #if HB_JSF
@@ -328,6 +331,7 @@ HB_DEV void rlc_scale_pair(g1& ra, g2& rs, const g1& apk, const g2a& sig, uint64
     pt_mul_2d_aff(rs, sig, q2, a, b);
 #endif
 }
+HB_DEV void rlc_scale_pair(g1& ra, g2& rs, const g1& apk, const g2a& sig, uint64_t c) { rlc_scale_g1(ra, apk, c); rlc_scale_g2(rs, sig, c); }
 
 // ------------------------------------------------------------------ codecs (reference crypto/bls/bls.go:67-71,109-118)
 // bytes are little-endian; the 12 u32 words of a canonical coordinate ARE its 48 bytes on this little-endian target

@@ -781,6 +781,40 @@ __global__ void __launch_bounds__(64, HB_SCALE_MINBLOCKS) k_rlc_scale(size_t B, 
   }
 #endif
 }
+// the same stage as two kernels, one ladder each (hbls.cu "scale_split"): the G1 ladder (+ shared-inversion affine conversion) and the
+// G2 ladder are different code over different fields -- ncu on the fused kernel: stall_no_instruction 1.3 per issue
+__global__ void k_rlc_scale_g1(size_t B, size_t ng, const g1* apk, rlc_coeffs co, g1a* pk_scaled_neg) {
+  for (size_t j0 = HB_TID; j0 < B; j0 += (size_t)HB_BATCH_K * HB_STRIDE) {
+    g1 ra[HB_BATCH_K]; fp z[HB_BATCH_K]; bool skip[HB_BATCH_K];
+    for (int k = 0; k < HB_BATCH_K; k++) {
+        const size_t j = j0 + (size_t)k * HB_STRIDE;
+        skip[k] = true;
+        if (j >= B) continue;
+        const g1 a = apk[j];
+        if (j < ng) ra[k] = a; else rlc_scale_g1(ra[k], a, co.c[j / ng]);
+        skip[k] = pt_is_inf(ra[k]);
+        if (!skip[k]) z[k] = ra[k].z;
+    }
+    f_batch_inv<fp, HB_BATCH_K>(z, skip);
+    for (int k = 0; k < HB_BATCH_K; k++) {
+        const size_t j = j0 + (size_t)k * HB_STRIDE;
+        if (j >= B) continue;
+        g1a pa;
+        if (skip[k]) { fp_zero(pa.x); fp_zero(pa.y); } else { pt_to_aff_zinv(pa, ra[k], z[k]); fp_neg(pa.y, pa.y); }
+        pk_scaled_neg[j] = pa;
+    }
+  }
+}
+__global__ void k_rlc_scale_g2(size_t B, size_t ng, const g1* apk, const g2a* sig, const g2a* hm, const uint8_t* ok_sig, const uint8_t* ok_hm,
+                               const uint8_t* ok_pk, rlc_coeffs co, g2* S, uint8_t* bad) {
+  for (size_t j = HB_TID; j < B; j += HB_STRIDE) {
+    const g2a sg = sig[j];
+    const bool b = !ok_sig[j] || !ok_hm[j] || (ok_pk && !ok_pk[j]) || fp_is_zero(apk[j].z) || aff_is_inf(sg) || aff_is_inf(hm[j]);
+    g2 rs;
+    if (j < ng) pt_from_aff(rs, sg); else rlc_scale_g2(rs, sg, co.c[j / ng]);
+    S[j] = rs; bad[j] = b ? 1 : 0;
+  }
+}
 // per group: affine sum of its S_j
 template <int G> __global__ void k_rlc_group_sum(size_t ngroups, const g2* S, g2a* Sg) {
   for (size_t g = HB_TID; g < ngroups; g += HB_STRIDE) {

@@ -69,6 +69,13 @@ template <int G> static int aggregate_verify_batch(int mode, uint32_t n, const u
         rlc_coeffs co;                                          // stands in for the host's ChaCha20 draw (hbls.cu rlc_draw)
         for (int k = 0; k < HB_RLC_GMAX; k++) { uint64_t x = s0 + 0x9e3779b97f4a7c15ull * (uint64_t)(k + 1); x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x ^= s1; co.c[k] = x; }
         run_seq(2, 2, [&] { k_rlc_scale(nr, ng, apk.data(), sig.data(), hm.data(), ok_sig.data(), ok_hm.data(), (const uint8_t*)nullptr, co, (const uint64_t*)nullptr, pk_scaled.data(), S.data(), bad.data()); });
+        {   // the two-kernel form of the stage (one ladder per kernel) must produce the same points and flags
+            std::vector<g1a> pk2(B); std::vector<g2> S2(B); std::vector<uint8_t> bad2(B, 0xee);
+            run_seq(2, 2, [&] { k_rlc_scale_g1(nr, ng, apk.data(), co, pk2.data()); });
+            run_seq(2, 2, [&] { k_rlc_scale_g2(nr, ng, apk.data(), sig.data(), hm.data(), ok_sig.data(), ok_hm.data(), (const uint8_t*)nullptr, co, S2.data(), bad2.data()); });
+            if (std::memcmp(pk2.data(), pk_scaled.data(), nr * sizeof(g1a)) != 0 || std::memcmp(bad2.data(), bad.data(), nr) != 0) return -8;
+            for (size_t j = 0; j < nr; j++) if (!pt_eq(S2[j], S[j])) return -8;
+        }
         run_seq(1, 2, [&] { k_rlc_group_sum<G>(ng, S.data(), Sg.data()); });
         run_pair([&] { k_rlc_pairing_split<G>(ng, pk_scaled.data(), hm.data(), Sg.data(), bad.data(), group_ok.data()); });
         {   // the two-kernel form (lines to memory, then the accumulator) must give the same verdicts -- in two chunks, like a large batch
