@@ -39,7 +39,7 @@ struct Ctx {
     bool stage_timing = false; Scratch* stage_sc = nullptr;
     int batch_mode = 1;                                     // 1: random-linear-combination groups + exact pass over failed groups, 0: exact per round
     // tuning (hbls_set_param)
-    long long rlc_min = 6144, rlc_g = 0, tpsm = 384, tpsm_split = 512, tpsm_light = 1024, coop_max = 6143, overlap = 1, coop_wpsm = 14, hash_coop_max = 592, mask_sort = 1, hash_split = 2, tpsm_sw = 512, hash_fallback = 0, rlc_two_phase = 2, tpsm_lines = 512, tpsm_accum = 512, tpsm_cof = 512, tpsm_dec = 512, tpsm_scale = 384, tpsm_scale_g1 = 384, scale_split = 1;
+    long long rlc_min = 6144, rlc_g = 0, tpsm = 384, tpsm_split = 512, tpsm_light = 1024, coop_max = 6143, overlap = 1, coop_wpsm = 14, hash_coop_max = 592, mask_sort = 1, hash_split = 2, tpsm_sw = 512, hash_fallback = 0, rlc_two_phase = 2, tpsm_lines = 512, tpsm_accum = 512, tpsm_cof = 512, tpsm_dec = 512, tpsm_scale = 384, tpsm_scale_g1 = 384, scale_split = 1, decode_split = 1;
     // coefficient stream: ChaCha20 keyed from /dev/urandom, block counter = call number
     uint32_t chacha_key[8] = {}; uint64_t rlc_calls = 0;
     // last batch
@@ -268,7 +268,10 @@ void launch_verify_tail(size_t B, const VerifyBufs& v, Scratch* sc, const uint8_
     // on the caller's stream, (B, sigma) after the decode on the decode stream with the signature's subgroup test beside it
     const bool warm = hit && split_ml;
     if (pairs) LAUNCH(k_g2_decode_pair, blocks_for(2 * B, 32), 32, sd, B, d_sig96, v.sig, v.ok_sig, warm ? 0 : 1);
-    else LAUNCH(k_g2_decode, capped_blocks(B, g.tpsm_dec, TPB), TPB, s, B, d_sig96, v.sig, v.ok_sig, 1);
+    else if (g.decode_split) {
+        LAUNCH(k_g2_decode, capped_blocks(B, g.tpsm_dec, TPB), TPB, s, B, d_sig96, v.sig, v.ok_sig, 0);
+        LAUNCH(k_g2_subgroup, capped_blocks(B, g.tpsm_dec, TPB), TPB, s, B, v.sig, v.ok_sig);
+    } else LAUNCH(k_g2_decode, capped_blocks(B, g.tpsm_dec, TPB), TPB, s, B, d_sig96, v.sig, v.ok_sig, 1);
     if (warm) {
         cudaEventRecord(sc->mid, sd);
         LAUNCH(k_miller_pq_coop, coop_grid, 32, sd, B, (const g1a*)nullptr, v.sig, v.ok_sig, v.f1, v.irr1);
@@ -613,7 +616,7 @@ int hbls_init_device(int device) {
         CK(cudaEventCreateWithFlags(&g.hm[i].filled, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&g.hm[i].read_done, cudaEventDisableTiming));
     }
     g.hm_cache = envll("HBLS_HM_CACHE", 1); g.mask_sort = envll("HBLS_MASK_SORT", 1); g.hash_coop_max = envll("HBLS_HASH_COOP_MAX", 592);
-    g.rlc_two_phase = envll("HBLS_RLC_2P", 2); g.tpsm_lines = envll("HBLS_TPSM_LINES", 512); g.tpsm_accum = envll("HBLS_TPSM_ACCUM", 512); g.tpsm_cof = envll("HBLS_TPSM_COF", 512); g.tpsm_dec = envll("HBLS_TPSM_DEC", 512); g.tpsm_scale = envll("HBLS_TPSM_SCALE", 384); g.tpsm_scale_g1 = envll("HBLS_TPSM_SCALE_G1", 384); g.scale_split = envll("HBLS_SCALE_SPLIT", 1);
+    g.rlc_two_phase = envll("HBLS_RLC_2P", 2); g.tpsm_lines = envll("HBLS_TPSM_LINES", 512); g.tpsm_accum = envll("HBLS_TPSM_ACCUM", 512); g.tpsm_cof = envll("HBLS_TPSM_COF", 512); g.tpsm_dec = envll("HBLS_TPSM_DEC", 512); g.tpsm_scale = envll("HBLS_TPSM_SCALE", 384); g.tpsm_scale_g1 = envll("HBLS_TPSM_SCALE_G1", 384); g.scale_split = envll("HBLS_SCALE_SPLIT", 1); g.decode_split = envll("HBLS_DECODE_SPLIT", 1);
     g.hash_split = envll("HBLS_HASH_SPLIT", 2); g.tpsm_sw = envll("HBLS_TPSM_SW", 512);
     cudaFuncSetAttribute(k_hash_sw, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_hash_cofactor, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
@@ -653,6 +656,7 @@ static long long* param_slot(const char* name) {
     if (!strcmp(name, "tpsm_scale")) return &g.tpsm_scale;
     if (!strcmp(name, "tpsm_scale_g1")) return &g.tpsm_scale_g1;
     if (!strcmp(name, "scale_split")) return &g.scale_split;
+    if (!strcmp(name, "decode_split")) return &g.decode_split;
     if (!strcmp(name, "tpsm_lines")) return &g.tpsm_lines;
     if (!strcmp(name, "tpsm_accum")) return &g.tpsm_accum;
     if (!strcmp(name, "tpsm_sw")) return &g.tpsm_sw;

@@ -59,6 +59,18 @@ __global__ void __launch_bounds__(64, HB_DEC_MINBLOCKS) k_g2_decode(size_t n, co
   }
 }
 
+// subgroup test of already-decoded affine points, one per thread (second half of k_g2_decode when the stage runs as two kernels,
+// hbls.cu "decode_split": square-root chains | G2 ladder); a point outside the subgroup loses its ok flag and is zeroed
+__global__ void __launch_bounds__(64, HB_DEC_MINBLOCKS) k_g2_subgroup(size_t n, g2a* pts, uint8_t* ok) {
+  for (size_t i = HB_TID; i < n; i += HB_STRIDE) {
+    if (!ok[i]) continue;
+    const g2a a = pts[i];
+    if (aff_is_inf(a)) continue;
+    g2 q; q.x = a.x; q.y = a.y; fp2_one(q.z);
+    if (!g2_in_subgroup(q)) { g2a z; fp2_zero(z.x); fp2_zero(z.y); pts[i] = z; ok[i] = 0; }
+  }
+}
+
 // ---- warp shuffle of a whole point
 template <class T> HB_DEV void shfl_down_struct(T& dst, const T& src, int off) {
     const uint32_t* s = reinterpret_cast<const uint32_t*>(&src);
