@@ -817,7 +817,10 @@ __global__ void k_rlc_scale_g1(size_t B, size_t ng, const g1* apk, rlc_coeffs co
     }
   }
 }
-__global__ void k_rlc_scale_g2(size_t B, size_t ng, const g1* apk, const g2a* sig, const g2a* hm, const uint8_t* ok_sig, const uint8_t* ok_hm,
+#ifndef HB_SCALE_G2_MINBLOCKS
+#define HB_SCALE_G2_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(64, HB_SCALE_G2_MINBLOCKS) k_rlc_scale_g2(size_t B, size_t ng, const g1* apk, const g2a* sig, const g2a* hm, const uint8_t* ok_sig, const uint8_t* ok_hm,
                                const uint8_t* ok_pk, rlc_coeffs co, g2* S, uint8_t* bad) {
   for (size_t j = HB_TID; j < B; j += HB_STRIDE) {
     const g2a sg = sig[j];
