@@ -39,7 +39,7 @@ struct Ctx {
     bool stage_timing = false; Scratch* stage_sc = nullptr;
     int batch_mode = 1;                                     // 1: random-linear-combination groups + exact pass over failed groups, 0: exact per round
     // tuning (hbls_set_param)
-    long long rlc_min = 6144, rlc_g = 0, tpsm = 384, tpsm_split = 512, tpsm_light = 1024, coop_max = 6143, overlap = 1, coop_wpsm = 14, hash_coop_max = 592, mask_sort = 1, hash_split = 2, tpsm_sw = 512, hash_fallback = 0, rlc_two_phase = 2, tpsm_lines = 512, tpsm_accum = 512, tpsm_cof = 512, tpsm_dec = 512, tpsm_scale = 384, tpsm_scale_g1 = 384, scale_split = 1, decode_split = 1;
+    long long rlc_min = 12288, rlc_g = 0, tpsm = 384, tpsm_split = 512, tpsm_light = 1024, coop_max = 4096, overlap = 1, coop_wpsm = 14, hash_coop_max = 592, mask_sort = 1, hash_split = 2, tpsm_sw = 512, hash_fallback = 0, rlc_two_phase = 2, tpsm_lines = 512, tpsm_accum = 512, tpsm_cof = 512, tpsm_dec = 512, tpsm_scale = 384, tpsm_scale_g1 = 384, scale_split = 1, decode_split = 1, exact_two_phase = 1;
     // coefficient stream: ChaCha20 keyed from /dev/urandom, block counter = call number
     uint32_t chacha_key[8] = {}; uint64_t rlc_calls = 0;
     // last batch
@@ -198,20 +198,30 @@ size_t rlc_group_size(size_t B) {
 }
 constexpr size_t RLC_CHUNK_GROUPS = 37888;             // two-phase form: groups per pass (148 SMs x 256 lane pairs)
 static bool rlc_applies(size_t B);
+static bool exact_two_phase(size_t B);
 size_t rlc_lines_bytes(size_t B) {
-    if (!g.rlc_two_phase || !rlc_applies(B)) return 0;
+    if (!g.rlc_two_phase) return 0;
+    if (!rlc_applies(B)) {      // exact form through the same kernels: "groups" of one round, two pairs each
+        if (!exact_two_phase(B)) return 0;
+        const size_t ngc = B < RLC_CHUNK_GROUPS ? B : RLC_CHUNK_GROUPS;
+        return (size_t)HB_ML_STEPS * 3 * 2 * ngc * 2 * sizeof(fp) + 256;
+    }
     const size_t G = rlc_group_size(B), ng = B / G, ngc = ng < RLC_CHUNK_GROUPS ? ng : RLC_CHUNK_GROUPS;
-    return (size_t)HB_ML_STEPS * 3 * (G + 1) * ngc * 2 * sizeof(fp) + 256;
+    const size_t rlc_bytes = (size_t)HB_ML_STEPS * 3 * (G + 1) * ngc * 2 * sizeof(fp);
+    // the exact pass over the rounds of failed groups runs through the same buffer ("groups" of one round, <= all rounds of the batch)
+    const size_t nlc = B < RLC_CHUNK_GROUPS ? B : RLC_CHUNK_GROUPS;
+    const size_t list_bytes = g.exact_two_phase ? (size_t)HB_ML_STEPS * 3 * 2 * nlc * 2 * sizeof(fp) + B * sizeof(g2a) + 256 : 0;
+    return (rlc_bytes > list_bytes ? rlc_bytes : list_bytes) + 256;
 }
 size_t verify_scratch_bytes(size_t B) {
-    return B * (sizeof(g2a) * 2 + sizeof(g1a) * 2 + sizeof(g1) + sizeof(g2) + 16 + 4 + 6) + HB_MASK_BINS * 4 + (B / HB_RLC_G + 1) * (sizeof(g2a) + 8) + 44 * 256
+    return B * (sizeof(g2a) * 2 + sizeof(g1a) * 2 + sizeof(g1) + sizeof(g2) + 16 + 4 + 7) + HB_MASK_BINS * 4 + (B / HB_RLC_G + 1) * (sizeof(g2a) + 8) + 44 * 256
            + (B <= 8192 ? B * (12 * sizeof(fp2) + 3) + 1024 : 0)                // latency path: Miller values of (B, sigma) and (-apk, H(m))
-           + (B >= 2 * HB_RLC_GMAX ? rlc_lines_bytes(B) : 0);                    // two-phase batched form: the line functions of one chunk
+           + rlc_lines_bytes(B);                                                 // two-kernel pairing: the line functions of one chunk
 }
 struct VerifyBufs { g2a* sig; g2a* hm; g1a* pkneg; g1* apk; uint8_t* ok_sig; uint8_t* ok_hm; uint8_t* ok_pk;
                     g1a* pk_scaled; g2* S; uint8_t* bad; g2a* Sg; uint8_t* group_ok; uint32_t* fail_list; unsigned* counts;
                     fp2* f1; uint8_t* irr1; fp2* f2; uint8_t* irr2; uint8_t* ok_sub;
-                    uint16_t* mask_cost; unsigned* mask_hist; uint32_t* mask_order; fp* lines; };
+                    uint16_t* mask_cost; unsigned* mask_hist; uint32_t* mask_order; fp* lines; uint8_t* verdict; };
 VerifyBufs carve_verify(Arena& ar, size_t B) {
     VerifyBufs v;
     v.sig = ar.take<g2a>(B); v.hm = ar.take<g2a>(B); v.pkneg = ar.take<g1a>(B); v.apk = ar.take<g1>(B);
@@ -220,8 +230,9 @@ VerifyBufs carve_verify(Arena& ar, size_t B) {
     v.Sg = ar.take<g2a>(B / HB_RLC_G + 1); v.group_ok = ar.take<uint8_t>(B / HB_RLC_G + 1);
     v.fail_list = ar.take<uint32_t>(B); v.counts = ar.take<unsigned>(2);
     v.mask_cost = ar.take<uint16_t>(B); v.mask_hist = ar.take<unsigned>(HB_MASK_BINS); v.mask_order = ar.take<uint32_t>(B);
+    v.verdict = ar.take<uint8_t>(B);
     v.lines = nullptr;
-    if (B >= 2 * HB_RLC_GMAX && rlc_lines_bytes(B)) v.lines = reinterpret_cast<fp*>(ar.take<uint8_t>(rlc_lines_bytes(B)));
+    if (rlc_lines_bytes(B)) v.lines = reinterpret_cast<fp*>(ar.take<uint8_t>(rlc_lines_bytes(B)));
     v.f1 = v.f2 = nullptr; v.irr1 = v.irr2 = v.ok_sub = nullptr;
     if (B <= 8192) { v.f1 = ar.take<fp2>(6 * B); v.irr1 = ar.take<uint8_t>(B); v.f2 = ar.take<fp2>(6 * B); v.irr2 = ar.take<uint8_t>(B); v.ok_sub = ar.take<uint8_t>(B); }
     return v;
@@ -236,6 +247,12 @@ void fork_point(size_t B, Scratch* sc, cudaStream_t s) {
 // batched (random-linear-combination) form applies: default mode and a batch large enough
 static bool rlc_applies(size_t B) { return g.batch_mode == 1 && (long long)B >= g.rlc_min && B >= 2 * HB_RLC_GMAX; }
 static bool latency_path(size_t B) { return !rlc_applies(B) && (long long)B <= g.coop_max; }
+// exact checks of batches beyond the warp-per-round range run as line kernel + accumulator kernel too (twice the lane pairs in the
+// first one; the second no longer carries the running points)
+static bool exact_two_phase(size_t B) { return g.rlc_two_phase >= 2 && g.exact_two_phase && !rlc_applies(B) && (long long)B > g.coop_max; }
+// exact check of n rounds (contiguous arrays) as "groups" of one round through k_rlc_lines_split<1> / k_rlc_accum_split<1>
+void launch_exact_two_phase(size_t n, const g2a* sig, const g1a* pkneg, const g2a* hm, const uint8_t* ok_a, const uint8_t* ok_b, const uint8_t* ok_c,
+                            uint8_t* bad, uint8_t* verdict, fp* lines, uint8_t* d_results, cudaStream_t s);
 #define STAGE_EV(i, sc, strm) do { if (g.stage_timing && (sc)->ev_ok) cudaEventRecord((sc)->ev[i], (strm)); } while (0)
 // v.apk holds the Jacobian (aggregate) public key of every round; ok_pk (nullable) = per-round "key decoded" flags of the triple form
 // h_msg (nullable): host copy of THE message when the call has a single one (one round, or a same-message batch) -- the key of the
@@ -352,7 +369,25 @@ void launch_verify_tail(size_t B, const VerifyBufs& v, Scratch* sc, const uint8_
         // return at once when the list is short or empty)
         LAUNCH(k_rlc_finish, blocks_for(nr, 256), 256, s, nr, ng, v.group_ok, d_results, v.fail_list, v.counts);
         LAUNCH(k_g1_normalize_list, heavy_blocks(nr), TPB, s, v.counts, v.fail_list, v.apk, v.pkneg, 1);
-        if (2 * nr >= (size_t)g.sm_count * HB_TPB_SPLIT)
+        if (two_phase && g.exact_two_phase) {
+            // the listed rounds, gathered into contiguous arrays, through the line / accumulator kernels as "groups" of one round; the
+            // launches are sized for the worst case and return at once beyond the device-side count
+            const size_t nlc = nr < RLC_CHUNK_GROUPS ? nr : RLC_CHUNK_GROUPS;
+            g2a* hm_c = reinterpret_cast<g2a*>(v.lines + (size_t)HB_ML_STEPS * 3 * 2 * nlc * 2);      // behind the chunk's lines
+            g2a* sig_c = reinterpret_cast<g2a*>(v.S); g1a* pk_c = v.pk_scaled;                        // both free after the group pass
+            const unsigned* cnt = v.counts;
+            LAUNCH(k_exact_prepare, blocks_for(nr, 256), 256, s, nr, (const uint32_t*)v.fail_list, (const g2a*)v.sig, (const g1a*)v.pkneg, (const g2a*)v.hm,
+                   (const uint8_t*)v.ok_sig, (const uint8_t*)v.ok_hm, ok_pk, pk_c, hm_c, sig_c, v.bad, d_results, cnt);
+            const bool lfull = 2 * nr >= (size_t)g.sm_count * HB_TPB_SPLIT;
+            const unsigned bt = lfull ? HB_TPB_SPLIT : 64;
+            for (size_t g0 = 0; g0 < nr; g0 += RLC_CHUNK_GROUPS) {
+                const size_t nc = nr - g0 < RLC_CHUNK_GROUPS ? nr - g0 : RLC_CHUNK_GROUPS;
+                const unsigned lb = lfull ? split_blocks(4 * nc) : blocks_for(4 * nc, 64), ab = lfull ? split_blocks(2 * nc) : blocks_for(2 * nc, 64);
+                LAUNCH(k_rlc_lines_split<1>, lb, bt, s, nr, g0, nc, (const g1a*)pk_c, (const g2a*)hm_c, (const g2a*)sig_c, v.lines, cnt);
+                LAUNCH(k_rlc_accum_split<1>, ab, bt, s, nr, g0, nc, (const fp*)v.lines, (const uint8_t*)v.bad, v.verdict, cnt);
+            }
+            LAUNCH(k_exact_publish, blocks_for(nr, 256), 256, s, nr, (const uint32_t*)v.fail_list, (const uint8_t*)v.verdict, d_results, cnt);
+        } else if (2 * nr >= (size_t)g.sm_count * HB_TPB_SPLIT)
             LAUNCH(k_pairing_verify_split_list, split_blocks(2 * nr), HB_TPB_SPLIT, s, v.counts, v.fail_list, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
         else
             LAUNCH(k_pairing_verify_split_list, blocks_for(2 * nr, 64), 64, s, v.counts, v.fail_list, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
@@ -377,6 +412,8 @@ void launch_verify_tail(size_t B, const VerifyBufs& v, Scratch* sc, const uint8_
             LAUNCH(k_pairing_coop2, coop_grid, 32, s, B, v.f1, v.irr1, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
         else if (coop)
             LAUNCH(k_pairing_coop, coop_grid, 32, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results);
+        else if (exact_two_phase(B) && v.lines)
+            launch_exact_two_phase(B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, v.bad, v.verdict, v.lines, d_results, s);
         else if (full)
             LAUNCH(k_pairing_verify_split, split_blocks(2 * B), HB_TPB_SPLIT, s, B, v.sig, v.pkneg, v.hm, v.ok_sig, v.ok_hm, ok_pk, d_results, (const int*)nullptr);
         else
@@ -389,6 +426,21 @@ void launch_verify_tail(size_t B, const VerifyBufs& v, Scratch* sc, const uint8_
     cudaEventRecord(sc->done, s);
     g.info_sc = sc; g.info_valid = true;
     if (g.stage_timing && sc->ev_ok) g.stage_sc = sc;
+}
+
+void launch_exact_two_phase(size_t n, const g2a* sig, const g1a* pkneg, const g2a* hm, const uint8_t* ok_a, const uint8_t* ok_b, const uint8_t* ok_c,
+                            uint8_t* bad, uint8_t* verdict, fp* lines, uint8_t* d_results, cudaStream_t s) {
+    LAUNCH(k_exact_prepare, blocks_for(n, 256), 256, s, n, (const uint32_t*)nullptr, sig, pkneg, hm, ok_a, ok_b, ok_c,
+           (g1a*)nullptr, (g2a*)nullptr, (g2a*)nullptr, bad, d_results);
+    const bool full = 2 * n >= (size_t)g.sm_count * HB_TPB_SPLIT;
+    for (size_t g0 = 0; g0 < n; g0 += RLC_CHUNK_GROUPS) {
+        const size_t nc = n - g0 < RLC_CHUNK_GROUPS ? n - g0 : RLC_CHUNK_GROUPS;
+        const unsigned bt = full ? HB_TPB_SPLIT : 64;
+        const unsigned lb = full ? split_blocks(4 * nc) : blocks_for(4 * nc, 64), ab = full ? split_blocks(2 * nc) : blocks_for(2 * nc, 64);
+        LAUNCH(k_rlc_lines_split<1>, lb, bt, s, n, g0, nc, pkneg, hm, sig, lines);
+        LAUNCH(k_rlc_accum_split<1>, ab, bt, s, n, g0, nc, (const fp*)lines, (const uint8_t*)bad, verdict);
+    }
+    LAUNCH(k_exact_publish, blocks_for(n, 256), 256, s, n, (const uint32_t*)nullptr, (const uint8_t*)verdict, d_results);
 }
 
 int single_op(int op, const void* a, size_t an, const void* b, size_t bn, void* out, size_t on, int* rc_out, uint32_t len = 0) {
@@ -590,7 +642,7 @@ int hbls_init_device(int device) {
     CK(cudaStreamCreateWithFlags(&g.aux[0], cudaStreamNonBlocking)); CK(cudaStreamCreateWithFlags(&g.aux[1], cudaStreamNonBlocking));
     { FILE* f = fopen("/dev/urandom", "rb"); if (!f || fread(g.chacha_key, 1, 32, f) != 32) { if (f) fclose(f); fprintf(stderr, "[hbls] cannot read /dev/urandom\n"); return HBLS_ERR_CUDA; } fclose(f); }
     auto envll = [](const char* name, long long dflt) { const char* e = getenv(name); return e ? atoll(e) : dflt; };
-    g.rlc_min = envll("HBLS_RLC_MIN", 6144); g.rlc_g = envll("HBLS_RLC_G", 0); g.coop_max = envll("HBLS_COOP_MAX", 6143);
+    g.rlc_min = envll("HBLS_RLC_MIN", 12288); g.rlc_g = envll("HBLS_RLC_G", 0); g.coop_max = envll("HBLS_COOP_MAX", 4096);
     g.tpsm = envll("HBLS_TPSM", 384); g.tpsm_split = envll("HBLS_TPSM_SPLIT", 512); g.tpsm_light = envll("HBLS_TPSM_LIGHT", 1024);
     // the heavy kernels keep their Fp12 temporaries in per-thread local memory: give L1 the whole 228 KB
 #if HB_SMEM_F
@@ -600,6 +652,8 @@ int hbls_init_device(int device) {
     cudaFuncSetAttribute(k_rlc_pairing_split<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_rlc_pairing_split<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
 #endif
+    cudaFuncSetAttribute(k_rlc_lines_split<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+    cudaFuncSetAttribute(k_rlc_accum_split<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_rlc_lines_split<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_rlc_lines_split<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_rlc_accum_split<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
@@ -616,7 +670,7 @@ int hbls_init_device(int device) {
         CK(cudaEventCreateWithFlags(&g.hm[i].filled, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&g.hm[i].read_done, cudaEventDisableTiming));
     }
     g.hm_cache = envll("HBLS_HM_CACHE", 1); g.mask_sort = envll("HBLS_MASK_SORT", 1); g.hash_coop_max = envll("HBLS_HASH_COOP_MAX", 592);
-    g.rlc_two_phase = envll("HBLS_RLC_2P", 2); g.tpsm_lines = envll("HBLS_TPSM_LINES", 512); g.tpsm_accum = envll("HBLS_TPSM_ACCUM", 512); g.tpsm_cof = envll("HBLS_TPSM_COF", 512); g.tpsm_dec = envll("HBLS_TPSM_DEC", 512); g.tpsm_scale = envll("HBLS_TPSM_SCALE", 384); g.tpsm_scale_g1 = envll("HBLS_TPSM_SCALE_G1", 384); g.scale_split = envll("HBLS_SCALE_SPLIT", 1); g.decode_split = envll("HBLS_DECODE_SPLIT", 1);
+    g.rlc_two_phase = envll("HBLS_RLC_2P", 2); g.tpsm_lines = envll("HBLS_TPSM_LINES", 512); g.tpsm_accum = envll("HBLS_TPSM_ACCUM", 512); g.tpsm_cof = envll("HBLS_TPSM_COF", 512); g.tpsm_dec = envll("HBLS_TPSM_DEC", 512); g.tpsm_scale = envll("HBLS_TPSM_SCALE", 384); g.tpsm_scale_g1 = envll("HBLS_TPSM_SCALE_G1", 384); g.scale_split = envll("HBLS_SCALE_SPLIT", 1); g.decode_split = envll("HBLS_DECODE_SPLIT", 1); g.exact_two_phase = envll("HBLS_EXACT_2P", 1);
     g.hash_split = envll("HBLS_HASH_SPLIT", 2); g.tpsm_sw = envll("HBLS_TPSM_SW", 512);
     cudaFuncSetAttribute(k_hash_sw, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     cudaFuncSetAttribute(k_hash_cofactor, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
@@ -657,6 +711,7 @@ static long long* param_slot(const char* name) {
     if (!strcmp(name, "tpsm_scale_g1")) return &g.tpsm_scale_g1;
     if (!strcmp(name, "scale_split")) return &g.scale_split;
     if (!strcmp(name, "decode_split")) return &g.decode_split;
+    if (!strcmp(name, "exact_two_phase")) return &g.exact_two_phase;
     if (!strcmp(name, "tpsm_lines")) return &g.tpsm_lines;
     if (!strcmp(name, "tpsm_accum")) return &g.tpsm_accum;
     if (!strcmp(name, "tpsm_sw")) return &g.tpsm_sw;

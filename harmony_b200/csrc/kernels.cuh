@@ -908,8 +908,10 @@ HB_DEV void line_load(fp& v, const fp* src) {
 #endif
 }
 template <int G> __global__ void __launch_bounds__(HB_TPB_SPLIT, HB_MINBLOCKS_SPLIT) k_rlc_lines_split(size_t ngtot, size_t g0, size_t ngroups, const g1a* pk_scaled_neg, const g2a* hm,
-                                 const g2a* Sg, fp* lines) {
+                                 const g2a* Sg, fp* lines, const unsigned* count = nullptr) {
     // groups g0 .. g0 + ngroups - 1 of ngtot (a chunk: the line buffer is sized for <= 37 888 groups); round of (k, g) = k * ngtot + g
+    // count (nullable): the number of groups is only known on the device (compacted list of the failed groups' rounds)
+    if (count) { const size_t n = *count; if (g0 >= n) return; ngtot = n; ngroups = n - g0 < ngroups ? n - g0 : ngroups; }
     const int role = threadIdx.x & 1;
     const size_t ppg = HB_STRIDE >> 1, npairs = (size_t)(G + 1) * ngroups;
     for (size_t it = 0; ; it++) {
@@ -941,7 +943,8 @@ template <int G> __global__ void __launch_bounds__(HB_TPB_SPLIT, HB_MINBLOCKS_SP
         }
     }
 }
-template <int G> __global__ void __launch_bounds__(HB_TPB_SPLIT, HB_MINBLOCKS_SPLIT) k_rlc_accum_split(size_t ngtot, size_t g0, size_t ngroups, const fp* lines, const uint8_t* bad, uint8_t* group_ok) {
+template <int G> __global__ void __launch_bounds__(HB_TPB_SPLIT, HB_MINBLOCKS_SPLIT) k_rlc_accum_split(size_t ngtot, size_t g0, size_t ngroups, const fp* lines, const uint8_t* bad, uint8_t* group_ok, const unsigned* count = nullptr) {
+    if (count) { const size_t n = *count; if (g0 >= n) return; ngtot = n; ngroups = n - g0 < ngroups ? n - g0 : ngroups; }
     const int role = threadIdx.x & 1;
     const size_t ppg = HB_STRIDE >> 1, npairs = (size_t)(G + 1) * ngroups;
     for (size_t it = 0; ; it++) {
@@ -986,6 +989,28 @@ template <int G> __global__ void __launch_bounds__(HB_TPB_SPLIT, HB_MINBLOCKS_SP
         const bool one = fp12_is_one(m);
         if (valid && role == 0) group_ok[g0 + g] = (one && !anybad) ? 1 : 0;
     }
+}
+// ---- the EXACT check through the same two kernels: a "group" of ONE round = the pairs (-apk_j, H(m_j)) and (B, sigma_j), i.e.
+// k_rlc_lines_split<1> / k_rlc_accum_split<1> with pk_scaled_neg = -apk (affine) and Sg = the decoded signatures.  These two small
+// kernels prepare the flags (a round with an identity operand is left to k_pairing_fixup: 0xFF, as in k_pairing_verify_split)
+// and publish the verdicts.  idx (nullable): the rounds are those of a compacted list (failed groups of the batched form).
+__global__ void k_exact_prepare(size_t n, const uint32_t* idx, const g2a* sig, const g1a* pk_neg, const g2a* hm, const uint8_t* ok_a, const uint8_t* ok_b,
+                                const uint8_t* ok_c, g1a* pk_c, g2a* hm_c, g2a* sig_c, uint8_t* bad, uint8_t* results, const unsigned* count = nullptr) {
+    if (count) n = *count;
+    const size_t t = HB_TID; if (t >= n) return;
+    const size_t j = idx ? idx[t] : t;
+    const g2a s = sig[j], h = hm[j]; const g1a p = pk_neg[j];
+    const bool good = (!ok_a || ok_a[j]) && (!ok_b || ok_b[j]) && (!ok_c || ok_c[j]);
+    const bool irregular = aff_is_inf(s) || aff_is_inf(h) || aff_is_inf(p);
+    bad[t] = (!good || irregular) ? 1 : 0;
+    if (pk_c) { pk_c[t] = p; hm_c[t] = h; sig_c[t] = s; }               // gathered copies (list form)
+    results[j] = irregular ? 0xFF : 0;
+}
+__global__ void k_exact_publish(size_t n, const uint32_t* idx, const uint8_t* verdict, uint8_t* results, const unsigned* count = nullptr) {
+    if (count) n = *count;
+    const size_t t = HB_TID; if (t >= n) return;
+    const size_t j = idx ? idx[t] : t;
+    if (results[j] != 0xFF) results[j] = verdict[t];
 }
 // verdicts of the groups -> per-round results; the rounds of failed groups are compacted into `list` for the exact pass.
 // counts[0] = rounds listed, counts[1] = groups that failed (hbls_last_batch_info)

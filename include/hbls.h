@@ -116,7 +116,7 @@ int hbls_aggregate_verify_batch(const hbls_committee* c, size_t B, const uint8_t
  *   (prod_j [e(B, sigma_j) e(-apk_j, H_j)]^{r_j} == 1; r_j = a_j + b_j z^2 from a fresh 64-bit draw per group position and call out of
  *   a ChaCha20 stream keyed from /dev/urandom at blsInit).  The rounds of every group that fails or holds an undecodable round are
  *   re-verified exactly (those rounds only), so results are the exact booleans; a bad round survives the batched test with
- *   probability <= 2^-63.  Batches under `rlc_min` rounds (default 6 144, hbls_set_param) always use mode 0, and up to `coop_max`
+ *   probability <= 2^-63.  Batches under `rlc_min` rounds (default 12 288, hbls_set_param) always use mode 0, and up to `coop_max`
  *   rounds the exact check runs one WARP per round (latency form, csrc/vm.cuh) instead of one lane pair.
  * mode 0: the exact per-round check only (identical semantics to N calls of hbls_aggregate_verify). */
 void hbls_set_batch_mode(int mode);

@@ -56,13 +56,25 @@ template <int G> static int aggregate_verify_batch(int mode, uint32_t n, const u
     run_seq(2, 3, [&] { k_mask_aggregate_serial(B, n, table.data(), &total, bitmaps, blen, apk.data()); });     // grid-stride: 6 "threads"
     run_seq(2, 2, [&] { k_g2_decode(B, sigs96, sig.data(), ok_sig.data(), 1); });
     run_seq(3, 1, [&] { k_hash_to_g2(B, msgs, msg_len, hm.data(), ok_hm.data()); });
-    int any_fail = 0;
+    int any_fail = 0; bool two_phase_mismatch = false; std::vector<uint8_t> list_check;
     auto exact = [&](size_t off, size_t cnt, const int* run_if) {
         run_seq(1, (unsigned)cnt, [&] { k_g1_normalize(cnt, apk.data() + off, pkneg.data() + off, 1, run_if); });
         run_pair([&] { k_pairing_verify_split(cnt, sig.data() + off, pkneg.data() + off, hm.data() + off, ok_sig.data() + off, ok_hm.data() + off,
                                               (const uint8_t*)nullptr, results + off, run_if); });
         run_seq(1, 2, [&] { k_pairing_fixup(cnt, sig.data() + off, pkneg.data() + off, hm.data() + off, ok_sig.data() + off, ok_hm.data() + off,
                                             (const uint8_t*)nullptr, results + off, run_if); });
+        if (run_if == nullptr && cnt) {      // the same verdicts through the line / accumulator kernels with "groups" of one round (hbls.cu launch_exact_two_phase)
+            std::vector<uint8_t> bad1(cnt), verdict(cnt, 0xee), res2(cnt, 0xee);
+            std::vector<fp> lines((size_t)HB_ML_STEPS * 3 * 2 * cnt * 2);
+            run_seq(1, (unsigned)cnt, [&] { k_exact_prepare(cnt, (const uint32_t*)nullptr, sig.data() + off, pkneg.data() + off, hm.data() + off, ok_sig.data() + off, ok_hm.data() + off,
+                                                            (const uint8_t*)nullptr, (g1a*)nullptr, (g2a*)nullptr, (g2a*)nullptr, bad1.data(), res2.data()); });
+            run_pair([&] { k_rlc_lines_split<1>(cnt, 0, cnt, pkneg.data() + off, hm.data() + off, sig.data() + off, lines.data()); });
+            run_pair([&] { k_rlc_accum_split<1>(cnt, 0, cnt, lines.data(), bad1.data(), verdict.data()); });
+            run_seq(1, (unsigned)cnt, [&] { k_exact_publish(cnt, (const uint32_t*)nullptr, verdict.data(), res2.data()); });
+            run_seq(1, 2, [&] { k_pairing_fixup(cnt, sig.data() + off, pkneg.data() + off, hm.data() + off, ok_sig.data() + off, ok_hm.data() + off,
+                                                (const uint8_t*)nullptr, res2.data(), (const int*)nullptr); });
+            if (std::memcmp(res2.data(), results + off, cnt) != 0) two_phase_mismatch = true;
+        }
     };
     if (mode == 1 && B >= (size_t)G) {
         const size_t ng = B / G, nr = ng * G, tail = B - nr;
@@ -93,7 +105,22 @@ template <int G> static int aggregate_verify_batch(int mode, uint32_t n, const u
         run_seq(2, (unsigned)((nr + 1) / 2), [&] { k_rlc_finish(nr, ng, group_ok.data(), results, list.data(), counts); });
         run_seq(1, 3, [&] { k_g1_normalize_list(&counts[0], list.data(), apk.data(), pkneg.data(), 1); });
         run_pair([&] { k_pairing_verify_split_list(&counts[0], list.data(), sig.data(), pkneg.data(), hm.data(), ok_sig.data(), ok_hm.data(), (const uint8_t*)nullptr, results); });
+        std::vector<uint8_t> res_before(results, results + B);
+        {   // the list through the line / accumulator kernels (gathered "groups" of one round, device-side count): same verdicts
+            std::vector<uint8_t> res2(B); std::vector<uint32_t> list2(B); unsigned counts2[2] = {0, 0};
+            run_seq(2, (unsigned)((nr + 1) / 2), [&] { k_rlc_finish(nr, ng, group_ok.data(), res2.data(), list2.data(), counts2); });
+            std::vector<g1a> pk_c(B); std::vector<g2a> hm_c(B), sig_c(B); std::vector<uint8_t> bad1(B, 0), verdict(B, 0xee);
+            std::vector<fp> lines((size_t)HB_ML_STEPS * 3 * 2 * (nr ? nr : 1) * 2);
+            run_seq(1, (unsigned)nr, [&] { k_exact_prepare(nr, list2.data(), sig.data(), pkneg.data(), hm.data(), ok_sig.data(), ok_hm.data(), (const uint8_t*)nullptr,
+                                                           pk_c.data(), hm_c.data(), sig_c.data(), bad1.data(), res2.data(), &counts2[0]); });
+            run_pair([&] { k_rlc_lines_split<1>(nr, 0, nr, pk_c.data(), hm_c.data(), sig_c.data(), lines.data(), &counts2[0]); });
+            run_pair([&] { k_rlc_accum_split<1>(nr, 0, nr, lines.data(), bad1.data(), verdict.data(), &counts2[0]); });
+            run_seq(1, (unsigned)nr, [&] { k_exact_publish(nr, list2.data(), verdict.data(), res2.data(), &counts2[0]); });
+            run_seq(1, 2, [&] { k_pairing_fixup_list(&counts2[0], list2.data(), sig.data(), pkneg.data(), hm.data(), ok_sig.data(), ok_hm.data(), (const uint8_t*)nullptr, res2.data()); });
+            list_check = std::move(res2);
+        }
         run_seq(1, 2, [&] { k_pairing_fixup_list(&counts[0], list.data(), sig.data(), pkneg.data(), hm.data(), ok_sig.data(), ok_hm.data(), (const uint8_t*)nullptr, results); });
+        if (std::memcmp(list_check.data(), results, nr) != 0) two_phase_mismatch = true;
         any_fail = counts[0] != 0;
         if (groups_failed_out) *groups_failed_out = (int)counts[1];
         if (tail) exact(nr, tail, nullptr);
@@ -102,6 +129,7 @@ template <int G> static int aggregate_verify_batch(int mode, uint32_t n, const u
         exact(0, B, nullptr);
     }
     if (any_fail_out) *any_fail_out = any_fail;
+    if (two_phase_mismatch) return -7;
     return 0;
 }
 extern "C" int emu_aggregate_verify_batch(int mode, uint32_t n, const uint8_t* pks48, size_t B, const uint8_t* bitmaps, size_t blen,

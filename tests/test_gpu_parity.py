@@ -520,12 +520,12 @@ def test_config4_ten_thousand_triples_one_percent_invalid(gbls, oracle):
         else: pk[48 * i:48 * i + 48] = b"\xff" * 48
     old = gbls.GetParam("rlc_min")
     try:
-        gbls.SetParam("rlc_min", 1024)               # batched groups (default threshold 6 144: below it the warp-per-item exact kernel is faster)
+        gbls.SetParam("rlc_min", 1024)               # batched groups (the default threshold is higher: below it the exact forms are faster)
         res = gbls.VerifyBatch(bytes(pk), bytes(sg), bytes(mm), 32)
         info = gbls.LastBatchInfo()
     finally: gbls.SetParam("rlc_min", old)
     assert info["mode"] == 1 and info["group_size"] == 4 and info["groups"] == k // 4
-    # default thresholds: 10 000 items >= rlc_min (6 144) -> batched groups as well; forcing the exact warp-per-item path must agree
+    # default thresholds decide the form of the second call; forcing the exact warp-per-item path must agree
     assert gbls.VerifyBatch(bytes(pk), bytes(sg), bytes(mm), 32) == res and gbls.LastBatchInfo()["mode"] == (1 if k >= old else 0)
     old_c = gbls.GetParam("coop_max")
     try:
