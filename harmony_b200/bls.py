@@ -84,6 +84,7 @@ def lib():
         sig("hbls_aggregate_verify_batch", c.c_int, vp, sz, vp, sz, vp, vp, sz, vp)
         sig("hbls_aggregate_verify_batch_device", c.c_int, vp, sz, vp, sz, vp, vp, sz, vp, vp)
         sig("hbls_verify_batch", c.c_int, sz, vp, vp, vp, sz, vp)
+        sig("hbls_verify_batch_status", c.c_int, sz, vp, vp, vp, sz, vp)
         sig("hbls_sign_hash_batch", c.c_int, sz, vp, vp, sz, vp, vp)
         sig("hbls_get_public_key_batch", c.c_int, sz, vp, vp)
         sig("hbls_map_to_g2", c.c_int, u8p, sz, vp)
@@ -322,6 +323,16 @@ def VerifyBatch(pks48: bytes, sigs96: bytes, msgs: bytes, msg_len: int) -> bytes
     rc = _need().hbls_verify_batch(k, _buf(pks48), _buf(sigs96), _buf(msgs), msg_len, res)
     if rc != 0: raise HblsError(f"hbls_verify_batch rc={rc}")
     return res.raw[:k]
+
+VB_BAD_SIG, VB_OK, VB_BAD_SIG_ENCODING, VB_BAD_KEY_ENCODING = 0, 1, 3, 4
+def VerifyBatchStatus(pks48: bytes, sigs96: bytes, msgs: bytes, msg_len: int) -> bytes:
+    """hbls_verify_batch_status: one VB_* byte per triple -- which of BytesToBLSPublicKey / Sign.Deserialize / VerifyHash failed,
+    in the order the reference meets them (consensus/view_change_msg.go:139-190, consensus/checks.go:20-39)."""
+    k = len(sigs96) // 96
+    st = ctypes.create_string_buffer(k if k else 1)
+    rc = _need().hbls_verify_batch_status(k, _buf(pks48), _buf(sigs96), _buf(msgs), msg_len, st)
+    if rc != 0: raise HblsError(f"hbls_verify_batch_status rc={rc}")
+    return st.raw[:k]
 
 PARTIAL_BYTES = 872
 def RlcPartial(pks48: bytes, sigs96: bytes, msgs: bytes, msg_len: int) -> bytes:

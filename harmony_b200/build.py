@@ -42,7 +42,7 @@ def build_host(force=False):
     """C++ host mirror (header-only hbls_host.hpp) + its test driver, linked against libhbls.so."""
     hd = os.path.join(ROOT, "harmony_b200", "host")
     src = os.path.join(hd, "hbls_host_test.cpp")
-    srcs = [src, os.path.join(hd, "hbls_host.hpp"), os.path.join(ROOT, "include", "hbls.h")]
+    srcs = [src, os.path.join(hd, "hbls_host.hpp"), os.path.join(hd, "hbls_consensus.hpp"), os.path.join(hd, "hbls_keyfile.hpp"), os.path.join(ROOT, "include", "hbls.h")]
     if not force and _newer(HOSTTEST, srcs) and os.path.getmtime(HOSTTEST) >= os.path.getmtime(LIB):
         return HOSTTEST
     cmd = ["g++", "-O2", "-std=c++17", "-Wall", "-o", HOSTTEST, src, "-L" + LIBDIR, "-lhbls", "-Wl,-rpath,$ORIGIN", "-pthread", "-ldl", "-lrt"]

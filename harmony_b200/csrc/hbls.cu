@@ -1067,16 +1067,14 @@ int hbls_aggregate_verify_items(size_t k, const hbls_committee* const* committee
     return 0;
 }
 
-int hbls_verify_batch(size_t k, const uint8_t* pk48, const uint8_t* sig96, const uint8_t* msgs, size_t msg_len, uint8_t* results) {
-    if (int e = ensure_init()) return e;
-    if (k == 0) return 0;
-    std::lock_guard<std::mutex> lk(g.mu);
-    Scratch* sc; if (int e = reserve(g.stream, verify_scratch_bytes(k) + k * (48 + 96 + msg_len + 1) + 4096, &sc)) return e;
+// shared body of hbls_verify_batch / hbls_verify_batch_status; flags_out (nullable): k_pack_flags bytes per item
+static int verify_batch_locked(size_t k, const uint8_t* pk48, const uint8_t* sig96, const uint8_t* msgs, size_t msg_len, uint8_t* results, uint8_t* flags_out) {
+    Scratch* sc; if (int e = reserve(g.stream, verify_scratch_bytes(k) + k * (48 + 96 + msg_len + 2) + 4096, &sc)) return e;
     ensure_stage_events(sc);
     Arena ar{sc->base, 0, sc->cap};
     VerifyBufs v = carve_verify(ar, k);
     uint8_t* dpk = ar.take<uint8_t>(k * 48); uint8_t* dsig = ar.take<uint8_t>(k * 96); uint8_t* dmsg = ar.take<uint8_t>(k * msg_len + 1);
-    uint8_t* dres = ar.take<uint8_t>(k);
+    uint8_t* dres = ar.take<uint8_t>(k); uint8_t* dflags = ar.take<uint8_t>(k);
     CK(cudaMemcpyAsync(dpk, pk48, k * 48, cudaMemcpyHostToDevice, g.stream));
     CK(cudaMemcpyAsync(dsig, sig96, k * 96, cudaMemcpyHostToDevice, g.stream));
     if (msg_len) CK(cudaMemcpyAsync(dmsg, msgs, k * msg_len, cudaMemcpyHostToDevice, g.stream));
@@ -1086,7 +1084,33 @@ int hbls_verify_batch(size_t k, const uint8_t* pk48, const uint8_t* sig96, const
     LAUNCH(k_g1_decode_jac, heavy_blocks(k), TPB, g.stream, k, dpk, v.apk, v.ok_pk, 1);
     launch_verify_tail(k, v, sc, dsig, dmsg, (uint32_t)msg_len, v.ok_pk, dres, g.stream, all_messages_equal(msgs, k, msg_len));
     CK(cudaMemcpyAsync(results, dres, k, cudaMemcpyDeviceToHost, g.stream));
+    if (flags_out) {
+        LAUNCH(k_pack_flags, blocks_for(k, 256), 256, g.stream, k, v.ok_sig, v.ok_hm, (const uint8_t*)v.ok_pk, dflags);
+        CK(cudaMemcpyAsync(flags_out, dflags, k, cudaMemcpyDeviceToHost, g.stream));
+    }
     CK(cudaStreamSynchronize(g.stream));
+    return 0;
+}
+int hbls_verify_batch(size_t k, const uint8_t* pk48, const uint8_t* sig96, const uint8_t* msgs, size_t msg_len, uint8_t* results) {
+    if (int e = ensure_init()) return e;
+    if (k == 0) return 0;
+    std::lock_guard<std::mutex> lk(g.mu);
+    return verify_batch_locked(k, pk48, sig96, msgs, msg_len, results, nullptr);
+}
+// same check, but the caller learns WHY an item failed, in the order the reference meets the errors: the sender key is decoded
+// first (BytesToBLSPublicKey, consensus/view_change_msg.go:159), then the signature (Sign.Deserialize, :168-179), then VerifyHash
+int hbls_verify_batch_status(size_t k, const uint8_t* pk48, const uint8_t* sig96, const uint8_t* msgs, size_t msg_len, uint8_t* status) {
+    if (int e = ensure_init()) return e;
+    if (k == 0) return 0;
+    if (!status) return HBLS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(g.mu);
+    std::vector<uint8_t> flags(k);
+    if (int e = verify_batch_locked(k, pk48, sig96, msgs, msg_len, status, flags.data())) return e;
+    for (size_t j = 0; j < k; j++) {
+        if (!(flags[j] & 4)) status[j] = HBLS_VB_BAD_KEY_ENCODING;
+        else if (!(flags[j] & 1)) status[j] = HBLS_VB_BAD_SIG_ENCODING;
+        else status[j] = status[j] == 1 ? HBLS_VB_OK : HBLS_VB_BAD_SIG;
+    }
     return 0;
 }
 

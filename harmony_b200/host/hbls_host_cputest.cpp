@@ -4,6 +4,7 @@
 // public-key LRU (crypto/bls/mask.go:35-55), and that every group operation refuses to run without blsInit (no CPU fallback).
 #include <cstdio>
 #include "hbls_host.hpp"
+#include "hbls_consensus.hpp"
 using namespace harmony;
 static int g_fail = 0;
 #define CHECK(c) do { if (!(c)) { fprintf(stderr, "CHECK FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); g_fail++; } } while (0)
@@ -70,6 +71,19 @@ int main() {
             CHECK(blsgen::LoadBLSKeyHexWithPassPhrase(std::string(raw.begin(), raw.end()), t.pass, sk, &err) && sk == t.sk);   // binary form fall-back
         }
         std::string sk, err; CHECK(!blsgen::LoadBLSKeyHexWithPassPhrase("", "", sk, &err) && !blsgen::LoadBLSKeyHexWithPassPhrase("zz", "", sk, &err));
+    }
+    // crypto/hash/hash.go Keccak256 (legacy padding) and the 48-byte view of a message the hash-to-G2 map reads
+    {
+        auto kh = [](const std::string& m) { auto d = hash::Keccak256((const uint8_t*)m.data(), m.size()); return bls_core::hex(d.data(), d.size()); };
+        CHECK(kh("") == "c5d2460186f7233c927e7db2dcc703c0e500b653ca82273b7bfad8045d85a470");
+        CHECK(kh("abc") == "4e03657aea45a94fc7d47ba826c8d667c0d1e6e33a64a036ec44f58fa12d6c45");
+        CHECK(kh("harmony-one") == "1eaafe555c82d1cb51afd79875683437858a9fb883c07487717921757d6717f9");      // staking/types/validator.go:30
+        CHECK(kh(std::string(135, 'a')) == "34367dc248bbd832f4e3e69dfaac2f92638bd0bbd18f2912ba4ef454919cf446");      // one-byte 0x81 padding
+        CHECK(kh(std::string(136, 'a')).substr(0, 16) == "a6c4d403279fe3e0" && kh(std::string(300, 'a')).substr(0, 16) == "5b7e0e47a96f32a8");
+        consensus::Bytes blob; consensus::put48(blob, consensus::NIL()); consensus::put48(blob, consensus::le64(0x0102));
+        consensus::put48(blob, consensus::Bytes(200, 7));
+        CHECK(blob.size() == 144 && blob[0] == 1 && blob[1] == 0 && blob[47] == 0 && blob[48] == 2 && blob[49] == 1 && blob[50] == 0 && blob[96] == 7 && blob[143] == 7);
+        CHECK(consensus::ValidPayloadLength == 128);
     }
     // no CPU fallback: without blsInit (no device here) group operations fail instead of computing on the host
     bls_core::PublicKey q{}; std::vector<uint8_t> k48(48, 0); k48[0] = 1;

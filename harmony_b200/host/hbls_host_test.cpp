@@ -4,9 +4,12 @@
 //   consensus/quorum/quorom_test.go    TestSubmitVote (:73-125, AggregateVotes == manual Add chain),
 //                                      TestAddNewVoteInvalidAggregateSig (:381-501), TestInvalidAggregateSig (:503-552)
 //   consensus/signature/signature_test.go, internal/chain/sig.go + engine.go:619-642
+//   consensus message signatures (consensus_service.go:115-119, checks.go:20-56) incl. the reference's signature vector, and a small
+//   view-change storm + NEWVIEW (view_change_construct.go:154-375, view_change.go:445-500) through hbls_consensus.hpp
 #include <cstdio>
 #include <cstdlib>
 #include "hbls_host.hpp"
+#include "hbls_consensus.hpp"
 
 using namespace harmony;
 static int g_fail = 0;
@@ -139,9 +142,75 @@ static void test_codecs_multibls_payload() {
     CHECK(s1->SignHash(std::vector<uint8_t>(8, 0)) == nullptr);
 }
 
+static consensus::Bytes sign_bytes(const bls::PrivateKeyWrapper& k, const consensus::Bytes& m) {
+    std::unique_ptr<bls_core::Sign> s(k.Pri->SignHash(m)); return s ? s->Serialize() : consensus::Bytes();
+}
+static void test_consensus_messages() {
+    using namespace consensus;
+    // the reference's only (sk, message) -> signature vector is signMessage("harmony-one") (staking/types/validator.go:30,525-527;
+    // rosetta/services/construction_create_test.go:460-467)
+    bls_core::SecretKey sk; CHECK(sk.DeserializeHexStr("c6d7603520311f7a4e6aac0b26701fc433b75b38df504cd416ef2b900cd66205"));
+    const std::string m0 = "harmony-one"; const Bytes msg(m0.begin(), m0.end());
+    const Bytes sig = signMessage(msg, &sk);
+    CHECK(bls_core::hex(sig.data(), sig.size()) == "68f800b6adf657b674903e04708060912b893b7c7b500788808247550ab3e186e56a44ebf3ca488f8ed1a42f6cef3a04bd5d2b2b7eb5a767848d3135b362e668ce6bba42c7b9d5666d8e3a83be707b5708e722c58939fe9b07c170f3b7062414");
+    std::unique_ptr<bls_core::PublicKey> pk(sk.GetPublicKey());
+    CHECK(verifyMessageSig(pk.get(), msg, sig).empty());
+    Bytes other = msg; other[0] ^= 1;
+    CHECK(verifyMessageSig(pk.get(), other, sig) == errMsgSig && verifyMessageSig(pk.get(), msg, Bytes(96, 0xff)) == errSigDeserialize);
+    auto errs = verifyMessageSigBatch({pk->Serialize(), pk->Serialize(), Bytes(48, 0xff), pk->Serialize(), pk->Serialize()}, {msg, other, msg, msg, msg},
+                                      {sig, sig, sig, Bytes(96, 0xff), Bytes(50, 1)});
+    CHECK(errs[0].empty() && errs[1] == errMsgSig && errs[2] == errKeyDeserialize && errs[3] == errSigDeserialize && errs[4] == errSigDeserialize);
+
+    // view-change storm on a 7-validator committee (quorum 5)
+    auto keys = make_keys(7);
+    std::vector<bls::PublicKeyWrapper> pubs; for (auto& k : keys) pubs.push_back(*k.Pub);
+    const uint64_t viewID = 41;
+    Bytes bh(32); for (int i = 0; i < 32; i++) bh[i] = (uint8_t)(3 * i + 5);
+    auto proof = [&](int signers, uint8_t bitmap) {
+        std::vector<std::unique_ptr<bls_core::Sign>> ss; std::vector<bls_core::Sign*> ptr;
+        for (int i = 0; i < signers; i++) { ss.emplace_back(keys[i].Pri->SignHash(bh)); ptr.push_back(ss.back().get()); }
+        Bytes p = bh; auto a = bls::AggregateSig(ptr)->Serialize(); p.insert(p.end(), a.begin(), a.end()); p.push_back(bitmap); return p;
+    };
+    const Bytes payload = proof(5, 0x1f), low = proof(4, 0x0f);
+    auto vcmsg = [&](int i, bool m1, const Bytes& pl) {
+        FBFTMessage m; m.ViewID = viewID; m.BlockNum = 9; m.SenderPubkey = Bytes(pubs[i].Bytes.begin(), pubs[i].Bytes.end()); m.LeaderPubkey = m.SenderPubkey;
+        if (m1) { m.Payload = pl; m.Block = {0xc0}; m.ViewchangeSig = sign_bytes(keys[i], pl); } else m.ViewchangeSig = sign_bytes(keys[i], NIL());
+        m.ViewidSig = sign_bytes(keys[i], le64(viewID)); return m;
+    };
+    std::vector<FBFTMessage> storm = {vcmsg(0, true, payload), vcmsg(1, true, payload), vcmsg(2, true, payload), vcmsg(3, false, {}), vcmsg(4, false, {}),
+                                      vcmsg(5, false, {}), vcmsg(6, true, low), vcmsg(0, true, payload), vcmsg(5, false, {})};
+    storm[5].ViewchangeSig = sign_bytes(keys[5], Bytes{0x02});                         // signed 0x02, not NIL
+    storm[8].ViewidSig = sign_bytes(keys[5], le64(viewID + 1));                        // signed another view
+    viewChange vc; CHECK(vc.Init(pubs).empty());
+    const uint64_t l0 = hbls_kernel_launch_count();
+    auto out = vc.ProcessViewChangeMsgs(storm);
+    CHECK(hbls_kernel_launch_count() > l0);
+    for (int i = 0; i < 5; i++) CHECK(out[i].empty());
+    CHECK(out[5] == errVerifyM2 && out[6] == errNoQuorum && out[7] == errDupM3 && out[8] == errViewIDSig);
+    CHECK(vc.m1Payload == payload && vc.bhpBitmap[viewID] == Bytes{0x07} && vc.nilBitmap[viewID] == Bytes{0x18} && vc.viewIDBitmap[viewID] == Bytes{0x1f});
+    // a decider with its own quorum rule (staked vote) accepts the 4-of-7 proof
+    viewChange vc2; CHECK(vc2.Init(pubs).empty()); vc2.isQuorumAchievedByMask = [](const Bytes& bm) { return quorum::CountSlotBits(bm, 7) >= 4; };
+    CHECK(vc2.ProcessViewChangeMsg(storm[6]).empty());
+    // NEWVIEW from what the storm collected
+    Bytes m2s, m2b, m3s, m3b; CHECK(vc.GetM2Bitmap(viewID, m2s, m2b) && vc.GetM3Bitmap(viewID, m3s, m3b) && m2b == Bytes{0x18} && m3b == Bytes{0x1f});
+    CHECK(!vc.GetM2Bitmap(viewID + 1, m2s, m2b)); CHECK(vc.GetM2Bitmap(viewID, m2s, m2b));
+    { bls_core::Sign manual; for (int i = 0; i < 5; i++) { bls_core::Sign s; CHECK(s.Deserialize(storm[i].ViewidSig)); manual.Add(&s); } CHECK(manual.Serialize() == m3s); }
+    FBFTMessage nv; nv.ViewID = viewID; nv.BlockNum = 9; nv.SenderPubkey = storm[0].SenderPubkey; nv.Payload = payload; nv.Block = {0xc0};
+    nv.hasM2 = nv.hasM3 = true; nv.M2AggSig = m2s; nv.M2Bitmap = m2b; nv.M3AggSig = m3s; nv.M3Bitmap = m3b;
+    viewChange validator; CHECK(validator.Init(pubs).empty());
+    CHECK(validator.OnNewViewChecks(nv).empty());
+    { auto bad = nv; bad.M3AggSig = m2s; CHECK(validator.OnNewViewChecks(bad) == errM3Verify); }
+    { auto bad = nv; bad.M2AggSig = m3s; CHECK(validator.OnNewViewChecks(bad) == errM2Verify); }
+    { auto bad = nv; bad.hasM3 = false; CHECK(validator.OnNewViewChecks(bad) == errM3Nil); }
+    { auto bad = nv; bad.Payload[3] ^= 1; CHECK(validator.OnNewViewChecks(bad) == errNewViewM1); }
+    { auto bad = nv; bad.Payload.resize(100); CHECK(validator.OnNewViewChecks(bad) == errPayloadLength); }
+    { auto bad = nv; bad.M3AggSig.assign(96, 0xff); CHECK(validator.OnNewViewChecks(bad) == errSigDeserialize); }
+    { auto bad = nv; bad.M3Bitmap = {0x0f}; CHECK(validator.OnNewViewChecks(bad) == errM3Verify); }                  // aggregate of 5 against 4 keys
+}
+
 int main() {
     if (bls_core::Init(bls_core::BLS12_381) != 0) { fprintf(stderr, "bls.Init failed: CUDA device required (no CPU fallback)\n"); return 2; }
-    test_mask(); test_quorum_votes(); test_codecs_multibls_payload();
+    test_mask(); test_quorum_votes(); test_codecs_multibls_payload(); test_consensus_messages();
     if (g_fail) { fprintf(stderr, "%d check(s) failed\n", g_fail); return 1; }
     printf("hbls_host_test: all checks passed\n");
     return 0;

@@ -150,6 +150,19 @@ int hbls_aggregate_verify_batch_device(const hbls_committee* c, size_t B, const 
  * view-change storm consensus/view_change_construct.go:237-375): results[j] = Deserialize ok && VerifyHash. */
 int hbls_verify_batch(size_t k, const uint8_t* pk48, const uint8_t* sig96, const uint8_t* msgs, size_t msg_len,
                       uint8_t* results);
+/* Same check with the reason of a failure, in the order the reference meets the errors when it parses and then checks a
+ * message (consensus/view_change_msg.go:139-190 ParseViewChangeMessage: BytesToBLSPublicKey(sender), Sign.Deserialize; then
+ * consensus/checks.go:20-39 verifyMessageSig / checks.go:186, view_change_construct.go:266,339 VerifyHash):
+ *   HBLS_VB_BAD_KEY_ENCODING  pk48 does not decode to a point of G1 (crypto/bls/mask.go:35-55 returns the error)
+ *   HBLS_VB_BAD_SIG_ENCODING  sig96 does not decode to a point of G2 ("err blsSignatureDeserialize")
+ *   HBLS_VB_BAD_SIG           both decode, VerifyHash(pk, msg) is false
+ *   HBLS_VB_OK                valid */
+#define HBLS_VB_BAD_SIG          0
+#define HBLS_VB_OK               1
+#define HBLS_VB_BAD_SIG_ENCODING 3
+#define HBLS_VB_BAD_KEY_ENCODING 4
+int hbls_verify_batch_status(size_t k, const uint8_t* pk48, const uint8_t* sig96, const uint8_t* msgs, size_t msg_len,
+                             uint8_t* status);
 
 /* Multi-committee batch (BASELINE configs[2]: 4 shards x 250 validators, 4 distinct messages, one batched pairing; crosslinks:
  * internal/chain/engine.go:592-604, node/harmony/node_cross_link.go:69-90).  Item j = (committees[j], bitmap_j, sig_j, msg_j);
