@@ -244,6 +244,37 @@ def other_configs(bls, world, rank, dist, device):
         ms, res = _median_ms(lambda: bls.VerifyBatch(pks4, sigs4, msgs4, 32))
         assert res == b"\x01" * k
         c4["one_gpu_verify_batch_all_valid"] = {"ms": ms, "triples_per_s": k / (ms * 1e-3)}
+    if rank == 0:
+        # ---- the storm as the reference meets it: one VIEWCHANGE message from every validator of a 250-key committee, 2/3 of them
+        # with an embedded PREPARED proof (consensus/view_change_construct.go:237-375 via harmony_b200/consensus.py): two device
+        # calls -- 2 n independent triples (messages of 1 / 8 / >= 128 bytes in one 48-byte batch) + the n_m1 quorum proofs
+        from harmony_b200 import consensus as cs
+        n = N_COMMITTEE; vid = 7
+        sksv = [wl.seeded_sk("bench-vc", i) for i in range(n)]
+        blobv = bls.GetPublicKeyBatch(b"".join(wl.sk_bytes(k) for k in sksv)); pksv = [blobv[48 * i:48 * i + 48] for i in range(n)]
+        bh = wl.seeded_bytes("bench-vc/hash", 0, 32); bmq = wl.bitmap_with_k("bench-vc/prep", 0, n, wl.quorum_k(n))
+        aggp, _ = bls.SignHashBatch(wl.sk_bytes(wl.round_signer_sum(sksv, bmq)), bh, 32)
+        payload = bh + aggp + bmq
+        is_m1 = [i % 3 != 2 for i in range(n)]
+        skb = b"".join(wl.sk_bytes(k) for k in sksv)
+        s_vc, _ = bls.SignHashBatch(skb, b"".join(cs._m48(payload if is_m1[i] else cs.NIL) for i in range(n)), 48)
+        s_id, _ = bls.SignHashBatch(skb, cs._m48(vid.to_bytes(8, "little")) * n, 48)
+        vmsgs = [cs.FBFTMessage(ViewID=vid, BlockNum=1, SenderPubkey=pksv[i], LeaderPubkey=pksv[0], Payload=payload if is_m1[i] else b"",
+                                Block=b"\xc0" if is_m1[i] else b"", ViewchangeSig=s_vc[96 * i:96 * i + 96], ViewidSig=s_id[96 * i:96 * i + 96]) for i in range(n)]
+        vc = cs.viewChange(pksv)
+        def storm():
+            vc.Reset(); return vc.ProcessViewChangeMsgs(vmsgs)
+        ms, res = _median_ms(storm, 5)
+        assert res == [None] * n and not vc.IsM1PayloadEmpty()
+        m3sig, m3bm = vc.GetM3Bitmap(vid)
+        nv = cs.FBFTMessage(ViewID=vid, BlockNum=1, SenderPubkey=pksv[0], Payload=payload, Block=b"\xc0", M3AggSig=m3sig, M3Bitmap=m3bm)
+        nv.M2AggSig, nv.M2Bitmap = vc.GetM2Bitmap(vid)
+        ms_nv, err = _median_ms(lambda: vc.OnNewViewChecks(nv), 5)
+        assert err is None
+        n_m1 = sum(is_m1)
+        c4["view_change_handlers"] = {"messages": n, "m1": n_m1, "m2": n - n_m1, "signature_checks": 2 * n + n_m1, "device_calls": 2, "ms": ms,
+                                      "messages_per_s": n / (ms * 1e-3), "new_view_checks_ms": ms_nv,
+                                      "what": "ProcessViewChangeMsgs over 250 VIEWCHANGE messages (errors and state identical to the sequential reference handlers: tests/test_consensus.py); NEWVIEW = M3 + M2 + M1 aggregate checks in one call"}
     def split(sg, ms_):
         if world > 1: dist.barrier()
         t0 = time.perf_counter()
