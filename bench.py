@@ -122,11 +122,11 @@ def cpu_rounds_per_s(orc, pks, bitmaps, sigs, msgs, blen, budget_s, threads):
 # (mul, sqr); "scale"/"pairing" are per GROUP of G rounds, the others per round of the 167/200/250-signer workload.
 EXEC_FP_OPS = {
     False: {"mask": (368.5, 137.8), "decode": (1478.0, 756.0), "hash": (3173.4, 1524.0),
-            4: {"scale": (4927.0, 2587.0), "pairing": (34661, 764)}, 8: {"scale": (11255.0, 5032.0), "pairing": (54329, 764)}},
+            4: {"scale": (4927.0, 2587.0), "pairing": (32456, 764)}, 8: {"scale": (11255.0, 5032.0), "pairing": (50360, 764)}},
     True: {"mask": (368.5, 137.8), "decode": (1478.0, 756.0), "hash": (3004.2, 855.5),
-            4: {"scale": (4571.5, 1257.0), "pairing": (34661, 764)}, 8: {"scale": (10544.0, 2372.0), "pairing": (54329, 764)}},      # shared inversions (HB_BATCH_INV, 8 items per inversion)
+            4: {"scale": (4571.5, 1257.0), "pairing": (32456, 764)}, 8: {"scale": (10544.0, 2372.0), "pairing": (50360, 764)}},      # shared inversions (HB_BATCH_INV, 8 items per inversion)
 }
-EXEC_FP_OPS_LINES = {4: (11105, 0), 8: (19989, 0)}     # the line kernel's share of "pairing" in the two-kernel form (k_rlc_lines_split; tests/test_emu_logic.py)
+EXEC_FP_OPS_LINES = {4: (8900, 0), 8: (16020, 0)}     # the line kernel's share of "pairing" in the two-kernel form (k_rlc_lines_split; tests/test_emu_logic.py)
 EXACT_PAIRING_FP_OPS = (20055, 497)      # exact mode: 2-pair Miller loop + final exponentiation per round (oracle counter, stages 4 + 5)
 def rlc_group_size(B, sm_count, tpb_split=512):
     """Mirror of the host's choice in hbls.cu launch_verify_tail: 8 when B/8 lane pairs still fill every SM, else 4."""

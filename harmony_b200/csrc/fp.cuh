@@ -215,6 +215,19 @@ HB_DEV void fp_sub_regs(uint32_t* r, const uint32_t* a, const uint32_t* b) {
 HB_FPFN void fp_add(fp& r, const fp& a, const fp& b) { fp_add_regs(r.l, a.l, b.l); }
 HB_FPFN void fp_sub(fp& r, const fp& a, const fp& b) { fp_sub_regs(r.l, a.l, b.l); }
 HB_FPFN void fp_dbl(fp& r, const fp& a) { fp_add_regs(r.l, a.l, a.l); }
+// r = a / 2 mod p: (a + (a odd ? p : 0)) >> 1.  a < p < 2^381, so the sum fits the 12 limbs; linear, hence valid on Montgomery forms.
+// (replaces multiplications by the constant 1/2 in the Miller doubling step: ~40 ALU instructions instead of 300 IMAD)
+HB_DEV void fp_half(fp& r, const fp& a) {
+    const uint32_t m = 0u - (a.l[0] & 1u);
+    uint32_t t[12];
+    add_cc(t[0], a.l[0], HB_P0 & m);
+#pragma unroll
+    for (int j = 1; j < 11; j++) addc_cc(t[j], a.l[j], p_limb(j) & m);
+    addc(t[11], a.l[11], HB_P11 & m);
+#pragma unroll
+    for (int j = 0; j < 11; j++) r.l[j] = (t[j] >> 1) | (t[j + 1] << 31);
+    r.l[11] = t[11] >> 1;
+}
 HB_DEV bool fp_is_zero(const fp& a) {
     uint32_t o = 0;
 #pragma unroll

@@ -13,11 +13,12 @@ typedef g2proj_t<fp2> g2proj;
 // doubling step; line = l0 + (l2 * xP) w^2 + (l3 * yP) w^3 up to an Fp2 factor
 template <class E> HB_NOINLINE void ml_dbl(g2proj_t<E>& t, E& l0, E& l2, E& l3) {
     hb_lockstep2<E>();
-    E A, B, C, Ee, F, H, s, b3; fp inv2;
-    fp_set(inv2, K_INV2); fp2_const(b3, K_B2_3);
-    fp2_mul(A, t.x, t.y); fp2_mul_fp(A, A, inv2);
+    // 4 products + 6 squarings of Fp2 (24 Fp products): the halvings and the product by the twist constant 3 b' = 12 (1 + i) are
+    // shifts / additions (fp2_half, fp2_mul_twist3b), not multiplications by constants (7 Fp products fewer per step than round 1)
+    E A, B, C, Ee, F, H, s;
+    fp2_mul(A, t.x, t.y); fp2_half(A, A);
     fp2_sqr(B, t.y); fp2_sqr(C, t.z);
-    fp2_mul(Ee, b3, C);
+    fp2_mul_twist3b(Ee, C);
     fp2_dbl(F, Ee); fp2_add(F, F, Ee);
     fp2_add(H, t.y, t.z); fp2_sqr(H, H); fp2_sub(H, H, B); fp2_sub(H, H, C);     // 2YZ
     fp2_sub(l0, B, Ee);                                                           // Y^2 - 3b'Z^2
@@ -25,7 +26,7 @@ template <class E> HB_NOINLINE void ml_dbl(g2proj_t<E>& t, E& l0, E& l2, E& l3) 
     l3 = H;
     E x3, y3, e2;
     fp2_sub(x3, B, F); fp2_mul(x3, x3, A);
-    fp2_add(y3, B, F); fp2_mul_fp(y3, y3, inv2); fp2_sqr(y3, y3);
+    fp2_add(y3, B, F); fp2_half(y3, y3); fp2_sqr(y3, y3);
     fp2_sqr(e2, Ee); fp2_dbl(s, e2); fp2_add(s, s, e2); fp2_sub(y3, y3, s);
     fp2_mul(t.z, B, H); t.x = x3; t.y = y3;
 }

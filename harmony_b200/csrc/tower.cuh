@@ -257,6 +257,7 @@ HB_ATTR_SUB void fp2_sub(fp2& r, const fp2& x, const fp2& y) { fp_sub(r.a, x.a, 
 HB_ATTR_NEG void fp2_neg(fp2& r, const fp2& x) { fp_neg(r.a, x.a); fp_neg(r.b, x.b); }
 HB_ATTR_CONJ void fp2_conj(fp2& r, const fp2& x) { r.a = x.a; fp_neg(r.b, x.b); }
 HB_ATTR_DBL void fp2_dbl(fp2& r, const fp2& x) { fp_dbl(r.a, x.a); fp_dbl(r.b, x.b); }
+HB_DEV void fp2_half(fp2& r, const fp2& x) { fp_half(r.a, x.a); fp_half(r.b, x.b); }
 HB_DEV void fp2_const(fp2& r, const uint32_t k[2][12]) { fp_set(r.a, k[0]); fp_set(r.b, k[1]); }
 HB_DEV void fp2_cmov(fp2& r, const fp2& x, bool c) { fp_cmov(r.a, x.a, c); fp_cmov(r.b, x.b, c); }
 
@@ -442,6 +443,7 @@ HB_ATTR_H void fp2_neg(fp2h& r, const fp2h& x) { fp_neg(r.c, x.c); }
 HB_ATTR_H void fp2_dbl(fp2h& r, const fp2h& x) { fp_dbl(r.c, x.c); }
 HB_ATTR_H void fp2_conj(fp2h& r, const fp2h& x) { fp n; fp_neg(n, x.c); r.c = x.c; fp_cmov(r.c, n, fp2h_role() == 1); }
 HB_ATTR_MULFP void fp2_mul_fp(fp2h& r, const fp2h& x, const fp& k) { fp_mul(r.c, x.c, k); }
+HB_DEV void fp2_half(fp2h& r, const fp2h& x) { fp_half(r.c, x.c); }
 // xi * (a + b i) = (a - b) + (a + b) i
 HB_ATTR_H void fp2_mul_xi(fp2h& r, const fp2h& x) {
     fp o, s, d; fp2h_partner(o, x.c);
@@ -533,6 +535,9 @@ template <class E> HB_DEV void hb_lockstep3() {
 
 // ------------------------------------------------------------------ Fp6 / Fp12, generic over the Fp2 carrier E (fp2 or fp2h)
 template <class E> struct fp6_t { E c0, c1, c2; };
+// 3 b' x for the twist constant b' = 4 (1 + i): 12 (1 + i) x by additions only (mul_xi, three doublings, one addition) instead of an
+// Fp2 product by a constant
+template <class E> HB_DEV void fp2_mul_twist3b(E& r, const E& x) { E t, u; fp2_mul_xi(t, x); fp2_dbl(t, t); fp2_dbl(t, t); fp2_dbl(u, t); fp2_add(r, t, u); }
 template <class E> struct fp12_t { fp6_t<E> c0, c1; };
 typedef fp6_t<fp2> fp6;
 typedef fp12_t<fp2> fp12;
