@@ -57,7 +57,7 @@
 
 namespace hb {
 
-struct fp { uint32_t l[12]; };
+struct alignas(16) fp { uint32_t l[12]; };      // 16-byte alignment: 128-bit local / global accesses for whole-element moves
 
 // modulus limbs as immediates (little-endian 32-bit)
 #define HB_P0  0xffffaaabu

@@ -1242,7 +1242,8 @@ int hbls_ballot_box_aggregate(const hbls_ballot_box* b, uint8_t out_sig96[96], u
 
 // ------------------------------------------------------------------ ONE batch split over several GPUs (BASELINE configs[3])
 struct PartialRecord { g2 S; fp2 f[6]; uint32_t n_items; uint32_t n_bad; };
-static_assert(sizeof(PartialRecord) == HBLS_PARTIAL_BYTES, "partial record layout");
+// the wire record is the first HBLS_PARTIAL_BYTES of the struct (field elements are 16-byte aligned: the struct may end in padding)
+static_assert(offsetof(PartialRecord, n_bad) + sizeof(uint32_t) == HBLS_PARTIAL_BYTES && sizeof(PartialRecord) >= HBLS_PARTIAL_BYTES, "partial record layout");
 int hbls_rlc_partial(size_t k, const uint8_t* pk48, const uint8_t* sig96, const uint8_t* msgs, size_t msg_len, uint8_t record[HBLS_PARTIAL_BYTES]) {
     if (int e = ensure_init()) return e;
     if (!record) return HBLS_ERR_ARG;
@@ -1279,21 +1280,21 @@ int hbls_rlc_partial(size_t k, const uint8_t* pk48, const uint8_t* sig96, const 
     CK(cudaMemcpyAsync(counts, v.counts, sizeof counts, cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
     rec.n_items = (uint32_t)k; rec.n_bad = counts[0];
-    memcpy(record, &rec, sizeof rec);
+    memcpy(record, &rec, HBLS_PARTIAL_BYTES);
     return 0;
 }
 int hbls_rlc_fold(size_t n, const uint8_t* records) {
     if (int e = ensure_init()) return e;
     if (!records) return HBLS_ERR_ARG;
     size_t items = 0, bad = 0;
-    for (size_t p = 0; p < n; p++) { PartialRecord r; memcpy(&r, records + p * sizeof r, sizeof r); items += r.n_items; bad += r.n_bad; }
+    for (size_t p = 0; p < n; p++) { PartialRecord r; memcpy(&r, records + p * HBLS_PARTIAL_BYTES, HBLS_PARTIAL_BYTES); items += r.n_items; bad += r.n_bad; }
     if (bad || items == 0) return 0;                                  // an undecodable / identity item somewhere, or nothing to prove: callers verify exactly
     std::lock_guard<std::mutex> lk(g.mu);
     Scratch* sc; if (int e = reserve(g.stream, n * (sizeof(g2) + 6 * sizeof(fp2)) + sizeof(g2) + sizeof(g2a) + 4096, &sc)) return e;
     Arena ar{sc->base, 0, sc->cap};
     g2* dS = ar.take<g2>(n); fp2* dparts = ar.take<fp2>(n * 6); g2* dsum = ar.take<g2>(1); g2a* dsg = ar.take<g2a>(1); uint8_t* dres = ar.take<uint8_t>(1);
     std::vector<g2> hs(n); std::vector<fp2> hf(n * 6);
-    for (size_t p = 0; p < n; p++) { PartialRecord r; memcpy(&r, records + p * sizeof r, sizeof r); hs[p] = r.S; for (int i = 0; i < 6; i++) hf[6 * p + i] = r.f[i]; }
+    for (size_t p = 0; p < n; p++) { PartialRecord r; memcpy(&r, records + p * HBLS_PARTIAL_BYTES, HBLS_PARTIAL_BYTES); hs[p] = r.S; for (int i = 0; i < 6; i++) hf[6 * p + i] = r.f[i]; }
     CK(cudaMemcpyAsync(dS, hs.data(), n * sizeof(g2), cudaMemcpyHostToDevice, g.stream));
     CK(cudaMemcpyAsync(dparts, hf.data(), n * 6 * sizeof(fp2), cudaMemcpyHostToDevice, g.stream));
     LAUNCH(k_g2_sum_jac, 1, HB_SUM_THREADS, g.stream, n, dS, dsum);
