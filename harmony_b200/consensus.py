@@ -46,6 +46,11 @@ errM2Verify = "[VerifyNewViewMsg] Unable to Verify Aggregated Signature of M2 (N
 errNewViewQuorum = "[onNewView] Quorum Not achieved"
 errNewViewM1 = "[onNewView] Failed to Verify Signature for M1 (prepare) message"
 errPayloadLength = "payload not have enough length"              # consensus_service.go:313-315, sig.go:23-25
+errAlreadyReceived = "already received message from the validator"          # leader.go:127-136,233-241 (logged, message dropped)
+errVoteSig = "received invalid BLS signature"                                # leader.go:171-180,287-290
+errDuplicateKey = "duplicate key found in votes"                              # quorum.go:361-363
+errAlreadySubmitted = "vote is already submitted"                             # quorum.go:366-368
+errKeyNotFound = "key not found"                                              # crypto/bls/mask.go:226-233 SetKeysAtomic
 
 # ------------------------------------------------------------------ crypto/hash/hash.go:9-17 (sha3.NewLegacyKeccak256)
 _RC = [0x0000000000000001, 0x0000000000008082, 0x800000000000808A, 0x8000000080008000, 0x000000000000808B, 0x0000000080000001,
@@ -96,6 +101,11 @@ class DeviceBackend:
     def verify_headers(self, com, sigs96, bitmaps, msgs, quorum) -> bytes:
         return com.VerifyHeaders(b"".join(sigs96), b"".join(bitmaps), b"".join(_m48(m) for m in msgs), 48, quorum)
     def aggregate_sigs(self, sigs96) -> bytes: return bls.AggregateSigBytes(sigs96)
+    def aggregate_keys(self, pks48) -> bytes:
+        """sum of a multi-key vote's sender keys (consensus/leader.go:161-169): PublicKey.Add over the LRU-decoded keys"""
+        acc = bls.PublicKey()
+        for k in pks48: acc.Add(bls.BytesToBLSPublicKey(k))          # ValueError when a key does not decode
+        return acc.Serialize()
 
 def _le64(v: int) -> bytes: return int(v).to_bytes(8, "little")
 def _popcount_slots(bitmap: bytes, n: int) -> int:
@@ -305,3 +315,71 @@ class viewChange:
             if m1_err: return m1_err
             if st["m1"] != bls.HDR_OK: return errNewViewM1
         return None
+
+# ------------------------------------------------------------------ the leader's vote collection ("the real CPU bottleneck")
+@dataclass
+class Vote:
+    """A PREPARE / COMMIT message as the leader reads it (consensus/leader.go:110-201, 203-345): one or several sender keys (a
+    validator running several BLS keys signs once with their sum) and the signature bytes in Payload."""
+    SenderPubkeys: List[bytes]
+    Payload: bytes
+
+class VoteCollector:
+    """onPrepare / onCommit over a QUEUE of votes for one phase of one block: every vote of the queue is checked against the same
+    message (block hash, or the commit payload) in ONE device call -- H(m) is hashed once --, then the reference's bookkeeping
+    (already-received test, decider.AddNewVote -> submitVote, bitmap.SetKeysAtomic, quorum transition) runs over the booleans in
+    arrival order.  The reference pays Deserialize + VerifyHash (~2 ms of cgo) per vote under consensus.mutex."""
+    def __init__(self, members: List[bytes], message: bytes, backend=None):
+        self.members = [bytes(m) for m in members]
+        self.index = {m: i for i, m in enumerate(self.members)}
+        self.message = bytes(message)
+        self.be = backend or DeviceBackend()
+        self.blen = (len(self.members) + 7) >> 3
+        self.quorum = 2 * len(self.members) // 3 + 1            # uniform vote: TwoThirdsSignersCount (quorum.go:409-411)
+        self.BallotBox = {}                                       # votepower.Round.BallotBox: key -> (SignerPubKeys, Signature)
+        self.bitmap = bytearray(self.blen)
+    def SignersCount(self) -> int: return len(self.BallotBox)                     # quorum.go:340-352
+    def IsQuorumAchieved(self) -> bool: return self.SignersCount() >= self.quorum  # one-node-one-vote.go:46-54
+    def onVotes(self, votes: List[Vote]):
+        """Returns (errors, quorum_at): errors[i] is None when vote i was counted, else why it was dropped; quorum_at = index of the
+        vote with which the quorum was first reached during this call (None if it was not, or was there before)."""
+        n = len(votes)
+        if n == 0: return [], None
+        pre = [None] * n; pks, sigs = [], []
+        for i, v in enumerate(votes):
+            pk = bytes(48)
+            if len(v.SenderPubkeys) == 1 and len(v.SenderPubkeys[0]) == 48: pk = bytes(v.SenderPubkeys[0])
+            elif len(v.SenderPubkeys) > 1:
+                try: pk = self.be.aggregate_keys(v.SenderPubkeys)
+                except ValueError: pre[i] = errKeyDeserialize
+            else: pre[i] = errKeyDeserialize
+            pks.append(pk); sigs.append(bytes(v.Payload) if len(v.Payload) == 96 else bytes(96))
+        st = self.be.verify_status(pks, sigs, [self.message] * n)
+        out, quorum_at = [], None
+        for i, v in enumerate(votes):
+            was = self.IsQuorumAchieved()
+            e = self._one(v, st[i], pre[i])
+            out.append(e)
+            if e is None and not was and self.IsQuorumAchieved() and quorum_at is None: quorum_at = i
+        return out, quorum_at
+    def _one(self, v, st, pre):
+        keys = [bytes(k) for k in v.SenderPubkeys]
+        if pre is not None or st == bls.VB_BAD_KEY_ENCODING: return errKeyDeserialize       # the message parser decodes the sender keys
+        if any(k in self.BallotBox for k in keys): return errAlreadyReceived       # leader.go:127-136
+        if len(v.Payload) != 96 or st == bls.VB_BAD_SIG_ENCODING: return errSigDeserialize
+        if st != bls.VB_OK: return errVoteSig
+        if len(set(keys)) != len(keys): return errDuplicateKey                      # submitVote (quorum.go:354-377)
+        if any(k not in self.index for k in keys):                                  # SetKeysAtomic fails AFTER the ballots were recorded
+            for k in keys: self.BallotBox[k] = (keys, bytes(v.Payload))
+            return errKeyNotFound
+        for k in keys: self.BallotBox[k] = (keys, bytes(v.Payload))
+        for k in keys: i = self.index[k]; self.bitmap[i >> 3] |= 1 << (i & 7)
+        return None
+    def AggregateVotes(self):
+        """consensus/quorum/quorum.go:164-196: one signature per ballot (a multi-key ballot is stored under each of its keys), then
+        the aggregate in one device call; with the bitmap this is the payload of PREPARED / COMMITTED."""
+        sigs, seen = [], set()
+        for key, (keys, sig) in self.BallotBox.items():
+            if any(k in seen for k in keys): continue
+            seen.update(keys); sigs.append(sig)
+        return (self.be.aggregate_sigs(sigs) if sigs else bytes(96)), bytes(self.bitmap)

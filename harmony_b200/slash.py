@@ -44,11 +44,8 @@ class Record:                                # double-sign.go:52-57
     Reporter: bytes = b""
 
 class DeviceBackend(_ConsensusBackend):
-    """consensus.DeviceBackend + the sum of a ballot's signer keys (PublicKey.Add over the LRU-decoded keys, double-sign.go:241-249)."""
-    def aggregate_keys(self, pks48) -> bytes:
-        acc = bls.PublicKey()
-        for k in pks48: acc.Add(bls.BytesToBLSPublicKey(k))          # ValueError when a key does not decode
-        return acc.Serialize()
+    """consensus.DeviceBackend (verify_status; aggregate_keys = the sum of a ballot's signer keys, double-sign.go:241-249) + a decode
+    probe used only to order two errors of one ballot."""
     def sig_decodes(self, sig: bytes) -> bool:
         try: bls.Sign().Deserialize(sig); return True
         except ValueError: return False

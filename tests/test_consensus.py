@@ -303,3 +303,118 @@ def test_consensus_message_signatures(gbls, oracle, fixtures):
     # raw status entry point: statuses in the order the reference meets the errors
     st = gbls.VerifyBatchStatus(b"".join(pks[:16]), b"".join(sigs[:16]), b"".join(cs.Keccak256(b) for b in bodies[:16]), 32)
     assert st[5] == gbls.VB_BAD_SIG_ENCODING and st[9] == gbls.VB_BAD_KEY_ENCODING and st[11] == gbls.VB_BAD_SIG and st[0] == gbls.VB_BAD_SIG and st[1] == gbls.VB_OK
+
+# ------------------------------------------------------------------ the leader's vote collection (consensus/leader.go:110-345, quorum.go:164-196,354-377)
+class OracleVoteBackend(OracleBackend):
+    def aggregate_keys(self, pks):
+        acc = bytes(48)
+        for k in pks:
+            if len(k) != 48 or not self.o.pk_check(k): raise ValueError("err blsPublicKeyDeserialize")
+            acc = self.o.pk_add(acc, k)
+        return acc
+
+class RefLeader:
+    """onPrepare / onCommit vote by vote, one oracle call per cgo call."""
+    def __init__(self, orc, members, message):
+        self.o = orc; self.members = list(members); self.index = {m: i for i, m in enumerate(members)}; self.message = message
+        self.box = {}; self.bitmap = bytearray((len(members) + 7) >> 3); self.quorum = 2 * len(members) // 3 + 1
+    def on_vote(self, v):
+        o = self.o
+        for k in v.SenderPubkeys:
+            if len(k) != 48 or not o.pk_check(k): return cs.errKeyDeserialize                # parser: BytesToBLSPublicKey
+        if not v.SenderPubkeys: return cs.errKeyDeserialize
+        if any(k in self.box for k in v.SenderPubkeys): return cs.errAlreadyReceived
+        if len(v.Payload) != 96 or not o.sig_check(v.Payload): return cs.errSigDeserialize
+        apk = v.SenderPubkeys[0]
+        if len(v.SenderPubkeys) > 1:
+            apk = bytes(48)
+            for k in v.SenderPubkeys: apk = o.pk_add(apk, k)
+        if not o.verify_hash(v.Payload, apk, self.message): return cs.errVoteSig
+        if len(set(v.SenderPubkeys)) != len(v.SenderPubkeys): return cs.errDuplicateKey
+        for k in v.SenderPubkeys: self.box[k] = (list(v.SenderPubkeys), v.Payload)
+        if any(k not in self.index for k in v.SenderPubkeys): return cs.errKeyNotFound
+        for k in v.SenderPubkeys: i = self.index[k]; self.bitmap[i >> 3] |= 1 << (i & 7)
+        return None
+    def aggregate(self):
+        sigs, seen = [], set()
+        for key, (keys, sig) in self.box.items():
+            if any(k in seen for k in keys): continue
+            seen.update(keys); sigs.append(sig)
+        return self.o.aggregate_sigs(sigs), bytes(self.bitmap)
+
+def build_votes(n, sign, pk_of, message, n_votes):
+    """single-key votes, multi-key votes (3 keys each, one signature with the key sum), and one fault of every kind"""
+    sks = [wl.seeded_sk("votes", i) for i in range(n + 2)]
+    pks = pk_of(sks)
+    members, outsider = pks[:n], pks[n]
+    votes, i = [], 0
+    while len(votes) < n_votes and i + 3 <= n:
+        if len(votes) % 5 == 4:
+            idx = [i, i + 1, i + 2]; i += 3
+            votes.append(cs.Vote([pks[j] for j in idx], sign(sum(sks[j] for j in idx) % wl.R_ORDER, message)))
+        else:
+            votes.append(cs.Vote([pks[i]], sign(sks[i], message))); i += 1
+    f = {}
+    votes[1].Payload = sign(sks[n + 1], message); f[1] = cs.errVoteSig                        # somebody else's signature
+    votes[2].Payload = BAD_SIG; f[2] = cs.errSigDeserialize
+    votes[3].SenderPubkeys = [BAD_KEY]; f[3] = cs.errKeyDeserialize
+    votes.append(cs.Vote(list(votes[0].SenderPubkeys), votes[0].Payload)); f[len(votes) - 1] = cs.errAlreadyReceived
+    votes.append(cs.Vote([outsider], sign(sks[n], message))); f[len(votes) - 1] = cs.errKeyNotFound      # valid signature, not in the committee
+    k = votes[5].SenderPubkeys[0]; sk5 = sks[pks.index(k)]
+    votes[5] = cs.Vote([k, k], sign(2 * sk5 % wl.R_ORDER, message)); f[5] = cs.errDuplicateKey
+    mk = votes[4]                                                                             # multi-key vote whose signature misses one key
+    votes[4] = cs.Vote(list(mk.SenderPubkeys), sign(sum(sks[pks.index(x)] for x in mk.SenderPubkeys[:2]) % wl.R_ORDER, message)); f[4] = cs.errVoteSig
+    votes.append(cs.Vote([mk.SenderPubkeys[0]], sign(sks[pks.index(mk.SenderPubkeys[0])], message)))      # one of its keys alone: fine
+    votes.append(cs.Vote(list(mk.SenderPubkeys), mk.Payload)); f[len(votes) - 1] = cs.errAlreadyReceived   # the full set again: one key has voted
+    return members, votes, f
+
+def check_votes(col, ref, votes, faults, com_verify):
+    got, quorum_at = col.onVotes(votes)
+    exp, q_exp = [], None
+    for i, v in enumerate(votes):
+        was = len(ref.box) >= ref.quorum
+        e = ref.on_vote(v); exp.append(e)
+        if e is None and not was and len(ref.box) >= ref.quorum and q_exp is None: q_exp = i
+    assert got == exp and quorum_at == q_exp
+    for i, e in faults.items(): assert exp[i] == e, (i, exp[i], e)
+    assert col.BallotBox == ref.box and bytes(col.bitmap) == bytes(ref.bitmap)
+    sig, bm = col.AggregateVotes(); rsig, rbm = ref.aggregate()
+    assert (sig, bm) == (rsig, rbm)
+    # the PREPARED / COMMITTED payload verifies against the bitmap -- unless a non-member's vote got in: the reference records the
+    # ballot (decider.AddNewVote) BEFORE bitmap.SetKeysAtomic rejects the key (leader.go:185-196), so its signature is aggregated
+    # without a bit; the mirror reproduces that (callers drop non-members at message validation)
+    assert com_verify(bm, sig) == (cs.errKeyNotFound not in exp)
+    return quorum_at
+
+def test_leader_vote_collection_host_logic(oracle):
+    n = 30; message = wl.commit_payload("votes", 0)
+    sign = lambda sk, m: oracle.sign_hash(wl.sk_bytes(sk), m)
+    members, votes, faults = build_votes(n, sign, lambda ks: [oracle.get_public_key(wl.sk_bytes(k)) for k in ks], message, 22)
+    be = OracleVoteBackend(oracle); och = oracle.committee(members)
+    col = cs.VoteCollector(members, message, backend=be); ref = RefLeader(oracle, members, message)
+    q = check_votes(col, ref, votes, faults, lambda bm, sig: oracle.committee_aggregate_verify(och, bm, sig, message) == 1)
+    assert be.calls["verify_status"] == 1 and q is not None and col.IsQuorumAchieved()
+    members_only = [v for i, v in enumerate(votes) if faults.get(i) != cs.errKeyNotFound]
+    col2 = cs.VoteCollector(members, message, backend=be); col2.onVotes(members_only)
+    sig2, bm2 = col2.AggregateVotes(); assert oracle.committee_aggregate_verify(och, bm2, sig2, message) == 1
+    # a second queue continues from the state of the first
+    more = [cs.Vote(list(votes[0].SenderPubkeys), votes[0].Payload)]
+    assert col.onVotes(more) == ([cs.errAlreadyReceived], None) and col.onVotes([]) == ([], None)
+
+@pytest.mark.gpu
+def test_leader_vote_collection_250(gbls, oracle):
+    """The leader's PREPARE / COMMIT collection for a 250-validator committee (consensus/leader.go:110-345): one device call for the
+    queue, H(m) hashed once; counted votes, drop reasons, quorum index, ballot box, bitmap and the aggregate equal the sequential
+    handlers run over the oracle."""
+    n = 250; message = wl.commit_payload("votes", 1)
+    def pk_of(ks):
+        blob = gbls.GetPublicKeyBatch(b"".join(wl.sk_bytes(k) for k in ks)); return [blob[48 * i:48 * i + 48] for i in range(len(ks))]
+    sign = lambda sk, m: oracle.sign_hash(wl.sk_bytes(sk), m)
+    members, votes, faults = build_votes(n, sign, pk_of, message, 175)
+    com = gbls.Committee(members)
+    col = cs.VoteCollector(members, message); ref = RefLeader(oracle, members, message)
+    q = check_votes(col, ref, votes, faults, lambda bm, sig: com.AggregateVerify(bm, sig, message))
+    assert q is not None and col.SignersCount() >= col.quorum
+    members_only = [v for i, v in enumerate(votes) if faults.get(i) != cs.errKeyNotFound]
+    col2 = cs.VoteCollector(members, message); col2.onVotes(members_only)
+    sig2, bm2 = col2.AggregateVotes(); assert com.AggregateVerify(bm2, sig2, message)
