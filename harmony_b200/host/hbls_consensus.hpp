@@ -6,6 +6,7 @@
 //   consensus/view_change_msg.go:139-190    ParseViewChangeMessage      consensus/checks.go:139-193   onViewChangeSanityCheck
 //   consensus/view_change_construct.go:237-375 ProcessViewChangeMsg, :122-151 GetM2Bitmap / GetM3Bitmap, :154-234 VerifyNewViewMsg
 //   consensus/view_change.go:445-500        onNewView (M3 quorum, M1 proof)
+//   consensus/leader.go:110-345             onPrepare / onCommit (VoteCollector)    staking/slash/double-sign.go:139-262 (slash::VerifyBallots)
 //
 // The reference makes one cgo call per VerifyHash under consensus.mutex.  Here the booleans of a whole batch of VIEWCHANGE
 // messages come from TWO device calls (hbls_verify_batch_status over the 2 N independent triples, hbls_verify_headers over the
@@ -272,5 +273,126 @@ private:
         return "";
     }
 };
+
+// ------------------------------------------------------------------ the leader's vote collection (consensus/leader.go:110-345)
+constexpr const char* errAlreadyReceived = "already received message from the validator";      // leader.go:127-136,233-241
+constexpr const char* errVoteSig = "received invalid BLS signature";                            // leader.go:171-180,287-290
+constexpr const char* errDuplicateKey = "duplicate key found in votes";                          // quorum.go:361-363
+constexpr const char* errKeyNotFound = "key not found";                                          // crypto/bls/mask.go:226-233
+
+// sum of a multi-key sender's keys (leader.go:161-169, double-sign.go:241-249): BytesToBLSPublicKey's LRU + PublicKey.Add
+inline bool aggregateKeys(const std::vector<Bytes>& keys, Bytes& out) {
+    bls_core::PublicKey acc;
+    for (auto& k : keys) { auto pk = bls::BytesToBLSPublicKey(k); if (!pk) return false; acc.Add(pk.get()); }
+    out = acc.Serialize(); return true;
+}
+
+struct Vote { std::vector<Bytes> SenderPubkeys; Bytes Payload; };      // PREPARE / COMMIT as the leader reads it: sender key(s) + signature
+
+// onPrepare / onCommit over a QUEUE of votes for one phase of one block: every vote against the same message in ONE device call (H(m)
+// hashed once), then the reference's bookkeeping (already-received test, AddNewVote -> submitVote, SetKeysAtomic, quorum transition)
+// in arrival order
+class VoteCollector {
+public:
+    struct Ballot { std::vector<Bytes> SignerPubKeys; Bytes Signature; };
+    std::map<Bytes, Ballot> BallotBox;          // votepower.Round.BallotBox: one entry per signer key
+    Bytes bitmap;
+    void Init(const std::vector<bls::PublicKeyWrapper>& members, const Bytes& message) {
+        index_.clear(); for (size_t i = 0; i < members.size(); i++) index_[Bytes(members[i].Bytes.begin(), members[i].Bytes.end())] = i;
+        message_ = message; bitmap.assign((members.size() + 7) >> 3, 0); BallotBox.clear();
+        quorum_ = (size_t)quorum::TwoThirdsSignersCount((int64_t)members.size());
+    }
+    size_t SignersCount() const { return BallotBox.size(); }                       // quorum.go:340-352
+    bool IsQuorumAchieved() const { return SignersCount() >= quorum_; }            // one-node-one-vote.go:46-54
+    // errors[i] == "" when vote i was counted; quorumAt = index of the vote that first reached the quorum in this call, or -1
+    std::vector<std::string> onVotes(const std::vector<Vote>& votes, long* quorumAt = nullptr) {
+        const size_t n = votes.size();
+        std::vector<std::string> out(n); if (quorumAt) *quorumAt = -1;
+        if (!n) return out;
+        std::vector<Bytes> pks(n), sigs(n), msgs(n, message_); std::vector<bool> keyErr(n, false);
+        for (size_t i = 0; i < n; i++) {
+            const Vote& v = votes[i];
+            if (v.SenderPubkeys.size() == 1) pks[i] = v.SenderPubkeys[0];
+            else if (v.SenderPubkeys.empty() || !aggregateKeys(v.SenderPubkeys, pks[i])) { keyErr[i] = true; pks[i] = Bytes(48, 0); }
+            sigs[i] = v.Payload;
+        }
+        const auto st = verifyStatus(pks, sigs, msgs);
+        for (size_t i = 0; i < n; i++) {
+            const bool was = IsQuorumAchieved();
+            out[i] = one(votes[i], st[i], keyErr[i]);
+            if (out[i].empty() && !was && IsQuorumAchieved() && quorumAt && *quorumAt < 0) *quorumAt = (long)i;
+        }
+        return out;
+    }
+    // consensus/quorum/quorum.go:164-196: one signature per ballot (a multi-key ballot sits under each of its keys), one device call
+    bool AggregateVotes(Bytes& sig) const {
+        Bytes blob; std::map<Bytes, bool> seen; size_t cnt = 0;
+        for (auto& kv : BallotBox) {
+            bool dup = false; for (auto& k : kv.second.SignerPubKeys) if (seen.count(k)) { dup = true; break; }
+            if (dup) continue;
+            for (auto& k : kv.second.SignerPubKeys) seen[k] = true;
+            blob.insert(blob.end(), kv.second.Signature.begin(), kv.second.Signature.end()); cnt++;
+        }
+        sig.assign(96, 0);
+        return cnt == 0 || hbls_aggregate_sigs(blob.data(), cnt, sig.data()) == 0;
+    }
+private:
+    std::map<Bytes, size_t> index_; Bytes message_; size_t quorum_ = 0;
+    std::string one(const Vote& v, uint8_t st, bool keyErr) {
+        if (keyErr || st == HBLS_VB_BAD_KEY_ENCODING) return errKeyDeserialize;             // the message parser decodes the sender keys
+        for (auto& k : v.SenderPubkeys) if (BallotBox.count(k)) return errAlreadyReceived;
+        if (st == HBLS_VB_BAD_SIG_ENCODING) return errSigDeserialize;
+        if (st != HBLS_VB_OK) return errVoteSig;
+        for (size_t a = 0; a < v.SenderPubkeys.size(); a++) for (size_t b = a + 1; b < v.SenderPubkeys.size(); b++)
+            if (v.SenderPubkeys[a] == v.SenderPubkeys[b]) return errDuplicateKey;             // submitVote (quorum.go:354-377)
+        for (auto& k : v.SenderPubkeys) BallotBox[k] = Ballot{v.SenderPubkeys, v.Payload};
+        for (auto& k : v.SenderPubkeys) if (!index_.count(k)) return errKeyNotFound;          // SetKeysAtomic, after the ballots were recorded
+        for (auto& k : v.SenderPubkeys) { const size_t i = index_[k]; bitmap[i >> 3] |= (uint8_t)(1u << (i & 7)); }
+        return "";
+    }
+};
 }  // namespace consensus
+
+namespace slash {      // == staking/slash/double-sign.go:139-168,215-262, the ballot checks that need no chain state
+using consensus::Bytes;
+constexpr const char* errSignerKeyNotRightSize = "bls keys from slash candidate not right side";
+constexpr const char* errSlashBlockNoConflict = "cannot slash for signing on non-conflicting blocks";
+constexpr const char* errNoMatchingDoubleSignKeys = "no matching double sign keys";
+constexpr const char* errFailVerifySlash = "could not verify bls key signature on slash";
+struct Vote { std::vector<Bytes> SignerPubKeys; std::array<uint8_t, 32> BlockHeaderHash{}; Bytes Signature; };
+struct Evidence { uint64_t Epoch = 0, Height = 0, ViewID = 0; uint32_t ShardID = 0; Vote FirstVote, SecondVote; };
+struct Record { slash::Evidence Evidence; };
+// per record "" or the first error slash.Verify would return from its ballot checks; the 2 R signature checks in ONE device call
+inline std::vector<std::string> VerifyBallots(const std::vector<Record>& records) {
+    std::vector<std::string> out(records.size());
+    std::vector<Bytes> pks, sigs, msgs; std::vector<std::pair<size_t, std::string>> owner;      // (record, error known before the device call)
+    for (size_t r = 0; r < records.size(); r++) {
+        const Vote &first = records[r].Evidence.FirstVote, &second = records[r].Evidence.SecondVote;
+        bool sized = true; for (auto* v : {&first, &second}) for (auto& k : v->SignerPubKeys) sized &= k.size() == bls::PublicKeySizeInBytes;
+        if (!sized) { out[r] = errSignerKeyNotRightSize; continue; }
+        if (first.BlockHeaderHash == second.BlockHeaderHash) { out[r] = errSlashBlockNoConflict; continue; }
+        bool match = false; for (auto& a : first.SignerPubKeys) for (auto& b : second.SignerPubKeys) match |= a == b;
+        if (!match) { out[r] = errNoMatchingDoubleSignKeys; continue; }
+        for (auto* v : {&first, &second}) {
+            // slash verification only happens in the staking era: 48-byte commit payload (double-sign.go:250-252)
+            Bytes apk(48, 0); std::string pre;
+            bls_core::Sign probe;
+            if (v->Signature.size() != 96) pre = consensus::errSigDeserialize;
+            else if (!consensus::aggregateKeys(v->SignerPubKeys, apk)) { pre = probe.Deserialize(v->Signature) ? consensus::errKeyDeserialize : consensus::errSigDeserialize; apk.assign(48, 0); }
+            pks.push_back(apk); sigs.push_back(v->Signature);
+            msgs.push_back(signature::ConstructCommitPayload(true, v->BlockHeaderHash, records[r].Evidence.Height, records[r].Evidence.ViewID));
+            owner.push_back({r, pre});
+        }
+    }
+    const auto st = consensus::verifyStatus(pks, sigs, msgs);
+    for (size_t k = 0; k < owner.size(); k++) {
+        const size_t r = owner[k].first;
+        if (!out[r].empty()) continue;                             // the first ballot already failed
+        if (!owner[k].second.empty()) out[r] = owner[k].second;
+        else if (st[k] == HBLS_VB_BAD_SIG_ENCODING) out[r] = consensus::errSigDeserialize;
+        else if (st[k] != HBLS_VB_OK) out[r] = errFailVerifySlash;
+    }
+    return out;
+}
+}  // namespace slash
 }  // namespace harmony

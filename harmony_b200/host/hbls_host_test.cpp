@@ -208,9 +208,56 @@ static void test_consensus_messages() {
     { auto bad = nv; bad.M3Bitmap = {0x0f}; CHECK(validator.OnNewViewChecks(bad) == errM3Verify); }                  // aggregate of 5 against 4 keys
 }
 
+static void test_leader_votes_and_slash() {
+    using namespace consensus;
+    // leader's COMMIT collection on a 7-validator committee (quorum 5): single-key votes, one 2-key vote, one fault of each kind
+    auto keys = make_keys(8);
+    std::vector<bls::PublicKeyWrapper> pubs; for (int i = 0; i < 7; i++) pubs.push_back(*keys[i].Pub);
+    auto kb = [&](int i) { return Bytes(keys[i].Pub->Bytes.begin(), keys[i].Pub->Bytes.end()); };
+    std::array<uint8_t, 32> bh; for (int i = 0; i < 32; i++) bh[i] = (uint8_t)(11 * i + 3);
+    const Bytes payload = signature::ConstructCommitPayload(true, bh, 77, 78);
+    auto vote1 = [&](int i) { return Vote{{kb(i)}, sign_bytes(keys[i], payload)}; };
+    // keys 1 and 2 belong to one validator: ONE signature that verifies against pk1 + pk2 (the sum of the two signatures)
+    std::unique_ptr<bls_core::Sign> s1(keys[1].Pri->SignHash(payload)), s2(keys[2].Pri->SignHash(payload));
+    Vote multi{{kb(1), kb(2)}, bls::AggregateSig({s1.get(), s2.get()})->Serialize()};
+    std::vector<Vote> votes = {vote1(0), multi, vote1(3), vote1(4), vote1(0), vote1(5), vote1(6), vote1(7)};
+    votes[2].Payload = sign_bytes(keys[4], payload);             // somebody else's signature
+    votes[5].Payload.assign(96, 0xff);                           // does not decode
+    VoteCollector col; col.Init(pubs, payload);
+    long q = -2; auto out = col.onVotes(votes, &q);
+    CHECK(out[0].empty() && out[1].empty() && out[2] == errVoteSig && out[3].empty() && out[4] == errAlreadyReceived && out[5] == errSigDeserialize);
+    CHECK(out[6].empty() && out[7] == errKeyNotFound);            // key 7 signs correctly but is not in the committee
+    CHECK(q == 6 && col.SignersCount() == 6 && col.bitmap == Bytes{0x57});      // keys 0,1,2,4,6 + the recorded outsider ballot (reference quirk)
+    { VoteCollector c2; c2.Init(pubs, payload); votes.pop_back(); c2.onVotes(votes); votes.push_back(vote1(3)); long q2 = -2; auto o2 = c2.onVotes({votes.back()}, &q2);
+      CHECK(o2[0].empty() && q2 == -1 && c2.bitmap == Bytes{0x5f});
+      Bytes agg; CHECK(c2.AggregateVotes(agg));
+      bls::Committee com; CHECK(com.Load(pubs).empty());
+      bls::SerializedSignature a96; std::copy(agg.begin(), agg.end(), a96.begin());
+      CHECK(bls::FastAggregateVerify(com, c2.bitmap, a96, payload) == 1); }
+
+    // double-sign evidence (staking/slash/double-sign.go): validator with keys 0 and 1 signs two blocks at one height / view
+    std::array<uint8_t, 32> h1 = bh, h2 = bh; h2[0] ^= 1;
+    auto ballot = [&](std::vector<int> idx, const std::array<uint8_t, 32>& h, const std::array<uint8_t, 32>& signedh) {
+        slash::Vote v; v.BlockHeaderHash = h; std::vector<std::unique_ptr<bls_core::Sign>> ss; std::vector<bls_core::Sign*> ptr;
+        const Bytes pl = signature::ConstructCommitPayload(true, signedh, 37, 38);
+        for (int i : idx) { v.SignerPubKeys.push_back(kb(i)); ss.emplace_back(keys[i].Pri->SignHash(pl)); ptr.push_back(ss.back().get()); }
+        v.Signature = bls::AggregateSig(ptr)->Serialize(); return v;
+    };
+    auto rec = [&](slash::Vote a, slash::Vote b) { slash::Record r; r.Evidence.Height = 37; r.Evidence.ViewID = 38; r.Evidence.FirstVote = a; r.Evidence.SecondVote = b; return r; };
+    std::vector<slash::Record> recs = {rec(ballot({0, 1}, h1, h1), ballot({0, 1}, h2, h2)), rec(ballot({0}, h1, h1), ballot({0, 2}, h2, h2)),
+                                       rec(ballot({0, 1}, h1, h1), ballot({0, 1}, h1, h1)), rec(ballot({0, 1}, h1, h1), ballot({2, 3}, h2, h2)),
+                                       rec(ballot({0, 1}, h1, h1), ballot({0, 1}, h2, h1)), rec(ballot({0, 1}, h1, h1), ballot({0, 1}, h2, h2)),
+                                       rec(ballot({0, 1}, h1, h1), ballot({0, 1}, h2, h2))};
+    recs[5].Evidence.FirstVote.Signature.assign(96, 0xff);
+    recs[6].Evidence.SecondVote.SignerPubKeys[1].assign(48, 0xff);
+    auto se = slash::VerifyBallots(recs);
+    CHECK(se[0].empty() && se[1].empty() && se[2] == slash::errSlashBlockNoConflict && se[3] == slash::errNoMatchingDoubleSignKeys);
+    CHECK(se[4] == slash::errFailVerifySlash && se[5] == errSigDeserialize && se[6] == errKeyDeserialize);
+}
+
 int main() {
     if (bls_core::Init(bls_core::BLS12_381) != 0) { fprintf(stderr, "bls.Init failed: CUDA device required (no CPU fallback)\n"); return 2; }
-    test_mask(); test_quorum_votes(); test_codecs_multibls_payload(); test_consensus_messages();
+    test_mask(); test_quorum_votes(); test_codecs_multibls_payload(); test_consensus_messages(); test_leader_votes_and_slash();
     if (g_fail) { fprintf(stderr, "%d check(s) failed\n", g_fail); return 1; }
     printf("hbls_host_test: all checks passed\n");
     return 0;
