@@ -121,6 +121,38 @@ extern "C" int emu_mul_wide_k_check(const uint32_t* a, const uint32_t* b, int n)
     }
     return bad;
 }
+// fp_half (conditional add of p + shift) on n values (12 words each, canonical): h + h == a and h == a * (1/2); the twist-constant
+// product by additions == the product by K_B2_3; and the doubling step built from them == the round-1 form that multiplied by
+// the constants 1/2 and 3b' (same point, same line).  Returns mismatches.
+extern "C" int emu_half_and_dbl_check(const uint32_t* vals, int n) {
+    int bad = 0;
+    fp inv2; fp_set(inv2, K_INV2);
+    for (int i = 0; i < n; i++) {
+        fp a, h, d, m; for (int j = 0; j < 12; j++) a.l[j] = vals[12 * i + j];
+        fp_half(h, a); fp_add(d, h, h); fp_mul(m, a, inv2);
+        if (!fp_eq(d, a) || !fp_eq(h, m)) bad++;
+    }
+    for (int i = 0; i + 5 < n; i += 6) {
+        fp2 c[3]; for (int k = 0; k < 3; k++) for (int j = 0; j < 12; j++) { c[k].a.l[j] = vals[12 * (i + 2 * k) + j]; c[k].b.l[j] = vals[12 * (i + 2 * k + 1) + j]; }
+        fp2 b3, e1, e2; fp2_const(b3, K_B2_3); fp2_mul(e1, b3, c[0]); fp2_mul_twist3b(e2, c[0]);
+        if (!fp2_eq(e1, e2)) bad++;
+        // round-1 doubling step (multiplications by the constants), restated
+        g2proj t; t.x = c[0]; t.y = c[1]; t.z = c[2];
+        fp2 A, B, C, Ee, F, H, s, l0, l2, l3, x3, y3, e2s, z3;
+        fp2_mul(A, t.x, t.y); fp2_mul_fp(A, A, inv2);
+        fp2_sqr(B, t.y); fp2_sqr(C, t.z); fp2_mul(Ee, b3, C);
+        fp2_dbl(F, Ee); fp2_add(F, F, Ee);
+        fp2_add(H, t.y, t.z); fp2_sqr(H, H); fp2_sub(H, H, B); fp2_sub(H, H, C);
+        fp2_sub(l0, B, Ee); fp2_sqr(s, t.x); fp2_dbl(l2, s); fp2_add(l2, l2, s); fp2_neg(l2, l2); l3 = H;
+        fp2_sub(x3, B, F); fp2_mul(x3, x3, A);
+        fp2_add(y3, B, F); fp2_mul_fp(y3, y3, inv2); fp2_sqr(y3, y3);
+        fp2_sqr(e2s, Ee); fp2_dbl(s, e2s); fp2_add(s, s, e2s); fp2_sub(y3, y3, s);
+        fp2_mul(z3, B, H);
+        fp2 n0, n2, n3; ml_dbl(t, n0, n2, n3);
+        if (!fp2_eq(t.x, x3) || !fp2_eq(t.y, y3) || !fp2_eq(t.z, z3) || !fp2_eq(n0, l0) || !fp2_eq(n2, l2) || !fp2_eq(n3, l3)) bad++;
+    }
+    return bad;
+}
 // binary-GCD inversion against the Fermat exponentiation on n values (Montgomery limbs in, 12 words each); returns mismatches
 extern "C" int emu_inv_gcd_check(const uint32_t* vals, int n) {
     int bad = 0;

@@ -162,6 +162,19 @@ def test_emu_karatsuba_wide_product(emu):
     assert emu.emu_mul_wide_k_check(A, Bv, n) == 0
 
 
+def test_emu_half_and_doubling_step(emu):
+    """fp_half == multiplication by 1/2, fp2_mul_twist3b == multiplication by 3b' = 12(1 + i), and the Miller doubling step built on
+    them gives the same running point and line as the round-1 form with the constant multiplications (edge values: 0, 1, p - 1, odd /
+    even, top bits set)."""
+    p = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
+    rng = random.Random(21)
+    vals = [0, 1, 2, 3, p - 1, p - 2, (p - 1) // 2, (p + 1) // 2, 1 << 380, (1 << 380) + 1, 0xffffffff, 1 << 32] + [rng.randrange(p) for _ in range(300)]
+    arr = (ctypes.c_uint32 * (12 * len(vals)))()
+    for i, v in enumerate(vals):
+        for j in range(12): arr[12 * i + j] = (v >> (32 * j)) & 0xffffffff
+    assert emu.emu_half_and_dbl_check(arr, len(vals)) == 0
+
+
 def test_emu_inv_gcd(emu):
     """fp_inv_gcd (binary extended Euclid, used on the latency path) == a^(p-2) on edge values and random ones."""
     p = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
