@@ -418,3 +418,51 @@ def test_leader_vote_collection_250(gbls, oracle):
     members_only = [v for i, v in enumerate(votes) if faults.get(i) != cs.errKeyNotFound]
     col2 = cs.VoteCollector(members, message); col2.onVotes(members_only)
     sig2, bm2 = col2.AggregateVotes(); assert com.AggregateVerify(bm2, sig2, message)
+
+# ------------------------------------------------------------------ randomized storms: batch == sequential for every arrival order
+def test_view_change_random_storms_host_logic(oracle):
+    """Seeded random storms on a small committee: random mix of M1 / M2 messages, two view ids, every fault of the menu at random
+    places, duplicates and retries in random order.  The batched handler must agree with the sequential restatement message by message
+    and in the final state, for ONE call over the whole queue and for the queue cut into several calls at random places."""
+    import random
+    n = 9; q = wl.quorum_k(n)
+    sks = [wl.seeded_sk("rnd", i) for i in range(n)]
+    pks = [oracle.get_public_key(wl.sk_bytes(k)) for k in sks]
+    cache = {}
+    def sign(sk, m):
+        key = (sk, bytes(m))
+        if key not in cache: cache[key] = oracle.sign_hash(wl.sk_bytes(sk), m)
+        return cache[key]
+    bh = wl.seeded_bytes("rnd/hash", 0, 32)
+    def proof(k, signed=None):
+        bm = wl.bitmap_with_k("rnd/bm", k, n, k)
+        return bh + sign(wl.round_signer_sum(sks, bm), signed or bh) + bm
+    good, low, wrong = proof(q), proof(q - 1), proof(q, signed=wl.seeded_bytes("rnd/hash", 1, 32))
+    be = OracleBackend(oracle)
+    for seed in range(12):
+        rng = random.Random(seed)
+        msgs = []
+        for _ in range(rng.randrange(4, 14)):
+            i = rng.randrange(n); vid = rng.choice((5, 6)); kind = rng.choice(("m1", "m1", "m2"))
+            payload = rng.choice((good, good, good, low, wrong, bh + BAD_SIG + good[128:], good[:-1])) if kind == "m1" else b""
+            m = FBFTMessage(ViewID=vid, BlockNum=3, SenderPubkey=pks[i], LeaderPubkey=pks[0], Payload=payload, Block=b"\xc0" if kind == "m1" else b"",
+                            ViewchangeSig=sign(sks[i], payload if kind == "m1" else NIL), ViewidSig=sign(sks[i], le64(vid)))
+            fault = rng.randrange(10)
+            if fault == 0: m.ViewidSig = sign(sks[i], le64(vid + 1))
+            elif fault == 1: m.ViewchangeSig = sign(sks[(i + 1) % n], payload if kind == "m1" else NIL)
+            elif fault == 2: m.ViewchangeSig = BAD_SIG
+            elif fault == 3: m.SenderPubkey = BAD_KEY
+            elif fault == 4 and kind == "m1": m.Block = b""                      # M1 payload without a block: judged as M2
+            msgs.append(m)
+            if rng.randrange(4) == 0: msgs.append(FBFTMessage(**{**m.__dict__}))   # immediate duplicate
+        rng.shuffle(msgs)
+        ref = RefViewChange(oracle, pks); exp = [ref.on_view_change(m) for m in msgs]
+        one = cs.viewChange(pks, backend=be)
+        assert one.ProcessViewChangeMsgs(msgs) == exp, seed
+        cut = cs.viewChange(pks, backend=be); got = []; pos = 0
+        while pos < len(msgs):
+            step = rng.randrange(1, 5); got += cut.ProcessViewChangeMsgs(msgs[pos:pos + step]); pos += step
+        assert got == exp, seed
+        for vc in (one, cut):
+            assert vc.bhpSigs == ref.bhpSigs and vc.nilSigs == ref.nilSigs and vc.viewIDSigs == ref.viewIDSigs and vc.GetM1Payload() == ref.m1Payload
+            assert {k: bytes(v) for k, v in vc.viewIDBitmap.items()} == {k: bytes(v) for k, v in ref.viewIDBitmap.items()}
